@@ -1,0 +1,113 @@
+"""ctypes binding of libcsd_b200.so (the C ABI in include/csd_b200.h).
+
+This is the only place the shared library is opened. There is NO fallback: if the library is
+missing or an entry point fails, the caller gets an exception. The reference binds its native
+code with torch.utils.cpp_extension.load at import (op/upfirdn2d.py:10-16, op/fused_act.py:11-17);
+here the library is prebuilt in-tree by `conditional_score_diffusion_b200.build`.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcsd_b200.so")
+
+CSD_MAX_SEGMENTS = 4
+
+c_int = ctypes.c_int
+c_int32 = ctypes.c_int32
+c_int64 = ctypes.c_int64
+c_float = ctypes.c_float
+c_void_p = ctypes.c_void_p
+
+
+class CsdError(RuntimeError):
+    """A libcsd_b200 entry point returned a non-zero status."""
+
+
+class ConvSegment(ctypes.Structure):
+    _fields_ = [
+        ("a", c_void_p),
+        ("pitch", c_int32),
+        ("c_off", c_int32),
+        ("c_cnt", c_int32),
+        ("taps", c_int32),
+    ]
+
+
+class ConvGemmDesc(ctypes.Structure):
+    _fields_ = [
+        ("batch", c_int32), ("h", c_int32), ("w", c_int32),
+        ("tile_w", c_int32), ("tile_h", c_int32), ("tile_b", c_int32),
+        ("nseg", c_int32),
+        ("n", c_int32),
+        ("n_store", c_int32),
+        ("n_tile", c_int32),
+        ("seg", ConvSegment * CSD_MAX_SEGMENTS),
+        ("wt", c_void_p),
+        ("wt_rows", c_int32),
+        ("k_total", c_int32),
+        ("wt_pitch", c_int32),
+        ("wt_k_off", c_int32),
+        ("k_valid", c_int32),
+        ("wt_batch_stride", c_int64),
+        ("z_batches", c_int32),
+        ("a_batch_step", c_int32),
+        ("out", c_void_p),
+        ("out_pitch", c_int32),
+        ("out_f32", c_int32),
+        ("out_z_stride", c_int64),
+        ("bias", c_void_p),
+        ("bias_per_row", c_int32),
+        ("temb", c_void_p),
+        ("temb_pitch", c_int32),
+        ("res", c_void_p),
+        ("res_pitch", c_int32),
+        ("res_z_stride", c_int64),
+        ("scale", c_float),
+    ]
+
+
+# name -> (restype, argtypes). Every symbol declared in include/csd_b200.h must be listed here;
+# tests/test_abi.py checks both directions against the header text.
+_PROTOTYPES = {
+    "csd_last_error": (ctypes.c_char_p, []),
+    "csd_abi_version": (c_int, []),
+    "csd_device_sm_count": (c_int, [ctypes.POINTER(c_int)]),
+    "csd_conv_gemm": (c_int, [ctypes.POINTER(ConvGemmDesc), c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Open libcsd_b200.so (once). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise CsdError(
+                    f"{LIB_PATH} is missing: build it with "
+                    "`python -m conditional_score_diffusion_b200.build` (needs nvcc). "
+                    "There is no CPU or PyTorch fallback for this path."
+                )
+            handle = ctypes.CDLL(LIB_PATH)
+            for name, (restype, argtypes) in _PROTOTYPES.items():
+                fn = getattr(handle, name)
+                fn.restype = restype
+                fn.argtypes = argtypes
+            _lib = handle
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        msg = lib().csd_last_error()
+        raise CsdError(f"libcsd_b200 status {status}: {msg.decode() if msg else '?'}")
+
+
+def exported_names():
+    return sorted(_PROTOTYPES)

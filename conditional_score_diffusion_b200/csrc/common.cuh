@@ -1,0 +1,100 @@
+// Shared host/device helpers for libcsd_b200 (sm_100a only).
+//
+// Everything in csrc/ is reached through the C ABI declared in include/csd_b200.h:
+// plain pointers and sizes in, int status out, caller-allocated outputs, caller's stream.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+
+#define CSD_OK 0
+#define CSD_ERR_INVALID 1   // bad argument (shape, alignment, null pointer)
+#define CSD_ERR_CUDA 2      // CUDA runtime/driver error (see csd_last_error)
+#define CSD_ERR_UNSUPPORTED 3
+
+namespace csd {
+
+// Thread-local last-error text, returned by csd_last_error().
+char* error_buffer();
+int set_error(int code, const char* fmt, ...);
+
+inline int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return CSD_OK;
+  return set_error(CSD_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CSD_CUDA(expr)                                         \
+  do {                                                         \
+    int _s = ::csd::check_cuda((expr), #expr);                 \
+    if (_s != CSD_OK) return _s;                               \
+  } while (0)
+
+#define CSD_REQUIRE(cond, ...)                                 \
+  do {                                                         \
+    if (!(cond)) return ::csd::set_error(CSD_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define CSD_LAUNCH_CHECK(name) CSD_CUDA(cudaGetLastError())
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+int num_sms();  // SM count of the current device (cached)
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// 16-byte vector of 8 bf16 values.
+struct __align__(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+// Streaming 16-byte global load/store (read-once data: keep it out of L1).
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+#endif  // __CUDACC__
+
+}  // namespace csd

@@ -1,0 +1,395 @@
+// tcgen05 implicit-GEMM convolution / GEMM for NHWC bf16 activations (sm_100a).
+//
+// One CTA computes a 128-pixel x n_tile output tile:
+//   warp 0   : TMA producer   - per (segment, tap, 32-channel chunk) one 4-D box load of the shifted
+//                               activation tile (out-of-image pixels are zero-filled by TMA = conv
+//                               padding) and one 3-D box load of the matching weight slab
+//   warp 1   : MMA issuer     - tcgen05.mma (M=128, N=n_sub<=256, K=16) from shared-memory
+//                               descriptors, fp32 accumulators in TMEM; tcgen05.commit releases stages
+//   warps 2-5: epilogue       - tcgen05.ld the accumulator rows, add bias / time-embedding
+//                               projection / residual, scale, store bf16 or fp32 rows
+// Shared memory holds a ring of `num_stages` {A: 128 rows x 64 B, B: n_tile rows x 64 B} stages in
+// the 64-byte-swizzled K-major layout shared by TMA and the UMMA descriptors.
+//
+// Reference ops replaced: nn.Conv2d 3x3/1x1 (models/layers.py:100-132), NIN (models/layers.py:555-564),
+// attention einsums (models/layerspp.py:82-86), `h += Dense_0(act(temb))[:, :, None, None]`, the
+// Conv_2 skip and `(x + h) / sqrt(2)` of ResnetBlockBigGANpp.forward (models/layerspp.py:260-274).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tensormap.cuh"
+#include "../../include/csd_b200.h"
+
+namespace csd {
+
+constexpr int kChunkK = 32;                       // channels per pipeline stage
+constexpr int kRowBytes = kChunkK * 2;            // 64 B of bf16 per row -> SWIZZLE_64B
+constexpr int kTileM = 128;                       // UMMA M
+constexpr int kAStageBytes = kTileM * kRowBytes;  // 8192
+constexpr int kConvThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kLayoutSw64 = 4;
+
+struct ConvGemmKernelParams {
+  int B, H, W, TW, TH, TB;
+  int tiles_w, tiles_h;
+  int nseg;
+  int seg_taps[CSD_MAX_SEGMENTS];
+  int seg_chunks[CSD_MAX_SEGMENTS];
+  int seg_coff[CSD_MAX_SEGMENTS];
+  int n_store, n_tile, n_sub, nsplit;
+  int wt_k_off;
+  int a_batch_step;
+  int num_stages, tmem_cols;
+  uint32_t stage_bytes, a_box_bytes, b_box_bytes;
+  void* out;
+  int out_pitch, out_f32;
+  long long out_z_stride;
+  const float* bias;
+  int bias_per_row;
+  const float* temb;
+  int temb_pitch;
+  const __nv_bfloat16* res;
+  int res_pitch;
+  long long res_z_stride;
+  float scale;
+};
+
+__global__ void __launch_bounds__(kConvThreads)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                 const __grid_constant__ CUtensorMap mapB, const ConvGemmKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned base: the swizzle pattern is a function of the shared-memory address bits.
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + p.num_stages * p.stage_bytes;
+  // barrier layout: full[num_stages], empty[num_stages], tmem_full, then the TMEM address slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int t = blockIdx.x;
+  const int tw = t % p.tiles_w;
+  const int th = (t / p.tiles_w) % p.tiles_h;
+  const int tb = t / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.TW, h0 = th * p.TH, b0 = tb * p.TB;
+  const int n0 = blockIdx.y * p.n_tile;
+  const int z = blockIdx.z;
+
+  int total_iters = 0;
+  for (int s = 0; s < p.nseg; ++s) total_iters += p.seg_taps[s] * p.seg_chunks[s];
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&mapA0);
+    ptx::prefetch_tensormap(&mapB);
+    for (int s = 0; s < p.num_stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      int kidx = 0;  // running 32-wide K block index into Wt
+      for (int s = 0; s < p.nseg; ++s) {
+        const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
+        const int taps = p.seg_taps[s];
+        for (int tap = 0; tap < taps; ++tap) {
+          const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
+          const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
+          for (int c = 0; c < p.seg_chunks[s]; ++c, ++it, ++kidx) {
+            const int stage = it % p.num_stages;
+            const uint32_t parity = ((it / p.num_stages) & 1) ^ 1;
+            ptx::mbar_wait(empty_bar(stage), parity);
+            const uint32_t a_dst = smem_base + stage * p.stage_bytes;
+            const uint32_t b_dst = a_dst + kAStageBytes;
+            ptx::mbar_arrive_expect_tx(full_bar(stage), p.a_box_bytes + p.b_box_bytes * p.nsplit);
+            ptx::tma_load_4d(a_dst, mapA, full_bar(stage), p.seg_coff[s] + c * kChunkK, w0 + dx, h0 + dy,
+                             b0 + z * p.a_batch_step);
+            for (int j = 0; j < p.nsplit; ++j) {
+              ptx::tma_load_3d(b_dst + j * p.b_box_bytes, &mapB, full_bar(stage), p.wt_k_off + kidx * kChunkK,
+                               n0 + j * p.n_sub, z);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)p.n_sub);
+      for (int it = 0; it < total_iters; ++it) {
+        const int stage = it % p.num_stages;
+        const uint32_t parity = (it / p.num_stages) & 1;
+        ptx::mbar_wait(full_bar(stage), parity);
+        ptx::tcgen05_fence_after();
+        const uint32_t a_addr = smem_base + stage * p.stage_bytes;
+        const uint32_t b_addr = a_addr + kAStageBytes;
+#pragma unroll
+        for (int kk = 0; kk < kChunkK / 16; ++kk) {
+          const uint64_t a_desc = ptx::make_smem_desc(a_addr + kk * 32, 16, 512, kLayoutSw64);
+          for (int j = 0; j < p.nsplit; ++j) {
+            const uint64_t b_desc =
+                ptx::make_smem_desc(b_addr + j * p.b_box_bytes + kk * 32, 16, 512, kLayoutSw64);
+            ptx::mma_bf16_ss(tmem_base + j * p.n_sub, a_desc, b_desc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        ptx::mma_commit(empty_bar(stage));  // frees the stage when the MMAs above have read it
+      }
+      ptx::mma_commit(tmem_full_bar);       // accumulator complete
+    }
+  } else {
+    // ===== epilogue (warps 2..5): warp q owns TMEM lanes [32q, 32q+32) with q = warp % 4 =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;  // row of the tile
+    const int wl = m % p.TW;
+    const int hl = (m / p.TW) % p.TH;
+    const int bl = m / (p.TW * p.TH);
+    const int b = b0 + bl, h = h0 + hl, w = w0 + wl;
+    const bool valid = (bl < p.TB) && (b < p.B) && (h < p.H) && (w < p.W);
+    const long long pix = ((long long)b * p.H + h) * p.W + w;
+
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tcgen05_fence_after();
+
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float row_bias = (p.bias != nullptr && p.bias_per_row && valid) ? p.bias[pix] : 0.0f;
+    const float* temb_row = (p.temb != nullptr && valid) ? p.temb + (long long)b * p.temb_pitch : nullptr;
+    const __nv_bfloat16* res_row =
+        (p.res != nullptr && valid) ? p.res + (long long)z * p.res_z_stride + pix * p.res_pitch : nullptr;
+
+    const int ncols = min(p.n_tile, p.n_store - n0);  // columns of this tile that are stored
+    for (int col = 0; col < ncols; col += 16) {
+      uint32_t r[16];
+      __syncwarp();
+      ptx::tmem_ld_x16(t_row + col, r);
+      ptx::tmem_ld_wait();
+      if (valid) {
+      const int n = n0 + col;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+      if (p.bias != nullptr) {
+        if (p.bias_per_row) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += row_bias;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n + i);
+        }
+      }
+      if (temb_row != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += __ldg(temb_row + n + i);
+      }
+      const int cnt = min(16, p.n_store - n);
+      if (res_row != nullptr) {
+        if (cnt == 16) {
+          const uint4* rp = reinterpret_cast<const uint4*>(res_row + n);
+          bf16x8 r0, r1;
+          *reinterpret_cast<uint4*>(&r0) = __ldg(rp);
+          *reinterpret_cast<uint4*>(&r1) = __ldg(rp + 1);
+          float f[16];
+          unpack8(r0, f);
+          unpack8(r1, f + 8);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += f[i];
+        } else {
+          for (int i = 0; i < cnt; ++i) v[i] += __bfloat162float(res_row[n + i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] *= p.scale;
+
+      if (p.out_f32) {
+        float* op = reinterpret_cast<float*>(p.out) + (long long)z * p.out_z_stride + pix * p.out_pitch + n;
+        if (cnt == 16) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4*>(op)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          for (int i = 0; i < cnt; ++i) op[i] = v[i];
+        }
+      } else {
+        __nv_bfloat16* op =
+            reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)z * p.out_z_stride + pix * p.out_pitch + n;
+        if (cnt == 16) {
+          bf16x8 o0 = pack8(v), o1 = pack8(v + 8);
+          reinterpret_cast<uint4*>(op)[0] = *reinterpret_cast<uint4*>(&o0);
+          reinterpret_cast<uint4*>(op)[1] = *reinterpret_cast<uint4*>(&o1);
+        } else if (cnt == 8) {
+          bf16x8 o0 = pack8(v);
+          reinterpret_cast<uint4*>(op)[0] = *reinterpret_cast<uint4*>(&o0);
+        } else {
+          for (int i = 0; i < cnt; ++i) op[i] = __float2bfloat16_rn(v[i]);
+        }
+      }
+      }  // valid
+    }
+  }
+
+  // teardown: everyone is done with TMEM before the allocating warp frees it
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+static int next_pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+// Host launcher shared by csd_conv_gemm and the program executor (which pre-encodes the maps).
+struct ConvGemmLaunch {
+  CUtensorMap mapA[CSD_MAX_SEGMENTS];
+  CUtensorMap mapB;
+  ConvGemmKernelParams p;
+  dim3 grid;
+  size_t smem;
+};
+
+int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
+  CSD_REQUIRE(d != nullptr, "null conv_gemm desc");
+  CSD_REQUIRE(d->nseg >= 1 && d->nseg <= CSD_MAX_SEGMENTS, "nseg=%d out of range", d->nseg);
+  CSD_REQUIRE(d->batch >= 1 && d->h >= 1 && d->w >= 1, "bad spatial dims %d %d %d", d->batch, d->h, d->w);
+  CSD_REQUIRE(d->tile_w >= 1 && d->tile_h >= 1 && d->tile_b >= 1 &&
+                  d->tile_w * d->tile_h * d->tile_b <= kTileM,
+              "tile box %dx%dx%d exceeds 128 pixels", d->tile_w, d->tile_h, d->tile_b);
+  CSD_REQUIRE(d->n_tile >= 16 && d->n_tile % 16 == 0 && d->n_tile <= 512, "n_tile=%d invalid", d->n_tile);
+  CSD_REQUIRE(d->n >= 1 && d->n_store >= 1, "n=%d n_store=%d invalid", d->n, d->n_store);
+  CSD_REQUIRE(d->out != nullptr && d->wt != nullptr, "null out / wt pointer");
+  CSD_REQUIRE(d->z_batches >= 1, "z_batches=%d", d->z_batches);
+
+  ConvGemmKernelParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->batch; p.H = d->h; p.W = d->w;
+  p.TW = d->tile_w; p.TH = d->tile_h; p.TB = d->tile_b;
+  p.tiles_w = ceil_div(d->w, d->tile_w);
+  p.tiles_h = ceil_div(d->h, d->tile_h);
+  const int tiles_b = ceil_div(d->batch, d->tile_b);
+  p.nseg = d->nseg;
+  p.n_store = d->n_store;
+  p.n_tile = d->n_tile;
+  if (d->n_tile <= 256) {
+    p.nsplit = 1;
+    p.n_sub = d->n_tile;
+  } else {
+    p.nsplit = 2;
+    p.n_sub = d->n_tile / 2;
+    CSD_REQUIRE(p.n_sub % 16 == 0, "n_tile=%d cannot be split into two multiples of 16", d->n_tile);
+  }
+  const int n_tiles = ceil_div(d->n_store, d->n_tile);
+  CSD_REQUIRE(d->wt_rows >= 1, "wt_rows=%d", d->wt_rows);
+  p.wt_k_off = d->wt_k_off;
+  p.a_batch_step = d->a_batch_step;
+  p.tmem_cols = next_pow2_cols(d->n_tile);
+
+  int k_total = 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    const csd_conv_segment& sg = d->seg[s];
+    CSD_REQUIRE(sg.a != nullptr, "segment %d: null tensor", s);
+    CSD_REQUIRE(sg.taps == 1 || sg.taps == 9, "segment %d: taps=%d (1 or 9)", s, sg.taps);
+    CSD_REQUIRE(sg.pitch % 8 == 0 && sg.c_cnt >= 1 && sg.c_off >= 0 && sg.c_off + sg.c_cnt <= sg.pitch,
+                "segment %d: bad channel range off=%d cnt=%d pitch=%d", s, sg.c_off, sg.c_cnt, sg.pitch);
+    p.seg_taps[s] = sg.taps;
+    p.seg_chunks[s] = ceil_div(sg.c_cnt, kChunkK);
+    p.seg_coff[s] = sg.c_off;
+    k_total += sg.taps * p.seg_chunks[s] * kChunkK;
+    // 4-D map over [batch, h, w, c]; dim 0 stops at the last valid channel so the remainder of a
+    // 32-channel chunk is zero-filled instead of reading the neighbouring channels.
+    const uint64_t z_extra = (uint64_t)(d->z_batches - 1) * (uint64_t)d->a_batch_step;
+    uint64_t dims[4] = {(uint64_t)(sg.c_off + sg.c_cnt), (uint64_t)d->w, (uint64_t)d->h,
+                        (uint64_t)d->batch + z_extra};
+    uint64_t strides[3] = {(uint64_t)sg.pitch * 2, (uint64_t)sg.pitch * 2 * d->w,
+                           (uint64_t)sg.pitch * 2 * d->w * d->h};
+    uint32_t box[4] = {(uint32_t)kChunkK, (uint32_t)d->tile_w, (uint32_t)d->tile_h, (uint32_t)d->tile_b};
+    int st = encode_tensor_map(&L->mapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, sg.a, dims, strides, box,
+                               TMA_SW_64);
+    if (st != CSD_OK) return st;
+  }
+  for (int s = d->nseg; s < CSD_MAX_SEGMENTS; ++s) L->mapA[s] = L->mapA[0];
+  CSD_REQUIRE(k_total == d->k_total, "k_total mismatch: segments give %d, desc says %d", k_total, d->k_total);
+  {
+    // 3-D map over Wt [z][rows][k]; rows beyond wt_rows and k beyond k_total are zero-filled.
+    const uint64_t zb = d->wt_batch_stride != 0 ? (uint64_t)d->z_batches : 1;
+    uint64_t dims[3] = {(uint64_t)(d->wt_k_off + (d->k_valid > 0 ? d->k_valid : d->k_total)), (uint64_t)d->wt_rows, zb};
+    const uint64_t row_bytes = (uint64_t)(d->wt_pitch > 0 ? d->wt_pitch : d->k_total) * 2;
+    uint64_t strides[2] = {row_bytes, d->wt_batch_stride != 0 ? (uint64_t)d->wt_batch_stride * 2
+                                                               : row_bytes * (uint64_t)d->wt_rows};
+    uint32_t box[3] = {(uint32_t)kChunkK, (uint32_t)p.n_sub, 1};
+    int st = encode_tensor_map(&L->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, d->wt, dims, strides, box,
+                               TMA_SW_64);
+    if (st != CSD_OK) return st;
+  }
+
+  p.a_box_bytes = (uint32_t)(d->tile_w * d->tile_h * d->tile_b * kRowBytes);
+  p.b_box_bytes = (uint32_t)(p.n_sub * kRowBytes);
+  p.stage_bytes = (uint32_t)((kAStageBytes + d->n_tile * kRowBytes + 1023) & ~1023);
+  const int total_iters = k_total / kChunkK;
+  const int budget = p.tmem_cols <= 128 ? 56 * 1024 : (p.tmem_cols <= 256 ? 100 * 1024 : 200 * 1024);
+  int stages = budget / (int)p.stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > total_iters) stages = total_iters;
+  if (stages < 2) stages = 2;
+  p.num_stages = stages;
+
+  p.out = d->out; p.out_pitch = d->out_pitch; p.out_f32 = d->out_f32; p.out_z_stride = d->out_z_stride;
+  p.bias = d->bias; p.bias_per_row = d->bias_per_row;
+  p.temb = d->temb; p.temb_pitch = d->temb_pitch;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(d->res); p.res_pitch = d->res_pitch;
+  p.res_z_stride = d->res_z_stride;
+  p.scale = d->scale;
+  CSD_REQUIRE(d->out_pitch % 8 == 0, "out_pitch=%d must be a multiple of 8", d->out_pitch);
+  CSD_REQUIRE(d->res == nullptr || d->res_pitch % 8 == 0, "res_pitch=%d must be a multiple of 8", d->res_pitch);
+
+  L->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * tiles_b), (unsigned)n_tiles, (unsigned)d->z_batches);
+  L->smem = (size_t)stages * p.stage_bytes + 1024 /*alignment slack*/ + 8 * (2 * kMaxStages + 2);
+  CSD_REQUIRE(L->smem <= 227 * 1024, "shared memory %zu exceeds 227 KB", L->smem);
+  // If z batches share the weights the z coordinate of the weight map must stay 0.
+  if (d->wt_batch_stride == 0 && d->z_batches > 1) {
+    return set_error(CSD_ERR_UNSUPPORTED, "z_batches > 1 requires wt_batch_stride != 0");
+  }
+  return CSD_OK;
+}
+
+int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_gemm_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
+                                                               L->mapB, L->p);
+  CSD_LAUNCH_CHECK("conv_gemm_kernel");
+  return CSD_OK;
+}
+
+}  // namespace csd
+
+extern "C" int csd_conv_gemm(const csd_conv_gemm_desc* desc, csd_stream_t stream) {
+  csd::ConvGemmLaunch L;
+  int st = csd::conv_gemm_prepare(desc, &L);
+  if (st != CSD_OK) return st;
+  return csd::conv_gemm_launch(&L, static_cast<cudaStream_t>(stream));
+}

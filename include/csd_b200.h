@@ -1,0 +1,211 @@
+/* libcsd_b200 — C ABI of the B200 (sm_100a) score-network / PC-sampler hot path.
+ *
+ * Drop-in boundary for GBATZOLIS/conditional_score_diffusion. The reference reaches native
+ * code through two pybind11 modules built at import time:
+ *   op/upfirdn2d.cpp:12-23      upfirdn2d(Tensor input, Tensor kernel, up_x, up_y, down_x, down_y,
+ *                                         pad_x0, pad_x1, pad_y0, pad_y1) -> Tensor
+ *   op/fused_bias_act.cpp:11-21 fused_bias_act(Tensor input, Tensor bias, Tensor refer, act, grad,
+ *                                              alpha, scale) -> Tensor
+ * and everything else on the hot path is ATen/cuDNN eager PyTorch. This library
+ * replaces both native modules and the eager op sequences of the score network and the
+ * predictor-corrector update, behind plain C entry points:
+ *
+ *   - every pointer is a DEVICE pointer unless the name says host; no torch / ATen types;
+ *   - outputs are caller-allocated; nothing here allocates device memory except
+ *     csd_program_create (tensor maps and the op table, host memory only);
+ *   - every launch goes to the cudaStream_t passed by the caller (pass torch's current stream);
+ *   - the return value is 0 (CSD_OK) or a non-zero status; csd_last_error() gives the text
+ *     (thread-local). Launch errors are checked after every launch (the reference's ops do not:
+ *     op/upfirdn2d_kernel.cu:209-369 has no cudaGetLastError).
+ *
+ * Internal activation layout of the score network: NHWC, bf16, channel pitch a multiple of 8
+ * (16 bytes). The module-surface ops (upfirdn2d, fused_bias_act, PC updates) are NCHW fp32
+ * like the reference's tensors.
+ */
+#ifndef CSD_B200_H_
+#define CSD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSD_ABI_VERSION 1
+
+typedef void* csd_stream_t; /* cudaStream_t */
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+const char* csd_last_error(void);
+int csd_abi_version(void);
+int csd_device_sm_count(int* out);
+
+/* ---- upfirdn2d: replaces op/upfirdn2d.cpp:12-23 + op/upfirdn2d_kernel.cu:209-369 -------------
+ * input  [planes, in_h, in_w] fp32 (planes = N*C; the reference views it as [major,H,W,minor=1],
+ *        op/upfirdn2d.py:99), kernel [kh, kw] fp32 (device), output [planes, out_h, out_w] fp32,
+ *        out = ((in*up + pad0 + pad1 - k) / down) + 1 (op/upfirdn2d.py:104-105).
+ * The backward pass is the same entry with up/down swapped, the flipped kernel and g_pad
+ * (op/upfirdn2d.py:25-44), so there is no separate backward symbol.                            */
+int csd_upfirdn2d_f32(const float* input, const float* kernel, float* output, int64_t planes, int in_h,
+                      int in_w, int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0,
+                      int pad_x1, int pad_y0, int pad_y1, csd_stream_t stream);
+int csd_upfirdn2d_out_size(int in_h, int in_w, int kh, int kw, int up_x, int up_y, int down_x,
+                           int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1, int* out_h,
+                           int* out_w);
+
+/* ---- fused_bias_act: replaces op/fused_bias_act.cpp:11-21 + fused_bias_act_kernel.cu:18-99 ---
+ * y = act(x + b[(i / step_b) % size_b]) * scale, act 1 = linear, 3 = leaky-relu(alpha);
+ * grad 0 = forward, 1 = first derivative w.r.t. x using refer's sign, 2 = second derivative (0
+ * for these activations). bias / refer may be NULL (size_b = 0 / no reference).                */
+int csd_fused_bias_act_f32(const float* x, const float* bias, const float* refer, float* y, int64_t n,
+                           int size_b, int64_t step_b, int act, int grad, float alpha, float scale,
+                           csd_stream_t stream);
+
+/* ---- predictor-corrector updates (sampling/predictors.py:79-102, correctors.py:51-108,
+ *      sampling/conditional.py:104-110). All tensors [batch, per_sample] fp32, contiguous.
+ *      Per-step scalars live in DEVICE tables indexed by *step_idx (a device int) so a captured
+ *      CUDA graph can be replayed for every step without host involvement.                     */
+
+/* y_pert = y + z * sigma_tab[*step]  (VESDE.marginal_prob, sde_lib.py:316-321). */
+int csd_ve_perturb_f32(const float* y, const float* z, float* y_pert, int64_t n, const float* sigma_tab,
+                       const int* step_idx, csd_stream_t stream);
+
+/* norms[0..batch) = ||grad_b||_2, norms[batch..2*batch) = ||noise_b||_2 (correctors.py:72-73). */
+int csd_langevin_norms_f32(const float* grad, const float* noise, float* norms, int batch,
+                           int64_t per_sample, csd_stream_t stream);
+
+/* step = 2*alpha*(snr*mean(noise_norm)/mean(grad_norm))^2; x_mean = x + step*grad;
+ * x_out = x_mean + sqrt(2*step)*noise (correctors.py:74-76). alpha_tab may be NULL (alpha = 1, VE).
+ * grad is first multiplied by grad_scale_tab[*step] when that table is non-NULL (the 1/sigma(t)
+ * of models/utils.py:50-74 for callers that pass the raw network output).                      */
+int csd_langevin_update_f32(const float* x, const float* grad, const float* noise, const float* norms,
+                            float* x_out, float* x_mean, int batch, int64_t per_sample, float snr,
+                            const float* alpha_tab, const int* step_idx, csd_stream_t stream);
+
+/* Reverse-diffusion predictor (predictors.py:79-102 with sde_lib.py:87-92,349-360):
+ * x_mean = x - (f_coef*x - g^2*score*pf) with f = f_coef_tab[*step]*x (0 for VE),
+ * g = g_tab[*step]; x_out = x_mean + g*noise (noise ignored / g_out=0 if probability_flow).     */
+int csd_reverse_diffusion_update_f32(const float* x, const float* score, const float* noise, float* x_out,
+                                     float* x_mean, int64_t n, const float* f_coef_tab,
+                                     const float* g_tab, int probability_flow, const int* step_idx,
+                                     csd_stream_t stream);
+
+/* Euler-Maruyama predictor (predictors.py:52-77): drift = d_coef*x - g^2*score*pf, dt = -1/N;
+ * x_mean = x + drift*dt ; x_out = x_mean + g*sqrt(-dt)*noise.                                  */
+int csd_euler_maruyama_update_f32(const float* x, const float* score, const float* noise, float* x_out,
+                                  float* x_mean, int64_t n, const float* d_coef_tab, const float* g_tab,
+                                  float dt, int probability_flow, const int* step_idx,
+                                  csd_stream_t stream);
+
+/* *step_idx += 1 (one thread). */
+int csd_step_advance(int* step_idx, csd_stream_t stream);
+
+/* ---- score-network building blocks (NHWC bf16) ----------------------------------------------- */
+
+/* out[b,h,w,c] (bf16, pitch c_pad, zero padded) = scale*src[b,c,h,w] + shift, channels taken from up
+ * to two NCHW fp32 sources (x then y: NCSNpp_paired.forward cat, models/ncsnpp.py:395-398;
+ * scale=2, shift=-1 is the `2*x-1` of models/ncsnpp.py:264-266).                               */
+int csd_nchw_to_nhwc_bf16(const float* src0, int c0, const float* src1, int c1, void* out, int c_pad,
+                          int batch, int h, int w, float scale, float shift, csd_stream_t stream);
+
+/* dst[b,c,h,w] fp32 = src[b,h,w,c_off+c] * (row_scale ? row_scale[b] : 1) for c < c_cnt.
+ * row_scale[b] carries the 1/sigma(t_b) of divide_by_sigmas (models/utils.py:50-74).           */
+int csd_nhwc_bf16_to_nchw(const void* src, int c_pitch, int c_off, int c_cnt, float* dst, int batch,
+                          int h, int w, const float* row_scale, csd_stream_t stream);
+
+/* GroupNorm statistics over the channel-concatenation of up to two NHWC bf16 tensors
+ * (torch.cat + nn.GroupNorm of models/layerspp.py:219,242; models/ncsnpp.py:325).
+ * sums[b, g, 0..1] += (sum x, sum x^2); the caller zeroes `sums` beforehand.                   */
+int csd_gn_stats_bf16(const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1,
+                      float* sums, int batch, int hw, int groups, csd_stream_t stream);
+
+/* out = [SiLU](GroupNorm(cat(src0,src1))) as bf16 NHWC with pitch c0+c1 (must be a multiple of 8).
+ * gamma/beta fp32 [c0+c1]; eps as in the module (1e-6).                                         */
+int csd_gn_apply_bf16(const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1,
+                      const float* sums, const float* gamma, const float* beta, void* out, int out_pitch,
+                      int batch, int hw, int groups, float eps, int apply_silu, csd_stream_t stream);
+
+/* Depthwise separable FIR resampling of an NHWC bf16 tensor with the [1,3,3,1] family
+ * (up_or_down_sampling.upsample_2d / downsample_2d, models/up_or_down_sampling.py:195-257):
+ * mode 1 = up x2 (pad (2,1), gain 4), mode 2 = down x2 (pad (1,1)). taps: 4 fp32 host values
+ * (the un-normalised 1-D filter). If add != NULL, out = fir(src) + add (output-skip pyramid,
+ * models/ncsnpp.py:344-349).                                                                    */
+int csd_fir_resample_nhwc_bf16(const void* src, void* out, const void* add, int batch, int h, int w,
+                               int c_pitch, int mode, const float* taps4_host, csd_stream_t stream);
+
+/* rows x cols softmax of fp32 logits (pitch in_pitch) times `scale`, bf16 output (pitch out_pitch,
+ * columns >= cols zero-filled): F.softmax of models/layerspp.py:82-85.                          */
+int csd_softmax_rows_f32_bf16(const float* logits, int in_pitch, void* probs, int out_pitch, int64_t rows,
+                              int cols, float scale, csd_stream_t stream);
+
+/* Time embedding (models/ncsnpp.py:242-260, models/layers.py:524-538, layerspp.py:32-41):
+ * embedding_type 0 = positional(labels, nf), 1 = Gaussian Fourier (fourier_w [nf]);
+ * temb = W1 @ act(W0 @ emb + b0) + b1, then act_temb = SiLU(temb) [batch, 4nf] fp32.            */
+int csd_time_embedding_f32(const float* labels, int batch, int nf, int embedding_type,
+                           const float* fourier_w, const float* w0, const float* b0, const float* w1,
+                           const float* b1, float* act_temb, csd_stream_t stream);
+
+/* All per-block Dense_0 projections in one pass (models/layerspp.py:262-263):
+ * out[b, j] = dot(act_temb[b,:], w[j,:]) + bias[j], w [total_out, in_dim] fp32.                 */
+int csd_dense_rows_f32(const float* act_temb, const float* w, const float* bias, float* out, int batch,
+                       int in_dim, int total_out, csd_stream_t stream);
+
+/* ---- tcgen05 implicit-GEMM convolution / GEMM -------------------------------------------------
+ * D[m, n] = sum over segments s, taps t, channels c of A_s[pixel(m)+offset(t), c] * Wt[n, k(s,t,c)]
+ * with A_s NHWC bf16 tensors (zero padded outside the image by TMA), Wt [n_rows, k_total] bf16
+ * K-major. 3x3 taps are offsets (dy,dx) in {-1,0,1}^2 in row-major (ky,kx) order (torch conv2d
+ * cross-correlation); 1 tap = 1x1 conv / plain GEMM. Epilogue: out = (D + bias + temb[b] + res)*scale.
+ * Replaces nn.Conv2d (models/layers.py:100-132), NIN (models/layers.py:555-564), the attention
+ * einsums (models/layerspp.py:82-86) and the `h += Dense_0(...)`, skip and 1/sqrt(2) of
+ * ResnetBlockBigGANpp.forward (models/layerspp.py:260-274).                                     */
+#define CSD_MAX_SEGMENTS 4
+
+typedef struct csd_conv_segment {
+  const void* a;       /* NHWC bf16 tensor [batch, h, w, pitch]                         */
+  int32_t pitch;       /* channel pitch of `a` in elements (multiple of 8)              */
+  int32_t c_off;       /* first channel used                                            */
+  int32_t c_cnt;       /* channels used (zero-filled up to the next multiple of 32)     */
+  int32_t taps;        /* 1 or 9                                                         */
+} csd_conv_segment;
+
+typedef struct csd_conv_gemm_desc {
+  int32_t batch, h, w;          /* spatial extent of A (and of the output)               */
+  int32_t tile_w, tile_h, tile_b; /* pixel box per CTA, product <= 128                    */
+  int32_t nseg;
+  int32_t n;                    /* output columns computed (rows of Wt used)             */
+  int32_t n_store;              /* output columns written (>= n allowed: zero columns)   */
+  int32_t n_tile;               /* columns per CTA: multiple of 16, <= 512                */
+  csd_conv_segment seg[CSD_MAX_SEGMENTS];
+  const void* wt;               /* bf16 [wt_batch?][wt_rows, k_total]                     */
+  int32_t wt_rows;              /* rows available (>= ceil(n / n_tile) * n_tile)         */
+  int32_t k_total;              /* sum over segments of taps * ceil32(c_cnt)             */
+  int32_t wt_pitch;             /* row pitch of Wt in elements (0 = k_total)              */
+  int32_t wt_k_off;             /* first K column of Wt used (attention: K inside [q|k])  */
+  int32_t k_valid;              /* K columns of Wt that exist (0 = k_total); rest zero-filled */
+  int64_t wt_batch_stride;      /* elements between z-batches of Wt (0 = shared weights)  */
+  int32_t z_batches;            /* gridDim.z: batched GEMM count (1 for convolutions)    */
+  int32_t a_batch_step;         /* A batch coordinate += z * a_batch_step                 */
+  void* out;                    /* bf16 or fp32, addressed [pixel * out_pitch + n]        */
+  int32_t out_pitch;
+  int32_t out_f32;              /* 0 = bf16, 1 = fp32                                     */
+  int64_t out_z_stride;         /* elements between z-batches of out                      */
+  const float* bias;            /* fp32, padded to the n_tile multiple, or NULL           */
+  int32_t bias_per_row;         /* 0 = bias[n], 1 = bias[m] (row index inside the z batch) */
+  const float* temb;            /* fp32 [batch, temb_pitch] (already offset), or NULL      */
+  int32_t temb_pitch;
+  const void* res;              /* bf16 residual addressed like out (pitch res_pitch), or NULL */
+  int32_t res_pitch;
+  int64_t res_z_stride;
+  float scale;
+} csd_conv_gemm_desc;
+
+int csd_conv_gemm(const csd_conv_gemm_desc* desc, csd_stream_t stream);
+
+/* ---- program: a recorded list of the ops above, executed with one C call -------------------- */
+/* (declared in the second half of this header, after the op record types)                      */
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CSD_B200_H_ */

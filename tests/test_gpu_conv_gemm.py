@@ -1,0 +1,205 @@
+"""Parity of the tcgen05 implicit-GEMM conv / GEMM kernel (csd_conv_gemm) against torch fp32.
+
+Inputs are rounded to bf16 first so that the only differences are fp32 accumulation order and the
+bf16 rounding of the stored output (tolerances below say which).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# bf16 output: half-ulp relative 2^-9 on values up to ~max|ref|, plus accumulation-order noise.
+BF16_RTOL = 2.0 ** -8
+F32_RTOL = 2e-5
+
+
+def _kern():
+    from conditional_score_diffusion_b200 import kernels
+    return kernels
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _report(name, got, ref, rtol):
+    err = (got.float() - ref).abs()
+    scale = ref.abs().max().item() + 1e-6
+    rel = err.max().item() / scale
+    print(f"[conv_gemm] {name}: max_abs_err={err.max().item():.4e} ref_max={scale:.4e} rel={rel:.3e} "
+          f"mean_abs_err={err.mean().item():.3e}")
+    if rel > rtol:
+        bad = (err > rtol * scale)
+        idx = bad.nonzero()[:8].tolist()
+        print(f"   first bad indices: {idx}  bad_frac={bad.float().mean().item():.4f}")
+    return rel
+
+
+def _conv_case(name, B, H, W, cin, cout, taps=9, bias=True, temb=False, res=False, scale=1.0,
+               c_pitch=None, out_f32=False, seed=0, tile=None, n_tile=None):
+    k = _kern()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dev = "cuda"
+    c_pitch = c_pitch or k.ceil_to(cin, 8)
+    x = torch.randn(B, cin, H, W, device=dev, generator=g).to(torch.bfloat16)
+    ks = 3 if taps == 9 else 1
+    wgt = (torch.randn(cout, cin, ks, ks, device=dev, generator=g) / math.sqrt(cin * ks * ks)).to(torch.bfloat16)
+    a = torch.zeros(B, H, W, c_pitch, device=dev, dtype=torch.bfloat16)
+    a[..., :cin] = _nhwc(x)
+    n_store = k.ceil_to(cout, 8)
+    out_pitch = n_store
+    wt = k.pack_conv_weight(wgt, n_pad=k.ceil_to(cout, 16) if cout <= 256 else 2 * k.ceil_to((cout + 1) // 2, 16))
+    npad = wt.shape[0]
+    bias_t = temb_t = res_t = None
+    ref = F.conv2d(x.float(), wgt.float(), padding=ks // 2)
+    if bias:
+        bias_t = torch.zeros(npad + 16, device=dev)
+        bias_t[:cout] = torch.randn(cout, device=dev, generator=g)
+        ref = ref + bias_t[:cout].view(1, -1, 1, 1)
+    if temb:
+        temb_t = torch.zeros(B, npad + 16, device=dev)
+        temb_t[:, :cout] = torch.randn(B, cout, device=dev, generator=g)
+        ref = ref + temb_t[:, :cout].reshape(B, cout, 1, 1)
+    if res:
+        r = torch.randn(B, cout, H, W, device=dev, generator=g).to(torch.bfloat16)
+        res_t = torch.zeros(B, H, W, out_pitch, device=dev, dtype=torch.bfloat16)
+        res_t[..., :cout] = _nhwc(r)
+        ref = ref + r.float()
+    ref = ref * scale
+    out = torch.full((B, H, W, out_pitch), float("nan"), device=dev,
+                     dtype=torch.float32 if out_f32 else torch.bfloat16)
+    k.conv_gemm([(a, c_pitch, 0, cin, taps)], wt, cout, out, batch=B, h=H, w=W, n_store=n_store,
+                bias=bias_t, temb=temb_t, temb_pitch=(npad + 16), res=res_t, res_pitch=out_pitch,
+                scale=scale, tile=tile, n_tile=n_tile)
+    torch.cuda.synchronize()
+    got = out[..., :cout].permute(0, 3, 1, 2)
+    assert torch.isfinite(out[..., :n_store].float()).all(), f"{name}: non-finite outputs"
+    if n_store > cout:
+        assert (out[..., cout:n_store].float() == 0).all(), f"{name}: padded output channels not zero"
+    rel = _report(name, got, ref, F32_RTOL if out_f32 else BF16_RTOL)
+    return rel
+
+
+def test_gemm_1x1_small():
+    assert _conv_case("1x1 64->96 16x16", 2, 16, 16, 64, 96, taps=1) < BF16_RTOL
+
+
+def test_gemm_1x1_f32_out():
+    assert _conv_case("1x1 64->96 16x16 f32", 2, 16, 16, 64, 96, taps=1, out_f32=True) < F32_RTOL
+
+
+def test_conv3x3_basic():
+    assert _conv_case("3x3 96->96 16x16", 2, 16, 16, 96, 96) < BF16_RTOL
+
+
+def test_conv3x3_epilogue_all():
+    assert _conv_case("3x3 96->192 +bias+temb+res*0.707", 3, 20, 20, 96, 192, temb=True, res=True,
+                      scale=1 / math.sqrt(2)) < BF16_RTOL
+
+
+def test_conv3x3_padded_input_channels():
+    assert _conv_case("3x3 6->96 (pitch 8)", 2, 32, 32, 6, 96) < BF16_RTOL
+
+
+def test_conv3x3_small_output_channels():
+    assert _conv_case("3x3 96->6", 2, 32, 32, 96, 6) < BF16_RTOL
+
+
+def test_conv3x3_n288_two_accumulators():
+    assert _conv_case("3x3 192->288 10x10 n_tile=288", 5, 10, 10, 192, 288, n_tile=288) < BF16_RTOL
+    assert _conv_case("3x3 192->288 10x10 n_tile=144", 5, 10, 10, 192, 288, n_tile=144) < BF16_RTOL
+
+
+def test_conv3x3_ragged_tiles():
+    # 5x5 images, batch not a multiple of the tile's batch extent, deep K
+    assert _conv_case("3x3 288->288 5x5 B=7", 7, 5, 5, 288, 288) < BF16_RTOL
+    assert _conv_case("3x3 96->96 13x11 B=3", 3, 13, 11, 96, 96) < BF16_RTOL
+
+
+def test_conv3x3_explicit_tiles():
+    for tile in [(16, 8, 1), (8, 16, 1), (8, 8, 2), (4, 4, 8), (32, 4, 1)]:
+        assert _conv_case(f"3x3 96->96 32x32 tile={tile}", 8, 32, 32, 96, 96, tile=tile) < BF16_RTOL
+
+
+def test_two_segments_concat_plus_skip():
+    """conv3x3 over cat([a1, a2]) plus a 1x1 skip conv over raw x folded in as extra K."""
+    k = _kern()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(5)
+    B, H, W, c1, c2, cs, cout = 2, 20, 20, 96, 64, 160, 96
+    a1 = torch.randn(B, c1, H, W, device=dev, generator=g).to(torch.bfloat16)
+    a2 = torch.randn(B, c2, H, W, device=dev, generator=g).to(torch.bfloat16)
+    xs = torch.randn(B, cs, H, W, device=dev, generator=g).to(torch.bfloat16)
+    w3 = (torch.randn(cout, c1 + c2, 3, 3, device=dev, generator=g) / math.sqrt(9 * (c1 + c2))).to(torch.bfloat16)
+    w1 = (torch.randn(cout, cs, 1, 1, device=dev, generator=g) / math.sqrt(cs)).to(torch.bfloat16)
+    ref = F.conv2d(torch.cat([a1, a2], 1).float(), w3.float(), padding=1) + F.conv2d(xs.float(), w1.float())
+    wt = torch.cat([k.pack_conv_weight(w3[:, :c1]), k.pack_conv_weight(w3[:, c1:]), k.pack_conv_weight(w1)], dim=1).contiguous()
+    out = torch.empty(B, H, W, cout, device=dev, dtype=torch.bfloat16)
+    k.conv_gemm([(_nhwc(a1), c1, 0, c1, 9), (_nhwc(a2), c2, 0, c2, 9), (_nhwc(xs), cs, 0, cs, 1)], wt, cout, out,
+                batch=B, h=H, w=W)
+    torch.cuda.synchronize()
+    assert _report("2 segments + skip", out.permute(0, 3, 1, 2), ref, BF16_RTOL) < BF16_RTOL
+
+
+def test_batched_gemm_attention_shapes():
+    """S[b] = Q[b] K[b]^T with Q,K slices of one [B, L, 2C] buffer; fp32 logits."""
+    k = _kern()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(7)
+    for (B, L, C) in [(3, 400, 192), (2, 100, 288), (4, 25, 288)]:
+        qk = torch.randn(B, L, 2 * C, device=dev, generator=g).to(torch.bfloat16)
+        ref = torch.einsum("blc,bmc->blm", qk[..., :C].float(), qk[..., C:].float())
+        lp = k.ceil_to(L, 8)
+        out = torch.full((B, L, lp), float("nan"), device=dev, dtype=torch.float32)
+        k.conv_gemm([(qk, 2 * C, 0, C, 1)], qk, L, out, batch=1, h=1, w=L, out_pitch=lp, n_store=L,
+                    n_tile=208 if L > 256 else k.ceil_to(L, 16), z_batches=B, a_batch_step=1,
+                    wt_batch_stride=L * 2 * C, wt_pitch=2 * C, wt_k_off=C, k_valid=C, wt_rows=L,
+                    out_z_stride=L * lp)
+        torch.cuda.synchronize()
+        assert _report(f"QK^T B={B} L={L} C={C}", out[..., :L], ref, F32_RTOL) < F32_RTOL
+
+
+def test_batched_gemm_weights_as_a_operand():
+    """V^T[b] = Wv^T h[b]^T: the weight matrix is the (unbatched) A image, h[b] the batched B."""
+    k = _kern()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(9)
+    B, L, C = 3, 100, 192
+    hh = torch.randn(B, L, C, device=dev, generator=g).to(torch.bfloat16)
+    wv = (torch.randn(C, C, device=dev, generator=g) / math.sqrt(C)).to(torch.bfloat16)  # [in, out]
+    bv = torch.randn(C + 16, device=dev, generator=g)
+    ref = torch.einsum("blc,cd->bdl", hh.float(), wv.float()) + bv[:C].view(1, C, 1)
+    lp = k.ceil_to(L, 8)
+    out = torch.zeros(B, C, lp, device=dev, dtype=torch.bfloat16)
+    a = wv.t().contiguous()  # [out, in] rows = output channel
+    k.conv_gemm([(a, C, 0, C, 1)], hh, L, out, batch=1, h=1, w=C, out_pitch=lp, n_store=L,
+                n_tile=k.ceil_to(L, 16), z_batches=B, a_batch_step=0, wt_batch_stride=L * C, wt_rows=L,
+                out_z_stride=C * lp, bias=bv, bias_per_row=True)
+    torch.cuda.synchronize()
+    assert _report("V^T", out[..., :L], ref, BF16_RTOL) < BF16_RTOL
+
+
+def test_conv3x3_full_resolution_timing():
+    """160x160, 96->96, B=8: correctness at the dominant shape plus a rough timing print."""
+    k = _kern()
+    rel = _conv_case("3x3 96->96 160x160 B=8", 8, 160, 160, 96, 96, temb=True, res=True, scale=0.5)
+    assert rel < BF16_RTOL
+    dev = "cuda"
+    B, H, W, C = 64, 160, 160, 96
+    a = torch.randn(B, H, W, C, device=dev).to(torch.bfloat16)
+    wt = k.pack_conv_weight((torch.randn(C, C, 3, 3, device=dev) / 30).to(torch.bfloat16))
+    out = torch.empty(B, H, W, C, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        k.conv_gemm([(a, C, 0, C, 9)], wt, C, out, batch=B, h=H, w=W)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        k.conv_gemm([(a, C, 0, C, 9)], wt, C, out, batch=B, h=H, w=W)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    flops = 2.0 * B * H * W * C * C * 9
+    print(f"[conv_gemm] 3x3 96->96 160x160 B=64: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s")
