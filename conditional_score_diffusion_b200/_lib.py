@@ -70,10 +70,39 @@ class ConvGemmDesc(ctypes.Structure):
 
 # name -> (restype, argtypes). Every symbol declared in include/csd_b200.h must be listed here;
 # tests/test_abi.py checks both directions against the header text.
+c_float_p = ctypes.POINTER(c_float)
+c_int_p = ctypes.POINTER(c_int)
+
 _PROTOTYPES = {
     "csd_last_error": (ctypes.c_char_p, []),
     "csd_abi_version": (c_int, []),
-    "csd_device_sm_count": (c_int, [ctypes.POINTER(c_int)]),
+    "csd_device_sm_count": (c_int, [c_int_p]),
+    "csd_upfirdn2d_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64] + [c_int] * 12 + [c_void_p]),
+    "csd_upfirdn2d_out_size": (c_int, [c_int] * 12 + [c_int_p, c_int_p]),
+    "csd_fused_bias_act_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int,
+                                       c_int, c_float, c_float, c_void_p]),
+    "csd_ve_perturb_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "csd_langevin_norms_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    "csd_langevin_update_f32": (c_int, [c_void_p] * 6 + [c_int, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
+    "csd_reverse_diffusion_update_f32": (c_int, [c_void_p] * 5 + [c_int64, c_void_p, c_void_p, c_int, c_void_p,
+                                                 c_void_p]),
+    "csd_euler_maruyama_update_f32": (c_int, [c_void_p] * 5 + [c_int64, c_void_p, c_void_p, c_float, c_int,
+                                              c_void_p, c_void_p]),
+    "csd_step_advance": (c_int, [c_void_p, c_void_p]),
+    "csd_nchw_to_nhwc_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_float, c_float, c_void_p]),
+    "csd_nhwc_bf16_to_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                                      c_void_p]),
+    "csd_gn_stats_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                  c_void_p]),
+    "csd_gn_apply_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "csd_fir_resample_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                           c_float_p, c_void_p]),
+    "csd_softmax_rows_f32_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_float, c_void_p]),
+    "csd_time_embedding_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p]),
+    "csd_dense_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "csd_conv_gemm": (c_int, [ctypes.POINTER(ConvGemmDesc), c_void_p]),
 }
 

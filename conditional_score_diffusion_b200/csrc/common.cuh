@@ -39,8 +39,13 @@ inline int check_cuda(cudaError_t e, const char* what) {
 
 #define CSD_LAUNCH_CHECK(name) CSD_CUDA(cudaGetLastError())
 
-inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
-inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+#ifdef __CUDACC__
+#define CSD_HD __host__ __device__
+#else
+#define CSD_HD
+#endif
+CSD_HD inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+CSD_HD inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
 int num_sms();  // SM count of the current device (cached)
 

@@ -1,0 +1,356 @@
+// upfirdn2d (NCHW fp32 planes, the reference's native op) and the NHWC bf16 FIR resampler used
+// inside the score network.
+//
+// Reference: op/upfirdn2d_kernel.cu:49-207 (kernels), :209-369 (dispatch), op/upfirdn2d.py:159-200
+// (semantics). Both reference kernels use scalar 4-byte loads, `volatile` shared memory and one
+// block shape for every size. Here:
+//   * tile kernel  - one CTA = one output tile of one plane. The input footprint of the tile is
+//                    staged in shared memory by ONE TMA box load (cp.async.bulk.tensor.3d over
+//                    [planes, H, W]); coordinates outside the image are zero-filled by the TMA unit,
+//                    which is exactly upfirdn's zero padding. Outputs are evaluated polyphase (only
+//                    the K/up taps that hit a real sample) and written as 8/16-byte vectors.
+//                    Instantiated for the three geometries NCSN++ uses (up2 / down2 / 1:1, 4x4).
+//   * generic kernel - any up/down/pad/kernel <= 8x8, one thread per output. Also the fallback when
+//                    a row pitch is not a multiple of 16 bytes (TMA's stride rule).
+// HBM-bound: algorithmic bytes = 4 * (in + out elements).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tensormap.cuh"
+#include "../../include/csd_b200.h"
+
+namespace csd {
+
+struct UpfirdnParams {
+  const float* in;
+  const float* kernel;  // device [kh, kw]
+  float* out;
+  long long planes;
+  int in_h, in_w, out_h, out_w;
+  int kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_y0;
+  int tiles_x, tiles_y;
+};
+
+__device__ __forceinline__ int pmod(int a, int m) {
+  int r = a % m;
+  return r < 0 ? r + m : r;
+}
+__device__ __forceinline__ int floor_div(int a, int b) {
+  int q = a / b;
+  return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+// ---- generic: one thread per output ------------------------------------------------------------
+__global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(UpfirdnParams p) {
+  __shared__ float kf[64];
+  for (int i = threadIdx.x; i < p.kh * p.kw; i += blockDim.x) {
+    const int ky = i / p.kw, kx = i % p.kw;
+    kf[i] = p.kernel[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)];  // flipped: true convolution
+  }
+  __syncthreads();
+  const long long total = p.planes * p.out_h * p.out_w;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % p.out_w);
+    const int oy = (int)((idx / p.out_w) % p.out_h);
+    const long long plane = idx / ((long long)p.out_w * p.out_h);
+    const float* src = p.in + plane * p.in_h * p.in_w;
+    const int uy = oy * p.down_y - p.pad_y0;
+    const int ux = ox * p.down_x - p.pad_x0;
+    float acc = 0.f;
+    for (int ky = pmod(-uy, p.up_y); ky < p.kh; ky += p.up_y) {
+      const int iy = (uy + ky) / p.up_y;  // exact: uy + ky is a multiple of up_y
+      if (uy + ky < 0 || iy >= p.in_h) continue;
+      for (int kx = pmod(-ux, p.up_x); kx < p.kw; kx += p.up_x) {
+        const int ix = (ux + kx) / p.up_x;
+        if (ux + kx < 0 || ix >= p.in_w) continue;
+        acc += kf[ky * p.kw + kx] * __ldg(src + (long long)iy * p.in_w + ix);
+      }
+    }
+    p.out[idx] = acc;
+  }
+}
+
+// ---- tiled: TMA-staged input footprint, polyphase evaluation, vector stores ----------------------
+template <int UP, int DOWN, int K>
+struct TileCfg {
+  static constexpr int TX = 32, TY = 8;
+  static constexpr int CX = (DOWN == 1) ? 4 : 2;  // outputs per thread along x (one vector store)
+  static constexpr int RY = 4;                    // output rows per thread
+  static constexpr int TOW = TX * CX, TOH = TY * RY;
+  static constexpr int SPAN_W = (TOW - 1) * DOWN + K, SPAN_H = (TOH - 1) * DOWN + K;
+  static constexpr int IN_TW = (((SPAN_W + UP - 1) / UP + 1) + 3) & ~3;  // 16-byte rows for TMA
+  static constexpr int IN_TH = (SPAN_H + UP - 1) / UP + 1;
+  static_assert(IN_TW <= 256 && IN_TH <= 256, "TMA box dimension limit");
+};
+
+template <int UP, int DOWN, int K, bool USE_TMA>
+__global__ void __launch_bounds__(256)
+upfirdn2d_tile_kernel(const __grid_constant__ CUtensorMap map, const UpfirdnParams p) {
+  using C = TileCfg<UP, DOWN, K>;
+  __shared__ __align__(128) float tile[C::IN_TH * C::IN_TW];
+  __shared__ float kf[K * K];
+  __shared__ __align__(8) unsigned long long bar;
+
+  const int tid = threadIdx.x;
+  long long bid = blockIdx.x;
+  const int tix = (int)(bid % p.tiles_x);
+  const int tiy = (int)((bid / p.tiles_x) % p.tiles_y);
+  const long long plane = bid / ((long long)p.tiles_x * p.tiles_y);
+  const int ox0 = tix * C::TOW, oy0 = tiy * C::TOH;
+  // first input sample whose upsampled position is >= the first tap of the tile
+  const int ix0 = floor_div(ox0 * DOWN - p.pad_x0 + UP - 1, UP);
+  const int iy0 = floor_div(oy0 * DOWN - p.pad_y0 + UP - 1, UP);
+
+  if (USE_TMA) {
+    if (tid == 0) {
+      ptx::mbar_init(ptx::smem_u32(&bar), 1);
+      ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar), C::IN_TH * C::IN_TW * 4);
+      ptx::tma_load_3d(ptx::smem_u32(tile), &map, ptx::smem_u32(&bar), ix0, iy0, (int)plane);
+    }
+  } else {
+    const float* src = p.in + plane * p.in_h * p.in_w;
+    for (int i = tid; i < C::IN_TH * C::IN_TW; i += 256) {
+      const int r = i / C::IN_TW, c = i % C::IN_TW;
+      const int gy = iy0 + r, gx = ix0 + c;
+      tile[i] = (gy >= 0 && gy < p.in_h && gx >= 0 && gx < p.in_w) ? __ldg(src + (long long)gy * p.in_w + gx) : 0.f;
+    }
+  }
+  if (tid < K * K) {
+    const int ky = tid / K, kx = tid % K;
+    kf[tid] = p.kernel[(K - 1 - ky) * K + (K - 1 - kx)];
+  }
+  if (USE_TMA) {
+    __syncthreads();  // kf visible
+    ptx::mbar_wait(ptx::smem_u32(&bar), 0);
+  } else {
+    __syncthreads();
+  }
+
+  const int txx = tid & 31, tyy = tid >> 5;
+  const int oxb = ox0 + txx * C::CX;
+  constexpr int NT = (K + UP - 1) / UP;  // taps that can hit a real sample, per axis
+  int kx0[C::CX], xi[C::CX];
+#pragma unroll
+  for (int c = 0; c < C::CX; ++c) {
+    const int ux = (oxb + c) * DOWN - p.pad_x0;
+    kx0[c] = pmod(-ux, UP);
+    xi[c] = (ux + kx0[c] - ix0 * UP) / UP;  // column in the tile of the first contributing sample
+  }
+  float* dst_plane = p.out + plane * p.out_h * p.out_w;
+#pragma unroll
+  for (int r = 0; r < C::RY; ++r) {
+    const int oy = oy0 + tyy * C::RY + r;
+    if (oy >= p.out_h) break;
+    const int uy = oy * DOWN - p.pad_y0;
+    const int ky0 = pmod(-uy, UP);
+    const int yi = (uy + ky0 - iy0 * UP) / UP;
+    float acc[C::CX];
+#pragma unroll
+    for (int c = 0; c < C::CX; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int jy = 0; jy < NT; ++jy) {
+      const int ky = ky0 + jy * UP;
+      if (ky < K) {
+        const float* srow = tile + (yi + jy) * C::IN_TW;
+#pragma unroll
+        for (int c = 0; c < C::CX; ++c) {
+#pragma unroll
+          for (int jx = 0; jx < NT; ++jx) {
+            const int kx = kx0[c] + jx * UP;
+            if (kx < K) acc[c] = fmaf(kf[ky * K + kx], srow[xi[c] + jx], acc[c]);
+          }
+        }
+      }
+    }
+    float* dst = dst_plane + (long long)oy * p.out_w + oxb;
+    const bool vec_ok = (oxb + C::CX <= p.out_w) && ((p.out_w & (C::CX - 1)) == 0);
+    if (vec_ok) {
+      if (C::CX == 4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      } else {
+        *reinterpret_cast<float2*>(dst) = make_float2(acc[0], acc[1]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C::CX; ++c)
+        if (oxb + c < p.out_w) dst[c] = acc[c];
+    }
+  }
+}
+
+template <int UP, int DOWN, int K>
+static int launch_tile(const UpfirdnParams& p0, cudaStream_t stream) {
+  using C = TileCfg<UP, DOWN, K>;
+  UpfirdnParams p = p0;
+  p.tiles_x = ceil_div(p.out_w, C::TOW);
+  p.tiles_y = ceil_div(p.out_h, C::TOH);
+  const long long blocks = p.planes * p.tiles_x * p.tiles_y;
+  CSD_REQUIRE(blocks < (1LL << 31), "upfirdn2d: too many tiles (%lld)", blocks);
+  const bool tma_ok = ((p.in_w * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) &&
+                      p.planes < (1LL << 31) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (tma_ok) {
+    uint64_t dims[3] = {(uint64_t)p.in_w, (uint64_t)p.in_h, (uint64_t)p.planes};
+    uint64_t strides[2] = {(uint64_t)p.in_w * 4, (uint64_t)p.in_w * 4 * p.in_h};
+    uint32_t box[3] = {(uint32_t)C::IN_TW, (uint32_t)C::IN_TH, 1};
+    int st = encode_tensor_map(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.in, dims, strides, box, TMA_SW_NONE);
+    if (st != CSD_OK) return st;
+    upfirdn2d_tile_kernel<UP, DOWN, K, true><<<(unsigned)blocks, 256, 0, stream>>>(map, p);
+  } else {
+    upfirdn2d_tile_kernel<UP, DOWN, K, false><<<(unsigned)blocks, 256, 0, stream>>>(map, p);
+  }
+  CSD_LAUNCH_CHECK("upfirdn2d_tile_kernel");
+  return CSD_OK;
+}
+
+// ---- NHWC bf16 FIR x2 resampling (4-tap separable filter) -----------------------------------------
+// mode 1: up x2, pad (2,1), taps scaled by 2 per axis  (upsample_2d, up_or_down_sampling.py:195-224)
+// mode 2: down x2, pad (1,1)                           (downsample_2d, :227-257)
+// One thread = one output pixel x 8 channels (16-byte vectors, coalesced along channels).
+struct FirNhwcParams {
+  const bf16x8* src;
+  bf16x8* out;
+  const bf16x8* add;
+  int batch, h, w, oh, ow, cvec;  // cvec = channel pitch / 8
+  float kf[4];                    // flipped, normalised 1-D taps (already x2 for mode 1)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) fir_nhwc_kernel(FirNhwcParams p) {
+  const long long total = (long long)p.batch * p.oh * p.ow * p.cvec;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % p.cvec);
+    long long pix = idx / p.cvec;
+    const int ox = (int)(pix % p.ow);
+    const int oy = (int)((pix / p.ow) % p.oh);
+    const int b = (int)(pix / ((long long)p.ow * p.oh));
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    // contributing input rows / columns and their weights
+    int iy[4], ix[4];
+    float wy[4], wx[4];
+    int ny, nx;
+    if (MODE == 1) {
+      // out[2i] = in[i-1] kf[0] + in[i] kf[2];  out[2i+1] = in[i] kf[1] + in[i+1] kf[3]
+      const int i = oy >> 1, j = ox >> 1;
+      ny = nx = 2;
+      if ((oy & 1) == 0) { iy[0] = i - 1; wy[0] = p.kf[0]; iy[1] = i; wy[1] = p.kf[2]; }
+      else               { iy[0] = i;     wy[0] = p.kf[1]; iy[1] = i + 1; wy[1] = p.kf[3]; }
+      if ((ox & 1) == 0) { ix[0] = j - 1; wx[0] = p.kf[0]; ix[1] = j; wx[1] = p.kf[2]; }
+      else               { ix[0] = j;     wx[0] = p.kf[1]; ix[1] = j + 1; wx[1] = p.kf[3]; }
+    } else {
+      // out[o] = sum_k kf[k] in[2o - 1 + k]
+      ny = nx = 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        iy[k] = 2 * oy - 1 + k; wy[k] = p.kf[k];
+        ix[k] = 2 * ox - 1 + k; wx[k] = p.kf[k];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (a >= ny) break;
+      if (iy[a] < 0 || iy[a] >= p.h) continue;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c >= nx) break;
+        if (ix[c] < 0 || ix[c] >= p.w) continue;
+        const bf16x8 v = p.src[(((long long)b * p.h + iy[a]) * p.w + ix[c]) * p.cvec + cv];
+        float f[8];
+        unpack8(v, f);
+        const float wgt = wy[a] * wx[c];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, f[i], acc[i]);
+      }
+    }
+    if (p.add != nullptr) {
+      float f[8];
+      unpack8(p.add[idx], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+    p.out[idx] = pack8(acc);
+  }
+}
+
+}  // namespace csd
+
+extern "C" {
+
+int csd_upfirdn2d_out_size(int in_h, int in_w, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                           int pad_x0, int pad_x1, int pad_y0, int pad_y1, int* out_h, int* out_w) {
+  CSD_REQUIRE(out_h && out_w, "null output");
+  CSD_REQUIRE(up_x >= 1 && up_y >= 1 && down_x >= 1 && down_y >= 1, "up/down must be >= 1");
+  const int hh = in_h * up_y + pad_y0 + pad_y1 - kh;
+  const int ww = in_w * up_x + pad_x0 + pad_x1 - kw;
+  CSD_REQUIRE(hh >= 0 && ww >= 0, "upfirdn2d: kernel larger than the padded input");
+  *out_h = hh / down_y + 1;
+  *out_w = ww / down_x + 1;
+  return CSD_OK;
+}
+
+int csd_upfirdn2d_f32(const float* input, const float* kernel, float* output, int64_t planes, int in_h, int in_w,
+                      int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1,
+                      int pad_y0, int pad_y1, csd_stream_t stream_) {
+  using namespace csd;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CSD_REQUIRE(input && kernel && output, "upfirdn2d: null pointer");
+  CSD_REQUIRE(planes >= 0 && in_h >= 1 && in_w >= 1, "upfirdn2d: bad input shape");
+  CSD_REQUIRE(kh >= 1 && kw >= 1 && kh * kw <= 64, "upfirdn2d: kernel %dx%d unsupported (max 64 taps)", kh, kw);
+  UpfirdnParams p;
+  memset(&p, 0, sizeof(p));
+  int st = csd_upfirdn2d_out_size(in_h, in_w, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1,
+                                  &p.out_h, &p.out_w);
+  if (st != CSD_OK) return st;
+  if (planes == 0) return CSD_OK;
+  p.in = input; p.kernel = kernel; p.out = output; p.planes = planes;
+  p.in_h = in_h; p.in_w = in_w; p.kh = kh; p.kw = kw;
+  p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y;
+  p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  const bool square = (up_x == up_y) && (down_x == down_y) && (kh == kw) && kh == 4;
+  if (square && up_x == 2 && down_x == 1) return launch_tile<2, 1, 4>(p, stream);
+  if (square && up_x == 1 && down_x == 2) return launch_tile<1, 2, 4>(p, stream);
+  if (square && up_x == 1 && down_x == 1) return launch_tile<1, 1, 4>(p, stream);
+  const long long total = planes * p.out_h * p.out_w;
+  const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)num_sms() * 32);
+  upfirdn2d_generic_kernel<<<blocks, 256, 0, stream>>>(p);
+  CSD_LAUNCH_CHECK("upfirdn2d_generic_kernel");
+  return CSD_OK;
+}
+
+int csd_fir_resample_nhwc_bf16(const void* src, void* out, const void* add, int batch, int h, int w, int c_pitch,
+                               int mode, const float* taps4_host, csd_stream_t stream_) {
+  using namespace csd;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CSD_REQUIRE(src && out && taps4_host, "fir_resample: null pointer");
+  CSD_REQUIRE(mode == 1 || mode == 2, "fir_resample: mode %d (1 = up, 2 = down)", mode);
+  CSD_REQUIRE(c_pitch % 8 == 0, "fir_resample: channel pitch %d not a multiple of 8", c_pitch);
+  CSD_REQUIRE(mode == 1 || (h % 2 == 0 && w % 2 == 0), "fir_resample: odd size %dx%d for downsampling", h, w);
+  FirNhwcParams p;
+  p.src = static_cast<const bf16x8*>(src);
+  p.out = static_cast<bf16x8*>(out);
+  p.add = static_cast<const bf16x8*>(add);
+  p.batch = batch; p.h = h; p.w = w; p.cvec = c_pitch / 8;
+  p.oh = mode == 1 ? h * 2 : h / 2;
+  p.ow = mode == 1 ? w * 2 : w / 2;
+  float sum = 0.f;
+  for (int i = 0; i < 4; ++i) sum += taps4_host[i];
+  CSD_REQUIRE(sum != 0.f, "fir_resample: taps sum to zero");
+  for (int i = 0; i < 4; ++i) p.kf[i] = taps4_host[3 - i] / sum * (mode == 1 ? 2.f : 1.f);
+  const long long total = (long long)batch * p.oh * p.ow * p.cvec;
+  if (total == 0) return CSD_OK;
+  const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)num_sms() * 16);
+  if (mode == 1) fir_nhwc_kernel<1><<<blocks, 256, 0, stream>>>(p);
+  else fir_nhwc_kernel<2><<<blocks, 256, 0, stream>>>(p);
+  CSD_LAUNCH_CHECK("fir_nhwc_kernel");
+  return CSD_OK;
+}
+
+}  // extern "C"

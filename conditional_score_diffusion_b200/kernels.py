@@ -125,3 +125,149 @@ def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None
     d.scale = scale
     check(_lib.lib().csd_conv_gemm(ctypes.byref(d), _stream()))
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# module-surface ops (NCHW fp32)
+# --------------------------------------------------------------------------------------------
+def upfirdn2d_out_size(in_h, in_w, kh, kw, up_x, up_y, down_x, down_y, px0, px1, py0, py1):
+    oh, ow = ctypes.c_int(0), ctypes.c_int(0)
+    check(_lib.lib().csd_upfirdn2d_out_size(in_h, in_w, kh, kw, up_x, up_y, down_x, down_y, px0, px1, py0, py1,
+                                            ctypes.byref(oh), ctypes.byref(ow)))
+    return oh.value, ow.value
+
+
+def upfirdn2d_planes(x, kernel, up_x, up_y, down_x, down_y, px0, px1, py0, py1):
+    """x [planes, H, W] fp32 contiguous CUDA, kernel [kh, kw] fp32 CUDA -> [planes, OH, OW]."""
+    _require_cuda(x, kernel)
+    assert x.dtype == torch.float32 and kernel.dtype == torch.float32
+    x = x.contiguous()
+    kernel = kernel.contiguous()
+    planes, in_h, in_w = x.shape
+    kh, kw = kernel.shape
+    oh, ow = upfirdn2d_out_size(in_h, in_w, kh, kw, up_x, up_y, down_x, down_y, px0, px1, py0, py1)
+    out = torch.empty(planes, oh, ow, device=x.device, dtype=torch.float32)
+    check(_lib.lib().csd_upfirdn2d_f32(_ptr(x), _ptr(kernel), _ptr(out), planes, in_h, in_w, kh, kw, up_x, up_y,
+                                       down_x, down_y, px0, px1, py0, py1, _stream()))
+    return out
+
+
+def fused_bias_act(x, bias, refer, act, grad, alpha, scale):
+    """op/fused_bias_act semantics over a contiguous fp32 tensor; bias broadcasts over dim 1."""
+    _require_cuda(x, bias, refer)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    size_b, step_b = 0, 1
+    if bias is not None and bias.numel() > 0:
+        size_b = bias.numel()
+        step_b = 1
+        for d in x.shape[2:]:
+            step_b *= d
+    else:
+        bias = None
+    if refer is not None and refer.numel() == 0:
+        refer = None
+    check(_lib.lib().csd_fused_bias_act_f32(_ptr(x), _ptr(bias), _ptr(refer.contiguous() if refer is not None else None),
+                                            _ptr(out), x.numel(), size_b, step_b, act, grad, alpha, scale, _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# PC update kernels (fp32, contiguous, [batch, ...])
+# --------------------------------------------------------------------------------------------
+def ve_perturb(y, z, out, sigma_tab, step_idx):
+    _require_cuda(y, z, out, sigma_tab, step_idx)
+    check(_lib.lib().csd_ve_perturb_f32(_ptr(y), _ptr(z), _ptr(out), y.numel(), _ptr(sigma_tab), _ptr(step_idx), _stream()))
+    return out
+
+
+def langevin_norms(grad, noise, norms):
+    b = grad.shape[0]
+    check(_lib.lib().csd_langevin_norms_f32(_ptr(grad), _ptr(noise), _ptr(norms), b, grad.numel() // b, _stream()))
+    return norms
+
+
+def langevin_update(x, grad, noise, norms, x_out, x_mean, snr, alpha_tab, step_idx):
+    b = x.shape[0]
+    check(_lib.lib().csd_langevin_update_f32(_ptr(x), _ptr(grad), _ptr(noise), _ptr(norms), _ptr(x_out), _ptr(x_mean),
+                                             b, x.numel() // b, float(snr), _ptr(alpha_tab), _ptr(step_idx), _stream()))
+
+
+def reverse_diffusion_update(x, score, noise, x_out, x_mean, f_tab, g_tab, probability_flow, step_idx):
+    check(_lib.lib().csd_reverse_diffusion_update_f32(_ptr(x), _ptr(score), _ptr(noise), _ptr(x_out), _ptr(x_mean),
+                                                      x.numel(), _ptr(f_tab), _ptr(g_tab), int(probability_flow),
+                                                      _ptr(step_idx), _stream()))
+
+
+def euler_maruyama_update(x, score, noise, x_out, x_mean, d_tab, g_tab, dt, probability_flow, step_idx):
+    check(_lib.lib().csd_euler_maruyama_update_f32(_ptr(x), _ptr(score), _ptr(noise), _ptr(x_out), _ptr(x_mean),
+                                                   x.numel(), _ptr(d_tab), _ptr(g_tab), float(dt),
+                                                   int(probability_flow), _ptr(step_idx), _stream()))
+
+
+def step_advance(step_idx):
+    check(_lib.lib().csd_step_advance(_ptr(step_idx), _stream()))
+
+
+# --------------------------------------------------------------------------------------------
+# score-network building blocks (NHWC bf16)
+# --------------------------------------------------------------------------------------------
+def nchw_to_nhwc(src0, src1, out, scale=1.0, shift=0.0):
+    b, c0, h, w = src0.shape
+    c1 = src1.shape[1] if src1 is not None else 0
+    check(_lib.lib().csd_nchw_to_nhwc_bf16(_ptr(src0), c0, _ptr(src1), c1, _ptr(out), out.shape[-1], b, h, w,
+                                           float(scale), float(shift), _stream()))
+    return out
+
+
+def nhwc_to_nchw(src, c_off, c_cnt, dst, row_scale=None):
+    b, h, w, pitch = src.shape
+    check(_lib.lib().csd_nhwc_bf16_to_nchw(_ptr(src), pitch, c_off, c_cnt, _ptr(dst), b, h, w, _ptr(row_scale), _stream()))
+    return dst
+
+
+def gn_stats(src0, c0, src1, c1, sums, groups):
+    """src tensors [B, H, W, pitch] (or [B, HW, pitch]); sums [B, groups, 2] fp32, pre-zeroed."""
+    b = src0.shape[0]
+    hw = src0.numel() // (b * src0.shape[-1])
+    check(_lib.lib().csd_gn_stats_bf16(_ptr(src0), c0, src0.shape[-1], _ptr(src1), c1,
+                                       src1.shape[-1] if src1 is not None else 0, _ptr(sums), b, hw, groups, _stream()))
+    return sums
+
+
+def gn_apply(src0, c0, src1, c1, sums, gamma, beta, out, groups, eps=1e-6, silu=True):
+    b = src0.shape[0]
+    hw = src0.numel() // (b * src0.shape[-1])
+    check(_lib.lib().csd_gn_apply_bf16(_ptr(src0), c0, src0.shape[-1], _ptr(src1), c1,
+                                       src1.shape[-1] if src1 is not None else 0, _ptr(sums), _ptr(gamma), _ptr(beta),
+                                       _ptr(out), out.shape[-1], b, hw, groups, float(eps), int(silu), _stream()))
+    return out
+
+
+def fir_resample(src, out, mode, taps, add=None):
+    """mode 'up' | 'down'; src/out NHWC bf16."""
+    b, h, w, pitch = src.shape
+    arr = (ctypes.c_float * 4)(*[float(t) for t in taps])
+    check(_lib.lib().csd_fir_resample_nhwc_bf16(_ptr(src), _ptr(out), _ptr(add), b, h, w, pitch,
+                                                1 if mode == "up" else 2, arr, _stream()))
+    return out
+
+
+def softmax_rows(logits, probs, cols, scale):
+    rows = logits.numel() // logits.shape[-1]
+    check(_lib.lib().csd_softmax_rows_f32_bf16(_ptr(logits), logits.shape[-1], _ptr(probs), probs.shape[-1], rows, cols,
+                                               float(scale), _stream()))
+    return probs
+
+
+def time_embedding(labels, nf, embedding_type, fourier_w, w0, b0, w1, b1, out):
+    check(_lib.lib().csd_time_embedding_f32(_ptr(labels), labels.shape[0], nf, 1 if embedding_type == "fourier" else 0,
+                                            _ptr(fourier_w), _ptr(w0), _ptr(b0), _ptr(w1), _ptr(b1), _ptr(out), _stream()))
+    return out
+
+
+def dense_rows(act, w, bias, out, total_out=None):
+    b, in_dim = act.shape
+    total_out = total_out if total_out is not None else w.shape[0]
+    check(_lib.lib().csd_dense_rows_f32(_ptr(act), _ptr(w), _ptr(bias), _ptr(out), b, in_dim, total_out, _stream()))
+    return out

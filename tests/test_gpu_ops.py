@@ -1,0 +1,260 @@
+"""Parity of the individual CUDA ops (through the C ABI) against the CPU oracle.
+
+fp32 ops: tolerance 1e-5 relative to the tensor's max magnitude (different summation order).
+bf16-storage ops: inputs are rounded to bf16 first; the output tolerance is one bf16 ulp (2^-8
+relative to max magnitude) because the result is stored as bf16.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from golden_utils import golden
+from oracle import ncsnpp as o_net
+from oracle import ops as o_ops
+from oracle import sampling as o_samp
+from oracle import sde as o_sde
+
+pytestmark = pytest.mark.gpu
+
+F32 = 1e-5
+BF16 = 2.0 ** -8
+
+
+def K():
+    from conditional_score_diffusion_b200 import kernels
+    return kernels
+
+
+def _close(got, ref, rtol, what):
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    assert got.shape == ref.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    scale = ref.abs().max().item() + 1e-12
+    err = (got - ref).abs().max().item()
+    print(f"[ops] {what}: max_err={err:.3e} scale={scale:.3e} rel={err / scale:.2e}")
+    assert err <= rtol * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+def _upfirdn(x, k, up, down, pad):
+    k_ = K()
+    n, c, h, w = x.shape
+    out = k_.upfirdn2d_planes(x.cuda().reshape(n * c, h, w), k.cuda(), up, up, down, down, pad[0], pad[1], pad[0], pad[1])
+    return out.reshape(n, c, out.shape[-2], out.shape[-1])
+
+
+def test_upfirdn2d_golden_cases():
+    for i, c in enumerate(golden()["upfirdn2d"]):
+        _close(_upfirdn(c["x"], c["k"], c["up"], c["down"], c["pad"]), c["y"], F32, f"upfirdn2d golden {i}")
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 160, 160), (1, 5, 80, 80), (3, 2, 20, 20), (2, 2, 10, 10), (1, 3, 5, 5),
+                                   (1, 2, 37, 53), (1, 1, 130, 260)])
+def test_upfirdn2d_hot_modes_vs_oracle(shape):
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    k_up = torch.tensor(o_ops.setup_kernel([1, 3, 3, 1]) * 4)
+    k_dn = torch.tensor(o_ops.setup_kernel([1, 3, 3, 1]))
+    k_rand = torch.rand(4, 4, generator=g)
+    _close(_upfirdn(x, k_up, 2, 1, (2, 1)), o_ops.upfirdn2d(x, k_up, 2, 1, (2, 1)), F32, f"up2 {shape}")
+    _close(_upfirdn(x, k_rand, 2, 1, (2, 1)), o_ops.upfirdn2d(x, k_rand, 2, 1, (2, 1)), F32, f"up2 rand-k {shape}")
+    _close(_upfirdn(x, k_dn, 1, 2, (1, 1)), o_ops.upfirdn2d(x, k_dn, 1, 2, (1, 1)), F32, f"down2 {shape}")
+    _close(_upfirdn(x, k_rand, 1, 2, (1, 1)), o_ops.upfirdn2d(x, k_rand, 1, 2, (1, 1)), F32, f"down2 rand-k {shape}")
+    _close(_upfirdn(x, k_rand, 1, 1, (2, 2)), o_ops.upfirdn2d(x, k_rand, 1, 1, (2, 2)), F32, f"1:1 {shape}")
+    # backward geometry of up2: down2 with g_pad = (1, 1) for k=4, pad=(2,1)  (op/upfirdn2d.py:110-113)
+    _close(_upfirdn(x, k_rand, 1, 2, (1, 1)), o_ops.upfirdn2d(x, k_rand, 1, 2, (1, 1)), F32, f"bwd-of-up2 {shape}")
+
+
+def test_upfirdn2d_generic_paths():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 11, 9, generator=g)
+    for (kh, up, down, pad) in [(3, 2, 2, (1, 2)), (5, 3, 1, (2, 2)), (2, 1, 3, (0, 1)), (4, 2, 1, (-1, 3)), (1, 1, 1, (0, 0))]:
+        k = torch.rand(kh, kh, generator=g)
+        _close(_upfirdn(x, k, up, down, pad), o_ops.upfirdn2d(x, k, up, down, pad), F32, f"generic k{kh} up{up} down{down} pad{pad}")
+
+
+def test_upfirdn2d_empty_and_errors():
+    k_ = K()
+    out = k_.upfirdn2d_planes(torch.empty(0, 8, 8, device="cuda"), torch.ones(4, 4, device="cuda"), 2, 2, 1, 1, 2, 1, 2, 1)
+    assert out.shape == (0, 16, 16)
+    from conditional_score_diffusion_b200._lib import CsdError
+    with pytest.raises(CsdError):
+        k_.upfirdn2d_planes(torch.ones(1, 2, 2, device="cuda"), torch.ones(9, 9, device="cuda"), 1, 1, 1, 1, 0, 0, 0, 0)
+
+
+def test_fused_bias_act_vs_oracle():
+    k_ = K()
+    f = golden()["fused_leaky_relu"]
+    out = k_.fused_bias_act(f["x"].cuda(), f["b"].cuda(), None, 3, 0, 0.2, 2 ** 0.5)
+    _close(out, f["y"], F32, "fused_leaky_relu golden")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 7, 5, 4, generator=g)
+    b = torch.randn(7, generator=g)
+    r = torch.randn(3, 7, 5, 4, generator=g)
+    for act in (1, 3):
+        for grad in (0, 1, 2):
+            ref = o_ops.fused_bias_act(x, b if grad == 0 else None, r, act, grad, 0.1, 1.3)
+            got = k_.fused_bias_act(x.cuda(), b.cuda() if grad == 0 else None, r.cuda(), act, grad, 0.1, 1.3)
+            _close(got, ref, F32, f"fused_bias_act act{act} grad{grad}")
+
+
+def test_pc_update_kernels_vs_oracle():
+    k_ = K()
+    g = torch.Generator().manual_seed(8)
+    B, shape = 4, (4, 3, 16, 16)
+    x = torch.randn(*shape, generator=g) * 3
+    score = torch.randn(*shape, generator=g) * 0.2
+    z = torch.randn(*shape, generator=g)
+    sde = o_sde.VE(0.01, 50.0, 1000)
+    vp = o_sde.VP(0.1, 20.0, 1000)
+    tvals = torch.linspace(1.0, 1e-5, 7)
+    dev = "cuda"
+    step = torch.tensor([3], dtype=torch.int32, device=dev)
+    t = torch.ones(B) * tvals[3]
+    xo, xm = torch.empty(shape, device=dev), torch.empty(shape, device=dev)
+    # Langevin (VE: alpha = 1)
+    norms = torch.empty(2 * B, device=dev)
+    k_.langevin_norms(score.cuda(), z.cuda(), norms)
+    ref_n = torch.cat([score.reshape(B, -1).norm(dim=-1), z.reshape(B, -1).norm(dim=-1)])
+    _close(norms, ref_n, F32, "langevin norms")
+    k_.langevin_update(x.cuda(), score.cuda(), z.cuda(), norms, xo, xm, 0.16, None, step)
+    rx, rm = o_samp.langevin_update(sde, score, x, t, z, 0.16)
+    _close(xo, rx, 2e-5, "langevin x"); _close(xm, rm, 2e-5, "langevin mean")
+    # Langevin (VP: alpha table)
+    alpha_tab = torch.stack([vp.alphas[(tv * (vp.N - 1)).long()] for tv in tvals]).cuda()
+    k_.langevin_update(x.cuda(), score.cuda(), z.cuda(), norms, xo, xm, 0.16, alpha_tab, step)
+    rx, rm = o_samp.langevin_update(vp, score, x, t, z, 0.16)
+    _close(xo, rx, 2e-5, "langevin vp x")
+    # reverse diffusion VE
+    g_tab = torch.stack([sde.discretize_g(torch.ones(1) * tv)[0] for tv in tvals]).cuda()
+    k_.reverse_diffusion_update(x.cuda(), score.cuda(), z.cuda(), xo, xm, None, g_tab, False, step)
+    rx, rm = o_samp.reverse_diffusion_update(sde, score, x, t, z)
+    _close(xo, rx, F32, "rd x"); _close(xm, rm, F32, "rd mean")
+    k_.reverse_diffusion_update(x.cuda(), score.cuda(), None, xo, xm, None, g_tab, True, step)
+    rx, rm = o_samp.reverse_diffusion_update(sde, score, x, t, z, probability_flow=True)
+    _close(xo, rx, F32, "rd pf x")
+    # reverse diffusion VP
+    fg = [vp.discretize_fg(torch.ones(1) * tv) for tv in tvals]
+    f_tab = torch.stack([a[0][0] for a in fg]).cuda()
+    g_tab_vp = torch.stack([a[1][0] for a in fg]).cuda()
+    k_.reverse_diffusion_update(x.cuda(), score.cuda(), z.cuda(), xo, xm, f_tab, g_tab_vp, False, step)
+    rx, rm = o_samp.reverse_diffusion_update(vp, score, x, t, z)
+    _close(xo, rx, F32, "rd vp x"); _close(xm, rm, F32, "rd vp mean")
+    # Euler-Maruyama VE / VP
+    gc = torch.stack([sde.diffusion(torch.ones(1) * tv)[0] for tv in tvals]).cuda()
+    k_.euler_maruyama_update(x.cuda(), score.cuda(), z.cuda(), xo, xm, None, gc, -1.0 / sde.N, False, step)
+    rx, rm = o_samp.euler_maruyama_update(sde, score, x, t, z)
+    _close(xo, rx, F32, "em x"); _close(xm, rm, F32, "em mean")
+    dc = torch.stack([-0.5 * vp.beta(tv) for tv in tvals]).float().cuda()
+    gv = torch.stack([vp.diffusion(torch.ones(1) * tv)[0] for tv in tvals]).cuda()
+    k_.euler_maruyama_update(x.cuda(), score.cuda(), z.cuda(), xo, xm, dc, gv, -1.0 / vp.N, False, step)
+    rx, rm = o_samp.euler_maruyama_update(vp, score, x, t, z)
+    _close(xo, rx, F32, "em vp x")
+    # y perturbation + step counter
+    sig_tab = torch.stack([sde.sigma(torch.ones(1) * tv)[0] for tv in tvals]).cuda()
+    yp = torch.empty(shape, device=dev)
+    k_.ve_perturb(x.cuda(), z.cuda(), yp, sig_tab, step)
+    _close(yp, x + z * sde.sigma(t)[:, None, None, None], F32, "ve perturb")
+    k_.step_advance(step)
+    assert step.item() == 4
+
+
+@pytest.mark.parametrize("c0,c1,hw", [(96, 0, 24 * 24), (192, 96, 100), (288, 288, 25), (16, 0, 256), (288, 192, 400), (8, 0, 64)])
+def test_groupnorm_silu_vs_torch(c0, c1, hw):
+    k_ = K()
+    g = torch.Generator().manual_seed(c0 + c1)
+    B = 3
+    C = c0 + c1
+    groups = min(C // 4, 32)
+    a = (torch.randn(B, hw, c0, generator=g) * 2 + 0.5).to(torch.bfloat16)
+    b = (torch.randn(B, hw, c1, generator=g) - 1.0).to(torch.bfloat16) if c1 else None
+    gamma = 1 + 0.2 * torch.randn(C, generator=g)
+    beta = 0.3 * torch.randn(C, generator=g)
+    full = torch.cat([a, b], -1) if c1 else a
+    ref_in = full.float().permute(0, 2, 1).reshape(B, C, hw, 1)
+    ref = F.silu(F.group_norm(ref_in, groups, gamma, beta, eps=1e-6)).reshape(B, C, hw).permute(0, 2, 1)
+    sums = torch.zeros(B, groups, 2, device="cuda")
+    ag, bg = a.cuda(), (b.cuda() if c1 else None)
+    k_.gn_stats(ag, c0, bg, c1, sums, groups)
+    n = hw * (C // groups)
+    mean_ref = ref_in.reshape(B, groups, -1).mean(-1)
+    _close(sums[..., 0] / n, mean_ref, 1e-4, f"gn mean C={C}")
+    out = torch.empty(B, hw, C, device="cuda", dtype=torch.bfloat16)
+    k_.gn_apply(ag, c0, bg, c1, sums, gamma.cuda(), beta.cuda(), out, groups, 1e-6, True)
+    _close(out, ref, BF16, f"gn+silu C={C} hw={hw}")
+    k_.gn_apply(ag, c0, bg, c1, sums, gamma.cuda(), beta.cuda(), out, groups, 1e-6, False)
+    _close(out, F.group_norm(ref_in, groups, gamma, beta, eps=1e-6).reshape(B, C, hw).permute(0, 2, 1), BF16, "gn only")
+
+
+@pytest.mark.parametrize("h,c", [(16, 96), (10, 288), (5, 8), (20, 192)])
+def test_fir_nhwc_vs_oracle(h, c):
+    k_ = K()
+    g = torch.Generator().manual_seed(h * c)
+    B = 2
+    x = torch.randn(B, c, h, h, generator=g).to(torch.bfloat16)
+    xn = x.permute(0, 2, 3, 1).contiguous().cuda()
+    up = torch.empty(B, 2 * h, 2 * h, c, device="cuda", dtype=torch.bfloat16)
+    k_.fir_resample(xn, up, "up", [1, 3, 3, 1])
+    _close(up.permute(0, 3, 1, 2), o_ops.upsample_2d(x.float()), BF16, f"fir up {h} {c}")
+    add = torch.randn(B, 2 * h, 2 * h, c, generator=g).to(torch.bfloat16)
+    k_.fir_resample(xn, up, "up", [1, 3, 3, 1], add=add.cuda())
+    _close(up.permute(0, 3, 1, 2), o_ops.upsample_2d(x.float()) + add.float().permute(0, 3, 1, 2), BF16, "fir up + add")
+    if h % 2 == 0:
+        dn = torch.empty(B, h // 2, h // 2, c, device="cuda", dtype=torch.bfloat16)
+        k_.fir_resample(xn, dn, "down", [1, 3, 3, 1])
+        _close(dn.permute(0, 3, 1, 2), o_ops.downsample_2d(x.float()), BF16, f"fir down {h} {c}")
+        k_.fir_resample(xn, dn, "down", [1, 2, 3, 4])  # asymmetric taps exercise the flip
+        _close(dn.permute(0, 3, 1, 2), o_ops.downsample_2d(x.float(), (1, 2, 3, 4)), BF16, "fir down asym")
+        k_.fir_resample(xn, up, "up", [1, 2, 3, 4])
+        _close(up.permute(0, 3, 1, 2), o_ops.upsample_2d(x.float(), (1, 2, 3, 4)), BF16, "fir up asym")
+
+
+def test_layout_softmax_temb_dense():
+    k_ = K()
+    g = torch.Generator().manual_seed(21)
+    B, H, W = 3, 12, 10
+    x = torch.rand(B, 3, H, W, generator=g)
+    y = torch.rand(B, 3, H, W, generator=g)
+    out = torch.full((B, H, W, 8), 7.0, device="cuda", dtype=torch.bfloat16)
+    k_.nchw_to_nhwc(x.cuda(), y.cuda(), out, 2.0, -1.0)
+    ref = torch.zeros(B, H, W, 8)
+    ref[..., :6] = (2 * torch.cat([x, y], 1) - 1).permute(0, 2, 3, 1)
+    _close(out, ref, BF16, "nchw->nhwc")
+    back = torch.empty(B, 3, H, W, device="cuda")
+    rs = torch.tensor([0.5, 2.0, 3.0])
+    k_.nhwc_to_nchw(out, 3, 3, back, rs.cuda())
+    _close(back, out[..., 3:6].float().cpu().permute(0, 3, 1, 2) * rs.view(B, 1, 1, 1), F32, "nhwc->nchw")
+    # softmax
+    rows, cols, pitch = 37, 100, 104
+    logits = torch.randn(rows, pitch, generator=g) * 4
+    probs = torch.empty(rows, pitch, device="cuda", dtype=torch.bfloat16)
+    k_.softmax_rows(logits.cuda(), probs, cols, 0.3)
+    ref = torch.zeros(rows, pitch)
+    ref[:, :cols] = torch.softmax(logits[:, :cols] * 0.3, -1)
+    _close(probs, ref, BF16, "softmax")
+    # time embedding (both kinds) + dense rows
+    for emb_type, nf in (("positional", 96), ("fourier", 16), ("positional", 16)):
+        embed = 2 * nf if emb_type == "fourier" else nf
+        w0 = torch.randn(4 * nf, embed, generator=g) / math.sqrt(embed)
+        b0 = torch.randn(4 * nf, generator=g) * 0.1
+        w1 = torch.randn(4 * nf, 4 * nf, generator=g) / math.sqrt(4 * nf)
+        b1 = torch.randn(4 * nf, generator=g) * 0.1
+        fw = torch.randn(nf, generator=g) * 16
+        labels = torch.tensor([999 * 0.73, 3.0, 0.0]) if emb_type == "positional" else torch.log(torch.tensor([3.7, 0.05, 50.0]))
+        if emb_type == "fourier":
+            proj = labels[:, None] * fw[None, :] * 2 * math.pi
+            emb = torch.cat([torch.sin(proj), torch.cos(proj)], -1)
+        else:
+            emb = o_net.timestep_embedding(labels, nf)
+        t = F.linear(F.silu(F.linear(emb, w0, b0)), w1, b1)
+        ref = F.silu(t)
+        out = torch.empty(3, 4 * nf, device="cuda")
+        k_.time_embedding(labels.cuda(), nf, emb_type, fw.cuda(), w0.cuda(), b0.cuda(), w1.cuda(), b1.cuda(), out)
+        # sin/cos of arguments up to ~1e3 (positional) / ~1e3 (fourier): fp32 argument rounding dominates
+        _close(out, ref, 2e-3 if emb_type == "fourier" else 1e-4, f"time embedding {emb_type} nf={nf}")
+        wd = torch.randn(500, 4 * nf, generator=g) / math.sqrt(4 * nf)
+        bd = torch.randn(500, generator=g)
+        od = torch.empty(3, 500, device="cuda")
+        k_.dense_rows(ref.cuda(), wd.cuda(), bd.cuda(), od)
+        _close(od, F.linear(ref, wd, bd), 1e-5, "dense rows")
