@@ -78,7 +78,8 @@ struct TileCfg {
   static constexpr int RY = 4;                    // output rows per thread
   static constexpr int TOW = TX * CX, TOH = TY * RY;
   static constexpr int SPAN_W = (TOW - 1) * DOWN + K, SPAN_H = (TOH - 1) * DOWN + K;
-  static constexpr int IN_TW = (((SPAN_W + UP - 1) / UP + 1) + 3) & ~3;  // 16-byte rows for TMA
+  // +3: the tile starts at a column that is a multiple of 4 (TMA needs 16-byte aligned box rows)
+  static constexpr int IN_TW = (((SPAN_W + UP - 1) / UP + 1) + 3 + 3) & ~3;
   static constexpr int IN_TH = (SPAN_H + UP - 1) / UP + 1;
   static_assert(IN_TW <= 256 && IN_TH <= 256, "TMA box dimension limit");
 };
@@ -98,7 +99,7 @@ upfirdn2d_tile_kernel(const __grid_constant__ CUtensorMap map, const UpfirdnPara
   const long long plane = bid / ((long long)p.tiles_x * p.tiles_y);
   const int ox0 = tix * C::TOW, oy0 = tiy * C::TOH;
   // first input sample whose upsampled position is >= the first tap of the tile
-  const int ix0 = floor_div(ox0 * DOWN - p.pad_x0 + UP - 1, UP);
+  const int ix0 = floor_div(floor_div(ox0 * DOWN - p.pad_x0 + UP - 1, UP), 4) * 4;
   const int iy0 = floor_div(oy0 * DOWN - p.pad_y0 + UP - 1, UP);
 
   if (USE_TMA) {
@@ -301,7 +302,6 @@ int csd_upfirdn2d_f32(const float* input, const float* kernel, float* output, in
                       int pad_y0, int pad_y1, csd_stream_t stream_) {
   using namespace csd;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CSD_REQUIRE(input && kernel && output, "upfirdn2d: null pointer");
   CSD_REQUIRE(planes >= 0 && in_h >= 1 && in_w >= 1, "upfirdn2d: bad input shape");
   CSD_REQUIRE(kh >= 1 && kw >= 1 && kh * kw <= 64, "upfirdn2d: kernel %dx%d unsupported (max 64 taps)", kh, kw);
   UpfirdnParams p;
@@ -309,7 +309,8 @@ int csd_upfirdn2d_f32(const float* input, const float* kernel, float* output, in
   int st = csd_upfirdn2d_out_size(in_h, in_w, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1,
                                   &p.out_h, &p.out_w);
   if (st != CSD_OK) return st;
-  if (planes == 0) return CSD_OK;
+  if (planes == 0) return CSD_OK;  // empty batch: nothing to launch (pointers may be null)
+  CSD_REQUIRE(input && kernel && output, "upfirdn2d: null pointer");
   p.in = input; p.kernel = kernel; p.out = output; p.planes = planes;
   p.in_h = in_h; p.in_w = in_w; p.kh = kh; p.kw = kw;
   p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y;
