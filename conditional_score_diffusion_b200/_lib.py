@@ -38,6 +38,7 @@ class ConvSegment(ctypes.Structure):
 class ConvGemmDesc(ctypes.Structure):
     _fields_ = [
         ("batch", c_int32), ("h", c_int32), ("w", c_int32),
+        ("in_h", c_int32), ("in_w", c_int32), ("stride", c_int32), ("pad", c_int32),
         ("tile_w", c_int32), ("tile_h", c_int32), ("tile_b", c_int32),
         ("nseg", c_int32),
         ("n", c_int32),

@@ -32,6 +32,7 @@ constexpr uint32_t kLayoutSw64 = 4;
 struct ConvGemmKernelParams {
   int B, H, W, TW, TH, TB;
   int tiles_w, tiles_h;
+  int stride, pad;
   int nseg;
   int seg_taps[CSD_MAX_SEGMENTS];
   int seg_chunks[CSD_MAX_SEGMENTS];
@@ -112,8 +113,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
         const int taps = p.seg_taps[s];
         for (int tap = 0; tap < taps; ++tap) {
-          const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
-          const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
+          const int dy = (taps == 9) ? (tap / 3 - p.pad) : 0;
+          const int dx = (taps == 9) ? (tap % 3 - p.pad) : 0;
           for (int c = 0; c < p.seg_chunks[s]; ++c, ++it, ++kidx) {
             const int stage = it % p.num_stages;
             const uint32_t parity = ((it / p.num_stages) & 1) ^ 1;
@@ -121,7 +122,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             const uint32_t a_dst = smem_base + stage * p.stage_bytes;
             const uint32_t b_dst = a_dst + kAStageBytes;
             ptx::mbar_arrive_expect_tx(full_bar(stage), p.a_box_bytes + p.b_box_bytes * p.nsplit);
-            ptx::tma_load_4d(a_dst, mapA, full_bar(stage), p.seg_coff[s] + c * kChunkK, w0 + dx, h0 + dy,
+            ptx::tma_load_4d(a_dst, mapA, full_bar(stage), p.seg_coff[s] + c * kChunkK, w0 * p.stride + dx, h0 * p.stride + dy,
                              b0 + z * p.a_batch_step);
             for (int j = 0; j < p.nsplit; ++j) {
               ptx::tma_load_3d(b_dst + j * p.b_box_bytes, &mapB, full_bar(stage), p.wt_k_off + kidx * kChunkK,
@@ -289,6 +290,11 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   p.tiles_h = ceil_div(d->h, d->tile_h);
   const int tiles_b = ceil_div(d->batch, d->tile_b);
   p.nseg = d->nseg;
+  p.stride = d->stride > 0 ? d->stride : 1;
+  p.pad = d->pad;
+  CSD_REQUIRE(p.stride == 1 || p.stride == 2, "stride=%d unsupported", p.stride);
+  CSD_REQUIRE(p.pad == 0 || p.pad == 1, "pad=%d unsupported", p.pad);
+  const int in_h = d->in_h > 0 ? d->in_h : d->h, in_w = d->in_w > 0 ? d->in_w : d->w;
   p.n_store = d->n_store;
   p.n_tile = d->n_tile;
   if (d->n_tile <= 256) {
@@ -319,13 +325,16 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     // 4-D map over [batch, h, w, c]; dim 0 stops at the last valid channel so the remainder of a
     // 32-channel chunk is zero-filled instead of reading the neighbouring channels.
     const uint64_t z_extra = (uint64_t)(d->z_batches - 1) * (uint64_t)d->a_batch_step;
-    uint64_t dims[4] = {(uint64_t)(sg.c_off + sg.c_cnt), (uint64_t)d->w, (uint64_t)d->h,
+    uint64_t dims[4] = {(uint64_t)(sg.c_off + sg.c_cnt), (uint64_t)in_w, (uint64_t)in_h,
                         (uint64_t)d->batch + z_extra};
-    uint64_t strides[3] = {(uint64_t)sg.pitch * 2, (uint64_t)sg.pitch * 2 * d->w,
-                           (uint64_t)sg.pitch * 2 * d->w * d->h};
-    uint32_t box[4] = {(uint32_t)kChunkK, (uint32_t)d->tile_w, (uint32_t)d->tile_h, (uint32_t)d->tile_b};
+    uint64_t strides[3] = {(uint64_t)sg.pitch * 2, (uint64_t)sg.pitch * 2 * in_w,
+                           (uint64_t)sg.pitch * 2 * in_w * in_h};
+    // with a traversal stride s the box spans (t-1)*s+1 source elements and delivers t of them
+    uint32_t box[4] = {(uint32_t)kChunkK, (uint32_t)((d->tile_w - 1) * p.stride + 1),
+                       (uint32_t)((d->tile_h - 1) * p.stride + 1), (uint32_t)d->tile_b};
+    uint32_t estr[4] = {1, (uint32_t)p.stride, (uint32_t)p.stride, 1};
     int st = encode_tensor_map(&L->mapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, sg.a, dims, strides, box,
-                               TMA_SW_64);
+                               TMA_SW_64, estr);
     if (st != CSD_OK) return st;
   }
   for (int s = d->nseg; s < CSD_MAX_SEGMENTS; ++s) L->mapA[s] = L->mapA[0];

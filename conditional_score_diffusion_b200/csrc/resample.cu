@@ -246,13 +246,21 @@ __global__ void __launch_bounds__(256) fir_nhwc_kernel(FirNhwcParams p) {
       else               { iy[0] = i;     wy[0] = p.kf[1]; iy[1] = i + 1; wy[1] = p.kf[3]; }
       if ((ox & 1) == 0) { ix[0] = j - 1; wx[0] = p.kf[0]; ix[1] = j; wx[1] = p.kf[2]; }
       else               { ix[0] = j;     wx[0] = p.kf[1]; ix[1] = j + 1; wx[1] = p.kf[3]; }
-    } else {
+    } else if (MODE == 2) {
       // out[o] = sum_k kf[k] in[2o - 1 + k]
       ny = nx = 4;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         iy[k] = 2 * oy - 1 + k; wy[k] = p.kf[k];
         ix[k] = 2 * ox - 1 + k; wx[k] = p.kf[k];
+      }
+    } else {
+      // same-rate filter with pad (2,2): out[o] = sum_k kf[k] in[o - 2 + k], o in [0, h]
+      ny = nx = 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        iy[k] = oy - 2 + k; wy[k] = p.kf[k];
+        ix[k] = ox - 2 + k; wx[k] = p.kf[k];
       }
     }
 #pragma unroll
@@ -331,16 +339,16 @@ int csd_fir_resample_nhwc_bf16(const void* src, void* out, const void* add, int 
   using namespace csd;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CSD_REQUIRE(src && out && taps4_host, "fir_resample: null pointer");
-  CSD_REQUIRE(mode == 1 || mode == 2, "fir_resample: mode %d (1 = up, 2 = down)", mode);
+  CSD_REQUIRE(mode >= 1 && mode <= 3, "fir_resample: mode %d (1 = up, 2 = down, 3 = pre-filter)", mode);
   CSD_REQUIRE(c_pitch % 8 == 0, "fir_resample: channel pitch %d not a multiple of 8", c_pitch);
-  CSD_REQUIRE(mode == 1 || (h % 2 == 0 && w % 2 == 0), "fir_resample: odd size %dx%d for downsampling", h, w);
+  CSD_REQUIRE(mode != 2 || (h % 2 == 0 && w % 2 == 0), "fir_resample: odd size %dx%d for downsampling", h, w);
   FirNhwcParams p;
   p.src = static_cast<const bf16x8*>(src);
   p.out = static_cast<bf16x8*>(out);
   p.add = static_cast<const bf16x8*>(add);
   p.batch = batch; p.h = h; p.w = w; p.cvec = c_pitch / 8;
-  p.oh = mode == 1 ? h * 2 : h / 2;
-  p.ow = mode == 1 ? w * 2 : w / 2;
+  p.oh = mode == 1 ? h * 2 : (mode == 2 ? h / 2 : h + 1);
+  p.ow = mode == 1 ? w * 2 : (mode == 2 ? w / 2 : w + 1);
   float sum = 0.f;
   for (int i = 0; i < 4; ++i) sum += taps4_host[i];
   CSD_REQUIRE(sum != 0.f, "fir_resample: taps sum to zero");
@@ -349,7 +357,8 @@ int csd_fir_resample_nhwc_bf16(const void* src, void* out, const void* add, int 
   if (total == 0) return CSD_OK;
   const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)num_sms() * 16);
   if (mode == 1) fir_nhwc_kernel<1><<<blocks, 256, 0, stream>>>(p);
-  else fir_nhwc_kernel<2><<<blocks, 256, 0, stream>>>(p);
+  else if (mode == 2) fir_nhwc_kernel<2><<<blocks, 256, 0, stream>>>(p);
+  else fir_nhwc_kernel<3><<<blocks, 256, 0, stream>>>(p);
   CSD_LAUNCH_CHECK("fir_nhwc_kernel");
   return CSD_OK;
 }

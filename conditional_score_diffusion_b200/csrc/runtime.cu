@@ -53,7 +53,7 @@ static EncodeTiledFn get_encoder() {
 
 int encode_tensor_map(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base,
                       const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                      TmaSwizzle swizzle) {
+                      TmaSwizzle swizzle, const uint32_t* elem_strides) {
   EncodeTiledFn enc = get_encoder();
   if (!enc) return set_error(CSD_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   CSD_REQUIRE(rank >= 1 && rank <= 5, "tensor map rank %d out of range", rank);
@@ -65,7 +65,7 @@ int encode_tensor_map(CUtensorMap* out, CUtensorMapDataType dtype, int rank, con
   for (int i = 0; i < rank; ++i) {
     gd[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
     CSD_REQUIRE(box[i] >= 1 && box[i] <= 256, "tensor map box[%d]=%u out of range", i, box[i]);
     CSD_REQUIRE(dims[i] >= 1, "tensor map dim[%d]=0", i);
   }

@@ -1,0 +1,616 @@
+"""Execution engine of the score network: NHWC bf16 activations, CUDA kernels only.
+
+The reference evaluates NCSNpp.forward (models/ncsnpp.py:238-388) as ~830 eager ATen ops on NCHW
+fp32 tensors. Here the same dataflow is *planned once* per (network, batch shape): weights are
+packed into the K-major bf16 layout of the tcgen05 conv/GEMM kernel, activations live in a pool of
+NHWC bf16 buffers, and the forward pass becomes a fixed launch list of libcsd_b200 kernels
+(~O(10) per block) that can be captured into one CUDA graph.
+
+torch is used for memory and streams only; every arithmetic op is a libcsd_b200 kernel and there is
+no fallback: a missing library or an unsupported configuration raises.
+"""
+import math
+import os
+
+import torch
+
+from . import kernels as K
+from ._lib import CsdError
+
+BF16 = torch.bfloat16
+SQRT1_2 = 1.0 / math.sqrt(2.0)
+
+
+class Act:
+    """NHWC bf16 activation: tensor [B, H, W, pitch] with `c` valid channels."""
+
+    __slots__ = ("t", "c")
+
+    def __init__(self, t, c):
+        self.t, self.c = t, c
+
+    @property
+    def shape(self):
+        return self.t.shape
+
+    @property
+    def pitch(self):
+        return self.t.shape[-1]
+
+
+class BufferPool:
+    """Stream-ordered reuse of activation buffers (all work is issued on one stream in plan order)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free = {}
+        self.all = []
+
+    def get(self, shape, dtype=BF16):
+        key = (tuple(shape), dtype)
+        lst = self.free.get(key)
+        if lst:
+            return lst.pop()
+        t = torch.empty(shape, device=self.device, dtype=dtype)
+        self.all.append(t)
+        return t
+
+    def put(self, t):
+        self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.all)
+
+
+def _groups(c):
+    return min(c // 4, 32)
+
+
+class PackedConv:
+    """bf16 K-major weights [n_pad, k_total] + fp32 bias [n_pad + 16] for csd_conv_gemm."""
+
+    def __init__(self, weights, bias, device):
+        # weights: list of [Cout, Cin_i, kh, kw] tensors concatenated along K (segments)
+        cout = weights[0].shape[0]
+        self.cout = cout
+        self.n_store = K.ceil_to(cout, 8)
+        n16 = K.ceil_to(cout, 16)
+        if n16 <= 256:
+            self.n_tile = n16
+        else:
+            self.n_tile = K.ceil_to((n16 + 1) // 2, 16)
+            if self.n_tile * 2 > 512:
+                self.n_tile = 256
+        n_tiles = math.ceil(self.n_store / self.n_tile)
+        self.n_pad = n_tiles * self.n_tile
+        parts = [K.pack_conv_weight(w.to(device), n_pad=self.n_pad) for w in weights]
+        self.wt = torch.cat(parts, dim=1).contiguous() if len(parts) > 1 else parts[0]
+        self.bias = torch.zeros(self.n_pad + 16, device=device, dtype=torch.float32)
+        if bias is not None:
+            self.bias[:cout] = bias.detach().to(device=device, dtype=torch.float32)
+
+
+def nin_as_conv(W):
+    """NIN weight [in, out] (models/layers.py:555-564) -> conv weight [out, in, 1, 1]."""
+    return W.detach().t().reshape(W.shape[1], W.shape[0], 1, 1)
+
+
+class Recorder:
+    """Launch list: (fn, args, kwargs) triples executed in order."""
+
+    def __init__(self):
+        self.ops = []
+
+    def add(self, fn, *args, **kwargs):
+        self.ops.append((fn, args, kwargs))
+
+    def run(self):
+        for fn, args, kwargs in self.ops:
+            fn(*args, **kwargs)
+
+    def __len__(self):
+        return len(self.ops)
+
+
+class BlockOps:
+    """Builders that append the kernels of one reference layer to a Recorder."""
+
+    def __init__(self, device, pool, rec, stats_arena):
+        self.device = device
+        self.pool = pool
+        self.rec = rec
+        self.stats = stats_arena  # fp32 [n_slots, ...] zeroed at the start of every forward
+        self.stats_used = 0
+
+    # -- helpers -----------------------------------------------------------------------------
+    def _stats_slot(self, batch, groups):
+        n = batch * groups * 2
+        if self.stats_used + n > self.stats.numel():
+            raise CsdError("GroupNorm statistics arena too small")
+        s = self.stats[self.stats_used:self.stats_used + n].view(batch, groups, 2)
+        self.stats_used += n
+        return s
+
+    def group_norm(self, srcs, gamma, beta, silu):
+        """srcs: list of 1 or 2 Act (channel concatenation). Returns a new Act."""
+        b, h, w, _ = srcs[0].shape
+        c = sum(a.c for a in srcs)
+        groups = _groups(c)
+        sums = self._stats_slot(b, groups)
+        s0 = srcs[0]
+        s1 = srcs[1] if len(srcs) > 1 else None
+        out = self.pool.get((b, h, w, c))
+        self.rec.add(K.gn_stats, s0.t, s0.c, s1.t if s1 else None, s1.c if s1 else 0, sums, groups)
+        self.rec.add(K.gn_apply, s0.t, s0.c, s1.t if s1 else None, s1.c if s1 else 0, sums, gamma, beta, out,
+                     groups, 1e-6, silu)
+        return Act(out, c)
+
+    def conv(self, segs, pc, out_hw=None, temb=None, temb_pitch=0, res=None, scale=1.0, stride=1, pad=1,
+             out=None):
+        """segs: list of (Act, taps). pc: PackedConv. Returns Act [B, oh, ow, n_store]."""
+        a0 = segs[0][0]
+        b, ih, iw, _ = a0.shape
+        oh, ow = out_hw if out_hw is not None else (ih, iw)
+        if out is None:
+            out = self.pool.get((b, oh, ow, pc.n_store))
+        seg_list = [(a.t, a.pitch, 0, a.c, taps) for a, taps in segs]
+        self.rec.add(K.conv_gemm, seg_list, pc.wt, pc.cout, out, batch=b, h=oh, w=ow, n_store=pc.n_store,
+                     n_tile=pc.n_tile, bias=pc.bias, temb=temb, temb_pitch=temb_pitch,
+                     res=res.t if res is not None else None, res_pitch=res.pitch if res is not None else 0,
+                     scale=scale, stride=stride, pad=pad, in_h=ih, in_w=iw)
+        return Act(out, pc.cout)
+
+    def fir(self, a, mode, taps, add=None):
+        b, h, w, p = a.shape
+        oh, ow = {"up": (h * 2, w * 2), "down": (h // 2, w // 2), "prefilter": (h + 1, w + 1)}[mode]
+        out = self.pool.get((b, oh, ow, p))
+        self.rec.add(K.fir_resample, a.t, out, mode, list(taps), add.t if add is not None else None)
+        return Act(out, a.c)
+
+    def release(self, *acts):
+        for a in acts:
+            if a is not None:
+                self.pool.put(a.t)
+
+    # -- reference layers ----------------------------------------------------------------------
+    def resblock(self, pk, srcs, tproj, tproj_pitch, fir_taps, skip_rescale):
+        """ResnetBlockBigGANpp / ResnetBlockDDPMpp forward (models/layerspp.py:195-209,242-274).
+
+        pk: dict with gn0/gn1 (gamma, beta), conv0, conv1 (PackedConv; conv1 already carries the
+        skip 1x1 weights as extra K segments when the block has Conv_2 / NIN_0), flags.
+        srcs: 1 or 2 Acts (the up path passes [h, skip] instead of materialising torch.cat).
+        """
+        a0 = self.group_norm(srcs, pk["gn0_w"], pk["gn0_b"], True)
+        raw = list(srcs)
+        own_raw = False
+        if pk["up"] or pk["down"]:
+            mode = "up" if pk["up"] else "down"
+            assert len(srcs) == 1
+            a0r = self.fir(a0, mode, fir_taps)
+            self.release(a0)
+            a0 = a0r
+            raw = [self.fir(srcs[0], mode, fir_taps)]
+            own_raw = True
+        temb = tproj[:, pk["temb_off"]:] if tproj is not None else None
+        h1 = self.conv([(a0, 9)], pk["conv0"], temb=temb, temb_pitch=tproj_pitch)
+        self.release(a0)
+        a1 = self.group_norm([h1], pk["gn1_w"], pk["gn1_b"], True)
+        self.release(h1)
+        scale = SQRT1_2 if skip_rescale else 1.0
+        if pk["has_skip_conv"]:
+            segs = [(a1, 9)] + [(r, 1) for r in raw]
+            out = self.conv(segs, pk["conv1"], scale=scale)
+        else:
+            assert len(raw) == 1
+            out = self.conv([(a1, 9)], pk["conv1"], res=raw[0], scale=scale)
+        self.release(a1)
+        if own_raw:
+            self.release(*raw)
+        return out
+
+    def attention(self, pk, x, skip_rescale):
+        """AttnBlockpp forward (models/layerspp.py:75-91) as GroupNorm + 5 GEMMs + softmax."""
+        b, h, w, _ = x.shape
+        c = x.c
+        L = h * w
+        lp = K.ceil_to(L, 8)
+        hn = self.group_norm([x], pk["gn_w"], pk["gn_b"], False)
+        hn_flat = Act(hn.t.view(b, 1, L, hn.pitch), c)
+        # q | k in one GEMM: [B, L, 2C]
+        qk = self.pool.get((b, 1, L, 2 * c))
+        self.rec.add(K.conv_gemm, [(hn_flat.t, hn.pitch, 0, c, 1)], pk["qk"].wt, 2 * c, qk, batch=b, h=1, w=L,
+                     n_store=2 * c, n_tile=pk["qk"].n_tile, bias=pk["qk"].bias)
+        # V^T[b] = Wv^T h[b]^T : A = weight image [C rows, C], B = hn[b] (batched over z)
+        vt = self.pool.get((b, c, lp))
+        nt_l = K.ceil_to(L, 16) if L <= 256 else K.ceil_to(math.ceil(L / math.ceil(L / 256)), 16)
+        self.rec.add(K.conv_gemm, [(pk["wv_img"], c, 0, c, 1)], hn.t, L, vt, batch=1, h=1, w=c, out_pitch=lp,
+                     n_store=L, n_tile=nt_l, z_batches=b, a_batch_step=0, wt_batch_stride=L * hn.pitch,
+                     wt_pitch=hn.pitch, k_valid=c, wt_rows=L, out_z_stride=c * lp, bias=pk["bv"],
+                     bias_per_row=True)
+        # logits S[b] = Q[b] K[b]^T (fp32)
+        s = self.pool.get((b, L, lp), torch.float32)
+        self.rec.add(K.conv_gemm, [(qk, 2 * c, 0, c, 1)], qk, L, s, batch=1, h=1, w=L, out_pitch=lp, n_store=L,
+                     n_tile=nt_l, z_batches=b, a_batch_step=1, wt_batch_stride=L * 2 * c, wt_pitch=2 * c,
+                     wt_k_off=c, k_valid=c, wt_rows=L, out_z_stride=L * lp)
+        p = self.pool.get((b, L, lp))
+        self.rec.add(K.softmax_rows, s, p, L, float(int(c) ** (-0.5)))
+        # O[b] = P[b] V[b] : A = P (K = L), B = V^T
+        o = self.pool.get((b, 1, L, c))
+        pc_o_ntile = pk["proj"].n_tile
+        self.rec.add(K.conv_gemm, [(p, lp, 0, L, 1)], vt, c, o, batch=1, h=1, w=L, out_pitch=c, n_store=c,
+                     n_tile=pc_o_ntile, z_batches=b, a_batch_step=1, wt_batch_stride=c * lp, wt_pitch=lp,
+                     k_valid=L, wt_rows=c, out_z_stride=L * c)
+        out = self.pool.get((b, h, w, K.ceil_to(c, 8)))
+        self.rec.add(K.conv_gemm, [(o, c, 0, c, 1)], pk["proj"].wt, c, out.view(b, 1, L, out.shape[-1]), batch=b,
+                     h=1, w=L, n_store=pk["proj"].n_store, n_tile=pk["proj"].n_tile, bias=pk["proj"].bias,
+                     res=x.t.view(b, 1, L, x.pitch), res_pitch=x.pitch, scale=SQRT1_2 if skip_rescale else 1.0)
+        for t in (hn.t, qk, vt, s, p, o):
+            self.pool.put(t)
+        return Act(out, c)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole-network plan
+# ------------------------------------------------------------------------------------------------
+def _gn_params(gn, device):
+    return (gn.weight.detach().to(device=device, dtype=torch.float32).contiguous(),
+            gn.bias.detach().to(device=device, dtype=torch.float32).contiguous())
+
+
+class NetEngine:
+    """Packs an NCSNpp module's parameters and plans/executes its forward pass on one device."""
+
+    def __init__(self, net):
+        self.net = net
+        self.device = None
+        self.packed = None
+        self.param_version = None
+        self.plans = {}
+
+    # -- weights ---------------------------------------------------------------------------------
+    def _version(self):
+        return tuple((id(p), p._version, p.device) for p in self.net.parameters())
+
+    def ensure_packed(self, device):
+        v = self._version()
+        if self.packed is not None and self.param_version == v and self.device == device:
+            return
+        if device.type != "cuda":
+            raise CsdError("the score network runs on CUDA only (libcsd_b200 has no CPU path)")
+        self.device = device
+        self.packed = self._pack(device)
+        self.param_version = v
+        self.plans = {}
+
+    def _pack_resblock(self, m, device, dense_w, dense_b):
+        from .models import layerspp
+        pk = {"up": getattr(m, "up", False), "down": getattr(m, "down", False)}
+        pk["gn0_w"], pk["gn0_b"] = _gn_params(m.GroupNorm_0, device)
+        pk["gn1_w"], pk["gn1_b"] = _gn_params(m.GroupNorm_1, device)
+        pk["conv0"] = PackedConv([m.Conv_0.weight.detach()], m.Conv_0.bias, device)
+        if hasattr(m, "Dense_0"):
+            pk["temb_off"] = sum(w.shape[0] for w in dense_w)
+            dense_w.append(m.Dense_0.weight.detach().to(device=device, dtype=torch.float32))
+            dense_b.append(m.Dense_0.bias.detach().to(device=device, dtype=torch.float32))
+        else:
+            pk["temb_off"] = None
+        skip_w, skip_b = None, None
+        if isinstance(m, layerspp.ResnetBlockBigGANpp):
+            if hasattr(m, "Conv_2"):
+                skip_w, skip_b = m.Conv_2.weight.detach(), m.Conv_2.bias.detach()
+        else:
+            if hasattr(m, "NIN_0"):
+                skip_w, skip_b = nin_as_conv(m.NIN_0.W), m.NIN_0.b.detach()
+            elif hasattr(m, "Conv_2"):
+                raise CsdError("conv_shortcut=True ResnetBlockDDPMpp is not supported by the engine")
+        pk["has_skip_conv"] = skip_w is not None
+        pk["conv1_w"] = m.Conv_1.weight.detach()
+        pk["conv1_b"] = m.Conv_1.bias.detach()
+        pk["skip_w"], pk["skip_b"] = skip_w, skip_b
+        pk["in_ch"], pk["out_ch"] = m.Conv_0.weight.shape[1], m.Conv_0.weight.shape[0]
+        return pk
+
+    @staticmethod
+    def finish_resblock(pk, split, device):
+        """Build conv1 (+ skip segments). `split`: channel counts of the raw input sources."""
+        key = ("conv1", tuple(split))
+        if key in pk:
+            return pk[key]
+        if pk["has_skip_conv"]:
+            ws = [pk["conv1_w"]]
+            off = 0
+            for c in split:
+                ws.append(pk["skip_w"][:, off:off + c])
+                off += c
+            assert off == pk["skip_w"].shape[1], (off, pk["skip_w"].shape)
+            pc = PackedConv(ws, pk["conv1_b"] + pk["skip_b"], device)
+        else:
+            pc = PackedConv([pk["conv1_w"]], pk["conv1_b"], device)
+        pk[key] = pc
+        return pc
+
+    def _pack_attn(self, m, device):
+        c = m.NIN_0.W.shape[0]
+        pk = {}
+        pk["gn_w"], pk["gn_b"] = _gn_params(m.GroupNorm_0, device)
+        wqk = torch.cat([nin_as_conv(m.NIN_0.W), nin_as_conv(m.NIN_1.W)], dim=0)
+        pk["qk"] = PackedConv([wqk], torch.cat([m.NIN_0.b.detach(), m.NIN_1.b.detach()]), device)
+        # A-operand "image" of the V^T GEMM: rows = output channel, K = input channel
+        pk["wv_img"] = m.NIN_2.W.detach().t().to(device=device, dtype=BF16).contiguous().view(1, 1, c, c)
+        pk["bv"] = torch.zeros(c + 16, device=device, dtype=torch.float32)
+        pk["bv"][:c] = m.NIN_2.b.detach().to(device)
+        pk["proj"] = PackedConv([nin_as_conv(m.NIN_3.W)], m.NIN_3.b.detach(), device)
+        return pk
+
+    def _pack(self, device):
+        from .models import layerspp, up_or_down_sampling
+        net = self.net
+        mods = net.all_modules
+        packed = [None] * len(mods)
+        dense_w, dense_b = [], []
+        for i, m in enumerate(mods):
+            if isinstance(m, (layerspp.ResnetBlockBigGANpp, layerspp.ResnetBlockDDPMpp)):
+                packed[i] = self._pack_resblock(m, device, dense_w, dense_b)
+            elif isinstance(m, layerspp.AttnBlockpp):
+                packed[i] = self._pack_attn(m, device)
+            elif isinstance(m, torch.nn.Conv2d):
+                packed[i] = PackedConv([m.weight.detach()], m.bias, device)
+            elif isinstance(m, layerspp.Combine):
+                packed[i] = PackedConv([m.Conv_0.weight.detach()], m.Conv_0.bias, device)
+            elif isinstance(m, torch.nn.GroupNorm):
+                packed[i] = _gn_params(m, device)
+            elif isinstance(m, (layerspp.Downsample, layerspp.Upsample)):
+                if hasattr(m, "Conv2d_0"):
+                    packed[i] = PackedConv([m.Conv2d_0.weight.detach()], m.Conv2d_0.bias, device)
+                elif hasattr(m, "Conv_0"):
+                    packed[i] = PackedConv([m.Conv_0.weight.detach()], m.Conv_0.bias, device)
+            elif isinstance(m, torch.nn.Linear):
+                packed[i] = (m.weight.detach().to(device=device, dtype=torch.float32).contiguous(),
+                             m.bias.detach().to(device=device, dtype=torch.float32).contiguous())
+            elif isinstance(m, layerspp.GaussianFourierProjection):
+                packed[i] = m.W.detach().to(device=device, dtype=torch.float32).contiguous()
+        out = {"mods": packed}
+        if dense_w:
+            total = sum(w.shape[0] for w in dense_w)
+            pad = 512  # epilogue reads a full n_tile of projection columns past the block's offset
+            wcat = torch.zeros(total + pad, dense_w[0].shape[1], device=device, dtype=torch.float32)
+            bcat = torch.zeros(total + pad, device=device, dtype=torch.float32)
+            wcat[:total] = torch.cat(dense_w, 0)
+            bcat[:total] = torch.cat(dense_b, 0)
+            out["dense_w"], out["dense_b"], out["dense_total"] = wcat, bcat, total + pad
+        return out
+
+    # -- plan ------------------------------------------------------------------------------------
+    def plan(self, batch, h, w, c0, c1):
+        key = (batch, h, w, c0, c1)
+        if key not in self.plans:
+            self.plans[key] = NetPlan(self, batch, h, w, c0, c1)
+        return self.plans[key]
+
+
+class NetPlan:
+    """Launch list of NCSNpp.forward for one batch shape (models/ncsnpp.py:238-388)."""
+
+    def __init__(self, eng, batch, h, w, c0, c1):
+        from .models import layerspp
+        net, dev, P = eng.net, eng.device, eng.packed
+        self.eng = eng
+        self.batch, self.h, self.w = batch, h, w
+        self.rec = Recorder()
+        self.pool = BufferPool(dev)
+        self.stats = torch.zeros(4 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+        ops = BlockOps(dev, self.pool, self.rec, self.stats)
+        rec = self.rec
+        mods, pk = net.all_modules, P["mods"]
+        nf = net.nf
+        fir_taps = tuple(net.fir_kernel)
+        if len(fir_taps) != 4:
+            raise CsdError("the engine supports 4-tap FIR kernels only (config.model.fir_kernel)")
+        if not net.fir:
+            raise CsdError("fir=False (naive resampling) is not supported by the engine yet")
+        skip_rescale = net.skip_rescale
+        channels = c0 + c1
+
+        # static inputs / outputs
+        self.in0 = torch.empty(batch, c0, h, w, device=dev, dtype=torch.float32)
+        self.in1 = torch.empty(batch, c1, h, w, device=dev, dtype=torch.float32) if c1 else None
+        self.labels = torch.empty(batch, device=dev, dtype=torch.float32)
+        self._outs = {}
+        self.row_scale = torch.ones(batch, device=dev, dtype=torch.float32)
+        self.row_scale1 = torch.ones(batch, device=dev, dtype=torch.float32)
+
+        rec.add(self.stats.zero_)
+        m_idx = 0
+        # ---- time embedding ----
+        fourier_w = None
+        if net.embedding_type == "fourier":
+            fourier_w = pk[m_idx]
+            m_idx += 1
+        tproj = None
+        tpitch = 0
+        if net.conditional:
+            (w0, b0), (w1, b1) = pk[m_idx], pk[m_idx + 1]
+            m_idx += 2
+            act_temb = torch.empty(batch, 4 * nf, device=dev, dtype=torch.float32)
+            rec.add(K.time_embedding, self.labels, nf, net.embedding_type, fourier_w, w0, b0, w1, b1, act_temb)
+            if "dense_w" in P:
+                tpitch = P["dense_total"]
+                tproj = torch.empty(batch, tpitch, device=dev, dtype=torch.float32)
+                rec.add(K.dense_rows, act_temb, P["dense_w"], P["dense_b"], tproj)
+        # ---- input ----
+        cpad = K.ceil_to(channels, 8)
+        xin = Act(torch.empty(batch, h, w, cpad, device=dev, dtype=BF16), channels)
+        if net.centered:
+            rec.add(K.nchw_to_nhwc, self.in0, self.in1, xin.t, 1.0, 0.0)
+        else:
+            rec.add(K.nchw_to_nhwc, self.in0, self.in1, xin.t, 2.0, -1.0)  # x = 2x - 1 (ncsnpp.py:264-266)
+        input_pyramid = xin if net.progressive_input != "none" else None
+
+        def resblock(idx, srcs):
+            p = pk[idx]
+            pc1 = eng.finish_resblock(p, [a.c for a in srcs], dev)
+            p = dict(p)
+            p["conv1"] = pc1
+            return ops.resblock(p, srcs, tproj if p["temb_off"] is not None else None, tpitch, fir_taps, skip_rescale)
+
+        hs = [ops.conv([(xin, 9)], pk[m_idx])]
+        m_idx += 1
+        refcount = {}
+
+        def hold(a):
+            refcount[id(a.t)] = refcount.get(id(a.t), 0) + 1
+            return a
+
+        def drop(a):
+            n = refcount.get(id(a.t), 0) - 1
+            refcount[id(a.t)] = n
+            if n <= 0:
+                ops.release(a)
+
+        hold(hs[0])
+        num_res = net.num_resolutions
+        for lvl in range(num_res):
+            for _ in range(net.num_res_blocks):
+                hcur = resblock(m_idx, [hs[-1]])
+                m_idx += 1
+                if hcur.shape[2] in net.attn_resolutions:
+                    h2 = ops.attention(pk[m_idx], hcur, skip_rescale)
+                    ops.release(hcur)
+                    hcur = h2
+                    m_idx += 1
+                hs.append(hold(hcur))
+            if lvl != num_res - 1:
+                if net.resblock_type == "ddpm":
+                    hcur = self._ddpm_downsample(ops, mods[m_idx], pk[m_idx], hs[-1], fir_taps)
+                else:
+                    hcur = resblock(m_idx, [hs[-1]])
+                m_idx += 1
+                if net.progressive_input == "input_skip":
+                    ip = ops.fir(input_pyramid, "down", fir_taps)
+                    if input_pyramid is not xin:
+                        ops.release(input_pyramid)
+                    input_pyramid = ip
+                    if net.combine_method != "sum":
+                        raise CsdError("progressive_combine='cat' is not supported by the engine yet")
+                    # Combine: conv1x1(pyramid) + h (layerspp.py:52-59)
+                    h2 = ops.conv([(input_pyramid, 1)], pk[m_idx], res=hcur, scale=1.0)
+                    ops.release(hcur)
+                    hcur = h2
+                    m_idx += 1
+                elif net.progressive_input == "residual":
+                    ip = self._fir_conv_down(ops, pk[m_idx], input_pyramid, fir_taps, res=hcur,
+                                             scale=SQRT1_2 if skip_rescale else 1.0)
+                    if input_pyramid is not xin:
+                        drop(input_pyramid)
+                    ops.release(hcur)
+                    input_pyramid = hold(ip)   # also pushed on hs below
+                    hcur = ip
+                    m_idx += 1
+                hs.append(hold(hcur))
+
+        hcur = hs[-1]
+        hold(hcur)
+        h2 = resblock(m_idx, [hcur]); m_idx += 1
+        drop(hcur)
+        h3 = ops.attention(pk[m_idx], h2, skip_rescale); m_idx += 1
+        ops.release(h2)
+        hcur = resblock(m_idx, [h3]); m_idx += 1
+        ops.release(h3)
+
+        pyramid = None
+        for lvl in reversed(range(num_res)):
+            for _ in range(net.num_res_blocks + 1):
+                skip = hs.pop()
+                h2 = resblock(m_idx, [hcur, skip])
+                m_idx += 1
+                ops.release(hcur)
+                drop(skip)
+                hcur = h2
+            if hcur.shape[2] in net.attn_resolutions:
+                h2 = ops.attention(pk[m_idx], hcur, skip_rescale)
+                ops.release(hcur)
+                hcur = h2
+                m_idx += 1
+            if net.progressive != "none":
+                if net.progressive == "residual":
+                    raise CsdError("progressive='residual' relies on upsample_conv_2d, which is dead code in the "
+                                   "reference (up_or_down_sampling.py:123 indexes with a negative step); unsupported")
+                gamma, beta = pk[m_idx]
+                a = ops.group_norm([hcur], gamma, beta, True)
+                m_idx += 1
+                if lvl == num_res - 1:
+                    pyramid = ops.conv([(a, 9)], pk[m_idx])
+                else:
+                    pu = ops.fir(pyramid, "up", fir_taps)
+                    ops.release(pyramid)
+                    pyramid = ops.conv([(a, 9)], pk[m_idx], res=pu, scale=1.0)
+                    ops.release(pu)
+                ops.release(a)
+                m_idx += 1
+            if lvl != 0:
+                if net.resblock_type == "ddpm":
+                    raise CsdError("resblock_type='ddpm' upsampling is not supported by the engine yet")
+                h2 = resblock(m_idx, [hcur])
+                ops.release(hcur)
+                hcur = h2
+                m_idx += 1
+        assert not hs
+        if net.progressive == "output_skip":
+            final = pyramid
+        else:
+            gamma, beta = pk[m_idx]
+            a = ops.group_norm([hcur], gamma, beta, True)
+            m_idx += 1
+            final = ops.conv([(a, 9)], pk[m_idx])
+            m_idx += 1
+        assert m_idx == len(mods), (m_idx, len(mods))
+        # ---- output: NHWC bf16 -> NCHW fp32, optional per-sample 1/sigma ----
+        rec.add(K.nhwc_to_nchw, final.t, 0, c0, self._out_view(0, c0), self.row_scale)
+        if c1:
+            rec.add(K.nhwc_to_nchw, final.t, c0, c1, self._out_view(c0, c1), self.row_scale1)
+        self.graph = None
+        self.warm = 0
+        self.use_graph = os.environ.get("CSD_NO_GRAPH", "0") != "1"
+
+    def _out_view(self, off, cnt):
+        # separate contiguous tensors per output group (the paired model returns a dict of two)
+        t = torch.empty(self.batch, cnt, self.h, self.w, device=self.eng.device, dtype=torch.float32)
+        self._outs[off] = t
+        return t
+
+    def _fir_conv_down(self, ops, pc, a, fir_taps, res=None, scale=1.0):
+        """layerspp.Downsample(with_conv=True, fir=True) = conv_downsample_2d + bias
+        (up_or_down_sampling.py:144-178): FIR with pad (2,2), then 3x3 stride-2 VALID conv."""
+        b, h, w, _ = a.shape
+        f = ops.fir(a, "prefilter", fir_taps)
+        out = ops.conv([(f, 9)], pc, out_hw=(h // 2, w // 2), res=res, scale=scale, stride=2, pad=0)
+        ops.release(f)
+        return out
+
+    def _ddpm_downsample(self, ops, m, pc, a, fir_taps):
+        raise CsdError("resblock_type='ddpm' is not supported by the engine yet")
+
+    # -- execution ---------------------------------------------------------------------------------
+    def run(self):
+        self.rec.run()
+
+    def launch(self):
+        """Run the launch list: eagerly the first time (and inside someone else's capture), as a
+        replayed CUDA graph afterwards."""
+        if not self.use_graph or torch.cuda.is_current_stream_capturing():
+            self.rec.run()
+            return
+        if self.graph is None:
+            if self.warm < 1:
+                self.rec.run()
+                self.warm += 1
+                return
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.rec.run()
+            self.graph = g
+        self.graph.replay()
+
+    def outputs(self):
+        return [self._outs[k] for k in sorted(self._outs)]

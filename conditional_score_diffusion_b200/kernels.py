@@ -79,11 +79,13 @@ def pick_tile(h, w, batch):
 def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None, n_tile=None,
               tile=None, bias=None, bias_per_row=False, temb=None, temb_pitch=0, res=None,
               res_pitch=0, scale=1.0, out_f32=None, z_batches=1, a_batch_step=0, wt_batch_stride=0,
-              out_z_stride=0, res_z_stride=0, wt_pitch=0, wt_k_off=0, k_valid=0, wt_rows=None):
+              out_z_stride=0, res_z_stride=0, wt_pitch=0, wt_k_off=0, k_valid=0, wt_rows=None,
+              stride=1, pad=1, in_h=0, in_w=0):
     """Launch csd_conv_gemm. segments: list of (tensor, pitch, c_off, c_cnt, taps)."""
     _require_cuda(wt, out, bias, temb, res, *[s[0] for s in segments])
     d = ConvGemmDesc()
     d.batch, d.h, d.w = batch, h, w
+    d.in_h, d.in_w, d.stride, d.pad = in_h, in_w, stride, pad
     tw, th, tb = tile if tile is not None else pick_tile(h, w, batch)
     d.tile_w, d.tile_h, d.tile_b = tw, th, tb
     d.nseg = len(segments)
@@ -245,11 +247,11 @@ def gn_apply(src0, c0, src1, c1, sums, gamma, beta, out, groups, eps=1e-6, silu=
 
 
 def fir_resample(src, out, mode, taps, add=None):
-    """mode 'up' | 'down'; src/out NHWC bf16."""
+    """mode 'up' | 'down' | 'prefilter'; src/out NHWC bf16."""
     b, h, w, pitch = src.shape
     arr = (ctypes.c_float * 4)(*[float(t) for t in taps])
     check(_lib.lib().csd_fir_resample_nhwc_bf16(_ptr(src), _ptr(out), _ptr(add), b, h, w, pitch,
-                                                1 if mode == "up" else 2, arr, _stream()))
+                                                {"up": 1, "down": 2, "prefilter": 3}[mode], arr, _stream()))
     return out
 
 

@@ -127,7 +127,8 @@ int csd_gn_apply_bf16(const void* src0, int c0, int pitch0, const void* src1, in
 
 /* Depthwise separable FIR resampling of an NHWC bf16 tensor with the [1,3,3,1] family
  * (up_or_down_sampling.upsample_2d / downsample_2d, models/up_or_down_sampling.py:195-257):
- * mode 1 = up x2 (pad (2,1), gain 4), mode 2 = down x2 (pad (1,1)). taps: 4 fp32 host values
+ * mode 1 = up x2 (pad (2,1), gain 4), mode 2 = down x2 (pad (1,1)), mode 3 = same-rate pre-filter with
+ * pad (2,2) (output (h+1) x (w+1); first half of conv_downsample_2d, :144-178). taps: 4 fp32 host values
  * (the un-normalised 1-D filter). If add != NULL, out = fir(src) + add (output-skip pyramid,
  * models/ncsnpp.py:344-349).                                                                    */
 int csd_fir_resample_nhwc_bf16(const void* src, void* out, const void* add, int batch, int h, int w,
@@ -169,7 +170,11 @@ typedef struct csd_conv_segment {
 } csd_conv_segment;
 
 typedef struct csd_conv_gemm_desc {
-  int32_t batch, h, w;          /* spatial extent of A (and of the output)               */
+  int32_t batch, h, w;          /* spatial extent of the OUTPUT (tiles cover output pixels) */
+  int32_t in_h, in_w;           /* spatial extent of A (0 = same as h, w)                  */
+  int32_t stride;               /* conv stride (1 or 2); taps read in[o*stride + k - pad]  */
+  int32_t pad;                  /* 1 = 'same' 3x3 (torch padding=1), 0 = valid / padded-after
+                                   (DDPM Downsample pads bottom/right: TMA zero-fills it)   */
   int32_t tile_w, tile_h, tile_b; /* pixel box per CTA, product <= 128                    */
   int32_t nseg;
   int32_t n;                    /* output columns computed (rows of Wt used)             */

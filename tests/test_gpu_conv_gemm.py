@@ -203,3 +203,38 @@ def test_conv3x3_full_resolution_timing():
     ms = e0.elapsed_time(e1) / 10
     flops = 2.0 * B * H * W * C * C * 9
     print(f"[conv_gemm] 3x3 96->96 160x160 B=64: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s")
+
+
+def test_conv3x3_stride2_valid():
+    """3x3 stride-2 VALID conv over an odd-sized (pre-filtered) input: second half of
+    conv_downsample_2d (models/up_or_down_sampling.py:144-178)."""
+    k = _kern()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(13)
+    for (B, H, cin, cout) in [(3, 17, 8, 32), (2, 33, 96, 192), (5, 11, 64, 64)]:
+        x = torch.randn(B, cin, H, H, device=dev, generator=g).to(torch.bfloat16)
+        wgt = (torch.randn(cout, cin, 3, 3, device=dev, generator=g) / math.sqrt(9 * cin)).to(torch.bfloat16)
+        ref = F.conv2d(x.float(), wgt.float(), stride=2, padding=0)
+        oh = ref.shape[-1]
+        out = torch.empty(B, oh, oh, cout, device=dev, dtype=torch.bfloat16)
+        k.conv_gemm([(_nhwc(x), cin, 0, cin, 9)], k.pack_conv_weight(wgt), cout, out, batch=B, h=oh, w=oh,
+                    stride=2, pad=0, in_h=H, in_w=H)
+        torch.cuda.synchronize()
+        assert _report(f"3x3 s2 valid {cin}->{cout} {H}->{oh}", out.permute(0, 3, 1, 2), ref, BF16_RTOL) < BF16_RTOL
+
+
+def test_conv3x3_stride2_ddpm_downsample():
+    """F.pad(x, (0,1,0,1)) + 3x3 stride-2 conv (models/layers.py:607-629): the bottom/right padding is
+    TMA's out-of-bounds zero fill."""
+    k = _kern()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(14)
+    B, H, cin, cout = 2, 16, 64, 64
+    x = torch.randn(B, cin, H, H, device=dev, generator=g).to(torch.bfloat16)
+    wgt = (torch.randn(cout, cin, 3, 3, device=dev, generator=g) / math.sqrt(9 * cin)).to(torch.bfloat16)
+    ref = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), wgt.float(), stride=2, padding=0)
+    out = torch.empty(B, H // 2, H // 2, cout, device=dev, dtype=torch.bfloat16)
+    k.conv_gemm([(_nhwc(x), cin, 0, cin, 9)], k.pack_conv_weight(wgt), cout, out, batch=B, h=H // 2, w=H // 2,
+                stride=2, pad=0, in_h=H, in_w=H)
+    torch.cuda.synchronize()
+    assert _report("ddpm downsample conv", out.permute(0, 3, 1, 2), ref, BF16_RTOL) < BF16_RTOL
