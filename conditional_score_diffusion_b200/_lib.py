@@ -82,13 +82,15 @@ _PROTOTYPES = {
     "csd_upfirdn2d_out_size": (c_int, [c_int] * 12 + [c_int_p, c_int_p]),
     "csd_fused_bias_act_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int,
                                        c_int, c_float, c_float, c_void_p]),
-    "csd_ve_perturb_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "csd_ve_perturb_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
+    "csd_broadcast_table_f32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "csd_langevin_norms_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
-    "csd_langevin_update_f32": (c_int, [c_void_p] * 6 + [c_int, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
-    "csd_reverse_diffusion_update_f32": (c_int, [c_void_p] * 5 + [c_int64, c_void_p, c_void_p, c_int, c_void_p,
-                                                 c_void_p]),
-    "csd_euler_maruyama_update_f32": (c_int, [c_void_p] * 5 + [c_int64, c_void_p, c_void_p, c_float, c_int,
-                                              c_void_p, c_void_p]),
+    "csd_langevin_update_f32": (c_int, [c_void_p] * 6 + [c_int, c_int64, c_float, c_void_p, c_void_p, c_int,
+                                        c_void_p]),
+    "csd_reverse_diffusion_update_f32": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_void_p, c_void_p, c_int,
+                                                 c_void_p, c_int, c_void_p]),
+    "csd_euler_maruyama_update_f32": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_void_p, c_void_p, c_float, c_int,
+                                              c_void_p, c_int, c_void_p]),
     "csd_step_advance": (c_int, [c_void_p, c_void_p]),
     "csd_nchw_to_nhwc_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                       c_float, c_float, c_void_p]),

@@ -10,6 +10,9 @@
 #include "common.cuh"
 #include "../../include/csd_b200.h"
 
+#include <algorithm>
+#include <initializer_list>
+
 namespace csd {
 
 static inline int ew_blocks(long long n_vec) {
@@ -40,16 +43,53 @@ fused_bias_act_kernel(const float* __restrict__ x, const float* __restrict__ bia
 }
 
 // ---- PC updates ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-ve_perturb_kernel(const float4* __restrict__ y, const float4* __restrict__ z, float4* __restrict__ out, long long n4,
-                  const float* __restrict__ ys, const float* __restrict__ zs, float* __restrict__ os, int tail,
-                  const float* __restrict__ sigma_tab, const int* __restrict__ step_idx) {
-  const float sigma = sigma_tab[*step_idx];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 a = y[i], b = z[i];
-    out[i] = make_float4(fmaf(b.x, sigma, a.x), fmaf(b.y, sigma, a.y), fmaf(b.z, sigma, a.z), fmaf(b.w, sigma, a.w));
+// Per-step / per-sample scalar lookup. Tables are [n_steps] (sample_stride = 0: one value per step,
+// shared by the batch) or [n_steps, batch] (sample_stride = 1). step_idx may be null (step 0), which
+// lets the class-based predictors / correctors pass plain per-sample [batch] arrays.
+struct CoefRef {
+  const float* tab;
+  const int* step_idx;
+  int sample_stride;
+  int batch;
+  __device__ __forceinline__ float at(int b, float dflt) const {
+    if (tab == nullptr) return dflt;
+    const int s = step_idx != nullptr ? *step_idx : 0;
+    return tab[(long long)s * (sample_stride ? batch : 1) + (long long)b * sample_stride];
   }
-  if (blockIdx.x == 0 && threadIdx.x < tail) os[threadIdx.x] = fmaf(zs[threadIdx.x], sigma, ys[threadIdx.x]);
+};
+
+// All update kernels use grid = (blocks per sample, batch): the sample index is blockIdx.y, so the
+// per-sample coefficients are CTA constants and the inner loop is pure 16-byte streaming.
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<1> { using type = float; };
+
+template <int VEC, typename F>
+__device__ __forceinline__ void map3(const float* a, const float* b, const float* c, float* o0, float* o1,
+                                     long long per_sample, F f) {
+  // o0[i], o1[i] = f(a[i], b[i], c[i]); any of b, c, o1 may be null
+  const long long base = (long long)blockIdx.y * per_sample;
+  const long long nvec = per_sample / VEC;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float va[VEC], vb[VEC], vc[VEC], r0[VEC], r1[VEC];
+    using V = typename VecT<VEC>::type;
+    *reinterpret_cast<V*>(va) = *reinterpret_cast<const V*>(a + base + i * VEC);
+    if (b != nullptr) *reinterpret_cast<V*>(vb) = *reinterpret_cast<const V*>(b + base + i * VEC);
+    if (c != nullptr) *reinterpret_cast<V*>(vc) = *reinterpret_cast<const V*>(c + base + i * VEC);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) f(va[k], b != nullptr ? vb[k] : 0.f, c != nullptr ? vc[k] : 0.f, r0[k], r1[k]);
+    *reinterpret_cast<V*>(o0 + base + i * VEC) = *reinterpret_cast<V*>(r0);
+    if (o1 != nullptr) *reinterpret_cast<V*>(o1 + base + i * VEC) = *reinterpret_cast<V*>(r1);
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+ve_perturb_kernel(const float* __restrict__ y, const float* __restrict__ z, float* __restrict__ out,
+                  long long per_sample, CoefRef sig) {
+  const float sigma = sig.at(blockIdx.y, 0.f);
+  map3<VEC>(y, z, nullptr, out, nullptr, per_sample,
+            [sigma](float a, float b, float, float& r0, float&) { r0 = fmaf(b, sigma, a); });
 }
 
 // One CTA row per sample slab; partial sums of squares are combined with atomics into sq[2*batch].
@@ -86,11 +126,11 @@ __global__ void sqrt_inplace_kernel(float* v, int n) {
   if (i < n) v[i] = sqrtf(v[i]);
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(256)
-langevin_update_kernel(const float* __restrict__ x, const float* __restrict__ grad, const float* __restrict__ noise,
-                       const float* __restrict__ norms, float* __restrict__ x_out, float* __restrict__ x_mean,
-                       int batch, long long total, float snr, const float* __restrict__ alpha_tab,
-                       const int* __restrict__ step_idx) {
+langevin_update_kernel(const float* x, const float* __restrict__ grad, const float* __restrict__ noise,
+                       const float* __restrict__ norms, float* x_out, float* __restrict__ x_mean,
+                       int batch, long long per_sample, float snr, CoefRef alpha_ref) {
   // batch-mean norms (correctors.py:72-73): every thread reduces the 2*batch floats (L1/L2 resident)
   float gsum = 0.f, zsum = 0.f;
   for (int b = 0; b < batch; ++b) {
@@ -98,56 +138,68 @@ langevin_update_kernel(const float* __restrict__ x, const float* __restrict__ gr
     zsum += __ldg(norms + batch + b);
   }
   const float gn = gsum / batch, zn = zsum / batch;
-  const float alpha = alpha_tab != nullptr ? alpha_tab[*step_idx] : 1.f;
   const float r = snr * zn / gn;
-  const float step = r * r * 2.f * alpha;
+  const float step = r * r * 2.f * alpha_ref.at(blockIdx.y, 1.f);
   const float nz = sqrtf(step * 2.f);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const float m = fmaf(step, grad[i], x[i]);
-    x_mean[i] = m;
-    x_out[i] = fmaf(nz, noise[i], m);
-  }
+  map3<VEC>(x, grad, noise, x_out, x_mean, per_sample, [step, nz](float xi, float g, float z, float& xo, float& xm) {
+    xm = fmaf(step, g, xi);
+    xo = fmaf(nz, z, xm);
+  });
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(256)
-reverse_diffusion_kernel(const float* __restrict__ x, const float* __restrict__ score, const float* __restrict__ noise,
-                         float* __restrict__ x_out, float* __restrict__ x_mean, long long n,
-                         const float* __restrict__ f_tab, const float* __restrict__ g_tab, int pf,
-                         const int* __restrict__ step_idx) {
-  const int s = *step_idx;
-  const float fc = f_tab != nullptr ? f_tab[s] : 0.f;
-  const float g = g_tab[s];
+reverse_diffusion_kernel(const float* x, const float* __restrict__ score, const float* __restrict__ noise,
+                         float* x_out, float* __restrict__ x_mean, long long per_sample, CoefRef f_ref,
+                         CoefRef g_ref, int pf) {
+  const float fc = f_ref.at(blockIdx.y, 0.f);
+  const float g = g_ref.at(blockIdx.y, 0.f);
   const float g2 = g * g * (pf ? 0.5f : 1.f);
   const float gz = pf ? 0.f : g;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float xi = x[i];
-    const float rev_f = fc * xi - g2 * score[i];
-    const float m = xi - rev_f;
-    x_mean[i] = m;
-    x_out[i] = (noise != nullptr) ? fmaf(gz, noise[i], m) : m;
-  }
+  map3<VEC>(x, score, noise, x_out, x_mean, per_sample, [fc, g2, gz](float xi, float sc, float z, float& xo, float& xm) {
+    const float rev_f = fc * xi - g2 * sc;
+    xm = xi - rev_f;
+    xo = fmaf(gz, z, xm);
+  });
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(256)
-euler_maruyama_kernel(const float* __restrict__ x, const float* __restrict__ score, const float* __restrict__ noise,
-                      float* __restrict__ x_out, float* __restrict__ x_mean, long long n,
-                      const float* __restrict__ d_tab, const float* __restrict__ g_tab, float dt, int pf,
-                      const int* __restrict__ step_idx) {
-  const int s = *step_idx;
-  const float dc = d_tab != nullptr ? d_tab[s] : 0.f;
-  const float g = g_tab[s];
+euler_maruyama_kernel(const float* x, const float* __restrict__ score, const float* __restrict__ noise,
+                      float* x_out, float* __restrict__ x_mean, long long per_sample, CoefRef d_ref,
+                      CoefRef g_ref, float dt, int pf) {
+  const float dc = d_ref.at(blockIdx.y, 0.f);
+  const float g = g_ref.at(blockIdx.y, 0.f);
   const float g2 = g * g * (pf ? 0.5f : 1.f);
   const float gz = (pf ? 0.f : g) * sqrtf(-dt);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float xi = x[i];
-    const float drift = dc * xi - g2 * score[i];
-    const float m = fmaf(drift, dt, xi);
-    x_mean[i] = m;
-    x_out[i] = (noise != nullptr) ? fmaf(gz, noise[i], m) : m;
-  }
+  map3<VEC>(x, score, noise, x_out, x_mean, per_sample, [dc, g2, gz, dt](float xi, float sc, float z, float& xo, float& xm) {
+    const float drift = dc * xi - g2 * sc;
+    xm = fmaf(drift, dt, xi);
+    xo = fmaf(gz, z, xm);
+  });
+}
+
+static inline dim3 ps_grid(int batch, long long per_sample, int vec) {
+  long long bx = ceil_div_ll(per_sample / vec, 256);
+  long long cap = std::max<long long>(1, ceil_div_ll((long long)num_sms() * 8, batch));
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  return dim3((unsigned)bx, (unsigned)batch, 1);
+}
+
+static inline bool vec4_ok(long long per_sample, std::initializer_list<const void*> ptrs) {
+  if (per_sample % 4 != 0) return false;
+  for (const void* p : ptrs)
+    if (p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) != 0) return false;
+  return true;
 }
 
 __global__ void step_advance_kernel(int* s) { *s += 1; }
+
+__global__ void broadcast_table_kernel(float* dst, int n, CoefRef ref) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = ref.at(i, 0.f);
+}
 
 }  // namespace csd
 
@@ -167,17 +219,17 @@ int csd_fused_bias_act_f32(const float* x, const float* bias, const float* refer
   return CSD_OK;
 }
 
-int csd_ve_perturb_f32(const float* y, const float* z, float* y_pert, int64_t n, const float* sigma_tab,
-                       const int* step_idx, csd_stream_t stream) {
+int csd_ve_perturb_f32(const float* y, const float* z, float* y_pert, int batch, int64_t per_sample,
+                       const float* sigma_tab, const int* step_idx, int sample_stride, csd_stream_t stream) {
   using namespace csd;
-  CSD_REQUIRE(y && z && y_pert && sigma_tab && step_idx, "ve_perturb: null pointer");
-  CSD_REQUIRE(((uintptr_t)y & 15) == 0 && ((uintptr_t)z & 15) == 0 && ((uintptr_t)y_pert & 15) == 0,
-              "ve_perturb: pointers must be 16-byte aligned");
-  const long long n4 = n / 4;
-  const int tail = (int)(n - n4 * 4);
-  ve_perturb_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(z), reinterpret_cast<float4*>(y_pert), n4,
-      y + n4 * 4, z + n4 * 4, y_pert + n4 * 4, tail, sigma_tab, step_idx);
+  CSD_REQUIRE(y && z && y_pert && sigma_tab, "ve_perturb: null pointer");
+  CSD_REQUIRE(batch >= 1 && batch <= 65535 && per_sample >= 1, "ve_perturb: bad batch / per_sample");
+  CoefRef sig{sigma_tab, step_idx, sample_stride, batch};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec4_ok(per_sample, {y, z, y_pert}))
+    ve_perturb_kernel<4><<<ps_grid(batch, per_sample, 4), 256, 0, st>>>(y, z, y_pert, per_sample, sig);
+  else
+    ve_perturb_kernel<1><<<ps_grid(batch, per_sample, 1), 256, 0, st>>>(y, z, y_pert, per_sample, sig);
   CSD_LAUNCH_CHECK("ve_perturb_kernel");
   return CSD_OK;
 }
@@ -199,39 +251,69 @@ int csd_langevin_norms_f32(const float* grad, const float* noise, float* norms, 
 
 int csd_langevin_update_f32(const float* x, const float* grad, const float* noise, const float* norms, float* x_out,
                             float* x_mean, int batch, int64_t per_sample, float snr, const float* alpha_tab,
-                            const int* step_idx, csd_stream_t stream) {
+                            const int* step_idx, int sample_stride, csd_stream_t stream) {
   using namespace csd;
   CSD_REQUIRE(x && grad && noise && norms && x_out && x_mean, "langevin_update: null pointer");
-  CSD_REQUIRE(alpha_tab == nullptr || step_idx != nullptr, "langevin_update: alpha table without a step index");
-  const long long total = (long long)batch * per_sample;
-  langevin_update_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, grad, noise, norms, x_out, x_mean, batch, total, snr, alpha_tab, step_idx);
+  CSD_REQUIRE(batch >= 1 && batch <= 65535 && per_sample >= 1, "langevin_update: bad batch / per_sample");
+  CoefRef a{alpha_tab, step_idx, sample_stride, batch};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec4_ok(per_sample, {x, grad, noise, x_out, x_mean}))
+    langevin_update_kernel<4><<<ps_grid(batch, per_sample, 4), 256, 0, st>>>(x, grad, noise, norms, x_out, x_mean, batch,
+                                                                            per_sample, snr, a);
+  else
+    langevin_update_kernel<1><<<ps_grid(batch, per_sample, 1), 256, 0, st>>>(x, grad, noise, norms, x_out, x_mean, batch,
+                                                                            per_sample, snr, a);
   CSD_LAUNCH_CHECK("langevin_update_kernel");
   return CSD_OK;
 }
 
 int csd_reverse_diffusion_update_f32(const float* x, const float* score, const float* noise, float* x_out,
-                                     float* x_mean, int64_t n, const float* f_coef_tab, const float* g_tab,
-                                     int probability_flow, const int* step_idx, csd_stream_t stream) {
+                                     float* x_mean, int batch, int64_t per_sample, const float* f_coef_tab,
+                                     const float* g_tab, int probability_flow, const int* step_idx,
+                                     int sample_stride, csd_stream_t stream) {
   using namespace csd;
-  CSD_REQUIRE(x && score && x_out && x_mean && g_tab && step_idx, "reverse_diffusion_update: null pointer");
+  CSD_REQUIRE(x && score && x_out && x_mean && g_tab, "reverse_diffusion_update: null pointer");
   CSD_REQUIRE(noise != nullptr || probability_flow, "reverse_diffusion_update: noise required unless probability flow");
-  reverse_diffusion_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, score, noise, x_out, x_mean, n, f_coef_tab, g_tab, probability_flow, step_idx);
+  CSD_REQUIRE(batch >= 1 && batch <= 65535 && per_sample >= 1, "reverse_diffusion_update: bad batch / per_sample");
+  CoefRef f{f_coef_tab, step_idx, sample_stride, batch}, g{g_tab, step_idx, sample_stride, batch};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec4_ok(per_sample, {x, score, noise, x_out, x_mean}))
+    reverse_diffusion_kernel<4><<<ps_grid(batch, per_sample, 4), 256, 0, st>>>(x, score, noise, x_out, x_mean, per_sample,
+                                                                              f, g, probability_flow);
+  else
+    reverse_diffusion_kernel<1><<<ps_grid(batch, per_sample, 1), 256, 0, st>>>(x, score, noise, x_out, x_mean, per_sample,
+                                                                              f, g, probability_flow);
   CSD_LAUNCH_CHECK("reverse_diffusion_kernel");
   return CSD_OK;
 }
 
 int csd_euler_maruyama_update_f32(const float* x, const float* score, const float* noise, float* x_out, float* x_mean,
-                                  int64_t n, const float* d_coef_tab, const float* g_tab, float dt,
-                                  int probability_flow, const int* step_idx, csd_stream_t stream) {
+                                  int batch, int64_t per_sample, const float* d_coef_tab, const float* g_tab, float dt,
+                                  int probability_flow, const int* step_idx, int sample_stride, csd_stream_t stream) {
   using namespace csd;
-  CSD_REQUIRE(x && score && x_out && x_mean && g_tab && step_idx, "euler_maruyama_update: null pointer");
+  CSD_REQUIRE(x && score && x_out && x_mean && g_tab, "euler_maruyama_update: null pointer");
   CSD_REQUIRE(noise != nullptr || probability_flow, "euler_maruyama_update: noise required unless probability flow");
   CSD_REQUIRE(dt < 0.f, "euler_maruyama_update: dt must be negative (reverse time)");
-  euler_maruyama_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, score, noise, x_out, x_mean, n, d_coef_tab, g_tab, dt, probability_flow, step_idx);
+  CSD_REQUIRE(batch >= 1 && batch <= 65535 && per_sample >= 1, "euler_maruyama_update: bad batch / per_sample");
+  CoefRef d{d_coef_tab, step_idx, sample_stride, batch}, g{g_tab, step_idx, sample_stride, batch};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec4_ok(per_sample, {x, score, noise, x_out, x_mean}))
+    euler_maruyama_kernel<4><<<ps_grid(batch, per_sample, 4), 256, 0, st>>>(x, score, noise, x_out, x_mean, per_sample, d,
+                                                                           g, dt, probability_flow);
+  else
+    euler_maruyama_kernel<1><<<ps_grid(batch, per_sample, 1), 256, 0, st>>>(x, score, noise, x_out, x_mean, per_sample, d,
+                                                                           g, dt, probability_flow);
   CSD_LAUNCH_CHECK("euler_maruyama_kernel");
+  return CSD_OK;
+}
+
+int csd_broadcast_table_f32(float* dst, int n, const float* tab, const int* step_idx, int sample_stride,
+                            csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(dst && tab && n >= 1, "broadcast_table: bad arguments");
+  CoefRef r{tab, step_idx, sample_stride, n};
+  broadcast_table_kernel<<<ceil_div(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(dst, n, r);
+  CSD_LAUNCH_CHECK("broadcast_table_kernel");
   return CSD_OK;
 }
 

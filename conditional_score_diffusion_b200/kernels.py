@@ -177,34 +177,52 @@ def fused_bias_act(x, bias, refer, act, grad, alpha, scale):
 # --------------------------------------------------------------------------------------------
 # PC update kernels (fp32, contiguous, [batch, ...])
 # --------------------------------------------------------------------------------------------
-def ve_perturb(y, z, out, sigma_tab, step_idx):
+def _per_sample(t):
+    b = t.shape[0]
+    return b, t.numel() // b
+
+
+def ve_perturb(y, z, out, sigma_tab, step_idx=None, sample_stride=0):
     _require_cuda(y, z, out, sigma_tab, step_idx)
-    check(_lib.lib().csd_ve_perturb_f32(_ptr(y), _ptr(z), _ptr(out), y.numel(), _ptr(sigma_tab), _ptr(step_idx), _stream()))
+    b, ps = _per_sample(y)
+    check(_lib.lib().csd_ve_perturb_f32(_ptr(y), _ptr(z), _ptr(out), b, ps, _ptr(sigma_tab), _ptr(step_idx),
+                                        sample_stride, _stream()))
     return out
 
 
 def langevin_norms(grad, noise, norms):
-    b = grad.shape[0]
-    check(_lib.lib().csd_langevin_norms_f32(_ptr(grad), _ptr(noise), _ptr(norms), b, grad.numel() // b, _stream()))
+    b, ps = _per_sample(grad)
+    check(_lib.lib().csd_langevin_norms_f32(_ptr(grad), _ptr(noise), _ptr(norms), b, ps, _stream()))
     return norms
 
 
-def langevin_update(x, grad, noise, norms, x_out, x_mean, snr, alpha_tab, step_idx):
-    b = x.shape[0]
+def langevin_update(x, grad, noise, norms, x_out, x_mean, snr, alpha_tab=None, step_idx=None, sample_stride=0):
+    b, ps = _per_sample(x)
     check(_lib.lib().csd_langevin_update_f32(_ptr(x), _ptr(grad), _ptr(noise), _ptr(norms), _ptr(x_out), _ptr(x_mean),
-                                             b, x.numel() // b, float(snr), _ptr(alpha_tab), _ptr(step_idx), _stream()))
+                                             b, ps, float(snr), _ptr(alpha_tab), _ptr(step_idx), sample_stride,
+                                             _stream()))
 
 
-def reverse_diffusion_update(x, score, noise, x_out, x_mean, f_tab, g_tab, probability_flow, step_idx):
+def reverse_diffusion_update(x, score, noise, x_out, x_mean, f_tab, g_tab, probability_flow=False, step_idx=None,
+                             sample_stride=0):
+    b, ps = _per_sample(x)
     check(_lib.lib().csd_reverse_diffusion_update_f32(_ptr(x), _ptr(score), _ptr(noise), _ptr(x_out), _ptr(x_mean),
-                                                      x.numel(), _ptr(f_tab), _ptr(g_tab), int(probability_flow),
-                                                      _ptr(step_idx), _stream()))
+                                                      b, ps, _ptr(f_tab), _ptr(g_tab), int(probability_flow),
+                                                      _ptr(step_idx), sample_stride, _stream()))
 
 
-def euler_maruyama_update(x, score, noise, x_out, x_mean, d_tab, g_tab, dt, probability_flow, step_idx):
+def euler_maruyama_update(x, score, noise, x_out, x_mean, d_tab, g_tab, dt, probability_flow=False, step_idx=None,
+                          sample_stride=0):
+    b, ps = _per_sample(x)
     check(_lib.lib().csd_euler_maruyama_update_f32(_ptr(x), _ptr(score), _ptr(noise), _ptr(x_out), _ptr(x_mean),
-                                                   x.numel(), _ptr(d_tab), _ptr(g_tab), float(dt),
-                                                   int(probability_flow), _ptr(step_idx), _stream()))
+                                                   b, ps, _ptr(d_tab), _ptr(g_tab), float(dt),
+                                                   int(probability_flow), _ptr(step_idx), sample_stride, _stream()))
+
+
+def broadcast_table(dst, tab, step_idx=None, sample_stride=0):
+    check(_lib.lib().csd_broadcast_table_f32(_ptr(dst), dst.numel(), _ptr(tab), _ptr(step_idx), sample_stride,
+                                             _stream()))
+    return dst
 
 
 def step_advance(step_idx):

@@ -1,0 +1,109 @@
+"""Conditional samplers (reference: sampling/conditional.py:8-254).
+
+`get_pc_conditional_sampler` keeps the reference signature; the {'x': cVESDE, 'y': VESDE} pair with
+use_path=False (the configuration every shipped config uses) runs on the fused CUDA-graph loop.
+"""
+import functools
+
+import torch
+
+from .. import kernels as K
+from ..models import utils as mutils
+from . import fused
+from .correctors import NoneCorrector, get_corrector
+from .predictors import NonePredictor, get_predictor
+from .unconditional import fused_kinds
+
+
+def get_conditional_sampling_fn(config, sde, shape, eps, predictor="default", corrector="default", p_steps="default",
+                                c_steps="default", snr="default", denoise="default", use_path="default"):
+    """sampling/conditional.py:8-45."""
+    predictor = get_predictor((config.sampling.predictor if predictor == "default" else predictor).lower())
+    corrector = get_corrector((config.sampling.corrector if corrector == "default" else corrector).lower())
+    p_steps = config.model.num_scales if p_steps == "default" else p_steps
+    c_steps = config.sampling.n_steps_each if c_steps == "default" else c_steps
+    snr = config.sampling.snr if snr == "default" else snr
+    denoise = config.sampling.noise_removal if denoise == "default" else denoise
+    use_path = False if use_path == "default" else use_path
+    return get_pc_conditional_sampler(sde=sde, shape=shape, predictor=predictor, corrector=corrector, snr=snr,
+                                      p_steps=p_steps, c_steps=c_steps,
+                                      probability_flow=config.sampling.probability_flow,
+                                      continuous=config.training.continuous, denoise=denoise, use_path=use_path,
+                                      eps=eps)
+
+
+def conditional_shared_predictor_update_fn(x, y, t, sde, model, predictor, probability_flow, continuous):
+    """sampling/conditional.py:230-242."""
+    score_fn = mutils.get_score_fn(sde, model, conditional=True, train=False, continuous=continuous)
+    score_fn = mutils.get_conditional_score_fn(score_fn, target_domain="x")
+    c_sde = sde["x"] if isinstance(sde, dict) else sde
+    obj = NonePredictor(c_sde, score_fn, probability_flow) if predictor is None else predictor(c_sde, score_fn,
+                                                                                              probability_flow)
+    return obj.update_fn(x, y, t)
+
+
+def conditional_shared_corrector_update_fn(x, y, t, sde, model, corrector, continuous, snr, n_steps):
+    """sampling/conditional.py:244-255."""
+    score_fn = mutils.get_score_fn(sde, model, conditional=True, train=False, continuous=continuous)
+    score_fn = mutils.get_conditional_score_fn(score_fn, target_domain="x")
+    c_sde = sde["x"] if isinstance(sde, dict) else sde
+    obj = NoneCorrector(c_sde, score_fn, snr, n_steps) if corrector is None else corrector(c_sde, score_fn, snr, n_steps)
+    return obj.update_fn(x, y, t)
+
+
+def get_pc_conditional_sampler(sde, shape, predictor, corrector, snr, p_steps, c_steps=1, probability_flow=False,
+                               continuous=False, denoise=True, use_path=False, eps=1e-5):
+    """Create a conditional PC sampler (sampling/conditional.py:47-228).
+
+    Returns f(model, y, show_evolution=False) -> (samples, info).
+    """
+    if use_path:
+        raise NotImplementedError("use_path=True (sampling/conditional.py:87-94,124-176) is a follow-up row "
+                                  "(SURVEY.md §8f item 2); every shipped config uses use_path=False")
+    kinds = fused_kinds(predictor, corrector)
+    pair = isinstance(sde, dict) and len(sde.keys()) == 2
+    predictor_update_fn = functools.partial(conditional_shared_predictor_update_fn, sde=sde, predictor=predictor,
+                                            probability_flow=probability_flow, continuous=continuous)
+    corrector_update_fn = functools.partial(conditional_shared_corrector_update_fn, sde=sde, corrector=corrector,
+                                            continuous=continuous, snr=snr, n_steps=c_steps)
+    cache = {}
+
+    def perturbed(y, vec_t):
+        if not pair:
+            return y
+        std = sde["y"].marginal_prob(vec_t, vec_t)[1].contiguous()
+        y = y.contiguous().float()
+        return K.ve_perturb(y, torch.randn_like(y), torch.empty_like(y), std, None, 1)
+
+    def pc_conditional_sampler(model, y, show_evolution=False, x_init=None, noise_source=None):
+        c_sde = sde["x"] if isinstance(sde, dict) else sde
+        if kinds is not None and pair and hasattr(model, "_engine"):
+            fs = cache.get(id(model))
+            if fs is None:
+                fs = fused.FusedPCSampler(model, sde, shape, kinds[0], kinds[1], snr, p_steps, c_steps,
+                                          probability_flow, continuous, denoise, eps, conditional=True)
+                cache[id(model)] = fs
+            samples, evo = fs.sample(y=y, x_init=x_init, noise_source=noise_source, show_evolution=show_evolution)
+            if show_evolution:
+                return samples, {"evolution": {"x": torch.stack(evo["x"]), "y": torch.stack(evo["y"])}}
+            return samples, {}
+        with torch.no_grad():
+            x = (c_sde.prior_sampling(shape) if x_init is None else x_init).to(model.device)
+            evolution = {"x": [], "y": []}
+            timesteps = torch.linspace(c_sde.T, eps, p_steps, device=model.device)
+            x_mean = x
+            for i in range(p_steps):
+                vec_t = torch.ones(x.shape[0], device=model.device) * timesteps[i]
+                y_t = perturbed(y, vec_t)
+                x, x_mean = corrector_update_fn(x=x, y=y_t, t=vec_t, model=model)
+                y_t = perturbed(y, vec_t)
+                x, x_mean = predictor_update_fn(x=x, y=y_t, t=vec_t, model=model)
+                if show_evolution:
+                    evolution["x"].append(x.cpu())
+                    evolution["y"].append(y_t.cpu())
+            if show_evolution:
+                return (x_mean if denoise else x), {"evolution": {"x": torch.stack(evolution["x"]),
+                                                                  "y": torch.stack(evolution["y"])}}
+            return (x_mean if denoise else x), {}
+
+    return pc_conditional_sampler

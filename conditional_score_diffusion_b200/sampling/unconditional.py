@@ -1,0 +1,116 @@
+"""Unconditional samplers (reference: sampling/unconditional.py:13-228).
+
+`get_pc_sampler` keeps the reference signature and return values. With an engine-backed NCSN++ and a
+(predictor, corrector) pair covered by the fused loop it runs `fused.FusedPCSampler` (one CUDA graph
+per step); otherwise it runs the same corrector-then-predictor loop through the predictor /
+corrector classes, whose updates are still single fused CUDA kernels.
+"""
+import functools
+
+import torch
+
+from ..models import utils as mutils
+from . import fused
+from .correctors import NoneCorrector, get_corrector, _CORRECTORS
+from .predictors import NonePredictor, ReverseDiffusionPredictor, get_predictor, _PREDICTORS
+
+_FUSED_PREDICTORS = {"reverse_diffusion": "reverse_diffusion", "euler_maruyama": "euler_maruyama", "none": "none",
+                     "conditional_reverse_diffusion": "reverse_diffusion",
+                     "conditional_euler_maruyama": "euler_maruyama", "conditional_none": "none"}
+_FUSED_CORRECTORS = {"langevin": "langevin", "none": "none", "conditional_langevin": "langevin",
+                     "conditional_none": "none"}
+
+
+def _registry_name(cls, registry):
+    if cls is None:
+        return "none"
+    for k, v in registry.items():
+        if v is cls:
+            return k
+    return None
+
+
+def fused_kinds(predictor, corrector):
+    """Map predictor / corrector classes to the fused loop's kinds, or None if not covered."""
+    p = _FUSED_PREDICTORS.get(_registry_name(predictor, _PREDICTORS))
+    c = _FUSED_CORRECTORS.get(_registry_name(corrector, _CORRECTORS))
+    return (p, c) if p is not None and c is not None else None
+
+
+def get_sampling_fn(config, sde, shape, eps, predictor="default", corrector="default", p_steps="default",
+                    c_steps="default", snr="default", denoise="default"):
+    """sampling/unconditional.py:13-75."""
+    predictor = get_predictor((config.sampling.predictor if predictor == "default" else predictor).lower())
+    corrector = get_corrector((config.sampling.corrector if corrector == "default" else corrector).lower())
+    p_steps = config.model.num_scales if p_steps == "default" else p_steps
+    c_steps = config.sampling.n_steps_each if c_steps == "default" else c_steps
+    snr = config.sampling.snr if snr == "default" else snr
+    denoise = config.sampling.noise_removal if denoise == "default" else denoise
+    name = config.sampling.method.lower()
+    if name == "pc":
+        return get_pc_sampler(sde=sde, shape=shape, predictor=predictor, corrector=corrector, snr=snr, p_steps=p_steps,
+                              c_steps=c_steps, probability_flow=config.sampling.probability_flow,
+                              continuous=config.training.continuous, denoise=denoise, eps=eps)
+    if name == "ode":
+        raise NotImplementedError("the black-box ODE sampler (sampling/unconditional.py:93-158) is not part of this "
+                                  "round's hot path (SURVEY.md §8f item 3)")
+    raise ValueError(f"Sampler name {name} unknown.")
+
+
+def shared_predictor_update_fn(x, t, sde, model, predictor, probability_flow, continuous):
+    """sampling/unconditional.py:347-356."""
+    score_fn = mutils.get_score_fn(sde, model, conditional=False, train=False, continuous=continuous)
+    obj = NonePredictor(sde, score_fn, probability_flow) if predictor is None else predictor(sde, score_fn, probability_flow)
+    return obj.update_fn(x, t)
+
+
+def shared_corrector_update_fn(x, t, sde, model, corrector, continuous, snr, n_steps):
+    """sampling/unconditional.py:358-367."""
+    score_fn = mutils.get_score_fn(sde, model, conditional=False, train=False, continuous=continuous)
+    obj = NoneCorrector(sde, score_fn, snr, n_steps) if corrector is None else corrector(sde, score_fn, snr, n_steps)
+    return obj.update_fn(x, t)
+
+
+def get_pc_sampler(sde, shape, predictor, corrector, snr, p_steps, c_steps, probability_flow=False, continuous=False,
+                   denoise=True, eps=1e-3):
+    """Create a Predictor-Corrector sampler (sampling/unconditional.py:161-228).
+
+    Returns pc_sampler(model, show_evolution=False) -> (samples, {'times', 'steps'[, 'evolution']}).
+    """
+    kinds = fused_kinds(predictor, corrector)
+    predictor_update_fn = functools.partial(shared_predictor_update_fn, sde=sde, predictor=predictor,
+                                            probability_flow=probability_flow, continuous=continuous)
+    corrector_update_fn = functools.partial(shared_corrector_update_fn, sde=sde, corrector=corrector,
+                                            continuous=continuous, snr=snr, n_steps=c_steps)
+    cache = {}
+
+    def pc_sampler(model, show_evolution=False, x_init=None, noise_source=None):
+        steps = p_steps * (c_steps + 1)
+        if kinds is not None and hasattr(model, "_engine"):
+            fs = cache.get(id(model))
+            if fs is None:
+                fs = fused.FusedPCSampler(model, sde, shape, kinds[0], kinds[1], snr, p_steps, c_steps,
+                                          probability_flow, continuous, denoise, eps, conditional=False)
+                cache[id(model)] = fs
+            samples, evo = fs.sample(x_init=x_init, noise_source=noise_source, show_evolution=show_evolution)
+            info = {"times": fs.timesteps.to(model.device), "steps": steps}
+            if show_evolution:
+                info["evolution"] = torch.stack(evo["x"])
+            return samples, info
+        evolution = []
+        with torch.no_grad():
+            x = (sde.prior_sampling(shape) if x_init is None else x_init).to(model.device).type(torch.float32)
+            timesteps = torch.linspace(sde.T, eps, p_steps, device=model.device)
+            x_mean = x
+            for i in range(p_steps):
+                vec_t = torch.ones(shape[0], device=model.device) * timesteps[i]
+                x, x_mean = corrector_update_fn(x, vec_t, model=model)
+                x, x_mean = predictor_update_fn(x, vec_t, model=model)
+                if show_evolution:
+                    evolution.append(x.cpu())
+            info = {"times": timesteps, "steps": steps}
+            if show_evolution:
+                info["evolution"] = torch.stack(evolution)
+            return (x_mean if denoise else x), info
+
+    return pc_sampler

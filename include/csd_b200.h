@@ -66,36 +66,45 @@ int csd_fused_bias_act_f32(const float* x, const float* bias, const float* refer
  *      Per-step scalars live in DEVICE tables indexed by *step_idx (a device int) so a captured
  *      CUDA graph can be replayed for every step without host involvement.                     */
 
-/* y_pert = y + z * sigma_tab[*step]  (VESDE.marginal_prob, sde_lib.py:316-321). */
-int csd_ve_perturb_f32(const float* y, const float* z, float* y_pert, int64_t n, const float* sigma_tab,
-                       const int* step_idx, csd_stream_t stream);
+/* Scalar lookup convention shared by the entry points below: a coefficient table is either
+ * [n_steps] (sample_stride = 0: one value per step, shared by the batch) or [n_steps, batch]
+ * (sample_stride = 1); step_idx is a DEVICE int (NULL = step 0, i.e. a plain [batch] array).      */
+
+/* y_pert[b] = y[b] + z[b] * sigma(b)  (VESDE.marginal_prob, sde_lib.py:316-321;
+ * sampling/conditional.py:107-108). per_sample must be a multiple of 4.                          */
+int csd_ve_perturb_f32(const float* y, const float* z, float* y_pert, int batch, int64_t per_sample,
+                       const float* sigma_tab, const int* step_idx, int sample_stride, csd_stream_t stream);
 
 /* norms[0..batch) = ||grad_b||_2, norms[batch..2*batch) = ||noise_b||_2 (correctors.py:72-73). */
 int csd_langevin_norms_f32(const float* grad, const float* noise, float* norms, int batch,
                            int64_t per_sample, csd_stream_t stream);
 
-/* step = 2*alpha*(snr*mean(noise_norm)/mean(grad_norm))^2; x_mean = x + step*grad;
- * x_out = x_mean + sqrt(2*step)*noise (correctors.py:74-76). alpha_tab may be NULL (alpha = 1, VE).
- * grad is first multiplied by grad_scale_tab[*step] when that table is non-NULL (the 1/sigma(t)
- * of models/utils.py:50-74 for callers that pass the raw network output).                      */
+/* step = 2*alpha(b)*(snr*mean(noise_norm)/mean(grad_norm))^2; x_mean = x + step*grad;
+ * x_out = x_mean + sqrt(2*step)*noise (correctors.py:74-76). alpha_tab NULL = 1 (VE).
+ * x_out may alias x.                                                                           */
 int csd_langevin_update_f32(const float* x, const float* grad, const float* noise, const float* norms,
                             float* x_out, float* x_mean, int batch, int64_t per_sample, float snr,
-                            const float* alpha_tab, const int* step_idx, csd_stream_t stream);
+                            const float* alpha_tab, const int* step_idx, int sample_stride,
+                            csd_stream_t stream);
 
-/* Reverse-diffusion predictor (predictors.py:79-102 with sde_lib.py:87-92,349-360):
- * x_mean = x - (f_coef*x - g^2*score*pf) with f = f_coef_tab[*step]*x (0 for VE),
- * g = g_tab[*step]; x_out = x_mean + g*noise (noise ignored / g_out=0 if probability_flow).     */
+/* Reverse-diffusion predictor (predictors.py:79-102 with sde_lib.py:87-92,186-194,349-360):
+ * rev_f = f_coef(b)*x - g(b)^2*score*(pf ? .5 : 1); x_mean = x - rev_f; x_out = x_mean + g*noise
+ * (no noise term if probability_flow). f_coef_tab NULL = 0 (VE). x_out may alias x.              */
 int csd_reverse_diffusion_update_f32(const float* x, const float* score, const float* noise, float* x_out,
-                                     float* x_mean, int64_t n, const float* f_coef_tab,
+                                     float* x_mean, int batch, int64_t per_sample, const float* f_coef_tab,
                                      const float* g_tab, int probability_flow, const int* step_idx,
-                                     csd_stream_t stream);
+                                     int sample_stride, csd_stream_t stream);
 
-/* Euler-Maruyama predictor (predictors.py:52-77): drift = d_coef*x - g^2*score*pf, dt = -1/N;
- * x_mean = x + drift*dt ; x_out = x_mean + g*sqrt(-dt)*noise.                                  */
+/* Euler-Maruyama predictor (predictors.py:52-77): drift = d_coef(b)*x - g(b)^2*score*(pf ? .5 : 1);
+ * x_mean = x + drift*dt; x_out = x_mean + g*sqrt(-dt)*noise, dt = -1/N.                          */
 int csd_euler_maruyama_update_f32(const float* x, const float* score, const float* noise, float* x_out,
-                                  float* x_mean, int64_t n, const float* d_coef_tab, const float* g_tab,
-                                  float dt, int probability_flow, const int* step_idx,
-                                  csd_stream_t stream);
+                                  float* x_mean, int batch, int64_t per_sample, const float* d_coef_tab,
+                                  const float* g_tab, float dt, int probability_flow, const int* step_idx,
+                                  int sample_stride, csd_stream_t stream);
+
+/* dst[i] = table value for sample i at the current step (time labels, 1/sigma row scales). */
+int csd_broadcast_table_f32(float* dst, int n, const float* tab, const int* step_idx, int sample_stride,
+                            csd_stream_t stream);
 
 /* *step_idx += 1 (one thread). */
 int csd_step_advance(int* step_idx, csd_stream_t stream);

@@ -158,6 +158,22 @@ def test_pc_update_kernels_vs_oracle():
     _close(yp, x + z * sde.sigma(t)[:, None, None, None], F32, "ve perturb")
     k_.step_advance(step)
     assert step.item() == 4
+    # per-sample coefficient arrays (sample_stride = 1, no step index) and odd per-sample sizes
+    xs = torch.randn(3, 3, 5, 5, generator=g)
+    ss = torch.randn(3, 3, 5, 5, generator=g)
+    zs = torch.randn(3, 3, 5, 5, generator=g)
+    gv3 = torch.tensor([0.5, 1.5, 2.5])
+    fv3 = torch.tensor([0.1, -0.2, 0.3])
+    xo3, xm3 = torch.empty(3, 3, 5, 5, device=dev), torch.empty(3, 3, 5, 5, device=dev)
+    k_.reverse_diffusion_update(xs.cuda(), ss.cuda(), zs.cuda(), xo3, xm3, fv3.cuda(), gv3.cuda(), False, None, 1)
+    ref_m = xs - (fv3.view(3, 1, 1, 1) * xs - gv3.view(3, 1, 1, 1) ** 2 * ss)
+    _close(xm3, ref_m, F32, "rd per-sample mean")
+    _close(xo3, ref_m + gv3.view(3, 1, 1, 1) * zs, F32, "rd per-sample x")
+    dst = torch.empty(5, device=dev)
+    k_.broadcast_table(dst, torch.arange(10, dtype=torch.float32, device=dev), step, 0)
+    assert (dst == 4).all()
+    k_.broadcast_table(dst, torch.arange(40, dtype=torch.float32, device=dev), step, 1)
+    assert dst.tolist() == [20.0, 21.0, 22.0, 23.0, 24.0]
 
 
 @pytest.mark.parametrize("c0,c1,hw", [(96, 0, 24 * 24), (192, 96, 100), (288, 288, 25), (16, 0, 256), (288, 192, 400), (8, 0, 64)])
