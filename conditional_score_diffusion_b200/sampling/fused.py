@@ -116,6 +116,7 @@ class FusedPCSampler:
         g = self.graphs.get(draw_noise)
         if g is None:
             self.draw_noise = draw_noise
+            rng_state = torch.cuda.get_rng_state(self.x.device)   # warm-up must not consume the caller's stream
             for _ in range(2):               # warm-up outside capture (lazy init, the plan's own warm-up)
                 self.x.normal_()
                 for n in self.noise_x + (self.noise_y if self.conditional else []):
@@ -126,6 +127,7 @@ class FusedPCSampler:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._step()
+            torch.cuda.set_rng_state(rng_state, self.x.device)
             self.graphs[draw_noise] = g
         self.draw_noise = draw_noise
         return g
