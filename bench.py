@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Headline benchmark: sampled images/sec, NCSN++ 160 px VE-SDE, predictor-corrector 1000 steps.
+
+Workload (BASELINE.json configs[1], SURVEY.md §8d "Config 2"): celebA_ours_NDV_160.py in its NCSN++
+form (`ncsnpp_paired`, nf 96, ch_mult (1,1,2,2,3,3), attention at 20/10/5, 6 in / 6 out channels,
+160x160), conditional PC sampler = conditional Langevin corrector + conditional reverse-diffusion
+predictor, snr 0.15, {'x': cVESDE(5e-3, 277.13, 1000), 'y': VESDE(5e-3, 0.5, 1000)}, batch 64 per GPU,
+synthetic y = rand, random-init weights with init_scale=1 (init_scale=0 weights make the Langevin
+step size overflow).
+
+A "step" is ONE PC step (corrector + predictor = 2 network evaluations + the update kernels) over
+the whole per-GPU batch. images/sec = batch * gpus / (seconds per step * 1000): every one of the
+1000 steps of a PC-1000 trajectory has the same cost, so K timed steps give the per-image throughput
+of the full trajectory (default K = 200; --steps 1000 times a complete PC-1000 trajectory).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Prints ONE JSON line (see the keys in main()). `--impl reference` times the CPU oracle port of the
+reference path (oracle/, PyTorch fp32 on all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PC_STEPS = 1000
+BATCH_PER_GPU = 64
+IMAGE = 160
+SNR = 0.15
+EPS = 1e-5
+METRIC = "sampled images/sec NCSN++ 160px VE PC-1000"
+
+
+def workload_config(image=IMAGE, nf=96, ch_mult=(1, 1, 2, 2, 3, 3), attn=(20, 10, 5), num_res_blocks=2):
+    """configs/ve/inverse_problems/super_resolution/celebA_ours_NDV_160.py:83-144 with
+    model.name='ncsnpp_paired'  and init_scale=1."""
+    ns = SimpleNamespace
+    return ns(
+        training=ns(continuous=True),
+        data=ns(image_size=image, effective_image_size=image, num_channels=6, centered=False),
+        model=ns(name="ncsnpp_paired", nf=nf, ch_mult=ch_mult, num_res_blocks=num_res_blocks,
+                 attn_resolutions=attn, dropout=0.1, resamp_with_conv=True, conditional=True, fir=True,
+                 fir_kernel=[1, 3, 3, 1], skip_rescale=True, resblock_type="biggan", progressive="output_skip",
+                 progressive_input="input_skip", progressive_combine="sum", embedding_type="positional",
+                 init_scale=1.0, fourier_scale=16, nonlinearity="swish", num_scales=1000,
+                 sigma_max_x=math.sqrt(3 * image * image), sigma_max_y=0.5, sigma_min_x=5e-3, sigma_min_y=5e-3),
+        sampling=ns(method="pc", predictor="conditional_reverse_diffusion", corrector="conditional_langevin",
+                    n_steps_each=1, noise_removal=True, probability_flow=False, snr=SNR),
+    )
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_steps(cfg, sample_batch, steps, warmup, time_budget_s):
+    """Time `steps` PC steps of the oracle (CPU, torch fp32, all host threads) at batch `sample_batch`."""
+    import torch
+    from oracle import ncsnpp as o_net
+    from oracle import sampling as o_samp
+    from oracle import sde as o_sde
+    from conditional_score_diffusion_b200.models import ncsnpp, utils  # noqa: F401  (weights + layout only)
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = utils.create_model(cfg)   # parameter container only: the oracle evaluates the state dict on CPU
+    params = {k: v.detach() for k, v in model.state_dict().items()}
+    o = o_net.model_options(cfg)
+    spec = o_net.build_spec(o)
+    sx = o_sde.VE(cfg.model.sigma_min_x, cfg.model.sigma_max_x, 1000)
+    sy = o_sde.VE(cfg.model.sigma_min_y, cfg.model.sigma_max_y, 1000)
+    model_fn = lambda d, l: o_net.forward_paired(params, o, d["x"], d["y"], l, spec)
+    score_fn = o_sde.score_fn_conditional_pair(model_fn, sx, sy, True)
+    shape = (sample_batch, 3, cfg.data.image_size, cfg.data.image_size)
+    y = torch.rand(*shape)
+    x = sx.prior_sampling(shape)
+    ts = torch.linspace(1.0, EPS, PC_STEPS)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            vec_t = torch.ones(sample_batch) * ts[i]
+            y_t = y + torch.randn_like(y) * sy.sigma(vec_t)[:, None, None, None]
+            grad = score_fn(x, y_t, vec_t)
+            x, _ = o_samp.langevin_update(sx, grad, x, vec_t, torch.randn_like(x), SNR)
+            y_t = y + torch.randn_like(y) * sy.sigma(vec_t)[:, None, None, None]
+            score = score_fn(x, y_t, vec_t)
+            x, _ = o_samp.reverse_diffusion_update(sx, score, x, vec_t, torch.randn_like(x))
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+                if sum(times) > time_budget_s:
+                    break
+    s_per_step = sum(times) / len(times)
+    return {"s_per_step": s_per_step, "steps_timed": len(times), "cores": cores,
+            "images_per_s": sample_batch / (s_per_step * PC_STEPS)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = workload_config()
+    sample_b = 1
+    r = cpu_oracle_steps(cfg, sample_b, args.steps, min(args.warmup, 1), time_budget_s=150.0)
+    sample = (f"batch {sample_b} of {BATCH_PER_GPU}, {r['steps_timed']} PC steps timed after 1 warm-up, oracle port of "
+              f"the reference path (torch CPU fp32), {r['cores']} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["images_per_s"], "unit": "images/s", "n_gpus": args.gpus,
+        "steps": r["steps_timed"], "warmup": min(args.warmup, 1), "ms_per_step": r["s_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "celebA_ours_NDV_160 as ncsnpp_paired nf96, conditional PC-1000, 160x160",
+                   "batch_per_step": sample_b, "pc_steps_per_image": PC_STEPS},
+        "cpu_baseline": {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": r["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def conv_profile(plan):
+    """CUDA-event time and algorithmic FLOPs of every tcgen05 conv/GEMM launch of one forward."""
+    import torch
+    from conditional_score_diffusion_b200 import kernels as K
+    ev = []
+    torch.cuda.synchronize()
+    for fn, a, kw in plan.rec.ops:
+        if fn is K.conv_gemm:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(*a, **kw)
+            e1.record()
+            segs, _, n, _ = a
+            pixels = kw["batch"] * kw["h"] * kw["w"] * kw.get("z_batches", 1)
+            k_real = sum(t * c for (_, _, _, c, t) in segs)
+            ev.append((e0, e1, 2.0 * pixels * n * k_real, (kw["h"], kw["w"], n, k_real)))
+        else:
+            fn(*a, **kw)
+    torch.cuda.synchronize()
+    rows = [(e0.elapsed_time(e1), fl, shp) for e0, e1, fl, shp in ev]
+    return rows
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from conditional_score_diffusion_b200 import _lib, sampling, sde_lib
+    from conditional_score_diffusion_b200.models import ncsnpp, utils  # noqa: F401
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the B200 path has no CPU fallback "
+                           "(use --impl reference for the CPU oracle timing)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = workload_config()
+    B, K_steps, W = BATCH_PER_GPU, args.steps, max(args.warmup, 3)
+
+    torch.manual_seed(0)
+    model = utils.create_model(cfg).to(dev).eval()
+    if world > 1:
+        # the only collective of the sampling path: one weight broadcast at init
+        flat = torch.cat([p.data.reshape(-1) for p in model.parameters()])
+        dist.broadcast(flat, src=0)
+        off = 0
+        for p in model.parameters():
+            p.data.copy_(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+    sde = {"x": sde_lib.cVESDE(cfg.model.sigma_min_x, cfg.model.sigma_max_x, 1000),
+           "y": sde_lib.VESDE(cfg.model.sigma_min_y, cfg.model.sigma_max_y, 1000)}
+    shape = (B, 3, IMAGE, IMAGE)
+    torch.manual_seed(1000 + rank)
+
+    def make_sampler(p_steps):
+        return sampling.get_pc_conditional_sampler(
+            sde, shape, sampling.get_predictor("conditional_reverse_diffusion"),
+            sampling.get_corrector("conditional_langevin"), SNR, p_steps, 1, continuous=True, denoise=True, eps=EPS)
+
+    # ---- device-resident timing: inputs already in HBM, K graph replays of one PC step ----
+    from conditional_score_diffusion_b200.sampling.fused import FusedPCSampler
+    fs = FusedPCSampler(model, sde, shape, "reverse_diffusion", "langevin", SNR, PC_STEPS, 1, False, True, True, EPS,
+                        conditional=True)
+    fs._setup(dev)
+    y_dev = torch.rand(*shape, device=dev)
+    fs.y.copy_(y_dev)
+    launches0 = _lib.lib().csd_launch_count()
+    fs.draw_noise = True
+    fs.x.copy_(torch.randn(*shape, device=dev) * cfg.model.sigma_max_x)
+    fs.step_idx.zero_()
+    fs._step()                      # eager step: counts this library's launches per PC step
+    launches_per_step = _lib.lib().csd_launch_count() - launches0
+    graph = fs._graph(draw_noise=True)
+    fs.x.copy_(torch.randn(*shape, device=dev) * cfg.model.sigma_max_x)
+    fs.step_idx.zero_()
+    for _ in range(W):
+        graph.replay()
+    fs.step_idx.zero_()             # the K timed steps walk the first K entries of the PC-1000 schedule
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(min(K_steps, PC_STEPS)):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    k_eff = min(K_steps, PC_STEPS)
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = t.item() / k_eff
+    clock_info = clocks.stop() if rank == 0 else None
+    finite = bool(torch.isfinite(fs.x).all().item())
+
+    # ---- end to end through the public API: host y in pinned memory -> samples back on the host ----
+    sampler = make_sampler(k_eff)
+    y_host = torch.rand(*shape).pin_memory()
+    out_host = torch.empty(*shape).pin_memory()
+    sampler(model, y_host.to(dev, non_blocking=True))      # builds the plan/graph for this p_steps (untimed)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    samples, _ = sampler(model, y_host.to(dev, non_blocking=True))   # H2D of y; prior drawn on host + H2D inside
+    out_host.copy_(samples, non_blocking=True)                       # D2H of the result
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s_per_step = t.item() / k_eff
+    bytes_img = 3 * IMAGE * IMAGE * 4 * B
+    e2e = {"value": B * world / (e2e_s_per_step * PC_STEPS), "unit": "images/s",
+           "h2d_bytes_per_step": 2 * bytes_img / k_eff, "d2h_bytes_per_step": bytes_img / k_eff,
+           "note": f"public get_pc_conditional_sampler call with p_steps={k_eff}: y and the host-drawn prior "
+                   f"go H2D once per call, samples D2H once per call (bytes amortised over the {k_eff} steps)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (tcgen05 conv/GEMM), CUDA events per launch ----
+    peaks = measured_peaks()
+    rows = conv_profile(fs.plan)
+    rows = conv_profile(fs.plan)     # second pass: warm
+    conv_ms = sum(r[0] for r in rows)
+    conv_flops = sum(r[1] for r in rows)
+    top = max(rows, key=lambda r: r[0])
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM)", "achieved": achieved,
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                "traffic": None, "peak_source": peaks["source"], "launches_per_forward": len(rows),
+                "ms_per_forward_in_kernel": conv_ms, "algorithmic_gflop_per_forward": conv_flops / 1e9,
+                "share_of_step": 2 * conv_ms / ms_per_step,
+                "top_launch": {"ms": top[0], "tflops": top[1] / (top[0] * 1e-3) / 1e12, "h_w_n_k": top[2]}}
+
+    # ---- CPU baseline (oracle port) on a bounded sample ----
+    cpu = cpu_oracle_steps(cfg, 1, 3, 1, time_budget_s=60.0)
+    cpu_baseline = {"value": cpu["images_per_s"], "unit": "images/s", "cores": cpu["cores"], "kind": "port",
+                    "sample": f"batch 1 of {B}, {cpu['steps_timed']} PC steps after 1 warm-up, oracle port (torch CPU "
+                              f"fp32, {cpu['cores']} threads), extrapolated x1000 steps"}
+
+    line = {
+        "metric": METRIC, "value": B * world / (ms_per_step * 1e-3 * PC_STEPS), "unit": "images/s",
+        "n_gpus": world, "steps": k_eff, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "celebA_ours_NDV_160 as ncsnpp_paired nf96 (48.5 M params), conditional PC sampler "
+                               "(conditional_langevin + conditional_reverse_diffusion, snr 0.15), 160x160",
+                   "batch_per_gpu": B, "global_batch": B * world, "pc_steps_per_image": PC_STEPS,
+                   "step": "one PC step = 2 score-network evaluations + update kernels over the batch",
+                   "parallelism": f"batch sharded over {world} GPU(s), one weight broadcast, no per-step collective",
+                   "l2": "activations per step (several GB) exceed the 126 MB L2; no flush needed",
+                   "weights": "random init, init_scale=1", "finite_output": finite},
+        "e2e": e2e, "gpu_launches": int(launches_per_step * k_eff), "launches_per_step": int(launches_per_step),
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info,
+        "plan_buffers_gb": fs.plan.pool.nbytes() / 1e9,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)  # 200 of the 1000 identical steps
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

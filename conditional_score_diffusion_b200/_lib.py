@@ -78,6 +78,7 @@ _PROTOTYPES = {
     "csd_last_error": (ctypes.c_char_p, []),
     "csd_abi_version": (c_int, []),
     "csd_device_sm_count": (c_int, [c_int_p]),
+    "csd_launch_count": (ctypes.c_longlong, []),
     "csd_upfirdn2d_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64] + [c_int] * 12 + [c_void_p]),
     "csd_upfirdn2d_out_size": (c_int, [c_int] * 12 + [c_int_p, c_int_p]),
     "csd_fused_bias_act_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int,

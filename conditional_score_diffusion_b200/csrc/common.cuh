@@ -37,7 +37,13 @@ inline int check_cuda(cudaError_t e, const char* what) {
     if (!(cond)) return ::csd::set_error(CSD_ERR_INVALID, __VA_ARGS__); \
   } while (0)
 
-#define CSD_LAUNCH_CHECK(name) CSD_CUDA(cudaGetLastError())
+// Every kernel launch in the library goes through this macro: it checks the launch and counts it
+// (csd_launch_count), so callers can report how many of OUR kernels a region launched.
+#define CSD_LAUNCH_CHECK(name)            \
+  do {                                    \
+    ::csd::count_launch();                \
+    CSD_CUDA(cudaGetLastError());         \
+  } while (0)
 
 #ifdef __CUDACC__
 #define CSD_HD __host__ __device__
@@ -48,6 +54,7 @@ CSD_HD inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 CSD_HD inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
 int num_sms();  // SM count of the current device (cached)
+void count_launch();
 
 #ifdef __CUDACC__
 

@@ -3,12 +3,16 @@
 #include "tensormap.cuh"
 #include "../../include/csd_b200.h"
 
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
 namespace csd {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 char* error_buffer() { return g_err; }
 
@@ -100,6 +104,8 @@ extern "C" {
 const char* csd_last_error(void) { return csd::error_buffer(); }
 
 int csd_abi_version(void) { return CSD_ABI_VERSION; }
+
+long long csd_launch_count(void) { return csd::g_launches.load(std::memory_order_relaxed); }
 
 int csd_device_sm_count(int* out) {
   if (!out) return csd::set_error(CSD_ERR_INVALID, "null output");

@@ -39,6 +39,9 @@ typedef void* csd_stream_t; /* cudaStream_t */
 const char* csd_last_error(void);
 int csd_abi_version(void);
 int csd_device_sm_count(int* out);
+/* Kernels launched by this library in this process so far (host-side count of <<<>>> launches; a
+ * captured CUDA graph replays them without passing here again). */
+long long csd_launch_count(void);
 
 /* ---- upfirdn2d: replaces op/upfirdn2d.cpp:12-23 + op/upfirdn2d_kernel.cu:209-369 -------------
  * input  [planes, in_h, in_w] fp32 (planes = N*C; the reference views it as [major,H,W,minor=1],
