@@ -40,6 +40,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("batch", c_int32), ("h", c_int32), ("w", c_int32),
         ("in_h", c_int32), ("in_w", c_int32), ("stride", c_int32), ("pad", c_int32),
         ("tile_w", c_int32), ("tile_h", c_int32), ("tile_b", c_int32),
+        ("mode", c_int32), ("mt", c_int32),
         ("nseg", c_int32),
         ("n", c_int32),
         ("n_store", c_int32),

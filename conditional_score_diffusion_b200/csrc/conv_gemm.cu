@@ -19,7 +19,15 @@
 #include "tensormap.cuh"
 #include "../../include/csd_b200.h"
 
+#include <cstdlib>
+
 namespace csd {
+
+#define CSD_TS(i)                                                                          \
+  do {                                                                                   \
+    if (p.debug_ts != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) \
+      p.debug_ts[i] = clock64();                                                         \
+  } while (0)
 
 constexpr int kChunkK = 32;                       // channels per pipeline stage
 constexpr int kRowBytes = kChunkK * 2;            // 64 B of bf16 per row -> SWIZZLE_64B
@@ -42,6 +50,12 @@ struct ConvGemmKernelParams {
   int a_batch_step;
   int num_stages, tmem_cols;
   uint32_t stage_bytes, a_box_bytes, b_box_bytes;
+  long long* debug_ts;  // perf experiment only: phase timestamps of one mid-grid CTA
+  int debug_nodata;  // perf experiment only: skip the steady-state loads (results are garbage)
+  // halo mode
+  int mt, a_stages, b_stages;
+  int seg_kbase[CSD_MAX_SEGMENTS];
+  uint32_t a_stage_bytes, b_stage_bytes;
   void* out;
   int out_pitch, out_f32;
   long long out_z_stride;
@@ -55,134 +69,21 @@ struct ConvGemmKernelParams {
   float scale;
 };
 
-__global__ void __launch_bounds__(kConvThreads)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
-                 const __grid_constant__ CUtensorMap mapB, const ConvGemmKernelParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte aligned base: the swizzle pattern is a function of the shared-memory address bits.
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + p.num_stages * p.stage_bytes;
-  // barrier layout: full[num_stages], empty[num_stages], tmem_full, then the TMEM address slot
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxStages);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  // tile coordinates
-  const int t = blockIdx.x;
-  const int tw = t % p.tiles_w;
-  const int th = (t / p.tiles_w) % p.tiles_h;
-  const int tb = t / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * p.TW, h0 = th * p.TH, b0 = tb * p.TB;
-  const int n0 = blockIdx.y * p.n_tile;
-  const int z = blockIdx.z;
-
-  int total_iters = 0;
-  for (int s = 0; s < p.nseg; ++s) total_iters += p.seg_taps[s] * p.seg_chunks[s];
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&mapA0);
-    ptx::prefetch_tensormap(&mapB);
-    for (int s = 0; s < p.num_stages; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
-    }
-    ptx::mbar_init(tmem_full_bar, 1);
-    ptx::fence_mbar_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    ptx::tmem_relinquish();
-  }
-  ptx::tcgen05_fence_before();
-  __syncthreads();
-  ptx::tcgen05_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int it = 0;
-      int kidx = 0;  // running 32-wide K block index into Wt
-      for (int s = 0; s < p.nseg; ++s) {
-        const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
-        const int taps = p.seg_taps[s];
-        for (int tap = 0; tap < taps; ++tap) {
-          const int dy = (taps == 9) ? (tap / 3 - p.pad) : 0;
-          const int dx = (taps == 9) ? (tap % 3 - p.pad) : 0;
-          for (int c = 0; c < p.seg_chunks[s]; ++c, ++it, ++kidx) {
-            const int stage = it % p.num_stages;
-            const uint32_t parity = ((it / p.num_stages) & 1) ^ 1;
-            ptx::mbar_wait(empty_bar(stage), parity);
-            const uint32_t a_dst = smem_base + stage * p.stage_bytes;
-            const uint32_t b_dst = a_dst + kAStageBytes;
-            ptx::mbar_arrive_expect_tx(full_bar(stage), p.a_box_bytes + p.b_box_bytes * p.nsplit);
-            ptx::tma_load_4d(a_dst, mapA, full_bar(stage), p.seg_coff[s] + c * kChunkK, w0 * p.stride + dx, h0 * p.stride + dy,
-                             b0 + z * p.a_batch_step);
-            for (int j = 0; j < p.nsplit; ++j) {
-              ptx::tma_load_3d(b_dst + j * p.b_box_bytes, &mapB, full_bar(stage), p.wt_k_off + kidx * kChunkK,
-                               n0 + j * p.n_sub, z);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)p.n_sub);
-      for (int it = 0; it < total_iters; ++it) {
-        const int stage = it % p.num_stages;
-        const uint32_t parity = (it / p.num_stages) & 1;
-        ptx::mbar_wait(full_bar(stage), parity);
-        ptx::tcgen05_fence_after();
-        const uint32_t a_addr = smem_base + stage * p.stage_bytes;
-        const uint32_t b_addr = a_addr + kAStageBytes;
-#pragma unroll
-        for (int kk = 0; kk < kChunkK / 16; ++kk) {
-          const uint64_t a_desc = ptx::make_smem_desc(a_addr + kk * 32, 16, 512, kLayoutSw64);
-          for (int j = 0; j < p.nsplit; ++j) {
-            const uint64_t b_desc =
-                ptx::make_smem_desc(b_addr + j * p.b_box_bytes + kk * 32, 16, 512, kLayoutSw64);
-            ptx::mma_bf16_ss(tmem_base + j * p.n_sub, a_desc, b_desc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-          }
-        }
-        ptx::mma_commit(empty_bar(stage));  // frees the stage when the MMAs above have read it
-      }
-      ptx::mma_commit(tmem_full_bar);       // accumulator complete
-    }
-  } else {
-    // ===== epilogue (warps 2..5): warp q owns TMEM lanes [32q, 32q+32) with q = warp % 4 =====
-    const int q = warp & 3;
-    const int m = q * 32 + lane;  // row of the tile
-    const int wl = m % p.TW;
-    const int hl = (m / p.TW) % p.TH;
-    const int bl = m / (p.TW * p.TH);
-    const int b = b0 + bl, h = h0 + hl, w = w0 + wl;
-    const bool valid = (bl < p.TB) && (b < p.B) && (h < p.H) && (w < p.W);
-    const long long pix = ((long long)b * p.H + h) * p.W + w;
-
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tcgen05_fence_after();
-
-    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float row_bias = (p.bias != nullptr && p.bias_per_row && valid) ? p.bias[pix] : 0.0f;
-    const float* temb_row = (p.temb != nullptr && valid) ? p.temb + (long long)b * p.temb_pitch : nullptr;
-    const __nv_bfloat16* res_row =
-        (p.res != nullptr && valid) ? p.res + (long long)z * p.res_z_stride + pix * p.res_pitch : nullptr;
-
-    const int ncols = min(p.n_tile, p.n_store - n0);  // columns of this tile that are stored
-    for (int col = 0; col < ncols; col += 16) {
-      uint32_t r[16];
-      __syncwarp();
-      ptx::tmem_ld_x16(t_row + col, r);
-      ptx::tmem_ld_wait();
-      if (valid) {
+// Epilogue of one accumulator row: thread = one output pixel (TMEM lane), 16 columns at a time.
+// out = (acc + bias + temb[b] + residual) * scale, stored as bf16 or fp32 rows.
+__device__ __forceinline__ void epilogue_rows(const ConvGemmKernelParams& p, uint32_t t_row, bool valid, long long pix,
+                                              int b, int n0, int z) {
+  const float row_bias = (p.bias != nullptr && p.bias_per_row && valid) ? p.bias[pix] : 0.0f;
+  const float* temb_row = (p.temb != nullptr && valid) ? p.temb + (long long)b * p.temb_pitch : nullptr;
+  const __nv_bfloat16* res_row =
+      (p.res != nullptr && valid) ? p.res + (long long)z * p.res_z_stride + pix * p.res_pitch : nullptr;
+  const int ncols = min(p.n_tile, p.n_store - n0);  // columns of this tile that are stored
+  for (int col = 0; col < ncols; col += 16) {
+    uint32_t r[16];
+    __syncwarp();
+    ptx::tmem_ld_x16(t_row + col, r);
+    ptx::tmem_ld_wait();
+    if (valid) {
       const int n = n0 + col;
       float v[16];
 #pragma unroll
@@ -242,8 +143,132 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           for (int i = 0; i < cnt; ++i) op[i] = __float2bfloat16_rn(v[i]);
         }
       }
-      }  // valid
     }
+  }
+}
+
+__global__ void __launch_bounds__(kConvThreads)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                 const __grid_constant__ CUtensorMap mapB, const ConvGemmKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned base: the swizzle pattern is a function of the shared-memory address bits.
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + p.num_stages * p.stage_bytes;
+  // barrier layout: full[num_stages], empty[num_stages], tmem_full, then the TMEM address slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int t = blockIdx.x;
+  const int tw = t % p.tiles_w;
+  const int th = (t / p.tiles_w) % p.tiles_h;
+  const int tb = t / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.TW, h0 = th * p.TH, b0 = tb * p.TB;
+  const int n0 = blockIdx.y * p.n_tile;
+  const int z = blockIdx.z;
+
+  int total_iters = 0;
+  for (int s = 0; s < p.nseg; ++s) total_iters += p.seg_taps[s] * p.seg_chunks[s];
+  if (threadIdx.x == 0) CSD_TS(0);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&mapA0);
+    ptx::prefetch_tensormap(&mapB);
+    for (int s = 0; s < p.num_stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) CSD_TS(1);
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      int kidx = 0;  // running 32-wide K block index into Wt
+      for (int s = 0; s < p.nseg; ++s) {
+        const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
+        const int taps = p.seg_taps[s];
+        for (int tap = 0; tap < taps; ++tap) {
+          const int dy = (taps == 9) ? (tap / 3 - p.pad) : 0;
+          const int dx = (taps == 9) ? (tap % 3 - p.pad) : 0;
+          for (int c = 0; c < p.seg_chunks[s]; ++c, ++it, ++kidx) {
+            const int stage = it % p.num_stages;
+            const uint32_t parity = ((it / p.num_stages) & 1) ^ 1;
+            ptx::mbar_wait(empty_bar(stage), parity);
+            const uint32_t a_dst = smem_base + stage * p.stage_bytes;
+            const uint32_t b_dst = a_dst + kAStageBytes;
+            ptx::mbar_arrive_expect_tx(full_bar(stage), p.a_box_bytes + p.b_box_bytes * p.nsplit);
+            ptx::tma_load_4d(a_dst, mapA, full_bar(stage), p.seg_coff[s] + c * kChunkK, w0 * p.stride + dx, h0 * p.stride + dy,
+                             b0 + z * p.a_batch_step);
+            for (int j = 0; j < p.nsplit; ++j) {
+              ptx::tma_load_3d(b_dst + j * p.b_box_bytes, &mapB, full_bar(stage), p.wt_k_off + kidx * kChunkK,
+                               n0 + j * p.n_sub, z);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)p.n_sub);
+      for (int it = 0; it < total_iters; ++it) {
+        const int stage = it % p.num_stages;
+        const uint32_t parity = (it / p.num_stages) & 1;
+        ptx::mbar_wait(full_bar(stage), parity);
+        ptx::tcgen05_fence_after();
+        if (it == 0) CSD_TS(3);
+        if (it == total_iters / 2) CSD_TS(8);
+        const uint32_t a_addr = smem_base + stage * p.stage_bytes;
+        const uint32_t b_addr = a_addr + kAStageBytes;
+#pragma unroll
+        for (int kk = 0; kk < kChunkK / 16; ++kk) {
+          const uint64_t a_desc = ptx::make_smem_desc(a_addr + kk * 32, 16, 512, kLayoutSw64);
+          for (int j = 0; j < p.nsplit; ++j) {
+            const uint64_t b_desc =
+                ptx::make_smem_desc(b_addr + j * p.b_box_bytes + kk * 32, 16, 512, kLayoutSw64);
+            ptx::mma_bf16_ss(tmem_base + j * p.n_sub, a_desc, b_desc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        ptx::mma_commit(empty_bar(stage));  // frees the stage when the MMAs above have read it
+      }
+      CSD_TS(4);
+      ptx::mma_commit(tmem_full_bar);       // accumulator complete
+    }
+  } else {
+    // ===== epilogue (warps 2..5): warp q owns TMEM lanes [32q, 32q+32) with q = warp % 4 =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;  // row of the tile
+    const int wl = m % p.TW;
+    const int hl = (m / p.TW) % p.TH;
+    const int bl = m / (p.TW * p.TH);
+    const int b = b0 + bl, h = h0 + hl, w = w0 + wl;
+    const bool valid = (bl < p.TB) && (b < p.B) && (h < p.H) && (w < p.W);
+    const long long pix = ((long long)b * p.H + h) * p.W + w;
+
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tcgen05_fence_after();
+    if (threadIdx.x == 64) CSD_TS(5);
+    epilogue_rows(p, tmem_base + ((uint32_t)(q * 32) << 16), valid, pix, b, n0, z);
+    if (threadIdx.x == 64) CSD_TS(6);
   }
 
   // teardown: everyone is done with TMEM before the allocating warp frees it
@@ -252,6 +277,171 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   if (warp == 1) {
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (lane == 0) CSD_TS(7);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Halo mode (3x3 stride-1 convolutions at the large resolutions).
+//
+// Per 32-channel chunk ONE TMA box load brings the (16*mt+2) x 10 pixel halo of the CTA's mt stacked
+// 16x8-pixel tiles into shared memory (64-byte swizzled rows, one row per pixel). All 9 taps of every
+// tile are then issued from that single copy: the UMMA descriptor of tap (ky,kx) of tile t starts
+// ((16t+ky)*10 + kx) rows into the halo and strides 10 rows between 8-row core-matrix groups (SBO).
+// This works because the hardware applies the 64-byte swizzle to absolute shared-memory address
+// bits, so a start address shifted by whole 64-byte rows stays consistent with what TMA wrote
+// (verified on B200 with tools/umma_halo_probe.cu). Compared with the per-tap kernel above the
+// activation bytes moved from L2 drop 9x -> ~1.3x of the tile, and with mt = 2 every weight slab
+// feeds two tiles. Weights stream through their own ring, one N x 64-byte slab per (chunk, tap).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kHaloTW = 8, kHaloTH = 16;
+constexpr int kMaxAStages = 4, kMaxBStages = 8;
+
+__global__ void __launch_bounds__(kConvThreads)
+conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                 const __grid_constant__ CUtensorMap mapB, const ConvGemmKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + p.a_stages * p.a_stage_bytes;
+  const uint32_t bar_base = b_base + p.b_stages * p.b_stage_bytes;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (kMaxAStages + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + kMaxBStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages);
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x;
+  const int tw = t % p.tiles_w;
+  const int th = (t / p.tiles_w) % p.tiles_h;
+  const int b = t / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * kHaloTW, h0 = th * kHaloTH * p.mt;
+  const int n0 = blockIdx.y * p.n_tile;
+  if (threadIdx.x == 0) CSD_TS(0);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&mapA0);
+    ptx::prefetch_tensormap(&mapB);
+    for (int s = 0; s < p.a_stages; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (threadIdx.x == 0) CSD_TS(1);
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int ia = 0, ib = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
+        const int taps = p.seg_taps[s];
+        const int halo = (taps == 9) ? 1 : 0;
+        const uint32_t a_bytes = (uint32_t)((kHaloTW + 2 * halo) * (kHaloTH * p.mt + 2 * halo) * kRowBytes);
+        const int nchunks = p.seg_chunks[s];
+        for (int c = 0; c < nchunks; ++c, ++ia) {
+          const int sa = ia % p.a_stages;
+          if (!(p.debug_nodata && ia >= p.a_stages)) {
+          ptx::mbar_wait(a_empty(sa), ((ia / p.a_stages) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(a_full(sa), a_bytes);
+          ptx::tma_load_4d(a_base + sa * p.a_stage_bytes, mapA, a_full(sa), p.seg_coff[s] + c * kChunkK, w0 - halo,
+                           h0 - halo, b);
+          }
+          for (int tap = 0; tap < taps; ++tap, ++ib) {
+            const int sb = ib % p.b_stages;
+            if (p.debug_nodata && ib >= p.b_stages) continue;
+            ptx::mbar_wait(b_empty(sb), ((ib / p.b_stages) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(b_full(sb), p.b_box_bytes * p.nsplit);
+            const int kidx = p.seg_kbase[s] + tap * nchunks + c;
+            for (int j = 0; j < p.nsplit; ++j)
+              ptx::tma_load_3d(b_base + sb * p.b_stage_bytes + j * p.b_box_bytes, &mapB, b_full(sb),
+                               p.wt_k_off + kidx * kChunkK, n0 + j * p.n_sub, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)p.n_sub);
+      int ia = 0, ib = 0;
+      uint32_t accumulate = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const int taps = p.seg_taps[s];
+        const int halo = (taps == 9) ? 1 : 0;
+        const int pitch = kHaloTW + 2 * halo;              // pixels per halo row
+        const uint32_t sbo = (uint32_t)pitch * kRowBytes;  // stride between 8-pixel core-matrix groups
+        for (int c = 0; c < p.seg_chunks[s]; ++c, ++ia) {
+          const int sa = ia % p.a_stages;
+          if (!(p.debug_nodata && ia >= p.a_stages)) ptx::mbar_wait(a_full(sa), (ia / p.a_stages) & 1);
+          ptx::tcgen05_fence_after();
+          if (ia == 0) CSD_TS(3);
+          if (ia == 1) CSD_TS(8);
+          const uint32_t a_addr = a_base + sa * p.a_stage_bytes;
+          for (int tap = 0; tap < taps; ++tap, ++ib) {
+            const int sb = ib % p.b_stages;
+            if (!(p.debug_nodata && ib >= p.b_stages)) ptx::mbar_wait(b_full(sb), (ib / p.b_stages) & 1);
+            ptx::tcgen05_fence_after();
+            const uint32_t b_addr = b_base + sb * p.b_stage_bytes;
+            const int dy = halo ? tap / 3 : 0, dx = halo ? tap % 3 : 0;
+            for (int tt = 0; tt < p.mt; ++tt) {
+              const uint32_t a_tile = a_addr + (uint32_t)(((kHaloTH * tt + dy) * pitch + dx) * kRowBytes);
+#pragma unroll
+              for (int kk = 0; kk < kChunkK / 16; ++kk) {
+                const uint64_t a_desc = ptx::make_smem_desc(a_tile + kk * 32, 16, sbo, kLayoutSw64);
+                for (int j = 0; j < p.nsplit; ++j) {
+                  const uint64_t b_desc =
+                      ptx::make_smem_desc(b_addr + j * p.b_box_bytes + kk * 32, 16, 512, kLayoutSw64);
+                  ptx::mma_bf16_ss(tmem_base + tt * p.n_tile + j * p.n_sub, a_desc, b_desc, idesc,
+                                   (accumulate || kk > 0) ? 1u : 0u);
+                }
+              }
+            }
+            accumulate = 1;
+            ptx::mma_commit(b_empty(sb));
+          }
+          ptx::mma_commit(a_empty(sa));
+        }
+      }
+      CSD_TS(4);
+      ptx::mma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue: warp q owns TMEM lanes [32q, 32q+32); one pass per stacked tile =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tcgen05_fence_after();
+    if (threadIdx.x == 64) CSD_TS(5);
+    for (int tt = 0; tt < p.mt; ++tt) {
+      const int h = h0 + kHaloTH * tt + m / kHaloTW, w = w0 + m % kHaloTW;
+      const bool valid = (h < p.H) && (w < p.W);
+      const long long pix = ((long long)b * p.H + h) * p.W + w;
+      epilogue_rows(p, tmem_base + ((uint32_t)(q * 32) << 16) + tt * p.n_tile, valid, pix, b, n0, 0);
+    }
+    if (threadIdx.x == 64) CSD_TS(6);
+  }
+
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (lane == 0) CSD_TS(7);
   }
 }
 
@@ -268,15 +458,22 @@ struct ConvGemmLaunch {
   ConvGemmKernelParams p;
   dim3 grid;
   size_t smem;
+  bool halo;
 };
 
 int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   CSD_REQUIRE(d != nullptr, "null conv_gemm desc");
   CSD_REQUIRE(d->nseg >= 1 && d->nseg <= CSD_MAX_SEGMENTS, "nseg=%d out of range", d->nseg);
   CSD_REQUIRE(d->batch >= 1 && d->h >= 1 && d->w >= 1, "bad spatial dims %d %d %d", d->batch, d->h, d->w);
-  CSD_REQUIRE(d->tile_w >= 1 && d->tile_h >= 1 && d->tile_b >= 1 &&
-                  d->tile_w * d->tile_h * d->tile_b <= kTileM,
+  const bool halo_mode = d->mode == 1;
+  L->halo = halo_mode;
+  const int mt = halo_mode ? (d->mt > 0 ? d->mt : 1) : 1;
+  CSD_REQUIRE(halo_mode || (d->tile_w >= 1 && d->tile_h >= 1 && d->tile_b >= 1 &&
+                            d->tile_w * d->tile_h * d->tile_b <= kTileM),
               "tile box %dx%dx%d exceeds 128 pixels", d->tile_w, d->tile_h, d->tile_b);
+  CSD_REQUIRE(!halo_mode || (d->z_batches == 1 && (d->stride <= 1) && d->pad == 1 && mt >= 1 && mt <= 4 &&
+                             mt * d->n_tile <= 512),
+              "halo mode needs stride 1, pad 1, no z batching and mt*n_tile <= 512 (mt=%d n_tile=%d)", mt, d->n_tile);
   CSD_REQUIRE(d->n_tile >= 16 && d->n_tile % 16 == 0 && d->n_tile <= 512, "n_tile=%d invalid", d->n_tile);
   CSD_REQUIRE(d->n >= 1 && d->n_store >= 1, "n=%d n_store=%d invalid", d->n, d->n_store);
   CSD_REQUIRE(d->out != nullptr && d->wt != nullptr, "null out / wt pointer");
@@ -285,10 +482,13 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   ConvGemmKernelParams& p = L->p;
   memset(&p, 0, sizeof(p));
   p.B = d->batch; p.H = d->h; p.W = d->w;
-  p.TW = d->tile_w; p.TH = d->tile_h; p.TB = d->tile_b;
-  p.tiles_w = ceil_div(d->w, d->tile_w);
-  p.tiles_h = ceil_div(d->h, d->tile_h);
-  const int tiles_b = ceil_div(d->batch, d->tile_b);
+  p.TW = halo_mode ? kHaloTW : d->tile_w;
+  p.TH = halo_mode ? kHaloTH : d->tile_h;
+  p.TB = halo_mode ? 1 : d->tile_b;
+  p.mt = mt;
+  p.tiles_w = ceil_div(d->w, p.TW);
+  p.tiles_h = ceil_div(d->h, p.TH * mt);
+  const int tiles_b = ceil_div(d->batch, p.TB);
   p.nseg = d->nseg;
   p.stride = d->stride > 0 ? d->stride : 1;
   p.pad = d->pad;
@@ -309,7 +509,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   CSD_REQUIRE(d->wt_rows >= 1, "wt_rows=%d", d->wt_rows);
   p.wt_k_off = d->wt_k_off;
   p.a_batch_step = d->a_batch_step;
-  p.tmem_cols = next_pow2_cols(d->n_tile);
+  p.tmem_cols = next_pow2_cols(d->n_tile * mt);
 
   int k_total = 0;
   for (int s = 0; s < d->nseg; ++s) {
@@ -321,6 +521,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     p.seg_taps[s] = sg.taps;
     p.seg_chunks[s] = ceil_div(sg.c_cnt, kChunkK);
     p.seg_coff[s] = sg.c_off;
+    p.seg_kbase[s] = k_total / kChunkK;
     k_total += sg.taps * p.seg_chunks[s] * kChunkK;
     // 4-D map over [batch, h, w, c]; dim 0 stops at the last valid channel so the remainder of a
     // 32-channel chunk is zero-filled instead of reading the neighbouring channels.
@@ -330,8 +531,13 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     uint64_t strides[3] = {(uint64_t)sg.pitch * 2, (uint64_t)sg.pitch * 2 * in_w,
                            (uint64_t)sg.pitch * 2 * in_w * in_h};
     // with a traversal stride s the box spans (t-1)*s+1 source elements and delivers t of them
-    uint32_t box[4] = {(uint32_t)kChunkK, (uint32_t)((d->tile_w - 1) * p.stride + 1),
-                       (uint32_t)((d->tile_h - 1) * p.stride + 1), (uint32_t)d->tile_b};
+    uint32_t box[4] = {(uint32_t)kChunkK, (uint32_t)((p.TW - 1) * p.stride + 1),
+                       (uint32_t)((p.TH - 1) * p.stride + 1), (uint32_t)p.TB};
+    if (halo_mode) {  // whole halo of the mt stacked tiles (a 1-tap segment needs no halo)
+      const int hl = sg.taps == 9 ? 1 : 0;
+      box[1] = (uint32_t)(kHaloTW + 2 * hl);
+      box[2] = (uint32_t)(kHaloTH * mt + 2 * hl);
+    }
     uint32_t estr[4] = {1, (uint32_t)p.stride, (uint32_t)p.stride, 1};
     int st = encode_tensor_map(&L->mapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, sg.a, dims, strides, box,
                                TMA_SW_64, estr);
@@ -352,7 +558,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     if (st != CSD_OK) return st;
   }
 
-  p.a_box_bytes = (uint32_t)(d->tile_w * d->tile_h * d->tile_b * kRowBytes);
+  p.a_box_bytes = (uint32_t)(p.TW * p.TH * p.TB * kRowBytes);
   p.b_box_bytes = (uint32_t)(p.n_sub * kRowBytes);
   p.stage_bytes = (uint32_t)((kAStageBytes + d->n_tile * kRowBytes + 1023) & ~1023);
   const int total_iters = k_total / kChunkK;
@@ -369,11 +575,36 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   p.res = reinterpret_cast<const __nv_bfloat16*>(d->res); p.res_pitch = d->res_pitch;
   p.res_z_stride = d->res_z_stride;
   p.scale = d->scale;
+  {
+    const char* e = getenv("CSD_DEBUG_NODATA");
+    p.debug_nodata = (e != nullptr && e[0] == '1') ? 1 : 0;
+    const char* t = getenv("CSD_DEBUG_TS");
+    p.debug_ts = (t != nullptr) ? reinterpret_cast<long long*>(strtoull(t, nullptr, 0)) : nullptr;
+  }
   CSD_REQUIRE(d->out_pitch % 8 == 0, "out_pitch=%d must be a multiple of 8", d->out_pitch);
   CSD_REQUIRE(d->res == nullptr || d->res_pitch % 8 == 0, "res_pitch=%d must be a multiple of 8", d->res_pitch);
 
   L->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * tiles_b), (unsigned)n_tiles, (unsigned)d->z_batches);
   L->smem = (size_t)stages * p.stage_bytes + 1024 /*alignment slack*/ + 8 * (2 * kMaxStages + 2);
+  if (halo_mode) {
+    p.a_stage_bytes = (uint32_t)(((kHaloTW + 2) * (kHaloTH * mt + 2) * kRowBytes + 1023) & ~1023);
+    p.b_stage_bytes = (uint32_t)((d->n_tile * kRowBytes + 1023) & ~1023);
+    // two CTAs per SM when TMEM allows it (<= 256 columns): keep each under ~110 KB
+    const int budget_h = p.tmem_cols <= 256 ? 108 * 1024 : 200 * 1024;
+    p.a_stages = 2;
+    int bs = (budget_h - p.a_stages * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
+    if (bs > kMaxBStages) bs = kMaxBStages;
+    if (bs >= 4 && p.a_stages < 3 &&
+        budget_h - 3 * (int)p.a_stage_bytes >= 4 * (int)p.b_stage_bytes) {  // room for a third halo buffer
+      p.a_stages = 3;
+      bs = (budget_h - 3 * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
+      if (bs > kMaxBStages) bs = kMaxBStages;
+    }
+    CSD_REQUIRE(bs >= 2, "halo mode: not enough shared memory for the weight ring (n_tile=%d mt=%d)", d->n_tile, mt);
+    p.b_stages = bs;
+    L->smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 +
+              8 * (2 * kMaxAStages + 2 * kMaxBStages + 2);
+  }
   CSD_REQUIRE(L->smem <= 227 * 1024, "shared memory %zu exceeds 227 KB", L->smem);
   // If z batches share the weights the z coordinate of the weight map must stay 0.
   if (d->wt_batch_stride == 0 && d->z_batches > 1) {
@@ -386,10 +617,16 @@ int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_gemm_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
-                                                               L->mapB, L->p);
+  if (L->halo) {
+    conv_halo_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
+                                                                 L->mapB, L->p);
+  } else {
+    conv_gemm_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
+                                                                 L->mapB, L->p);
+  }
   CSD_LAUNCH_CHECK("conv_gemm_kernel");
   return CSD_OK;
 }

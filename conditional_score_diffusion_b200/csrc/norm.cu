@@ -50,7 +50,24 @@ __global__ void gn_stats_kernel(GnParams p) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (pp < ppb) {
-    for (long long pix = lo + pp; pix < hi; pix += ppb) {
+    // 4 independent 16-byte loads in flight per thread (HBM latency hiding)
+    long long pix = lo + pp;
+    for (; pix + 3LL * ppb < hi; pix += 4LL * ppb) {
+      bf16x8 v4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v4[u] = gn_load(p, b, pix + (long long)u * ppb, v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v4[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += f[i];
+          q[i] = fmaf(f[i], f[i], q[i]);
+        }
+      }
+    }
+    for (; pix < hi; pix += ppb) {
       float f[8];
       unpack8(gn_load(p, b, pix, v), f);
 #pragma unroll
@@ -108,7 +125,24 @@ __global__ void gn_apply_kernel(GnParams p) {
     sc[i] = scale[v * 8 + i];
     sh[i] = shift[v * 8 + i];
   }
-  for (long long pix = lo + pp; pix < hi; pix += ppb) {
+  long long pix = lo + pp;
+  for (; pix + 3LL * ppb < hi; pix += 4LL * ppb) {
+    bf16x8 v4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v4[u] = gn_load(p, b, pix + (long long)u * ppb, v);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v4[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = fmaf(f[i], sc[i], sh[i]);
+        f[i] = p.silu ? silu_f(y) : y;
+      }
+      p.out[((long long)b * p.hw + pix + (long long)u * ppb) * p.out_pv + v] = pack8(f);
+    }
+  }
+  for (; pix < hi; pix += ppb) {
     float f[8];
     unpack8(gn_load(p, b, pix, v), f);
 #pragma unroll
@@ -138,8 +172,8 @@ static int gn_fill(GnParams& p, const void* src0, int c0, int pitch0, const void
   const int ppb = std::max(1, 256 / V);
   *threads = V * ppb;
   *smem = sizeof(float) * 2 * C;
-  int slabs = ceil_div(num_sms() * 4, batch);
-  const int max_slabs = std::max(1, hw / (ppb * 4));
+  int slabs = ceil_div(num_sms() * 8, batch);
+  const int max_slabs = std::max(1, hw / (ppb * 8));
   p.slabs = std::max(1, std::min(slabs, max_slabs));
   return CSD_OK;
 }

@@ -5,6 +5,7 @@ libcsd_b200.so on torch's current stream and raises on any error; none has a PyT
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -51,6 +52,10 @@ def pack_conv_weight(weight, n_pad=None, dtype=_BF16):
 
 
 _TILE_CACHE = {}
+# Halo mode (one activation load per 32-channel chunk feeds all 9 taps) is opt-in: measured on B200 it
+# does not beat the per-tap kernel while pixels are the M operand (tcgen05.mma has a ~100-cycle floor per
+# M=128 instruction, tools/mma_rate_probe.cu), see DESIGN.md.
+HALO_DEFAULT = os.environ.get("CSD_HALO", "0") == "1"
 
 
 def pick_tile(h, w, batch):
@@ -80,7 +85,7 @@ def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None
               tile=None, bias=None, bias_per_row=False, temb=None, temb_pitch=0, res=None,
               res_pitch=0, scale=1.0, out_f32=None, z_batches=1, a_batch_step=0, wt_batch_stride=0,
               out_z_stride=0, res_z_stride=0, wt_pitch=0, wt_k_off=0, k_valid=0, wt_rows=None,
-              stride=1, pad=1, in_h=0, in_w=0):
+              stride=1, pad=1, in_h=0, in_w=0, halo=None, mt=None):
     """Launch csd_conv_gemm. segments: list of (tensor, pitch, c_off, c_cnt, taps)."""
     _require_cuda(wt, out, bias, temb, res, *[s[0] for s in segments])
     d = ConvGemmDesc()
@@ -88,6 +93,8 @@ def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None
     d.in_h, d.in_w, d.stride, d.pad = in_h, in_w, stride, pad
     tw, th, tb = tile if tile is not None else pick_tile(h, w, batch)
     d.tile_w, d.tile_h, d.tile_b = tw, th, tb
+    n_store_ = n_store if n_store is not None else n
+    nt_ = n_tile if n_tile is not None else None
     d.nseg = len(segments)
     k_total = 0
     for i, (a, pitch, c_off, c_cnt, taps) in enumerate(segments):
@@ -104,6 +111,13 @@ def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None
         n16 = ceil_to(d.n_store, 16)
         n_tile = n16 if n16 <= 256 else (ceil_to(n16 // 2, 16) if n16 <= 512 else 256)
     d.n_tile = n_tile
+    if halo is None:
+        halo = (HALO_DEFAULT and tile is None and segments[0][4] == 9 and stride == 1 and pad == 1 and z_batches == 1
+                and w % 8 == 0 and h >= 16 and n_tile <= 512)
+    if halo:
+        if mt is None:
+            mt = 2 if (2 * n_tile <= 256 and h % 32 == 0) else 1
+        d.mode, d.mt = 1, mt
     d.wt = wt.data_ptr()
     d.wt_rows = wt_rows if wt_rows is not None else wt.shape[-2]
     d.k_total = k_total

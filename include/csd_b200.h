@@ -187,7 +187,10 @@ typedef struct csd_conv_gemm_desc {
   int32_t stride;               /* conv stride (1 or 2); taps read in[o*stride + k - pad]  */
   int32_t pad;                  /* 1 = 'same' 3x3 (torch padding=1), 0 = valid / padded-after
                                    (DDPM Downsample pads bottom/right: TMA zero-fills it)   */
-  int32_t tile_w, tile_h, tile_b; /* pixel box per CTA, product <= 128                    */
+  int32_t tile_w, tile_h, tile_b; /* pixel box per CTA, product <= 128 (ignored in halo mode) */
+  int32_t mode;                 /* 0 = one TMA box per tap; 1 = halo: 16x8-pixel tiles, one halo load per
+                                   32-channel chunk feeds all 9 taps (3x3, stride 1, pad 1 only)   */
+  int32_t mt;                   /* halo mode: vertically stacked tiles per CTA (1..4), mt*n_tile <= 512 */
   int32_t nseg;
   int32_t n;                    /* output columns computed (rows of Wt used)             */
   int32_t n_store;              /* output columns written (>= n allowed: zero columns)   */

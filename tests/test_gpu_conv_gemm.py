@@ -238,3 +238,92 @@ def test_conv3x3_stride2_ddpm_downsample():
                 stride=2, pad=0, in_h=H, in_w=H)
     torch.cuda.synchronize()
     assert _report("ddpm downsample conv", out.permute(0, 3, 1, 2), ref, BF16_RTOL) < BF16_RTOL
+
+
+def _halo_case(name, B, H, W, cin, cout, mt, seed=0, temb=True, res=True, n_tile=None):
+    """Halo-mode kernel against the same fp32 reference (and implicitly against the per-tap kernel)."""
+    k = _kern()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.randn(B, cin, H, W, device=dev, generator=g).to(torch.bfloat16)
+    wgt = (torch.randn(cout, cin, 3, 3, device=dev, generator=g) / math.sqrt(9 * cin)).to(torch.bfloat16)
+    npad = k.ceil_to(cout, 16) if n_tile is None else k.ceil_to(cout, n_tile)
+    wt = k.pack_conv_weight(wgt, n_pad=npad)
+    bias = torch.zeros(npad + 16, device=dev)
+    bias[:cout] = torch.randn(cout, device=dev, generator=g)
+    ref = F.conv2d(x.float(), wgt.float(), padding=1) + bias[:cout].view(1, -1, 1, 1)
+    temb_t = res_t = None
+    if temb:
+        temb_t = torch.zeros(B, npad + 16, device=dev)
+        temb_t[:, :cout] = torch.randn(B, cout, device=dev, generator=g)
+        ref = ref + temb_t[:, :cout].reshape(B, cout, 1, 1)
+    if res:
+        r = torch.randn(B, cout, H, W, device=dev, generator=g).to(torch.bfloat16)
+        res_t = _nhwc(r)
+        ref = ref + r.float()
+    ref = ref * 0.5
+    out = torch.full((B, H, W, cout), float("nan"), device=dev, dtype=torch.bfloat16)
+    k.conv_gemm([(_nhwc(x), cin, 0, cin, 9)], wt, cout, out, batch=B, h=H, w=W, bias=bias, temb=temb_t,
+                temb_pitch=npad + 16, res=res_t, res_pitch=cout, scale=0.5, halo=True, mt=mt, n_tile=n_tile)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all(), f"{name}: non-finite"
+    return _report(name, out.permute(0, 3, 1, 2), ref, BF16_RTOL)
+
+
+def test_halo_mode_basic():
+    assert _halo_case("halo 96->96 32x32 mt=1", 2, 32, 32, 96, 96, 1) < BF16_RTOL
+    assert _halo_case("halo 96->96 32x32 mt=2", 2, 32, 32, 96, 96, 2) < BF16_RTOL
+    assert _halo_case("halo 96->96 64x64 mt=4", 2, 64, 64, 96, 96, 4) < BF16_RTOL
+
+
+def test_halo_mode_ragged_and_wide():
+    assert _halo_case("halo 192->192 40x40 mt=1 (ragged h)", 3, 40, 40, 192, 192, 1) < BF16_RTOL
+    assert _halo_case("halo 96->192 80x80 mt=2 (ragged h)", 2, 80, 80, 96, 192, 2, n_tile=None) < BF16_RTOL
+    assert _halo_case("halo 64->96 24x20 mt=1 (ragged w)", 2, 24, 20, 64, 96, 1) < BF16_RTOL
+    assert _halo_case("halo 192->288 16x16 n_tile=144", 2, 16, 16, 192, 288, 1, n_tile=144) < BF16_RTOL
+    assert _halo_case("halo 192->288 16x16 n_tile=288", 2, 16, 16, 192, 288, 1, n_tile=288) < BF16_RTOL
+    assert _halo_case("halo 8->96 32x32 (padded cin)", 2, 32, 32, 8, 96, 2) < BF16_RTOL
+
+
+def test_halo_mode_segments_and_skip():
+    k = _kern()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(25)
+    B, H, W, c1, c2, cs, cout = 2, 32, 32, 96, 64, 160, 96
+    a1 = torch.randn(B, c1, H, W, device=dev, generator=g).to(torch.bfloat16)
+    a2 = torch.randn(B, c2, H, W, device=dev, generator=g).to(torch.bfloat16)
+    xs = torch.randn(B, cs, H, W, device=dev, generator=g).to(torch.bfloat16)
+    w3 = (torch.randn(cout, c1 + c2, 3, 3, device=dev, generator=g) / math.sqrt(9 * (c1 + c2))).to(torch.bfloat16)
+    w1 = (torch.randn(cout, cs, 1, 1, device=dev, generator=g) / math.sqrt(cs)).to(torch.bfloat16)
+    ref = F.conv2d(torch.cat([a1, a2], 1).float(), w3.float(), padding=1) + F.conv2d(xs.float(), w1.float())
+    wt = torch.cat([k.pack_conv_weight(w3[:, :c1]), k.pack_conv_weight(w3[:, c1:]), k.pack_conv_weight(w1)], dim=1).contiguous()
+    for mt in (1, 2):
+        out = torch.empty(B, H, W, cout, device=dev, dtype=torch.bfloat16)
+        k.conv_gemm([(_nhwc(a1), c1, 0, c1, 9), (_nhwc(a2), c2, 0, c2, 9), (_nhwc(xs), cs, 0, cs, 1)], wt, cout, out,
+                    batch=B, h=H, w=W, halo=True, mt=mt)
+        torch.cuda.synchronize()
+        assert _report(f"halo 2 segments + skip mt={mt}", out.permute(0, 3, 1, 2), ref, BF16_RTOL) < BF16_RTOL
+
+
+def test_halo_vs_tap_timing():
+    k = _kern()
+    dev = "cuda"
+    for (B, H, cin, cout) in [(64, 160, 96, 96), (64, 160, 192, 96), (64, 80, 96, 96), (64, 80, 192, 192), (64, 40, 192, 192)]:
+        a = torch.randn(B, H, H, cin, device=dev).to(torch.bfloat16)
+        wt = k.pack_conv_weight((torch.randn(cout, cin, 3, 3, device=dev) / 30).to(torch.bfloat16))
+        out = torch.empty(B, H, H, cout, device=dev, dtype=torch.bfloat16)
+        flops = 2.0 * B * H * H * cin * cout * 9
+        for label, kw in [("tap", dict(halo=False)), ("halo mt=1", dict(halo=True, mt=1)), ("halo mt=2", dict(halo=True, mt=2)),
+                          ("halo mt=4", dict(halo=True, mt=4))]:
+            if kw.get("mt", 1) * k.ceil_to(cout, 16) > 512:
+                continue
+            for _ in range(2):
+                k.conv_gemm([(a, cin, 0, cin, 9)], wt, cout, out, batch=B, h=H, w=H, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                k.conv_gemm([(a, cin, 0, cin, 9)], wt, cout, out, batch=B, h=H, w=H, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            print(f"[conv timing] {H}x{H} {cin}->{cout} {label:10s}: {ms:.3f} ms  {flops / ms / 1e9:.0f} TFLOP/s")
