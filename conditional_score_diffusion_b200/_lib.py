@@ -67,6 +67,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("res_pitch", c_int32),
         ("res_z_stride", c_int64),
         ("scale", c_float),
+        ("stat_partials", c_void_p),
     ]
 
 

@@ -42,7 +42,7 @@ def _digest(paths):
         with open(p, "rb") as f:
             h.update(p.encode())
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
     return h.hexdigest()
 
 
@@ -52,9 +52,14 @@ def _all_inputs():
     return [os.path.abspath(f) for f in files]
 
 
+def _extra_flags():
+    """Developer-only extra nvcc flags (e.g. CSD_NVCC_EXTRA=-DCSD_ENABLE_PHASE_TIMESTAMPS)."""
+    return os.environ.get("CSD_NVCC_EXTRA", "").split()
+
+
 def _compile_one(src):
     obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [_nvcc()] + NVCC_FLAGS + _extra_flags() + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return src, obj, r.returncode, r.stdout + r.stderr
 

@@ -58,7 +58,8 @@ void count_launch();
 
 #ifdef __CUDACC__
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// SiLU with the fast-division path (2 MUFU + 2 FP ops); |error| < 2 ulp of fp32, far below bf16 storage.
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -23,11 +23,15 @@
 
 namespace csd {
 
+#ifdef CSD_ENABLE_PHASE_TIMESTAMPS
 #define CSD_TS(i)                                                                          \
   do {                                                                                   \
     if (p.debug_ts != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) \
       p.debug_ts[i] = clock64();                                                         \
   } while (0)
+#else
+#define CSD_TS(i) do { } while (0)
+#endif
 
 constexpr int kChunkK = 32;                       // channels per pipeline stage
 constexpr int kRowBytes = kChunkK * 2;            // 64 B of bf16 per row -> SWIZZLE_64B
@@ -50,6 +54,7 @@ struct ConvGemmKernelParams {
   int a_batch_step;
   int num_stages, tmem_cols;
   uint32_t stage_bytes, a_box_bytes, b_box_bytes;
+  float* stat_partials;  // [tiles, n_store, 2] per-tile per-channel (sum, sumsq) of the stored output, or null
   long long* debug_ts;  // perf experiment only: phase timestamps of one mid-grid CTA
   int debug_nodata;  // perf experiment only: skip the steady-state loads (results are garbage)
   // halo mode
@@ -71,43 +76,65 @@ struct ConvGemmKernelParams {
 
 // Epilogue of one accumulator row: thread = one output pixel (TMEM lane), 16 columns at a time.
 // out = (acc + bias + temb[b] + residual) * scale, stored as bf16 or fp32 rows.
+// Latency hiding: the per-column addend (bias + temb) comes from a shared-memory table built while the
+// main loop runs (s_add, may be null), and the residual of chunk k+1 is fetched while chunk k's
+// tcgen05.ld is in flight, so no global-load latency sits between TMEM read and the store.
 __device__ __forceinline__ void epilogue_rows(const ConvGemmKernelParams& p, uint32_t t_row, bool valid, long long pix,
-                                              int b, int n0, int z) {
+                                              int b, int n0, int z, const float* s_add) {
   const float row_bias = (p.bias != nullptr && p.bias_per_row && valid) ? p.bias[pix] : 0.0f;
   const float* temb_row = (p.temb != nullptr && valid) ? p.temb + (long long)b * p.temb_pitch : nullptr;
   const __nv_bfloat16* res_row =
       (p.res != nullptr && valid) ? p.res + (long long)z * p.res_z_stride + pix * p.res_pitch : nullptr;
   const int ncols = min(p.n_tile, p.n_store - n0);  // columns of this tile that are stored
+  uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
+  if (res_row != nullptr && ncols >= 16) {
+    const uint4* rp = reinterpret_cast<const uint4*>(res_row + n0);
+    rn0 = __ldg(rp);
+    rn1 = __ldg(rp + 1);
+  }
   for (int col = 0; col < ncols; col += 16) {
     uint32_t r[16];
     __syncwarp();
     ptx::tmem_ld_x16(t_row + col, r);
+    const int n = n0 + col;
+    const int cnt = min(16, p.n_store - n);
+    const uint4 rc0 = rn0, rc1 = rn1;
+    if (res_row != nullptr && col + 32 <= ncols) {  // next chunk is complete: prefetch its residual
+      const uint4* rp = reinterpret_cast<const uint4*>(res_row + n + 16);
+      rn0 = __ldg(rp);
+      rn1 = __ldg(rp + 1);
+    }
     ptx::tmem_ld_wait();
     if (valid) {
-      const int n = n0 + col;
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-      if (p.bias != nullptr) {
-        if (p.bias_per_row) {
+      if (s_add != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += row_bias;
-        } else {
+        for (int i = 0; i < 16; i += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(s_add + col + i);
+          v[i] += a.x; v[i + 1] += a.y; v[i + 2] += a.z; v[i + 3] += a.w;
+        }
+      } else {
+        if (p.bias != nullptr) {
+          if (p.bias_per_row) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n + i);
+            for (int i = 0; i < 16; ++i) v[i] += row_bias;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n + i);
+          }
+        }
+        if (temb_row != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(temb_row + n + i);
         }
       }
-      if (temb_row != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += __ldg(temb_row + n + i);
-      }
-      const int cnt = min(16, p.n_store - n);
       if (res_row != nullptr) {
         if (cnt == 16) {
-          const uint4* rp = reinterpret_cast<const uint4*>(res_row + n);
           bf16x8 r0, r1;
-          *reinterpret_cast<uint4*>(&r0) = __ldg(rp);
-          *reinterpret_cast<uint4*>(&r1) = __ldg(rp + 1);
+          *reinterpret_cast<uint4*>(&r0) = rc0;
+          *reinterpret_cast<uint4*>(&r1) = rc1;
           float f[16];
           unpack8(r0, f);
           unpack8(r1, f + 8);
@@ -147,6 +174,21 @@ __device__ __forceinline__ void epilogue_rows(const ConvGemmKernelParams& p, uin
   }
 }
 
+// Built by the 128 epilogue threads while the main loop runs: s_add[i] = bias[n0+i] + temb[b, n0+i].
+// Only when every row of the tile belongs to the same image b (tile_b == 1) and the bias is per column.
+__device__ __forceinline__ const float* build_addend_table(const ConvGemmKernelParams& p, uint32_t s_add_addr, int b,
+                                                           int n0, int et /*0..127*/) {
+  if (p.bias_per_row || (p.bias == nullptr && p.temb == nullptr)) return nullptr;
+  float* s_add = reinterpret_cast<float*>(__cvta_shared_to_generic(s_add_addr));
+  for (int i = et; i < p.n_tile; i += 128) {
+    float a = p.bias != nullptr ? __ldg(p.bias + n0 + i) : 0.f;
+    if (p.temb != nullptr) a += __ldg(p.temb + (long long)b * p.temb_pitch + n0 + i);
+    s_add[i] = a;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+  return s_add;
+}
+
 __global__ void __launch_bounds__(kConvThreads)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
@@ -160,6 +202,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxStages);
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1);
+  const uint32_t s_add_addr = bar_base + 8u * (2 * kMaxStages + 2);  // 16-byte aligned, n_tile floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -264,10 +307,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const bool valid = (bl < p.TB) && (b < p.B) && (h < p.H) && (w < p.W);
     const long long pix = ((long long)b * p.H + h) * p.W + w;
 
+    const float* s_add = (p.TB == 1 && b0 < p.B) ? build_addend_table(p, s_add_addr, b0, n0, threadIdx.x - 64) : nullptr;
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tcgen05_fence_after();
     if (threadIdx.x == 64) CSD_TS(5);
-    epilogue_rows(p, tmem_base + ((uint32_t)(q * 32) << 16), valid, pix, b, n0, z);
+    epilogue_rows(p, tmem_base + ((uint32_t)(q * 32) << 16), valid, pix, b, n0, z, s_add);
     if (threadIdx.x == 64) CSD_TS(6);
   }
 
@@ -313,6 +357,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + kMaxBStages + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages);
   const uint32_t tmem_slot = tmem_full_bar + 8u;
+  const uint32_t s_add_addr = tmem_full_bar + 16u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -424,6 +469,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     // ===== epilogue: warp q owns TMEM lanes [32q, 32q+32); one pass per stacked tile =====
     const int q = warp & 3;
     const int m = q * 32 + lane;
+    const float* s_add = build_addend_table(p, s_add_addr, b, n0, threadIdx.x - 64);
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tcgen05_fence_after();
     if (threadIdx.x == 64) CSD_TS(5);
@@ -431,7 +477,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const int h = h0 + kHaloTH * tt + m / kHaloTW, w = w0 + m % kHaloTW;
       const bool valid = (h < p.H) && (w < p.W);
       const long long pix = ((long long)b * p.H + h) * p.W + w;
-      epilogue_rows(p, tmem_base + ((uint32_t)(q * 32) << 16) + tt * p.n_tile, valid, pix, b, n0, 0);
+      epilogue_rows(p, tmem_base + ((uint32_t)(q * 32) << 16) + tt * p.n_tile, valid, pix, b, n0, 0, s_add);
     }
     if (threadIdx.x == 64) CSD_TS(6);
   }
@@ -441,6 +487,245 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   if (warp == 1) {
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (lane == 0) CSD_TS(7);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Transposed halo mode ("weights are the M operand") for 3x3 stride-1 convolutions.
+//
+// tcgen05.mma with cta_group::1 costs ~100 cycles per M=128 instruction however small N is (measured,
+// tools/mma_rate_probe.cu: N=96 -> 101 cycles, N=256 -> 128 cycles), so with pixels on M a 96-channel
+// layer can use at most 47% of the tensor pipe. Here the roles are swapped: D^T[c_out, pixel] with
+// M = 128 output channels (rows of the weight slab, zero rows beyond C_out come from TMA's
+// out-of-bounds fill) and N = 256 pixels (a 32 x 8 pixel macro-tile). The pixel operand is the same
+// single halo buffer as in conv_halo_kernel - (32+2) x 10 pixels, one TMA box per 32-channel chunk -
+// addressed per tap by a shifted descriptor (SBO = 10 rows). One instruction then does 128 x 256 x 16
+// MACs in 128 cycles.
+// Epilogue: TMEM lane = output channel, column = pixel; bias / temb are per-lane scalars, the
+// per-channel GroupNorm partial sums of the stored output are free per-thread accumulations.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTPix = 256;      // pixels per CTA (N of the MMA)
+constexpr int kTRows = 32;      // image rows per macro tile
+constexpr int kTChan = 128;     // output channels per CTA (M of the MMA)
+
+__global__ void __launch_bounds__(kConvThreads)
+conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                   const __grid_constant__ CUtensorMap mapB, const ConvGemmKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;                                   // pixel halos
+  const uint32_t b_base = smem_base + p.a_stages * p.a_stage_bytes;    // weight slabs
+  const uint32_t bar_base = b_base + p.b_stages * p.b_stage_bytes;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (kMaxAStages + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + kMaxBStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages);
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x;
+  const int tw = t % p.tiles_w;
+  const int th = (t / p.tiles_w) % p.tiles_h;
+  const int b = t / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * kHaloTW, h0 = th * kTRows;
+  const int n0 = blockIdx.y * kTChan;
+  if (threadIdx.x == 0) CSD_TS(0);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&mapA0);
+    ptx::prefetch_tensormap(&mapB);
+    for (int s = 0; s < p.a_stages; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, kTPix);
+    ptx::tmem_relinquish();
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ia = 0, ib = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
+        const int taps = p.seg_taps[s];
+        const int halo = (taps == 9) ? 1 : 0;
+        const uint32_t a_bytes = (uint32_t)((kHaloTW + 2 * halo) * (kTRows + 2 * halo) * kRowBytes);
+        const int nchunks = p.seg_chunks[s];
+        for (int c = 0; c < nchunks; ++c, ++ia) {
+          const int sa = ia % p.a_stages;
+          ptx::mbar_wait(a_empty(sa), ((ia / p.a_stages) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(a_full(sa), a_bytes);
+          ptx::tma_load_4d(a_base + sa * p.a_stage_bytes, mapA, a_full(sa), p.seg_coff[s] + c * kChunkK, w0 - halo,
+                           h0 - halo, b);
+          for (int tap = 0; tap < taps; ++tap, ++ib) {
+            const int sb = ib % p.b_stages;
+            ptx::mbar_wait(b_empty(sb), ((ib / p.b_stages) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(b_full(sb), kTChan * kRowBytes);
+            const int kidx = p.seg_kbase[s] + tap * nchunks + c;
+            ptx::tma_load_3d(b_base + sb * p.b_stage_bytes, &mapB, b_full(sb), p.wt_k_off + kidx * kChunkK, n0, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)kTPix);
+      int ia = 0, ib = 0;
+      uint32_t accumulate = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const int taps = p.seg_taps[s];
+        const int halo = (taps == 9) ? 1 : 0;
+        const int pitch = kHaloTW + 2 * halo;
+        const uint32_t sbo = (uint32_t)pitch * kRowBytes;
+        for (int c = 0; c < p.seg_chunks[s]; ++c, ++ia) {
+          const int sa = ia % p.a_stages;
+          ptx::mbar_wait(a_full(sa), (ia / p.a_stages) & 1);
+          ptx::tcgen05_fence_after();
+          if (ia == 0) CSD_TS(3);
+          if (ia == 1) CSD_TS(8);
+          const uint32_t px_addr = a_base + sa * p.a_stage_bytes;
+          for (int tap = 0; tap < taps; ++tap, ++ib) {
+            const int sb = ib % p.b_stages;
+            ptx::mbar_wait(b_full(sb), (ib / p.b_stages) & 1);
+            ptx::tcgen05_fence_after();
+            const uint32_t w_addr = b_base + sb * p.b_stage_bytes;
+            const int dy = halo ? tap / 3 : 0, dx = halo ? tap % 3 : 0;
+            const uint32_t px_tap = px_addr + (uint32_t)((dy * pitch + dx) * kRowBytes);
+#pragma unroll
+            for (int kk = 0; kk < kChunkK / 16; ++kk) {
+              const uint64_t w_desc = ptx::make_smem_desc(w_addr + kk * 32, 16, 512, kLayoutSw64);   // M operand
+              const uint64_t x_desc = ptx::make_smem_desc(px_tap + kk * 32, 16, sbo, kLayoutSw64);   // N operand
+              ptx::mma_bf16_ss(tmem_base, w_desc, x_desc, idesc, (accumulate || kk > 0) ? 1u : 0u);
+            }
+            accumulate = 1;
+            ptx::mma_commit(b_empty(sb));
+          }
+          ptx::mma_commit(a_empty(sa));
+        }
+      }
+      CSD_TS(4);
+      ptx::mma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue =====
+    // Phase A: TMEM lane = output channel, column = pixel. Each thread adds its channel's bias + temb,
+    //          rounds to bf16 and writes stage[pixel][channel] into the (now idle) operand rings: a
+    //          warp writes 32 consecutive channels of one pixel = 64 contiguous bytes, conflict free.
+    // Phase B: the staged tile is read back as 16-byte channel vectors, pixel-major, so residual loads
+    //          and output stores are fully coalesced NHWC rows; scale, residual and the per-channel
+    //          GroupNorm partial sums are applied here.
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;                  // 0..127
+    const int cl = q * 32 + lane;                     // channel inside the CTA's 128-channel block
+    const int c = n0 + cl;
+    const int cb = min(kTChan, p.n_store - n0);       // channels of this block that are stored (multiple of 8)
+    const bool c_valid = cl < cb;
+    const float add_c = c_valid ? ((p.bias != nullptr ? __ldg(p.bias + c) : 0.f) +
+                                   (p.temb != nullptr ? __ldg(p.temb + (long long)b * p.temb_pitch + c) : 0.f))
+                                : 0.f;
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tcgen05_fence_after();
+    if (threadIdx.x == 64) CSD_TS(5);
+    const int spitch = cb;                            // staging row pitch in elements
+    __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(__cvta_shared_to_generic(smem_base));
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int col = 0; col < kTPix; col += 32) {
+      uint32_t r0[16], r1[16];
+      __syncwarp();
+      ptx::tmem_ld_x16(t_row + col, r0);
+      ptx::tmem_ld_x16(t_row + col + 16, r1);
+      ptx::tmem_ld_wait();
+      if (c_valid) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          stage[(col + i) * spitch + cl] = __float2bfloat16_rn(__uint_as_float(r0[i]) + add_c);
+          stage[(col + 16 + i) * spitch + cl] = __float2bfloat16_rn(__uint_as_float(r1[i]) + add_c);
+        }
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // Phase B
+    const int V = cb >> 3;                            // 16-byte vectors per pixel
+    const int ppass = min(128 / V, 16);               // pixels handled per pass (bounds the reduction scratch)
+    const int v = et % V, pl = et / V;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+    if (pl < ppass) {
+      const bf16x8* stage_v = reinterpret_cast<const bf16x8*>(stage);
+      for (int m = pl; m < kTPix; m += ppass) {
+        const int h = h0 + m / kHaloTW, w = w0 + m % kHaloTW;
+        if (h < p.H && w < p.W) {
+          const long long pix = ((long long)b * p.H + h) * p.W + w;
+          float f[8];
+          unpack8(stage_v[m * V + v], f);
+          if (p.res != nullptr) {
+            float rr[8];
+            bf16x8 rv;
+            *reinterpret_cast<uint4*>(&rv) = __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch + n0) + v);
+            unpack8(rv, rr);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += rr[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] *= p.scale;
+          const bf16x8 o = pack8(f);
+          reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_pitch + n0)[v] =
+              *reinterpret_cast<const uint4*>(&o);
+          if (p.stat_partials != nullptr) {
+            float g[8];
+            unpack8(o, g);   // statistics of exactly what the consumer will read
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              s1[i] += g[i];
+              s2[i] = fmaf(g[i], g[i], s2[i]);
+            }
+          }
+        }
+      }
+    }
+    if (p.stat_partials != nullptr) {
+      // reduce the ppass partial rows per channel vector through shared memory (after the staging tile)
+      float* red = reinterpret_cast<float*>(__cvta_shared_to_generic(smem_base + kTPix * kTChan * 2));
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // staging reads done (red may not alias, but keep order)
+      if (pl < ppass) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          red[(pl * kTChan + v * 8 + i) * 2] = s1[i];
+          red[(pl * kTChan + v * 8 + i) * 2 + 1] = s2[i];
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < cb) {
+        float a1 = 0.f, a2 = 0.f;
+        for (int r = 0; r < ppass; ++r) {
+          a1 += red[(r * kTChan + et) * 2];
+          a2 += red[(r * kTChan + et) * 2 + 1];
+        }
+        float* sp = p.stat_partials + ((long long)blockIdx.x * p.n_store + n0 + et) * 2;
+        sp[0] = a1;
+        sp[1] = a2;
+      }
+    }
+    if (threadIdx.x == 64) CSD_TS(6);
+  }
+
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTPix);
     if (lane == 0) CSD_TS(7);
   }
 }
@@ -459,21 +744,26 @@ struct ConvGemmLaunch {
   dim3 grid;
   size_t smem;
   bool halo;
+  bool transposed;
 };
 
 int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   CSD_REQUIRE(d != nullptr, "null conv_gemm desc");
   CSD_REQUIRE(d->nseg >= 1 && d->nseg <= CSD_MAX_SEGMENTS, "nseg=%d out of range", d->nseg);
   CSD_REQUIRE(d->batch >= 1 && d->h >= 1 && d->w >= 1, "bad spatial dims %d %d %d", d->batch, d->h, d->w);
-  const bool halo_mode = d->mode == 1;
+  const bool t_mode = d->mode == 2;
+  const bool halo_mode = d->mode == 1 || t_mode;
   L->halo = halo_mode;
-  const int mt = halo_mode ? (d->mt > 0 ? d->mt : 1) : 1;
+  L->transposed = t_mode;
+  const int mt = t_mode ? 2 : (halo_mode ? (d->mt > 0 ? d->mt : 1) : 1);
   CSD_REQUIRE(halo_mode || (d->tile_w >= 1 && d->tile_h >= 1 && d->tile_b >= 1 &&
                             d->tile_w * d->tile_h * d->tile_b <= kTileM),
               "tile box %dx%dx%d exceeds 128 pixels", d->tile_w, d->tile_h, d->tile_b);
   CSD_REQUIRE(!halo_mode || (d->z_batches == 1 && (d->stride <= 1) && d->pad == 1 && mt >= 1 && mt <= 4 &&
-                             mt * d->n_tile <= 512),
+                             (t_mode || mt * d->n_tile <= 512)),
               "halo mode needs stride 1, pad 1, no z batching and mt*n_tile <= 512 (mt=%d n_tile=%d)", mt, d->n_tile);
+  CSD_REQUIRE(!t_mode || (d->out_f32 == 0 && d->bias_per_row == 0),
+              "transposed halo mode writes bf16 with per-channel bias only");
   CSD_REQUIRE(d->n_tile >= 16 && d->n_tile % 16 == 0 && d->n_tile <= 512, "n_tile=%d invalid", d->n_tile);
   CSD_REQUIRE(d->n >= 1 && d->n_store >= 1, "n=%d n_store=%d invalid", d->n, d->n_store);
   CSD_REQUIRE(d->out != nullptr && d->wt != nullptr, "null out / wt pointer");
@@ -509,7 +799,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   CSD_REQUIRE(d->wt_rows >= 1, "wt_rows=%d", d->wt_rows);
   p.wt_k_off = d->wt_k_off;
   p.a_batch_step = d->a_batch_step;
-  p.tmem_cols = next_pow2_cols(d->n_tile * mt);
+  p.tmem_cols = t_mode ? kTPix : next_pow2_cols(d->n_tile * mt);
 
   int k_total = 0;
   for (int s = 0; s < d->nseg; ++s) {
@@ -552,7 +842,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     const uint64_t row_bytes = (uint64_t)(d->wt_pitch > 0 ? d->wt_pitch : d->k_total) * 2;
     uint64_t strides[2] = {row_bytes, d->wt_batch_stride != 0 ? (uint64_t)d->wt_batch_stride * 2
                                                                : row_bytes * (uint64_t)d->wt_rows};
-    uint32_t box[3] = {(uint32_t)kChunkK, (uint32_t)p.n_sub, 1};
+    uint32_t box[3] = {(uint32_t)kChunkK, (uint32_t)(t_mode ? kTChan : p.n_sub), 1};
     int st = encode_tensor_map(&L->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, d->wt, dims, strides, box,
                                TMA_SW_64);
     if (st != CSD_OK) return st;
@@ -585,10 +875,10 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   CSD_REQUIRE(d->res == nullptr || d->res_pitch % 8 == 0, "res_pitch=%d must be a multiple of 8", d->res_pitch);
 
   L->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * tiles_b), (unsigned)n_tiles, (unsigned)d->z_batches);
-  L->smem = (size_t)stages * p.stage_bytes + 1024 /*alignment slack*/ + 8 * (2 * kMaxStages + 2);
+  L->smem = (size_t)stages * p.stage_bytes + 1024 /*alignment slack*/ + 8 * (2 * kMaxStages + 2) + 4 * 512;
   if (halo_mode) {
     p.a_stage_bytes = (uint32_t)(((kHaloTW + 2) * (kHaloTH * mt + 2) * kRowBytes + 1023) & ~1023);
-    p.b_stage_bytes = (uint32_t)((d->n_tile * kRowBytes + 1023) & ~1023);
+    p.b_stage_bytes = (uint32_t)(((t_mode ? kTChan : d->n_tile) * kRowBytes + 1023) & ~1023);
     // two CTAs per SM when TMEM allows it (<= 256 columns): keep each under ~110 KB
     const int budget_h = p.tmem_cols <= 256 ? 108 * 1024 : 200 * 1024;
     p.a_stages = 2;
@@ -603,8 +893,11 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     CSD_REQUIRE(bs >= 2, "halo mode: not enough shared memory for the weight ring (n_tile=%d mt=%d)", d->n_tile, mt);
     p.b_stages = bs;
     L->smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 +
-              8 * (2 * kMaxAStages + 2 * kMaxBStages + 2);
+              8 * (2 * kMaxAStages + 2 * kMaxBStages + 2) + 4 * 512;
+    if (t_mode) L->grid.y = (unsigned)ceil_div(d->n_store, kTChan);
   }
+  p.stat_partials = t_mode ? d->stat_partials : nullptr;
+  CSD_REQUIRE(d->stat_partials == nullptr || t_mode, "stat_partials are produced by the transposed halo mode only");
   CSD_REQUIRE(L->smem <= 227 * 1024, "shared memory %zu exceeds 227 KB", L->smem);
   // If z batches share the weights the z coordinate of the weight map must stay 0.
   if (d->wt_batch_stride == 0 && d->z_batches > 1) {
@@ -618,9 +911,13 @@ int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
   if (!attr_set) {
     CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CSD_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(conv_halo_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  if (L->halo) {
+  if (L->transposed) {
+    conv_halo_t_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
+                                                                   L->mapB, L->p);
+  } else if (L->halo) {
     conv_halo_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
                                                                  L->mapB, L->p);
   } else {

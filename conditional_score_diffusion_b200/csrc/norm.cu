@@ -172,7 +172,7 @@ static int gn_fill(GnParams& p, const void* src0, int c0, int pitch0, const void
   const int ppb = std::max(1, 256 / V);
   *threads = V * ppb;
   *smem = sizeof(float) * 2 * C;
-  int slabs = ceil_div(num_sms() * 8, batch);
+  int slabs = ceil_div(num_sms() * 16, batch);
   const int max_slabs = std::max(1, hw / (ppb * 8));
   p.slabs = std::max(1, std::min(slabs, max_slabs));
   return CSD_OK;

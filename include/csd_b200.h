@@ -189,7 +189,8 @@ typedef struct csd_conv_gemm_desc {
                                    (DDPM Downsample pads bottom/right: TMA zero-fills it)   */
   int32_t tile_w, tile_h, tile_b; /* pixel box per CTA, product <= 128 (ignored in halo mode) */
   int32_t mode;                 /* 0 = one TMA box per tap; 1 = halo: 16x8-pixel tiles, one halo load per
-                                   32-channel chunk feeds all 9 taps (3x3, stride 1, pad 1 only)   */
+                                   32-channel chunk feeds all 9 taps (3x3, stride 1, pad 1 only);
+                                   2 = transposed halo: M = 128 output channels, N = 32x8 pixels     */
   int32_t mt;                   /* halo mode: vertically stacked tiles per CTA (1..4), mt*n_tile <= 512 */
   int32_t nseg;
   int32_t n;                    /* output columns computed (rows of Wt used)             */
@@ -217,6 +218,8 @@ typedef struct csd_conv_gemm_desc {
   int32_t res_pitch;
   int64_t res_z_stride;
   float scale;
+  float* stat_partials;         /* mode 2 only: [pixel tiles, n_store, 2] per-tile per-channel (sum, sum of
+                                   squares) of the stored bf16 output (GroupNorm statistics), or NULL */
 } csd_conv_gemm_desc;
 
 int csd_conv_gemm(const csd_conv_gemm_desc* desc, csd_stream_t stream);

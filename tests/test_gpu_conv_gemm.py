@@ -73,7 +73,7 @@ def _conv_case(name, B, H, W, cin, cout, taps=9, bias=True, temb=False, res=Fals
                      dtype=torch.float32 if out_f32 else torch.bfloat16)
     k.conv_gemm([(a, c_pitch, 0, cin, taps)], wt, cout, out, batch=B, h=H, w=W, n_store=n_store,
                 bias=bias_t, temb=temb_t, temb_pitch=(npad + 16), res=res_t, res_pitch=out_pitch,
-                scale=scale, tile=tile, n_tile=n_tile)
+                scale=scale, tile=tile, n_tile=n_tile, transposed=False)
     torch.cuda.synchronize()
     got = out[..., :cout].permute(0, 3, 1, 2)
     assert torch.isfinite(out[..., :n_store].float()).all(), f"{name}: non-finite outputs"
@@ -313,8 +313,8 @@ def test_halo_vs_tap_timing():
         wt = k.pack_conv_weight((torch.randn(cout, cin, 3, 3, device=dev) / 30).to(torch.bfloat16))
         out = torch.empty(B, H, H, cout, device=dev, dtype=torch.bfloat16)
         flops = 2.0 * B * H * H * cin * cout * 9
-        for label, kw in [("tap", dict(halo=False)), ("halo mt=1", dict(halo=True, mt=1)), ("halo mt=2", dict(halo=True, mt=2)),
-                          ("halo mt=4", dict(halo=True, mt=4))]:
+        for label, kw in [("tap", dict(halo=False, transposed=False)), ("halo mt=1", dict(halo=True, mt=1)),
+                          ("halo mt=2", dict(halo=True, mt=2)), ("halo mt=4", dict(halo=True, mt=4))]:
             if kw.get("mt", 1) * k.ceil_to(cout, 16) > 512:
                 continue
             for _ in range(2):
@@ -323,6 +323,103 @@ def test_halo_vs_tap_timing():
             e0.record()
             for _ in range(5):
                 k.conv_gemm([(a, cin, 0, cin, 9)], wt, cout, out, batch=B, h=H, w=H, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            print(f"[conv timing] {H}x{H} {cin}->{cout} {label:10s}: {ms:.3f} ms  {flops / ms / 1e9:.0f} TFLOP/s")
+
+
+def _t_case(name, B, H, W, cin, cout, seed=0, temb=True, res=True, stats=True):
+    """Transposed halo mode (weights = M operand, 256 pixels = N) against torch fp32."""
+    k = _kern()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.randn(B, cin, H, W, device=dev, generator=g).to(torch.bfloat16)
+    wgt = (torch.randn(cout, cin, 3, 3, device=dev, generator=g) / math.sqrt(9 * cin)).to(torch.bfloat16)
+    npad = k.ceil_to(cout, 16)
+    wt = k.pack_conv_weight(wgt, n_pad=npad)
+    bias = torch.zeros(npad + 16, device=dev)
+    bias[:cout] = torch.randn(cout, device=dev, generator=g)
+    ref = F.conv2d(x.float(), wgt.float(), padding=1) + bias[:cout].view(1, -1, 1, 1)
+    temb_t = res_t = None
+    if temb:
+        temb_t = torch.zeros(B, npad + 16, device=dev)
+        temb_t[:, :cout] = torch.randn(B, cout, device=dev, generator=g)
+        ref = ref + temb_t[:, :cout].reshape(B, cout, 1, 1)
+    if res:
+        r = torch.randn(B, cout, H, W, device=dev, generator=g).to(torch.bfloat16)
+        res_t = _nhwc(r)
+        ref = ref + r.float()
+    ref = ref * 0.5
+    n_store = k.ceil_to(cout, 8)
+    out = torch.full((B, H, W, n_store), float("nan"), device=dev, dtype=torch.bfloat16)
+    tiles = B * math.ceil(H / 32) * math.ceil(W / 8)
+    partials = torch.full((tiles, n_store, 2), float("nan"), device=dev) if stats else None
+    k.conv_gemm([(_nhwc(x), cin, 0, cin, 9)], wt, cout, out, batch=B, h=H, w=W, n_store=n_store, bias=bias, temb=temb_t,
+                temb_pitch=npad + 16, res=res_t, res_pitch=cout, scale=0.5, transposed=True, stat_partials=partials)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all(), f"{name}: non-finite"
+    rel = _report(name, out[..., :cout].permute(0, 3, 1, 2), ref, T_RTOL)
+    if stats:
+        tp = tiles // B
+        ps = partials.view(B, tp, n_store, 2).sum(1)
+        o32 = out.float().reshape(B, H * W, n_store)
+        assert torch.allclose(ps[..., 0], o32.sum(1), rtol=1e-4, atol=1e-2), f"{name}: channel sums"
+        assert torch.allclose(ps[..., 1], (o32 * o32).sum(1), rtol=1e-4, atol=1e-2), f"{name}: channel sums of squares"
+    return rel
+
+
+# The transposed epilogue stages (acc + bias + temb) as bf16 before the residual add and the final
+# bf16 store: two roundings instead of one, hence 2^-7 instead of 2^-8.
+T_RTOL = 2.0 ** -7
+
+
+def test_transposed_halo_mode():
+    assert _t_case("T 96->96 32x32", 2, 32, 32, 96, 96) < T_RTOL
+    assert _t_case("T 96->96 80x80 (ragged h)", 2, 80, 80, 96, 96) < T_RTOL
+    assert _t_case("T 192->192 40x40 (2 channel blocks)", 3, 40, 40, 192, 192) < T_RTOL
+    assert _t_case("T 64->96 24x20 (ragged w)", 2, 24, 20, 64, 96) < T_RTOL
+    assert _t_case("T 96->6 32x32 (tiny cout)", 2, 32, 32, 96, 6, temb=False, res=False) < T_RTOL
+    assert _t_case("T 8->96 32x32 (padded cin)", 2, 32, 32, 8, 96, res=False) < T_RTOL
+    assert _t_case("T 288->288 16x16", 2, 16, 16, 288, 288) < T_RTOL
+
+
+def test_transposed_segments_and_skip():
+    k = _kern()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(35)
+    B, H, W, c1, c2, cs, cout = 2, 32, 32, 96, 64, 160, 96
+    a1 = torch.randn(B, c1, H, W, device=dev, generator=g).to(torch.bfloat16)
+    a2 = torch.randn(B, c2, H, W, device=dev, generator=g).to(torch.bfloat16)
+    xs = torch.randn(B, cs, H, W, device=dev, generator=g).to(torch.bfloat16)
+    w3 = (torch.randn(cout, c1 + c2, 3, 3, device=dev, generator=g) / math.sqrt(9 * (c1 + c2))).to(torch.bfloat16)
+    w1 = (torch.randn(cout, cs, 1, 1, device=dev, generator=g) / math.sqrt(cs)).to(torch.bfloat16)
+    ref = F.conv2d(torch.cat([a1, a2], 1).float(), w3.float(), padding=1) + F.conv2d(xs.float(), w1.float())
+    wt = torch.cat([k.pack_conv_weight(w3[:, :c1]), k.pack_conv_weight(w3[:, c1:]), k.pack_conv_weight(w1)], dim=1).contiguous()
+    out = torch.empty(B, H, W, cout, device=dev, dtype=torch.bfloat16)
+    k.conv_gemm([(_nhwc(a1), c1, 0, c1, 9), (_nhwc(a2), c2, 0, c2, 9), (_nhwc(xs), cs, 0, cs, 1)], wt, cout, out,
+                batch=B, h=H, w=W, transposed=True)
+    torch.cuda.synchronize()
+    assert _report("T 2 segments + skip", out.permute(0, 3, 1, 2), ref, T_RTOL) < T_RTOL
+
+
+def test_transposed_timing():
+    k = _kern()
+    dev = "cuda"
+    for (B, H, cin, cout) in [(64, 160, 96, 96), (64, 160, 192, 96), (64, 80, 96, 96), (64, 80, 192, 192), (64, 40, 192, 192),
+                              (64, 160, 96, 6)]:
+        a = torch.randn(B, H, H, cin, device=dev).to(torch.bfloat16)
+        wt = k.pack_conv_weight((torch.randn(cout, cin, 3, 3, device=dev) / 30).to(torch.bfloat16))
+        ns = k.ceil_to(cout, 8)
+        out = torch.empty(B, H, H, ns, device=dev, dtype=torch.bfloat16)
+        flops = 2.0 * B * H * H * cin * cout * 9
+        for label, kw in [("tap", dict(halo=False, transposed=False)), ("transposed", dict(transposed=True))]:
+            for _ in range(2):
+                k.conv_gemm([(a, cin, 0, cin, 9)], wt, cout, out, batch=B, h=H, w=H, n_store=ns, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                k.conv_gemm([(a, cin, 0, cin, 9)], wt, cout, out, batch=B, h=H, w=H, n_store=ns, **kw)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5

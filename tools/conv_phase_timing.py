@@ -9,7 +9,7 @@ a = torch.randn(B, H, H, cin, device="cuda").to(torch.bfloat16)
 wt = k.pack_conv_weight((torch.randn(cout, cin, 3, 3, device="cuda") / 30).to(torch.bfloat16))
 out = torch.empty(B, H, H, cout, device="cuda", dtype=torch.bfloat16)
 names = ["start", "setup done", "-", "first full", "mma issued", "epi start", "epi end", "dealloc", "mid"]
-for label, kw in [("tap", dict(halo=False)), ("halo mt=1", dict(halo=True, mt=1)), ("halo mt=2", dict(halo=True, mt=2))]:
+for label, kw in [("tap", dict(halo=False)), ("halo mt=2", dict(halo=True, mt=2)), ("transposed", dict(transposed=True))]:
     for rep in range(2):
         ts.zero_()
         k.conv_gemm([(a, cin, 0, cin, 9)], wt, cout, out, batch=B, h=H, w=H, **kw)
