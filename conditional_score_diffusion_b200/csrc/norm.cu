@@ -18,7 +18,8 @@ struct GnParams {
   int v0, v1;          // 8-channel vectors taken from each source
   int pv0, pv1;        // pitch of each source in vectors
   int batch, hw, groups, cpg;
-  float* sums;         // [batch, groups, 2]
+  float* sums0;        // per-channel (sum, sum of squares): [batch, c0, 2]
+  float* sums1;        //                                     [batch, c1, 2]
   const float* gamma;
   const float* beta;
   bf16x8* out;
@@ -33,10 +34,13 @@ __device__ __forceinline__ bf16x8 gn_load(const GnParams& p, int b, long long pi
   return p.src1[((long long)b * p.hw + pix) * p.pv1 + (v - p.v0)];
 }
 
-// grid = batch * slabs; block = V * PPB threads (V = vectors per pixel). Dynamic smem: 2*C floats.
-__global__ void gn_stats_kernel(GnParams p) {
+// Per-channel statistics of ONE tensor. grid = batch * slabs; block = V * PPB threads (V = vectors per
+// pixel). Dynamic smem: 2*C floats. Each tensor's sums are computed once and shared by every GroupNorm
+// that reads the tensor (the down-path activations are normalised twice: by the next block and, through
+// the skip concatenation, by the up path).
+__global__ void gn_chan_stats_kernel(GnParams p) {
   extern __shared__ float sm[];
-  const int V = p.v0 + p.v1, C = V * 8;
+  const int V = p.v0, C = V * 8;
   float* csum = sm;
   float* csq = sm + C;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
@@ -50,9 +54,8 @@ __global__ void gn_stats_kernel(GnParams p) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (pp < ppb) {
-    // 4 independent 16-byte loads in flight per thread (HBM latency hiding)
     long long pix = lo + pp;
-    for (; pix + 3LL * ppb < hi; pix += 4LL * ppb) {
+    for (; pix + 3LL * ppb < hi; pix += 4LL * ppb) {   // 4 independent 16-byte loads in flight
       bf16x8 v4[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) v4[u] = gn_load(p, b, pix + (long long)u * ppb, v);
@@ -83,35 +86,56 @@ __global__ void gn_stats_kernel(GnParams p) {
     }
   }
   __syncthreads();
-  for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
-    float a = 0.f, c = 0.f;
-    for (int i = 0; i < p.cpg; ++i) {
-      a += csum[g * p.cpg + i];
-      c += csq[g * p.cpg + i];
-    }
-    atomicAdd(p.sums + ((long long)b * p.groups + g) * 2, a);
-    atomicAdd(p.sums + ((long long)b * p.groups + g) * 2 + 1, c);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(p.sums0 + ((long long)b * C + c) * 2, csum[c]);
+    atomicAdd(p.sums0 + ((long long)b * C + c) * 2 + 1, csq[c]);
   }
 }
 
-// Same decomposition; per-channel scale/shift are built once per CTA in shared memory.
+// chan_sums[b, c] = sum over the image's pixel tiles of the per-tile partial sums written by the
+// transposed convolution epilogue (deterministic: no atomics).
+__global__ void gn_finalize_partials_kernel(const float* __restrict__ partials, float* __restrict__ chan_sums,
+                                            int tiles_per_img, int c2 /* channels * 2 */) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c2) return;
+  const float* p0 = partials + (long long)b * tiles_per_img * c2 + i;
+  float acc = 0.f;
+  for (int t = 0; t < tiles_per_img; ++t) acc += p0[(long long)t * c2];
+  chan_sums[(long long)b * c2 + i] = acc;
+}
+
+// Normalise + affine (+SiLU) over the channel concatenation of up to two tensors; the group statistics
+// are assembled from the tensors' per-channel sums. Dynamic smem: 2*C + 2*G floats.
 __global__ void gn_apply_kernel(GnParams p) {
   extern __shared__ float sm[];
-  const int V = p.v0 + p.v1, C = V * 8;
+  const int V = p.v0 + p.v1, C = V * 8, C0 = p.v0 * 8;
   float* scale = sm;
   float* shift = sm + C;
+  float* gmean = sm + 2 * C;
+  float* grstd = gmean + p.groups;
   const int b = blockIdx.x / p.slabs, slab = blockIdx.x % p.slabs;
   const float inv_n = 1.f / ((float)p.hw * (float)p.cpg);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / p.cpg;
-    const float su = p.sums[((long long)b * p.groups + g) * 2];
-    const float sq = p.sums[((long long)b * p.groups + g) * 2 + 1];
+  for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
+    float su = 0.f, sq = 0.f;
+    for (int i = 0; i < p.cpg; ++i) {
+      const int c = g * p.cpg + i;
+      const float* sp = (c < C0) ? p.sums0 + ((long long)b * C0 + c) * 2
+                                 : p.sums1 + ((long long)b * (C - C0) + (c - C0)) * 2;
+      su += sp[0];
+      sq += sp[1];
+    }
     const float mean = su * inv_n;
     const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + p.eps);
-    const float sc = rstd * p.gamma[c];
+    gmean[g] = mean;
+    grstd[g] = rsqrtf(var + p.eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / p.cpg;
+    const float sc = grstd[g] * p.gamma[c];
     scale[c] = sc;
-    shift[c] = p.beta[c] - mean * sc;
+    shift[c] = p.beta[c] - gmean[g] * sc;
   }
   __syncthreads();
   const int ppb = blockDim.x / V;
@@ -171,7 +195,7 @@ static int gn_fill(GnParams& p, const void* src0, int c0, int pitch0, const void
   p.batch = batch; p.hw = hw; p.groups = groups; p.cpg = C / groups;
   const int ppb = std::max(1, 256 / V);
   *threads = V * ppb;
-  *smem = sizeof(float) * 2 * C;
+  *smem = sizeof(float) * (2 * C + 2 * groups);
   int slabs = ceil_div(num_sms() * 16, batch);
   const int max_slabs = std::max(1, hw / (ppb * 8));
   p.slabs = std::max(1, std::min(slabs, max_slabs));
@@ -317,27 +341,39 @@ dense_rows_kernel(const float* __restrict__ act, const float* __restrict__ w, co
 
 extern "C" {
 
-int csd_gn_stats_bf16(const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1, float* sums,
-                      int batch, int hw, int groups, csd_stream_t stream) {
+int csd_gn_chan_stats_bf16(const void* src, int c, int pitch, float* chan_sums, int batch, int hw,
+                           csd_stream_t stream) {
   using namespace csd;
-  CSD_REQUIRE(sums != nullptr && batch >= 1 && hw >= 1, "gn_stats: bad arguments");
+  CSD_REQUIRE(chan_sums != nullptr && batch >= 1 && hw >= 1, "gn_chan_stats: bad arguments");
   GnParams p;
   memset(&p, 0, sizeof(p));
   int threads;
   size_t smem;
-  int st = gn_fill(p, src0, c0, pitch0, src1, c1, pitch1, batch, hw, groups, &threads, &smem);
+  int st = gn_fill(p, src, c, pitch, nullptr, 0, 0, batch, hw, 1, &threads, &smem);
   if (st != CSD_OK) return st;
-  p.sums = sums;
-  gn_stats_kernel<<<batch * p.slabs, threads, smem, static_cast<cudaStream_t>(stream)>>>(p);
-  CSD_LAUNCH_CHECK("gn_stats_kernel");
+  p.sums0 = chan_sums;
+  gn_chan_stats_kernel<<<batch * p.slabs, threads, sizeof(float) * 2 * c, static_cast<cudaStream_t>(stream)>>>(p);
+  CSD_LAUNCH_CHECK("gn_chan_stats_kernel");
   return CSD_OK;
 }
 
-int csd_gn_apply_bf16(const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1, const float* sums,
-                      const float* gamma, const float* beta, void* out, int out_pitch, int batch, int hw, int groups,
-                      float eps, int apply_silu, csd_stream_t stream) {
+int csd_gn_finalize_partials_f32(const float* partials, float* chan_sums, int batch, int tiles_per_img, int c,
+                                 csd_stream_t stream) {
   using namespace csd;
-  CSD_REQUIRE(sums && gamma && beta && out && batch >= 1 && hw >= 1, "gn_apply: bad arguments");
+  CSD_REQUIRE(partials && chan_sums && batch >= 1 && tiles_per_img >= 1 && c >= 1, "gn_finalize_partials: bad arguments");
+  dim3 grid((unsigned)ceil_div(2 * c, 128), (unsigned)batch);
+  gn_finalize_partials_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(partials, chan_sums, tiles_per_img,
+                                                                                  2 * c);
+  CSD_LAUNCH_CHECK("gn_finalize_partials_kernel");
+  return CSD_OK;
+}
+
+int csd_gn_apply_bf16(const void* src0, int c0, int pitch0, const float* sums0, const void* src1, int c1, int pitch1,
+                      const float* sums1, const float* gamma, const float* beta, void* out, int out_pitch, int batch,
+                      int hw, int groups, float eps, int apply_silu, csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(sums0 && gamma && beta && out && batch >= 1 && hw >= 1, "gn_apply: bad arguments");
+  CSD_REQUIRE(src1 == nullptr || sums1 != nullptr, "gn_apply: second source without its channel sums");
   GnParams p;
   memset(&p, 0, sizeof(p));
   int threads;
@@ -345,7 +381,8 @@ int csd_gn_apply_bf16(const void* src0, int c0, int pitch0, const void* src1, in
   int st = gn_fill(p, src0, c0, pitch0, src1, c1, pitch1, batch, hw, groups, &threads, &smem);
   if (st != CSD_OK) return st;
   CSD_REQUIRE(out_pitch % 8 == 0 && out_pitch >= (p.v0 + p.v1) * 8, "gn_apply: out pitch %d too small", out_pitch);
-  p.sums = const_cast<float*>(sums);
+  p.sums0 = const_cast<float*>(sums0);
+  p.sums1 = const_cast<float*>(sums1);
   p.gamma = gamma; p.beta = beta;
   p.out = static_cast<bf16x8*>(out);
   p.out_pv = out_pitch / 8;

@@ -22,12 +22,13 @@ SQRT1_2 = 1.0 / math.sqrt(2.0)
 
 
 class Act:
-    """NHWC bf16 activation: tensor [B, H, W, pitch] with `c` valid channels."""
+    """NHWC bf16 activation: tensor [B, H, W, pitch] with `c` valid channels and, once some GroupNorm
+    needs them, its per-channel (sum, sum of squares) [B, c, 2]."""
 
-    __slots__ = ("t", "c")
+    __slots__ = ("t", "c", "sums")
 
-    def __init__(self, t, c):
-        self.t, self.c = t, c
+    def __init__(self, t, c, sums=None):
+        self.t, self.c, self.sums = t, c, sums
 
     @property
     def shape(self):
@@ -123,25 +124,34 @@ class BlockOps:
         self.stats_used = 0
 
     # -- helpers -----------------------------------------------------------------------------
-    def _stats_slot(self, batch, groups):
-        n = batch * groups * 2
-        if self.stats_used + n > self.stats.numel():
+    def _stats_slot(self, batch, channels):
+        n = batch * channels * 2
+        n_al = (n + 63) // 64 * 64
+        if self.stats_used + n_al > self.stats.numel():
             raise CsdError("GroupNorm statistics arena too small")
-        s = self.stats[self.stats_used:self.stats_used + n].view(batch, groups, 2)
-        self.stats_used += n
+        s = self.stats[self.stats_used:self.stats_used + n].view(batch, channels, 2)
+        self.stats_used += n_al
         return s
+
+    def ensure_sums(self, a):
+        """Per-channel sums of a tensor: produced by the convolution that wrote it when that ran in the
+        transposed mode, otherwise by one statistics pass - in both cases once per tensor."""
+        if a.sums is None:
+            a.sums = self._stats_slot(a.shape[0], a.c)
+            self.rec.add(K.gn_chan_stats, a.t, a.c, a.sums)
+        return a.sums
 
     def group_norm(self, srcs, gamma, beta, silu):
         """srcs: list of 1 or 2 Act (channel concatenation). Returns a new Act."""
         b, h, w, _ = srcs[0].shape
         c = sum(a.c for a in srcs)
         groups = _groups(c)
-        sums = self._stats_slot(b, groups)
         s0 = srcs[0]
         s1 = srcs[1] if len(srcs) > 1 else None
+        sums0 = self.ensure_sums(s0)
+        sums1 = self.ensure_sums(s1) if s1 is not None else None
         out = self.pool.get((b, h, w, c))
-        self.rec.add(K.gn_stats, s0.t, s0.c, s1.t if s1 else None, s1.c if s1 else 0, sums, groups)
-        self.rec.add(K.gn_apply, s0.t, s0.c, s1.t if s1 else None, s1.c if s1 else 0, sums, gamma, beta, out,
+        self.rec.add(K.gn_apply, s0.t, s0.c, sums0, s1.t if s1 else None, s1.c if s1 else 0, sums1, gamma, beta, out,
                      groups, 1e-6, silu)
         return Act(out, c)
 
@@ -154,11 +164,21 @@ class BlockOps:
         if out is None:
             out = self.pool.get((b, oh, ow, pc.n_store))
         seg_list = [(a.t, a.pitch, 0, a.c, taps) for a, taps in segs]
+        use_t = (K.TRANSPOSED_DEFAULT and pc.cout >= 32 and K.transposed_eligible(seg_list, oh, ow, stride, pad))
+        partials = sums = None
+        if use_t and pc.cout % 8 == 0:
+            # GroupNorm statistics of the output for free: per-tile partial sums from the epilogue
+            tiles_img = math.ceil(oh / 32) * math.ceil(ow / 8)
+            partials = self.pool.get((b * tiles_img, pc.n_store, 2), torch.float32)
+            sums = self._stats_slot(b, pc.cout)
         self.rec.add(K.conv_gemm, seg_list, pc.wt, pc.cout, out, batch=b, h=oh, w=ow, n_store=pc.n_store,
                      n_tile=pc.n_tile, bias=pc.bias, temb=temb, temb_pitch=temb_pitch,
                      res=res.t if res is not None else None, res_pitch=res.pitch if res is not None else 0,
-                     scale=scale, stride=stride, pad=pad, in_h=ih, in_w=iw)
-        return Act(out, pc.cout)
+                     scale=scale, stride=stride, pad=pad, in_h=ih, in_w=iw, transposed=use_t, stat_partials=partials)
+        if partials is not None:
+            self.rec.add(K.gn_finalize_partials, partials, sums, b, tiles_img, pc.cout)
+            self.pool.put(partials)
+        return Act(out, pc.cout, sums)
 
     def fir(self, a, mode, taps, add=None):
         b, h, w, p = a.shape
@@ -398,7 +418,7 @@ class NetPlan:
         self.batch, self.h, self.w = batch, h, w
         self.rec = Recorder()
         self.pool = BufferPool(dev)
-        self.stats = torch.zeros(4 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+        self.stats = torch.zeros(48 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
         ops = BlockOps(dev, self.pool, self.rec, self.stats)
         rec = self.rec
         mods, pk = net.all_modules, P["mods"]

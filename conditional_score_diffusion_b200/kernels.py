@@ -278,20 +278,24 @@ def nhwc_to_nchw(src, c_off, c_cnt, dst, row_scale=None):
     return dst
 
 
-def gn_stats(src0, c0, src1, c1, sums, groups):
-    """src tensors [B, H, W, pitch] (or [B, HW, pitch]); sums [B, groups, 2] fp32, pre-zeroed."""
-    b = src0.shape[0]
-    hw = src0.numel() // (b * src0.shape[-1])
-    check(_lib.lib().csd_gn_stats_bf16(_ptr(src0), c0, src0.shape[-1], _ptr(src1), c1,
-                                       src1.shape[-1] if src1 is not None else 0, _ptr(sums), b, hw, groups, _stream()))
-    return sums
+def gn_chan_stats(src, c, chan_sums):
+    """src [B, H, W, pitch] (or [B, HW, pitch]) bf16; chan_sums [B, c, 2] fp32, pre-zeroed."""
+    b = src.shape[0]
+    hw = src.numel() // (b * src.shape[-1])
+    check(_lib.lib().csd_gn_chan_stats_bf16(_ptr(src), c, src.shape[-1], _ptr(chan_sums), b, hw, _stream()))
+    return chan_sums
 
 
-def gn_apply(src0, c0, src1, c1, sums, gamma, beta, out, groups, eps=1e-6, silu=True):
+def gn_finalize_partials(partials, chan_sums, batch, tiles_per_img, c):
+    check(_lib.lib().csd_gn_finalize_partials_f32(_ptr(partials), _ptr(chan_sums), batch, tiles_per_img, c, _stream()))
+    return chan_sums
+
+
+def gn_apply(src0, c0, sums0, src1, c1, sums1, gamma, beta, out, groups, eps=1e-6, silu=True):
     b = src0.shape[0]
     hw = src0.numel() // (b * src0.shape[-1])
-    check(_lib.lib().csd_gn_apply_bf16(_ptr(src0), c0, src0.shape[-1], _ptr(src1), c1,
-                                       src1.shape[-1] if src1 is not None else 0, _ptr(sums), _ptr(gamma), _ptr(beta),
+    check(_lib.lib().csd_gn_apply_bf16(_ptr(src0), c0, src0.shape[-1], _ptr(sums0), _ptr(src1), c1,
+                                       src1.shape[-1] if src1 is not None else 0, _ptr(sums1), _ptr(gamma), _ptr(beta),
                                        _ptr(out), out.shape[-1], b, hw, groups, float(eps), int(silu), _stream()))
     return out
 

@@ -125,17 +125,25 @@ int csd_nchw_to_nhwc_bf16(const float* src0, int c0, const float* src1, int c1, 
 int csd_nhwc_bf16_to_nchw(const void* src, int c_pitch, int c_off, int c_cnt, float* dst, int batch,
                           int h, int w, const float* row_scale, csd_stream_t stream);
 
-/* GroupNorm statistics over the channel-concatenation of up to two NHWC bf16 tensors
- * (torch.cat + nn.GroupNorm of models/layerspp.py:219,242; models/ncsnpp.py:325).
- * sums[b, g, 0..1] += (sum x, sum x^2); the caller zeroes `sums` beforehand.                   */
-int csd_gn_stats_bf16(const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1,
-                      float* sums, int batch, int hw, int groups, csd_stream_t stream);
+/* Per-channel GroupNorm statistics of ONE NHWC bf16 tensor: chan_sums[b, c, 0..1] += (sum x, sum x^2);
+ * the caller zeroes chan_sums beforehand. A tensor's sums are computed once and reused by every
+ * GroupNorm that reads it (nn.GroupNorm call sites: models/layerspp.py:67,219,231; ncsnpp.py:200-233). */
+int csd_gn_chan_stats_bf16(const void* src, int c, int pitch, float* chan_sums, int batch, int hw,
+                           csd_stream_t stream);
 
-/* out = [SiLU](GroupNorm(cat(src0,src1))) as bf16 NHWC with pitch c0+c1 (must be a multiple of 8).
- * gamma/beta fp32 [c0+c1]; eps as in the module (1e-6).                                         */
-int csd_gn_apply_bf16(const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1,
-                      const float* sums, const float* gamma, const float* beta, void* out, int out_pitch,
-                      int batch, int hw, int groups, float eps, int apply_silu, csd_stream_t stream);
+/* chan_sums[b, c, :] = sum over the image's pixel tiles of the per-tile partials that csd_conv_gemm
+ * (mode 2) writes from its epilogue: partials [batch * tiles_per_img, c, 2]. No atomics.          */
+int csd_gn_finalize_partials_f32(const float* partials, float* chan_sums, int batch, int tiles_per_img, int c,
+                                 csd_stream_t stream);
+
+/* out = [SiLU](GroupNorm(cat(src0, src1))) as bf16 NHWC (pitch out_pitch >= c0 + c1, multiple of 8):
+ * the `torch.cat([h, hs.pop()], dim=1)` + GroupNorm + SiLU of models/ncsnpp.py:325 / layerspp.py:242
+ * without materialising the concatenation first. sums0 / sums1 are the per-channel sums of each source;
+ * gamma / beta fp32 [c0 + c1]; eps as in the module (1e-6).                                       */
+int csd_gn_apply_bf16(const void* src0, int c0, int pitch0, const float* sums0, const void* src1, int c1,
+                      int pitch1, const float* sums1, const float* gamma, const float* beta, void* out,
+                      int out_pitch, int batch, int hw, int groups, float eps, int apply_silu,
+                      csd_stream_t stream);
 
 /* Depthwise separable FIR resampling of an NHWC bf16 tensor with the [1,3,3,1] family
  * (up_or_down_sampling.upsample_2d / downsample_2d, models/up_or_down_sampling.py:195-257):

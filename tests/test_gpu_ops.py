@@ -190,17 +190,26 @@ def test_groupnorm_silu_vs_torch(c0, c1, hw):
     full = torch.cat([a, b], -1) if c1 else a
     ref_in = full.float().permute(0, 2, 1).reshape(B, C, hw, 1)
     ref = F.silu(F.group_norm(ref_in, groups, gamma, beta, eps=1e-6)).reshape(B, C, hw).permute(0, 2, 1)
-    sums = torch.zeros(B, groups, 2, device="cuda")
     ag, bg = a.cuda(), (b.cuda() if c1 else None)
-    k_.gn_stats(ag, c0, bg, c1, sums, groups)
-    n = hw * (C // groups)
-    mean_ref = ref_in.reshape(B, groups, -1).mean(-1)
-    _close(sums[..., 0] / n, mean_ref, 1e-4, f"gn mean C={C}")
+    sums0 = torch.zeros(B, c0, 2, device="cuda")
+    k_.gn_chan_stats(ag, c0, sums0)
+    _close(sums0[..., 0], a.float().sum(1), 1e-4, f"channel sums C0={c0}")
+    _close(sums0[..., 1], (a.float() ** 2).sum(1), 1e-4, f"channel sums of squares C0={c0}")
+    sums1 = None
+    if c1:
+        sums1 = torch.zeros(B, c1, 2, device="cuda")
+        k_.gn_chan_stats(bg, c1, sums1)
     out = torch.empty(B, hw, C, device="cuda", dtype=torch.bfloat16)
-    k_.gn_apply(ag, c0, bg, c1, sums, gamma.cuda(), beta.cuda(), out, groups, 1e-6, True)
+    k_.gn_apply(ag, c0, sums0, bg, c1, sums1, gamma.cuda(), beta.cuda(), out, groups, 1e-6, True)
     _close(out, ref, BF16, f"gn+silu C={C} hw={hw}")
-    k_.gn_apply(ag, c0, bg, c1, sums, gamma.cuda(), beta.cuda(), out, groups, 1e-6, False)
+    k_.gn_apply(ag, c0, sums0, bg, c1, sums1, gamma.cuda(), beta.cuda(), out, groups, 1e-6, False)
     _close(out, F.group_norm(ref_in, groups, gamma, beta, eps=1e-6).reshape(B, C, hw).permute(0, 2, 1), BF16, "gn only")
+    # per-tile partials -> channel sums (the path fed by the transposed convolution's epilogue)
+    tiles = 7
+    parts = torch.randn(B * tiles, c0, 2, device="cuda")
+    fin = torch.empty(B, c0, 2, device="cuda")
+    k_.gn_finalize_partials(parts, fin, B, tiles, c0)
+    _close(fin, parts.view(B, tiles, c0, 2).sum(1), 1e-5, "finalize partials")
 
 
 @pytest.mark.parametrize("h,c", [(16, 96), (10, 288), (5, 8), (20, 192)])
