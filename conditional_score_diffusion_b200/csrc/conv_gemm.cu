@@ -884,12 +884,10 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     p.a_stages = 2;
     int bs = (budget_h - p.a_stages * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
     if (bs > kMaxBStages) bs = kMaxBStages;
-    if (bs >= 4 && p.a_stages < 3 &&
-        budget_h - 3 * (int)p.a_stage_bytes >= 4 * (int)p.b_stage_bytes) {  // room for a third halo buffer
-      p.a_stages = 3;
-      bs = (budget_h - 3 * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
-      if (bs > kMaxBStages) bs = kMaxBStages;
-    }
+    // A halo lasts 9 taps, so two halo buffers already cover its load latency; the weight ring is the
+    // latency-critical one (one slab per tap) and gets the rest of the budget. A third halo buffer is
+    // only taken when the weight ring is already at its maximum depth.
+    if (bs == kMaxBStages && budget_h - 3 * (int)p.a_stage_bytes >= kMaxBStages * (int)p.b_stage_bytes) p.a_stages = 3;
     CSD_REQUIRE(bs >= 2, "halo mode: not enough shared memory for the weight ring (n_tile=%d mt=%d)", d->n_tile, mt);
     p.b_stages = bs;
     L->smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 +
