@@ -241,30 +241,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (threadIdx.x == 0) CSD_TS(1);
 
+  // Single-thread issue loops: ring position / parity are running counters (no division) and the UMMA
+  // descriptors advance by adding to their low word, so the instruction stream between two tcgen05.mma
+  // stays shorter than the MMA itself.
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      int it = 0;
-      int kidx = 0;  // running 32-wide K block index into Wt
+      uint32_t stage = 0, par = 1;
+      int kcol = p.wt_k_off;  // running K column into Wt
+      const uint32_t tx_bytes = p.a_box_bytes + p.b_box_bytes * p.nsplit;
       for (int s = 0; s < p.nseg; ++s) {
         const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
         const int taps = p.seg_taps[s];
         for (int tap = 0; tap < taps; ++tap) {
           const int dy = (taps == 9) ? (tap / 3 - p.pad) : 0;
           const int dx = (taps == 9) ? (tap % 3 - p.pad) : 0;
-          for (int c = 0; c < p.seg_chunks[s]; ++c, ++it, ++kidx) {
-            const int stage = it % p.num_stages;
-            const uint32_t parity = ((it / p.num_stages) & 1) ^ 1;
-            ptx::mbar_wait(empty_bar(stage), parity);
+          const int cw = w0 * p.stride + dx, ch = h0 * p.stride + dy;
+          for (int c = 0; c < p.seg_chunks[s]; ++c, kcol += kChunkK) {
+            ptx::mbar_wait(empty_bar(stage), par);
             const uint32_t a_dst = smem_base + stage * p.stage_bytes;
             const uint32_t b_dst = a_dst + kAStageBytes;
-            ptx::mbar_arrive_expect_tx(full_bar(stage), p.a_box_bytes + p.b_box_bytes * p.nsplit);
-            ptx::tma_load_4d(a_dst, mapA, full_bar(stage), p.seg_coff[s] + c * kChunkK, w0 * p.stride + dx, h0 * p.stride + dy,
-                             b0 + z * p.a_batch_step);
-            for (int j = 0; j < p.nsplit; ++j) {
-              ptx::tma_load_3d(b_dst + j * p.b_box_bytes, &mapB, full_bar(stage), p.wt_k_off + kidx * kChunkK,
-                               n0 + j * p.n_sub, z);
-            }
+            ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+            ptx::tma_load_4d(a_dst, mapA, full_bar(stage), p.seg_coff[s] + c * kChunkK, cw, ch, b0 + z * p.a_batch_step);
+            ptx::tma_load_3d(b_dst, &mapB, full_bar(stage), kcol, n0, z);
+            if (p.nsplit > 1) ptx::tma_load_3d(b_dst + p.b_box_bytes, &mapB, full_bar(stage), kcol, n0 + p.n_sub, z);
+            if (++stage == (uint32_t)p.num_stages) { stage = 0; par ^= 1u; }
           }
         }
       }
@@ -273,27 +274,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)p.n_sub);
+      const uint32_t hi = ptx::smem_desc_hi(512, kLayoutSw64);
+      const bool split = p.nsplit > 1;
+      const uint32_t b2_off = p.b_box_bytes >> 4;
+      uint32_t stage = 0, par = 0, accumulate = 0;
       for (int it = 0; it < total_iters; ++it) {
-        const int stage = it % p.num_stages;
-        const uint32_t parity = (it / p.num_stages) & 1;
-        ptx::mbar_wait(full_bar(stage), parity);
+        ptx::mbar_wait(full_bar(stage), par);
         ptx::tcgen05_fence_after();
-        if (it == 0) CSD_TS(3);
-        if (it == total_iters / 2) CSD_TS(8);
-        const uint32_t a_addr = smem_base + stage * p.stage_bytes;
-        const uint32_t b_addr = a_addr + kAStageBytes;
-#pragma unroll
-        for (int kk = 0; kk < kChunkK / 16; ++kk) {
-          const uint64_t a_desc = ptx::make_smem_desc(a_addr + kk * 32, 16, 512, kLayoutSw64);
-          for (int j = 0; j < p.nsplit; ++j) {
-            const uint64_t b_desc =
-                ptx::make_smem_desc(b_addr + j * p.b_box_bytes + kk * 32, 16, 512, kLayoutSw64);
-            ptx::mma_bf16_ss(tmem_base + j * p.n_sub, a_desc, b_desc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-          }
-        }
+        const uint32_t a_lo = ptx::smem_desc_lo(smem_base + stage * p.stage_bytes, 16);
+        const uint32_t b_lo = a_lo + (kAStageBytes >> 4);
+        ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(hi, a_lo), ptx::smem_desc_join(hi, b_lo), idesc, accumulate);
+        if (split)
+          ptx::mma_bf16_ss(tmem_base + p.n_sub, ptx::smem_desc_join(hi, a_lo), ptx::smem_desc_join(hi, b_lo + b2_off), idesc,
+                           accumulate);
+        ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(hi, a_lo + 2), ptx::smem_desc_join(hi, b_lo + 2), idesc, 1u);
+        if (split)
+          ptx::mma_bf16_ss(tmem_base + p.n_sub, ptx::smem_desc_join(hi, a_lo + 2), ptx::smem_desc_join(hi, b_lo + b2_off + 2),
+                           idesc, 1u);
+        accumulate = 1u;
         ptx::mma_commit(empty_bar(stage));  // frees the stage when the MMAs above have read it
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; par ^= 1u; }
       }
-      CSD_TS(4);
       ptx::mma_commit(tmem_full_bar);       // accumulator complete
     }
   } else {
@@ -400,7 +401,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         const int nchunks = p.seg_chunks[s];
         for (int c = 0; c < nchunks; ++c, ++ia) {
           const int sa = ia % p.a_stages;
-          if (!(p.debug_nodata && ia >= p.a_stages)) {
+          if (!((p.debug_nodata & 2) && ia >= p.a_stages)) {
           ptx::mbar_wait(a_empty(sa), ((ia / p.a_stages) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(a_full(sa), a_bytes);
           ptx::tma_load_4d(a_base + sa * p.a_stage_bytes, mapA, a_full(sa), p.seg_coff[s] + c * kChunkK, w0 - halo,
@@ -408,7 +409,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           }
           for (int tap = 0; tap < taps; ++tap, ++ib) {
             const int sb = ib % p.b_stages;
-            if (p.debug_nodata && ib >= p.b_stages) continue;
+            if ((p.debug_nodata & 1) && ib >= p.b_stages) continue;
             ptx::mbar_wait(b_empty(sb), ((ib / p.b_stages) & 1) ^ 1);
             ptx::mbar_arrive_expect_tx(b_full(sb), p.b_box_bytes * p.nsplit);
             const int kidx = p.seg_kbase[s] + tap * nchunks + c;
@@ -432,14 +433,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         const uint32_t sbo = (uint32_t)pitch * kRowBytes;  // stride between 8-pixel core-matrix groups
         for (int c = 0; c < p.seg_chunks[s]; ++c, ++ia) {
           const int sa = ia % p.a_stages;
-          if (!(p.debug_nodata && ia >= p.a_stages)) ptx::mbar_wait(a_full(sa), (ia / p.a_stages) & 1);
+          if (!((p.debug_nodata & 2) && ia >= p.a_stages)) ptx::mbar_wait(a_full(sa), (ia / p.a_stages) & 1);
           ptx::tcgen05_fence_after();
           if (ia == 0) CSD_TS(3);
           if (ia == 1) CSD_TS(8);
           const uint32_t a_addr = a_base + sa * p.a_stage_bytes;
           for (int tap = 0; tap < taps; ++tap, ++ib) {
             const int sb = ib % p.b_stages;
-            if (!(p.debug_nodata && ib >= p.b_stages)) ptx::mbar_wait(b_full(sb), (ib / p.b_stages) & 1);
+            if (!((p.debug_nodata & 1) && ib >= p.b_stages)) ptx::mbar_wait(b_full(sb), (ib / p.b_stages) & 1);
             ptx::tcgen05_fence_after();
             const uint32_t b_addr = b_base + sb * p.b_stage_bytes;
             const int dy = halo ? tap / 3 : 0, dx = halo ? tap % 3 : 0;
@@ -509,7 +510,9 @@ constexpr int kTPix = 256;      // pixels per CTA (N of the MMA)
 constexpr int kTRows = 32;      // image rows per macro tile
 constexpr int kTChan = 128;     // output channels per CTA (M of the MMA)
 
-__global__ void __launch_bounds__(kConvThreads)
+constexpr int kTThreads = 320;  // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
+
+__global__ void __launch_bounds__(kTThreads)
 conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                    const __grid_constant__ CUtensorMap mapB, const ConvGemmKernelParams p) {
@@ -518,10 +521,8 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   const uint32_t a_base = smem_base;                                   // pixel halos
   const uint32_t b_base = smem_base + p.a_stages * p.a_stage_bytes;    // weight slabs
   const uint32_t bar_base = b_base + p.b_stages * p.b_stage_bytes;
-  auto a_full = [&](int s) { return bar_base + 8u * s; };
-  auto a_empty = [&](int s) { return bar_base + 8u * (kMaxAStages + s); };
-  auto b_full = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + kMaxBStages + s); };
+  const uint32_t a_full0 = bar_base, a_empty0 = bar_base + 8u * kMaxAStages;
+  const uint32_t b_full0 = bar_base + 8u * (2 * kMaxAStages), b_empty0 = b_full0 + 8u * kMaxBStages;
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages);
   const uint32_t tmem_slot = tmem_full_bar + 8u;
 
@@ -533,13 +534,12 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   const int b = t / (p.tiles_w * p.tiles_h);
   const int w0 = tw * kHaloTW, h0 = th * kTRows;
   const int n0 = blockIdx.y * kTChan;
-  if (threadIdx.x == 0) CSD_TS(0);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&mapA0);
     ptx::prefetch_tensormap(&mapB);
-    for (int s = 0; s < p.a_stages; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < p.a_stages; ++s) { ptx::mbar_init(a_full0 + 8u * s, 1); ptx::mbar_init(a_empty0 + 8u * s, 1); }
+    for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full0 + 8u * s, 1); ptx::mbar_init(b_empty0 + 8u * s, 1); }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_mbar_init();
   }
@@ -553,27 +553,31 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // Both issue loops below are single-thread instruction streams whose latency bounds the tensor pipe
+  // (one tcgen05.mma pair per weight slab = 256 tensor cycles): ring positions and barrier parities are
+  // running counters (no division), and the UMMA descriptors are advanced by adding to their low word.
   if (warp == 0) {
     if (lane == 0) {
-      int ia = 0, ib = 0;
+      uint32_t sa = 0, a_par = 1, sb = 0, b_par = 1;
       for (int s = 0; s < p.nseg; ++s) {
         const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
         const int taps = p.seg_taps[s];
         const int halo = (taps == 9) ? 1 : 0;
         const uint32_t a_bytes = (uint32_t)((kHaloTW + 2 * halo) * (kTRows + 2 * halo) * kRowBytes);
         const int nchunks = p.seg_chunks[s];
-        for (int c = 0; c < nchunks; ++c, ++ia) {
-          const int sa = ia % p.a_stages;
-          ptx::mbar_wait(a_empty(sa), ((ia / p.a_stages) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(a_full(sa), a_bytes);
-          ptx::tma_load_4d(a_base + sa * p.a_stage_bytes, mapA, a_full(sa), p.seg_coff[s] + c * kChunkK, w0 - halo,
-                           h0 - halo, b);
-          for (int tap = 0; tap < taps; ++tap, ++ib) {
-            const int sb = ib % p.b_stages;
-            ptx::mbar_wait(b_empty(sb), ((ib / p.b_stages) & 1) ^ 1);
-            ptx::mbar_arrive_expect_tx(b_full(sb), kTChan * kRowBytes);
-            const int kidx = p.seg_kbase[s] + tap * nchunks + c;
-            ptx::tma_load_3d(b_base + sb * p.b_stage_bytes, &mapB, b_full(sb), p.wt_k_off + kidx * kChunkK, n0, 0);
+        const int kstep = nchunks * kChunkK;
+        for (int c = 0; c < nchunks; ++c) {
+          ptx::mbar_wait(a_empty0 + 8u * sa, a_par);
+          ptx::mbar_arrive_expect_tx(a_full0 + 8u * sa, a_bytes);
+          ptx::tma_load_4d(a_base + sa * p.a_stage_bytes, mapA, a_full0 + 8u * sa, p.seg_coff[s] + c * kChunkK,
+                           w0 - halo, h0 - halo, b);
+          if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+          int kcol = p.wt_k_off + (p.seg_kbase[s] + c) * kChunkK;
+          for (int tap = 0; tap < taps; ++tap, kcol += kstep) {
+            ptx::mbar_wait(b_empty0 + 8u * sb, b_par);
+            ptx::mbar_arrive_expect_tx(b_full0 + 8u * sb, kTChan * kRowBytes);
+            ptx::tma_load_3d(b_base + sb * p.b_stage_bytes, &mapB, b_full0 + 8u * sb, kcol, n0, 0);
+            if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
           }
         }
       }
@@ -581,52 +585,69 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)kTPix);
-      int ia = 0, ib = 0;
+      const uint32_t w_hi = ptx::smem_desc_hi(512, kLayoutSw64);
+      uint32_t sa = 0, a_par = 0, sb = 0, b_par = 0;
       uint32_t accumulate = 0;
       for (int s = 0; s < p.nseg; ++s) {
-        const int taps = p.seg_taps[s];
-        const int halo = (taps == 9) ? 1 : 0;
-        const int pitch = kHaloTW + 2 * halo;
-        const uint32_t sbo = (uint32_t)pitch * kRowBytes;
-        for (int c = 0; c < p.seg_chunks[s]; ++c, ++ia) {
-          const int sa = ia % p.a_stages;
-          ptx::mbar_wait(a_full(sa), (ia / p.a_stages) & 1);
-          ptx::tcgen05_fence_after();
-          if (ia == 0) CSD_TS(3);
-          if (ia == 1) CSD_TS(8);
-          const uint32_t px_addr = a_base + sa * p.a_stage_bytes;
-          for (int tap = 0; tap < taps; ++tap, ++ib) {
-            const int sb = ib % p.b_stages;
-            ptx::mbar_wait(b_full(sb), (ib / p.b_stages) & 1);
+        const int nchunks = p.seg_chunks[s];
+        if (p.seg_taps[s] == 9) {
+          constexpr int pitch = kHaloTW + 2;
+          const uint32_t x_hi = ptx::smem_desc_hi(pitch * kRowBytes, kLayoutSw64);
+          for (int c = 0; c < nchunks; ++c) {
+            ptx::mbar_wait(a_full0 + 8u * sa, a_par);
             ptx::tcgen05_fence_after();
-            const uint32_t w_addr = b_base + sb * p.b_stage_bytes;
-            const int dy = halo ? tap / 3 : 0, dx = halo ? tap % 3 : 0;
-            const uint32_t px_tap = px_addr + (uint32_t)((dy * pitch + dx) * kRowBytes);
+            const uint32_t x_lo0 = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
 #pragma unroll
-            for (int kk = 0; kk < kChunkK / 16; ++kk) {
-              const uint64_t w_desc = ptx::make_smem_desc(w_addr + kk * 32, 16, 512, kLayoutSw64);   // M operand
-              const uint64_t x_desc = ptx::make_smem_desc(px_tap + kk * 32, 16, sbo, kLayoutSw64);   // N operand
-              ptx::mma_bf16_ss(tmem_base, w_desc, x_desc, idesc, (accumulate || kk > 0) ? 1u : 0u);
+            for (int tap = 0; tap < 9; ++tap) {
+              ptx::mbar_wait(b_full0 + 8u * sb, b_par);
+              ptx::tcgen05_fence_after();
+              const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
+              const uint32_t x_lo = x_lo0 + (uint32_t)((((tap / 3) * pitch + (tap % 3)) * kRowBytes) >> 4);
+              ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi, x_lo), idesc,
+                               accumulate);
+              ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi, x_lo + 2),
+                               idesc, 1u);
+              accumulate = 1u;
+              ptx::mma_commit(b_empty0 + 8u * sb);
+              if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
             }
-            accumulate = 1;
-            ptx::mma_commit(b_empty(sb));
+            ptx::mma_commit(a_empty0 + 8u * sa);
+            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
           }
-          ptx::mma_commit(a_empty(sa));
+        } else {
+          const uint32_t x_hi = ptx::smem_desc_hi(kHaloTW * kRowBytes, kLayoutSw64);
+          for (int c = 0; c < nchunks; ++c) {
+            ptx::mbar_wait(a_full0 + 8u * sa, a_par);
+            ptx::mbar_wait(b_full0 + 8u * sb, b_par);
+            ptx::tcgen05_fence_after();
+            const uint32_t x_lo = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
+            const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
+            ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi, x_lo), idesc,
+                             accumulate);
+            ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi, x_lo + 2),
+                             idesc, 1u);
+            accumulate = 1u;
+            ptx::mma_commit(b_empty0 + 8u * sb);
+            if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
+            ptx::mma_commit(a_empty0 + 8u * sa);
+            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+          }
         }
       }
-      CSD_TS(4);
       ptx::mma_commit(tmem_full_bar);
     }
   } else {
-    // ===== epilogue =====
-    // Phase A: TMEM lane = output channel, column = pixel. Each thread adds its channel's bias + temb,
-    //          rounds to bf16 and writes stage[pixel][channel] into the (now idle) operand rings: a
-    //          warp writes 32 consecutive channels of one pixel = 64 contiguous bytes, conflict free.
+    // ===== epilogue (8 warps) =====
+    // Phase A: TMEM lane = output channel, column = pixel. Warp w reads lane quadrant w % 4 (the hardware's
+    //          TMEM access rule) and the pixel half (w - 2) / 4; each thread adds its channel's bias + temb,
+    //          rounds to bf16 and writes stage[pixel][channel] into the (now idle) operand rings: a warp
+    //          writes 32 consecutive channels of one pixel = 64 contiguous bytes, conflict free.
     // Phase B: the staged tile is read back as 16-byte channel vectors, pixel-major, so residual loads
     //          and output stores are fully coalesced NHWC rows; scale, residual and the per-channel
     //          GroupNorm partial sums are applied here.
     const int q = warp & 3;
-    const int et = threadIdx.x - 64;                  // 0..127
+    const int half = (warp - 2) >> 2;                 // 0: pixels [0,128), 1: pixels [128,256)
+    const int et = threadIdx.x - 64;                  // 0..255
     const int cl = q * 32 + lane;                     // channel inside the CTA's 128-channel block
     const int c = n0 + cl;
     const int cb = min(kTChan, p.n_store - n0);       // channels of this block that are stored (multiple of 8)
@@ -636,41 +657,48 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
                                 : 0.f;
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tcgen05_fence_after();
-    if (threadIdx.x == 64) CSD_TS(5);
     const int spitch = cb;                            // staging row pitch in elements
     __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(__cvta_shared_to_generic(smem_base));
-    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int col = 0; col < kTPix; col += 32) {
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (kTPix / 2));
+    __nv_bfloat16* stage_c = stage + (half * (kTPix / 2)) * spitch + cl;
+#pragma unroll 1
+    for (int col = 0; col < kTPix / 2; col += 32) {
       uint32_t r0[16], r1[16];
       __syncwarp();
       ptx::tmem_ld_x16(t_row + col, r0);
       ptx::tmem_ld_x16(t_row + col + 16, r1);
       ptx::tmem_ld_wait();
       if (c_valid) {
+        __nv_bfloat16* sp = stage_c + col * spitch;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          stage[(col + i) * spitch + cl] = __float2bfloat16_rn(__uint_as_float(r0[i]) + add_c);
-          stage[(col + 16 + i) * spitch + cl] = __float2bfloat16_rn(__uint_as_float(r1[i]) + add_c);
+          sp[i * spitch] = __float2bfloat16_rn(__uint_as_float(r0[i]) + add_c);
+          sp[(16 + i) * spitch] = __float2bfloat16_rn(__uint_as_float(r1[i]) + add_c);
         }
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     // Phase B
     const int V = cb >> 3;                            // 16-byte vectors per pixel
-    const int ppass = min(128 / V, 16);               // pixels handled per pass (bounds the reduction scratch)
+    const int ppass = min(256 / V, 32);               // pixels handled per pass (bounds the reduction scratch)
     const int v = et % V, pl = et / V;
     float s1[8], s2[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
     if (pl < ppass) {
-      const bf16x8* stage_v = reinterpret_cast<const bf16x8*>(stage);
+      const uint4* stage_v = reinterpret_cast<const uint4*>(stage) + v;
+      const bool has_res = p.res != nullptr;
+      const bool has_stats = p.stat_partials != nullptr;
+      const float scale = p.scale;
       for (int m = pl; m < kTPix; m += ppass) {
-        const int h = h0 + m / kHaloTW, w = w0 + m % kHaloTW;
+        const int h = h0 + (m >> 3), w = w0 + (m & 7);
         if (h < p.H && w < p.W) {
           const long long pix = ((long long)b * p.H + h) * p.W + w;
           float f[8];
-          unpack8(stage_v[m * V + v], f);
-          if (p.res != nullptr) {
+          bf16x8 sv;
+          *reinterpret_cast<uint4*>(&sv) = stage_v[m * V];
+          unpack8(sv, f);
+          if (has_res) {
             float rr[8];
             bf16x8 rv;
             *reinterpret_cast<uint4*>(&rv) = __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch + n0) + v);
@@ -679,11 +707,11 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
             for (int i = 0; i < 8; ++i) f[i] += rr[i];
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] *= p.scale;
+          for (int i = 0; i < 8; ++i) f[i] *= scale;
           const bf16x8 o = pack8(f);
           reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_pitch + n0)[v] =
               *reinterpret_cast<const uint4*>(&o);
-          if (p.stat_partials != nullptr) {
+          if (has_stats) {
             float g[8];
             unpack8(o, g);   // statistics of exactly what the consumer will read
 #pragma unroll
@@ -698,7 +726,6 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
     if (p.stat_partials != nullptr) {
       // reduce the ppass partial rows per channel vector through shared memory (after the staging tile)
       float* red = reinterpret_cast<float*>(__cvta_shared_to_generic(smem_base + kTPix * kTChan * 2));
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // staging reads done (red may not alias, but keep order)
       if (pl < ppass) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -706,7 +733,7 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           red[(pl * kTChan + v * 8 + i) * 2 + 1] = s2[i];
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (et < cb) {
         float a1 = 0.f, a2 = 0.f;
         for (int r = 0; r < ppass; ++r) {
@@ -718,7 +745,6 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         sp[1] = a2;
       }
     }
-    if (threadIdx.x == 64) CSD_TS(6);
   }
 
   ptx::tcgen05_fence_before();
@@ -726,7 +752,6 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   if (warp == 1) {
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc(tmem_base, kTPix);
-    if (lane == 0) CSD_TS(7);
   }
 }
 
@@ -867,7 +892,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   p.scale = d->scale;
   {
     const char* e = getenv("CSD_DEBUG_NODATA");
-    p.debug_nodata = (e != nullptr && e[0] == '1') ? 1 : 0;
+    p.debug_nodata = (e != nullptr) ? atoi(e) : 0;  // bit 0: skip weight loads, bit 1: skip activation loads
     const char* t = getenv("CSD_DEBUG_TS");
     p.debug_ts = (t != nullptr) ? reinterpret_cast<long long*>(strtoull(t, nullptr, 0)) : nullptr;
   }
@@ -913,7 +938,7 @@ int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
     attr_set = true;
   }
   if (L->transposed) {
-    conv_halo_t_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
+    conv_halo_t_kernel<<<L->grid, kTThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
                                                                    L->mapB, L->p);
   } else if (L->halo) {
     conv_halo_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],

@@ -163,6 +163,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+// The same descriptor split into its 32-bit halves: only the start address (low word) changes inside an
+// issue loop, so the loop adds (byte offset >> 4) to the low word instead of rebuilding the descriptor.
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+__device__ __forceinline__ uint64_t smem_desc_join(uint32_t hi, uint32_t lo) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B (K-major both), fp32 accumulate, M = 128
 // (cute::UMMA::InstrDescriptor bit layout: c_format [4,6), a_format [7,10), b_format [10,13),
 //  a_major 15, b_major 16, n >> 3 at [17,23), m >> 4 at [24,29)).
