@@ -207,7 +207,7 @@ def conv_profile(plan):
             e1.record()
             segs, _, n, _ = a
             pixels = kw["batch"] * kw["h"] * kw["w"] * kw.get("z_batches", 1)
-            k_real = sum(t * c for (_, _, _, c, t) in segs)
+            k_real = sum(sg[4] * sg[3] for sg in segs)
             ev.append((e0, e1, 2.0 * pixels * n * k_real, (kw["h"], kw["w"], n, k_real)))
         else:
             fn(*a, **kw)

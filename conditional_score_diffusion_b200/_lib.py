@@ -32,6 +32,9 @@ class ConvSegment(ctypes.Structure):
         ("c_off", c_int32),
         ("c_cnt", c_int32),
         ("taps", c_int32),
+        ("norm", c_void_p),
+        ("norm_silu", c_int32),
+        ("reserved_", c_int32),
     ]
 
 
@@ -101,6 +104,8 @@ _PROTOTYPES = {
                                       c_void_p]),
     "csd_gn_chan_stats_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "csd_gn_finalize_partials_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "csd_gn_coeffs_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                  c_int, c_int, c_float, c_void_p]),
     "csd_gn_apply_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "csd_fir_resample_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -61,6 +61,15 @@ void count_launch();
 // SiLU with the fast-division path (2 MUFU + 2 FP ops); |error| < 2 ulp of fp32, far below bf16 storage.
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
+// SiLU through one MUFU op: x*sigmoid(x) = h + h*tanh(h) with h = x/2 (tanh.approx.f32, max rel. error
+// 2^-11: below the bf16 rounding applied to the result). Used where MUFU throughput is the constraint.
+__device__ __forceinline__ float silu_tanh(float v) {
+  const float h = 0.5f * v;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -61,6 +61,11 @@ struct ConvGemmKernelParams {
   int mt, a_stages, b_stages;
   int seg_kbase[CSD_MAX_SEGMENTS];
   uint32_t a_stage_bytes, b_stage_bytes;
+  // transposed mode: fused GroupNorm(+SiLU) prologue (per-segment (scale, shift) tables [batch, c_cnt, 2])
+  const float* seg_norm[CSD_MAX_SEGMENTS];
+  int seg_silu[CSD_MAX_SEGMENTS];
+  int seg_ccnt[CSD_MAX_SEGMENTS];
+  int has_norm;
   void* out;
   int out_pitch, out_f32;
   long long out_z_stride;
@@ -505,6 +510,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 // MACs in 128 cycles.
 // Epilogue: TMEM lane = output channel, column = pixel; bias / temb are per-lane scalars, the
 // per-channel GroupNorm partial sums of the stored output are free per-thread accumulations.
+//
+// Fused GroupNorm + SiLU prologue (segments with a `norm` table): the 8 epilogue warps are idle while the
+// main loop runs, so they transform every pixel-halo stage in place between TMA arrival and MMA issue:
+// y = SiLU(x * scale[b,c] + shift[b,c]) on the 16-byte units of the swizzled tile (physical unit j' of row
+// r holds logical channels 8*(j' ^ ((r >> 1) & 3)) .. +8 under SWIZZLE_64B), skipping halo pixels outside
+// the image (they must stay the zeros TMA wrote: the reference pads the *normalised* activation,
+// models/layers.py:119-132 padding=1 after models/layerspp.py:242). A stage then goes
+// TMA -> a_full -> transform -> fence.proxy.async -> a_ready -> MMA -> a_empty. One halo stage is transformed
+// once and feeds all 9 taps, so the MUFU work is 1/9 of what a per-tap operand transform would cost.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kTPix = 256;      // pixels per CTA (N of the MMA)
 constexpr int kTRows = 32;      // image rows per macro tile
@@ -525,6 +539,8 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   const uint32_t b_full0 = bar_base + 8u * (2 * kMaxAStages), b_empty0 = b_full0 + 8u * kMaxBStages;
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages);
   const uint32_t tmem_slot = tmem_full_bar + 8u;
+  const uint32_t a_ready0 = tmem_full_bar + 16u;                 // kMaxAStages barriers, 256 arrivals each
+  const uint32_t coef_addr = a_ready0 + 8u * kMaxAStages;        // float2 per padded K channel (16-byte aligned)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -534,12 +550,14 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   const int b = t / (p.tiles_w * p.tiles_h);
   const int w0 = tw * kHaloTW, h0 = th * kTRows;
   const int n0 = blockIdx.y * kTChan;
+  if (threadIdx.x == 0) CSD_TS(0);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&mapA0);
     ptx::prefetch_tensormap(&mapB);
     for (int s = 0; s < p.a_stages; ++s) { ptx::mbar_init(a_full0 + 8u * s, 1); ptx::mbar_init(a_empty0 + 8u * s, 1); }
     for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full0 + 8u * s, 1); ptx::mbar_init(b_empty0 + 8u * s, 1); }
+    for (int s = 0; s < p.a_stages; ++s) ptx::mbar_init(a_ready0 + 8u * s, kTThreads - 64);
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_mbar_init();
   }
@@ -552,6 +570,7 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   ptx::tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) CSD_TS(1);
 
   // Both issue loops below are single-thread instruction streams whose latency bounds the tensor pipe
   // (one tcgen05.mma pair per weight slab = 256 tensor cycles): ring positions and barrier parities are
@@ -588,14 +607,18 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       const uint32_t w_hi = ptx::smem_desc_hi(512, kLayoutSw64);
       uint32_t sa = 0, a_par = 0, sb = 0, b_par = 0;
       uint32_t accumulate = 0;
+      // with the fused prologue a stage is usable once the transform warps have released it
+      const uint32_t a_go0 = p.has_norm ? a_ready0 : a_full0;
       for (int s = 0; s < p.nseg; ++s) {
         const int nchunks = p.seg_chunks[s];
         if (p.seg_taps[s] == 9) {
           constexpr int pitch = kHaloTW + 2;
           const uint32_t x_hi = ptx::smem_desc_hi(pitch * kRowBytes, kLayoutSw64);
           for (int c = 0; c < nchunks; ++c) {
-            ptx::mbar_wait(a_full0 + 8u * sa, a_par);
+            ptx::mbar_wait(a_go0 + 8u * sa, a_par);
             ptx::tcgen05_fence_after();
+            if (c == 0 && s == 0) CSD_TS(3);
+            if (c == 1 && s == 0) CSD_TS(8);
             const uint32_t x_lo0 = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
@@ -617,7 +640,7 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         } else {
           const uint32_t x_hi = ptx::smem_desc_hi(kHaloTW * kRowBytes, kLayoutSw64);
           for (int c = 0; c < nchunks; ++c) {
-            ptx::mbar_wait(a_full0 + 8u * sa, a_par);
+            ptx::mbar_wait(a_go0 + 8u * sa, a_par);
             ptx::mbar_wait(b_full0 + 8u * sb, b_par);
             ptx::tcgen05_fence_after();
             const uint32_t x_lo = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
@@ -634,6 +657,7 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           }
         }
       }
+      CSD_TS(4);
       ptx::mma_commit(tmem_full_bar);
     }
   } else {
@@ -655,8 +679,71 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
     const float add_c = c_valid ? ((p.bias != nullptr ? __ldg(p.bias + c) : 0.f) +
                                    (p.temb != nullptr ? __ldg(p.temb + (long long)b * p.temb_pitch + c) : 0.f))
                                 : 0.f;
+    if (p.has_norm) {
+      // ---- fused GroupNorm(+SiLU) prologue: transform every pixel-halo stage in place ----
+      float2* tab = reinterpret_cast<float2*>(__cvta_shared_to_generic(coef_addr));
+      {
+        int base = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int nch = p.seg_chunks[s] * kChunkK;
+          const float2* src = reinterpret_cast<const float2*>(p.seg_norm[s]);
+          for (int i = et; i < nch; i += kTThreads - 64)
+            tab[base + i] = (src != nullptr && i < p.seg_ccnt[s]) ? __ldg(src + (long long)b * p.seg_ccnt[s] + i)
+                                                                  : make_float2(0.f, 0.f);
+          base += nch;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      uint32_t sa = 0, a_par = 0;
+      int base = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const bool norm = p.seg_norm[s] != nullptr;
+        const bool act = p.seg_silu[s] != 0;
+        const int halo = (p.seg_taps[s] == 9) ? 1 : 0;
+        const int pitch = kHaloTW + 2 * halo;
+        const int units = pitch * (kTRows + 2 * halo) * 4;       // 16-byte units of the stage
+        for (int c = 0; c < p.seg_chunks[s]; ++c) {
+          ptx::mbar_wait(a_full0 + 8u * sa, a_par);
+          if (norm) {
+            uint4* st = reinterpret_cast<uint4*>(__cvta_shared_to_generic(a_base + sa * p.a_stage_bytes));
+            const float2* tc = tab + base + c * kChunkK;
+            for (int u = et; u < units; u += kTThreads - 64) {
+              const int r = u >> 2;
+              const int hy = halo ? r / (kHaloTW + 2) : (r >> 3);
+              const int hx = r - hy * pitch;
+              const int gh = h0 - halo + hy, gw = w0 - halo + hx;
+              if (gh < 0 || gh >= p.H || gw < 0 || gw >= p.W) continue;   // conv padding stays zero
+              const int j = (u & 3) ^ ((r >> 1) & 3);                      // SWIZZLE_64B: logical 16-byte unit
+              const float4* cf = reinterpret_cast<const float4*>(tc + j * 8);
+              bf16x8 v;
+              *reinterpret_cast<uint4*>(&v) = st[u];
+              float f[8];
+              unpack8(v, f);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 k2 = cf[i];                                   // (scale, shift) of two channels
+                float y0 = fmaf(f[2 * i], k2.x, k2.y), y1 = fmaf(f[2 * i + 1], k2.z, k2.w);
+                if (act) {
+                  y0 = silu_tanh(y0);
+                  y1 = silu_tanh(y1);
+                }
+                f[2 * i] = y0;
+                f[2 * i + 1] = y1;
+              }
+              v = pack8(f);
+              st[u] = *reinterpret_cast<const uint4*>(&v);
+            }
+            ptx::fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async reads
+          }
+          ptx::mbar_arrive(a_ready0 + 8u * sa);
+          if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+        }
+        base += p.seg_chunks[s] * kChunkK;
+      }
+    }
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tcgen05_fence_after();
+    if (threadIdx.x == 64) CSD_TS(5);
     const int spitch = cb;                            // staging row pitch in elements
     __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(__cvta_shared_to_generic(smem_base));
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (kTPix / 2));
@@ -678,6 +765,7 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (threadIdx.x == 64) CSD_TS(9);
     // Phase B
     const int V = cb >> 3;                            // 16-byte vectors per pixel
     const int ppass = min(256 / V, 32);               // pixels handled per pass (bounds the reduction scratch)
@@ -745,6 +833,7 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         sp[1] = a2;
       }
     }
+    if (threadIdx.x == 64) CSD_TS(6);
   }
 
   ptx::tcgen05_fence_before();
@@ -752,6 +841,7 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   if (warp == 1) {
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc(tmem_base, kTPix);
+    if (lane == 0) CSD_TS(7);
   }
 }
 
@@ -827,8 +917,10 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   p.tmem_cols = t_mode ? kTPix : next_pow2_cols(d->n_tile * mt);
 
   int k_total = 0;
+  int k_total_chan = 0;  // padded channels over all segments (one (scale, shift) slot each)
   for (int s = 0; s < d->nseg; ++s) {
     const csd_conv_segment& sg = d->seg[s];
+    k_total_chan += ceil_div(sg.c_cnt, kChunkK) * kChunkK;
     CSD_REQUIRE(sg.a != nullptr, "segment %d: null tensor", s);
     CSD_REQUIRE(sg.taps == 1 || sg.taps == 9, "segment %d: taps=%d (1 or 9)", s, sg.taps);
     CSD_REQUIRE(sg.pitch % 8 == 0 && sg.c_cnt >= 1 && sg.c_off >= 0 && sg.c_off + sg.c_cnt <= sg.pitch,
@@ -838,6 +930,12 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     p.seg_coff[s] = sg.c_off;
     p.seg_kbase[s] = k_total / kChunkK;
     k_total += sg.taps * p.seg_chunks[s] * kChunkK;
+    CSD_REQUIRE(sg.norm == nullptr || (t_mode && sg.c_off == 0),
+                "segment %d: the fused GroupNorm prologue needs the transposed halo mode and c_off == 0", s);
+    p.seg_norm[s] = sg.norm;
+    p.seg_silu[s] = sg.norm_silu;
+    p.seg_ccnt[s] = sg.c_cnt;
+    if (sg.norm != nullptr) p.has_norm = 1;
     // 4-D map over [batch, h, w, c]; dim 0 stops at the last valid channel so the remainder of a
     // 32-channel chunk is zero-filled instead of reading the neighbouring channels.
     const uint64_t z_extra = (uint64_t)(d->z_batches - 1) * (uint64_t)d->a_batch_step;
@@ -914,9 +1012,18 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     // only taken when the weight ring is already at its maximum depth.
     if (bs == kMaxBStages && budget_h - 3 * (int)p.a_stage_bytes >= kMaxBStages * (int)p.b_stage_bytes) p.a_stages = 3;
     CSD_REQUIRE(bs >= 2, "halo mode: not enough shared memory for the weight ring (n_tile=%d mt=%d)", d->n_tile, mt);
+    size_t tail = 8 * (2 * kMaxAStages + 2 * kMaxBStages + 2) + 4 * 512;
+    if (t_mode && p.has_norm) {
+      // TMA -> transform -> MMA: three halo buffers (one loading, one being normalised, one feeding the tensor
+      // core), the a_ready barriers and the (scale, shift) table of every K channel
+      tail = 8 * (2 * kMaxAStages + 2 * kMaxBStages + 2) + 8 * kMaxAStages + (size_t)k_total_chan * 8 + 16;
+      p.a_stages = 3;
+      bs = ((int)(113 * 1024 - 1024 - tail) - p.a_stages * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
+      if (bs > kMaxBStages) bs = kMaxBStages;
+      CSD_REQUIRE(bs >= 3, "fused GroupNorm prologue: not enough shared memory for the weight ring");
+    }
     p.b_stages = bs;
-    L->smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 +
-              8 * (2 * kMaxAStages + 2 * kMaxBStages + 2) + 4 * 512;
+    L->smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + tail;
     if (t_mode) L->grid.y = (unsigned)ceil_div(d->n_store, kTChan);
   }
   p.stat_partials = t_mode ? d->stat_partials : nullptr;

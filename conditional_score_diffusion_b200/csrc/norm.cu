@@ -178,6 +178,35 @@ __global__ void gn_apply_kernel(GnParams p) {
   }
 }
 
+// (scale, shift) per (image, channel) of a GroupNorm over the channel concatenation of up to two tensors:
+// coef[b, c] = (rstd_g * gamma_c, beta_c - mean_g * rstd_g * gamma_c), written per source tensor so that a
+// convolution segment can look its channels up directly. Consumed by the fused GroupNorm+SiLU prologue of
+// the transposed convolution kernel (conv_gemm.cu), which replaces gn_apply for those layers.
+// grid = batch, block = 256. cpg <= 18 for every NCSN++ width, so the per-channel group loop is short.
+__global__ void __launch_bounds__(256)
+gn_coeffs_kernel(const float* __restrict__ sums0, int c0, const float* __restrict__ sums1, int c1,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float2* __restrict__ coef0,
+                 float2* __restrict__ coef1, int hw, int cpg, float eps) {
+  const int b = blockIdx.x, C = c0 + c1;
+  const float inv_n = 1.f / ((float)hw * (float)cpg);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g0 = (c / cpg) * cpg;
+    float su = 0.f, sq = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      const int cc = g0 + i;
+      const float* sp = (cc < c0) ? sums0 + ((long long)b * c0 + cc) * 2 : sums1 + ((long long)b * c1 + (cc - c0)) * 2;
+      su += sp[0];
+      sq += sp[1];
+    }
+    const float mean = su * inv_n;
+    const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+    const float sc = rsqrtf(var + eps) * gamma[c];
+    const float2 v = make_float2(sc, beta[c] - mean * sc);
+    if (c < c0) coef0[(long long)b * c0 + c] = v;
+    else coef1[(long long)b * c1 + (c - c0)] = v;
+  }
+}
+
 static int gn_fill(GnParams& p, const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1, int batch,
                    int hw, int groups, int* threads, size_t* smem) {
   CSD_REQUIRE(src0 != nullptr && c0 >= 8 && c0 % 8 == 0 && pitch0 % 8 == 0 && c0 <= pitch0,
@@ -389,6 +418,21 @@ int csd_gn_apply_bf16(const void* src0, int c0, int pitch0, const float* sums0, 
   p.eps = eps; p.silu = apply_silu;
   gn_apply_kernel<<<batch * p.slabs, threads, smem, static_cast<cudaStream_t>(stream)>>>(p);
   CSD_LAUNCH_CHECK("gn_apply_kernel");
+  return CSD_OK;
+}
+
+int csd_gn_coeffs_f32(const float* sums0, int c0, const float* sums1, int c1, const float* gamma, const float* beta,
+                      float* coef0, float* coef1, int batch, int hw, int groups, float eps, csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(sums0 && gamma && beta && coef0 && batch >= 1 && hw >= 1 && c0 >= 1, "gn_coeffs: bad arguments");
+  if (sums1 == nullptr) c1 = 0;
+  CSD_REQUIRE(c1 == 0 || coef1 != nullptr, "gn_coeffs: second source without its coefficient output");
+  CSD_REQUIRE(groups >= 1 && (c0 + c1) % groups == 0, "gn_coeffs: %d channels not divisible by %d groups", c0 + c1,
+              groups);
+  gn_coeffs_kernel<<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums0, c0, sums1, c1, gamma, beta, reinterpret_cast<float2*>(coef0), reinterpret_cast<float2*>(coef1), hw,
+      (c0 + c1) / groups, eps);
+  CSD_LAUNCH_CHECK("gn_coeffs_kernel");
   return CSD_OK;
 }
 

@@ -155,15 +155,38 @@ class BlockOps:
                      groups, 1e-6, silu)
         return Act(out, c)
 
+    def gn_coeffs(self, srcs, gamma, beta):
+        """(scale, shift) tables of GroupNorm over the concatenation of `srcs`, one [B, c, 2] tensor per source:
+        the fused-prologue replacement of group_norm() for convolutions that run in the transposed mode."""
+        b, h, w, _ = srcs[0].shape
+        c = sum(a.c for a in srcs)
+        s0 = srcs[0]
+        s1 = srcs[1] if len(srcs) > 1 else None
+        sums0 = self.ensure_sums(s0)
+        sums1 = self.ensure_sums(s1) if s1 is not None else None
+        coef0 = self.pool.get((b, s0.c, 2), torch.float32)
+        coef1 = self.pool.get((b, s1.c, 2), torch.float32) if s1 is not None else None
+        self.rec.add(K.gn_coeffs, sums0, s0.c, sums1, s1.c if s1 else 0, gamma, beta, coef0, coef1, h * w, _groups(c),
+                     1e-6)
+        return [coef0] + ([coef1] if s1 is not None else [])
+
+    @staticmethod
+    def fusable(srcs, cout):
+        """GroupNorm+SiLU can ride in the convolution's prologue when the 3x3 conv runs in the transposed mode."""
+        _, h, w, _ = srcs[0].shape
+        return (K.FUSE_GN_DEFAULT and K.TRANSPOSED_DEFAULT and cout >= 32 and cout % 8 == 0
+                and K.transposed_shape_ok(h, w) and all(a.c % 8 == 0 for a in srcs))
+
     def conv(self, segs, pc, out_hw=None, temb=None, temb_pitch=0, res=None, scale=1.0, stride=1, pad=1,
              out=None):
-        """segs: list of (Act, taps). pc: PackedConv. Returns Act [B, oh, ow, n_store]."""
+        """segs: list of (Act, taps[, coef]); coef = fused GroupNorm+SiLU table of that segment (gn_coeffs).
+        pc: PackedConv. Returns Act [B, oh, ow, n_store]."""
         a0 = segs[0][0]
         b, ih, iw, _ = a0.shape
         oh, ow = out_hw if out_hw is not None else (ih, iw)
         if out is None:
             out = self.pool.get((b, oh, ow, pc.n_store))
-        seg_list = [(a.t, a.pitch, 0, a.c, taps) for a, taps in segs]
+        seg_list = [(sg[0].t, sg[0].pitch, 0, sg[0].c, sg[1], sg[2] if len(sg) > 2 else None, True) for sg in segs]
         use_t = (K.TRANSPOSED_DEFAULT and pc.cout >= 32 and K.transposed_eligible(seg_list, oh, ow, stride, pad))
         partials = sums = None
         if use_t and pc.cout % 8 == 0:
@@ -200,30 +223,44 @@ class BlockOps:
         skip 1x1 weights as extra K segments when the block has Conv_2 / NIN_0), flags.
         srcs: 1 or 2 Acts (the up path passes [h, skip] instead of materialising torch.cat).
         """
-        a0 = self.group_norm(srcs, pk["gn0_w"], pk["gn0_b"], True)
         raw = list(srcs)
         own_raw = False
-        if pk["up"] or pk["down"]:
-            mode = "up" if pk["up"] else "down"
-            assert len(srcs) == 1
-            a0r = self.fir(a0, mode, fir_taps)
-            self.release(a0)
-            a0 = a0r
-            raw = [self.fir(srcs[0], mode, fir_taps)]
-            own_raw = True
+        resample = pk["up"] or pk["down"]
         temb = tproj[:, pk["temb_off"]:] if tproj is not None else None
-        h1 = self.conv([(a0, 9)], pk["conv0"], temb=temb, temb_pitch=tproj_pitch)
-        self.release(a0)
-        a1 = self.group_norm([h1], pk["gn1_w"], pk["gn1_b"], True)
-        self.release(h1)
+        if not resample and self.fusable(srcs, pk["out_ch"]):
+            # GroupNorm_0 + SiLU in the prologue of Conv_0: one 9-tap segment per source, no normalised copy
+            coefs = self.gn_coeffs(srcs, pk["gn0_w"], pk["gn0_b"])
+            h1 = self.conv([(a, 9, cf) for a, cf in zip(srcs, coefs)], pk["conv0_split"], temb=temb,
+                           temb_pitch=tproj_pitch)
+            for cf in coefs:
+                self.pool.put(cf)
+        else:
+            a0 = self.group_norm(srcs, pk["gn0_w"], pk["gn0_b"], True)
+            if resample:
+                mode = "up" if pk["up"] else "down"
+                assert len(srcs) == 1
+                a0r = self.fir(a0, mode, fir_taps)
+                self.release(a0)
+                a0 = a0r
+                raw = [self.fir(srcs[0], mode, fir_taps)]
+                own_raw = True
+            h1 = self.conv([(a0, 9)], pk["conv0"], temb=temb, temb_pitch=tproj_pitch)
+            self.release(a0)
         scale = SQRT1_2 if skip_rescale else 1.0
+        if self.fusable([h1], pk["out_ch"]):
+            (cf,) = self.gn_coeffs([h1], pk["gn1_w"], pk["gn1_b"])
+            first, a1 = (h1, 9, cf), None
+        else:
+            a1 = self.group_norm([h1], pk["gn1_w"], pk["gn1_b"], True)
+            first, cf = (a1, 9), None
         if pk["has_skip_conv"]:
-            segs = [(a1, 9)] + [(r, 1) for r in raw]
-            out = self.conv(segs, pk["conv1"], scale=scale)
+            out = self.conv([first] + [(r, 1) for r in raw], pk["conv1"], scale=scale)
         else:
             assert len(raw) == 1
-            out = self.conv([(a1, 9)], pk["conv1"], res=raw[0], scale=scale)
-        self.release(a1)
+            out = self.conv([first], pk["conv1"], res=raw[0], scale=scale)
+        self.release(h1, a1)
+        if cf is not None:
+            self.pool.put(cf)
         if own_raw:
             self.release(*raw)
         return out
@@ -308,6 +345,7 @@ class NetEngine:
         pk["gn0_w"], pk["gn0_b"] = _gn_params(m.GroupNorm_0, device)
         pk["gn1_w"], pk["gn1_b"] = _gn_params(m.GroupNorm_1, device)
         pk["conv0"] = PackedConv([m.Conv_0.weight.detach()], m.Conv_0.bias, device)
+        pk["conv0_w"], pk["conv0_b"] = m.Conv_0.weight.detach(), m.Conv_0.bias
         if hasattr(m, "Dense_0"):
             pk["temb_off"] = sum(w.shape[0] for w in dense_w)
             dense_w.append(m.Dense_0.weight.detach().to(device=device, dtype=torch.float32))
@@ -329,6 +367,22 @@ class NetEngine:
         pk["skip_w"], pk["skip_b"] = skip_w, skip_b
         pk["in_ch"], pk["out_ch"] = m.Conv_0.weight.shape[1], m.Conv_0.weight.shape[0]
         return pk
+
+    @staticmethod
+    def finish_conv0(pk, split, device):
+        """Conv_0 packed with one K segment per raw input source (the fused-prologue form: the concatenation is
+        never materialised, so every source is its own 9-tap segment)."""
+        if len(split) == 1:
+            return pk["conv0"]
+        key = ("conv0", tuple(split))
+        if key not in pk:
+            ws, off = [], 0
+            for c in split:
+                ws.append(pk["conv0_w"][:, off:off + c])
+                off += c
+            assert off == pk["conv0_w"].shape[1]
+            pk[key] = PackedConv(ws, pk["conv0_b"], device)
+        return pk[key]
 
     @staticmethod
     def finish_resblock(pk, split, device):
@@ -471,6 +525,7 @@ class NetPlan:
             pc1 = eng.finish_resblock(p, [a.c for a in srcs], dev)
             p = dict(p)
             p["conv1"] = pc1
+            p["conv0_split"] = eng.finish_conv0(pk[idx], [a.c for a in srcs], dev)
             return ops.resblock(p, srcs, tproj if p["temb_off"] is not None else None, tpitch, fir_taps, skip_rescale)
 
         hs = [ops.conv([(xin, 9)], pk[m_idx])]

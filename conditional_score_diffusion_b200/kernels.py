@@ -82,6 +82,9 @@ def pick_tile(h, w, batch):
 
 
 TRANSPOSED_DEFAULT = os.environ.get("CSD_NO_TRANSPOSED", "0") != "1"
+# GroupNorm+SiLU applied inside the transposed convolution (no normalised copy in HBM); CSD_NO_FUSE_GN=1 keeps
+# the separate gn_apply pass (A/B measurements).
+FUSE_GN_DEFAULT = os.environ.get("CSD_NO_FUSE_GN", "0") != "1"
 
 
 def transposed_eligible(segments, h, w, stride=1, pad=1, z_batches=1):
@@ -92,13 +95,19 @@ def transposed_eligible(segments, h, w, stride=1, pad=1, z_batches=1):
             and (h % 32 == 0 or h >= 64))
 
 
+def transposed_shape_ok(h, w):
+    return w % 8 == 0 and (h % 32 == 0 or h >= 64)
+
+
 def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None, n_tile=None,
               tile=None, bias=None, bias_per_row=False, temb=None, temb_pitch=0, res=None,
               res_pitch=0, scale=1.0, out_f32=None, z_batches=1, a_batch_step=0, wt_batch_stride=0,
               out_z_stride=0, res_z_stride=0, wt_pitch=0, wt_k_off=0, k_valid=0, wt_rows=None,
               stride=1, pad=1, in_h=0, in_w=0, halo=None, mt=None, transposed=None, stat_partials=None):
-    """Launch csd_conv_gemm. segments: list of (tensor, pitch, c_off, c_cnt, taps)."""
+    """Launch csd_conv_gemm. segments: list of (tensor, pitch, c_off, c_cnt, taps[, norm, norm_silu]): `norm` is the
+    [batch, c_cnt, 2] (scale, shift) table of gn_coeffs for the fused GroupNorm(+SiLU) prologue (transposed mode)."""
     _require_cuda(wt, out, bias, temb, res, *[s[0] for s in segments])
+    segments = [tuple(s) + (None, True)[len(s) - 5:] for s in segments]
     d = ConvGemmDesc()
     d.batch, d.h, d.w = batch, h, w
     d.in_h, d.in_w, d.stride, d.pad = in_h, in_w, stride, pad
@@ -108,13 +117,17 @@ def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None
     nt_ = n_tile if n_tile is not None else None
     d.nseg = len(segments)
     k_total = 0
-    for i, (a, pitch, c_off, c_cnt, taps) in enumerate(segments):
+    for i, (a, pitch, c_off, c_cnt, taps, norm, norm_silu) in enumerate(segments):
         assert a.dtype == _BF16
         d.seg[i].a = a.data_ptr()
         d.seg[i].pitch = pitch
         d.seg[i].c_off = c_off
         d.seg[i].c_cnt = c_cnt
         d.seg[i].taps = taps
+        if norm is not None:
+            assert norm.dtype == torch.float32 and norm.is_cuda and norm.numel() == batch * c_cnt * 2
+            d.seg[i].norm = norm.data_ptr()
+            d.seg[i].norm_silu = int(bool(norm_silu))
         k_total += taps * ceil_to(c_cnt, 32)
     d.n = n
     d.n_store = n_store if n_store is not None else n
@@ -289,6 +302,14 @@ def gn_chan_stats(src, c, chan_sums):
 def gn_finalize_partials(partials, chan_sums, batch, tiles_per_img, c):
     check(_lib.lib().csd_gn_finalize_partials_f32(_ptr(partials), _ptr(chan_sums), batch, tiles_per_img, c, _stream()))
     return chan_sums
+
+
+def gn_coeffs(sums0, c0, sums1, c1, gamma, beta, coef0, coef1, hw, groups, eps=1e-6):
+    """(scale, shift) tables of GroupNorm over cat(src0, src1) for the fused conv prologue: coef_i [B, c_i, 2]."""
+    b = sums0.shape[0]
+    check(_lib.lib().csd_gn_coeffs_f32(_ptr(sums0), c0, _ptr(sums1), c1, _ptr(gamma), _ptr(beta), _ptr(coef0),
+                                       _ptr(coef1), b, hw, groups, float(eps), _stream()))
+    return coef0, coef1
 
 
 def gn_apply(src0, c0, sums0, src1, c1, sums1, gamma, beta, out, groups, eps=1e-6, silu=True):

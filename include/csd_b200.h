@@ -145,6 +145,15 @@ int csd_gn_apply_bf16(const void* src0, int c0, int pitch0, const float* sums0, 
                       int out_pitch, int batch, int hw, int groups, float eps, int apply_silu,
                       csd_stream_t stream);
 
+/* Fused-prologue form of the GroupNorm above: instead of writing the normalised tensor, write per (image,
+ * channel) the pair (scale, shift) = (rstd_g * gamma_c, beta_c - mean_g * rstd_g * gamma_c) of the GroupNorm
+ * over cat(src0, src1), split per source: coef0 [batch, c0, 2], coef1 [batch, c1, 2] fp32. A csd_conv_gemm
+ * segment that carries such a table (csd_conv_segment.norm) applies y = SiLU(x * scale + shift) to its
+ * operand tile in shared memory, so GroupNorm -> SiLU -> conv3x3 (models/layerspp.py:242-266) is one kernel
+ * and the normalised activation never exists in HBM.                                              */
+int csd_gn_coeffs_f32(const float* sums0, int c0, const float* sums1, int c1, const float* gamma, const float* beta,
+                      float* coef0, float* coef1, int batch, int hw, int groups, float eps, csd_stream_t stream);
+
 /* Depthwise separable FIR resampling of an NHWC bf16 tensor with the [1,3,3,1] family
  * (up_or_down_sampling.upsample_2d / downsample_2d, models/up_or_down_sampling.py:195-257):
  * mode 1 = up x2 (pad (2,1), gain 4), mode 2 = down x2 (pad (1,1)), mode 3 = same-rate pre-filter with
@@ -187,6 +196,10 @@ typedef struct csd_conv_segment {
   int32_t c_off;       /* first channel used                                            */
   int32_t c_cnt;       /* channels used (zero-filled up to the next multiple of 32)     */
   int32_t taps;        /* 1 or 9                                                         */
+  const float* norm;   /* mode 2 only: [batch, c_cnt, 2] (scale, shift) from csd_gn_coeffs_f32; the kernel
+                          feeds act(x * scale + shift) to the MMA instead of x. NULL = raw operand      */
+  int32_t norm_silu;   /* 1 = SiLU after the affine map (GroupNorm -> SiLU), 0 = affine only           */
+  int32_t reserved_;
 } csd_conv_segment;
 
 typedef struct csd_conv_gemm_desc {

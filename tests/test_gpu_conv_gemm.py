@@ -424,3 +424,80 @@ def test_transposed_timing():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5
             print(f"[conv timing] {H}x{H} {cin}->{cout} {label:10s}: {ms:.3f} ms  {flops / ms / 1e9:.0f} TFLOP/s")
+
+
+def _t_norm_case(name, B, H, W, cins, cout, seed=0, silu=True, skip_c=0):
+    """Transposed mode with the fused GroupNorm(+SiLU) prologue: segments carry (scale, shift) tables and the
+    kernel feeds act(x * scale + shift) to the MMA. Reference: the same map in fp32, rounded to bf16 (what
+    gn_apply would have stored), then torch conv2d in fp32. Out-of-image taps must see zeros (padding of the
+    normalised tensor), which a naive transform of the zero-filled halo would break (act(shift) != 0)."""
+    k = _kern()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(seed)
+    xs, coefs, normed = [], [], []
+    for c in cins:
+        x = torch.randn(B, c, H, W, device=dev, generator=g).to(torch.bfloat16)
+        sc = torch.rand(B, c, device=dev, generator=g) + 0.5
+        sh = torch.randn(B, c, device=dev, generator=g)
+        y = x.float() * sc[:, :, None, None] + sh[:, :, None, None]
+        if silu:
+            y = F.silu(y)
+        xs.append(x)
+        coefs.append(torch.stack([sc, sh], dim=-1).contiguous())
+        normed.append(y.to(torch.bfloat16).float())
+    cin = sum(cins)
+    wgt = (torch.randn(cout, cin, 3, 3, device=dev, generator=g) / math.sqrt(9 * cin)).to(torch.bfloat16)
+    ref = F.conv2d(torch.cat(normed, 1), wgt.float(), padding=1)
+    parts, off = [], 0
+    for c in cins:
+        parts.append(k.pack_conv_weight(wgt[:, off:off + c]))
+        off += c
+    segs = [(_nhwc(x), c, 0, c, 9, cf, silu) for x, c, cf in zip(xs, cins, coefs)]
+    if skip_c:
+        xr = torch.randn(B, skip_c, H, W, device=dev, generator=g).to(torch.bfloat16)
+        w1 = (torch.randn(cout, skip_c, 1, 1, device=dev, generator=g) / math.sqrt(skip_c)).to(torch.bfloat16)
+        ref = ref + F.conv2d(xr.float(), w1.float())
+        parts.append(k.pack_conv_weight(w1))
+        segs.append((_nhwc(xr), skip_c, 0, skip_c, 1))
+    wt = torch.cat(parts, dim=1).contiguous()
+    out = torch.full((B, H, W, cout), float("nan"), device=dev, dtype=torch.bfloat16)
+    k.conv_gemm(segs, wt, cout, out, batch=B, h=H, w=W, transposed=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all(), f"{name}: non-finite"
+    return _report(name, out.permute(0, 3, 1, 2), ref, T_NORM_RTOL)
+
+
+# tanh.approx SiLU (rel. error 2^-11) can flip the bf16 rounding of an operand now and then: one extra bf16
+# half-ulp on a few of the K products, far inside the output's own bf16 rounding.
+T_NORM_RTOL = 2.0 ** -7
+
+
+def test_transposed_fused_groupnorm_prologue():
+    assert _t_norm_case("TN 96->96 32x32", 2, 32, 32, [96], 96) < T_NORM_RTOL
+    assert _t_norm_case("TN 96->96 80x80 ragged", 2, 80, 80, [96], 96, seed=1) < T_NORM_RTOL
+    assert _t_norm_case("TN 64->96 24x24 padded cin", 2, 24, 24, [64], 96, seed=2) < T_NORM_RTOL
+    assert _t_norm_case("TN (96+96)->96 64x64 cat + skip", 2, 64, 64, [96, 96], 96, seed=3, skip_c=192) < T_NORM_RTOL
+    assert _t_norm_case("TN (192+96)->192 32x32 cat", 2, 32, 32, [192, 96], 192, seed=4, skip_c=288) < T_NORM_RTOL
+    assert _t_norm_case("TN 192->192 32x32 affine only", 2, 32, 32, [192], 192, seed=5, silu=False) < T_NORM_RTOL
+
+
+def test_gn_coeffs_match_group_norm():
+    k = _kern()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(9)
+    B, H, W, c0, c1 = 3, 16, 16, 192, 96
+    C, groups = c0 + c1, 32
+    a0 = torch.randn(B, H, W, c0, device=dev, generator=g).to(torch.bfloat16)
+    a1 = (torch.randn(B, H, W, c1, device=dev, generator=g) * 2 + 1).to(torch.bfloat16)
+    gamma, beta = torch.randn(C, device=dev, generator=g), torch.randn(C, device=dev, generator=g)
+    s0, s1 = torch.zeros(B, c0, 2, device=dev), torch.zeros(B, c1, 2, device=dev)
+    k.gn_chan_stats(a0, c0, s0)
+    k.gn_chan_stats(a1, c1, s1)
+    f0, f1 = torch.empty(B, c0, 2, device=dev), torch.empty(B, c1, 2, device=dev)
+    k.gn_coeffs(s0, c0, s1, c1, gamma, beta, f0, f1, H * W, groups)
+    torch.cuda.synchronize()
+    x = torch.cat([a0, a1], dim=-1).float().permute(0, 3, 1, 2)
+    ref = F.group_norm(x, groups, gamma, beta, eps=1e-6)
+    coef = torch.cat([f0, f1], dim=1)
+    got = x * coef[:, :, 0, None, None] + coef[:, :, 1, None, None]
+    assert (got - ref).abs().max().item() < 2e-4 * ref.abs().max().item()

@@ -33,7 +33,7 @@ for fn, a, kw, e0, e1 in evs:
     by_kind[name][0] += 1; by_kind[name][1] += ms
     if fn is K.conv_gemm:
         segs, _, n, _ = a
-        k_real = sum(t * c for (_, _, _, c, t) in segs)
+        k_real = sum(sg[4] * sg[3] for sg in segs)
         pix = kw["batch"] * kw["h"] * kw["w"] * kw.get("z_batches", 1)
         key = ("conv", kw["h"], kw["w"], n, k_real, len(segs), kw.get("z_batches", 1))
         by_shape[key][0] += 1; by_shape[key][1] += ms; by_shape[key][2] += 2.0 * pix * n * k_real
