@@ -19,6 +19,7 @@
 #include "tensormap.cuh"
 #include "../../include/csd_b200.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace csd {
@@ -29,8 +30,15 @@ namespace csd {
     if (p.debug_ts != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) \
       p.debug_ts[i] = clock64();                                                         \
   } while (0)
+// persistent kernel: timestamps of the probe CTA's 6th tile, one slot per role event
+#define CSD_TSP(i)                                                                          \
+  do {                                                                                    \
+    if (p.debug_ts != nullptr && blockIdx.x == gridDim.x / 2 && tile == (int)blockIdx.x + 5 * (int)gridDim.x) \
+      p.debug_ts[i] = clock64();                                                          \
+  } while (0)
 #else
 #define CSD_TS(i) do { } while (0)
+#define CSD_TSP(i) do { } while (0)
 #endif
 
 constexpr int kChunkK = 32;                       // channels per pipeline stage
@@ -62,6 +70,8 @@ struct ConvGemmKernelParams {
   int seg_kbase[CSD_MAX_SEGMENTS];
   uint32_t a_stage_bytes, b_stage_bytes;
   // transposed mode: fused GroupNorm(+SiLU) prologue (per-segment (scale, shift) tables [batch, c_cnt, 2])
+  int num_tiles, n_blocks;   // persistent transposed kernel: tiles = spatial tiles x 128-channel blocks
+  int out_box_c;             // channel extent of its TMA store box = staging row pitch
   const float* seg_norm[CSD_MAX_SEGMENTS];
   int seg_silu[CSD_MAX_SEGMENTS];
   int seg_ccnt[CSD_MAX_SEGMENTS];
@@ -845,6 +855,387 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Persistent form of the transposed halo kernel (the one the engine launches for mode 2).
+//
+// conv_halo_t_kernel above spends ~45% of each CTA's life outside its main loop (pipeline fill ~3.5k
+// cycles, epilogue ~8.7k cycles against ~6.9k tensor cycles for a 96-channel layer; measured with
+// tools/conv_phase_timing.py) and relies on a second resident CTA to fill the gap. Here ONE CTA per SM
+// walks a static list of tiles (tile = blockIdx.x + i * gridDim.x) with five specialised roles:
+//   warp 0      TMA producer      pixel halos + weight slabs, rings shared by consecutive tiles
+//   warp 1      MMA issuer        accumulator alternates between two 256-column TMEM buffers
+//   warps 2-5   operand transform fused GroupNorm(+SiLU) of every pixel-halo stage (when a segment has `norm`)
+//   warps 6-13  epilogue          TMEM -> staging smem -> coalesced NHWC rows (+residual, scale, GN partial sums)
+// so the epilogue of tile i, the main loop of tile i+1 and the loads/transforms of tile i+2 overlap, and
+// the fill/drain cost is paid once per SM instead of once per tile. The whole 227 KB of shared memory
+// belongs to the CTA: 3 pixel-halo buffers, up to 12 weight slabs, a dedicated 64 KB staging tile.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPThreads = 448;
+constexpr int kPTransformThreads = 128;
+constexpr int kPEpiThreads = 256;
+constexpr int kPMaxBStages = 12;
+constexpr int kPStagePitch = 128;                                  // staging row pitch (channels), constant
+constexpr int kPStagingBytes = kTPix * kPStagePitch * 2;           // 64 KB
+constexpr int kPBarBytes = 8 * (3 * kMaxAStages + 2 * kPMaxBStages + 4 + 1) + 8;   // barriers + tmem slot, 16-aligned
+
+struct TileCoord {
+  int b, h0, w0, n0, sp;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmKernelParams& p, int tile) {
+  TileCoord t;
+  const int nb = tile % p.n_blocks;
+  t.sp = tile / p.n_blocks;
+  const int tw = t.sp % p.tiles_w;
+  const int r = t.sp / p.tiles_w;
+  const int th = r % p.tiles_h;
+  t.b = r / p.tiles_h;
+  t.w0 = tw * kHaloTW;
+  t.h0 = th * kTRows;
+  t.n0 = nb * kTChan;
+  return t;
+}
+
+__global__ void __launch_bounds__(kPThreads, 1)
+conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                    const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+                    const ConvGemmKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;                                   // pixel halos
+  const uint32_t b_base = a_base + p.a_stages * p.a_stage_bytes;       // weight slabs
+  const uint32_t stage_base = b_base + p.b_stages * p.b_stage_bytes;   // epilogue staging tile (1 KB aligned)
+  const uint32_t bar_base = stage_base + kPStagingBytes;
+  const uint32_t a_full0 = bar_base, a_empty0 = a_full0 + 8u * kMaxAStages, a_ready0 = a_empty0 + 8u * kMaxAStages;
+  const uint32_t b_full0 = a_ready0 + 8u * kMaxAStages, b_empty0 = b_full0 + 8u * kPMaxBStages;
+  const uint32_t tmem_full0 = b_empty0 + 8u * kPMaxBStages, tmem_empty0 = tmem_full0 + 16u;
+  const uint32_t tmem_slot = tmem_empty0 + 16u;
+  const uint32_t coef_addr = bar_base + kPBarBytes;                    // float2 per padded K channel
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&mapA0);
+    ptx::prefetch_tensormap(&mapB);
+    ptx::prefetch_tensormap(&mapOut);
+    for (int s = 0; s < p.a_stages; ++s) {
+      ptx::mbar_init(a_full0 + 8u * s, 1);
+      ptx::mbar_init(a_empty0 + 8u * s, 1);
+      ptx::mbar_init(a_ready0 + 8u * s, kPTransformThreads);
+    }
+    for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full0 + 8u * s, 1); ptx::mbar_init(b_empty0 + 8u * s, 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full0 + 8u * s, 1); ptx::mbar_init(tmem_empty0 + 8u * s, kPEpiThreads); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 2 * kTPix);   // both accumulators: all 512 columns (one CTA per SM)
+    ptx::tmem_relinquish();
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t sa = 0, a_par = 1, sb = 0, b_par = 1;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        CSD_TSP(10);
+        for (int s = 0; s < p.nseg; ++s) {
+          const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
+          const int taps = p.seg_taps[s];
+          const int halo = (taps == 9) ? 1 : 0;
+          const uint32_t a_bytes = (uint32_t)((kHaloTW + 2 * halo) * (kTRows + 2 * halo) * kRowBytes);
+          const int nchunks = p.seg_chunks[s];
+          const int kstep = nchunks * kChunkK;
+          for (int c = 0; c < nchunks; ++c) {
+            if (!(p.debug_nodata & 2)) {
+            ptx::mbar_wait(a_empty0 + 8u * sa, a_par);
+            if (s == 0 && c == 0) CSD_TSP(11);
+            ptx::mbar_arrive_expect_tx(a_full0 + 8u * sa, a_bytes);
+            ptx::tma_load_4d(a_base + sa * p.a_stage_bytes, mapA, a_full0 + 8u * sa, p.seg_coff[s] + c * kChunkK,
+                             tc.w0 - halo, tc.h0 - halo, tc.b);
+            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+            }
+            int kcol = p.wt_k_off + (p.seg_kbase[s] + c) * kChunkK;
+            for (int tap = 0; tap < taps; ++tap, kcol += kstep) {
+              if (p.debug_nodata & 1) continue;   // perf experiment: no weight traffic
+              ptx::mbar_wait(b_empty0 + 8u * sb, b_par);
+              ptx::mbar_arrive_expect_tx(b_full0 + 8u * sb, kTChan * kRowBytes);
+              ptx::tma_load_3d(b_base + sb * p.b_stage_bytes, &mapB, b_full0 + 8u * sb, kcol, tc.n0, 0);
+              if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)kTPix);
+      const uint32_t w_hi = ptx::smem_desc_hi(512, kLayoutSw64);
+      const uint32_t a_go0 = p.has_norm ? a_ready0 : a_full0;
+      uint32_t sa = 0, a_par = 0, sb = 0, b_par = 0;
+      uint32_t acc = 0, acc_par = 1;   // a fresh tmem_empty barrier passes a wait on parity 1
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        CSD_TSP(12);
+        ptx::mbar_wait(tmem_empty0 + 8u * acc, acc_par);   // epilogue has drained this accumulator
+        ptx::tcgen05_fence_after();
+        CSD_TSP(0);
+        const uint32_t d_tmem = tmem_base + acc * kTPix;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int nchunks = p.seg_chunks[s];
+          if (p.seg_taps[s] == 9) {
+            constexpr int pitch = kHaloTW + 2;
+            const uint32_t x_hi = ptx::smem_desc_hi(pitch * kRowBytes, kLayoutSw64);
+            for (int c = 0; c < nchunks; ++c) {
+              if (!(p.debug_nodata & 2)) ptx::mbar_wait(a_go0 + 8u * sa, a_par);
+              ptx::tcgen05_fence_after();
+              if (s == 0 && c == 0) CSD_TSP(1);
+              if (s == 0 && c == 1) CSD_TSP(13);
+              const uint32_t x_lo0 = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                if (!(p.debug_nodata & 1)) ptx::mbar_wait(b_full0 + 8u * sb, b_par);
+                ptx::tcgen05_fence_after();
+                const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
+                const uint32_t x_lo = x_lo0 + (uint32_t)((((tap / 3) * pitch + (tap % 3)) * kRowBytes) >> 4);
+                ptx::mma_bf16_ss(d_tmem, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi, x_lo), idesc,
+                                 accumulate);
+                ptx::mma_bf16_ss(d_tmem, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi, x_lo + 2),
+                                 idesc, 1u);
+                accumulate = 1u;
+                ptx::mma_commit(b_empty0 + 8u * sb);
+                if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
+              }
+              ptx::mma_commit(a_empty0 + 8u * sa);
+              if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+            }
+          } else {
+            const uint32_t x_hi = ptx::smem_desc_hi(kHaloTW * kRowBytes, kLayoutSw64);
+            for (int c = 0; c < nchunks; ++c) {
+              ptx::mbar_wait(a_go0 + 8u * sa, a_par);
+              ptx::mbar_wait(b_full0 + 8u * sb, b_par);
+              ptx::tcgen05_fence_after();
+              const uint32_t x_lo = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
+              const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
+              ptx::mma_bf16_ss(d_tmem, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi, x_lo), idesc,
+                               accumulate);
+              ptx::mma_bf16_ss(d_tmem, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi, x_lo + 2),
+                               idesc, 1u);
+              accumulate = 1u;
+              ptx::mma_commit(b_empty0 + 8u * sb);
+              if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
+              ptx::mma_commit(a_empty0 + 8u * sa);
+              if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+            }
+          }
+        }
+        CSD_TSP(2);
+        ptx::mma_commit(tmem_full0 + 8u * acc);
+        if (++acc == 2u) { acc = 0; acc_par ^= 1u; }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== operand transform: fused GroupNorm(+SiLU) of the pixel halos =====
+    // Thread (j, rg): j = logical 16-byte unit (8 channels) of the 64-byte rows, rg = row group. Its 8
+    // (scale, shift) pairs sit in registers for the whole stage; it walks rows rg, rg+32, ... two at a time
+    // (independent load -> math -> store chains). A warp touches 8 consecutive rows x 4 units = 512 contiguous
+    // bytes per access: conflict free. y = SiLU(x*sc + sh) = h + h*tanh(h), h = x*(sc/2) + sh/2: 3 FP + 1 MUFU.
+    if (p.has_norm) {
+      const int tt = threadIdx.x - 64;   // 0..127
+      const int j = tt & 3, rg = tt >> 2;
+      float2* tab = reinterpret_cast<float2*>(__cvta_shared_to_generic(coef_addr));
+      uint32_t sa = 0, a_par = 0;
+      int tab_b = -1;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        if (tc.b != tab_b) {             // (scale, shift) of this image's channels, all segments back to back
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          int base = 0;
+          for (int s = 0; s < p.nseg; ++s) {
+            const int nch = p.seg_chunks[s] * kChunkK;
+            const float2* src = reinterpret_cast<const float2*>(p.seg_norm[s]);
+            const float pre = p.seg_silu[s] ? 0.5f : 1.0f;     // SiLU path stores (sc/2, sh/2)
+            for (int i = tt; i < nch; i += kPTransformThreads) {
+              float2 v = make_float2(0.f, 0.f);
+              if (src != nullptr && i < p.seg_ccnt[s]) v = __ldg(src + (long long)tc.b * p.seg_ccnt[s] + i);
+              tab[base + i] = make_float2(v.x * pre, v.y * pre);
+            }
+            base += nch;
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          tab_b = tc.b;
+        }
+        int base = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const bool norm = p.seg_norm[s] != nullptr;
+          const bool act = p.seg_silu[s] != 0;
+          const int halo = (p.seg_taps[s] == 9) ? 1 : 0;
+          const int pitch = kHaloTW + 2 * halo;
+          const int rows = pitch * (kTRows + 2 * halo);
+          for (int c = 0; c < p.seg_chunks[s]; ++c) {
+            ptx::mbar_wait(a_full0 + 8u * sa, a_par);
+            if (tt == 0 && s == 0 && c == 0) CSD_TSP(8);
+            if (norm) {
+              uint4* st = reinterpret_cast<uint4*>(__cvta_shared_to_generic(a_base + sa * p.a_stage_bytes));
+              float4 cf[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) cf[i] = *reinterpret_cast<const float4*>(tab + base + c * kChunkK + j * 8 + 2 * i);
+              auto row_unit = [&](int r) -> int {     // 16-byte unit index of this thread's channels in row r, or -1
+                const int hy = halo ? r / (kHaloTW + 2) : (r >> 3);
+                const int hx = r - hy * pitch;
+                const int gh = tc.h0 - halo + hy, gw = tc.w0 - halo + hx;
+                const bool ok = r < rows && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;   // conv padding stays zero
+                return ok ? r * 4 + (j ^ ((r >> 1) & 3)) : -1;                          // SWIZZLE_64B unit
+              };
+              auto apply = [&](uint4 raw) -> uint4 {
+                bf16x8 v;
+                *reinterpret_cast<uint4*>(&v) = raw;
+                float f[8];
+                unpack8(v, f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float y0 = fmaf(f[2 * i], cf[i].x, cf[i].y), y1 = fmaf(f[2 * i + 1], cf[i].z, cf[i].w);
+                  if (act) {
+                    float t0, t1;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(y0));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(y1));
+                    y0 = fmaf(y0, t0, y0);
+                    y1 = fmaf(y1, t1, y1);
+                  }
+                  f[2 * i] = y0;
+                  f[2 * i + 1] = y1;
+                }
+                v = pack8(f);
+                return *reinterpret_cast<const uint4*>(&v);
+              };
+              for (int r = rg; r < rows; r += 64) {
+                const int u0 = row_unit(r), u1 = row_unit(r + 32);
+                uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
+                if (u0 >= 0) x0 = st[u0];
+                if (u1 >= 0) x1 = st[u1];
+                x0 = apply(x0);
+                x1 = apply(x1);
+                if (u0 >= 0) st[u0] = x0;
+                if (u1 >= 0) st[u1] = x1;
+              }
+              ptx::fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async reads
+            }
+            ptx::mbar_arrive(a_ready0 + 8u * sa);
+            if (tt == 0 && s == 0 && c == 0) CSD_TSP(9);
+            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+          }
+          base += p.seg_chunks[s] * kChunkK;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue (8 warps) =====
+    // TMEM lane = output channel, column = pixel. Warp w reads lane quadrant w % 4 (the hardware's TMEM access
+    // rule) and one pixel half. Each thread owns ONE channel: out = acc * scale + (bias + temb) * scale, its
+    // GroupNorm partial sums (sum, sum of squares over the valid pixels) are plain register accumulations,
+    // and the bf16 value goes to stage[pixel][channel] (a warp writes 32 consecutive channels of one pixel =
+    // 64 contiguous bytes: conflict free). The accumulator is handed back to the MMA warp as soon as it has
+    // been read; one elected thread then writes the staged 32 x 8 pixel tile to the NHWC output with a single
+    // TMA store (rows beyond the image and channels beyond n_store are clipped by the TMA unit), which
+    // drains while the warps wait for the next accumulator. Residual adds are not done here: the engine
+    // appends the residual as an extra K segment with identity weights, so it rides on the tensor core.
+    const int et = threadIdx.x - 192;                 // 0..255
+    const int q = warp & 3;
+    const int half = (warp - 6) >> 2;                 // 0: pixels [0,128), 1: pixels [128,256)
+    const int cl = q * 32 + lane;                     // channel inside the tile's 128-channel block
+    const int spitch = p.out_box_c;                   // staging row pitch = channel extent of the TMA store box
+    __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(__cvta_shared_to_generic(stage_base));
+    __nv_bfloat16* stage_c = stage + (half * (kTPix / 2)) * spitch + cl;
+    const bool has_stats = p.stat_partials != nullptr;
+    const float scale = p.scale;
+    uint32_t acc = 0, full_par = 0;
+    bool store_pending = false;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int c = tc.n0 + cl;
+      const int cb = min(kTChan, p.n_store - tc.n0);  // channels of this block that are stored (multiple of 8)
+      const bool c_valid = cl < cb;
+      const float add_cs = c_valid ? scale * ((p.bias != nullptr ? __ldg(p.bias + c) : 0.f) +
+                                              (p.temb != nullptr ? __ldg(p.temb + (long long)tc.b * p.temb_pitch + c) : 0.f))
+                                   : 0.f;
+      // valid pixel columns of this half (rows beyond the image) and valid pixels per 8-pixel row (ragged width;
+      // the engine only launches w % 8 == 0, where w_lim is always 8)
+      const int w_lim = min(kHaloTW, p.W - tc.w0);
+      const int m_lim = (w_lim == kHaloTW ? min(kTPix, (p.H - tc.h0) * kHaloTW) - half * (kTPix / 2) : 0);
+      const int m_lim_h = min(kTPix, (p.H - tc.h0) * kHaloTW) - half * (kTPix / 2);
+      if (et == 0) CSD_TSP(3);
+      ptx::mbar_wait(tmem_full0 + 8u * acc, full_par);
+      ptx::tcgen05_fence_after();
+      if (et == 0) CSD_TSP(4);
+      if (et == 0 && store_pending) ptx::bulk_wait_group_read0();   // previous tile's store has left the staging tile
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const uint32_t t_row = tmem_base + acc * kTPix + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (kTPix / 2));
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int col = 0; col < kTPix / 2; col += 32) {
+        uint32_t r0[16], r1[16];
+        __syncwarp();
+        ptx::tmem_ld_x16(t_row + col, r0);
+        ptx::tmem_ld_x16(t_row + col + 16, r1);
+        ptx::tmem_ld_wait();
+        if (c_valid) {
+          __nv_bfloat16* sp = stage_c + col * spitch;
+          if (col + 32 <= m_lim) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = fmaf(__uint_as_float(i < 16 ? r0[i] : r1[i - 16]), scale, add_cs);
+              s1 += v;
+              s2 = fmaf(v, v, s2);
+              sp[i * spitch] = __float2bfloat16_rn(v);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = fmaf(__uint_as_float(i < 16 ? r0[i] : r1[i - 16]), scale, add_cs);
+              if (col + i < m_lim_h && (i & 7) < w_lim) {
+                s1 += v;
+                s2 = fmaf(v, v, s2);
+              }
+              sp[i * spitch] = __float2bfloat16_rn(v);
+            }
+          }
+        }
+      }
+      ptx::tcgen05_fence_before();
+      ptx::mbar_arrive(tmem_empty0 + 8u * acc);       // accumulator free: the next tile's MMAs may overwrite it
+      if (++acc == 2u) { acc = 0; full_par ^= 1u; }
+      if (has_stats && c_valid) {
+        float2* sp2 = reinterpret_cast<float2*>(p.stat_partials) + ((long long)(tc.sp * 2 + half) * p.n_store + c);
+        *sp2 = make_float2(s1, s2);
+      }
+      ptx::fence_proxy_async_smem();                  // staged tile -> visible to the TMA store (async proxy)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et == 0) {
+        CSD_TSP(5);
+        ptx::tma_store_4d(&mapOut, stage_base, tc.n0, tc.w0, tc.h0, tc.b);
+        ptx::bulk_commit_group();
+      }
+      store_pending = true;
+    }
+    if (et == 0 && store_pending) ptx::bulk_wait_group0();
+  }
+
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc(tmem_base, 2 * kTPix);
+  }
+}
+
 static int next_pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -855,11 +1246,13 @@ static int next_pow2_cols(int n) {
 struct ConvGemmLaunch {
   CUtensorMap mapA[CSD_MAX_SEGMENTS];
   CUtensorMap mapB;
+  CUtensorMap mapOut;
   ConvGemmKernelParams p;
   dim3 grid;
   size_t smem;
   bool halo;
   bool transposed;
+  bool persistent;
 };
 
 int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
@@ -870,6 +1263,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   const bool halo_mode = d->mode == 1 || t_mode;
   L->halo = halo_mode;
   L->transposed = t_mode;
+  L->persistent = false;
   const int mt = t_mode ? 2 : (halo_mode ? (d->mt > 0 ? d->mt : 1) : 1);
   CSD_REQUIRE(halo_mode || (d->tile_w >= 1 && d->tile_h >= 1 && d->tile_b >= 1 &&
                             d->tile_w * d->tile_h * d->tile_b <= kTileM),
@@ -1025,6 +1419,34 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     p.b_stages = bs;
     L->smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + tail;
     if (t_mode) L->grid.y = (unsigned)ceil_div(d->n_store, kTChan);
+    L->persistent = false;
+    static const bool legacy_t = getenv("CSD_T_LEGACY") != nullptr;   // A/B switch: one tile per CTA
+    if (t_mode && !legacy_t) {
+      // persistent kernel: one CTA per SM, whole shared memory
+      L->persistent = true;
+      p.n_blocks = ceil_div(d->n_store, kTChan);
+      p.num_tiles = p.tiles_w * p.tiles_h * tiles_b * p.n_blocks;
+      p.a_stages = 3;
+      const size_t fixed = 1024 + (size_t)p.a_stages * p.a_stage_bytes + kPStagingBytes + kPBarBytes +
+                           (size_t)k_total_chan * 8 + 16;
+      CSD_REQUIRE(fixed + 4 * (size_t)p.b_stage_bytes <= 227 * 1024, "transposed conv: K=%d channels too many for the "
+                  "shared-memory coefficient table", k_total_chan);
+      int pbs = (int)((227 * 1024 - fixed) / p.b_stage_bytes);
+      if (pbs > kPMaxBStages) pbs = kPMaxBStages;
+      p.b_stages = pbs;
+      L->smem = fixed + (size_t)pbs * p.b_stage_bytes;
+      const int sms = num_sms();
+      L->grid = dim3((unsigned)std::min(p.num_tiles, sms), 1, 1);
+      CSD_REQUIRE(d->res == nullptr, "transposed conv: pass the residual as a 1-tap segment with identity weights");
+      // TMA store map over out [batch, h, w, out_pitch], box = 128 (or n_store) channels x 8 x 32 pixels
+      p.out_box_c = std::min(kTChan, d->n_store);
+      uint64_t odims[4] = {(uint64_t)d->n_store, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->batch};
+      uint64_t ostr[3] = {(uint64_t)d->out_pitch * 2, (uint64_t)d->out_pitch * 2 * d->w,
+                          (uint64_t)d->out_pitch * 2 * d->w * d->h};
+      uint32_t obox[4] = {(uint32_t)p.out_box_c, (uint32_t)kHaloTW, (uint32_t)kTRows, 1};
+      int st = encode_tensor_map(&L->mapOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out, odims, ostr, obox, TMA_SW_NONE);
+      if (st != CSD_OK) return st;
+    }
   }
   p.stat_partials = t_mode ? d->stat_partials : nullptr;
   CSD_REQUIRE(d->stat_partials == nullptr || t_mode, "stat_partials are produced by the transposed halo mode only");
@@ -1042,9 +1464,13 @@ int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
     CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CSD_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CSD_CUDA(cudaFuncSetAttribute(conv_halo_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(conv_halo_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  if (L->transposed) {
+  if (L->persistent) {
+    conv_halo_tp_kernel<<<L->grid, kPThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
+                                                                   L->mapB, L->mapOut, L->p);
+  } else if (L->transposed) {
     conv_halo_t_kernel<<<L->grid, kTThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
                                                                    L->mapB, L->p);
   } else if (L->halo) {

@@ -89,6 +89,7 @@ class PackedConv:
         self.bias = torch.zeros(self.n_pad + 16, device=device, dtype=torch.float32)
         if bias is not None:
             self.bias[:cout] = bias.detach().to(device=device, dtype=torch.float32)
+        self.identity_skip = False
 
 
 def nin_as_conv(W):
@@ -171,6 +172,12 @@ class BlockOps:
         return [coef0] + ([coef1] if s1 is not None else [])
 
     @staticmethod
+    def will_transpose(h, w, cout):
+        """3x3 stride-1 convolutions with >= 32 output channels on images that tile into 32x8-pixel macro tiles
+        run in the persistent transposed kernel (output channels on M, 256 pixels on N)."""
+        return K.TRANSPOSED_DEFAULT and cout >= 32 and cout % 8 == 0 and K.transposed_shape_ok(h, w)
+
+    @staticmethod
     def fusable(srcs, cout):
         """GroupNorm+SiLU can ride in the convolution's prologue when the 3x3 conv runs in the transposed mode."""
         _, h, w, _ = srcs[0].shape
@@ -187,11 +194,13 @@ class BlockOps:
         if out is None:
             out = self.pool.get((b, oh, ow, pc.n_store))
         seg_list = [(sg[0].t, sg[0].pitch, 0, sg[0].c, sg[1], sg[2] if len(sg) > 2 else None, True) for sg in segs]
-        use_t = (K.TRANSPOSED_DEFAULT and pc.cout >= 32 and K.transposed_eligible(seg_list, oh, ow, stride, pad))
+        use_t = (self.will_transpose(oh, ow, pc.cout) and K.transposed_eligible(seg_list, oh, ow, stride, pad))
+        if use_t and res is not None:
+            raise CsdError("transposed conv takes its residual as an identity K segment (engine planning error)")
         partials = sums = None
-        if use_t and pc.cout % 8 == 0:
-            # GroupNorm statistics of the output for free: per-tile partial sums from the epilogue
-            tiles_img = math.ceil(oh / 32) * math.ceil(ow / 8)
+        if use_t:
+            # GroupNorm statistics of the output for free: per-(tile, pixel half) partial sums from the epilogue
+            tiles_img = math.ceil(oh / 32) * math.ceil(ow / 8) * 2
             partials = self.pool.get((b * tiles_img, pc.n_store, 2), torch.float32)
             sums = self._stats_slot(b, pc.cout)
         self.rec.add(K.conv_gemm, seg_list, pc.wt, pc.cout, out, batch=b, h=oh, w=ow, n_store=pc.n_store,
@@ -255,6 +264,10 @@ class BlockOps:
             first, cf = (a1, 9), None
         if pk["has_skip_conv"]:
             out = self.conv([first] + [(r, 1) for r in raw], pk["conv1"], scale=scale)
+        elif pk["conv1"].identity_skip:
+            # x + h as one more K segment with identity weights: exact (bf16 x times 1.0 into the fp32 accumulator)
+            assert len(raw) == 1
+            out = self.conv([first, (raw[0], 1)], pk["conv1"], scale=scale)
         else:
             assert len(raw) == 1
             out = self.conv([first], pk["conv1"], res=raw[0], scale=scale)
@@ -385,11 +398,21 @@ class NetEngine:
         return pk[key]
 
     @staticmethod
-    def finish_resblock(pk, split, device):
-        """Build conv1 (+ skip segments). `split`: channel counts of the raw input sources."""
-        key = ("conv1", tuple(split))
+    def finish_resblock(pk, split, device, identity_skip=False):
+        """Build conv1 (+ skip segments). `split`: channel counts of the raw input sources. identity_skip: the
+        block has no skip convolution and its convolutions run in the transposed kernel, whose epilogue takes no
+        residual tensor - the residual is appended as a 1-tap K segment with identity weights instead."""
+        key = ("conv1", tuple(split), identity_skip)
         if key in pk:
             return pk[key]
+        if identity_skip and not pk["has_skip_conv"]:
+            c = pk["out_ch"]
+            assert split == [c] or tuple(split) == (c,)
+            eye = torch.eye(c, device=pk["conv1_w"].device, dtype=pk["conv1_w"].dtype).view(c, c, 1, 1)
+            pc = PackedConv([pk["conv1_w"], eye], pk["conv1_b"], device)
+            pc.identity_skip = True
+            pk[key] = pc
+            return pc
         if pk["has_skip_conv"]:
             ws = [pk["conv1_w"]]
             off = 0
@@ -522,7 +545,9 @@ class NetPlan:
 
         def resblock(idx, srcs):
             p = pk[idx]
-            pc1 = eng.finish_resblock(p, [a.c for a in srcs], dev)
+            _, sh, sw, _ = srcs[0].shape
+            ident = (not (p["up"] or p["down"])) and ops.will_transpose(sh, sw, p["out_ch"])
+            pc1 = eng.finish_resblock(p, [a.c for a in srcs], dev, identity_skip=ident)
             p = dict(p)
             p["conv1"] = pc1
             p["conv0_split"] = eng.finish_conv0(pk[idx], [a.c for a in srcs], dev)

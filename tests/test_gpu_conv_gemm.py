@@ -341,37 +341,47 @@ def _t_case(name, B, H, W, cin, cout, seed=0, temb=True, res=True, stats=True):
     bias = torch.zeros(npad + 16, device=dev)
     bias[:cout] = torch.randn(cout, device=dev, generator=g)
     ref = F.conv2d(x.float(), wgt.float(), padding=1) + bias[:cout].view(1, -1, 1, 1)
-    temb_t = res_t = None
+    temb_t = None
+    segs = [(_nhwc(x), cin, 0, cin, 9)]
     if temb:
         temb_t = torch.zeros(B, npad + 16, device=dev)
         temb_t[:, :cout] = torch.randn(B, cout, device=dev, generator=g)
         ref = ref + temb_t[:, :cout].reshape(B, cout, 1, 1)
     if res:
+        # the transposed kernel takes a residual as one more K segment with identity weights (exact in fp32)
         r = torch.randn(B, cout, H, W, device=dev, generator=g).to(torch.bfloat16)
-        res_t = _nhwc(r)
+        eye = torch.eye(cout, device=dev, dtype=torch.bfloat16).view(cout, cout, 1, 1)
+        wt = torch.cat([wt, k.pack_conv_weight(eye, n_pad=npad)], dim=1).contiguous()
+        segs.append((_nhwc(r), cout, 0, cout, 1))
         ref = ref + r.float()
     ref = ref * 0.5
     n_store = k.ceil_to(cout, 8)
     out = torch.full((B, H, W, n_store), float("nan"), device=dev, dtype=torch.bfloat16)
-    tiles = B * math.ceil(H / 32) * math.ceil(W / 8)
+    tiles = B * math.ceil(H / 32) * math.ceil(W / 8) * 2     # partial sums per (tile, pixel half)
     partials = torch.full((tiles, n_store, 2), float("nan"), device=dev) if stats else None
-    k.conv_gemm([(_nhwc(x), cin, 0, cin, 9)], wt, cout, out, batch=B, h=H, w=W, n_store=n_store, bias=bias, temb=temb_t,
-                temb_pitch=npad + 16, res=res_t, res_pitch=cout, scale=0.5, transposed=True, stat_partials=partials)
+    k.conv_gemm(segs, wt, cout, out, batch=B, h=H, w=W, n_store=n_store, bias=bias, temb=temb_t,
+                temb_pitch=npad + 16, scale=0.5, transposed=True, stat_partials=partials)
     torch.cuda.synchronize()
     assert torch.isfinite(out.float()).all(), f"{name}: non-finite"
     rel = _report(name, out[..., :cout].permute(0, 3, 1, 2), ref, T_RTOL)
     if stats:
+        # the sums are taken from the fp32 values before their bf16 rounding: they differ from the sums of the
+        # stored tensor by at most 2^-9 per element (random sign), bounded here by 1e-3 of the absolute sums
         tp = tiles // B
         ps = partials.view(B, tp, n_store, 2).sum(1)
+        assert torch.isfinite(ps).all(), f"{name}: unwritten statistics partials"
         o32 = out.float().reshape(B, H * W, n_store)
-        assert torch.allclose(ps[..., 0], o32.sum(1), rtol=1e-4, atol=1e-2), f"{name}: channel sums"
-        assert torch.allclose(ps[..., 1], (o32 * o32).sum(1), rtol=1e-4, atol=1e-2), f"{name}: channel sums of squares"
+        e1 = (ps[..., 0] - o32.sum(1)).abs() - 1e-3 * o32.abs().sum(1) - 1e-3
+        e2 = (ps[..., 1] - (o32 * o32).sum(1)).abs() - 2e-3 * (o32 * o32).sum(1) - 1e-3
+        assert e1.max().item() <= 0, f"{name}: channel sums off by {e1.max().item():.3e}"
+        assert e2.max().item() <= 0, f"{name}: channel sums of squares off by {e2.max().item():.3e}"
+        r32 = ref.reshape(B, cout, H * W).sum(2)
+        assert (ps[..., :cout, 0] - r32).abs().max().item() <= 2e-3 * ref.abs().reshape(B, cout, -1).sum(2).max().item()
     return rel
 
 
-# The transposed epilogue stages (acc + bias + temb) as bf16 before the residual add and the final
-# bf16 store: two roundings instead of one, hence 2^-7 instead of 2^-8.
-T_RTOL = 2.0 ** -7
+# One bf16 rounding of the fp32 result (residuals ride on the tensor core as an identity K segment).
+T_RTOL = 2.0 ** -8
 
 
 def test_transposed_halo_mode():

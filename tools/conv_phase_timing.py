@@ -1,26 +1,34 @@
-"""GPU probe: phase timestamps (SM clock) of one mid-grid CTA of the conv kernels.
+"""GPU probe: role timestamps (SM clock) of the 6th tile of one mid-grid CTA of the persistent transposed conv.
 Needs a build with CSD_NVCC_EXTRA=-DCSD_ENABLE_PHASE_TIMESTAMPS."""
-import os, sys, torch
+import math, os, sys, torch
 sys.path.insert(0, ".")
 ts = torch.zeros(16, dtype=torch.int64, device="cuda")
 os.environ["CSD_DEBUG_TS"] = hex(ts.data_ptr())
 from conditional_score_diffusion_b200 import kernels as k
-names = {1: "setup done", 3: "first A full", 8: "second A full", 4: "mma issued", 5: "accum ready", 9: "staged",
-         6: "epi end", 7: "dealloc"}
-for (B, H, cin, cout, with_res) in ((64, 160, 96, 96, False), (64, 160, 96, 96, True), (64, 160, 192, 96, False),
-                                    (64, 80, 192, 192, False)):
-    a = torch.randn(B, H, H, cin, device="cuda").to(torch.bfloat16)
-    wt = k.pack_conv_weight((torch.randn(cout, cin, 3, 3, device="cuda") / 30).to(torch.bfloat16))
-    out = torch.empty(B, H, H, cout, device="cuda", dtype=torch.bfloat16)
-    res = torch.randn(B, H, H, cout, device="cuda").to(torch.bfloat16) if with_res else None
-    for label, kw in [("tap", dict(transposed=False)), ("transposed", dict(transposed=True))]:
-        for rep in range(3):
-            ts.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            k.conv_gemm([(a, cin, 0, cin, 9)], wt, cout, out, batch=B, h=H, w=H, res=res, res_pitch=cout, **kw)
-            e1.record()
-            torch.cuda.synchronize()
-        t = ts.tolist()
-        print(f"H={H} cin={cin} cout={cout} res={with_res} {label}: {e0.elapsed_time(e1)*1e3:.0f} us; cycles since CTA start:",
-              {names[i]: t[i] - t[0] for i in (1, 3, 8, 4, 5, 9, 6, 7) if t[i]})
+names = {10: "prod tile start", 11: "prod A0 slot free", 8: "xform A0 full", 9: "xform A0 done", 12: "mma wants acc",
+         0: "mma acc free", 1: "mma A0 go", 13: "mma A1 go", 2: "mma issued", 3: "epi waits", 4: "epi acc full",
+         5: "epi staged", 6: "epi stored", 7: "epi stats"}
+dev = "cuda"
+for (B, H, cin, cout, full) in ((64, 160, 96, 96, False), (64, 160, 96, 96, True), (64, 160, 192, 96, True), (64, 80, 192, 192, True)):
+    a = torch.randn(B, H, H, cin, device=dev).to(torch.bfloat16)
+    wt = k.pack_conv_weight((torch.randn(cout, cin, 3, 3, device=dev) / 30).to(torch.bfloat16))
+    out = torch.empty(B, H, H, cout, device=dev, dtype=torch.bfloat16)
+    kw = {}
+    seg = (a, cin, 0, cin, 9)
+    if full:   # what the engine launches: fused GroupNorm prologue, temb, residual, statistics
+        coef = torch.rand(B, cin, 2, device=dev)
+        seg = (a, cin, 0, cin, 9, coef, True)
+        tiles = B * math.ceil(H / 32) * math.ceil(H / 8)
+        kw = dict(temb=torch.randn(B, cout + 32, device=dev), temb_pitch=cout + 32,
+                  bias=torch.randn(cout + 32, device=dev), stat_partials=torch.empty(tiles, cout, 2, device=dev))
+    for rep in range(3):
+        ts.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        k.conv_gemm([seg], wt, cout, out, batch=B, h=H, w=H, transposed=True, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+    t = ts.tolist()
+    t0 = min(v for v in t if v)
+    ev = sorted((t[i] - t0, names[i]) for i in names if t[i])
+    print(f"H={H} cin={cin} cout={cout} full={full}: {e0.elapsed_time(e1)*1e3:.0f} us;", ", ".join(f"{n}@{c}" for c, n in ev))
