@@ -862,16 +862,17 @@ conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
 // cycles, epilogue ~8.7k cycles against ~6.9k tensor cycles for a 96-channel layer; measured with
 // tools/conv_phase_timing.py) and relies on a second resident CTA to fill the gap. Here ONE CTA per SM
 // walks a static list of tiles (tile = blockIdx.x + i * gridDim.x) with five specialised roles:
-//   warp 0      TMA producer      pixel halos + weight slabs, rings shared by consecutive tiles
+//   warp 0 / 18 TMA producers     pixel halos / weight slabs (separate threads: independent run-ahead), rings
+//                                 shared by consecutive tiles
 //   warp 1      MMA issuer        accumulator alternates between two 256-column TMEM buffers
-//   warps 2-5   operand transform fused GroupNorm(+SiLU) of every pixel-halo stage (when a segment has `norm`)
-//   warps 6-13  epilogue          TMEM -> staging smem -> coalesced NHWC rows (+residual, scale, GN partial sums)
+//   warps 2-9   operand transform fused GroupNorm(+SiLU) of every pixel-halo stage (when a segment has `norm`)
+//   warps 10-17 epilogue          TMEM -> (scale, bias, temb, GN partial sums) -> staging smem -> one TMA store
 // so the epilogue of tile i, the main loop of tile i+1 and the loads/transforms of tile i+2 overlap, and
 // the fill/drain cost is paid once per SM instead of once per tile. The whole 227 KB of shared memory
 // belongs to the CTA: 3 pixel-halo buffers, up to 12 weight slabs, a dedicated 64 KB staging tile.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kPThreads = 448;
-constexpr int kPTransformThreads = 128;
+constexpr int kPThreads = 608;
+constexpr int kPTransformThreads = 256;
 constexpr int kPEpiThreads = 256;
 constexpr int kPMaxBStages = 12;
 constexpr int kPStagePitch = 128;                                  // staging row pitch (channels), constant
@@ -940,28 +941,40 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer A: pixel halos. Separate from the weight producer so that the halo ring can run a whole
+    //       tile ahead (the transform needs that lead) instead of being throttled by the weight ring's depth =====
     if (lane == 0) {
-      uint32_t sa = 0, a_par = 1, sb = 0, b_par = 1;
+      uint32_t sa = 0, a_par = 1;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         CSD_TSP(10);
         for (int s = 0; s < p.nseg; ++s) {
           const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
-          const int taps = p.seg_taps[s];
-          const int halo = (taps == 9) ? 1 : 0;
+          const int halo = (p.seg_taps[s] == 9) ? 1 : 0;
           const uint32_t a_bytes = (uint32_t)((kHaloTW + 2 * halo) * (kTRows + 2 * halo) * kRowBytes);
-          const int nchunks = p.seg_chunks[s];
-          const int kstep = nchunks * kChunkK;
-          for (int c = 0; c < nchunks; ++c) {
-            if (!(p.debug_nodata & 2)) {
+          for (int c = 0; c < p.seg_chunks[s]; ++c) {
+            if (p.debug_nodata & 2) continue;
             ptx::mbar_wait(a_empty0 + 8u * sa, a_par);
             if (s == 0 && c == 0) CSD_TSP(11);
             ptx::mbar_arrive_expect_tx(a_full0 + 8u * sa, a_bytes);
             ptx::tma_load_4d(a_base + sa * p.a_stage_bytes, mapA, a_full0 + 8u * sa, p.seg_coff[s] + c * kChunkK,
                              tc.w0 - halo, tc.h0 - halo, tc.b);
             if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
-            }
+          }
+        }
+      }
+    }
+  } else if (warp == kPThreads / 32 - 1) {
+    // ===== TMA producer B: one 128-channel x 32-K weight slab per (chunk, tap) =====
+    if (lane == 0) {
+      uint32_t sb = 0, b_par = 1;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        for (int s = 0; s < p.nseg; ++s) {
+          const int taps = p.seg_taps[s];
+          const int nchunks = p.seg_chunks[s];
+          const int kstep = nchunks * kChunkK;
+          for (int c = 0; c < nchunks; ++c) {
             int kcol = p.wt_k_off + (p.seg_kbase[s] + c) * kChunkK;
             for (int tap = 0; tap < taps; ++tap, kcol += kstep) {
               if (p.debug_nodata & 1) continue;   // perf experiment: no weight traffic
@@ -1042,14 +1055,15 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         if (++acc == 2u) { acc = 0; acc_par ^= 1u; }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // ===== operand transform: fused GroupNorm(+SiLU) of the pixel halos =====
     // Thread (j, rg): j = logical 16-byte unit (8 channels) of the 64-byte rows, rg = row group. Its 8
     // (scale, shift) pairs sit in registers for the whole stage; it walks rows rg, rg+32, ... two at a time
-    // (independent load -> math -> store chains). A warp touches 8 consecutive rows x 4 units = 512 contiguous
+    // (independent load -> math -> store chains; the stage is shared-memory-latency bound, hence 8 warps).
+    // A warp touches 8 consecutive rows x 4 units = 512 contiguous
     // bytes per access: conflict free. y = SiLU(x*sc + sh) = h + h*tanh(h), h = x*(sc/2) + sh/2: 3 FP + 1 MUFU.
     if (p.has_norm) {
-      const int tt = threadIdx.x - 64;   // 0..127
+      const int tt = threadIdx.x - 64;   // 0..255
       const int j = tt & 3, rg = tt >> 2;
       float2* tab = reinterpret_cast<float2*>(__cvta_shared_to_generic(coef_addr));
       uint32_t sa = 0, a_par = 0;
@@ -1057,7 +1071,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         if (tc.b != tab_b) {             // (scale, shift) of this image's channels, all segments back to back
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          asm volatile("bar.sync 2, 256;" ::: "memory");
           int base = 0;
           for (int s = 0; s < p.nseg; ++s) {
             const int nch = p.seg_chunks[s] * kChunkK;
@@ -1070,7 +1084,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             }
             base += nch;
           }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          asm volatile("bar.sync 2, 256;" ::: "memory");
           tab_b = tc.b;
         }
         int base = 0;
@@ -1116,8 +1130,8 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 v = pack8(f);
                 return *reinterpret_cast<const uint4*>(&v);
               };
-              for (int r = rg; r < rows; r += 64) {
-                const int u0 = row_unit(r), u1 = row_unit(r + 32);
+              for (int r = rg; r < rows; r += 128) {
+                const int u0 = row_unit(r), u1 = row_unit(r + 64);
                 uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
                 if (u0 >= 0) x0 = st[u0];
                 if (u1 >= 0) x1 = st[u1];
@@ -1147,9 +1161,9 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     // TMA store (rows beyond the image and channels beyond n_store are clipped by the TMA unit), which
     // drains while the warps wait for the next accumulator. Residual adds are not done here: the engine
     // appends the residual as an extra K segment with identity weights, so it rides on the tensor core.
-    const int et = threadIdx.x - 192;                 // 0..255
+    const int et = threadIdx.x - 320;                 // 0..255
     const int q = warp & 3;
-    const int half = (warp - 6) >> 2;                 // 0: pixels [0,128), 1: pixels [128,256)
+    const int half = (warp - 10) >> 2;                // 0: pixels [0,128), 1: pixels [128,256)
     const int cl = q * 32 + lane;                     // channel inside the tile's 128-channel block
     const int spitch = p.out_box_c;                   // staging row pitch = channel extent of the TMA store box
     __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(__cvta_shared_to_generic(stage_base));
@@ -1426,7 +1440,9 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
       L->persistent = true;
       p.n_blocks = ceil_div(d->n_store, kTChan);
       p.num_tiles = p.tiles_w * p.tiles_h * tiles_b * p.n_blocks;
-      p.a_stages = 3;
+      // with the fused prologue a halo goes TMA -> transform -> MMA: a fourth buffer lets the next tile's first
+      // chunk be fetched and normalised while the current tile still has two chunks to multiply
+      p.a_stages = p.has_norm ? 4 : 3;
       const size_t fixed = 1024 + (size_t)p.a_stages * p.a_stage_bytes + kPStagingBytes + kPBarBytes +
                            (size_t)k_total_chan * 8 + 16;
       CSD_REQUIRE(fixed + 4 * (size_t)p.b_stage_bytes <= 227 * 1024, "transposed conv: K=%d channels too many for the "
