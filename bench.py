@@ -167,6 +167,62 @@ def cpu_oracle_steps(cfg, sample_batch, steps, warmup, time_budget_s):
             "images_per_s": sample_batch / (s_per_step * PC_STEPS)}
 
 
+def torch_eager_gpu_steps(cfg, batch, steps, warmup):
+    """Context number, not a contract arm: the oracle's plain-PyTorch restatement of the reference path run on
+    cuda:0 with PyTorch defaults (fp32 storage, cuDNN convolutions with TF32 allowed, fp32 matmul, eager launches) -
+    the closest stand-in for "stock PyTorch + cuDNN" that can travel to the GPU box (the reference itself is not
+    installed there). Its FIR resampling goes through F.conv2d like the reference's own `upfirdn2d_native` branch
+    (op/upfirdn2d.py:159-200), not through the reference's JIT-built CUDA op."""
+    import torch
+    from oracle import ncsnpp as o_net
+    from oracle import sampling as o_samp
+    from oracle import sde as o_sde
+    from conditional_score_diffusion_b200.models import ncsnpp, utils  # noqa: F401
+    torch.manual_seed(0)
+    model = utils.create_model(cfg)
+    torch.set_default_device("cuda")
+    params = {k: v.detach().cuda() for k, v in model.state_dict().items()}
+    o = o_net.model_options(cfg)
+    spec = o_net.build_spec(o)
+    sx = o_sde.VE(cfg.model.sigma_min_x, cfg.model.sigma_max_x, 1000)
+    sy = o_sde.VE(cfg.model.sigma_min_y, cfg.model.sigma_max_y, 1000)
+    model_fn = lambda d, l: o_net.forward_paired(params, o, d["x"], d["y"], l, spec)
+    score_fn = o_sde.score_fn_conditional_pair(model_fn, sx, sy, True)
+    shape = (batch, 3, cfg.data.image_size, cfg.data.image_size)
+    y = torch.rand(*shape)
+    x = torch.randn(*shape) * cfg.model.sigma_max_x
+    ts = torch.linspace(1.0, EPS, PC_STEPS)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            if i == warmup:
+                torch.cuda.synchronize()
+                e0.record()
+            vec_t = torch.ones(batch) * ts[i]
+            y_t = y + torch.randn_like(y) * sy.sigma(vec_t)[:, None, None, None]
+            grad = score_fn(x, y_t, vec_t)
+            x, _ = o_samp.langevin_update(sx, grad, x, vec_t, torch.randn_like(x), SNR)
+            y_t = y + torch.randn_like(y) * sy.sigma(vec_t)[:, None, None, None]
+            score = score_fn(x, y_t, vec_t)
+            x, _ = o_samp.reverse_diffusion_update(sx, score, x, vec_t, torch.randn_like(x))
+        e1.record()
+        torch.cuda.synchronize()
+    torch.set_default_device("cpu")
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "images_per_s": batch / (ms * 1e-3 * PC_STEPS), "batch": batch, "steps": steps,
+            "what": "oracle restatement of the reference path in eager PyTorch on cuda:0 (fp32 storage, cuDNN TF32 "
+                    "convolutions, F.conv2d FIR); context only"}
+
+
+def run_torch_eager_gpu(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    r = torch_eager_gpu_steps(workload_config(), BATCH_PER_GPU, max(3, min(args.steps, 20)), 2)
+    print(json.dumps({"impl": "torch_eager_gpu", "metric": METRIC, "value": r["images_per_s"], "unit": "images/s",
+                      "ms_per_step": r["ms_per_step"], "n_gpus": 1, "steps": r["steps"], "dtype": "f32/tf32",
+                      "config": {"workload": "same as the b200 arm", "batch_per_gpu": r["batch"]}, "note": r["what"]}))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -372,10 +428,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)  # 200 of the 1000 identical steps
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_eager_gpu"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_eager_gpu":
+        run_torch_eager_gpu(args)
     else:
         run_b200(args)
 
