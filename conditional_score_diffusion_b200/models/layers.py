@@ -69,3 +69,66 @@ class NIN(nn.Module):
         super().__init__()
         self.W = nn.Parameter(default_init(scale=init_scale)((in_dim, num_units)), requires_grad=True)
         self.b = nn.Parameter(torch.zeros(num_units), requires_grad=True)
+
+
+class AttnBlock(nn.Module):
+    """DDPM channel-wise self-attention block (models/layers.py:567-590): GroupNorm(32) -> q,k,v NIN ->
+    softmax(q k^T / sqrt(C)) v -> NIN -> x + h."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.GroupNorm_0 = nn.GroupNorm(num_groups=32, num_channels=channels, eps=1e-6)
+        self.NIN_0 = NIN(channels, channels)
+        self.NIN_1 = NIN(channels, channels)
+        self.NIN_2 = NIN(channels, channels)
+        self.NIN_3 = NIN(channels, channels, init_scale=0.0)
+
+
+class Upsample(nn.Module):
+    """Nearest x2 (+ 3x3 conv) (models/layers.py:593-604)."""
+
+    def __init__(self, channels, with_conv=False):
+        super().__init__()
+        if with_conv:
+            self.Conv_0 = ddpm_conv3x3(channels, channels)
+        self.with_conv = with_conv
+
+
+class Downsample(nn.Module):
+    """pad (0,1,0,1) + 3x3 stride-2 VALID conv, or 2x2 average pooling (models/layers.py:607-629)."""
+
+    def __init__(self, channels, with_conv=False, dim=2):
+        super().__init__()
+        if dim != 2:
+            raise NotImplementedError("3-D DDPM layers are outside the B200 hot path (SURVEY.md §2)")
+        if with_conv:
+            self.Conv_0 = ddpm_conv3x3(channels, channels, stride=2, padding=0)
+        self.with_conv = with_conv
+
+
+class ResnetBlockDDPM(nn.Module):
+    """The ResNet block used in DDPM (models/layers.py:632-675): GroupNorm(32) everywhere, NIN shortcut when the
+    channel count changes, plain `x + h`."""
+
+    def __init__(self, act, in_ch, out_ch=None, temb_dim=None, conv_shortcut=False, dropout=0.1, dim=2):
+        super().__init__()
+        if dim != 2:
+            raise NotImplementedError("3-D DDPM layers are outside the B200 hot path (SURVEY.md §2)")
+        out_ch = out_ch if out_ch is not None else in_ch
+        self.GroupNorm_0 = nn.GroupNorm(num_groups=32, num_channels=in_ch, eps=1e-6)
+        self.act = act
+        self.Conv_0 = ddpm_conv3x3(in_ch, out_ch)
+        if temb_dim is not None:
+            self.Dense_0 = nn.Linear(temb_dim, out_ch)
+            self.Dense_0.weight.data = default_init()(self.Dense_0.weight.data.shape)
+            nn.init.zeros_(self.Dense_0.bias)
+        self.GroupNorm_1 = nn.GroupNorm(num_groups=32, num_channels=out_ch, eps=1e-6)
+        self.Dropout_0 = nn.Dropout(dropout)
+        self.Conv_1 = ddpm_conv3x3(out_ch, out_ch, init_scale=0.0)
+        if in_ch != out_ch:
+            if conv_shortcut:
+                self.Conv_2 = ddpm_conv3x3(in_ch, out_ch)
+            else:
+                self.NIN_0 = NIN(in_ch, out_ch)
+        self.out_ch, self.in_ch, self.conv_shortcut = out_ch, in_ch, conv_shortcut
+        self.skip_rescale = False

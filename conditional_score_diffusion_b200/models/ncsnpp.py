@@ -17,23 +17,7 @@ import torch.nn as nn
 from . import layers, layerspp, utils
 from ..engine import NetEngine
 
-try:  # the reference subclasses pl.LightningModule (models/ncsnpp.py:23,40)
-    import pytorch_lightning as pl
-    _Base = pl.LightningModule
-except Exception:  # pragma: no cover - Lightning is not installed in the build image
-    class _Base(nn.Module):
-        @property
-        def device(self):
-            try:
-                return next(self.parameters()).device
-            except StopIteration:
-                return torch.device("cpu")
-
-        def save_hyperparameters(self, *args, **kwargs):
-            pass
-
-        def log(self, *args, **kwargs):
-            pass
+from .engine_net import EngineNet as _Base
 
 ResnetBlockDDPM = layerspp.ResnetBlockDDPMpp
 ResnetBlockBigGAN = layerspp.ResnetBlockBigGANpp
@@ -185,46 +169,9 @@ class NCSNpp(_Base):
             modules.append(nn.GroupNorm(num_groups=min(in_ch // 4, 32), num_channels=in_ch, eps=1e-6))
             modules.append(conv3x3(in_ch, channels, init_scale=init_scale))
         self.all_modules = nn.ModuleList(modules)
+        self.arch = "ncsnpp"
+        self.in_channels = self.out_channels = channels
         self._engine = NetEngine(self)
-
-    # ---- execution --------------------------------------------------------------------------------
-    def _check_inference(self, *tensors):
-        if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors if torch.is_tensor(t))
-                                        or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(
-                "NCSNpp backward (training / likelihood divergence) is not implemented by the B200 engine yet; "
-                "call the network under torch.no_grad(). No PyTorch fallback is provided on purpose.")
-        if self.training and self.config.model.dropout > 0:
-            raise NotImplementedError("dropout (train mode) is not implemented by the B200 engine; use .eval()")
-
-    def _run(self, x0, x1, time_cond, scale0=None, scale1=None, clone=True):
-        """x0 [B,c0,H,W] (+ optional x1 [B,c1,H,W], channel-concatenated after x0), time_cond [B]."""
-        self._check_inference(x0, x1, time_cond)
-        if x0.device.type != "cuda":
-            raise RuntimeError("NCSNpp runs on CUDA tensors only (libcsd_b200 has no CPU path)")
-        eng = self._engine
-        eng.ensure_packed(x0.device)
-        b, c0, h, w = x0.shape
-        c1 = x1.shape[1] if x1 is not None else 0
-        if c0 + c1 != self.config.data.num_channels:
-            raise ValueError(f"expected {self.config.data.num_channels} input channels, got {c0 + c1}")
-        plan = eng.plan(b, h, w, c0, c1)
-        plan.in0.copy_(x0)
-        if x1 is not None:
-            plan.in1.copy_(x1)
-        plan.labels.copy_(time_cond.to(torch.float32))
-        if scale0 is not None:
-            plan.row_scale.copy_(scale0)
-        else:
-            plan.row_scale.fill_(1.0)
-        if c1:
-            if scale1 is not None:
-                plan.row_scale1.copy_(scale1)
-            else:
-                plan.row_scale1.fill_(1.0)
-        plan.launch()
-        outs = plan.outputs()
-        return [o.clone() for o in outs] if clone else outs
 
     def forward(self, x, time_cond):
         return self._run(x, None, time_cond)[0]

@@ -46,7 +46,7 @@ class FusedPCSampler:
         m._engine.ensure_packed(device)
         b, c, h, w = self.shape
         c1 = c if self.conditional else 0
-        if self.conditional and m.config.data.num_channels != 2 * c:
+        if self.conditional and m.in_channels != 2 * c:
             raise ValueError("conditional pair sampler expects x and y with the same channel count")
         self.plan = m._engine.plan(b, h, w, c, c1)
         self.x = self.plan.in0                      # state lives in the network input buffer

@@ -91,3 +91,33 @@ def test_training_mode_raises_loudly():
     with pytest.raises(RuntimeError):
         with torch.no_grad():
             m.cpu()({"x": f["x"], "y": f["y"]}, f["labels"])
+
+
+def test_paired_forward_transposed_levels_vs_oracle():
+    """64x64, nf 32: the 64 px and 32 px levels run in the persistent transposed kernel (fused GroupNorm+SiLU
+    prologue, skip / identity-residual K segments, epilogue GroupNorm sums); everything else as in the tiny nets."""
+    from conditional_score_diffusion_b200.models import ncsnpp, utils  # noqa: F401
+    f = golden()["ncsnpp_paired"]
+    cfg = to_namespace(f["config"])
+    cfg.data.image_size = cfg.data.effective_image_size = 64
+    cfg.model.nf = 32
+    cfg.model.attn_resolutions = (16,)
+    torch.manual_seed(41)
+    m = utils.create_model(cfg)
+    g = torch.Generator().manual_seed(42)
+    with torch.no_grad():
+        for pn, p in m.named_parameters():
+            if pn.endswith("bias") or pn.endswith(".b"):
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    o = o_net.model_options(cfg)
+    B = 3
+    x = torch.randn(B, 3, 64, 64, generator=g) * 5
+    y = torch.rand(B, 3, 64, 64, generator=g)
+    labels = torch.rand(B, generator=g) * 999
+    ref = o_net.forward_paired(sd, o, x, y, labels)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out = m({"x": x.cuda(), "y": y.cuda()}, labels.cuda())
+    _check(out["x"], ref["x"], "paired 64px x vs oracle")
+    _check(out["y"], ref["y"], "paired 64px y vs oracle")
