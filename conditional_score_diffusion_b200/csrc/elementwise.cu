@@ -92,6 +92,48 @@ ve_perturb_kernel(const float* __restrict__ y, const float* __restrict__ z, floa
             [sigma](float a, float b, float, float& r0, float&) { r0 = fmaf(b, sigma, a); });
 }
 
+// Forward perturbation of the denoising score-matching losses (losses.py:126-133,190-192,218-220):
+// out = mean_coef[b] * x + std[b] * z (mean_coef null = 1: VE SDEs).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+sde_perturb_kernel(const float* __restrict__ x, const float* __restrict__ z, float* __restrict__ out,
+                   long long per_sample, const float* __restrict__ mean_coef, const float* __restrict__ stdv) {
+  const float m = mean_coef != nullptr ? mean_coef[blockIdx.y] : 1.f;
+  const float sd = stdv[blockIdx.y];
+  map3<VEC>(x, z, nullptr, out, nullptr, per_sample,
+            [m, sd](float a, float b, float, float& r0, float&) { r0 = fmaf(b, sd, m * a); });
+}
+
+// Per-sample denoising score-matching residual: losses[b] += w[b] * sum_i (a[b]*score_i + c[b]*z_i)^2
+// (losses.py:139-145 / 197-203 / 223-229: a = 1, c = 1/std, w = g^2 * reduce factor with likelihood weighting;
+// a = std, c = 1 without). One CTA row per sample slab, partial sums combined with atomics.
+__global__ void __launch_bounds__(256)
+dsm_loss_kernel(const float* __restrict__ score, const float* __restrict__ z, const float* __restrict__ a,
+                const float* __restrict__ c, const float* __restrict__ w, float* __restrict__ losses,
+                long long per_sample, int slabs) {
+  const int b = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+  const long long chunk = ceil_div_ll(per_sample, slabs);
+  const long long lo = slab * chunk, hi = min(per_sample, lo + chunk);
+  const float* sp = score + (long long)b * per_sample;
+  const float* zp = z + (long long)b * per_sample;
+  const float ab = a[b], cb = c[b];
+  float acc = 0.f;
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float r = fmaf(ab, sp[i], cb * zp[i]);
+    acc = fmaf(r, r, acc);
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    atomicAdd(losses + b, t * w[b]);
+  }
+}
+
 // One CTA row per sample slab; partial sums of squares are combined with atomics into sq[2*batch].
 __global__ void __launch_bounds__(256)
 sumsq_pair_kernel(const float* __restrict__ g, const float* __restrict__ z, float* __restrict__ sq, int batch,
@@ -231,6 +273,32 @@ int csd_ve_perturb_f32(const float* y, const float* z, float* y_pert, int batch,
   else
     ve_perturb_kernel<1><<<ps_grid(batch, per_sample, 1), 256, 0, st>>>(y, z, y_pert, per_sample, sig);
   CSD_LAUNCH_CHECK("ve_perturb_kernel");
+  return CSD_OK;
+}
+
+int csd_sde_perturb_f32(const float* x, const float* z, float* out, int batch, int64_t per_sample,
+                        const float* mean_coef, const float* std_dev, csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(x && z && out && std_dev, "sde_perturb: null pointer");
+  CSD_REQUIRE(batch >= 1 && batch <= 65535 && per_sample >= 1, "sde_perturb: bad batch / per_sample");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec4_ok(per_sample, {x, z, out}))
+    sde_perturb_kernel<4><<<ps_grid(batch, per_sample, 4), 256, 0, st>>>(x, z, out, per_sample, mean_coef, std_dev);
+  else
+    sde_perturb_kernel<1><<<ps_grid(batch, per_sample, 1), 256, 0, st>>>(x, z, out, per_sample, mean_coef, std_dev);
+  CSD_LAUNCH_CHECK("sde_perturb_kernel");
+  return CSD_OK;
+}
+
+int csd_dsm_loss_f32(const float* score, const float* z, const float* a, const float* c, const float* w, float* losses,
+                     int batch, int64_t per_sample, csd_stream_t stream_) {
+  using namespace csd;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CSD_REQUIRE(score && z && a && c && w && losses && batch >= 1 && per_sample >= 1, "dsm_loss: bad arguments");
+  int slabs = (int)std::max<long long>(1, std::min<long long>(ceil_div_ll(per_sample, 8192),
+                                                              ceil_div_ll((long long)num_sms() * 4, batch)));
+  dsm_loss_kernel<<<batch * slabs, 256, 0, stream>>>(score, z, a, c, w, losses, per_sample, slabs);
+  CSD_LAUNCH_CHECK("dsm_loss_kernel");
   return CSD_OK;
 }
 

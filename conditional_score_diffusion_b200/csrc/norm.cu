@@ -39,12 +39,8 @@ __device__ __forceinline__ bf16x8 gn_load(const GnParams& p, int b, long long pi
 // that reads the tensor (the down-path activations are normalised twice: by the next block and, through
 // the skip concatenation, by the up path).
 __global__ void gn_chan_stats_kernel(GnParams p) {
-  extern __shared__ float sm[];
+  extern __shared__ float sm[];     // [ppb][2*C] partial sums, reduced by a fixed-order tree (no shared atomics)
   const int V = p.v0, C = V * 8;
-  float* csum = sm;
-  float* csq = sm + C;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const int b = blockIdx.x / p.slabs, slab = blockIdx.x % p.slabs;
   const int ppb = blockDim.x / V;
   const int v = threadIdx.x % V, pp = threadIdx.x / V;
@@ -79,30 +75,43 @@ __global__ void gn_chan_stats_kernel(GnParams p) {
         q[i] = fmaf(f[i], f[i], q[i]);
       }
     }
+    float* row = sm + (size_t)pp * 2 * C + v * 16;   // (sum, sumsq) interleaved per channel
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(csum + v * 8 + i, s[i]);
-      atomicAdd(csq + v * 8 + i, q[i]);
+      row[2 * i] = s[i];
+      row[2 * i + 1] = q[i];
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    atomicAdd(p.sums0 + ((long long)b * C + c) * 2, csum[c]);
-    atomicAdd(p.sums0 + ((long long)b * C + c) * 2 + 1, csq[c]);
+  for (int c2 = threadIdx.x; c2 < 2 * C; c2 += blockDim.x) {
+    float a = 0.f;
+    for (int r = 0; r < ppb; ++r) a += sm[(size_t)r * 2 * C + c2];
+    atomicAdd(p.sums0 + (long long)b * 2 * C + c2, a);
   }
 }
 
 // chan_sums[b, c] = sum over the image's pixel tiles of the per-tile partial sums written by the
 // transposed convolution epilogue (deterministic: no atomics).
-__global__ void gn_finalize_partials_kernel(const float* __restrict__ partials, float* __restrict__ chan_sums,
-                                            int tiles_per_img, int c2 /* channels * 2 */) {
+__global__ void __launch_bounds__(256)
+gn_finalize_partials_kernel(const float* __restrict__ partials, float* __restrict__ chan_sums, int tiles_per_img,
+                            int c2 /* channels * 2 */) {
+  // block (32, 8): 32 consecutive (channel, sum|sumsq) slots x 8 tile lanes; fixed-order tree -> deterministic
+  __shared__ float red[8][33];
   const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c2) return;
-  const float* p0 = partials + (long long)b * tiles_per_img * c2 + i;
+  const int i = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  for (int t = 0; t < tiles_per_img; ++t) acc += p0[(long long)t * c2];
-  chan_sums[(long long)b * c2 + i] = acc;
+  if (i < c2) {
+    const float* p0 = partials + (long long)b * tiles_per_img * c2 + i;
+    for (int t = threadIdx.y; t < tiles_per_img; t += 8) acc += p0[(long long)t * c2];
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < c2) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += red[k][threadIdx.x];
+    chan_sums[(long long)b * c2 + i] = a;
+  }
 }
 
 // Normalise + affine (+SiLU) over the channel concatenation of up to two tensors; the group statistics
@@ -381,7 +390,8 @@ int csd_gn_chan_stats_bf16(const void* src, int c, int pitch, float* chan_sums, 
   int st = gn_fill(p, src, c, pitch, nullptr, 0, 0, batch, hw, 1, &threads, &smem);
   if (st != CSD_OK) return st;
   p.sums0 = chan_sums;
-  gn_chan_stats_kernel<<<batch * p.slabs, threads, sizeof(float) * 2 * c, static_cast<cudaStream_t>(stream)>>>(p);
+  const size_t stat_smem = sizeof(float) * 2 * c * (size_t)(threads / (c / 8));
+  gn_chan_stats_kernel<<<batch * p.slabs, threads, stat_smem, static_cast<cudaStream_t>(stream)>>>(p);
   CSD_LAUNCH_CHECK("gn_chan_stats_kernel");
   return CSD_OK;
 }
@@ -390,9 +400,9 @@ int csd_gn_finalize_partials_f32(const float* partials, float* chan_sums, int ba
                                  csd_stream_t stream) {
   using namespace csd;
   CSD_REQUIRE(partials && chan_sums && batch >= 1 && tiles_per_img >= 1 && c >= 1, "gn_finalize_partials: bad arguments");
-  dim3 grid((unsigned)ceil_div(2 * c, 128), (unsigned)batch);
-  gn_finalize_partials_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(partials, chan_sums, tiles_per_img,
-                                                                                  2 * c);
+  dim3 grid((unsigned)ceil_div(2 * c, 32), (unsigned)batch);
+  gn_finalize_partials_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(partials, chan_sums,
+                                                                                          tiles_per_img, 2 * c);
   CSD_LAUNCH_CHECK("gn_finalize_partials_kernel");
   return CSD_OK;
 }

@@ -235,6 +235,22 @@ def ve_perturb(y, z, out, sigma_tab, step_idx=None, sample_stride=0):
     return out
 
 
+def sde_perturb(x, z, out, mean_coef, std):
+    """out = mean_coef[b] * x + std[b] * z (mean_coef None = 1)."""
+    _require_cuda(x, z, out, mean_coef, std)
+    b, ps = _per_sample(x)
+    check(_lib.lib().csd_sde_perturb_f32(_ptr(x), _ptr(z), _ptr(out), b, ps, _ptr(mean_coef), _ptr(std), _stream()))
+    return out
+
+
+def dsm_loss(score, z, a, c, w, losses):
+    """losses[b] += w[b] * sum((a[b] * score + c[b] * z)^2); `losses` is pre-zeroed by the caller."""
+    _require_cuda(score, z, a, c, w, losses)
+    b, ps = _per_sample(score)
+    check(_lib.lib().csd_dsm_loss_f32(_ptr(score), _ptr(z), _ptr(a), _ptr(c), _ptr(w), _ptr(losses), b, ps, _stream()))
+    return losses
+
+
 def langevin_norms(grad, noise, norms):
     b, ps = _per_sample(grad)
     check(_lib.lib().csd_langevin_norms_f32(_ptr(grad), _ptr(noise), _ptr(norms), b, ps, _stream()))

@@ -105,6 +105,18 @@ int csd_euler_maruyama_update_f32(const float* x, const float* score, const floa
                                   const float* g_tab, float dt, int probability_flow, const int* step_idx,
                                   int sample_stride, csd_stream_t stream);
 
+/* ---- denoising score-matching losses (losses.py:99-234) ---------------------------------------------
+ * out[b] = mean_coef[b] * x[b] + std_dev[b] * z[b]: SDE.marginal_prob mean + std * z (losses.py:126-133,190-192,
+ * 218-220). mean_coef NULL = 1 (VE SDEs). All [batch] arrays are device pointers.                      */
+int csd_sde_perturb_f32(const float* x, const float* z, float* out, int batch, int64_t per_sample,
+                        const float* mean_coef, const float* std_dev, csd_stream_t stream);
+
+/* losses[b] += w[b] * sum_i (a[b] * score[b,i] + c[b] * z[b,i])^2 (losses.py:139-145,197-203,223-229:
+ * likelihood weighting a = 1, c = 1/std, w = g(t)^2 * (1/per_sample or 1/2); otherwise a = std, c = 1).
+ * The caller zeroes `losses` and may accumulate several terms (the x and y parts of the CMDE loss).   */
+int csd_dsm_loss_f32(const float* score, const float* z, const float* a, const float* c, const float* w, float* losses,
+                     int batch, int64_t per_sample, csd_stream_t stream);
+
 /* dst[i] = table value for sample i at the current step (time labels, 1/sigma row scales). */
 int csd_broadcast_table_f32(float* dst, int n, const float* tab, const int* step_idx, int sample_stride,
                             csd_stream_t stream);

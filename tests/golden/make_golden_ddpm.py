@@ -66,6 +66,52 @@ def main():
         else:
             rec["out"] = out.clone()
         fx[name] = rec
+    # ---- evaluation losses (losses.py:99-234) on those networks, RNG draws replayed and stored ----------------
+    import numpy as np
+    import losses as ref_losses
+    import sde_lib
+    hw, B = 16, 2
+    smax = float(np.sqrt(3 * hw * hw))
+    g = torch.Generator().manual_seed(8)
+    xb = torch.rand(B, 3, hw, hw, generator=g)
+    yb = torch.rand(B, 3, hw, hw, generator=g)
+    models = {}
+    for name, out_ch in (("ddpm_paired", 6), ("ddpm_paired_SR3", 3)):
+        cfg = small_ddpm_config(name, out_ch)
+        mdl = mutils.create_model(cfg).eval()
+        last = max(int(k.split(".")[1]) for k in sd_paired)
+        mdl.load_state_dict({k: (v[:out_ch] if k.startswith(f"all_modules.{last}.") else v)
+                             for k, v in sd_paired.items()}, strict=True)
+        models[name] = mdl
+    eps = 1e-5
+    # SR3 estimator: one conditional SDE, only x perturbed
+    sde = sde_lib.cVESDE(sigma_min=5e-3, sigma_max=smax, N=1000)
+    rec = {"x": xb, "y": yb, "sigma_min": 5e-3, "sigma_max": smax, "eps": eps}
+    for lw in (True, False):
+        fn = ref_losses.get_general_sde_loss_fn(sde, train=False, conditional=True, reduce_mean=True, continuous=True,
+                                                likelihood_weighting=lw, eps=eps)
+        torch.manual_seed(123)
+        with torch.no_grad():
+            rec[f"loss_lw{int(lw)}"] = fn(models["ddpm_paired_SR3"], (yb, xb)).clone()
+    torch.manual_seed(123)
+    rec["t"] = torch.rand(B) * (sde.T - eps) + eps
+    rec["z"] = torch.randn_like(xb)
+    fx["loss_sr3"] = rec
+    # CMDE estimator: x and y SDEs
+    sdes = {"x": sde_lib.cVESDE(sigma_min=5e-3, sigma_max=smax, N=1000), "y": sde_lib.VESDE(sigma_min=5e-3, sigma_max=0.5, N=1000)}
+    rec = {"x": xb, "y": yb, "sigma_max_x": smax, "sigma_max_y": 0.5, "sigma_min": 5e-3, "eps": eps}
+    for rm in (True, False):
+        fn = ref_losses.get_general_sde_loss_fn(sdes, train=False, conditional=True, reduce_mean=rm, continuous=True,
+                                                likelihood_weighting=True, eps=eps)
+        torch.manual_seed(321)
+        with torch.no_grad():
+            rec[f"loss_rm{int(rm)}"] = fn(models["ddpm_paired"], (yb, xb)).clone()
+    torch.manual_seed(321)
+    rec["t"] = torch.rand(B) * (1 - eps) + eps
+    rec["z_y"] = torch.randn_like(yb)
+    rec["z_x"] = torch.randn_like(xb)
+    fx["loss_cmde"] = rec
+
     path = os.path.join(OUT, "reference_vectors_ddpm.pt")
     torch.save(fx, path)
     print("wrote", path, f"{os.path.getsize(path) / 1e6:.2f} MB")

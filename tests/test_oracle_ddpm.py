@@ -51,3 +51,45 @@ def test_ddpm_module_surface():
         missing, unexpected = model.load_state_dict(weights, strict=True)
         assert not missing and not unexpected
         assert [k for k in model.state_dict()] == list(weights)
+
+
+def _score_fns(fx, sd, sd3):
+    from oracle import sde as o_sde
+    cfg_p, cfg_s = to_namespace(fx["ddpm_paired"]["config"]), to_namespace(fx["ddpm_paired_SR3"]["config"])
+    o_p, o_s = o_ddpm.model_options(cfg_p), o_ddpm.model_options(cfg_s)
+    ls, lc = fx["loss_sr3"], fx["loss_cmde"]
+    sx = o_sde.VE(ls["sigma_min"], ls["sigma_max"], 1000)
+    sy = o_sde.VE(lc["sigma_min"], lc["sigma_max_y"], 1000)
+
+    def sr3_score(d, t):      # get_score_fn, conditional cVESDE branch (models/utils.py:207-221): labels = t (N-1)
+        out = o_ddpm.forward_paired_sr3(sd3, o_s, d["x"], d["y"], t * 999)
+        return out / sx.sigma(t)[:, None, None, None]
+
+    def pair_score(d, t):     # dict branch (models/utils.py:172-186)
+        out = o_ddpm.forward_paired(sd, o_p, d["x"], d["y"], t * 999)
+        return {"x": out["x"] / sx.sigma(t)[:, None, None, None], "y": out["y"] / sy.sigma(t)[:, None, None, None]}
+
+    return sx, sy, sr3_score, pair_score
+
+
+def test_loss_oracle_matches_reference():
+    from oracle import losses as o_loss
+    fx, sd, sd3 = ddpm_golden()
+    sx, sy, sr3_score, pair_score = _score_fns(fx, sd, sd3)
+    ls, lc = fx["loss_sr3"], fx["loss_cmde"]
+    for lw in (True, False):
+        got = o_loss.sr3_loss(sr3_score, sx, ls["y"], ls["x"], ls["t"], ls["z"], True, lw)
+        ref = ls[f"loss_lw{int(lw)}"]
+        assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item()), (lw, got.item(), ref.item())
+    for rm in (True, False):
+        got = o_loss.cmde_loss(pair_score, sx, sy, lc["y"], lc["x"], lc["t"], lc["z_x"], lc["z_y"], rm)
+        ref = lc[f"loss_rm{int(rm)}"]
+        assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item()), (rm, got.item(), ref.item())
+
+
+def test_training_loss_raises_without_backward():
+    import pytest
+    from conditional_score_diffusion_b200 import losses, sde_lib
+    fn = losses.get_general_sde_loss_fn(sde_lib.cVESDE(5e-3, 27.7, 1000), train=True, conditional=True)
+    with pytest.raises(NotImplementedError):
+        fn(None, (torch.zeros(1, 3, 4, 4), torch.zeros(1, 3, 4, 4)))

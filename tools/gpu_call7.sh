@@ -1,0 +1,5 @@
+set -x
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/step_launches_r1.csv python tools/step_ncu_target.py 64 > gpurun_out/ncu_step.log 2>&1; tail -2 gpurun_out/ncu_step.log
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_halo_tp -s 4 -c 2 -o gpurun_out/conv_halo_tp_full_r1 python tools/step_ncu_target.py 64 > gpurun_out/ncu_tp.log 2>&1; tail -2 gpurun_out/ncu_tp.log
+timeout 900 ncu --profile-from-start off --set full --clock-control none -k regex:"gn_apply|fir_nhwc|gn_chan_stats|langevin|reverse_diffusion|ve_perturb" -c 24 -o gpurun_out/hbm_kernels_full_r1 python tools/step_ncu_target.py 64 > gpurun_out/ncu_hbm.log 2>&1; tail -2 gpurun_out/ncu_hbm.log
+ls -la gpurun_out | tail -8
