@@ -72,6 +72,7 @@ struct ConvGemmKernelParams {
   // transposed mode: fused GroupNorm(+SiLU) prologue (per-segment (scale, shift) tables [batch, c_cnt, 2])
   int num_tiles, n_blocks;   // persistent transposed kernel: tiles = spatial tiles x 128-channel blocks
   int out_box_c;             // channel extent of its TMA store box = staging row pitch
+  int t_rows, t_pix;         // macro tile = t_rows x 8 pixels (32 -> N = 256, or 20 -> N = 160 for 40-row images)
   const float* seg_norm[CSD_MAX_SEGMENTS];
   int seg_silu[CSD_MAX_SEGMENTS];
   int seg_ccnt[CSD_MAX_SEGMENTS];
@@ -521,8 +522,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 // Epilogue: TMEM lane = output channel, column = pixel; bias / temb are per-lane scalars, the
 // per-channel GroupNorm partial sums of the stored output are free per-thread accumulations.
 //
-// Fused GroupNorm + SiLU prologue (segments with a `norm` table): the 8 epilogue warps are idle while the
-// main loop runs, so they transform every pixel-halo stage in place between TMA arrival and MMA issue:
+// Fused GroupNorm + SiLU prologue (segments with a `norm` table): dedicated warps transform every pixel-halo
+// stage in place between TMA arrival and MMA issue:
 // y = SiLU(x * scale[b,c] + shift[b,c]) on the 16-byte units of the swizzled tile (physical unit j' of row
 // r holds logical channels 8*(j' ^ ((r >> 1) & 3)) .. +8 under SWIZZLE_64B), skipping halo pixels outside
 // the image (they must stay the zeros TMA wrote: the reference pads the *normalised* activation,
@@ -530,337 +531,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 // TMA -> a_full -> transform -> fence.proxy.async -> a_ready -> MMA -> a_empty. One halo stage is transformed
 // once and feeds all 9 taps, so the MUFU work is 1/9 of what a per-tap operand transform would cost.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kTPix = 256;      // pixels per CTA (N of the MMA)
-constexpr int kTRows = 32;      // image rows per macro tile
+constexpr int kTPix = 256;      // TMEM columns per accumulator = max pixels per CTA tile (N of the MMA)
+constexpr int kTRows = 32;      // max image rows per macro tile (tiles are t_rows x 8 pixels, t_rows = 32 or 20)
 constexpr int kTChan = 128;     // output channels per CTA (M of the MMA)
 
-constexpr int kTThreads = 320;  // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
-
-__global__ void __launch_bounds__(kTThreads)
-conv_halo_t_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
-                   const __grid_constant__ CUtensorMap mapB, const ConvGemmKernelParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_base = smem_base;                                   // pixel halos
-  const uint32_t b_base = smem_base + p.a_stages * p.a_stage_bytes;    // weight slabs
-  const uint32_t bar_base = b_base + p.b_stages * p.b_stage_bytes;
-  const uint32_t a_full0 = bar_base, a_empty0 = bar_base + 8u * kMaxAStages;
-  const uint32_t b_full0 = bar_base + 8u * (2 * kMaxAStages), b_empty0 = b_full0 + 8u * kMaxBStages;
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages);
-  const uint32_t tmem_slot = tmem_full_bar + 8u;
-  const uint32_t a_ready0 = tmem_full_bar + 16u;                 // kMaxAStages barriers, 256 arrivals each
-  const uint32_t coef_addr = a_ready0 + 8u * kMaxAStages;        // float2 per padded K channel (16-byte aligned)
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x;
-  const int tw = t % p.tiles_w;
-  const int th = (t / p.tiles_w) % p.tiles_h;
-  const int b = t / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * kHaloTW, h0 = th * kTRows;
-  const int n0 = blockIdx.y * kTChan;
-  if (threadIdx.x == 0) CSD_TS(0);
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&mapA0);
-    ptx::prefetch_tensormap(&mapB);
-    for (int s = 0; s < p.a_stages; ++s) { ptx::mbar_init(a_full0 + 8u * s, 1); ptx::mbar_init(a_empty0 + 8u * s, 1); }
-    for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full0 + 8u * s, 1); ptx::mbar_init(b_empty0 + 8u * s, 1); }
-    for (int s = 0; s < p.a_stages; ++s) ptx::mbar_init(a_ready0 + 8u * s, kTThreads - 64);
-    ptx::mbar_init(tmem_full_bar, 1);
-    ptx::fence_mbar_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, kTPix);
-    ptx::tmem_relinquish();
-  }
-  ptx::tcgen05_fence_before();
-  __syncthreads();
-  ptx::tcgen05_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  if (threadIdx.x == 0) CSD_TS(1);
-
-  // Both issue loops below are single-thread instruction streams whose latency bounds the tensor pipe
-  // (one tcgen05.mma pair per weight slab = 256 tensor cycles): ring positions and barrier parities are
-  // running counters (no division), and the UMMA descriptors are advanced by adding to their low word.
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t sa = 0, a_par = 1, sb = 0, b_par = 1;
-      for (int s = 0; s < p.nseg; ++s) {
-        const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
-        const int taps = p.seg_taps[s];
-        const int halo = (taps == 9) ? 1 : 0;
-        const uint32_t a_bytes = (uint32_t)((kHaloTW + 2 * halo) * (kTRows + 2 * halo) * kRowBytes);
-        const int nchunks = p.seg_chunks[s];
-        const int kstep = nchunks * kChunkK;
-        for (int c = 0; c < nchunks; ++c) {
-          ptx::mbar_wait(a_empty0 + 8u * sa, a_par);
-          ptx::mbar_arrive_expect_tx(a_full0 + 8u * sa, a_bytes);
-          ptx::tma_load_4d(a_base + sa * p.a_stage_bytes, mapA, a_full0 + 8u * sa, p.seg_coff[s] + c * kChunkK,
-                           w0 - halo, h0 - halo, b);
-          if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
-          int kcol = p.wt_k_off + (p.seg_kbase[s] + c) * kChunkK;
-          for (int tap = 0; tap < taps; ++tap, kcol += kstep) {
-            ptx::mbar_wait(b_empty0 + 8u * sb, b_par);
-            ptx::mbar_arrive_expect_tx(b_full0 + 8u * sb, kTChan * kRowBytes);
-            ptx::tma_load_3d(b_base + sb * p.b_stage_bytes, &mapB, b_full0 + 8u * sb, kcol, n0, 0);
-            if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)kTPix);
-      const uint32_t w_hi = ptx::smem_desc_hi(512, kLayoutSw64);
-      uint32_t sa = 0, a_par = 0, sb = 0, b_par = 0;
-      uint32_t accumulate = 0;
-      // with the fused prologue a stage is usable once the transform warps have released it
-      const uint32_t a_go0 = p.has_norm ? a_ready0 : a_full0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const int nchunks = p.seg_chunks[s];
-        if (p.seg_taps[s] == 9) {
-          constexpr int pitch = kHaloTW + 2;
-          const uint32_t x_hi = ptx::smem_desc_hi(pitch * kRowBytes, kLayoutSw64);
-          for (int c = 0; c < nchunks; ++c) {
-            ptx::mbar_wait(a_go0 + 8u * sa, a_par);
-            ptx::tcgen05_fence_after();
-            if (c == 0 && s == 0) CSD_TS(3);
-            if (c == 1 && s == 0) CSD_TS(8);
-            const uint32_t x_lo0 = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              ptx::mbar_wait(b_full0 + 8u * sb, b_par);
-              ptx::tcgen05_fence_after();
-              const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
-              const uint32_t x_lo = x_lo0 + (uint32_t)((((tap / 3) * pitch + (tap % 3)) * kRowBytes) >> 4);
-              ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi, x_lo), idesc,
-                               accumulate);
-              ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi, x_lo + 2),
-                               idesc, 1u);
-              accumulate = 1u;
-              ptx::mma_commit(b_empty0 + 8u * sb);
-              if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
-            }
-            ptx::mma_commit(a_empty0 + 8u * sa);
-            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
-          }
-        } else {
-          const uint32_t x_hi = ptx::smem_desc_hi(kHaloTW * kRowBytes, kLayoutSw64);
-          for (int c = 0; c < nchunks; ++c) {
-            ptx::mbar_wait(a_go0 + 8u * sa, a_par);
-            ptx::mbar_wait(b_full0 + 8u * sb, b_par);
-            ptx::tcgen05_fence_after();
-            const uint32_t x_lo = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
-            const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
-            ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi, x_lo), idesc,
-                             accumulate);
-            ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi, x_lo + 2),
-                             idesc, 1u);
-            accumulate = 1u;
-            ptx::mma_commit(b_empty0 + 8u * sb);
-            if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
-            ptx::mma_commit(a_empty0 + 8u * sa);
-            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
-          }
-        }
-      }
-      CSD_TS(4);
-      ptx::mma_commit(tmem_full_bar);
-    }
-  } else {
-    // ===== epilogue (8 warps) =====
-    // Phase A: TMEM lane = output channel, column = pixel. Warp w reads lane quadrant w % 4 (the hardware's
-    //          TMEM access rule) and the pixel half (w - 2) / 4; each thread adds its channel's bias + temb,
-    //          rounds to bf16 and writes stage[pixel][channel] into the (now idle) operand rings: a warp
-    //          writes 32 consecutive channels of one pixel = 64 contiguous bytes, conflict free.
-    // Phase B: the staged tile is read back as 16-byte channel vectors, pixel-major, so residual loads
-    //          and output stores are fully coalesced NHWC rows; scale, residual and the per-channel
-    //          GroupNorm partial sums are applied here.
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;                 // 0: pixels [0,128), 1: pixels [128,256)
-    const int et = threadIdx.x - 64;                  // 0..255
-    const int cl = q * 32 + lane;                     // channel inside the CTA's 128-channel block
-    const int c = n0 + cl;
-    const int cb = min(kTChan, p.n_store - n0);       // channels of this block that are stored (multiple of 8)
-    const bool c_valid = cl < cb;
-    const float add_c = c_valid ? ((p.bias != nullptr ? __ldg(p.bias + c) : 0.f) +
-                                   (p.temb != nullptr ? __ldg(p.temb + (long long)b * p.temb_pitch + c) : 0.f))
-                                : 0.f;
-    if (p.has_norm) {
-      // ---- fused GroupNorm(+SiLU) prologue: transform every pixel-halo stage in place ----
-      float2* tab = reinterpret_cast<float2*>(__cvta_shared_to_generic(coef_addr));
-      {
-        int base = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const int nch = p.seg_chunks[s] * kChunkK;
-          const float2* src = reinterpret_cast<const float2*>(p.seg_norm[s]);
-          for (int i = et; i < nch; i += kTThreads - 64)
-            tab[base + i] = (src != nullptr && i < p.seg_ccnt[s]) ? __ldg(src + (long long)b * p.seg_ccnt[s] + i)
-                                                                  : make_float2(0.f, 0.f);
-          base += nch;
-        }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      uint32_t sa = 0, a_par = 0;
-      int base = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const bool norm = p.seg_norm[s] != nullptr;
-        const bool act = p.seg_silu[s] != 0;
-        const int halo = (p.seg_taps[s] == 9) ? 1 : 0;
-        const int pitch = kHaloTW + 2 * halo;
-        const int units = pitch * (kTRows + 2 * halo) * 4;       // 16-byte units of the stage
-        for (int c = 0; c < p.seg_chunks[s]; ++c) {
-          ptx::mbar_wait(a_full0 + 8u * sa, a_par);
-          if (norm) {
-            uint4* st = reinterpret_cast<uint4*>(__cvta_shared_to_generic(a_base + sa * p.a_stage_bytes));
-            const float2* tc = tab + base + c * kChunkK;
-            for (int u = et; u < units; u += kTThreads - 64) {
-              const int r = u >> 2;
-              const int hy = halo ? r / (kHaloTW + 2) : (r >> 3);
-              const int hx = r - hy * pitch;
-              const int gh = h0 - halo + hy, gw = w0 - halo + hx;
-              if (gh < 0 || gh >= p.H || gw < 0 || gw >= p.W) continue;   // conv padding stays zero
-              const int j = (u & 3) ^ ((r >> 1) & 3);                      // SWIZZLE_64B: logical 16-byte unit
-              const float4* cf = reinterpret_cast<const float4*>(tc + j * 8);
-              bf16x8 v;
-              *reinterpret_cast<uint4*>(&v) = st[u];
-              float f[8];
-              unpack8(v, f);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 k2 = cf[i];                                   // (scale, shift) of two channels
-                float y0 = fmaf(f[2 * i], k2.x, k2.y), y1 = fmaf(f[2 * i + 1], k2.z, k2.w);
-                if (act) {
-                  y0 = silu_tanh(y0);
-                  y1 = silu_tanh(y1);
-                }
-                f[2 * i] = y0;
-                f[2 * i + 1] = y1;
-              }
-              v = pack8(f);
-              st[u] = *reinterpret_cast<const uint4*>(&v);
-            }
-            ptx::fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async reads
-          }
-          ptx::mbar_arrive(a_ready0 + 8u * sa);
-          if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
-        }
-        base += p.seg_chunks[s] * kChunkK;
-      }
-    }
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tcgen05_fence_after();
-    if (threadIdx.x == 64) CSD_TS(5);
-    const int spitch = cb;                            // staging row pitch in elements
-    __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(__cvta_shared_to_generic(smem_base));
-    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (kTPix / 2));
-    __nv_bfloat16* stage_c = stage + (half * (kTPix / 2)) * spitch + cl;
-#pragma unroll 1
-    for (int col = 0; col < kTPix / 2; col += 32) {
-      uint32_t r0[16], r1[16];
-      __syncwarp();
-      ptx::tmem_ld_x16(t_row + col, r0);
-      ptx::tmem_ld_x16(t_row + col + 16, r1);
-      ptx::tmem_ld_wait();
-      if (c_valid) {
-        __nv_bfloat16* sp = stage_c + col * spitch;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          sp[i * spitch] = __float2bfloat16_rn(__uint_as_float(r0[i]) + add_c);
-          sp[(16 + i) * spitch] = __float2bfloat16_rn(__uint_as_float(r1[i]) + add_c);
-        }
-      }
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (threadIdx.x == 64) CSD_TS(9);
-    // Phase B
-    const int V = cb >> 3;                            // 16-byte vectors per pixel
-    const int ppass = min(256 / V, 32);               // pixels handled per pass (bounds the reduction scratch)
-    const int v = et % V, pl = et / V;
-    float s1[8], s2[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-    if (pl < ppass) {
-      const uint4* stage_v = reinterpret_cast<const uint4*>(stage) + v;
-      const bool has_res = p.res != nullptr;
-      const bool has_stats = p.stat_partials != nullptr;
-      const float scale = p.scale;
-      for (int m = pl; m < kTPix; m += ppass) {
-        const int h = h0 + (m >> 3), w = w0 + (m & 7);
-        if (h < p.H && w < p.W) {
-          const long long pix = ((long long)b * p.H + h) * p.W + w;
-          float f[8];
-          bf16x8 sv;
-          *reinterpret_cast<uint4*>(&sv) = stage_v[m * V];
-          unpack8(sv, f);
-          if (has_res) {
-            float rr[8];
-            bf16x8 rv;
-            *reinterpret_cast<uint4*>(&rv) = __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch + n0) + v);
-            unpack8(rv, rr);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] += rr[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] *= scale;
-          const bf16x8 o = pack8(f);
-          reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_pitch + n0)[v] =
-              *reinterpret_cast<const uint4*>(&o);
-          if (has_stats) {
-            float g[8];
-            unpack8(o, g);   // statistics of exactly what the consumer will read
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              s1[i] += g[i];
-              s2[i] = fmaf(g[i], g[i], s2[i]);
-            }
-          }
-        }
-      }
-    }
-    if (p.stat_partials != nullptr) {
-      // reduce the ppass partial rows per channel vector through shared memory (after the staging tile)
-      float* red = reinterpret_cast<float*>(__cvta_shared_to_generic(smem_base + kTPix * kTChan * 2));
-      if (pl < ppass) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          red[(pl * kTChan + v * 8 + i) * 2] = s1[i];
-          red[(pl * kTChan + v * 8 + i) * 2 + 1] = s2[i];
-        }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (et < cb) {
-        float a1 = 0.f, a2 = 0.f;
-        for (int r = 0; r < ppass; ++r) {
-          a1 += red[(r * kTChan + et) * 2];
-          a2 += red[(r * kTChan + et) * 2 + 1];
-        }
-        float* sp = p.stat_partials + ((long long)blockIdx.x * p.n_store + n0 + et) * 2;
-        sp[0] = a1;
-        sp[1] = a2;
-      }
-    }
-    if (threadIdx.x == 64) CSD_TS(6);
-  }
-
-  ptx::tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    ptx::tcgen05_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTPix);
-    if (lane == 0) CSD_TS(7);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------
-// Persistent form of the transposed halo kernel (the one the engine launches for mode 2).
+// The transposed halo kernel (mode 2), persistent.
 //
-// conv_halo_t_kernel above spends ~45% of each CTA's life outside its main loop (pipeline fill ~3.5k
+// A one-tile-per-CTA version of this kernel spent ~45% of each CTA's life outside its main loop (pipeline fill ~3.5k
 // cycles, epilogue ~8.7k cycles against ~6.9k tensor cycles for a 96-channel layer; measured with
-// tools/conv_phase_timing.py) and relies on a second resident CTA to fill the gap. Here ONE CTA per SM
+// tools/conv_phase_timing.py) and relied on a second resident CTA to fill the gap. Here ONE CTA per SM
 // walks a static list of tiles (tile = blockIdx.x + i * gridDim.x) with five specialised roles:
 //   warp 0 / 18 TMA producers     pixel halos / weight slabs (separate threads: independent run-ahead), rings
 //                                 shared by consecutive tiles
@@ -891,7 +571,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmKernelParams& p, 
   const int th = r % p.tiles_h;
   t.b = r / p.tiles_h;
   t.w0 = tw * kHaloTW;
-  t.h0 = th * kTRows;
+  t.h0 = th * p.t_rows;
   t.n0 = nb * kTChan;
   return t;
 }
@@ -951,7 +631,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         for (int s = 0; s < p.nseg; ++s) {
           const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
           const int halo = (p.seg_taps[s] == 9) ? 1 : 0;
-          const uint32_t a_bytes = (uint32_t)((kHaloTW + 2 * halo) * (kTRows + 2 * halo) * kRowBytes);
+          const uint32_t a_bytes = (uint32_t)((kHaloTW + 2 * halo) * (p.t_rows + 2 * halo) * kRowBytes);
           for (int c = 0; c < p.seg_chunks[s]; ++c) {
             if (p.debug_nodata & 2) continue;
             ptx::mbar_wait(a_empty0 + 8u * sa, a_par);
@@ -990,7 +670,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)kTPix);
+      const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)p.t_pix);
       const uint32_t w_hi = ptx::smem_desc_hi(512, kLayoutSw64);
       const uint32_t a_go0 = p.has_norm ? a_ready0 : a_full0;
       uint32_t sa = 0, a_par = 0, sb = 0, b_par = 0;
@@ -1093,7 +773,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           const bool act = p.seg_silu[s] != 0;
           const int halo = (p.seg_taps[s] == 9) ? 1 : 0;
           const int pitch = kHaloTW + 2 * halo;
-          const int rows = pitch * (kTRows + 2 * halo);
+          const int rows = pitch * (p.t_rows + 2 * halo);
           for (int c = 0; c < p.seg_chunks[s]; ++c) {
             ptx::mbar_wait(a_full0 + 8u * sa, a_par);
             if (tt == 0 && s == 0 && c == 0) CSD_TSP(8);
@@ -1167,7 +847,8 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     const int cl = q * 32 + lane;                     // channel inside the tile's 128-channel block
     const int spitch = p.out_box_c;                   // staging row pitch = channel extent of the TMA store box
     __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(__cvta_shared_to_generic(stage_base));
-    __nv_bfloat16* stage_c = stage + (half * (kTPix / 2)) * spitch + cl;
+    const int half_pix = p.t_pix >> 1;                // pixels (accumulator columns) per epilogue half: 128 or 80
+    __nv_bfloat16* stage_c = stage + (half * half_pix) * spitch + cl;
     const bool has_stats = p.stat_partials != nullptr;
     const float scale = p.scale;
     uint32_t acc = 0, full_par = 0;
@@ -1183,22 +864,22 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       // valid pixel columns of this half (rows beyond the image) and valid pixels per 8-pixel row (ragged width;
       // the engine only launches w % 8 == 0, where w_lim is always 8)
       const int w_lim = min(kHaloTW, p.W - tc.w0);
-      const int m_lim = (w_lim == kHaloTW ? min(kTPix, (p.H - tc.h0) * kHaloTW) - half * (kTPix / 2) : 0);
-      const int m_lim_h = min(kTPix, (p.H - tc.h0) * kHaloTW) - half * (kTPix / 2);
+      const int m_lim_h = min(half_pix, min(p.t_pix, (p.H - tc.h0) * kHaloTW) - half * half_pix);
+      const int m_lim = (w_lim == kHaloTW ? m_lim_h : 0);
       if (et == 0) CSD_TSP(3);
       ptx::mbar_wait(tmem_full0 + 8u * acc, full_par);
       ptx::tcgen05_fence_after();
       if (et == 0) CSD_TSP(4);
       if (et == 0 && store_pending) ptx::bulk_wait_group_read0();   // previous tile's store has left the staging tile
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const uint32_t t_row = tmem_base + acc * kTPix + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (kTPix / 2));
+      const uint32_t t_row = tmem_base + acc * kTPix + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * half_pix);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-      for (int col = 0; col < kTPix / 2; col += 32) {
+      for (int col = 0; col < half_pix; col += 32) {
         uint32_t r0[16], r1[16];
         __syncwarp();
         ptx::tmem_ld_x16(t_row + col, r0);
-        ptx::tmem_ld_x16(t_row + col + 16, r1);
+        ptx::tmem_ld_x16(t_row + col + 16, r1);      // (a 80-column half reads 16 columns past its end: unused)
         ptx::tmem_ld_wait();
         if (c_valid) {
           __nv_bfloat16* sp = stage_c + col * spitch;
@@ -1218,7 +899,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 s1 += v;
                 s2 = fmaf(v, v, s2);
               }
-              sp[i * spitch] = __float2bfloat16_rn(v);
+              if (col + i < half_pix) sp[i * spitch] = __float2bfloat16_rn(v);   // never into the other half's rows
             }
           }
         }
@@ -1299,8 +980,13 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   p.TH = halo_mode ? kHaloTH : d->tile_h;
   p.TB = halo_mode ? 1 : d->tile_b;
   p.mt = mt;
+  // transposed mode: macro tile = t_rows x 8 pixels. 32 rows (N = 256) by default; 20 rows (N = 160) when that
+  // tiles the image exactly and 32 would waste more than the shorter MMA loses (40-row images).
+  // kernels.transposed_tile_rows() mirrors this rule for the statistics-partials geometry.
+  p.t_rows = (t_mode && d->h % 32 != 0 && d->h < 64 && d->h % 20 == 0) ? 20 : kTRows;
+  p.t_pix = p.t_rows * kHaloTW;
   p.tiles_w = ceil_div(d->w, p.TW);
-  p.tiles_h = ceil_div(d->h, p.TH * mt);
+  p.tiles_h = t_mode ? ceil_div(d->h, p.t_rows) : ceil_div(d->h, p.TH * mt);
   const int tiles_b = ceil_div(d->batch, p.TB);
   p.nseg = d->nseg;
   p.stride = d->stride > 0 ? d->stride : 1;
@@ -1357,7 +1043,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     if (halo_mode) {  // whole halo of the mt stacked tiles (a 1-tap segment needs no halo)
       const int hl = sg.taps == 9 ? 1 : 0;
       box[1] = (uint32_t)(kHaloTW + 2 * hl);
-      box[2] = (uint32_t)(kHaloTH * mt + 2 * hl);
+      box[2] = (uint32_t)((t_mode ? p.t_rows : kHaloTH * mt) + 2 * hl);
     }
     uint32_t estr[4] = {1, (uint32_t)p.stride, (uint32_t)p.stride, 1};
     int st = encode_tensor_map(&L->mapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, sg.a, dims, strides, box,
@@ -1434,8 +1120,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     L->smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + tail;
     if (t_mode) L->grid.y = (unsigned)ceil_div(d->n_store, kTChan);
     L->persistent = false;
-    static const bool legacy_t = getenv("CSD_T_LEGACY") != nullptr;   // A/B switch: one tile per CTA
-    if (t_mode && !legacy_t) {
+    if (t_mode) {
       // persistent kernel: one CTA per SM, whole shared memory
       L->persistent = true;
       p.n_blocks = ceil_div(d->n_store, kTChan);
@@ -1459,7 +1144,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
       uint64_t odims[4] = {(uint64_t)d->n_store, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->batch};
       uint64_t ostr[3] = {(uint64_t)d->out_pitch * 2, (uint64_t)d->out_pitch * 2 * d->w,
                           (uint64_t)d->out_pitch * 2 * d->w * d->h};
-      uint32_t obox[4] = {(uint32_t)p.out_box_c, (uint32_t)kHaloTW, (uint32_t)kTRows, 1};
+      uint32_t obox[4] = {(uint32_t)p.out_box_c, (uint32_t)kHaloTW, (uint32_t)p.t_rows, 1};
       int st = encode_tensor_map(&L->mapOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out, odims, ostr, obox, TMA_SW_NONE);
       if (st != CSD_OK) return st;
     }
@@ -1479,16 +1164,12 @@ int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
   if (!attr_set) {
     CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CSD_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CSD_CUDA(cudaFuncSetAttribute(conv_halo_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CSD_CUDA(cudaFuncSetAttribute(conv_halo_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   if (L->persistent) {
     conv_halo_tp_kernel<<<L->grid, kPThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
                                                                    L->mapB, L->mapOut, L->p);
-  } else if (L->transposed) {
-    conv_halo_t_kernel<<<L->grid, kTThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
-                                                                   L->mapB, L->p);
   } else if (L->halo) {
     conv_halo_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
                                                                  L->mapB, L->p);

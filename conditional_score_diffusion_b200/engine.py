@@ -200,7 +200,7 @@ class BlockOps:
         partials = sums = None
         if use_t:
             # GroupNorm statistics of the output for free: per-(tile, pixel half) partial sums from the epilogue
-            tiles_img = math.ceil(oh / 32) * math.ceil(ow / 8) * 2
+            tiles_img = math.ceil(oh / K.transposed_tile_rows(oh)) * math.ceil(ow / 8) * 2
             partials = self.pool.get((b * tiles_img, pc.n_store, 2), torch.float32)
             sums = self._stats_slot(b, pc.cout)
         self.rec.add(K.conv_gemm, seg_list, pc.wt, pc.cout, out, batch=b, h=oh, w=ow, n_store=pc.n_store,

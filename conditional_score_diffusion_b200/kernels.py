@@ -91,12 +91,16 @@ def transposed_eligible(segments, h, w, stride=1, pad=1, z_batches=1):
     """3x3 stride-1 convs whose image tiles well into 32x8-pixel macro tiles run in the transposed halo
     mode (output channels on M, 256 pixels on N): measured faster on B200 whenever the 32-row tiling
     wastes < ~20% of the rows (tests/test_gpu_conv_gemm.py::test_transposed_timing)."""
-    return (segments[0][4] == 9 and stride == 1 and pad == 1 and z_batches == 1 and w % 8 == 0
-            and (h % 32 == 0 or h >= 64))
+    return (segments[0][4] == 9 and stride == 1 and pad == 1 and z_batches == 1 and transposed_shape_ok(h, w))
 
 
 def transposed_shape_ok(h, w):
-    return w % 8 == 0 and (h % 32 == 0 or h >= 64)
+    return w % 8 == 0 and (h % 32 == 0 or h >= 64 or h % 20 == 0)
+
+
+def transposed_tile_rows(h):
+    """Rows of the transposed kernel's macro tile (conv_gemm_prepare): 32, or 20 for images such as 40x40."""
+    return 20 if (h % 32 != 0 and h < 64 and h % 20 == 0) else 32
 
 
 def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None, n_tile=None,

@@ -357,7 +357,7 @@ def _t_case(name, B, H, W, cin, cout, seed=0, temb=True, res=True, stats=True):
     ref = ref * 0.5
     n_store = k.ceil_to(cout, 8)
     out = torch.full((B, H, W, n_store), float("nan"), device=dev, dtype=torch.bfloat16)
-    tiles = B * math.ceil(H / 32) * math.ceil(W / 8) * 2     # partial sums per (tile, pixel half)
+    tiles = B * math.ceil(H / k.transposed_tile_rows(H)) * math.ceil(W / 8) * 2     # partial sums per (tile, half)
     partials = torch.full((tiles, n_store, 2), float("nan"), device=dev) if stats else None
     k.conv_gemm(segs, wt, cout, out, batch=B, h=H, w=W, n_store=n_store, bias=bias, temb=temb_t,
                 temb_pitch=npad + 16, scale=0.5, transposed=True, stat_partials=partials)
@@ -387,7 +387,8 @@ T_RTOL = 2.0 ** -8
 def test_transposed_halo_mode():
     assert _t_case("T 96->96 32x32", 2, 32, 32, 96, 96) < T_RTOL
     assert _t_case("T 96->96 80x80 (ragged h)", 2, 80, 80, 96, 96) < T_RTOL
-    assert _t_case("T 192->192 40x40 (2 channel blocks)", 3, 40, 40, 192, 192) < T_RTOL
+    assert _t_case("T 192->192 40x40 (2 channel blocks, 20-row tiles)", 3, 40, 40, 192, 192) < T_RTOL
+    assert _t_case("T 96->96 20x24 (one 20-row tile)", 2, 20, 24, 96, 96, seed=7) < T_RTOL
     assert _t_case("T 64->96 24x20 (ragged w)", 2, 24, 20, 64, 96) < T_RTOL
     assert _t_case("T 96->6 32x32 (tiny cout)", 2, 32, 32, 96, 6, temb=False, res=False) < T_RTOL
     assert _t_case("T 8->96 32x32 (padded cin)", 2, 32, 32, 8, 96, res=False) < T_RTOL
@@ -489,6 +490,7 @@ def test_transposed_fused_groupnorm_prologue():
     assert _t_norm_case("TN (96+96)->96 64x64 cat + skip", 2, 64, 64, [96, 96], 96, seed=3, skip_c=192) < T_NORM_RTOL
     assert _t_norm_case("TN (192+96)->192 32x32 cat", 2, 32, 32, [192, 96], 192, seed=4, skip_c=288) < T_NORM_RTOL
     assert _t_norm_case("TN 192->192 32x32 affine only", 2, 32, 32, [192], 192, seed=5, silu=False) < T_NORM_RTOL
+    assert _t_norm_case("TN (192+192)->192 40x40 20-row tiles", 2, 40, 40, [192, 192], 192, seed=6, skip_c=384) < T_NORM_RTOL
 
 
 def test_gn_coeffs_match_group_norm():

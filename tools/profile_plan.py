@@ -46,6 +46,6 @@ print(f"total {total:.3f} ms over {len(evs)} ops (B={B})")
 for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1][1]):
     print(f"  {k:24s} n={v[0]:4d}  {v[1]:8.3f} ms  {100 * v[1] / total:5.1f}%")
 print("top shapes:")
-for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:40]:
+for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:90]:
     tf = f"{v[2] / v[1] / 1e9:7.1f} TF/s" if v[2] else ""
     print(f"  {str(k):70s} n={v[0]:3d} {v[1]:8.3f} ms {tf}")
