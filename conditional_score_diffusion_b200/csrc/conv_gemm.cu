@@ -46,7 +46,7 @@ constexpr int kRowBytes = kChunkK * 2;            // 64 B of bf16 per row -> SWI
 constexpr int kTileM = 128;                       // UMMA M
 constexpr int kAStageBytes = kTileM * kRowBytes;  // 8192
 constexpr int kConvThreads = 192;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr uint32_t kLayoutSw64 = 4;
 
 struct ConvGemmKernelParams {
@@ -1069,7 +1069,14 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   p.b_box_bytes = (uint32_t)(p.n_sub * kRowBytes);
   p.stage_bytes = (uint32_t)((kAStageBytes + d->n_tile * kRowBytes + 1023) & ~1023);
   const int total_iters = k_total / kChunkK;
-  const int budget = p.tmem_cols <= 128 ? 56 * 1024 : (p.tmem_cols <= 256 ? 100 * 1024 : 200 * 1024);
+  int budget = p.tmem_cols <= 128 ? 56 * 1024 : (p.tmem_cols <= 256 ? 100 * 1024 : 200 * 1024);
+  {
+    // Small grids (the 5/10/20 px levels: fewer CTAs than SMs) run one CTA per SM whatever their footprint and
+    // their K loop is TMA-latency bound, so they take the whole shared memory for a deeper ring instead of
+    // leaving room for co-resident CTAs that will never come.
+    const long long ctas = (long long)p.tiles_w * p.tiles_h * tiles_b * n_tiles * d->z_batches;
+    if (!halo_mode && ctas <= num_sms()) budget = 200 * 1024;
+  }
   int stages = budget / (int)p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > total_iters) stages = total_iters;
