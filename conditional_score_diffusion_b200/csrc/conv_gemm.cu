@@ -46,6 +46,12 @@ constexpr int kRowBytes = kChunkK * 2;            // 64 B of bf16 per row -> SWI
 constexpr int kTileM = 128;                       // UMMA M
 constexpr int kAStageBytes = kTileM * kRowBytes;  // 8192
 constexpr int kConvThreads = 192;
+// conv_gemm_kernel: a single thread can start one TMA load every ~360 cycles however small the box is (measured,
+// tools/tma_rate_probe.cu: 8 KB and 16 KB boxes, tiled or bulk, all cost the same per issue; two issuing threads
+// reach 1.7x), while one pipeline stage is only ~200 tensor cycles of work. The loads of consecutive stages are
+// therefore issued by kTapProducers threads in different warps, round-robin.
+constexpr int kTapProducers = 4;
+constexpr int kTapThreads = kConvThreads + 32 * (kTapProducers - 1);   // warps 6.. are the extra producers
 constexpr int kMaxStages = 12;
 constexpr uint32_t kLayoutSw64 = 4;
 
@@ -61,6 +67,8 @@ struct ConvGemmKernelParams {
   int wt_k_off;
   int a_batch_step;
   int num_stages, tmem_cols;
+  int producers;  // per-tap kernel: issuing threads; num_stages is a multiple of it, so a ring slot always belongs to
+                  // the same producer (the two-phase mbarrier parity scheme needs every use of a slot seen in order)
   uint32_t stage_bytes, a_box_bytes, b_box_bytes;
   float* stat_partials;  // [tiles, n_store, 2] per-tile per-channel (sum, sumsq) of the stored output, or null
   long long* debug_ts;  // perf experiment only: phase timestamps of one mid-grid CTA
@@ -205,7 +213,7 @@ __device__ __forceinline__ const float* build_addend_table(const ConvGemmKernelP
   return s_add;
 }
 
-__global__ void __launch_bounds__(kConvThreads)
+__global__ void __launch_bounds__(kTapThreads)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                  const __grid_constant__ CUtensorMap mapB, const ConvGemmKernelParams p) {
@@ -260,10 +268,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   // Single-thread issue loops: ring position / parity are running counters (no division) and the UMMA
   // descriptors advance by adding to their low word, so the instruction stream between two tcgen05.mma
   // stays shorter than the MMA itself.
-  if (warp == 0) {
-    // ===== TMA producer =====
+  if (warp == 0 || warp >= kConvThreads / 32) {
+    // ===== TMA producers: producer j issues the loads of the stages whose running index is j mod kTapProducers =====
     if (lane == 0) {
+      const int me = (warp == 0) ? 0 : warp - kConvThreads / 32 + 1;
       uint32_t stage = 0, par = 1;
+      int turn = 0;
       int kcol = p.wt_k_off;  // running K column into Wt
       const uint32_t tx_bytes = p.a_box_bytes + p.b_box_bytes * p.nsplit;
       for (int s = 0; s < p.nseg; ++s) {
@@ -274,13 +284,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           const int dx = (taps == 9) ? (tap % 3 - p.pad) : 0;
           const int cw = w0 * p.stride + dx, ch = h0 * p.stride + dy;
           for (int c = 0; c < p.seg_chunks[s]; ++c, kcol += kChunkK) {
-            ptx::mbar_wait(empty_bar(stage), par);
-            const uint32_t a_dst = smem_base + stage * p.stage_bytes;
-            const uint32_t b_dst = a_dst + kAStageBytes;
-            ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-            ptx::tma_load_4d(a_dst, mapA, full_bar(stage), p.seg_coff[s] + c * kChunkK, cw, ch, b0 + z * p.a_batch_step);
-            ptx::tma_load_3d(b_dst, &mapB, full_bar(stage), kcol, n0, z);
-            if (p.nsplit > 1) ptx::tma_load_3d(b_dst + p.b_box_bytes, &mapB, full_bar(stage), kcol, n0 + p.n_sub, z);
+            if (turn == me) {
+              ptx::mbar_wait(empty_bar(stage), par);
+#ifdef CSD_ENABLE_PHASE_TIMESTAMPS
+              if (p.debug_ts != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && me == 0 &&
+                  (kcol - p.wt_k_off) / kChunkK < 96)
+                p.debug_ts[64 + (kcol - p.wt_k_off) / kChunkK] = clock64();
+#endif
+              const uint32_t a_dst = smem_base + stage * p.stage_bytes;
+              const uint32_t b_dst = a_dst + kAStageBytes;
+              ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+              ptx::tma_load_4d(a_dst, mapA, full_bar(stage), p.seg_coff[s] + c * kChunkK, cw, ch, b0 + z * p.a_batch_step);
+              ptx::tma_load_3d(b_dst, &mapB, full_bar(stage), kcol, n0, z);
+              if (p.nsplit > 1) ptx::tma_load_3d(b_dst + p.b_box_bytes, &mapB, full_bar(stage), kcol, n0 + p.n_sub, z);
+            }
+            if (++turn == p.producers) turn = 0;
             if (++stage == (uint32_t)p.num_stages) { stage = 0; par ^= 1u; }
           }
         }
@@ -294,9 +312,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const bool split = p.nsplit > 1;
       const uint32_t b2_off = p.b_box_bytes >> 4;
       uint32_t stage = 0, par = 0, accumulate = 0;
+      bool ready = ptx::mbar_test_wait(full_bar(0), 0);
       for (int it = 0; it < total_iters; ++it) {
-        ptx::mbar_wait(full_bar(stage), par);
+        if (!ready) ptx::mbar_wait(full_bar(stage), par);
         ptx::tcgen05_fence_after();
+        // look at the next stage's barrier now: the test's latency overlaps with the MMAs issued below
+        uint32_t nstage = stage + 1, npar = par;
+        if (nstage == (uint32_t)p.num_stages) { nstage = 0; npar ^= 1u; }
+        ready = (it + 1 < total_iters) && ptx::mbar_test_wait(full_bar(nstage), npar);
         const uint32_t a_lo = ptx::smem_desc_lo(smem_base + stage * p.stage_bytes, 16);
         const uint32_t b_lo = a_lo + (kAStageBytes >> 4);
         ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(hi, a_lo), ptx::smem_desc_join(hi, b_lo), idesc, accumulate);
@@ -309,7 +332,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                            idesc, 1u);
         accumulate = 1u;
         ptx::mma_commit(empty_bar(stage));  // frees the stage when the MMAs above have read it
-        if (++stage == (uint32_t)p.num_stages) { stage = 0; par ^= 1u; }
+        stage = nstage;
+        par = npar;
       }
       ptx::mma_commit(tmem_full_bar);       // accumulator complete
     }
@@ -542,8 +566,9 @@ constexpr int kTChan = 128;     // output channels per CTA (M of the MMA)
 // cycles, epilogue ~8.7k cycles against ~6.9k tensor cycles for a 96-channel layer; measured with
 // tools/conv_phase_timing.py) and relied on a second resident CTA to fill the gap. Here ONE CTA per SM
 // walks a static list of tiles (tile = blockIdx.x + i * gridDim.x) with five specialised roles:
-//   warp 0 / 18 TMA producers     pixel halos / weight slabs (separate threads: independent run-ahead), rings
-//                                 shared by consecutive tiles
+//   warp 0      TMA producer A    pixel halos (own thread: runs a whole tile ahead of the weights)
+//   warps 18-20 TMA producers B   weight slabs, round-robin: one thread starts a TMA load only every ~360 cycles
+//                                 (tools/tma_rate_probe.cu) and a chunk needs nine 8 KB slabs per 2304 tensor cycles
 //   warp 1      MMA issuer        accumulator alternates between two 256-column TMEM buffers
 //   warps 2-9   operand transform fused GroupNorm(+SiLU) of every pixel-halo stage (when a segment has `norm`)
 //   warps 10-17 epilogue          TMEM -> (scale, bias, temb, GN partial sums) -> staging smem -> one TMA store
@@ -551,7 +576,8 @@ constexpr int kTChan = 128;     // output channels per CTA (M of the MMA)
 // the fill/drain cost is paid once per SM instead of once per tile. The whole 227 KB of shared memory
 // belongs to the CTA: 3 pixel-halo buffers, up to 12 weight slabs, a dedicated 64 KB staging tile.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kPThreads = 608;
+constexpr int kPBProducers = 3;                                    // weight-slab producer warps (issue-rate bound)
+constexpr int kPThreads = 576 + 32 * kPBProducers;
 constexpr int kPTransformThreads = 256;
 constexpr int kPEpiThreads = 256;
 constexpr int kPMaxBStages = 12;
@@ -644,9 +670,12 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         }
       }
     }
-  } else if (warp == kPThreads / 32 - 1) {
-    // ===== TMA producer B: one 128-channel x 32-K weight slab per (chunk, tap) =====
+  } else if (warp >= 18) {
+    // ===== TMA producers B: one 128-channel x 32-K weight slab per (chunk, tap); slab i is issued by producer
+    //       i mod kPBProducers, every producer tracks the whole ring so slots and parities stay consistent =====
     if (lane == 0) {
+      const int me = warp - 18;
+      int turn = 0;
       uint32_t sb = 0, b_par = 1;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
@@ -658,9 +687,12 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             int kcol = p.wt_k_off + (p.seg_kbase[s] + c) * kChunkK;
             for (int tap = 0; tap < taps; ++tap, kcol += kstep) {
               if (p.debug_nodata & 1) continue;   // perf experiment: no weight traffic
-              ptx::mbar_wait(b_empty0 + 8u * sb, b_par);
-              ptx::mbar_arrive_expect_tx(b_full0 + 8u * sb, kTChan * kRowBytes);
-              ptx::tma_load_3d(b_base + sb * p.b_stage_bytes, &mapB, b_full0 + 8u * sb, kcol, tc.n0, 0);
+              if (turn == me) {
+                ptx::mbar_wait(b_empty0 + 8u * sb, b_par);
+                ptx::mbar_arrive_expect_tx(b_full0 + 8u * sb, kTChan * kRowBytes);
+                ptx::tma_load_3d(b_base + sb * p.b_stage_bytes, &mapB, b_full0 + 8u * sb, kcol, tc.n0, 0);
+              }
+              if (++turn == kPBProducers) turn = 0;
               if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
             }
           }
@@ -693,10 +725,15 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
               if (s == 0 && c == 0) CSD_TSP(1);
               if (s == 0 && c == 1) CSD_TSP(13);
               const uint32_t x_lo0 = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
+              bool b_ready = ptx::mbar_test_wait(b_full0 + 8u * sb, b_par);
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
-                if (!(p.debug_nodata & 1)) ptx::mbar_wait(b_full0 + 8u * sb, b_par);
+                if (!b_ready && !(p.debug_nodata & 1)) ptx::mbar_wait(b_full0 + 8u * sb, b_par);
                 ptx::tcgen05_fence_after();
+                // test the next slab's barrier before issuing this slab's MMAs (latency overlaps with tensor work)
+                uint32_t nsb = sb + 1, nb_par = b_par;
+                if (nsb == (uint32_t)p.b_stages) { nsb = 0; nb_par ^= 1u; }
+                b_ready = ptx::mbar_test_wait(b_full0 + 8u * nsb, nb_par);
                 const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
                 const uint32_t x_lo = x_lo0 + (uint32_t)((((tap / 3) * pitch + (tap % 3)) * kRowBytes) >> 4);
                 ptx::mma_bf16_ss(d_tmem, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi, x_lo), idesc,
@@ -705,7 +742,8 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                                  idesc, 1u);
                 accumulate = 1u;
                 ptx::mma_commit(b_empty0 + 8u * sb);
-                if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
+                sb = nsb;
+                b_par = nb_par;
               }
               ptx::mma_commit(a_empty0 + 8u * sa);
               if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
@@ -1081,6 +1119,12 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > total_iters) stages = total_iters;
   if (stages < 2) stages = 2;
+  if (stages >= kTapProducers) {
+    stages -= stages % kTapProducers;
+    p.producers = kTapProducers;
+  } else {
+    p.producers = stages;
+  }
   p.num_stages = stages;
 
   p.out = d->out; p.out_pitch = d->out_pitch; p.out_f32 = d->out_f32; p.out_z_stride = d->out_z_stride;
@@ -1141,6 +1185,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
                   "shared-memory coefficient table", k_total_chan);
       int pbs = (int)((227 * 1024 - fixed) / p.b_stage_bytes);
       if (pbs > kPMaxBStages) pbs = kPMaxBStages;
+      pbs -= pbs % kPBProducers;   // a ring slot always belongs to the same weight producer (mbarrier parity scheme)
       p.b_stages = pbs;
       L->smem = fixed + (size_t)pbs * p.b_stage_bytes;
       const int sms = num_sms();
@@ -1181,8 +1226,8 @@ int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
     conv_halo_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
                                                                  L->mapB, L->p);
   } else {
-    conv_gemm_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
-                                                                 L->mapB, L->p);
+    conv_gemm_kernel<<<L->grid, kTapThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
+                                                                L->mapB, L->p);
   }
   CSD_LAUNCH_CHECK("conv_gemm_kernel");
   return CSD_OK;

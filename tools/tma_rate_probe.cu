@@ -11,6 +11,16 @@ using namespace csd;
 
 constexpr int kRing = 8, kSlab = 8192;
 
+__device__ __forceinline__ bool test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+// MODE 0/1/2 as in the header; 3 = 256 rows x 64 B (16 KB box, half as many issues per byte);
+// 4 = MODE 0 with a non-blocking test_wait spin instead of try_wait; 5 = MODE 0 issued by TWO threads (two warps,
+// each with its own ring half)
 template <int MODE>
 __global__ void __launch_bounds__(64) probe(const __grid_constant__ CUtensorMap map, const char* base, long long* cyc,
                                             int iters, int rows_total, int kcols) {
@@ -21,24 +31,33 @@ __global__ void __launch_bounds__(64) probe(const __grid_constant__ CUtensorMap 
     ptx::fence_mbar_init();
   }
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  const uint32_t s0 = (ptx::smem_u32(smem) + 1023u) & ~1023u;
+  constexpr int kBytes = MODE == 3 ? 2 * kSlab : kSlab;
+  constexpr int kR = MODE == 3 ? kRing / 2 : (MODE == 5 ? kRing / 2 : kRing);
+  if (MODE == 5) { if (threadIdx.x != 0 && threadIdx.x != 32) return; }
+  else if (threadIdx.x != 0) return;
+  const int who = threadIdx.x / 32;                     // MODE 5: second issuing thread uses the upper ring half
+  if (MODE == 5) iters /= 2;
+  const uint32_t s0 = ((ptx::smem_u32(smem) + 1023u) & ~1023u) + who * (kRing / 2) * kSlab;
   const long long t0 = clock64();
   // different CTAs walk different slabs (row block by CTA, K column by iteration) like the conv kernels do
-  const int rb = (blockIdx.x * 131) % (rows_total / 128);
-  for (int it = 0; it < iters + kRing; ++it) {
-    const int s = it % kRing;
-    if (it >= kRing) ptx::mbar_wait(ptx::smem_u32(&bars[s]), ((it / kRing) - 1) & 1);
+  const int rb = (blockIdx.x * 131 + who * 7) % (rows_total / 256);
+  for (int it = 0; it < iters + kR; ++it) {
+    const int s = it % kR;
+    const uint32_t bar = ptx::smem_u32(&bars[s + who * (kRing / 2)]);
+    if (it >= kR) {
+      if (MODE == 4) { while (!test_wait(bar, ((it / kR) - 1) & 1)) { } }
+      else ptx::mbar_wait(bar, ((it / kR) - 1) & 1);
+    }
     if (it < iters) {
-      const uint32_t bar = ptx::smem_u32(&bars[s]);
-      ptx::mbar_arrive_expect_tx(bar, kSlab);
+      ptx::mbar_arrive_expect_tx(bar, kBytes);
       const int kc = (it * 7 + blockIdx.x) % kcols;
-      if (MODE == 0) ptx::tma_load_3d(s0 + s * kSlab, &map, bar, kc * 32, rb * 128, 0);
+      if (MODE == 0 || MODE == 4 || MODE == 5) ptx::tma_load_3d(s0 + s * kSlab, &map, bar, kc * 32, rb * 128, 0);
+      if (MODE == 3) ptx::tma_load_3d(s0 + s * 2 * kSlab, &map, bar, kc * 32, rb * 256, 0);
       if (MODE == 1) ptx::tma_load_3d(s0 + s * kSlab, &map, bar, (kc / 2) * 64, rb * 128 + (kc & 1) * 64, 0);
       if (MODE == 2) ptx::bulk_load_1d(s0 + s * kSlab, base + ((long long)(rb * kcols + kc)) * kSlab, kSlab, bar);
     }
   }
-  if (blockIdx.x == 0) *cyc = clock64() - t0;
+  if (blockIdx.x == 0 && who == 0) *cyc = clock64() - t0;
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -58,13 +77,14 @@ int main(int argc, char** argv) {
   long long* cyc;
   cudaMallocManaged(&cyc, 8);
   const int iters = 4000;
-  const char* names[3] = {"128 rows x 64 B (SW64 box)", "64 rows x 128 B (SW128 box)", "8 KB contiguous bulk copy"};
-  for (int ctas : {148, 26, 1}) {
-    for (int mode = 0; mode < 3; ++mode) {
+  const char* names[6] = {"128 rows x 64 B (SW64 box)", "64 rows x 128 B (SW128 box)", "8 KB contiguous bulk copy",
+                          "256 rows x 64 B (16 KB box)", "128 x 64 B, test_wait spin", "128 x 64 B, two issuing threads"};
+  for (int ctas : {148, 1}) {
+    for (int mode = 0; mode < 6; ++mode) {
       CUtensorMap map;
       cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 1};
       cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * rows};
-      cuuint32_t box[3] = {mode == 1 ? 64u : 32u, mode == 1 ? 64u : 128u, 1};
+      cuuint32_t box[3] = {mode == 1 ? 64u : 32u, mode == 1 ? 64u : (mode == 3 ? 256u : 128u), 1};
       cuuint32_t es[3] = {1, 1, 1};
       enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, d, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
           mode == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -74,6 +94,9 @@ int main(int argc, char** argv) {
         if (mode == 0) { cudaFuncSetAttribute(probe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); probe<0><<<ctas, 64, smem>>>(map, d, cyc, iters, rows, kcols); }
         if (mode == 1) { cudaFuncSetAttribute(probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); probe<1><<<ctas, 64, smem>>>(map, d, cyc, iters, rows, kcols); }
         if (mode == 2) { cudaFuncSetAttribute(probe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); probe<2><<<ctas, 64, smem>>>(map, d, cyc, iters, rows, kcols); }
+        if (mode == 3) { cudaFuncSetAttribute(probe<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); probe<3><<<ctas, 64, smem>>>(map, d, cyc, iters / 2, rows, kcols); }
+        if (mode == 4) { cudaFuncSetAttribute(probe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); probe<4><<<ctas, 64, smem>>>(map, d, cyc, iters, rows, kcols); }
+        if (mode == 5) { cudaFuncSetAttribute(probe<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); probe<5><<<ctas, 64, smem>>>(map, d, cyc, iters, rows, kcols); }
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
       }
