@@ -74,6 +74,11 @@ class ConvGemmDesc(ctypes.Structure):
     ]
 
 
+class PixMajorGeom(ctypes.Structure):
+    _fields_ = [("q", c_int64), ("kp", c_int64), ("row_pitch", c_int64), ("wp", c_int32), ("ips", c_int32),
+                ("splits", c_int32), ("margin", c_int32)]
+
+
 # name -> (restype, argtypes). Every symbol declared in include/csd_b200.h must be listed here;
 # tests/test_abi.py checks both directions against the header text.
 c_float_p = ctypes.POINTER(c_float)
@@ -117,6 +122,35 @@ _PROTOTYPES = {
                                        c_void_p, c_void_p, c_void_p]),
     "csd_dense_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "csd_conv_gemm": (c_int, [ctypes.POINTER(ConvGemmDesc), c_void_p]),
+    # ---- training backward ----
+    "csd_pixmajor_geometry": (c_int, [c_int, c_int, c_int, ctypes.POINTER(PixMajorGeom)]),
+    "csd_nhwc_to_pixmajor_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          ctypes.POINTER(PixMajorGeom), c_int, c_void_p, c_void_p]),
+    "csd_wgrad_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, ctypes.POINTER(PixMajorGeom), c_void_p,
+                                    c_void_p]),
+    "csd_wgrad_reduce_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_int64, c_int64,
+                                     c_int, c_int, c_void_p]),
+    "csd_gn_bwd_stats_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                      c_int, c_int, c_int, c_void_p]),
+    "csd_gn_bwd_coeffs_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_int, c_int, c_float, c_void_p]),
+    "csd_gn_bwd_apply_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                      c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "csd_fir_resample_bwd_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float_p, c_int,
+                                               c_void_p]),
+    "csd_softmax_bwd_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_float,
+                                     c_void_p]),
+    "csd_transpose_bf16": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p]),
+    "csd_axpy_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]),
+    "csd_zero_stuff_nhwc_bf16": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "csd_nchw_grad_to_nhwc_bf16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                           c_int, c_int, c_void_p]),
+    "csd_bias_temb_grad_f32": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "csd_sgemm_small_f32": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_int,
+                                    c_float, c_void_p, c_int, c_void_p, c_void_p]),
+    "csd_silu_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "csd_time_features_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "csd_dsm_loss_bwd_f32": (c_int, [c_void_p] * 7 + [c_int, c_int64, c_void_p]),
 }
 
 _lib = None

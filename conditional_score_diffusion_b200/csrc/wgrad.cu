@@ -1,0 +1,372 @@
+// Weight gradients of the convolutions / 1x1 projections of the score network (training backward).
+//
+// Reference: the reference has no hand-written backward - `loss.backward()` (losses.py:345-407 via Lightning)
+// reaches cuDNN's wgrad for nn.Conv2d (models/layers.py:100-132) and ATen's einsum backward for NIN
+// (models/layers.py:546-564). The contraction is
+//     dW[co, ci, ky, kx] = sum over (image, output pixel o) of  g[o, co] * a[o*stride + k - pad, ci]
+// i.e. a GEMM whose K dimension is the PIXEL index. tcgen05 takes K-major operands from shared memory, so
+// both tensors are first re-laid-out from NHWC into a "pixel-major" form (one row per channel, pixels
+// contiguous, on a zero-padded (H+2) x Wp grid, Wp = ceil8(W+2)):
+//   - the activation is written in three copies shifted by kx-1 = -1, 0, +1 pixels, so that every tap's
+//     operand starts on a 16-byte boundary (TMA box rows must be 16-byte aligned in global memory; a ky
+//     shift is a whole padded row = a multiple of 8 elements);
+//   - the output gradient is written once, on the INPUT grid at (o*stride + 1 - pad): for the stride-2
+//     convolutions this is the zero-stuffed gradient, which turns their wgrad into the stride-1 form.
+// Because g is zero on every padding position of the grid, products that involve a wrapped / out-of-image
+// activation position vanish, and the flat shift (ky-1)*Wp selects the tap.
+//
+// wgrad_gemm_kernel: one CTA = (128 output channels) x (n_tile input channels) x (one tap) x (one split of the
+// batch); K loop over 64-pixel chunks (128-byte swizzled rows) through a TMA ring; fp32 accumulators in TMEM;
+// partial sums per split are written to a scratch tensor and reduced in a fixed order by wgrad_reduce_kernel
+// (deterministic: no atomics), which also applies the layer's output scale and scatters into the reference's
+// parameter layout ([Cout, Cin, kh, kw] for nn.Conv2d, [in, out] for NIN.W).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tensormap.cuh"
+#include "../../include/csd_b200.h"
+
+#include <algorithm>
+
+namespace csd {
+
+// ---------------------------------------------------------------------------------------------------------
+// NHWC bf16 -> pixel-major copies
+// ---------------------------------------------------------------------------------------------------------
+struct PixMajorParams {
+  const __nv_bfloat16* src;
+  int pitch, c_off, c_cnt;
+  int batch, h, w;             // source extent
+  int stride, offset;          // grid position of source pixel (y, x) = (y*stride + offset, x*stride + offset)
+  int wp;                      // padded grid row width
+  long long q;                 // padded grid pixels per image = (grid_h + 2) * wp
+  int ips;                     // images per split
+  int margin;                  // first data column of a row
+  long long row_pitch;         // elements per channel row = margin + kp + margin
+  int ncopies;                 // 1 (centre only) or 3 (kx = 0, 1, 2)
+  long long copy_stride;       // elements between copies
+  __nv_bfloat16* out;          // [copies][splits][c_cnt][row_pitch]
+};
+
+// grid (ceil(c_cnt / 64), h, batch), block 256. One source row (b, y) x 64 channels per CTA: 64-pixel x 64-channel
+// tiles are read along channels (16-byte vectors), transposed through shared memory, and written along pixels.
+__global__ void __launch_bounds__(256) pixmajor_kernel(const PixMajorParams p) {
+  __shared__ __nv_bfloat16 tile[64][66];   // [channel][pixel], +2 padding: conflict-free column reads
+  const int c0 = blockIdx.x * 64;
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int split = b / p.ips, bl = b % p.ips;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gy = y * p.stride + p.offset;
+  const long long row0 = (long long)p.margin + (long long)bl * p.q + (long long)(gy + 1) * p.wp;
+  for (int x0 = 0; x0 < p.w; x0 += 64) {
+    // load: thread -> (pixel = t / 8 (+32), 8-channel vector = t % 8)
+    const int cv = threadIdx.x & 7;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int px = (threadIdx.x >> 3) + half * 32;
+      const int x = x0 + px;
+      const int c = c0 + cv * 8;
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = 0.f;
+      if (x < p.w && c < p.c_cnt) {
+        const __nv_bfloat16* sp = p.src + (((long long)b * p.h + y) * p.w + x) * p.pitch + p.c_off + c;
+        if (c + 8 <= p.c_cnt && ((p.c_off | p.pitch) & 7) == 0) {
+          bf16x8 v = *reinterpret_cast<const bf16x8*>(sp);
+          unpack8(v, f);
+        } else {
+          for (int i = 0; i < 8 && c + i < p.c_cnt; ++i) f[i] = __bfloat162float(sp[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tile[cv * 8 + i][px] = __float2bfloat16_rn(f[i]);
+    }
+    __syncthreads();
+    // store: warp -> 8 channels; lane -> pixels lane and lane + 32
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int cl = warp * 8 + k;
+      const int c = c0 + cl;
+      if (c >= p.c_cnt) break;
+      __nv_bfloat16* rowp = p.out + ((long long)split * p.c_cnt + c) * p.row_pitch + row0;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int px = lane + half * 32;
+        const int x = x0 + px;
+        if (x >= p.w) continue;
+        const __nv_bfloat16 v = tile[cl][px];
+        const int gx = x * p.stride + p.offset;
+        if (p.ncopies == 1) {
+          rowp[gx + 1] = v;
+        } else {
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) rowp[(long long)kx * p.copy_stride + gx + 2 - kx] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// split-K wgrad GEMM on tcgen05
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWK = 64;                       // pixels (K elements) per stage: 128-byte rows, SWIZZLE_128B
+constexpr int kWM = 128;                      // UMMA M (output channels per CTA)
+constexpr int kWABytes = kWM * kWK * 2;       // 16 KB
+constexpr int kWThreads = 224;                // warp 0: g producer, warp 1: MMA, warps 2-5: epilogue, warp 6: a producer
+constexpr int kWMaxStages = 8;
+constexpr uint32_t kLayoutSw128 = 2;
+
+struct WgradParams {
+  int taps, wp, margin, k_chunks;
+  int cout, cin, n_tile, n_tiles;
+  int num_stages, tmem_cols;
+  uint32_t stage_bytes, b_bytes;
+  float* partial;   // [splits][taps][cout][cin]
+};
+
+__global__ void __launch_bounds__(kWThreads, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapA0,
+                  const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+                  const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + p.num_stages * p.stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kWMaxStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kWMaxStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kWMaxStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x / p.n_tiles, nt = blockIdx.x % p.n_tiles;
+  const int m0 = mt * kWM, n0 = nt * p.n_tile;
+  const int tap = blockIdx.y, split = blockIdx.z;
+  const int ky = p.taps == 9 ? tap / 3 : 1, kx = p.taps == 9 ? tap % 3 : 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&mapG);
+    for (int s = 0; s < p.num_stages; ++s) {
+      ptx::mbar_init(full_bar(s), 2);    // one arrive.expect_tx per producer
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {                       // ===== producer of the output-gradient operand (M side) =====
+      uint32_t stage = 0, par = 1;
+      for (int k = 0; k < p.k_chunks; ++k) {
+        ptx::mbar_wait(empty_bar(stage), par);
+        ptx::mbar_arrive_expect_tx(full_bar(stage), (uint32_t)kWABytes);
+        ptx::tma_load_3d(smem_base + stage * p.stage_bytes, &mapG, full_bar(stage), p.margin + k * kWK, m0, split);
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; par ^= 1u; }
+      }
+    }
+  } else if (warp == 6) {
+    if (lane == 0) {                       // ===== producer of the activation operand (N side) =====
+      const CUtensorMap* mapA = kx == 0 ? &mapA0 : (kx == 1 ? &mapA1 : &mapA2);
+      ptx::prefetch_tensormap(mapA);
+      const int col0 = p.margin + (ky - 1) * p.wp;
+      uint32_t stage = 0, par = 1;
+      for (int k = 0; k < p.k_chunks; ++k) {
+        ptx::mbar_wait(empty_bar(stage), par);
+        ptx::mbar_arrive_expect_tx(full_bar(stage), p.b_bytes);
+        ptx::tma_load_3d(smem_base + stage * p.stage_bytes + kWABytes, mapA, full_bar(stage), col0 + k * kWK, n0, split);
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; par ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                       // ===== MMA issuer =====
+      const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)p.n_tile);
+      const uint32_t hi = ptx::smem_desc_hi(1024, kLayoutSw128);
+      uint32_t stage = 0, par = 0, accumulate = 0;
+      for (int k = 0; k < p.k_chunks; ++k) {
+        ptx::mbar_wait(full_bar(stage), par);
+        ptx::tcgen05_fence_after();
+        const uint32_t a_lo = ptx::smem_desc_lo(smem_base + stage * p.stage_bytes, 16);
+        const uint32_t b_lo = a_lo + (kWABytes >> 4);
+#pragma unroll
+        for (int kk = 0; kk < kWK / 16; ++kk) {   // 32 bytes of K per instruction inside the 128-byte swizzled row
+          ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(hi, a_lo + 2 * kk), ptx::smem_desc_join(hi, b_lo + 2 * kk), idesc,
+                           accumulate);
+          accumulate = 1u;
+        }
+        ptx::mma_commit(empty_bar(stage));
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; par ^= 1u; }
+      }
+      ptx::mma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue (warps 2..5): TMEM lane = output channel =====
+    const int q = warp & 3;
+    const int co = m0 + q * 32 + lane;
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tcgen05_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* orow = p.partial + (((long long)split * p.taps + tap) * p.cout + co) * p.cin;
+    const int ncols = min(p.n_tile, p.cin - n0);
+    for (int col = 0; col < ncols; col += 16) {
+      uint32_t r[16];
+      __syncwarp();
+      ptx::tmem_ld_x16(t_row + col, r);
+      ptx::tmem_ld_wait();
+      if (co < p.cout) {
+        const int cnt = min(16, ncols - col);
+        for (int i = 0; i < cnt; ++i) orow[n0 + col + i] = __uint_as_float(r[i]);
+      }
+    }
+  }
+
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// dW[co*s_co + (ci_off+ci)*s_ci + tap*s_tap] (+)= scale * sum_split partial[split][tap][co][ci]
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int cout, int cin, float scale,
+                    float* __restrict__ dw, long long s_co, long long s_ci, long long s_tap, int ci_off, int accumulate) {
+  const long long per_split = (long long)taps * cout * cin;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_split;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % cin);
+    const int co = (int)((idx / cin) % cout);
+    const int tap = (int)(idx / ((long long)cin * cout));
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[(long long)s * per_split + idx];
+    float* o = dw + co * s_co + (long long)(ci_off + ci) * s_ci + tap * s_tap;
+    *o = accumulate ? (*o + acc * scale) : acc * scale;
+  }
+}
+
+static int next_pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+}  // namespace csd
+
+extern "C" {
+
+int csd_pixmajor_geometry(int batch, int grid_h, int grid_w, csd_pixmajor_geom* g) {
+  using namespace csd;
+  CSD_REQUIRE(g != nullptr && batch >= 1 && grid_h >= 1 && grid_w >= 1, "pixmajor_geometry: bad arguments");
+  g->wp = (grid_w + 2 + 7) / 8 * 8;
+  g->q = (int64_t)(grid_h + 2) * g->wp;
+  // images per split: K per CTA of at least ~4096 pixels, but keep >= ~16 splits for the large images
+  int64_t ips = (4096 + g->q - 1) / g->q;
+  if (ips < 1) ips = 1;
+  if (ips > batch) ips = batch;
+  g->ips = (int32_t)ips;
+  g->splits = (batch + g->ips - 1) / g->ips;
+  const int64_t ks = g->ips * g->q;
+  g->kp = (ks + 63) / 64 * 64;
+  g->margin = (g->wp + 8 + 63) / 64 * 64;
+  g->row_pitch = g->margin + g->kp + g->margin;
+  return CSD_OK;
+}
+
+int csd_nhwc_to_pixmajor_bf16(const void* src, int pitch, int c_off, int c_cnt, int batch, int h, int w, int stride,
+                              int offset, const csd_pixmajor_geom* g, int ncopies, void* out, csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(src && out && g, "nhwc_to_pixmajor: null pointer");
+  CSD_REQUIRE(ncopies == 1 || ncopies == 3, "nhwc_to_pixmajor: ncopies %d (1 or 3)", ncopies);
+  CSD_REQUIRE(c_cnt >= 1 && c_off >= 0 && c_off + c_cnt <= pitch, "nhwc_to_pixmajor: bad channel range");
+  CSD_REQUIRE(stride >= 1 && offset >= 0 && batch >= 1 && batch <= 65535 && h >= 1 && h <= 65535 && w >= 1,
+              "nhwc_to_pixmajor: bad shape");
+  // the last source pixel must land inside the padded grid the geometry was built for
+  CSD_REQUIRE((w - 1) * stride + offset + 2 < g->wp && (int64_t)((h - 1) * stride + offset + 2) * g->wp <= g->q,
+              "nhwc_to_pixmajor: source %dx%d (stride %d, offset %d) does not fit the grid (wp=%d)", h, w, stride, offset,
+              g->wp);
+  PixMajorParams p;
+  p.src = static_cast<const __nv_bfloat16*>(src);
+  p.pitch = pitch; p.c_off = c_off; p.c_cnt = c_cnt;
+  p.batch = batch; p.h = h; p.w = w; p.stride = stride; p.offset = offset;
+  p.wp = g->wp; p.q = g->q; p.ips = g->ips; p.margin = g->margin; p.row_pitch = g->row_pitch;
+  p.ncopies = ncopies;
+  p.copy_stride = (long long)g->splits * c_cnt * g->row_pitch;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  dim3 grid((unsigned)ceil_div(c_cnt, 64), (unsigned)h, (unsigned)batch);
+  pixmajor_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CSD_LAUNCH_CHECK("pixmajor_kernel");
+  return CSD_OK;
+}
+
+int csd_wgrad_gemm_bf16(const void* g_pm, int cout, const void* a_pm, int cin, int taps, const csd_pixmajor_geom* g,
+                        float* partial, csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(g_pm && a_pm && g && partial, "wgrad_gemm: null pointer");
+  CSD_REQUIRE(taps == 1 || taps == 9, "wgrad_gemm: taps %d (1 or 9)", taps);
+  CSD_REQUIRE(cout >= 1 && cin >= 1, "wgrad_gemm: bad channel counts");
+  WgradParams p;
+  p.taps = taps; p.wp = g->wp; p.margin = g->margin; p.k_chunks = (int)(g->kp / kWK);
+  p.cout = cout; p.cin = cin;
+  const int n16 = ceil_div(cin, 16) * 16;
+  p.n_tiles = ceil_div(n16, 256);
+  p.n_tile = ceil_div(ceil_div(n16, p.n_tiles), 16) * 16;
+  p.b_bytes = (uint32_t)p.n_tile * kWK * 2;
+  p.stage_bytes = kWABytes + p.b_bytes;
+  p.num_stages = std::min<int>(kWMaxStages, (int)((200 * 1024) / p.stage_bytes));
+  p.tmem_cols = next_pow2_cols(p.n_tile);
+  p.partial = partial;
+  const int m_tiles = ceil_div(cout, kWM);
+
+  CUtensorMap mapG, mapA[3];
+  {
+    uint64_t dims[3] = {(uint64_t)g->row_pitch, (uint64_t)cout, (uint64_t)g->splits};
+    uint64_t strides[2] = {(uint64_t)g->row_pitch * 2, (uint64_t)g->row_pitch * 2 * cout};
+    uint32_t box[3] = {(uint32_t)kWK, (uint32_t)kWM, 1};
+    int st = encode_tensor_map(&mapG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, g_pm, dims, strides, box, TMA_SW_128);
+    if (st != CSD_OK) return st;
+  }
+  const long long copy_stride = (long long)g->splits * cin * g->row_pitch;
+  for (int kx = 0; kx < 3; ++kx) {
+    // a 1-tap contraction has the centre copy only (stored first)
+    const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(a_pm) + (taps == 9 ? kx * copy_stride : 0);
+    uint64_t dims[3] = {(uint64_t)g->row_pitch, (uint64_t)cin, (uint64_t)g->splits};
+    uint64_t strides[2] = {(uint64_t)g->row_pitch * 2, (uint64_t)g->row_pitch * 2 * cin};
+    uint32_t box[3] = {(uint32_t)kWK, (uint32_t)p.n_tile, 1};
+    int st = encode_tensor_map(&mapA[kx], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, TMA_SW_128);
+    if (st != CSD_OK) return st;
+  }
+  const size_t smem = (size_t)p.num_stages * p.stage_bytes + 8 * (2 * kWMaxStages + 2) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSD_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(m_tiles * p.n_tiles), (unsigned)taps, (unsigned)g->splits);
+  wgrad_gemm_kernel<<<grid, kWThreads, smem, static_cast<cudaStream_t>(stream)>>>(mapG, mapA[0], mapA[1], mapA[2], p);
+  CSD_LAUNCH_CHECK("wgrad_gemm_kernel");
+  return CSD_OK;
+}
+
+int csd_wgrad_reduce_f32(const float* partial, int splits, int taps, int cout, int cin, float scale, float* dw,
+                         int64_t stride_co, int64_t stride_ci, int64_t stride_tap, int ci_off, int accumulate,
+                         csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(partial && dw && splits >= 1 && taps >= 1 && cout >= 1 && cin >= 1, "wgrad_reduce: bad arguments");
+  const long long per_split = (long long)taps * cout * cin;
+  const int blocks = (int)std::min<long long>(ceil_div_ll(per_split, 256), (long long)num_sms() * 8);
+  wgrad_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, splits, taps, cout, cin, scale, dw,
+                                                                           stride_co, stride_ci, stride_tap, ci_off,
+                                                                           accumulate);
+  CSD_LAUNCH_CHECK("wgrad_reduce_kernel");
+  return CSD_OK;
+}
+
+}  // extern "C"

@@ -368,3 +368,133 @@ def dense_rows(act, w, bias, out, total_out=None):
     total_out = total_out if total_out is not None else w.shape[0]
     check(_lib.lib().csd_dense_rows_f32(_ptr(act), _ptr(w), _ptr(bias), _ptr(out), b, in_dim, total_out, _stream()))
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# training backward (adjoints of the kernels above)
+# --------------------------------------------------------------------------------------------
+def pixmajor_geometry(batch, grid_h, grid_w):
+    g = _lib.PixMajorGeom()
+    check(_lib.lib().csd_pixmajor_geometry(batch, grid_h, grid_w, ctypes.byref(g)))
+    return g
+
+
+def pixmajor_alloc(geom, channels, ncopies, device):
+    """Zero-filled pixel-major buffer [copies, splits, channels, row_pitch] bf16 (the zeros are the grid padding;
+    csd_nhwc_to_pixmajor_bf16 never writes them, so the buffer is zeroed once and reused for the same pattern)."""
+    return torch.zeros(ncopies, geom.splits, channels, geom.row_pitch, device=device, dtype=_BF16)
+
+
+def nhwc_to_pixmajor(src, c_off, c_cnt, geom, out, stride=1, offset=0):
+    b, h, w, pitch = src.shape
+    check(_lib.lib().csd_nhwc_to_pixmajor_bf16(_ptr(src), pitch, c_off, c_cnt, b, h, w, stride, offset,
+                                               ctypes.byref(geom), out.shape[0], _ptr(out), _stream()))
+    return out
+
+
+def wgrad_gemm(g_pm, cout, a_pm, cin, taps, geom, partial):
+    check(_lib.lib().csd_wgrad_gemm_bf16(_ptr(g_pm), cout, _ptr(a_pm), cin, taps, ctypes.byref(geom), _ptr(partial),
+                                         _stream()))
+    return partial
+
+
+def wgrad_reduce(partial, splits, taps, cout, cin, scale, dw, stride_co, stride_ci, stride_tap, ci_off=0,
+                 accumulate=False):
+    check(_lib.lib().csd_wgrad_reduce_f32(_ptr(partial), splits, taps, cout, cin, float(scale), _ptr(dw), stride_co,
+                                          stride_ci, stride_tap, ci_off, int(accumulate), _stream()))
+    return dw
+
+
+def gn_bwd_stats(x, c, dy, dy_c_off, fwd_coef, s, s_c_off, silu):
+    b = x.shape[0]
+    hw = x.numel() // (b * x.shape[-1])
+    check(_lib.lib().csd_gn_bwd_stats_bf16(_ptr(x), c, x.shape[-1], _ptr(dy), dy.shape[-1], dy_c_off, _ptr(fwd_coef),
+                                           _ptr(s), s.shape[1], s_c_off, b, hw, int(silu), _stream()))
+
+
+def gn_bwd_coeffs(sums0, c0, sums1, c1, gamma, s, bwd_coef, dgamma, dbeta, hw, groups, eps=1e-6):
+    b = sums0.shape[0]
+    check(_lib.lib().csd_gn_bwd_coeffs_f32(_ptr(sums0), c0, _ptr(sums1), c1, _ptr(gamma), _ptr(s), _ptr(bwd_coef),
+                                           _ptr(dgamma), _ptr(dbeta), b, hw, groups, float(eps), _stream()))
+
+
+def gn_bwd_apply(x, c, dy, dy_c_off, fwd_coef, bwd_coef, b_c_off, dx, silu, accumulate):
+    b = x.shape[0]
+    hw = x.numel() // (b * x.shape[-1])
+    check(_lib.lib().csd_gn_bwd_apply_bf16(_ptr(x), c, x.shape[-1], _ptr(dy), dy.shape[-1], dy_c_off, _ptr(fwd_coef),
+                                           _ptr(bwd_coef), bwd_coef.shape[1], b_c_off, _ptr(dx), dx.shape[-1], b, hw,
+                                           int(silu), int(accumulate), _stream()))
+
+
+def fir_resample_bwd(g, din, mode, taps, accumulate=False):
+    """g: gradient of the forward output, din [B, h, w, pitch]: gradient of the forward input."""
+    b, h, w, pitch = din.shape
+    arr = (ctypes.c_float * 4)(*[float(t) for t in taps])
+    check(_lib.lib().csd_fir_resample_bwd_nhwc_bf16(_ptr(g), _ptr(din), b, h, w, pitch,
+                                                    {"up": 1, "down": 2, "prefilter": 3}[mode], arr, int(accumulate),
+                                                    _stream()))
+    return din
+
+
+def softmax_bwd(probs, dp, ds, cols, scale):
+    rows = probs.numel() // probs.shape[-1]
+    check(_lib.lib().csd_softmax_bwd_bf16(_ptr(probs), probs.shape[-1], _ptr(dp), dp.shape[-1], _ptr(ds), ds.shape[-1],
+                                          rows, cols, float(scale), _stream()))
+    return ds
+
+
+def transpose(src, out, rows, cols):
+    """src [z, rows, pitch_in] -> out [z, cols, pitch_out] (bf16)."""
+    z = src.shape[0]
+    check(_lib.lib().csd_transpose_bf16(_ptr(src), src.shape[-1], src.shape[-2] * src.shape[-1], _ptr(out), out.shape[-1],
+                                        out.shape[-2] * out.shape[-1], rows, cols, z, _stream()))
+    return out
+
+
+def axpy(src, dst, alpha=1.0, accumulate=True):
+    assert src.numel() == dst.numel()
+    check(_lib.lib().csd_axpy_bf16(_ptr(src), _ptr(dst), src.numel(), float(alpha), int(accumulate), _stream()))
+    return dst
+
+
+def zero_stuff(src, dst, stride, offset):
+    b, h, w, pitch = src.shape
+    check(_lib.lib().csd_zero_stuff_nhwc_bf16(_ptr(src), _ptr(dst), b, h, w, dst.shape[1], dst.shape[2], pitch, stride,
+                                              offset, _stream()))
+    return dst
+
+
+def nchw_grad_to_nhwc(g0, c0, rs0, g1, c1, rs1, out):
+    b, h, w, cpad = out.shape
+    check(_lib.lib().csd_nchw_grad_to_nhwc_bf16(_ptr(g0), c0, _ptr(rs0), _ptr(g1), c1, _ptr(rs1), _ptr(out), cpad, b, h, w,
+                                                _stream()))
+    return out
+
+
+def bias_temb_grad(chan_sums, c, scale, dbias0=None, dbias1=None, dtproj=None, tproj_pitch=0):
+    check(_lib.lib().csd_bias_temb_grad_f32(_ptr(chan_sums), chan_sums.shape[0], c, float(scale), _ptr(dbias0),
+                                            _ptr(dbias1), _ptr(dtproj), tproj_pitch, _stream()))
+
+
+def sgemm_small(ta, tb, m, n, k, a, lda, b, ldb, c, ldc, alpha=1.0, beta=0.0, bias=None):
+    check(_lib.lib().csd_sgemm_small_f32(int(ta), int(tb), m, n, k, float(alpha), _ptr(a), lda, _ptr(b), ldb, float(beta),
+                                         _ptr(c), ldc, _ptr(bias), _stream()))
+    return c
+
+
+def silu_f32(x, y, dy=None):
+    check(_lib.lib().csd_silu_f32(_ptr(x), _ptr(dy), _ptr(y), x.numel(), int(dy is not None), _stream()))
+    return y
+
+
+def time_features(labels, nf, embedding_type, fourier_w, emb):
+    check(_lib.lib().csd_time_features_f32(_ptr(labels), labels.shape[0], nf, 1 if embedding_type == "fourier" else 0,
+                                           _ptr(fourier_w), _ptr(emb), _stream()))
+    return emb
+
+
+def dsm_loss_bwd(score, z, a, c, w, grad_losses, dscore):
+    b, ps = _per_sample(score)
+    check(_lib.lib().csd_dsm_loss_bwd_f32(_ptr(score), _ptr(z), _ptr(a), _ptr(c), _ptr(w), _ptr(grad_losses), _ptr(dscore),
+                                          b, ps, _stream()))
+    return dscore

@@ -257,8 +257,115 @@ typedef struct csd_conv_gemm_desc {
 
 int csd_conv_gemm(const csd_conv_gemm_desc* desc, csd_stream_t stream);
 
-/* ---- program: a recorded list of the ops above, executed with one C call -------------------- */
-/* (declared in the second half of this header, after the op record types)                      */
+/* ---- training backward ------------------------------------------------------------------------------
+ * The reference obtains every gradient from PyTorch autograd (`loss.backward()` under Lightning,
+ * lightning_modules/BaseSdeGenerativeModel.py:57-60; losses.py:345-407 in the non-Lightning step_fn): cuDNN
+ * dgrad / wgrad for nn.Conv2d, ATen backward for nn.GroupNorm, nn.SiLU, F.softmax, einsum, and the custom
+ * autograd.Function of upfirdn2d (op/upfirdn2d.py:19-142). The entry points below are the adjoints of this
+ * library's forward kernels. Activation gradients are NHWC bf16 (same pitch as the activation), parameter
+ * gradients fp32 in the reference's parameter layout. Data gradients of convolutions (dgrad) are csd_conv_gemm
+ * calls with flipped / transposed packed weights (stride-2 convolutions through csd_zero_stuff_nhwc_bf16).   */
+
+/* Pixel-major operand layout of the weight-gradient GEMM: one row per channel, pixels contiguous on a zero
+ * padded (grid_h + 2) x wp grid, `ips` images per split-K slice; rows are [margin | kp | margin] elements.     */
+typedef struct csd_pixmajor_geom {
+  int64_t q;          /* padded grid pixels per image = (grid_h + 2) * wp                */
+  int64_t kp;         /* K extent of one split (ips * q rounded up to 64)                */
+  int64_t row_pitch;  /* elements per channel row = margin + kp + margin                  */
+  int32_t wp;         /* padded row width = ceil8(grid_w + 2)                            */
+  int32_t ips;        /* images per split                                                */
+  int32_t splits;     /* ceil(batch / ips)                                               */
+  int32_t margin;     /* zero columns before / after the data (>= wp + 8, multiple of 64) */
+} csd_pixmajor_geom;
+
+int csd_pixmajor_geometry(int batch, int grid_h, int grid_w, csd_pixmajor_geom* g);
+
+/* out[copy][split][c][margin + bl*q + (y*stride+offset+1)*wp + (x*stride+offset) + 2 - copy_kx] = src[b, y, x, c_off+c]
+ * with b = split*ips + bl. ncopies = 3 writes the kx = 0,1,2 shifted copies a 3x3 contraction needs (copy index =
+ * kx), ncopies = 1 only the centre (kx = 1). `out` must have been zero-filled once: positions the pattern
+ * does not touch are the grid's zero padding and are never written.                                          */
+int csd_nhwc_to_pixmajor_bf16(const void* src, int pitch, int c_off, int c_cnt, int batch, int h, int w, int stride,
+                              int offset, const csd_pixmajor_geom* g, int ncopies, void* out, csd_stream_t stream);
+
+/* partial[split][tap][co][ci] = sum over the split's grid pixels q of g_pm[split][co][q] * a_pm[kx][split][ci][q +
+ * (ky-1)*wp] (tcgen05, fp32 accumulation): the wgrad of nn.Conv2d 3x3 (taps = 9) / 1x1 and NIN (taps = 1).     */
+int csd_wgrad_gemm_bf16(const void* g_pm, int cout, const void* a_pm, int cin, int taps, const csd_pixmajor_geom* g,
+                        float* partial, csd_stream_t stream);
+
+/* dw[co*stride_co + (ci_off+ci)*stride_ci + tap*stride_tap] (+)= scale * sum_split partial[split][tap][co][ci]
+ * (fixed summation order). nn.Conv2d weight [Cout, Cin, 3, 3]: strides (Cin*9, 9, 1); NIN.W [in, out]: (1, out, 0). */
+int csd_wgrad_reduce_f32(const float* partial, int splits, int taps, int cout, int cin, float scale, float* dw,
+                         int64_t stride_co, int64_t stride_ci, int64_t stride_tap, int ci_off, int accumulate,
+                         csd_stream_t stream);
+
+/* GroupNorm(+SiLU) backward in three passes (adjoint of csd_gn_apply_bf16 / the fused conv prologue):
+ * stats:  s[b, s_c_off + c, 0..1] += (sum_p du, sum_p du * x), du = dy * silu'(x*scale + shift) (or dy), per source;
+ *         fwd_coef = that source's (scale, shift) table from csd_gn_coeffs_f32; the caller zeroes s beforehand.
+ * coeffs: bwd_coef[b, c, 0..3] = (A, B, C, 0) with dx = A*du + B*x + C over the channel concatenation; if dgamma /
+ *         dbeta are given, dgamma[c] += sum_b rstd*(S2 - mean*S1), dbeta[c] += sum_b S1.
+ * apply:  dx (=|+=) A*du + B*x + C for one source.                                                            */
+int csd_gn_bwd_stats_bf16(const void* x, int c, int x_pitch, const void* dy, int dy_pitch, int dy_c_off,
+                          const float* fwd_coef, float* s, int c_total, int s_c_off, int batch, int hw, int silu,
+                          csd_stream_t stream);
+int csd_gn_bwd_coeffs_f32(const float* sums0, int c0, const float* sums1, int c1, const float* gamma, const float* s,
+                          float* bwd_coef, float* dgamma, float* dbeta, int batch, int hw, int groups, float eps,
+                          csd_stream_t stream);
+int csd_gn_bwd_apply_bf16(const void* x, int c, int x_pitch, const void* dy, int dy_pitch, int dy_c_off,
+                          const float* fwd_coef, const float* bwd_coef, int c_total, int b_c_off, void* dx, int dx_pitch,
+                          int batch, int hw, int silu, int accumulate, csd_stream_t stream);
+
+/* Adjoint of csd_fir_resample_nhwc_bf16 (UpFirDn2dBackward, op/upfirdn2d.py:19-85): g is the gradient of the
+ * forward OUTPUT, din [batch, h, w, c_pitch] the gradient of the forward input (h, w = forward input extent),
+ * same mode numbers and taps as the forward call.                                                            */
+int csd_fir_resample_bwd_nhwc_bf16(const void* g, void* din, int batch, int h, int w, int c_pitch, int mode,
+                                   const float* taps4_host, int accumulate, csd_stream_t stream);
+
+/* ds = scale * p * (dp - sum_j p_j dp_j) per row: adjoint of csd_softmax_rows_f32_bf16 (dp fp32, ds bf16 with
+ * columns >= cols zero-filled up to ds_pitch).                                                               */
+int csd_softmax_bwd_bf16(const void* probs, int p_pitch, const float* dp, int dp_pitch, void* ds, int ds_pitch,
+                         int64_t rows, int cols, float scale, csd_stream_t stream);
+
+/* out[z, c, r] = in[z, r, c] (bf16; the K-major operands of the attention backward GEMMs).                   */
+int csd_transpose_bf16(const void* in, int in_pitch, int64_t in_z_stride, void* out, int out_pitch, int64_t out_z_stride,
+                       int rows, int cols, int z, csd_stream_t stream);
+
+/* dst = alpha * src (+ dst if accumulate): gradient of a residual / skip addition. n elements, multiple of 8. */
+int csd_axpy_bf16(const void* src, void* dst, int64_t n, float alpha, int accumulate, csd_stream_t stream);
+
+/* dst[b, y*stride+offset, x*stride+offset, :] = src[b, y, x, :], zero elsewhere: turns the data gradient of a
+ * stride-2 convolution into a stride-1 convolution with the flipped weights.                                  */
+int csd_zero_stuff_nhwc_bf16(const void* src, void* dst, int batch, int h, int w, int dst_h, int dst_w, int c_pitch,
+                             int stride, int offset, csd_stream_t stream);
+
+/* Adjoint of csd_nhwc_bf16_to_nchw: out[b,h,w,c] = g0[b,c,h,w]*row_scale0[b] (c < c0), g1[...]*row_scale1[b]
+ * (c0 <= c < c0+c1), 0 for padding channels. g0 / g1 may be NULL (no gradient for that output group).          */
+int csd_nchw_grad_to_nhwc_bf16(const float* g0, int c0, const float* row_scale0, const float* g1, int c1,
+                               const float* row_scale1, void* out, int c_pad, int batch, int h, int w,
+                               csd_stream_t stream);
+
+/* From chan_sums [batch, c, 2] of an output gradient (csd_gn_chan_stats_bf16): dbias0/1[c] += scale * sum_b sums,
+ * dtproj[b*tproj_pitch + c] += scale * sums[b, c] (gradient of the `h += Dense_0(act(temb))` add). Any may be NULL. */
+int csd_bias_temb_grad_f32(const float* chan_sums, int batch, int c, float scale, float* dbias0, float* dbias1,
+                           float* dtproj, int tproj_pitch, csd_stream_t stream);
+
+/* Small fp32 GEMM for the time-embedding MLP / Dense_0 projections and their gradients:
+ * C = alpha * op(A) op(B) + beta * C + bias[n], op(A)(m,k) = trans_a ? A[k*lda+m] : A[m*lda+k], op(B)(k,n) =
+ * trans_b ? B[n*ldb+k] : B[k*ldb+n].                                                                          */
+int csd_sgemm_small_f32(int trans_a, int trans_b, int m, int n, int k, float alpha, const float* a, int lda,
+                        const float* b, int ldb, float beta, float* c, int ldc, const float* bias, csd_stream_t stream);
+
+/* y = silu(x) (grad = 0) or y = dy * silu'(x) (grad = 1), fp32.                                               */
+int csd_silu_f32(const float* x, const float* dy, float* y, int64_t n, int grad, csd_stream_t stream);
+
+/* The sinusoidal / Gaussian-Fourier features alone (first stage of csd_time_embedding_f32): emb [batch, nf] or
+ * [batch, 2nf].                                                                                              */
+int csd_time_features_f32(const float* labels, int batch, int nf, int embedding_type, const float* fourier_w, float* emb,
+                          csd_stream_t stream);
+
+/* Adjoint of csd_dsm_loss_f32: dscore[b,i] = grad_losses[b] * 2*w[b]*a[b] * (a[b]*score[b,i] + c[b]*z[b,i]).   */
+int csd_dsm_loss_bwd_f32(const float* score, const float* z, const float* a, const float* c, const float* w,
+                         const float* grad_losses, float* dscore, int batch, int64_t per_sample, csd_stream_t stream);
+
 
 #ifdef __cplusplus
 }
