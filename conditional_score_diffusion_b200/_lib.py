@@ -145,7 +145,7 @@ _PROTOTYPES = {
     "csd_zero_stuff_nhwc_bf16": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     "csd_nchw_grad_to_nhwc_bf16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                                            c_int, c_int, c_void_p]),
-    "csd_bias_temb_grad_f32": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "csd_bias_temb_grad_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "csd_sgemm_small_f32": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_int,
                                     c_float, c_void_p, c_int, c_void_p, c_void_p]),
     "csd_silu_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),

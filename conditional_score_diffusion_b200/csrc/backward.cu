@@ -343,13 +343,13 @@ nchw_grad_to_nhwc_kernel(const float* __restrict__ s0, int c0, const float* __re
 
 // ---- bias / time-embedding projection gradients from per-(image, channel) sums of the output gradient -----------
 __global__ void __launch_bounds__(128)
-bias_temb_grad_kernel(const float* __restrict__ sums, int batch, int c, float scale, float* dbias0, float* dbias1,
-                      float* dtproj, int tpitch) {
+bias_temb_grad_kernel(const float* __restrict__ sums, int sums_c, int batch, int c, float scale, float* dbias0,
+                      float* dbias1, float* dtproj, int tpitch) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   float acc = 0.f;
   for (int b = 0; b < batch; ++b) {
-    const float v = sums[((long long)b * c + ch) * 2] * scale;
+    const float v = sums[((long long)b * sums_c + ch) * 2] * scale;
     acc += v;
     if (dtproj != nullptr) dtproj[(long long)b * tpitch + ch] += v;
   }
@@ -582,12 +582,12 @@ int csd_nchw_grad_to_nhwc_bf16(const float* g0, int c0, const float* row_scale0,
   return CSD_OK;
 }
 
-int csd_bias_temb_grad_f32(const float* chan_sums, int batch, int c, float scale, float* dbias0, float* dbias1,
-                           float* dtproj, int tproj_pitch, csd_stream_t stream) {
+int csd_bias_temb_grad_f32(const float* chan_sums, int sums_c, int batch, int c, float scale, float* dbias0,
+                           float* dbias1, float* dtproj, int tproj_pitch, csd_stream_t stream) {
   using namespace csd;
-  CSD_REQUIRE(chan_sums && batch >= 1 && c >= 1, "bias_temb_grad: bad arguments");
-  bias_temb_grad_kernel<<<ceil_div(c, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(chan_sums, batch, c, scale, dbias0,
-                                                                                      dbias1, dtproj, tproj_pitch);
+  CSD_REQUIRE(chan_sums && batch >= 1 && c >= 1 && sums_c >= c, "bias_temb_grad: bad arguments");
+  bias_temb_grad_kernel<<<ceil_div(c, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(chan_sums, sums_c, batch, c, scale,
+                                                                                      dbias0, dbias1, dtproj, tproj_pitch);
   CSD_LAUNCH_CHECK("bias_temb_grad_kernel");
   return CSD_OK;
 }

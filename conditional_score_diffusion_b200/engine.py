@@ -67,12 +67,57 @@ def _groups(c):
     return min(c // 4, 32)
 
 
+class WSrc:
+    """Where one block of a packed weight comes from: a live parameter (so the pack can be refreshed in place after
+    an optimizer step) and where its gradient goes. kind: 'conv' = nn.Conv2d weight [Cout, Cin, kh, kw] (optionally a
+    slice [ci_off, ci_off + ci_cnt) of its input channels), 'nin' = NIN.W [in, out] (models/layers.py:555-564) used as
+    a 1x1 conv, 'eye' = identity (a residual carried as a K segment; no parameter)."""
+
+    __slots__ = ("param", "kind", "ci_off", "ci_cnt")
+
+    def __init__(self, param, kind="conv", ci_off=0, ci_cnt=None):
+        self.param, self.kind, self.ci_off, self.ci_cnt = param, kind, ci_off, ci_cnt
+
+    def weight(self, device):
+        """[Cout, Cin_slice, kh, kw] view of the live parameter."""
+        if self.kind == "eye":
+            c = self.param
+            return torch.eye(c, device=device, dtype=torch.float32).view(c, c, 1, 1)
+        w = self.param.detach()
+        if self.kind == "nin":
+            w = w.t().reshape(w.shape[1], w.shape[0], 1, 1)
+        if self.ci_cnt is not None:
+            w = w[:, self.ci_off:self.ci_off + self.ci_cnt]
+        return w
+
+
+def _as_segments(weights):
+    """Accept the older call form (a list of weight tensors / parameters) as well as lists of WSrc stacks."""
+    segs = []
+    for w in weights:
+        if isinstance(w, WSrc):
+            segs.append([w])
+        elif isinstance(w, (list, tuple)):
+            segs.append(list(w))
+        else:
+            segs.append([WSrc(w)])
+    return segs
+
+
 class PackedConv:
-    """bf16 K-major weights [n_pad, k_total] + fp32 bias [n_pad + 16] for csd_conv_gemm."""
+    """bf16 K-major weights [n_pad, k_total] + fp32 bias [n_pad + 16] for csd_conv_gemm.
+
+    segments: one entry per K segment; an entry is a WSrc or a list of WSrc stacked along the output channels (the
+    attention q|k projection). bias: a parameter / tensor, or a list of (parameter, co_off) that are summed into the
+    bias vector (Conv_1.bias + Conv_2.bias when the skip convolution rides as a K segment). The device buffers are
+    persistent: refresh() re-packs them in place from the live parameters, so recorded launch lists stay valid
+    across optimizer steps."""
 
     def __init__(self, weights, bias, device):
-        # weights: list of [Cout, Cin_i, kh, kw] tensors concatenated along K (segments)
-        cout = weights[0].shape[0]
+        self.segs = _as_segments(weights)
+        self.device = device
+        w0 = [s.weight(device) for s in self.segs[0]]
+        cout = sum(w.shape[0] for w in w0)
         self.cout = cout
         self.n_store = K.ceil_to(cout, 8)
         n16 = K.ceil_to(cout, 16)
@@ -84,12 +129,67 @@ class PackedConv:
                 self.n_tile = 256
         n_tiles = math.ceil(self.n_store / self.n_tile)
         self.n_pad = n_tiles * self.n_tile
-        parts = [K.pack_conv_weight(w.to(device), n_pad=self.n_pad) for w in weights]
-        self.wt = torch.cat(parts, dim=1).contiguous() if len(parts) > 1 else parts[0]
+        if bias is None:
+            self.bias_srcs = []
+        elif isinstance(bias, (list, tuple)):
+            self.bias_srcs = [(b, off) for b, off in bias]
+        else:
+            self.bias_srcs = [(bias, 0)]
+        self.wt = None
         self.bias = torch.zeros(self.n_pad + 16, device=device, dtype=torch.float32)
-        if bias is not None:
-            self.bias[:cout] = bias.detach().to(device=device, dtype=torch.float32)
         self.identity_skip = False
+        self._dgrads = {}
+        self.refresh()
+
+    def seg_weight(self, i):
+        ws = [s.weight(self.device).to(self.device) for s in self.segs[i]]
+        return ws[0] if len(ws) == 1 else torch.cat(ws, 0)
+
+    def refresh(self):
+        parts = [K.pack_conv_weight(self.seg_weight(i), n_pad=self.n_pad) for i in range(len(self.segs))]
+        wt = torch.cat(parts, dim=1) if len(parts) > 1 else parts[0]
+        if self.wt is None:
+            self.wt = wt.contiguous()
+        else:
+            self.wt.copy_(wt)
+        if self.bias_srcs:
+            self.bias.zero_()
+            for b, off in self.bias_srcs:
+                self.bias[off:off + b.shape[0]] += b.detach().to(device=self.device, dtype=torch.float32)
+        for d in self._dgrads.values():
+            d.refresh()
+
+    def dgrad(self, i, scale=1.0):
+        """Packed weights of the data gradient of segment i: [Cin_i, Cout, kh, kw] = scale * W_i flipped in (ky, kx)
+        and transposed in (co, ci), so that d a_i = conv(d out, this) with the same 'same' padding."""
+        key = (i, float(scale))
+        if key not in self._dgrads:
+            self._dgrads[key] = DgradPack(self, i, scale)
+        return self._dgrads[key]
+
+
+class DgradPack:
+    def __init__(self, pc, i, scale):
+        self.pc, self.i, self.scale = pc, i, scale
+        self.wt = None
+        w = pc.seg_weight(i)
+        self.cout = w.shape[1]                     # output channels of the dgrad = input channels of the segment
+        self.n_store = K.ceil_to(self.cout, 8)
+        n16 = K.ceil_to(self.cout, 16)
+        self.n_tile = n16 if n16 <= 256 else K.ceil_to((n16 + 1) // 2, 16)
+        if self.n_tile * 2 > 512 and n16 > 256:
+            self.n_tile = 256
+        self.n_pad = math.ceil(self.n_store / self.n_tile) * self.n_tile
+        self.refresh()
+
+    def refresh(self):
+        w = self.pc.seg_weight(self.i).to(torch.float32)
+        wd = (w.flip(2, 3).transpose(0, 1) * self.scale).contiguous()
+        wt = K.pack_conv_weight(wd, n_pad=self.n_pad)
+        if self.wt is None:
+            self.wt = wt
+        else:
+            self.wt.copy_(wt)
 
 
 def nin_as_conv(W):
@@ -211,6 +311,19 @@ class BlockOps:
             self.rec.add(K.gn_finalize_partials, partials, sums, b, tiles_img, pc.cout)
             self.pool.put(partials)
         return Act(out, pc.cout, sums)
+
+    def time_embedding(self, labels, nf, embedding_type, fourier_w, lin0, lin1, P, mods=None):
+        """temb MLP (fused kernel) + every block's Dense_0 projection in one launch. Returns (tproj, pitch)."""
+        (w0, b0), (w1, b1) = lin0, lin1
+        batch = labels.shape[0]
+        act_temb = torch.empty(batch, w1.shape[0], device=self.device, dtype=torch.float32)
+        self.rec.add(K.time_embedding, labels, nf, embedding_type, fourier_w, w0, b0, w1, b1, act_temb)
+        if "dense_w" not in P:
+            return None, 0
+        tpitch = P["dense_total"]
+        tproj = torch.empty(batch, tpitch, device=self.device, dtype=torch.float32)
+        self.rec.add(K.dense_rows, act_temb, P["dense_w"], P["dense_b"], tproj)
+        return tproj, tpitch
 
     def fir(self, a, mode, taps, add=None):
         b, h, w, p = a.shape
@@ -335,11 +448,16 @@ class NetEngine:
         self.device = None
         self.packed = None
         self.param_version = None
+        self.param_structure = None
         self.plans = {}
+        self.train_plans = {}
 
     # -- weights ---------------------------------------------------------------------------------
     def _version(self):
         return tuple((id(p), p._version, p.device) for p in self.net.parameters())
+
+    def _structure(self):
+        return tuple((id(p), p.data_ptr(), p.device) for p in self.net.parameters())
 
     def ensure_packed(self, device):
         v = self._version()
@@ -347,10 +465,48 @@ class NetEngine:
             return
         if device.type != "cuda":
             raise CsdError("the score network runs on CUDA only (libcsd_b200 has no CPU path)")
+        st = self._structure()
+        if (self.packed is not None and self.device == device and self.param_structure == st
+                and all(p.device == device for p in self.net.parameters())):
+            # same parameter tensors, new values (an optimizer step): re-pack in place, recorded plans stay valid
+            self._refresh()
+            self.param_version = v
+            return
         self.device = device
         self.packed = self._pack(device)
         self.param_version = v
+        self.param_structure = st
         self.plans = {}
+        self.train_plans = {}
+
+    def _refresh(self):
+        seen = set()
+
+        def visit(obj):
+            if id(obj) in seen:
+                return
+            seen.add(id(obj))
+            if isinstance(obj, PackedConv):
+                obj.refresh()
+            elif isinstance(obj, dict):
+                if "wv_img" in obj:
+                    self._refresh_attn(obj)
+                for v in list(obj.values()):
+                    visit(v)
+            elif isinstance(obj, (list, tuple)):
+                for v in obj:
+                    visit(v)
+
+        visit(self.packed["mods"])
+        if "dense_mods" in self.packed:
+            self._refresh_dense(self.packed)
+
+    @staticmethod
+    def _refresh_dense(out):
+        total = out["dense_total"] - 512
+        dev = out["dense_w"].device
+        out["dense_w"][:total] = torch.cat([d.weight.detach().to(dev, torch.float32) for d in out["dense_mods"]], 0)
+        out["dense_b"][:total] = torch.cat([d.bias.detach().to(dev, torch.float32) for d in out["dense_mods"]], 0)
 
     def _pack_resblock(self, m, device, dense_w, dense_b):
         from .models import layers, layerspp
@@ -358,27 +514,29 @@ class NetEngine:
         pk["gn0_w"], pk["gn0_b"] = _gn_params(m.GroupNorm_0, device)
         pk["gn1_w"], pk["gn1_b"] = _gn_params(m.GroupNorm_1, device)
         pk["groups0"], pk["groups1"] = m.GroupNorm_0.num_groups, m.GroupNorm_1.num_groups
-        pk["conv0"] = PackedConv([m.Conv_0.weight.detach()], m.Conv_0.bias, device)
-        pk["conv0_w"], pk["conv0_b"] = m.Conv_0.weight.detach(), m.Conv_0.bias
+        pk["mod"] = m
+        pk["conv0"] = PackedConv([WSrc(m.Conv_0.weight)], m.Conv_0.bias, device)
+        pk["conv0_w"], pk["conv0_b"] = m.Conv_0.weight, m.Conv_0.bias
         if hasattr(m, "Dense_0"):
-            pk["temb_off"] = sum(w.shape[0] for w in dense_w)
-            dense_w.append(m.Dense_0.weight.detach().to(device=device, dtype=torch.float32))
-            dense_b.append(m.Dense_0.bias.detach().to(device=device, dtype=torch.float32))
+            pk["temb_off"] = sum(d.weight.shape[0] for d in dense_w)
+            dense_w.append(m.Dense_0)
+            dense_b.append(m.Dense_0)
         else:
             pk["temb_off"] = None
-        skip_w, skip_b = None, None
+        skip_w, skip_b, skip_kind = None, None, "conv"
         if isinstance(m, layerspp.ResnetBlockBigGANpp):
             if hasattr(m, "Conv_2"):
-                skip_w, skip_b = m.Conv_2.weight.detach(), m.Conv_2.bias.detach()
+                skip_w, skip_b = m.Conv_2.weight, m.Conv_2.bias
         else:
             if hasattr(m, "NIN_0"):
-                skip_w, skip_b = nin_as_conv(m.NIN_0.W), m.NIN_0.b.detach()
+                skip_w, skip_b, skip_kind = m.NIN_0.W, m.NIN_0.b, "nin"
             elif hasattr(m, "Conv_2"):
                 raise CsdError("conv_shortcut=True DDPM ResNet blocks are not supported by the engine")
         pk["has_skip_conv"] = skip_w is not None
-        pk["conv1_w"] = m.Conv_1.weight.detach()
-        pk["conv1_b"] = m.Conv_1.bias.detach()
-        pk["skip_w"], pk["skip_b"] = skip_w, skip_b
+        pk["conv1_w"] = m.Conv_1.weight
+        pk["conv1_b"] = m.Conv_1.bias
+        pk["skip_w"], pk["skip_b"], pk["skip_kind"] = skip_w, skip_b, skip_kind
+        pk["skip_cin"] = None if skip_w is None else (skip_w.shape[0] if skip_kind == "nin" else skip_w.shape[1])
         pk["in_ch"], pk["out_ch"] = m.Conv_0.weight.shape[1], m.Conv_0.weight.shape[0]
         return pk
 
@@ -392,7 +550,7 @@ class NetEngine:
         if key not in pk:
             ws, off = [], 0
             for c in split:
-                ws.append(pk["conv0_w"][:, off:off + c])
+                ws.append(WSrc(pk["conv0_w"], "conv", off, c))
                 off += c
             assert off == pk["conv0_w"].shape[1]
             pk[key] = PackedConv(ws, pk["conv0_b"], device)
@@ -409,37 +567,43 @@ class NetEngine:
         if identity_skip and not pk["has_skip_conv"]:
             c = pk["out_ch"]
             assert split == [c] or tuple(split) == (c,)
-            eye = torch.eye(c, device=pk["conv1_w"].device, dtype=pk["conv1_w"].dtype).view(c, c, 1, 1)
-            pc = PackedConv([pk["conv1_w"], eye], pk["conv1_b"], device)
+            pc = PackedConv([WSrc(pk["conv1_w"]), WSrc(c, "eye")], pk["conv1_b"], device)
             pc.identity_skip = True
             pk[key] = pc
             return pc
         if pk["has_skip_conv"]:
-            ws = [pk["conv1_w"]]
+            ws = [WSrc(pk["conv1_w"])]
             off = 0
             for c in split:
-                ws.append(pk["skip_w"][:, off:off + c])
+                ws.append(WSrc(pk["skip_w"], pk["skip_kind"], off, c))
                 off += c
-            assert off == pk["skip_w"].shape[1], (off, pk["skip_w"].shape)
-            pc = PackedConv(ws, pk["conv1_b"] + pk["skip_b"], device)
+            assert off == pk["skip_cin"], (off, pk["skip_cin"])
+            pc = PackedConv(ws, [(pk["conv1_b"], 0), (pk["skip_b"], 0)], device)
         else:
-            pc = PackedConv([pk["conv1_w"]], pk["conv1_b"], device)
+            pc = PackedConv([WSrc(pk["conv1_w"])], pk["conv1_b"], device)
         pk[key] = pc
         return pc
 
     def _pack_attn(self, m, device):
         c = m.NIN_0.W.shape[0]
-        pk = {}
+        pk = {"mod": m}
         pk["gn_w"], pk["gn_b"] = _gn_params(m.GroupNorm_0, device)
         pk["groups"] = m.GroupNorm_0.num_groups
-        wqk = torch.cat([nin_as_conv(m.NIN_0.W), nin_as_conv(m.NIN_1.W)], dim=0)
-        pk["qk"] = PackedConv([wqk], torch.cat([m.NIN_0.b.detach(), m.NIN_1.b.detach()]), device)
+        pk["qk"] = PackedConv([[WSrc(m.NIN_0.W, "nin"), WSrc(m.NIN_1.W, "nin")]], [(m.NIN_0.b, 0), (m.NIN_1.b, c)], device)
         # A-operand "image" of the V^T GEMM: rows = output channel, K = input channel
-        pk["wv_img"] = m.NIN_2.W.detach().t().to(device=device, dtype=BF16).contiguous().view(1, 1, c, c)
+        pk["wv_img"] = torch.empty(1, 1, c, c, device=device, dtype=BF16)
         pk["bv"] = torch.zeros(c + 16, device=device, dtype=torch.float32)
-        pk["bv"][:c] = m.NIN_2.b.detach().to(device)
-        pk["proj"] = PackedConv([nin_as_conv(m.NIN_3.W)], m.NIN_3.b.detach(), device)
+        pk["v"] = PackedConv([WSrc(m.NIN_2.W, "nin")], m.NIN_2.b, device)   # training backward (dgrad of V)
+        pk["proj"] = PackedConv([WSrc(m.NIN_3.W, "nin")], m.NIN_3.b, device)
+        self._refresh_attn(pk)
         return pk
+
+    @staticmethod
+    def _refresh_attn(pk):
+        m = pk["mod"]
+        c = m.NIN_2.W.shape[0]
+        pk["wv_img"].copy_(m.NIN_2.W.detach().t().reshape(1, 1, c, c))
+        pk["bv"][:c] = m.NIN_2.b.detach()
 
     def _pack(self, device):
         from .models import layers, layerspp
@@ -453,18 +617,18 @@ class NetEngine:
             elif isinstance(m, (layerspp.AttnBlockpp, layers.AttnBlock)):
                 packed[i] = self._pack_attn(m, device)
             elif isinstance(m, (layers.Upsample, layers.Downsample)):
-                packed[i] = PackedConv([m.Conv_0.weight.detach()], m.Conv_0.bias, device) if m.with_conv else None
+                packed[i] = PackedConv([WSrc(m.Conv_0.weight)], m.Conv_0.bias, device) if m.with_conv else None
             elif isinstance(m, torch.nn.Conv2d):
-                packed[i] = PackedConv([m.weight.detach()], m.bias, device)
+                packed[i] = PackedConv([WSrc(m.weight)], m.bias, device)
             elif isinstance(m, layerspp.Combine):
-                packed[i] = PackedConv([m.Conv_0.weight.detach()], m.Conv_0.bias, device)
+                packed[i] = PackedConv([WSrc(m.Conv_0.weight)], m.Conv_0.bias, device)
             elif isinstance(m, torch.nn.GroupNorm):
                 packed[i] = _gn_params(m, device) + (m.num_groups,)
             elif isinstance(m, (layerspp.Downsample, layerspp.Upsample)):
                 if hasattr(m, "Conv2d_0"):
-                    packed[i] = PackedConv([m.Conv2d_0.weight.detach()], m.Conv2d_0.bias, device)
+                    packed[i] = PackedConv([WSrc(m.Conv2d_0.weight)], m.Conv2d_0.bias, device)
                 elif hasattr(m, "Conv_0"):
-                    packed[i] = PackedConv([m.Conv_0.weight.detach()], m.Conv_0.bias, device)
+                    packed[i] = PackedConv([WSrc(m.Conv_0.weight)], m.Conv_0.bias, device)
             elif isinstance(m, torch.nn.Linear):
                 packed[i] = (m.weight.detach().to(device=device, dtype=torch.float32).contiguous(),
                              m.bias.detach().to(device=device, dtype=torch.float32).contiguous())
@@ -472,13 +636,13 @@ class NetEngine:
                 packed[i] = m.W.detach().to(device=device, dtype=torch.float32).contiguous()
         out = {"mods": packed}
         if dense_w:
-            total = sum(w.shape[0] for w in dense_w)
+            total = sum(d.weight.shape[0] for d in dense_w)
             pad = 512  # epilogue reads a full n_tile of projection columns past the block's offset
-            wcat = torch.zeros(total + pad, dense_w[0].shape[1], device=device, dtype=torch.float32)
-            bcat = torch.zeros(total + pad, device=device, dtype=torch.float32)
-            wcat[:total] = torch.cat(dense_w, 0)
-            bcat[:total] = torch.cat(dense_b, 0)
-            out["dense_w"], out["dense_b"], out["dense_total"] = wcat, bcat, total + pad
+            out["dense_w"] = torch.zeros(total + pad, dense_w[0].weight.shape[1], device=device, dtype=torch.float32)
+            out["dense_b"] = torch.zeros(total + pad, device=device, dtype=torch.float32)
+            out["dense_total"] = total + pad
+            out["dense_mods"] = list(dense_w)
+            self._refresh_dense(out)
         return out
 
     # -- plan ------------------------------------------------------------------------------------
@@ -487,6 +651,14 @@ class NetEngine:
         if key not in self.plans:
             self.plans[key] = NetPlan(self, batch, h, w, c0, c1)
         return self.plans[key]
+
+    def train_plan(self, batch, h, w, c0, c1, want_params=True, want_input=False):
+        """Forward + backward plan (engine_train.TrainPlan) for differentiating the network."""
+        from .engine_train import TrainPlan
+        key = (batch, h, w, c0, c1, want_params, want_input)
+        if key not in self.train_plans:
+            self.train_plans[key] = TrainPlan(self, batch, h, w, c0, c1, want_params, want_input)
+        return self.train_plans[key]
 
 
 class NetPlan:
@@ -497,9 +669,9 @@ class NetPlan:
         self.eng = eng
         self.batch, self.h, self.w = batch, h, w
         self.rec = Recorder()
-        self.pool = BufferPool(dev)
+        self.pool = self._make_pool(dev)
         self.stats = torch.zeros(48 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
-        ops = BlockOps(dev, self.pool, self.rec, self.stats)
+        ops = self.ops = self._make_ops(dev)
 
         # static inputs / outputs
         self.in0 = torch.empty(batch, c0, h, w, device=dev, dtype=torch.float32)
@@ -512,6 +684,7 @@ class NetPlan:
         self.rec.add(self.stats.zero_)
         build = {"ncsnpp": self._build_ncsnpp, "ddpm": self._build_ddpm}[getattr(net, "arch", "ncsnpp")]
         final = build(ops, c0, c1)
+        self.final_act = final
         # ---- output: NHWC bf16 -> NCHW fp32, optional per-sample 1/sigma. A network that returns as many channels
         #      as it takes is split back into the (x, y) groups it was fed; otherwise (SR3) there is one output ----
         out_c = net.out_channels
@@ -524,19 +697,17 @@ class NetPlan:
         self.warm = 0
         self.use_graph = os.environ.get("CSD_NO_GRAPH", "0") != "1"
 
+    def _make_pool(self, dev):
+        return BufferPool(dev)
+
+    def _make_ops(self, dev):
+        return BlockOps(dev, self.pool, self.rec, self.stats)
+
     def _time_embedding(self, pk, m_idx, fourier_w):
         """temb MLP + every block's Dense_0 projection in two launches. Returns (tproj, pitch)."""
-        net, dev, P, rec = self.eng.net, self.eng.device, self.eng.packed, self.rec
-        nf = net.nf
-        (w0, b0), (w1, b1) = pk[m_idx], pk[m_idx + 1]
-        act_temb = torch.empty(self.batch, 4 * nf, device=dev, dtype=torch.float32)
-        rec.add(K.time_embedding, self.labels, nf, net.embedding_type, fourier_w, w0, b0, w1, b1, act_temb)
-        if "dense_w" not in P:
-            return None, 0
-        tpitch = P["dense_total"]
-        tproj = torch.empty(self.batch, tpitch, device=dev, dtype=torch.float32)
-        rec.add(K.dense_rows, act_temb, P["dense_w"], P["dense_b"], tproj)
-        return tproj, tpitch
+        net, P = self.eng.net, self.eng.packed
+        return self.ops.time_embedding(self.labels, net.nf, net.embedding_type, fourier_w, pk[m_idx], pk[m_idx + 1], P,
+                                       (net.all_modules[m_idx], net.all_modules[m_idx + 1]))
 
     def _input(self, c0, c1):
         """cat(x, y) + `2x - 1` + NCHW fp32 -> NHWC bf16 in one kernel."""
@@ -547,6 +718,7 @@ class NetPlan:
             self.rec.add(K.nchw_to_nhwc, self.in0, self.in1, xin.t, 1.0, 0.0)
         else:
             self.rec.add(K.nchw_to_nhwc, self.in0, self.in1, xin.t, 2.0, -1.0)  # x = 2x - 1
+        self.xin_act = xin
         return xin
 
     def _build_ddpm(self, ops, c0, c1):
@@ -670,17 +842,11 @@ class NetPlan:
         tproj = None
         tpitch = 0
         if net.conditional:
-            (w0, b0), (w1, b1) = pk[m_idx], pk[m_idx + 1]
+            tproj, tpitch = self._time_embedding(pk, m_idx, fourier_w)
             m_idx += 2
-            act_temb = torch.empty(batch, 4 * nf, device=dev, dtype=torch.float32)
-            rec.add(K.time_embedding, self.labels, nf, net.embedding_type, fourier_w, w0, b0, w1, b1, act_temb)
-            if "dense_w" in P:
-                tpitch = P["dense_total"]
-                tproj = torch.empty(batch, tpitch, device=dev, dtype=torch.float32)
-                rec.add(K.dense_rows, act_temb, P["dense_w"], P["dense_b"], tproj)
         # ---- input ----
         cpad = K.ceil_to(channels, 8)
-        xin = Act(torch.empty(batch, h, w, cpad, device=dev, dtype=BF16), channels)
+        xin = self.xin_act = Act(torch.empty(batch, h, w, cpad, device=dev, dtype=BF16), channels)
         if net.centered:
             rec.add(K.nchw_to_nhwc, self.in0, self.in1, xin.t, 1.0, 0.0)
         else:

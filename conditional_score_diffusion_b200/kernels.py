@@ -472,7 +472,7 @@ def nchw_grad_to_nhwc(g0, c0, rs0, g1, c1, rs1, out):
 
 
 def bias_temb_grad(chan_sums, c, scale, dbias0=None, dbias1=None, dtproj=None, tproj_pitch=0):
-    check(_lib.lib().csd_bias_temb_grad_f32(_ptr(chan_sums), chan_sums.shape[0], c, float(scale), _ptr(dbias0),
+    check(_lib.lib().csd_bias_temb_grad_f32(_ptr(chan_sums), chan_sums.shape[1], chan_sums.shape[0], c, float(scale), _ptr(dbias0),
                                             _ptr(dbias1), _ptr(dtproj), tproj_pitch, _stream()))
 
 

@@ -2,8 +2,8 @@
 
 The reference's networks subclass pl.LightningModule (models/ncsnpp.py:23,40; models/ddpm.py:24,81) and run
 eager ATen ops in forward(). Here a network is a parameter container with the reference's module order and names;
-its arithmetic is the planned CUDA launch list of `engine.NetEngine`. Inference only: calling forward with autograd
-enabled on parameters that require grad raises (there is no silent PyTorch fallback).
+its arithmetic is the planned CUDA launch list of `engine.NetEngine`; with autograd enabled the network is one
+autograd node whose backward is the planned reverse launch list of `engine_train.TrainPlan` (no PyTorch fallback).
 """
 import torch
 import torch.nn as nn
@@ -27,31 +27,56 @@ except Exception:  # pragma: no cover - Lightning is not installed in the build 
             pass
 
 
+class _NetFunction(torch.autograd.Function):
+    """The whole score network as ONE autograd node: forward = the training plan's launch list, backward = its
+    reverse launch list (engine_train.TrainPlan). Parameters are passed as inputs so `loss.backward()` fills their
+    `.grad` exactly as it does for the reference's eager module (losses.py:345-407)."""
+
+    @staticmethod
+    def forward(ctx, net, plan, x0, x1, time_cond, scale0, scale1, *params):
+        net._load_inputs(plan, x0, x1, time_cond, scale0, scale1)
+        plan.launch()
+        ctx.plan = plan
+        ctx.has_x1 = x1 is not None
+        ctx.n_params = len(params)
+        plan.forward_serial = getattr(plan, "forward_serial", 0) + 1
+        ctx.serial = plan.forward_serial
+        return tuple(o.clone() for o in plan.outputs())
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        plan = ctx.plan
+        if ctx.serial != plan.forward_serial:
+            raise RuntimeError("the score network was evaluated again before backward(): its stored activations were "
+                               "overwritten (one live autograd graph per network and batch shape)")
+        for buf, g in zip(plan.gouts, gouts):
+            if g is None:
+                buf.zero_()
+            else:
+                buf.copy_(g)
+        plan.run_backward()
+        gx0 = gx1 = None
+        if plan.want_input:
+            gx0 = plan.gin[0].clone()
+            if ctx.has_x1:
+                gx1 = plan.gin[1].clone()
+        pg = plan.param_grads() if plan.want_params else [None] * ctx.n_params
+        return (None, None, gx0, gx1, None, None, None) + tuple(pg)
+
+
 class EngineNet(_Base):
     """forward() plumbing shared by the engine-backed networks: copy inputs into the plan's static buffers, launch
-    (CUDA graph after the first call), clone the outputs."""
+    (CUDA graph after the first call), clone the outputs. With autograd enabled the call goes through
+    `_NetFunction` (planned backward pass); otherwise through the inference plan."""
 
-    def _check_inference(self, *tensors):
-        if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors if torch.is_tensor(t))
-                                        or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(
-                "score-network backward (training / likelihood divergence) is not implemented by the B200 engine yet; "
-                "call the network under torch.no_grad(). No PyTorch fallback is provided on purpose.")
-        if self.training and self.config.model.dropout > 0:
-            raise NotImplementedError("dropout (train mode) is not implemented by the B200 engine; use .eval()")
+    def _needs_grad(self, *tensors):
+        if not torch.is_grad_enabled():
+            return False, False
+        want_in = any(t.requires_grad for t in tensors if torch.is_tensor(t))
+        want_p = any(p.requires_grad for p in self.parameters())
+        return want_p, want_in
 
-    def _run(self, x0, x1, time_cond, scale0=None, scale1=None, clone=True):
-        """x0 [B,c0,H,W] (+ optional x1 [B,c1,H,W], channel-concatenated after x0), time_cond [B]."""
-        self._check_inference(x0, x1, time_cond)
-        if x0.device.type != "cuda":
-            raise RuntimeError("the score network runs on CUDA tensors only (libcsd_b200 has no CPU path)")
-        eng = self._engine
-        eng.ensure_packed(x0.device)
-        b, c0, h, w = x0.shape
-        c1 = x1.shape[1] if x1 is not None else 0
-        if c0 + c1 != self.in_channels:
-            raise ValueError(f"expected {self.in_channels} input channels, got {c0 + c1}")
-        plan = eng.plan(b, h, w, c0, c1)
+    def _load_inputs(self, plan, x0, x1, time_cond, scale0, scale1):
         plan.in0.copy_(x0)
         if x1 is not None:
             plan.in1.copy_(x1)
@@ -65,6 +90,28 @@ class EngineNet(_Base):
                 plan.row_scale1.copy_(scale1)
             else:
                 plan.row_scale1.fill_(1.0)
+
+    def _run(self, x0, x1, time_cond, scale0=None, scale1=None, clone=True):
+        """x0 [B,c0,H,W] (+ optional x1 [B,c1,H,W], channel-concatenated after x0), time_cond [B]."""
+        if x0.device.type != "cuda":
+            raise RuntimeError("the score network runs on CUDA tensors only (libcsd_b200 has no CPU path)")
+        want_p, want_in = self._needs_grad(x0, x1)
+        if self.training and self.config.model.dropout > 0:
+            raise NotImplementedError("dropout (train mode with config.model.dropout > 0) is not implemented by the B200 "
+                                      "engine; set config.model.dropout = 0 or call .eval()")
+        eng = self._engine
+        eng.ensure_packed(x0.device)
+        b, c0, h, w = x0.shape
+        c1 = x1.shape[1] if x1 is not None else 0
+        if c0 + c1 != self.in_channels:
+            raise ValueError(f"expected {self.in_channels} input channels, got {c0 + c1}")
+        if want_p or want_in:
+            plan = eng.train_plan(b, h, w, c0, c1, want_params=want_p, want_input=want_in)
+            params = [p for p in self.parameters()]
+            outs = _NetFunction.apply(self, plan, x0, x1, time_cond, scale0, scale1, *params)
+            return list(outs)
+        plan = eng.plan(b, h, w, c0, c1)
+        self._load_inputs(plan, x0, x1, time_cond, scale0, scale1)
         plan.launch()
         outs = plan.outputs()
         return [o.clone() for o in outs] if clone else outs

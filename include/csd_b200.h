@@ -343,10 +343,11 @@ int csd_nchw_grad_to_nhwc_bf16(const float* g0, int c0, const float* row_scale0,
                                const float* row_scale1, void* out, int c_pad, int batch, int h, int w,
                                csd_stream_t stream);
 
-/* From chan_sums [batch, c, 2] of an output gradient (csd_gn_chan_stats_bf16): dbias0/1[c] += scale * sum_b sums,
- * dtproj[b*tproj_pitch + c] += scale * sums[b, c] (gradient of the `h += Dense_0(act(temb))` add). Any may be NULL. */
-int csd_bias_temb_grad_f32(const float* chan_sums, int batch, int c, float scale, float* dbias0, float* dbias1,
-                           float* dtproj, int tproj_pitch, csd_stream_t stream);
+/* From chan_sums [batch, sums_c, 2] of an output gradient (csd_gn_chan_stats_bf16; sums_c >= c, e.g. the channel
+ * pitch): dbias0/1[ch] += scale * sum_b sums[b, ch], dtproj[b*tproj_pitch + ch] += scale * sums[b, ch] for ch < c
+ * (gradient of the bias and of the `h += Dense_0(act(temb))` add). Any output may be NULL.                      */
+int csd_bias_temb_grad_f32(const float* chan_sums, int sums_c, int batch, int c, float scale, float* dbias0,
+                           float* dbias1, float* dtproj, int tproj_pitch, csd_stream_t stream);
 
 /* Small fp32 GEMM for the time-embedding MLP / Dense_0 projections and their gradients:
  * C = alpha * op(A) op(B) + beta * C + bias[n], op(A)(m,k) = trans_a ? A[k*lda+m] : A[m*lda+k], op(B)(k,n) =

@@ -38,3 +38,15 @@ def cmde_loss(score_fn, sde_x, sde_y, y, x, t, z_x, z_y, reduce_mean=True):
     cat = torch.cat((lx, ly), dim=-1)
     per = cat.mean(dim=-1) if reduce_mean else 0.5 * cat.sum(dim=-1)
     return per.mean()
+
+
+def uncond_loss(score_fn, sde, x, t, z, reduce_mean=True, likelihood_weighting=False):
+    """Unconditional branch (losses.py:207-232)."""
+    std = sde.sigma(t)
+    score = score_fn(x + _bc(std, x) * z, t)
+    if likelihood_weighting:
+        g2 = sde.diffusion(t) ** 2
+        losses = _reduce(torch.square(score + z / _bc(std, x)), reduce_mean) * g2
+    else:
+        losses = _reduce(torch.square(score * _bc(std, x) + z), reduce_mean)
+    return losses.mean()

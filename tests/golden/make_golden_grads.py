@@ -1,0 +1,129 @@
+"""Golden GRADIENTS of the training losses, generated from the UNMODIFIED reference with PyTorch autograd on CPU.
+
+Run in the BUILD container (reference mounted at /root/reference):  python tests/golden/make_golden_grads.py
+Reads the networks (configs + state dicts) already stored in reference_vectors.pt / reference_vectors_ddpm.pt, so the
+fixture written here (tests/golden/reference_grads.pt) only carries the random draws, the loss values and the
+parameter / input gradients (bf16: half the bytes; the parity tolerance is far above one bf16 ulp).
+
+Cases (dropout = 0 so that train mode is deterministic; the reference's RNG draws are replayed and stored):
+  cmde   ncsnpp_paired, two-SDE CMDE loss (losses.py:119-146), reduce_mean=True, likelihood weighting
+  uncond ncsnpp (Fourier embedding, residual input pyramid), losses.py:207-232 without likelihood weighting, plus the
+         input gradient d sum(score * eps) / dx of likelihood.get_div_fn (likelihood.py:26-37)
+  sr3    ddpm_paired_SR3, SR3 loss (losses.py:185-206) with likelihood weighting
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from make_golden import OUT, ConfigDict, install_shims  # noqa: E402
+
+
+def to_config(d):
+    c = ConfigDict()
+    for k, v in d.items():
+        setattr(c, k, to_config(v) if isinstance(v, dict) else v)
+    return c
+
+
+def grads_of(model):
+    return {n: p.grad.detach().to(torch.bfloat16) for n, p in model.named_parameters() if p.grad is not None}
+
+
+def main():
+    install_shims()
+    import losses as ref_losses
+    import sde_lib
+    from models import ddpm, ncsnpp, utils as mutils  # noqa: F401
+    torch.set_num_threads(4)
+    base = torch.load(os.path.join(OUT, "reference_vectors.pt"), weights_only=False)
+    base_ddpm = torch.load(os.path.join(OUT, "reference_vectors_ddpm.pt"), weights_only=False)
+    fx = {}
+    eps = 1e-5
+    hw, B = 16, 2
+    smax = float(np.sqrt(3 * hw * hw))
+    g = torch.Generator().manual_seed(21)
+    xb = torch.rand(B, 3, hw, hw, generator=g)
+    yb = torch.rand(B, 3, hw, hw, generator=g)
+
+    def build(rec, sd, name=None, out_ch=None):
+        cfg = to_config(rec["config"])
+        cfg.model.dropout = 0.0
+        if name is not None:
+            cfg.model.name = name
+            cfg.model.output_channels = out_ch
+        model = mutils.create_model(cfg)
+        model.load_state_dict(sd, strict=True)
+        return model
+
+    # ---- CMDE on ncsnpp_paired ----
+    rec = base["ncsnpp_paired"]
+    model = build(rec, rec["state_dict"])
+    sdes = {"x": sde_lib.cVESDE(sigma_min=5e-3, sigma_max=smax, N=1000),
+            "y": sde_lib.VESDE(sigma_min=5e-3, sigma_max=0.5, N=1000)}
+    fn = ref_losses.get_general_sde_loss_fn(sdes, train=True, conditional=True, reduce_mean=True, continuous=True,
+                                            likelihood_weighting=True, eps=eps)
+    torch.manual_seed(501)
+    loss = fn(model, (yb, xb))
+    loss.backward()
+    torch.manual_seed(501)
+    t = torch.rand(B) * (1 - eps) + eps
+    z_y = torch.randn_like(yb)
+    z_x = torch.randn_like(xb)
+    fx["cmde"] = {"x": xb, "y": yb, "t": t, "z_x": z_x, "z_y": z_y, "loss": loss.detach().clone(),
+                  "grads": grads_of(model), "sigma_max_x": smax, "sigma_max_y": 0.5, "sigma_min": 5e-3, "eps": eps}
+
+    # ---- unconditional on ncsnpp (cifar-like) + input gradient of the Hutchinson estimator ----
+    rec = base["ncsnpp_cifar"]
+    model = build(rec, rec["state_dict"])
+    sde = sde_lib.VESDE(sigma_min=0.01, sigma_max=50, N=1000)
+    fn = ref_losses.get_sde_loss_fn(sde, train=True, reduce_mean=True, continuous=True, likelihood_weighting=False, eps=eps)
+    torch.manual_seed(502)
+    loss = fn(model, xb)
+    loss.backward()
+    torch.manual_seed(502)
+    t = torch.rand(B) * (sde.T - eps) + eps
+    z = torch.randn_like(xb)
+    out = {"x": xb, "t": t, "z": z, "loss": loss.detach().clone(), "grads": grads_of(model), "sigma_min": 0.01,
+           "sigma_max": 50.0, "eps": eps}
+    model.zero_grad()
+    score_fn = mutils.get_score_fn(sde, model, conditional=False, train=False, continuous=True)
+    xs = (xb + 0.3 * torch.randn(xb.shape, generator=g)).requires_grad_(True)
+    ts = torch.tensor([0.4, 0.9])
+    probe = torch.randint(0, 2, xb.shape, generator=g).float() * 2 - 1
+    with torch.enable_grad():
+        s = score_fn(xs, ts)
+        gx = torch.autograd.grad(torch.sum(s * probe), xs)[0]
+    out.update(div_x=xs.detach().clone(), div_t=ts, div_eps=probe, div_score=s.detach().clone(), div_grad=gx.clone())
+    fx["uncond"] = out
+
+    # ---- SR3 on ddpm_paired_SR3 ----
+    rec = base_ddpm["ddpm_paired"]
+    sd_paired = {k: v.float() for k, v in rec["state_dict_bf16"].items()}
+    last = max(int(k.split(".")[1]) for k in sd_paired)
+    sd = {k: (v[:3] if k.startswith(f"all_modules.{last}.") else v) for k, v in sd_paired.items()}
+    model = build(base_ddpm["ddpm_paired_SR3"], sd)
+    sde = sde_lib.cVESDE(sigma_min=5e-3, sigma_max=smax, N=1000)
+    fn = ref_losses.get_general_sde_loss_fn(sde, train=True, conditional=True, reduce_mean=True, continuous=True,
+                                            likelihood_weighting=True, eps=eps)
+    torch.manual_seed(503)
+    loss = fn(model, (yb, xb))
+    loss.backward()
+    torch.manual_seed(503)
+    t = torch.rand(B) * (sde.T - eps) + eps
+    z = torch.randn_like(xb)
+    fx["sr3"] = {"x": xb, "y": yb, "t": t, "z": z, "loss": loss.detach().clone(), "grads": grads_of(model),
+                 "sigma_max": smax, "sigma_min": 5e-3, "eps": eps}
+
+    path = os.path.join(OUT, "reference_grads.pt")
+    torch.save(fx, path)
+    print("wrote", path, f"{os.path.getsize(path) / 1e6:.2f} MB")
+    for k, v in fx.items():
+        gn = sum(float(gg.float().pow(2).sum()) for gg in v["grads"].values()) ** 0.5
+        print(k, "loss", float(v["loss"]), "params with grad", len(v["grads"]), "grad norm", gn)
+
+
+if __name__ == "__main__":
+    main()

@@ -84,10 +84,11 @@ def test_forward_scaled_fuses_sigma_division():
     _check(out["y"], f["out_y"] * inv["y"].view(2, 1, 1, 1), "scaled y")
 
 
-def test_training_mode_raises_loudly():
+def test_unsupported_modes_raise_loudly():
     f, m = _model("paired")
-    with pytest.raises(NotImplementedError):
-        m({"x": f["x"].cuda(), "y": f["y"].cuda()}, f["labels"].cuda())  # grad enabled
+    with pytest.raises(NotImplementedError):       # dropout > 0 in train mode is not implemented: no silent skip
+        m.train()({"x": f["x"].cuda(), "y": f["y"].cuda()}, f["labels"].cuda())
+    m.eval()
     with pytest.raises(RuntimeError):
         with torch.no_grad():
             m.cpu()({"x": f["x"], "y": f["y"]}, f["labels"])

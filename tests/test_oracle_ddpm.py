@@ -87,9 +87,11 @@ def test_loss_oracle_matches_reference():
         assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item()), (rm, got.item(), ref.item())
 
 
-def test_training_loss_raises_without_backward():
+def test_training_loss_has_no_cpu_fallback():
+    """The training loss runs on the CUDA path only: CPU tensors raise instead of falling back to eager PyTorch."""
     import pytest
     from conditional_score_diffusion_b200 import losses, sde_lib
+    from conditional_score_diffusion_b200._lib import CsdError
     fn = losses.get_general_sde_loss_fn(sde_lib.cVESDE(5e-3, 27.7, 1000), train=True, conditional=True)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(CsdError):
         fn(None, (torch.zeros(1, 3, 4, 4), torch.zeros(1, 3, 4, 4)))

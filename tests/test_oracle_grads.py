@@ -1,0 +1,93 @@
+"""Pin the oracle's GRADIENTS (autograd through the CPU restatement) against gradients produced by the real reference
+(tests/golden/make_golden_grads.py -> tests/golden/reference_grads.pt). CPU only. The fixture stores gradients in
+bf16, so the bound is 2^-8 of each tensor's max magnitude plus 1e-4 of the largest gradient in the network."""
+import os
+
+import torch
+
+from golden_utils import golden, to_namespace
+from oracle import ddpm as o_ddpm
+from oracle import losses as o_loss
+from oracle import ncsnpp as o_net
+from oracle import sde as o_sde
+from test_oracle_ddpm import ddpm_golden
+
+_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_grads.pt")
+
+
+def grads_golden():
+    return torch.load(_PATH, map_location="cpu", weights_only=False)
+
+
+def _leaf(sd):
+    return {k: v.clone().float().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+
+
+def _check(params, ref, what):
+    gmax = max(v.float().abs().max().item() for v in ref.values())
+    worst = 0.0
+    for k, r in ref.items():
+        g = params[k].grad
+        assert g is not None, f"{what}: no oracle gradient for {k}"
+        r = r.float()
+        tol = 2.0 ** -8 * r.abs().max().item() + 1e-4 * gmax
+        err = (g - r).abs().max().item()
+        worst = max(worst, err / gmax)
+        assert err <= tol, f"{what}: {k} err {err:.3e} tol {tol:.3e}"
+    print(f"[oracle grads] {what}: {len(ref)} tensors, worst err / max grad = {worst:.2e}")
+
+
+def _nodrop(cfg_dict):
+    cfg = to_namespace(cfg_dict)
+    cfg.model.dropout = 0.0
+    return cfg
+
+
+def test_cmde_gradients():
+    f, g = golden()["ncsnpp_paired"], grads_golden()["cmde"]
+    o = o_net.model_options(_nodrop(f["config"]))
+    params = _leaf(f["state_dict"])
+    sx, sy = o_sde.VE(g["sigma_min"], g["sigma_max_x"], 1000), o_sde.VE(g["sigma_min"], g["sigma_max_y"], 1000)
+
+    def score_fn(d, t):     # get_score_fn dict branch (models/utils.py:172-186), both scores
+        out = o_net.forward_paired(params, o, d["x"], d["y"], t * 999)
+        return {"x": out["x"] / sx.sigma(t)[:, None, None, None], "y": out["y"] / sy.sigma(t)[:, None, None, None]}
+
+    loss = o_loss.cmde_loss(score_fn, sx, sy, g["y"], g["x"], g["t"], g["z_x"], g["z_y"], True)
+    assert abs(loss.item() - g["loss"].item()) <= 1e-5 * abs(g["loss"].item())
+    loss.backward()
+    _check(params, g["grads"], "cmde")
+
+
+def test_unconditional_gradients_and_divergence_input_gradient():
+    f, g = golden()["ncsnpp_cifar"], grads_golden()["uncond"]
+    o = o_net.model_options(_nodrop(f["config"]))
+    params = _leaf(f["state_dict"])
+    sde = o_sde.VE(g["sigma_min"], g["sigma_max"], 1000)
+    score_fn = o_sde.score_fn_unconditional(lambda x, l: o_net.forward(params, o, x, l), sde, True, "fourier")
+    loss = o_loss.uncond_loss(score_fn, sde, g["x"], g["t"], g["z"], True, False)
+    assert abs(loss.item() - g["loss"].item()) <= 1e-5 * abs(g["loss"].item())
+    loss.backward()
+    _check(params, g["grads"], "uncond")
+    xs = g["div_x"].clone().requires_grad_(True)
+    s = score_fn(xs, g["div_t"])
+    gx = torch.autograd.grad(torch.sum(s * g["div_eps"]), xs)[0]
+    scale = g["div_grad"].abs().max().item()
+    assert (s - g["div_score"]).abs().max().item() <= 1e-4 * g["div_score"].abs().max().item()
+    assert (gx - g["div_grad"]).abs().max().item() <= 1e-4 * scale
+
+
+def test_sr3_gradients():
+    fx, _, sd3 = ddpm_golden()
+    g = grads_golden()["sr3"]
+    o = o_ddpm.model_options(_nodrop(fx["ddpm_paired_SR3"]["config"]))
+    params = _leaf(sd3)
+    sx = o_sde.VE(g["sigma_min"], g["sigma_max"], 1000)
+
+    def score(d, t):
+        return o_ddpm.forward_paired_sr3(params, o, d["x"], d["y"], t * 999) / sx.sigma(t)[:, None, None, None]
+
+    loss = o_loss.sr3_loss(score, sx, g["y"], g["x"], g["t"], g["z"], True, True)
+    assert abs(loss.item() - g["loss"].item()) <= 1e-5 * abs(g["loss"].item())
+    loss.backward()
+    _check(params, g["grads"], "sr3")
