@@ -142,6 +142,7 @@ _PROTOTYPES = {
                                      c_void_p]),
     "csd_transpose_bf16": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p]),
     "csd_axpy_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]),
+    "csd_dropout_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p, ctypes.c_uint64, c_void_p]),
     "csd_zero_stuff_nhwc_bf16": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     "csd_nchw_grad_to_nhwc_bf16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                                            c_int, c_int, c_void_p]),

@@ -295,6 +295,36 @@ axpy_bf16_kernel(const bf16x8* __restrict__ src, bf16x8* dst, long long nvec, fl
   }
 }
 
+// ---- dropout: out = keep(seed, salt, i) ? x / (1 - p) : 0, mask recomputed from a counter-based hash ------------
+// The same call applied to the gradient is the backward pass (no mask tensor is stored). nn.Dropout in
+// ResnetBlockBigGANpp / ResnetBlockDDPM (models/layerspp.py:266, models/layers.py:664) draws from torch's
+// generator; here the per-step seed is drawn from it too (a device int64), the per-element stream is our own.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+dropout_bf16_kernel(const bf16x8* __restrict__ x, bf16x8* __restrict__ out, long long nvec, float p,
+                    const long long* __restrict__ seed, unsigned long long salt) {
+  const unsigned long long s = mix64((unsigned long long)(*seed) ^ (salt * 0x9E3779B97F4A7C15ULL));
+  const unsigned int thresh = (unsigned int)(p * 65536.f);
+  const float inv_keep = 1.f / (1.f - p);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long r0 = mix64(s + 2ULL * (unsigned long long)i);
+    const unsigned long long r1 = mix64(s + 2ULL * (unsigned long long)i + 1ULL);
+    float f[8];
+    unpack8(x[i], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const unsigned int u = (unsigned int)(((k < 4 ? r0 : r1) >> (16 * (k & 3))) & 0xFFFFu);
+      f[k] = u >= thresh ? f[k] * inv_keep : 0.f;
+    }
+    out[i] = pack8(f);
+  }
+}
+
 // ---- zero stuffing: dst[b, y*s+off, x*s+off, :] = src[b, y, x, :], zero elsewhere --------------------------------
 __global__ void __launch_bounds__(256)
 zero_stuff_kernel(const bf16x8* __restrict__ src, bf16x8* __restrict__ dst, int batch, int h, int w, int dh, int dw,
@@ -555,6 +585,19 @@ int csd_axpy_bf16(const void* src, void* dst, int64_t n, float alpha, int accumu
   axpy_bf16_kernel<<<flat_blocks(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16x8*>(src), static_cast<bf16x8*>(dst), n / 8, alpha, accumulate);
   CSD_LAUNCH_CHECK("axpy_bf16_kernel");
+  return CSD_OK;
+}
+
+int csd_dropout_bf16(const void* x, void* out, int64_t n, float p, const int64_t* seed_dev, uint64_t salt,
+                     csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(x && out && seed_dev && n >= 0 && n % 8 == 0, "dropout: element count must be a multiple of 8");
+  CSD_REQUIRE(p >= 0.f && p < 1.f, "dropout: p = %f out of [0, 1)", (double)p);
+  if (n == 0) return CSD_OK;
+  dropout_bf16_kernel<<<flat_blocks(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16x8*>(x), static_cast<bf16x8*>(out), n / 8, p, reinterpret_cast<const long long*>(seed_dev),
+      (unsigned long long)salt);
+  CSD_LAUNCH_CHECK("dropout_bf16_kernel");
   return CSD_OK;
 }
 

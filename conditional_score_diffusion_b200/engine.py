@@ -325,6 +325,10 @@ class BlockOps:
         self.rec.add(K.dense_rows, act_temb, P["dense_w"], P["dense_b"], tproj)
         return tproj, tpitch
 
+    def dropout(self, a):
+        """Dropout_0 of the ResNet blocks: identity outside training (nn.Dropout in eval mode)."""
+        return a
+
     def fir(self, a, mode, taps, add=None):
         b, h, w, p = a.shape
         oh, ow = {"up": (h * 2, w * 2), "down": (h // 2, w // 2), "prefilter": (h + 1, w + 1)}[mode]
@@ -373,7 +377,7 @@ class BlockOps:
             (cf,) = self.gn_coeffs([h1], pk["gn1_w"], pk["gn1_b"], pk["groups1"])
             first, a1 = (h1, 9, cf), None
         else:
-            a1 = self.group_norm([h1], pk["gn1_w"], pk["gn1_b"], True, pk["groups1"])
+            a1 = self.dropout(self.group_norm([h1], pk["gn1_w"], pk["gn1_b"], True, pk["groups1"]))
             first, cf = (a1, 9), None
         if pk["has_skip_conv"]:
             out = self.conv([first] + [(r, 1) for r in raw], pk["conv1"], scale=scale)
@@ -652,12 +656,12 @@ class NetEngine:
             self.plans[key] = NetPlan(self, batch, h, w, c0, c1)
         return self.plans[key]
 
-    def train_plan(self, batch, h, w, c0, c1, want_params=True, want_input=False):
+    def train_plan(self, batch, h, w, c0, c1, want_params=True, want_input=False, dropout=0.0):
         """Forward + backward plan (engine_train.TrainPlan) for differentiating the network."""
         from .engine_train import TrainPlan
-        key = (batch, h, w, c0, c1, want_params, want_input)
+        key = (batch, h, w, c0, c1, want_params, want_input, float(dropout))
         if key not in self.train_plans:
-            self.train_plans[key] = TrainPlan(self, batch, h, w, c0, c1, want_params, want_input)
+            self.train_plans[key] = TrainPlan(self, batch, h, w, c0, c1, want_params, want_input, float(dropout))
         return self.train_plans[key]
 
 

@@ -36,9 +36,19 @@ class NoRecyclePool(BufferPool):
 class TrainOps(BlockOps):
     """BlockOps that keeps every activation and records a tape of (kind, info) for the backward builder."""
 
-    def __init__(self, device, pool, rec, stats_arena):
+    def __init__(self, device, pool, rec, stats_arena, dropout_p=0.0, seed_dev=None):
         super().__init__(device, pool, rec, stats_arena)
         self.tape = []
+        self.dropout_p, self.seed_dev, self.n_dropout = dropout_p, seed_dev, 0
+
+    def dropout(self, a):
+        if self.dropout_p <= 0.0:
+            return a
+        self.n_dropout += 1
+        salt = self.n_dropout
+        self.rec.add(K.dropout, a.t, a.t, self.dropout_p, self.seed_dev, salt)     # in place: only the dropped tensor is used
+        self.tape.append(("dropout", dict(act=a, salt=salt)))
+        return a
 
     @staticmethod
     def fusable(srcs, cout):
@@ -131,8 +141,10 @@ class TrainOps(BlockOps):
 class TrainPlan(NetPlan):
     """Forward + backward launch lists of one network for one batch shape."""
 
-    def __init__(self, eng, batch, h, w, c0, c1, want_params=True, want_input=False):
+    def __init__(self, eng, batch, h, w, c0, c1, want_params=True, want_input=False, dropout=0.0):
         self.want_params, self.want_input = want_params, want_input
+        self.dropout_p = dropout
+        self.dropout_seed = torch.zeros(1, device=eng.device, dtype=torch.int64)
         super().__init__(eng, batch, h, w, c0, c1)
         self.use_graph = False        # eager launch lists (activations are read again by the backward pass)
         self.c0, self.c1 = c0, c1
@@ -142,7 +154,7 @@ class TrainPlan(NetPlan):
         return NoRecyclePool(dev)
 
     def _make_ops(self, dev):
-        return TrainOps(dev, self.pool, self.rec, self.stats)
+        return TrainOps(dev, self.pool, self.rec, self.stats, self.dropout_p, self.dropout_seed)
 
     # -- gradient storage ------------------------------------------------------------------------------------
     def _param_views(self):
@@ -400,6 +412,13 @@ class TrainPlan(NetPlan):
             bwd.add(K.gn_bwd_apply, a.t, a.c, dy, off, cf, bcoef, off, ga[0], info["silu"], ga[1])
             ga[1] = True
             off += a.c
+
+    def _bwd_dropout(self, info):
+        a = info["act"]
+        if not self._has_grad(a):
+            return
+        g = self._grad(a)[0]
+        self.bwd.add(K.dropout, g, g, self.dropout_p, self.dropout_seed, info["salt"])
 
     def _bwd_fir(self, info):
         out = info["out"]

@@ -457,6 +457,11 @@ def axpy(src, dst, alpha=1.0, accumulate=True):
     return dst
 
 
+def dropout(x, out, p, seed_dev, salt):
+    check(_lib.lib().csd_dropout_bf16(_ptr(x), _ptr(out), x.numel(), float(p), _ptr(seed_dev), int(salt), _stream()))
+    return out
+
+
 def zero_stuff(src, dst, stride, offset):
     b, h, w, pitch = src.shape
     check(_lib.lib().csd_zero_stuff_nhwc_bf16(_ptr(src), _ptr(dst), b, h, w, dst.shape[1], dst.shape[2], pitch, stride,

@@ -35,6 +35,8 @@ class _NetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, plan, x0, x1, time_cond, scale0, scale1, *params):
         net._load_inputs(plan, x0, x1, time_cond, scale0, scale1)
+        if plan.dropout_p > 0:
+            plan.dropout_seed.random_()       # torch's CUDA generator: torch.manual_seed makes the masks reproducible
         plan.launch()
         ctx.plan = plan
         ctx.has_x1 = x1 is not None
@@ -96,9 +98,10 @@ class EngineNet(_Base):
         if x0.device.type != "cuda":
             raise RuntimeError("the score network runs on CUDA tensors only (libcsd_b200 has no CPU path)")
         want_p, want_in = self._needs_grad(x0, x1)
-        if self.training and self.config.model.dropout > 0:
-            raise NotImplementedError("dropout (train mode with config.model.dropout > 0) is not implemented by the B200 "
-                                      "engine; set config.model.dropout = 0 or call .eval()")
+        p_drop = float(self.config.model.dropout) if self.training else 0.0
+        if p_drop > 0 and not (want_p or want_in):
+            raise NotImplementedError("train-mode dropout without autograd (torch.no_grad() on a .train() network) is "
+                                      "not planned by the B200 engine; call .eval() for inference")
         eng = self._engine
         eng.ensure_packed(x0.device)
         b, c0, h, w = x0.shape
@@ -106,7 +109,7 @@ class EngineNet(_Base):
         if c0 + c1 != self.in_channels:
             raise ValueError(f"expected {self.in_channels} input channels, got {c0 + c1}")
         if want_p or want_in:
-            plan = eng.train_plan(b, h, w, c0, c1, want_params=want_p, want_input=want_in)
+            plan = eng.train_plan(b, h, w, c0, c1, want_params=want_p, want_input=want_in, dropout=p_drop)
             params = [p for p in self.parameters()]
             outs = _NetFunction.apply(self, plan, x0, x1, time_cond, scale0, scale1, *params)
             return list(outs)

@@ -332,6 +332,12 @@ int csd_transpose_bf16(const void* in, int in_pitch, int64_t in_z_stride, void* 
 /* dst = alpha * src (+ dst if accumulate): gradient of a residual / skip addition. n elements, multiple of 8. */
 int csd_axpy_bf16(const void* src, void* dst, int64_t n, float alpha, int accumulate, csd_stream_t stream);
 
+/* nn.Dropout of the ResNet blocks (models/layerspp.py:266, models/layers.py:664) in train mode: out[i] = keep_i ?
+ * x[i] / (1 - p) : 0 with keep_i a counter-based hash of (*seed_dev, salt, i). Calling it on the gradient with the
+ * same (seed, salt) is the backward pass; no mask is stored. out may alias x. n multiple of 8.                 */
+int csd_dropout_bf16(const void* x, void* out, int64_t n, float p, const int64_t* seed_dev, uint64_t salt,
+                     csd_stream_t stream);
+
 /* dst[b, y*stride+offset, x*stride+offset, :] = src[b, y, x, :], zero elsewhere: turns the data gradient of a
  * stride-2 convolution into a stride-1 convolution with the flipped weights.                                  */
 int csd_zero_stuff_nhwc_bf16(const void* src, void* dst, int batch, int h, int w, int dst_h, int dst_w, int c_pitch,

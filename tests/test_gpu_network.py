@@ -86,8 +86,9 @@ def test_forward_scaled_fuses_sigma_division():
 
 def test_unsupported_modes_raise_loudly():
     f, m = _model("paired")
-    with pytest.raises(NotImplementedError):       # dropout > 0 in train mode is not implemented: no silent skip
-        m.train()({"x": f["x"].cuda(), "y": f["y"].cuda()}, f["labels"].cuda())
+    with pytest.raises(NotImplementedError):       # train-mode dropout has no inference plan: no silent skip
+        with torch.no_grad():
+            m.train()({"x": f["x"].cuda(), "y": f["y"].cuda()}, f["labels"].cuda())
     m.eval()
     with pytest.raises(RuntimeError):
         with torch.no_grad():
