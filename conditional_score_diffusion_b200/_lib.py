@@ -74,6 +74,12 @@ class ConvGemmDesc(ctypes.Structure):
     ]
 
 
+class PackJob(ctypes.Structure):
+    _fields_ = [("src", c_void_p), ("src2", c_void_p), ("dst", c_void_p), ("s_row", c_int64), ("s_col", c_int64),
+                ("s_tap", c_int64), ("rows", c_int32), ("cols", c_int32), ("taps", c_int32), ("k_pad", c_int32),
+                ("dst_pitch", c_int32), ("flip", c_int32), ("kind", c_int32), ("scale", c_float)]
+
+
 class PixMajorGeom(ctypes.Structure):
     _fields_ = [("q", c_int64), ("kp", c_int64), ("row_pitch", c_int64), ("wp", c_int32), ("ips", c_int32),
                 ("splits", c_int32), ("margin", c_int32)]
@@ -122,6 +128,7 @@ _PROTOTYPES = {
                                        c_void_p, c_void_p, c_void_p]),
     "csd_dense_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "csd_conv_gemm": (c_int, [ctypes.POINTER(ConvGemmDesc), c_void_p]),
+    "csd_pack_weights": (c_int, [c_void_p, c_int, c_int64, c_void_p]),
     # ---- training backward ----
     "csd_pixmajor_geometry": (c_int, [c_int, c_int, c_int, ctypes.POINTER(PixMajorGeom)]),
     "csd_nhwc_to_pixmajor_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

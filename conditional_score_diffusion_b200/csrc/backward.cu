@@ -77,11 +77,12 @@ __global__ void gn_bwd_stats_kernel(GnBwdStatsParams p) {
 }
 
 // Pass 2 (tiny): per (image, channel) coefficients of dx = A * du + B * x + Cc, from the forward sums (mean, rstd per
-// group) and S. grid = batch.
+// group) and S. grid = batch. When `contrib` is set, S[b, c] is then overwritten with this image's contribution to
+// (dgamma_c, dbeta_c) = (rstd * (S2 - mean * S1), S1), which gn_bwd_param_reduce_kernel sums over the batch.
 __global__ void __launch_bounds__(256)
 gn_bwd_coeffs_kernel(const float* __restrict__ sums0, int c0, const float* __restrict__ sums1, int c1,
-                     const float* __restrict__ gamma, const float* __restrict__ s, float4* __restrict__ coef, int hw,
-                     int cpg, float eps) {
+                     const float* __restrict__ gamma, float* __restrict__ s, float4* __restrict__ coef, int hw,
+                     int cpg, float eps, int contrib) {
   const int b = blockIdx.x, C = c0 + c1;
   const float inv_n = 1.f / ((float)hw * (float)cpg);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -105,58 +106,83 @@ gn_bwd_coeffs_kernel(const float* __restrict__ sums0, int c0, const float* __res
     }
     m1 *= inv_n;
     m2 *= inv_n;
-    coef[(long long)b * C + c] = make_float4(rstd * gamma[c], -rstd * rstd * m2, -rstd * m1 + rstd * rstd * m2 * mean, 0.f);
+    coef[(long long)b * C + c] = make_float4(rstd * gamma[c], -rstd * rstd * m2, -rstd * m1 + rstd * rstd * m2 * mean, rstd);
+  }
+  if (!contrib) return;
+  __syncthreads();   // every thread has finished reading S (coef[..].w carries rstd; mean is recomputed)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g0 = (c / cpg) * cpg;
+    float su = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      const int cc = g0 + i;
+      su += (cc < c0) ? sums0[((long long)b * c0 + cc) * 2] : sums1[((long long)b * c1 + (cc - c0)) * 2];
+    }
+    const float mean = su * inv_n;
+    const float rstd = coef[(long long)b * C + c].w;
+    float* sp = s + ((long long)b * C + c) * 2;
+    const float s1 = sp[0], s2 = sp[1];
+    sp[0] = rstd * (s2 - mean * s1);
+    sp[1] = s1;
   }
 }
 
-// dgamma[c] += sum_b rstd * (S2 - mean * S1), dbeta[c] += sum_b S1. One thread per channel, batch loop in order.
-__global__ void __launch_bounds__(128)
-gn_bwd_param_kernel(const float* __restrict__ sums0, int c0, const float* __restrict__ sums1, int c1,
-                    const float* __restrict__ s, float* __restrict__ dgamma, float* __restrict__ dbeta, int batch, int hw,
-                    int cpg, float eps) {
-  const int C = c0 + c1;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float inv_n = 1.f / ((float)hw * (float)cpg);
-  const int g0 = (c / cpg) * cpg;
-  float dg = 0.f, db = 0.f;
-  for (int b = 0; b < batch; ++b) {
-    float su = 0.f, sq = 0.f;
-    for (int i = 0; i < cpg; ++i) {
-      const int cc = g0 + i;
-      const float* sp = (cc < c0) ? sums0 + ((long long)b * c0 + cc) * 2 : sums1 + ((long long)b * c1 + (cc - c0)) * 2;
-      su += sp[0];
-      sq += sp[1];
+// dgamma[c] += sum_b contrib[b, c, 0], dbeta[c] += sum_b contrib[b, c, 1]. block (32, 8): 32 channels x 8 batch lanes,
+// fixed-order tree (deterministic).
+__global__ void __launch_bounds__(256)
+gn_bwd_param_reduce_kernel(const float* __restrict__ contrib, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                           int batch, int C) {
+  __shared__ float red[2][8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    for (int b = threadIdx.y; b < batch; b += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(contrib + ((long long)b * C + c) * 2);
+      a0 += v.x;
+      a1 += v.y;
     }
-    const float mean = su * inv_n;
-    const float rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.f) + eps);
-    const float s1 = s[((long long)b * C + c) * 2], s2 = s[((long long)b * C + c) * 2 + 1];
-    dg = fmaf(rstd, s2 - mean * s1, dg);
-    db += s1;
   }
-  dgamma[c] += dg;
-  dbeta[c] += db;
+  red[0][threadIdx.y][threadIdx.x] = a0;
+  red[1][threadIdx.y][threadIdx.x] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float g = 0.f, bt = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { g += red[0][k][threadIdx.x]; bt += red[1][k][threadIdx.x]; }
+    dgamma[c] += g;
+    dbeta[c] += bt;
+  }
 }
 
 // Pass 3 (per source tensor): dx = A * dy * silu'(u) + B * x + C, written or accumulated into dx.
+// grid = batch * slabs, block = V * ppb threads (V = 8-channel vectors per pixel): every thread keeps the coefficients
+// of its 8 channels in registers and streams pixels (same decomposition as gn_apply_kernel).
 struct GnBwdApplyParams {
   const bf16x8* x; int xv, xpv;
   const bf16x8* dy; int dy_pv, dy_voff;
   const float2* coef;        // forward (scale, shift) of this source [batch, c, 2]
-  const float4* bcoef;       // backward (A, B, C) [batch, c_total, 4], this source starts at channel b_coff
+  const float4* bcoef;       // backward (A, B, C, rstd) [batch, c_total, 4], this source starts at channel b_coff
   int c_total, b_coff;
   bf16x8* dx; int dx_pv;
-  int hw, silu, accumulate;
-  long long total;           // batch * hw * xv
+  int hw, silu, accumulate, slabs;
 };
 
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdApplyParams p) {
-  const int C = p.xv * 8;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < p.total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(idx % p.xv);
-    const long long bp = idx / p.xv;          // b * hw + pix
-    const int b = (int)(bp / p.hw);
+__global__ void gn_bwd_apply_kernel(GnBwdApplyParams p) {
+  const int V = p.xv, C = V * 8;
+  const int b = blockIdx.x / p.slabs, slab = blockIdx.x % p.slabs;
+  const int ppb = blockDim.x / V;
+  const int v = threadIdx.x % V, pp = threadIdx.x / V;
+  if (pp >= ppb) return;
+  const long long chunk = ceil_div_ll(p.hw, p.slabs);
+  const long long lo = slab * chunk, hi = min((long long)p.hw, lo + chunk);
+  float sc[8], sh[8], ca[8], cb[8], cc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 fc = p.coef[(long long)b * C + v * 8 + i];
+    const float4 bc = p.bcoef[(long long)b * p.c_total + p.b_coff + v * 8 + i];
+    sc[i] = fc.x; sh[i] = fc.y; ca[i] = bc.x; cb[i] = bc.y; cc[i] = bc.z;
+  }
+  for (long long pix = lo + pp; pix < hi; pix += ppb) {
+    const long long bp = (long long)b * p.hw + pix;
     float fx[8], fd[8], o[8];
     unpack8(p.x[bp * p.xpv + v], fx);
     unpack8(p.dy[bp * p.dy_pv + p.dy_voff + v], fd);
@@ -167,10 +193,8 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdApplyParams p) {
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float2 fc = __ldg(p.coef + (long long)b * C + v * 8 + i);
-      const float4 bc = __ldg(p.bcoef + (long long)b * p.c_total + p.b_coff + v * 8 + i);
-      const float du = p.silu ? fd[i] * silu_grad(fmaf(fx[i], fc.x, fc.y)) : fd[i];
-      o[i] += fmaf(bc.x, du, fmaf(bc.y, fx[i], bc.z));
+      const float du = p.silu ? fd[i] * silu_grad(fmaf(fx[i], sc[i], sh[i])) : fd[i];
+      o[i] += fmaf(ca[i], du, fmaf(cb[i], fx[i], cc[i]));
     }
     p.dx[bp * p.dx_pv + v] = pack8(o);
   }
@@ -488,7 +512,7 @@ int csd_gn_bwd_stats_bf16(const void* x, int c, int x_pitch, const void* dy, int
   return CSD_OK;
 }
 
-int csd_gn_bwd_coeffs_f32(const float* sums0, int c0, const float* sums1, int c1, const float* gamma, const float* s,
+int csd_gn_bwd_coeffs_f32(const float* sums0, int c0, const float* sums1, int c1, const float* gamma, float* s,
                           float* bwd_coef, float* dgamma, float* dbeta, int batch, int hw, int groups, float eps,
                           csd_stream_t stream) {
   using namespace csd;
@@ -497,12 +521,13 @@ int csd_gn_bwd_coeffs_f32(const float* sums0, int c0, const float* sums1, int c1
   const int C = c0 + c1;
   CSD_REQUIRE(groups >= 1 && C % groups == 0, "gn_bwd_coeffs: %d channels not divisible by %d groups", C, groups);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int contrib = (dgamma != nullptr && dbeta != nullptr) ? 1 : 0;
   gn_bwd_coeffs_kernel<<<batch, 256, 0, st>>>(sums0, c0, sums1, c1, gamma, s, reinterpret_cast<float4*>(bwd_coef), hw,
-                                              C / groups, eps);
+                                              C / groups, eps, contrib);
   CSD_LAUNCH_CHECK("gn_bwd_coeffs_kernel");
-  if (dgamma != nullptr && dbeta != nullptr) {
-    gn_bwd_param_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums0, c0, sums1, c1, s, dgamma, dbeta, batch, hw, C / groups, eps);
-    CSD_LAUNCH_CHECK("gn_bwd_param_kernel");
+  if (contrib) {
+    gn_bwd_param_reduce_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, st>>>(s, dgamma, dbeta, batch, C);
+    CSD_LAUNCH_CHECK("gn_bwd_param_reduce_kernel");
   }
   return CSD_OK;
 }
@@ -522,8 +547,12 @@ int csd_gn_bwd_apply_bf16(const void* x, int c, int x_pitch, const void* dy, int
   p.c_total = c_total; p.b_coff = b_c_off;
   p.dx = static_cast<bf16x8*>(dx); p.dx_pv = dx_pitch / 8;
   p.hw = hw; p.silu = silu; p.accumulate = accumulate;
-  p.total = (long long)batch * hw * p.xv;
-  gn_bwd_apply_kernel<<<flat_blocks(p.total), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const int V = c / 8;
+  CSD_REQUIRE(V <= 1024, "gn_bwd_apply: %d channels exceed the 8192 supported", c);
+  const int ppb = std::max(1, 256 / V);
+  int slabs = ceil_div(num_sms() * 16, batch);
+  p.slabs = std::max(1, std::min(slabs, std::max(1, hw / (ppb * 4))));
+  gn_bwd_apply_kernel<<<batch * p.slabs, V * ppb, 0, static_cast<cudaStream_t>(stream)>>>(p);
   CSD_LAUNCH_CHECK("gn_bwd_apply_kernel");
   return CSD_OK;
 }

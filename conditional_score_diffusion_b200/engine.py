@@ -139,7 +139,75 @@ class PackedConv:
         self.bias = torch.zeros(self.n_pad + 16, device=device, dtype=torch.float32)
         self.identity_skip = False
         self._dgrads = {}
+        PackedConv.generation += 1
         self.refresh()
+
+    generation = 0     # bumped whenever a packed operand is created: invalidates the engine's batched pack table
+
+    @staticmethod
+    def _block_jobs(src, dst, dst_off, k_pad, dst_pitch, dgrad, scale):
+        """csd_pack_weights job of one WSrc block, or None when the block cannot take the fast path."""
+        p = src.param
+        if src.kind == "eye" or not (torch.is_tensor(p) and p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+            return None
+        if src.kind == "nin":
+            cin_tot, cout = p.shape
+            taps, cin = 1, (src.ci_cnt if src.ci_cnt is not None else cin_tot)
+            s_co, s_ci, s_tap, off = 1, cout, 0, src.ci_off * cout
+        else:
+            cout, cin_tot = p.shape[0], p.shape[1]
+            taps = p.shape[2] * p.shape[3]
+            cin = src.ci_cnt if src.ci_cnt is not None else cin_tot
+            s_co, s_ci, s_tap, off = cin_tot * taps, taps, 1, src.ci_off * taps
+        if dgrad:
+            return K.pack_job(p.detach(), dst, cin, cout, taps, k_pad, dst_pitch, s_ci, s_co, s_tap, flip=True, scale=scale,
+                              src_off=off, dst_off=dst_off), cout
+        return K.pack_job(p.detach(), dst, cout, cin, taps, k_pad, dst_pitch, s_co, s_ci, s_tap, src_off=off,
+                          dst_off=dst_off), cout
+
+    def jobs(self):
+        """Job list that refreshes this operand (weights, bias, data-gradient packs), or None -> torch refresh."""
+        out = []
+        k_total = self.wt.shape[1]
+        koff = 0
+        for i, seg in enumerate(self.segs):
+            w0 = seg[0].weight(self.device)
+            taps, cin = w0.shape[2] * w0.shape[3], w0.shape[1]
+            cpad = K.ceil_to(cin, 32)
+            co = 0
+            for src in seg:
+                if src.kind == "eye":
+                    co += src.param
+                    continue
+                r = self._block_jobs(src, self.wt, co * k_total + koff, cpad, k_total, False, 1.0)
+                if r is None:
+                    return None
+                out.append(r[0])
+                co += r[1]
+            koff += taps * cpad
+        by_off = {}
+        for b, off in self.bias_srcs:
+            if not (b.is_cuda and b.dtype == torch.float32 and b.is_contiguous()):
+                return None
+            by_off.setdefault(off, []).append(b.detach())
+        for off, bs in by_off.items():
+            if len(bs) > 2 or (len(bs) == 2 and bs[0].numel() != bs[1].numel()):
+                return None
+            out.append(K.bias_job(self.bias, off, bs[0], bs[1] if len(bs) == 2 else None))
+        for d in self._dgrads.values():
+            seg = self.segs[d.i]
+            cout_total = sum(s.weight(self.device).shape[0] for s in seg)
+            k_pad = K.ceil_to(cout_total, 32)
+            w0 = seg[0].weight(self.device)
+            taps = w0.shape[2] * w0.shape[3]
+            co = 0
+            for src in seg:
+                r = self._block_jobs(src, d.wt, co, k_pad, taps * k_pad, True, d.scale)
+                if r is None:
+                    return None
+                out.append(r[0])
+                co += r[1]
+        return out
 
     def seg_weight(self, i):
         ws = [s.weight(self.device).to(self.device) for s in self.segs[i]]
@@ -172,6 +240,7 @@ class DgradPack:
     def __init__(self, pc, i, scale):
         self.pc, self.i, self.scale = pc, i, scale
         self.wt = None
+        PackedConv.generation += 1
         w = pc.seg_weight(i)
         self.cout = w.shape[1]                     # output channels of the dgrad = input channels of the segment
         self.n_store = K.ceil_to(self.cout, 8)
@@ -453,6 +522,7 @@ class NetEngine:
         self.packed = None
         self.param_version = None
         self.param_structure = None
+        self._pack_table = None
         self.plans = {}
         self.train_plans = {}
 
@@ -480,10 +550,76 @@ class NetEngine:
         self.packed = self._pack(device)
         self.param_version = v
         self.param_structure = st
+        self._pack_table = None
         self.plans = {}
         self.train_plans = {}
 
     def _refresh(self):
+        """Re-pack every operand from the live parameters: one csd_pack_weights launch when all parameters are fp32
+        CUDA tensors (the normal case), the per-tensor torch path otherwise."""
+        if self._pack_table is None or self._pack_table[0] != PackedConv.generation:
+            self._pack_table = (PackedConv.generation, self._build_pack_table())
+        table = self._pack_table[1]
+        if table is not None:
+            table.run()
+            return
+        self._refresh_torch()
+
+    def _walk_packed(self, fn):
+        seen = set()
+
+        def visit(obj):
+            if id(obj) in seen:
+                return
+            seen.add(id(obj))
+            if isinstance(obj, PackedConv):
+                fn(obj)
+            elif isinstance(obj, dict):
+                if "wv_img" in obj:
+                    fn(obj)
+                for v in list(obj.values()):
+                    visit(v)
+            elif isinstance(obj, (list, tuple)):
+                for v in obj:
+                    visit(v)
+
+        visit(self.packed["mods"])
+
+    def _build_pack_table(self):
+        jobs, ok = [], [True]
+
+        def add(obj):
+            if isinstance(obj, PackedConv):
+                j = obj.jobs()
+                if j is None:
+                    ok[0] = False
+                else:
+                    jobs.extend(j)
+            else:           # attention dict: the V^T GEMM's weight image and row bias
+                m = obj["mod"]
+                c = m.NIN_2.W.shape[0]
+                W, bvec = m.NIN_2.W, m.NIN_2.b
+                if not (W.is_cuda and W.dtype == torch.float32 and W.is_contiguous() and bvec.is_cuda):
+                    ok[0] = False
+                    return
+                jobs.append(K.pack_job(W.detach(), obj["wv_img"], c, c, 1, c, c, 1, c, 0))
+                jobs.append(K.bias_job(obj["bv"], 0, bvec.detach()))
+
+        self._walk_packed(add)
+        if "dense_mods" in self.packed:
+            off = 0
+            for d in self.packed["dense_mods"]:
+                if not (d.weight.is_cuda and d.weight.dtype == torch.float32 and d.weight.is_contiguous()):
+                    ok[0] = False
+                    break
+                jobs.append(K.bias_job(self.packed["dense_w"], off * d.weight.shape[1], d.weight.detach()))
+                jobs.append(K.bias_job(self.packed["dense_b"], off, d.bias.detach()))
+                off += d.weight.shape[0]
+        if not ok[0]:
+            return None
+        return K.PackTable(jobs, self.device)
+
+    def _refresh_torch(self):
         seen = set()
 
         def visit(obj):

@@ -146,8 +146,8 @@ class TrainPlan(NetPlan):
         self.dropout_p = dropout
         self.dropout_seed = torch.zeros(1, device=eng.device, dtype=torch.int64)
         super().__init__(eng, batch, h, w, c0, c1)
-        self.use_graph = False        # eager launch lists (activations are read again by the backward pass)
         self.c0, self.c1 = c0, c1
+        self.bwd_graph, self.bwd_warm = None, 0
         self._build_backward()
 
     def _make_pool(self, dev):
@@ -212,6 +212,7 @@ class TrainPlan(NetPlan):
         self.bwd = Recorder()
         self.agrads, self.scratch, self.pm_bufs = {}, {}, {}
         self._param_views()
+        self.one = torch.ones(1, 1, device=dev, dtype=torch.float32)
         self.bstats = torch.zeros(32 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
         self.bstats_used = 0
         self.partial_numel = 0
@@ -537,8 +538,8 @@ class TrainPlan(NetPlan):
             bwd.add(K.gn_chan_stats, dqk, 2 * c, sums)
             dbqk = self._bstat_slot(2 * c)
             bwd.add(K.bias_temb_grad, sums, 2 * c, 1.0, dbqk, None, None, 0)
-            bwd.add(self._add_f32, dbqk, 0, c, self.pgrad(m.NIN_0.b))
-            bwd.add(self._add_f32, dbqk, c, c, self.pgrad(m.NIN_1.b))
+            bwd.add(self._add_f32, self.one, dbqk, 0, c, self.pgrad(m.NIN_0.b))
+            bwd.add(self._add_f32, self.one, dbqk, c, c, self.pgrad(m.NIN_1.b))
             sums_v = self._bstat_slot(b * c * 2).view(b, c, 2)
             bwd.add(K.gn_chan_stats, dv, c, sums_v)
             bwd.add(K.bias_temb_grad, sums_v, c, 1.0, self.pgrad(m.NIN_2.b), None, None, 0)
@@ -569,14 +570,28 @@ class TrainPlan(NetPlan):
                                        cols, z, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
     @staticmethod
-    def _add_f32(src, off, n, dst):
+    def _add_f32(one, src, off, n, dst):
         """dst[0:n] += src[off:off+n] through the small-GEMM entry point (1x1 'GEMM' with beta = 1)."""
-        ones = src.new_ones(1, 1)
-        K.sgemm_small(0, 0, 1, n, 1, ones, 1, src[off:], n, dst, n, beta=1.0)
+        K.sgemm_small(0, 0, 1, n, 1, one, 1, src[off:], n, dst, n, beta=1.0)
 
     # -- execution -----------------------------------------------------------------------------------------------
     def run_backward(self):
-        self.bwd.run()
+        """Run the reverse launch list: eagerly the first time, as a replayed CUDA graph afterwards (the list is static:
+        every buffer, including the parameter-gradient buffer and the split-K scratch, belongs to the plan)."""
+        if not self.use_graph or torch.cuda.is_current_stream_capturing():
+            self.bwd.run()
+            return
+        if self.bwd_graph is None:
+            if self.bwd_warm < 1:
+                self.bwd.run()
+                self.bwd_warm += 1
+                return
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.bwd.run()
+            self.bwd_graph = g
+        self.bwd_graph.replay()
 
     def param_grads(self):
         """Fresh fp32 gradient tensors in net.parameters() order (views of one clone of the flat buffer)."""

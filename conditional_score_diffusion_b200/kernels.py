@@ -370,6 +370,42 @@ def dense_rows(act, w, bias, out, total_out=None):
     return out
 
 
+class PackTable:
+    """Device-resident job table of csd_pack_weights (built once per packed network; one launch per refresh)."""
+
+    def __init__(self, jobs, device):
+        import numpy as np
+        self.n = len(jobs)
+        self.max_elems = max([1] + [j.rows * j.cols * j.taps if j.kind == 0 else j.rows for j in jobs])
+        arr = (_lib.PackJob * self.n)(*jobs)
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        self.dev = torch.from_numpy(raw).to(device)
+
+    def run(self):
+        if self.n:
+            check(_lib.lib().csd_pack_weights(_ptr(self.dev), self.n, self.max_elems, _stream()))
+
+
+def pack_job(src, dst, rows, cols, taps, k_pad, dst_pitch, s_row, s_col, s_tap, flip=False, scale=1.0, src_off=0, dst_off=0):
+    """kind-0 job; src fp32 tensor (+ element offset), dst bf16 tensor (+ element offset)."""
+    j = _lib.PackJob()
+    j.src = src.data_ptr() + 4 * src_off
+    j.src2 = None
+    j.dst = dst.data_ptr() + 2 * dst_off
+    j.s_row, j.s_col, j.s_tap = s_row, s_col, s_tap
+    j.rows, j.cols, j.taps, j.k_pad, j.dst_pitch = rows, cols, taps, k_pad, dst_pitch
+    j.flip, j.kind, j.scale = int(flip), 0, float(scale)
+    return j
+
+
+def bias_job(dst, dst_off, src, src2=None):
+    j = _lib.PackJob()
+    j.src, j.src2 = src.data_ptr(), (src2.data_ptr() if src2 is not None else None)
+    j.dst = dst.data_ptr() + 4 * dst_off
+    j.rows, j.cols, j.taps, j.kind, j.scale = src.numel(), 1, 1, 1, 1.0
+    return j
+
+
 # --------------------------------------------------------------------------------------------
 # training backward (adjoints of the kernels above)
 # --------------------------------------------------------------------------------------------

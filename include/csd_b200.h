@@ -257,6 +257,24 @@ typedef struct csd_conv_gemm_desc {
 
 int csd_conv_gemm(const csd_conv_gemm_desc* desc, csd_stream_t stream);
 
+/* ---- batched weight packing -------------------------------------------------------------------------------
+ * One job = one block of a packed operand. kind 0: dst (bf16) [(r)*dst_pitch + tap*k_pad + c] = scale * src[r*s_row +
+ * c*s_col + ts*s_tap], ts = flip ? taps-1-tap : tap, for r < rows, c < cols, tap < taps (dst / src already offset to
+ * the block; padding elements of dst are never written and stay zero). Forward nn.Conv2d weight [Cout,Cin,kh,kw]: r =
+ * co, c = ci, (s_row, s_col, s_tap) = (Cin*taps, taps, 1); its data gradient: r = ci, c = co, flip = 1; NIN.W [in,out]:
+ * (1, out, 0). kind 1: dst (fp32) [i] = src[i] + src2[i] for i < rows (bias vectors; src2 may be NULL).         */
+typedef struct csd_pack_job {
+  const float* src;
+  const float* src2;
+  void* dst;
+  int64_t s_row, s_col, s_tap;
+  int32_t rows, cols, taps, k_pad, dst_pitch, flip, kind;
+  float scale;
+} csd_pack_job;
+
+/* Runs all jobs of a device-resident table in one launch (max_elems = largest rows*cols*taps, sizes the grid). */
+int csd_pack_weights(const csd_pack_job* jobs_dev, int njobs, int64_t max_elems, csd_stream_t stream);
+
 /* ---- training backward ------------------------------------------------------------------------------
  * The reference obtains every gradient from PyTorch autograd (`loss.backward()` under Lightning,
  * lightning_modules/BaseSdeGenerativeModel.py:57-60; losses.py:345-407 in the non-Lightning step_fn): cuDNN
@@ -301,13 +319,14 @@ int csd_wgrad_reduce_f32(const float* partial, int splits, int taps, int cout, i
 /* GroupNorm(+SiLU) backward in three passes (adjoint of csd_gn_apply_bf16 / the fused conv prologue):
  * stats:  s[b, s_c_off + c, 0..1] += (sum_p du, sum_p du * x), du = dy * silu'(x*scale + shift) (or dy), per source;
  *         fwd_coef = that source's (scale, shift) table from csd_gn_coeffs_f32; the caller zeroes s beforehand.
- * coeffs: bwd_coef[b, c, 0..3] = (A, B, C, 0) with dx = A*du + B*x + C over the channel concatenation; if dgamma /
- *         dbeta are given, dgamma[c] += sum_b rstd*(S2 - mean*S1), dbeta[c] += sum_b S1.
+ * coeffs: bwd_coef[b, c, 0..3] = (A, B, C, rstd) with dx = A*du + B*x + C over the channel concatenation; if dgamma /
+ *         dbeta are given, dgamma[c] += sum_b rstd*(S2 - mean*S1), dbeta[c] += sum_b S1 (s is overwritten with the
+ *         per-image contributions on the way).
  * apply:  dx (=|+=) A*du + B*x + C for one source.                                                            */
 int csd_gn_bwd_stats_bf16(const void* x, int c, int x_pitch, const void* dy, int dy_pitch, int dy_c_off,
                           const float* fwd_coef, float* s, int c_total, int s_c_off, int batch, int hw, int silu,
                           csd_stream_t stream);
-int csd_gn_bwd_coeffs_f32(const float* sums0, int c0, const float* sums1, int c1, const float* gamma, const float* s,
+int csd_gn_bwd_coeffs_f32(const float* sums0, int c0, const float* sums1, int c1, const float* gamma, float* s,
                           float* bwd_coef, float* dgamma, float* dbeta, int batch, int hw, int groups, float eps,
                           csd_stream_t stream);
 int csd_gn_bwd_apply_bf16(const void* x, int c, int x_pitch, const void* dy, int dy_pitch, int dy_c_off,
