@@ -75,3 +75,66 @@ def max_over_ranks(value, device):
     if world()[1] > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t.item()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# training: data-parallel gradient all-reduce (the only collective of the backward path)
+# ------------------------------------------------------------------------------------------------------------
+def _shared_flat(grads):
+    """If every gradient is a view into ONE contiguous fp32 buffer, in order (what engine_train.TrainPlan.param_grads
+    returns), hand back a flat view over that span so it can be reduced in place with a single collective."""
+    if not grads:
+        return None
+    base = grads[0].untyped_storage()
+    end = None
+    lo = grads[0].storage_offset()
+    for g in grads:
+        if g.dtype != torch.float32 or not g.is_contiguous() or g.untyped_storage().data_ptr() != base.data_ptr():
+            return None
+        if end is not None and g.storage_offset() < end:
+            return None
+        end = g.storage_offset() + g.numel()
+    flat = torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(base, lo, (end - lo,), (1,))
+    return flat
+
+
+def allreduce_gradients(module_or_params, average=True, bucket_bytes=64 << 20, group=None):
+    """Sum (or average) the .grad of every parameter over the ranks: the DDP gradient all-reduce the reference gets
+    from Lightning's accelerator='ddp' (run_lib.py:55-57). Gradients produced by the engine's backward pass live in
+    one flat buffer and are reduced in place with ONE collective over NVLink; otherwise they are packed into buckets of
+    `bucket_bytes`. Returns the number of bytes reduced."""
+    rank, world_size = world()
+    params = module_or_params.parameters() if hasattr(module_or_params, "parameters") else module_or_params
+    grads = [p.grad for p in params if p.grad is not None]
+    if world_size == 1 or not grads:
+        return 0
+    flat = _shared_flat(grads)
+    if flat is not None:
+        dist.all_reduce(flat, group=group)
+        if average:
+            flat.div_(world_size)
+        return flat.numel() * 4
+    total, bucket, size = 0, [], 0
+
+    def flush():
+        nonlocal bucket, size, total
+        if not bucket:
+            return
+        buf = torch.cat([g.reshape(-1).to(torch.float32) for g in bucket])
+        dist.all_reduce(buf, group=group)
+        if average:
+            buf.div_(world_size)
+        off = 0
+        for g in bucket:
+            g.copy_(buf[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        total += buf.numel() * 4
+        bucket, size = [], 0
+
+    for g in grads:
+        bucket.append(g)
+        size += g.numel() * 4
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    return total

@@ -52,9 +52,48 @@ def get_sampling_fn(config, sde, shape, eps, predictor="default", corrector="def
                               c_steps=c_steps, probability_flow=config.sampling.probability_flow,
                               continuous=config.training.continuous, denoise=denoise, eps=eps)
     if name == "ode":
-        raise NotImplementedError("the black-box ODE sampler (sampling/unconditional.py:93-158) is not part of this "
-                                  "round's hot path (SURVEY.md §8f item 3)")
+        return get_ode_sampler(sde=sde, shape=shape, denoise=denoise, eps=eps)
     raise ValueError(f"Sampler name {name} unknown.")
+
+
+def get_ode_sampler(sde, shape, denoise=False, rtol=1e-5, atol=1e-5, method="RK45", eps=1e-3):
+    """Probability-flow ODE sampler with scipy's black-box integrator (sampling/unconditional.py:93-158).
+
+    Returns ode_sampler(model, z=None) -> (samples, nfe). The right-hand side is one engine forward (CUDA graph replay)
+    per call; the state crosses the host once per evaluation, as in the reference."""
+    import numpy as np
+    from scipy import integrate
+
+    def denoise_update_fn(model, x):
+        score_fn = mutils.get_score_fn(sde, model, conditional=False, train=False, continuous=True)
+        predictor_obj = ReverseDiffusionPredictor(sde, score_fn, probability_flow=False)
+        vec_eps = torch.ones(x.shape[0], device=x.device) * eps
+        _, x = predictor_obj.update_fn(x, vec_eps)
+        return x
+
+    def drift_fn(model, x, t):
+        score_fn = mutils.get_score_fn(sde, model, conditional=False, train=False, continuous=True)
+        rsde = sde.reverse(score_fn, probability_flow=True)
+        return rsde.sde(x, t)[0]
+
+    def ode_sampler(model, z=None):
+        with torch.no_grad():
+            x = sde.prior_sampling(shape).to(model.device) if z is None else z
+
+            def ode_func(t, x):
+                x = mutils.from_flattened_numpy(x, shape).to(model.device).type(torch.float32)
+                vec_t = torch.ones(shape[0], device=x.device) * t
+                return mutils.to_flattened_numpy(drift_fn(model, x, vec_t))
+
+            solution = integrate.solve_ivp(ode_func, (sde.T, eps), mutils.to_flattened_numpy(x), rtol=rtol, atol=atol,
+                                           method=method)
+            nfe = solution.nfev
+            x = torch.tensor(solution.y[:, -1]).reshape(shape).to(model.device).type(torch.float32)
+            if denoise:
+                x = denoise_update_fn(model, x)
+            return x, nfe
+
+    return ode_sampler
 
 
 def shared_predictor_update_fn(x, t, sde, model, predictor, probability_flow, continuous):

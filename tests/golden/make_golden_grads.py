@@ -99,6 +99,24 @@ def main():
     out.update(div_x=xs.detach().clone(), div_t=ts, div_eps=probe, div_score=s.detach().clone(), div_grad=gx.clone())
     fx["uncond"] = out
 
+    # ---- likelihood (likelihood.py:40-113) and the probability-flow ODE sampler (sampling/unconditional.py:93-158) on
+    #      the same network; loose solver tolerances keep the run short, the Hutchinson probe is stored ----
+    import likelihood as ref_likelihood
+    from sampling.unconditional import get_ode_sampler
+    model.eval()
+    sde_l = sde_lib.VESDE(sigma_min=0.01, sigma_max=50, N=1000)
+    like_fn = ref_likelihood.get_likelihood_fn(sde_l, lambda v: (v + 1.0) / 2.0, rtol=1e-3, atol=1e-3, eps=1e-5)
+    torch.manual_seed(504)
+    bpd, z_lat, nfe = like_fn(model, xb)
+    torch.manual_seed(504)
+    probe_l = torch.randint_like(xb, low=0, high=2).float() * 2 - 1.0
+    fx["likelihood"] = {"x": xb, "epsilon": probe_l, "bpd": bpd.clone(), "z": z_lat.clone(), "nfe": nfe, "rtol": 1e-3,
+                        "atol": 1e-3, "eps": 1e-5, "sigma_min": 0.01, "sigma_max": 50.0}
+    ode = get_ode_sampler(sde_l, tuple(xb.shape), denoise=True, rtol=1e-3, atol=1e-3, eps=1e-3)
+    z0 = torch.randn(xb.shape, generator=g) * 50.0
+    xs_ode, nfe_ode = ode(model, z=z0.clone())
+    fx["ode_sampler"] = {"z": z0, "samples": xs_ode.clone(), "nfe": nfe_ode, "rtol": 1e-3, "atol": 1e-3, "eps": 1e-3}
+
     # ---- SR3 on ddpm_paired_SR3 ----
     rec = base_ddpm["ddpm_paired"]
     sd_paired = {k: v.float() for k, v in rec["state_dict_bf16"].items()}
@@ -120,7 +138,10 @@ def main():
     path = os.path.join(OUT, "reference_grads.pt")
     torch.save(fx, path)
     print("wrote", path, f"{os.path.getsize(path) / 1e6:.2f} MB")
+    print("likelihood bpd", fx["likelihood"]["bpd"], "nfe", fx["likelihood"]["nfe"], "ode nfe", fx["ode_sampler"]["nfe"])
     for k, v in fx.items():
+        if "grads" not in v:
+            continue
         gn = sum(float(gg.float().pow(2).sum()) for gg in v["grads"].values()) ** 0.5
         print(k, "loss", float(v["loss"]), "params with grad", len(v["grads"]), "grad norm", gn)
 

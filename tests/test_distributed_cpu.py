@@ -42,8 +42,23 @@ def _worker(rank, world_size, port, results):
 
         out, info = D.sample_sharded(fake_sampler, model, y, gather=True, seed=7)
         lo, hi = D.shard_range(10, rank, world_size)
+        # training: gradient all-reduce, (a) gradients as views of one flat buffer (the engine's layout) reduced in
+        # place with one collective, (b) ordinary per-parameter gradients through the bucketed path
+        params = [p for p in model.parameters()]
+        flat = torch.full((sum(p.numel() for p in params),), float(rank + 1))
+        off = 0
+        for p in params:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        n_flat = D.allreduce_gradients(model, average=True)
+        flat_ok = bool(torch.all(flat == 1.5)) and n_flat == flat.numel() * 4
+        for i, p in enumerate(params):
+            p.grad = torch.full_like(p, float((rank + 1) * (i + 1)))
+        n_b = D.allreduce_gradients(params, average=False, bucket_bytes=256)
+        bucket_ok = all(bool(torch.all(p.grad == 3.0 * (i + 1))) for i, p in enumerate(params)) and n_b == n_flat
         results[rank] = {"same": same, "changed": changed, "nbytes": nbytes, "out": out.clone(), "n": info["n"],
-                         "range": (lo, hi), "max": D.max_over_ranks(float(rank + 1), torch.device("cpu"))}
+                         "range": (lo, hi), "max": D.max_over_ranks(float(rank + 1), torch.device("cpu")),
+                         "flat_ok": flat_ok, "bucket_ok": bucket_ok}
     finally:
         dist.destroy_process_group()
 
@@ -86,3 +101,5 @@ def test_broadcast_shard_gather_world2():
     assert torch.allclose(frac[:5], frac[:1].expand(5)) and torch.allclose(frac[5:], frac[5:6].expand(5))
     assert abs(frac[0].item() - frac[5].item()) > 1e-6
     assert r[0]["max"] == 2.0 and r[1]["max"] == 2.0
+    assert r[0]["flat_ok"] and r[1]["flat_ok"], "in-place all-reduce of the flat gradient buffer"
+    assert r[0]["bucket_ok"] and r[1]["bucket_ok"], "bucketed gradient all-reduce"
