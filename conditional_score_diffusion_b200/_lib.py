@@ -101,6 +101,7 @@ _PROTOTYPES = {
                                        c_int, c_float, c_float, c_void_p]),
     "csd_ve_perturb_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "csd_sde_perturb_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "csd_inpaint_merge_f32": (c_int, [c_void_p] * 6 + [c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "csd_dsm_loss_f32": (c_int, [c_void_p] * 6 + [c_int, c_int64, c_void_p]),
     "csd_broadcast_table_f32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "csd_langevin_norms_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),

@@ -221,6 +221,26 @@ euler_maruyama_kernel(const float* x, const float* __restrict__ score, const flo
   });
 }
 
+// Inpainting projection after a predictor / corrector update (sampling/unconditional.py:266-277):
+// masked = mean_coef * data + std * z;  x_out = x (1 - m) + masked m;  x_mean = x_out (1 - m) + mean_coef * data * m
+// (the reference builds x_mean from the already merged x: kept as is).
+__global__ void __launch_bounds__(256)
+inpaint_merge_kernel(const float* x, const float* __restrict__ data, const float* __restrict__ z,
+                     const float* __restrict__ mask, float* x_out, float* __restrict__ x_mean, long long per_sample,
+                     const float* __restrict__ mean_coef, const float* __restrict__ stdv) {
+  const int b = blockIdx.y;
+  const float mc = mean_coef != nullptr ? mean_coef[b] : 1.f;
+  const float sd = stdv[b];
+  const long long base = (long long)b * per_sample;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x) {
+    const float m = mask[base + i];
+    const float dm = mc * data[base + i];
+    const float xo = x[base + i] * (1.f - m) + fmaf(sd, z[base + i], dm) * m;
+    x_out[base + i] = xo;
+    x_mean[base + i] = xo * (1.f - m) + dm * m;
+  }
+}
+
 static inline dim3 ps_grid(int batch, long long per_sample, int vec) {
   long long bx = ceil_div_ll(per_sample / vec, 256);
   long long cap = std::max<long long>(1, ceil_div_ll((long long)num_sms() * 8, batch));
@@ -287,6 +307,17 @@ int csd_sde_perturb_f32(const float* x, const float* z, float* out, int batch, i
   else
     sde_perturb_kernel<1><<<ps_grid(batch, per_sample, 1), 256, 0, st>>>(x, z, out, per_sample, mean_coef, std_dev);
   CSD_LAUNCH_CHECK("sde_perturb_kernel");
+  return CSD_OK;
+}
+
+int csd_inpaint_merge_f32(const float* x, const float* data, const float* z, const float* mask, float* x_out, float* x_mean,
+                          int batch, int64_t per_sample, const float* mean_coef, const float* std_dev, csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(x && data && z && mask && x_out && x_mean && std_dev, "inpaint_merge: null pointer");
+  CSD_REQUIRE(batch >= 1 && batch <= 65535 && per_sample >= 1, "inpaint_merge: bad batch / per_sample");
+  inpaint_merge_kernel<<<ps_grid(batch, per_sample, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, data, z, mask, x_out, x_mean, per_sample, mean_coef, std_dev);
+  CSD_LAUNCH_CHECK("inpaint_merge_kernel");
   return CSD_OK;
 }
 

@@ -247,6 +247,14 @@ def sde_perturb(x, z, out, mean_coef, std):
     return out
 
 
+def inpaint_merge(x, data, z, mask, x_out, x_mean, mean_coef, std):
+    _require_cuda(x, data, z, mask, x_out, x_mean, mean_coef, std)
+    b, ps = _per_sample(x)
+    check(_lib.lib().csd_inpaint_merge_f32(_ptr(x), _ptr(data), _ptr(z), _ptr(mask), _ptr(x_out), _ptr(x_mean), b, ps,
+                                           _ptr(mean_coef), _ptr(std), _stream()))
+    return x_out, x_mean
+
+
 def dsm_loss(score, z, a, c, w, losses):
     """losses[b] += w[b] * sum((a[b] * score + c[b] * z)^2); `losses` is pre-zeroed by the caller."""
     _require_cuda(score, z, a, c, w, losses)

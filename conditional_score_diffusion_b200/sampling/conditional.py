@@ -57,9 +57,6 @@ def get_pc_conditional_sampler(sde, shape, predictor, corrector, snr, p_steps, c
 
     Returns f(model, y, show_evolution=False) -> (samples, info).
     """
-    if use_path:
-        raise NotImplementedError("use_path=True (sampling/conditional.py:87-94,124-176) is a follow-up row "
-                                  "(SURVEY.md §8f item 2); every shipped config uses use_path=False")
     kinds = fused_kinds(predictor, corrector)
     pair = isinstance(sde, dict) and len(sde.keys()) == 2
     predictor_update_fn = functools.partial(conditional_shared_predictor_update_fn, sde=sde, predictor=predictor,
@@ -74,6 +71,50 @@ def get_pc_conditional_sampler(sde, shape, predictor, corrector, snr, p_steps, c
         std = sde["y"].marginal_prob(vec_t, vec_t)[1].contiguous()
         y = y.contiguous().float()
         return K.ve_perturb(y, torch.randn_like(y), torch.empty_like(y), std, None, 1)
+
+    def backward_kernel_sample(y0, y_tpt, vec_t, vec_tau):
+        """y_t ~ p(y_t | y_0, y_{t+tau}) (VESDE.compute_backward_kernel, sde_lib.py:323-339) in two fused passes:
+        mean = a y_0 + b y_{t+tau}, then mean + std z."""
+        s_t = sde["y"].marginal_prob(vec_t, vec_t)[1] ** 2
+        s_tau = sde["y"].marginal_prob(vec_t, vec_t + vec_tau)[1] ** 2
+        a = ((s_tau - s_t) / s_tau).float().contiguous()
+        b = (s_t / s_tau).float().contiguous()
+        std = torch.sqrt(s_t * (s_tau - s_t) / s_tau).float().contiguous()
+        mean = K.sde_perturb(y0, y_tpt, torch.empty_like(y0), a, b)
+        return K.sde_perturb(mean, torch.randn_like(y0), torch.empty_like(y0), None, std)
+
+    def pc_conditional_sampler_path(model, y, show_evolution=False, x_init=None):
+        """use_path=True (sampling/conditional.py:87-94,124-176): y walks down ONE consistent path y_T -> y_0 through
+        the backward kernel; predictor first, then the corrector on the same y_t."""
+        if not pair:
+            raise NotImplementedError("use_path=True needs the {'x', 'y'} SDE pair (sampling/conditional.py:86-87)")
+        c_sde = sde["x"]
+        with torch.no_grad():
+            dev = model.device
+            y = y.to(dev).contiguous().float()
+            x = (c_sde.prior_sampling(shape) if x_init is None else x_init).to(dev)
+            timesteps = torch.linspace(c_sde.T, eps, p_steps, device=dev)
+            tau = timesteps[0] - timesteps[1]
+            ones = torch.ones(x.shape[0], device=dev)
+            std_T = sde["y"].marginal_prob(ones, ones * (timesteps[0] + tau))[1].float().contiguous()
+            y_tpt = K.sde_perturb(y, torch.randn_like(y), torch.empty_like(y), None, std_T)
+            evolution = {"x": [], "y": []}
+            x_mean = x
+            for i in range(p_steps):
+                vec_t = ones * timesteps[i]
+                y_tpt = backward_kernel_sample(y, y_tpt, vec_t, ones * tau)
+                x, x_mean = predictor_update_fn(x=x, y=y_tpt, t=vec_t, model=model)
+                x, x_mean = corrector_update_fn(x=x, y=y_tpt, t=vec_t, model=model)
+                if show_evolution:
+                    evolution["x"].append(x.cpu())
+                    evolution["y"].append(y_tpt.cpu())
+            if show_evolution:
+                return (x_mean if denoise else x), {"evolution": {"x": torch.stack(evolution["x"]),
+                                                                  "y": torch.stack(evolution["y"])}}
+            return (x_mean if denoise else x), {}
+
+    if use_path:
+        return pc_conditional_sampler_path
 
     def pc_conditional_sampler(model, y, show_evolution=False, x_init=None, noise_source=None):
         c_sde = sde["x"] if isinstance(sde, dict) else sde

@@ -117,6 +117,12 @@ int csd_sde_perturb_f32(const float* x, const float* z, float* out, int batch, i
 int csd_dsm_loss_f32(const float* score, const float* z, const float* a, const float* c, const float* w, float* losses,
                      int batch, int64_t per_sample, csd_stream_t stream);
 
+/* Inpainting projection after each predictor / corrector update (get_pc_inpainter, sampling/unconditional.py:266-277):
+ * masked = mean_coef[b]*data + std_dev[b]*z; x_out = x*(1-mask) + masked*mask; x_mean = x_out*(1-mask) +
+ * mean_coef[b]*data*mask. mask has the shape of data. x_out may alias x. mean_coef NULL = 1 (VE SDEs).            */
+int csd_inpaint_merge_f32(const float* x, const float* data, const float* z, const float* mask, float* x_out, float* x_mean,
+                          int batch, int64_t per_sample, const float* mean_coef, const float* std_dev, csd_stream_t stream);
+
 /* dst[i] = table value for sample i at the current step (time labels, 1/sigma row scales). */
 int csd_broadcast_table_f32(float* dst, int n, const float* tab, const int* step_idx, int sample_stride,
                             csd_stream_t stream);

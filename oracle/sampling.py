@@ -103,3 +103,56 @@ def pc_conditional_sampler(score_fn, sde_x, sde_y, y, shape, snr, p_steps, c_ste
         if record is not None:
             record.append(x.clone())
     return (x_mean if denoise else x), {}
+
+
+def pc_conditional_sampler_path(score_fn, sde_x, sde_y, y, shape, snr, p_steps, eps=1e-5, denoise=True,
+                                randn_like=torch.randn_like, x_init=None, record=None):
+    """get_pc_conditional_sampler(..., use_path=True)(model, y) (sampling/conditional.py:87-94,124-176): y follows one
+    path through p(y_t | y_0, y_{t+tau}) (VESDE.compute_backward_kernel, sde_lib.py:323-339); predictor, then corrector."""
+    x = sde_x.prior_sampling(shape) if x_init is None else x_init.clone()
+    timesteps = torch.linspace(sde_x.T, eps, p_steps)
+    tau = timesteps[0] - timesteps[1]
+    ones = torch.ones(x.shape[0])
+    y_tpt = y + randn_like(y) * _bc(sde_y.sigma(ones * (timesteps[0] + tau)), y)
+    x_mean = x
+    for i in range(p_steps):
+        vec_t = ones * timesteps[i]
+        s_t, s_tau = sde_y.sigma(vec_t) ** 2, sde_y.sigma(vec_t + tau) ** 2
+        mean = y * _bc((s_tau - s_t) / s_tau, y) + y_tpt * _bc(s_t / s_tau, y)
+        y_tpt = mean + randn_like(y) * _bc(torch.sqrt(s_t * (s_tau - s_t) / s_tau), y)
+        score = score_fn(x, y_tpt, vec_t)
+        x, x_mean = reverse_diffusion_update(sde_x, score, x, vec_t, randn_like(x))
+        grad = score_fn(x, y_tpt, vec_t)
+        x, x_mean = langevin_update(sde_x, grad, x, vec_t, randn_like(x), snr)
+        if record is not None:
+            record.append(x.clone())
+    return (x_mean if denoise else x), {}
+
+
+def pc_inpainter(score_fn, sde, data, mask, snr, eps=1e-5, denoise=True, randn_like=torch.randn_like, x_init=None,
+                 record=None):
+    """get_pc_inpainter(...)(model, data, mask) (sampling/unconditional.py:230-345) for a VE SDE with the Langevin
+    corrector and the reverse-diffusion predictor: after each update the known pixels are re-imposed at the current
+    noise level; x_mean is rebuilt from the merged x (reference quirk, :275)."""
+    prior = sde.prior_sampling(data.shape) if x_init is None else x_init.clone()
+    x = data * mask + prior * (1.0 - mask)
+    timesteps = torch.linspace(sde.T, eps, sde.N)
+    x_mean = x
+
+    def merge(x, vec_t):
+        std = sde.sigma(vec_t)
+        masked = data + randn_like(x) * _bc(std, x)
+        x = x * (1.0 - mask) + masked * mask
+        return x, x * (1.0 - mask) + data * mask
+
+    for i in range(sde.N):
+        vec_t = torch.ones(data.shape[0]) * timesteps[i]
+        grad = score_fn(x, vec_t)
+        x, _ = langevin_update(sde, grad, x, vec_t, randn_like(x), snr)
+        x, x_mean = merge(x, vec_t)
+        score = score_fn(x, vec_t)
+        x, _ = reverse_diffusion_update(sde, score, x, vec_t, randn_like(x))
+        x, x_mean = merge(x, vec_t)
+        if record is not None:
+            record.append(x.clone())
+    return (x_mean if denoise else x), {}

@@ -117,6 +117,33 @@ def main():
     xs_ode, nfe_ode = ode(model, z=z0.clone())
     fx["ode_sampler"] = {"z": z0, "samples": xs_ode.clone(), "nfe": nfe_ode, "rtol": 1e-3, "atol": 1e-3, "eps": 1e-3}
 
+    # ---- inpainting (sampling/unconditional.py:230-345) on the unconditional network, 4 noise levels ----
+    from sampling import predictors, correctors
+    from sampling.unconditional import get_pc_inpainter
+    from sampling.conditional import get_pc_conditional_sampler
+    sde_i = sde_lib.VESDE(sigma_min=0.01, sigma_max=50, N=4)
+    inpainter = get_pc_inpainter(sde_i, predictors.get_predictor("reverse_diffusion"), correctors.get_corrector("langevin"),
+                                 snr=0.16, n_steps=1, continuous=True, denoise=True, eps=1e-5)
+    mask = torch.ones_like(xb)
+    mask[:, :, 4:12, 4:12] = 0.0
+    torch.manual_seed(505)
+    xi, info_i = inpainter(model, xb, mask, show_evolution=True)
+    fx["inpaint"] = {"data": xb, "mask": mask, "samples": xi.clone(), "evolution": info_i["evolution"].clone(), "seed": 505,
+                     "snr": 0.16, "N": 4, "sigma_min": 0.01, "sigma_max": 50.0, "eps": 1e-5}
+    # ---- use_path conditional sampler (sampling/conditional.py:87-94,124-176) on ncsnpp_paired ----
+    recp = base["ncsnpp_paired"]
+    model_p = build(recp, recp["state_dict"]).eval()
+    sdes_p = {"x": sde_lib.cVESDE(sigma_min=5e-3, sigma_max=smax, N=1000),
+              "y": sde_lib.VESDE(sigma_min=5e-3, sigma_max=0.5, N=1000)}
+    sampler_p = get_pc_conditional_sampler(sdes_p, (B, 3, hw, hw), predictors.get_predictor("conditional_reverse_diffusion"),
+                                           correctors.get_corrector("conditional_langevin"), snr=0.15, p_steps=3, c_steps=1,
+                                           continuous=True, denoise=True, use_path=True, eps=1e-5)
+    torch.manual_seed(506)
+    xp, info_p = sampler_p(model_p, yb, show_evolution=True)
+    fx["pc_use_path"] = {"y": yb, "samples": xp.clone(), "evolution_x": info_p["evolution"]["x"].clone(),
+                         "evolution_y": info_p["evolution"]["y"].clone(), "seed": 506, "snr": 0.15, "p_steps": 3,
+                         "sigma_min": 5e-3, "sigma_max_x": smax, "sigma_max_y": 0.5, "eps": 1e-5}
+
     # ---- SR3 on ddpm_paired_SR3 ----
     rec = base_ddpm["ddpm_paired"]
     sd_paired = {k: v.float() for k, v in rec["state_dict_bf16"].items()}

@@ -168,3 +168,76 @@ def test_class_based_updates_vs_oracle():
         step = (0.16 * sde_o.sigma(s["t"])) ** 2 * 2
         ref_mean = s["x"] + step[:, None, None, None] * s["score"]
         assert _rel(xm2, ref_mean) < STATE_TOL
+
+
+def _opts(name):
+    return o_net.model_options(to_namespace(golden()[f"ncsnpp_{name}"]["config"]))
+
+
+class _Replay:
+    """Replays the CUDA generator's draws in the order the sampler consumed them (same seed, same shapes)."""
+
+    def __init__(self, seed):
+        torch.manual_seed(seed)
+
+    def __call__(self, like):
+        return torch.randn(like.shape, device="cuda").cpu()
+
+
+def test_pc_inpainter_vs_oracle_replayed_noise():
+    """get_pc_inpainter (sampling/unconditional.py:230-345) on the engine: same draws fed to the CPU oracle (pinned to
+    the reference's trajectory by tests/test_oracle_grads.py)."""
+    from conditional_score_diffusion_b200.sampling import unconditional
+    sampling, sde_lib, utils = _pkg()
+    f, m = _model("cifar")
+    g = torch.Generator().manual_seed(31)
+    data = torch.rand(2, 3, 16, 16, generator=g)
+    mask = torch.ones_like(data)
+    mask[:, :, 3:11, 5:13] = 0.0
+    x_init = torch.randn(2, 3, 16, 16, generator=g) * 50
+    sde = sde_lib.VESDE(0.01, 50, 4)
+    fn = unconditional.get_pc_inpainter(sde, sampling.get_predictor("reverse_diffusion"), sampling.get_corrector("langevin"),
+                                        snr=0.16, n_steps=1, continuous=True, denoise=True, eps=1e-5)
+    torch.manual_seed(77)
+    got, info = fn(m, data.cuda(), mask.cuda(), show_evolution=True, x_init=x_init)
+    sde_o = o_sde.VE(0.01, 50, 4)
+    score_fn = o_sde.score_fn_unconditional(lambda x, l: o_net.forward(f["state_dict"], _opts("cifar"), x, l), sde_o, True,
+                                            "fourier")
+    rec = []
+    ref, _ = o_samp.pc_inpainter(score_fn, sde_o, data, mask, 0.16, eps=1e-5, randn_like=_Replay(77), x_init=x_init, record=rec)
+    evo = info["evolution"][1:]
+    for i in range(4):
+        print(f"[inpaint] step {i}: rel {_rel(evo[i], rec[i]):.3e}")
+    assert _rel(evo[0], rec[0]) < STATE_TOL
+    assert _rel(got, ref) < 5 * STATE_TOL
+    # known pixels of the denoised output equal the data exactly (x_mean = ... + data * mask)
+    assert torch.allclose(got.cpu() * mask, data * mask, atol=1e-6)
+
+
+def test_pc_conditional_use_path_vs_oracle_replayed_noise():
+    """get_pc_conditional_sampler(use_path=True) (sampling/conditional.py:87-94,124-176) on the engine."""
+    from conditional_score_diffusion_b200.sampling import conditional
+    sampling, sde_lib, utils = _pkg()
+    f, m = _model("paired")
+    p = golden()["pc_conditional"]
+    y = p["y"]
+    g = torch.Generator().manual_seed(32)
+    x_init = torch.randn(y.shape, generator=g) * p["sigma_max_x"]
+    sde = {"x": sde_lib.cVESDE(p["sigma_min_x"], p["sigma_max_x"], p["N"]), "y": sde_lib.VESDE(p["sigma_min_y"], p["sigma_max_y"], p["N"])}
+    fn = conditional.get_pc_conditional_sampler(sde, tuple(y.shape), sampling.get_predictor("conditional_reverse_diffusion"),
+                                                sampling.get_corrector("conditional_langevin"), snr=p["snr"], p_steps=3, c_steps=1,
+                                                continuous=True, denoise=True, use_path=True, eps=p["eps"])
+    torch.manual_seed(78)
+    got, info = fn(m, y.cuda(), show_evolution=True, x_init=x_init)
+    sx = o_sde.VE(p["sigma_min_x"], p["sigma_max_x"], p["N"])
+    sy = o_sde.VE(p["sigma_min_y"], p["sigma_max_y"], p["N"])
+    score_fn = o_sde.score_fn_conditional_pair(lambda d, l: o_net.forward_paired(f["state_dict"], _opts("paired"), d["x"], d["y"], l),
+                                               sx, sy, True)
+    rec = []
+    ref, _ = o_samp.pc_conditional_sampler_path(score_fn, sx, sy, y, tuple(y.shape), p["snr"], 3, eps=p["eps"],
+                                                randn_like=_Replay(78), x_init=x_init, record=rec)
+    evo = info["evolution"]["x"]
+    for i in range(3):
+        print(f"[use_path] step {i}: rel {_rel(evo[i], rec[i]):.3e}")
+    assert _rel(evo[0], rec[0]) < STATE_TOL
+    assert _rel(got, ref) < 5 * STATE_TOL

@@ -118,3 +118,31 @@ def test_likelihood_and_ode_sampler():
     print(f"[oracle] ode sampler nfe {nfe_s} ref {go['nfe']}")
     assert abs(nfe_s - go["nfe"]) <= 6
     assert (xs - go["samples"]).abs().max().item() <= 5e-2 * go["samples"].abs().max().item()
+
+
+def test_inpainter_and_use_path_sampler():
+    """Oracle PC inpainter / use_path conditional sampler against the reference's trajectories (RNG replayed)."""
+    from oracle import sampling as o_samp
+    f, gi = golden()["ncsnpp_cifar"], grads_golden()["inpaint"]
+    o = o_net.model_options(_nodrop(f["config"]))
+    sd = {k: v.float() for k, v in f["state_dict"].items()}
+    sde = o_sde.VE(gi["sigma_min"], gi["sigma_max"], gi["N"])
+    score_fn = o_sde.score_fn_unconditional(lambda x, l: o_net.forward(sd, o, x, l), sde, True, "fourier")
+    torch.manual_seed(gi["seed"])
+    rec = []
+    xs, _ = o_samp.pc_inpainter(score_fn, sde, gi["data"], gi["mask"], gi["snr"], eps=gi["eps"], record=rec)
+    ref = gi["evolution"][1:]
+    assert (torch.stack(rec) - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    assert (xs - gi["samples"]).abs().max().item() <= 1e-3 * gi["samples"].abs().max().item()
+    fp, gp = golden()["ncsnpp_paired"], grads_golden()["pc_use_path"]
+    op = o_net.model_options(_nodrop(fp["config"]))
+    sdp = {k: v.float() for k, v in fp["state_dict"].items()}
+    sx, sy = o_sde.VE(gp["sigma_min"], gp["sigma_max_x"], 1000), o_sde.VE(gp["sigma_min"], gp["sigma_max_y"], 1000)
+    score_p = o_sde.score_fn_conditional_pair(lambda d, l: o_net.forward_paired(sdp, op, d["x"], d["y"], l), sx, sy, True)
+    torch.manual_seed(gp["seed"])
+    rec = []
+    xs, _ = o_samp.pc_conditional_sampler_path(score_p, sx, sy, gp["y"], tuple(gp["y"].shape), gp["snr"], gp["p_steps"],
+                                               eps=gp["eps"], record=rec)
+    ref = gp["evolution_x"]
+    assert (torch.stack(rec) - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    assert (xs - gp["samples"]).abs().max().item() <= 1e-3 * gp["samples"].abs().max().item()
