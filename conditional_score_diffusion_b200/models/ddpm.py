@@ -1,13 +1,13 @@
 """DDPM U-Net score network (reference: models/ddpm.py:80-213, 275-298).
 
 This is the network most shipped configs select (`model.name = 'ddpm_paired'`). Same registry
-names ('ddpm', 'ddpm_paired', 'ddpm_paired_SR3'), constructor (`DDPM(config)`), `all_modules` order and state-dict
+names ('ddpm', 'ddpm_paired', 'ddpm_paired_SR3', 'ddpm_2xSR', 'ddpm_KxSR'), constructor (`DDPM(config)`), `all_modules` order and state-dict
 keys as the reference; forward() runs the planned CUDA launch list of `engine.NetEngine` (the same kernels as
 NCSN++: GroupNorm(32)+SiLU fused into the 3x3 convolutions where they run in the transposed mode, NIN shortcut as an
 extra K segment, nearest-neighbour x2 as a 2-tap FIR, pad(0,1,0,1)+stride-2 conv through TMA zero fill).
 
 Not carried over: 'ddpm_multi_speed_haar' (broken in the reference: un-imported InvertibleDownsampling2D,
-models/ddpm.py:219), 'ddpm_2xSR' / 'ddpm_KxSR' (squeeze / torchvision resize wrappers around the same network).
+models/ddpm.py:219). With autograd enabled the network is differentiable (engine_train.TrainPlan).
 """
 import functools
 
@@ -128,3 +128,24 @@ class DDPM_paired(DDPM):
     def forward_scaled(self, input_dict, labels, inv_std):
         ox, oy = self._run(input_dict["x"], input_dict["y"], labels, scale0=inv_std["x"], scale1=inv_std["y"])
         return {"x": ox, "y": oy}
+
+
+from .engine_net import ResizeSRMixin, SqueezeSRMixin, SqueezeBlock  # noqa: E402,F401
+
+
+@utils.register_model(name="ddpm_2xSR")
+class DDPM_2xSR(SqueezeSRMixin, DDPM):
+    """models/ddpm.py:300-314."""
+
+    def __init__(self, config, *args, **kwargs):
+        super().__init__(config)
+        self._init_sr(config)
+
+
+@utils.register_model(name="ddpm_KxSR")
+class ddpm_KxSR(ResizeSRMixin, DDPM):
+    """models/ddpm.py:316-331."""
+
+    def __init__(self, config, *args, **kwargs):
+        super().__init__(config)
+        self._init_sr(config)

@@ -122,3 +122,65 @@ class EngineNet(_Base):
     def forward_scaled(self, x, time_cond, inv_std):
         """forward(x, time_cond) * inv_std[:, None, None, None], fused into the output kernel."""
         return self._run(x, None, time_cond, scale0=inv_std)[0]
+
+
+class SqueezeBlock(nn.Module):
+    """models/ncsnpp.py:403-416: space-to-depth by 2 (channel order c*4 + dy*2 + dx) and its inverse. A pure
+    permutation of the data: layout plumbing around the engine call, done with tensor views."""
+
+    def forward(self, z, reverse=False):
+        B, C, H, W = z.shape
+        if not reverse:
+            z = z.reshape(B, C, H // 2, 2, W // 2, 2).permute(0, 1, 3, 5, 2, 4)
+            return z.reshape(B, 4 * C, H // 2, W // 2)
+        z = z.reshape(B, C // 4, 2, 2, H, W).permute(0, 1, 4, 2, 5, 3)
+        return z.reshape(B, C // 4, H * 2, W * 2)
+
+
+class SqueezeSRMixin:
+    """forward of the *_2xSR wrappers (models/ncsnpp.py:418-433, models/ddpm.py:300-314): x is squeezed to the
+    resolution of y, concatenated, and the x part of the output is un-squeezed."""
+
+    def _init_sr(self, config):
+        self.squeeze_block = SqueezeBlock()
+
+    def _sr_forward(self, input_dict, labels, inv_std=None):
+        x = self.squeeze_block(input_dict["x"]).contiguous()
+        y = input_dict["y"]
+        s0 = inv_std["x"] if inv_std is not None else None
+        s1 = inv_std["y"] if inv_std is not None else None
+        ox, oy = self._run(x, y, labels, scale0=s0, scale1=s1)
+        return {"x": self.squeeze_block(ox, reverse=True), "y": oy}
+
+    def forward(self, input_dict, labels):
+        return self._sr_forward(input_dict, labels)
+
+    def forward_scaled(self, input_dict, labels, inv_std):
+        return self._sr_forward(input_dict, labels, inv_std)
+
+
+class ResizeSRMixin:
+    """forward of the *_KxSR wrappers (models/ncsnpp.py:435-449, models/ddpm.py:316-331): y is bilinearly resized to
+    the target resolution before the network and its score back to the low resolution after it, with the same
+    torchvision Resize transforms the reference constructs (pre/post-processing of the condition, not network work)."""
+
+    def _init_sr(self, config):
+        from torchvision.transforms import Resize
+        from torchvision.transforms.functional import InterpolationMode
+        self.resize_to_GT = Resize(config.data.target_resolution, interpolation=InterpolationMode.BILINEAR)
+        self.resize_to_LQ = Resize(config.data.target_resolution // config.data.scale,
+                                   interpolation=InterpolationMode.BILINEAR)
+
+    def _sr_forward(self, input_dict, labels, inv_std=None):
+        x = input_dict["x"]
+        y = self.resize_to_GT(input_dict["y"]).contiguous()
+        s0 = inv_std["x"] if inv_std is not None else None
+        s1 = inv_std["y"] if inv_std is not None else None
+        ox, oy = self._run(x, y, labels, scale0=s0, scale1=s1)
+        return {"x": ox, "y": self.resize_to_LQ(oy)}
+
+    def forward(self, input_dict, labels):
+        return self._sr_forward(input_dict, labels)
+
+    def forward_scaled(self, input_dict, labels, inv_std):
+        return self._sr_forward(input_dict, labels, inv_std)

@@ -6,8 +6,8 @@ state-dict keys (`all_modules.<i>.<Sub>.<param>`: the positional order of `all_m
 checkpoint contract, models/ncsnpp.py:236-382). `forward(x, time_cond)` returns a fresh NCHW fp32
 tensor like the reference; internally it runs the planned CUDA launch list of `engine.NetEngine`.
 
-Inference only in this round: calling forward with autograd enabled on parameters that require grad
-raises (there is no silent PyTorch fallback).
+With autograd enabled the network is one autograd node backed by the planned backward pass
+(engine_train.TrainPlan); there is no PyTorch fallback.
 """
 import functools
 
@@ -195,3 +195,24 @@ class NCSNpp_paired(NCSNpp):
     def forward_scaled(self, input_dict, labels, inv_std):
         ox, oy = self._run(input_dict["x"], input_dict["y"], labels, scale0=inv_std["x"], scale1=inv_std["y"])
         return {"x": ox, "y": oy}
+
+
+from .engine_net import ResizeSRMixin, SqueezeSRMixin, SqueezeBlock  # noqa: E402,F401
+
+
+@utils.register_model(name="ncsnpp_2xSR")
+class NCSNpp_2xSR(SqueezeSRMixin, NCSNpp):
+    """models/ncsnpp.py:418-433."""
+
+    def __init__(self, config, *args, **kwargs):
+        super().__init__(config)
+        self._init_sr(config)
+
+
+@utils.register_model(name="ncsnpp_KxSR")
+class NCSNpp_KxSR(ResizeSRMixin, NCSNpp):
+    """models/ncsnpp.py:435-449."""
+
+    def __init__(self, config, *args, **kwargs):
+        super().__init__(config)
+        self._init_sr(config)

@@ -123,3 +123,48 @@ def test_paired_forward_transposed_levels_vs_oracle():
         out = m({"x": x.cuda(), "y": y.cuda()}, labels.cuda())
     _check(out["x"], ref["x"], "paired 64px x vs oracle")
     _check(out["y"], ref["y"], "paired 64px y vs oracle")
+
+
+def test_sr_wrappers_squeeze_and_resize():
+    """ncsnpp_2xSR / ncsnpp_KxSR (models/ncsnpp.py:403-449): the squeeze is pixel_unshuffle's permutation, the wrappers
+    feed the same network as ncsnpp_paired (identical all_modules / state dict) with x squeezed resp. y resized."""
+    import torch.nn.functional as F
+    from conditional_score_diffusion_b200.models import ncsnpp, utils  # noqa: F401
+    from conditional_score_diffusion_b200.models.engine_net import SqueezeBlock
+    z = torch.randn(2, 3, 8, 6)
+    sq = SqueezeBlock()
+    assert torch.equal(sq(z), F.pixel_unshuffle(z, 2))
+    assert torch.equal(sq(sq(z), reverse=True), z)
+    f = golden()["ncsnpp_paired"]
+    cfg = to_namespace(f["config"])
+    cfg.data.num_channels = 15               # 4*3 squeezed x channels + 3 y channels
+    torch.manual_seed(7)
+    cfg.model.name = "ncsnpp_2xSR"
+    m2 = utils.create_model(cfg).cuda().eval()
+    cfg.model.name = "ncsnpp_paired"
+    mp = utils.create_model(cfg)
+    mp.load_state_dict(m2.state_dict(), strict=True)
+    mp = mp.cuda().eval()
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 3, 32, 32, generator=g).cuda()
+    y = torch.rand(2, 3, 16, 16, generator=g).cuda()
+    labels = torch.tensor([300.0, 40.0]).cuda()
+    with torch.no_grad():
+        o2 = m2({"x": x, "y": y}, labels)
+        op = mp({"x": F.pixel_unshuffle(x, 2), "y": y}, labels)
+    assert o2["x"].shape == x.shape and o2["y"].shape == y.shape
+    assert torch.allclose(o2["x"], F.pixel_shuffle(op["x"], 2)) and torch.allclose(o2["y"], op["y"])
+    # KxSR: y at low resolution, resized to the target before the network and back after it
+    cfg = to_namespace(f["config"])
+    cfg.data.target_resolution, cfg.data.scale = 16, 2
+    cfg.model.name = "ncsnpp_KxSR"
+    mk = utils.create_model(cfg)
+    mk.load_state_dict(f["state_dict"], strict=True)
+    mk = mk.cuda().eval()
+    _, mref = _model("paired")
+    ylo = torch.rand(2, 3, 8, 8, generator=g).cuda()
+    with torch.no_grad():
+        ok = mk({"x": f["x"].cuda(), "y": ylo}, f["labels"].cuda())
+        oref = mref({"x": f["x"].cuda(), "y": mk.resize_to_GT(ylo)}, f["labels"].cuda())
+    assert ok["y"].shape == ylo.shape
+    assert torch.allclose(ok["x"], oref["x"]) and torch.allclose(ok["y"], mk.resize_to_LQ(oref["y"]))
