@@ -241,6 +241,49 @@ inpaint_merge_kernel(const float* x, const float* __restrict__ data, const float
   }
 }
 
+// ---- fused optimizer step over the flat parameter buffer --------------------------------------------------------
+// out[0] += sum x^2 (block partials combined with one atomic per block).
+__global__ void __launch_bounds__(256) sumsq_f32_kernel(const float* __restrict__ x, long long n, float* out) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc = fmaf(x[i], x[i], acc);
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    atomicAdd(out, t);
+  }
+}
+
+// clip_grad_norm_ + torch.optim.Adam (L2 weight decay, no amsgrad) + ExponentialMovingAverage.update in one pass:
+//   g *= min(1, max_norm / (||g|| + 1e-6));  g += wd p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+//   p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps);  ema -= (1 - decay) (ema - p)
+__global__ void __launch_bounds__(256)
+fused_adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                      float* __restrict__ ema, long long n, float lr, float b1, float b2, float eps, float wd, float bc1,
+                      float rsqrt_bc2, float max_norm, const float* __restrict__ gnorm_sq, float one_minus_decay) {
+  float clip = 1.f;
+  if (max_norm >= 0.f) clip = fminf(1.f, max_norm / (sqrtf(*gnorm_sq) + 1e-6f));
+  const float step = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float pi = p[i];
+    const float gi = fmaf(wd, pi, g[i] * clip);
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    pi -= step * mi / fmaf(sqrtf(vi), rsqrt_bc2, eps);
+    p[i] = pi;
+    if (ema != nullptr) {
+      const float e = ema[i];
+      ema[i] = e - one_minus_decay * (e - pi);
+    }
+  }
+}
+
 static inline dim3 ps_grid(int batch, long long per_sample, int vec) {
   long long bx = ceil_div_ll(per_sample / vec, 256);
   long long cap = std::max<long long>(1, ceil_div_ll((long long)num_sms() * 8, batch));
@@ -307,6 +350,30 @@ int csd_sde_perturb_f32(const float* x, const float* z, float* out, int batch, i
   else
     sde_perturb_kernel<1><<<ps_grid(batch, per_sample, 1), 256, 0, st>>>(x, z, out, per_sample, mean_coef, std_dev);
   CSD_LAUNCH_CHECK("sde_perturb_kernel");
+  return CSD_OK;
+}
+
+int csd_sumsq_f32(const float* x, int64_t n, float* out, csd_stream_t stream_) {
+  using namespace csd;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CSD_REQUIRE(x && out && n >= 1, "sumsq: bad arguments");
+  CSD_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
+  sumsq_f32_kernel<<<ew_blocks(n), 256, 0, stream>>>(x, n, out);
+  CSD_LAUNCH_CHECK("sumsq_f32_kernel");
+  return CSD_OK;
+}
+
+int csd_fused_adam_ema_f32(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr, float beta1,
+                           float beta2, float eps, float weight_decay, float bias_corr1, float bias_corr2, float max_norm,
+                           const float* gnorm_sq, float ema_decay, csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(p && g && m && v && n >= 1, "fused_adam_ema: null pointer");
+  CSD_REQUIRE(max_norm < 0.f || gnorm_sq != nullptr, "fused_adam_ema: clipping needs the squared gradient norm");
+  CSD_REQUIRE(bias_corr1 > 0.f && bias_corr2 > 0.f, "fused_adam_ema: bias corrections must be positive");
+  fused_adam_ema_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay, bias_corr1, rsqrtf(bias_corr2), max_norm, gnorm_sq,
+      1.f - ema_decay);
+  CSD_LAUNCH_CHECK("fused_adam_ema_kernel");
   return CSD_OK;
 }
 

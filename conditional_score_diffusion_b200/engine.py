@@ -554,6 +554,10 @@ class NetEngine:
         self.plans = {}
         self.train_plans = {}
 
+    def invalidate(self):
+        """Parameters were modified outside autograd's version tracking (a fused optimizer kernel): re-pack on next use."""
+        self.param_version = None
+
     def _refresh(self):
         """Re-pack every operand from the live parameters: one csd_pack_weights launch when all parameters are fp32
         CUDA tensors (the normal case), the per-tensor torch path otherwise."""

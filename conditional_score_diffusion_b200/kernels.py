@@ -378,6 +378,19 @@ def dense_rows(act, w, bias, out, total_out=None):
     return out
 
 
+def sumsq(x, out):
+    check(_lib.lib().csd_sumsq_f32(_ptr(x), x.numel(), _ptr(out), _stream()))
+    return out
+
+
+def fused_adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, max_norm, gnorm_sq,
+                   ema_decay):
+    _require_cuda(p, g, m, v, ema, gnorm_sq)
+    check(_lib.lib().csd_fused_adam_ema_f32(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(ema), p.numel(), float(lr), float(beta1),
+                                            float(beta2), float(eps), float(weight_decay), float(bias_corr1),
+                                            float(bias_corr2), float(max_norm), _ptr(gnorm_sq), float(ema_decay), _stream()))
+
+
 class PackTable:
     """Device-resident job table of csd_pack_weights (built once per packed network; one launch per refresh)."""
 

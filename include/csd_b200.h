@@ -263,6 +263,19 @@ typedef struct csd_conv_gemm_desc {
 
 int csd_conv_gemm(const csd_conv_gemm_desc* desc, csd_stream_t stream);
 
+/* ---- fused optimizer step ----------------------------------------------------------------
+ * The reference runs torch.nn.utils.clip_grad_norm_ + optim.Adam.step (losses.py:38-52) and then
+ * ExponentialMovingAverage.update (models/ema.py:64-93: a Python loop of 3 kernels per parameter tensor) after every
+ * training step. Over a flat fp32 parameter buffer this is one reduction and one elementwise pass.              */
+/* out[0] = sum x^2 (device scalar).                                                                            */
+int csd_sumsq_f32(const float* x, int64_t n, float* out, csd_stream_t stream);
+/* g' = g * min(1, max_norm / (sqrt(*gnorm_sq) + 1e-6)) (max_norm < 0: no clipping) + weight_decay * p;
+ * m = beta1 m + (1-beta1) g'; v = beta2 v + (1-beta2) g'^2; p -= lr / bias_corr1 * m / (sqrt(v / bias_corr2) + eps);
+ * ema -= (1 - ema_decay) * (ema - p) (ema may be NULL). torch.optim.Adam (no amsgrad) semantics.                */
+int csd_fused_adam_ema_f32(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr, float beta1,
+                           float beta2, float eps, float weight_decay, float bias_corr1, float bias_corr2, float max_norm,
+                           const float* gnorm_sq, float ema_decay, csd_stream_t stream);
+
 /* ---- batched weight packing -------------------------------------------------------------------------------
  * One job = one block of a packed operand. kind 0: dst (bf16) [(r)*dst_pitch + tap*k_pad + c] = scale * src[r*s_row +
  * c*s_col + ts*s_tap], ts = flip ? taps-1-tap : tap, for r < rows, c < cols, tap < taps (dst / src already offset to

@@ -1,7 +1,7 @@
 """GPU probe: one training step of BASELINE config 4 (edges2shoes_SR3.py: ddpm_paired_SR3, nf 128, ch_mult (1,1,2,2),
 attention at 16/8, 64x64, dropout 0.1, batch 50 per GPU, SR3 loss with likelihood weighting, Adam 2e-4, clip 1.0):
 step time with CUDA events and a per-kernel breakdown of the forward and the backward launch lists.
-usage: python tools/train_step_profile.py [batch] [image_size] [eager_torch_reference 0|1]"""
+usage: python tools/train_step_profile.py [batch] [image_size] [fused]   (fused = optim.FusedAdamEMA instead of torch Adam)"""
 import collections
 import math
 import sys
@@ -37,8 +37,14 @@ def main():
     sde = sde_lib.cVESDE(5e-3, math.sqrt(3 * HW * HW), 1000)
     loss_fn = losses.get_general_sde_loss_fn(sde, train=True, conditional=True, reduce_mean=True, continuous=True,
                                              likelihood_weighting=True)
-    opt = losses.get_optimizer(cfg, model.parameters())
-    optimize_fn = losses.optimization_manager(cfg)
+    fused = len(sys.argv) > 3 and sys.argv[3] == "fused"
+    if fused:
+        from conditional_score_diffusion_b200 import optim
+        opt = optim.FusedAdamEMA(model.parameters(), lr=2e-4, grad_clip=1.0, ema_decay=0.999, warmup=2500, model=model)
+        optimize_fn = lambda o, p, step: o.step()
+    else:
+        opt = losses.get_optimizer(cfg, model.parameters())
+        optimize_fn = losses.optimization_manager(cfg)
     x = torch.rand(B, 3, HW, HW, device="cuda")
     y = torch.rand(B, 3, HW, HW, device="cuda")
 
