@@ -138,6 +138,9 @@ _PROTOTYPES = {
                                           ctypes.POINTER(PixMajorGeom), c_int, c_void_p, c_void_p]),
     "csd_wgrad_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, ctypes.POINTER(PixMajorGeom), c_void_p,
                                     c_void_p]),
+    "csd_wgrad_direct_splits": (c_int, [c_int] * 6 + [c_int_p]),
+    "csd_wgrad_direct_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_void_p, c_int, c_void_p]),
     "csd_wgrad_reduce_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_int64, c_int64,
                                      c_int, c_int, c_void_p]),
     "csd_gn_bwd_stats_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,

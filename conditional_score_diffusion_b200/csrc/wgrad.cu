@@ -26,6 +26,7 @@
 #include "../../include/csd_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace csd {
 
@@ -252,6 +253,203 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Direct wgrad: MN-major operands straight from the NHWC tensors (no pixel-major copies)
+// ---------------------------------------------------------------------------------------------------------
+// The contraction index is the pixel, and in NHWC the channels of one pixel are contiguous, so a TMA box of
+// [64 channels x 16 x 8 pixels] lands in shared memory as 128 rows (pixels = K) of 128 bytes (64 channels = M or N):
+// exactly the MN-major SWIZZLE_128B canonical layout of tcgen05 (8 K-rows of 128 bytes per 1024-byte group, the next
+// 64 channels LBO bytes further). One CTA owns (128 output channels) x (n_tile <= 128 input channels) x (the three kx
+// taps of one ky) and loops over its share of 16x8-pixel tiles: per tile it loads the gradient tile and ONE
+// (16+2)x(8+2)-pixel halo of the activation (TMA zero-fills outside the image = the convolution padding); the operand
+// of tap (ky, kx) for tile row r is the 16 consecutive halo rows starting (r + ky) * 18 + kx rows into that copy - a
+// descriptor start-address shift, valid because the swizzle is a function of absolute shared-memory address bits
+// (same trick as the forward halo kernels). Three fp32 accumulators (one per kx) live in TMEM for the whole loop.
+// Compared with the pixel-major path: no re-layout passes, and each loaded byte feeds 3 taps instead of 1.
+constexpr int kDTW = 16, kDTH = 8;                       // pixel tile
+constexpr int kDHW = kDTW + 2, kDHH = kDTH + 2;          // halo
+constexpr int kDGBlock = kDTW * kDTH * 128;              // 16 KB: 128 pixels x 64 channels
+constexpr int kDABlock = ((kDHW * kDHH * 128 + 1023) / 1024) * 1024;   // 23 KB (180 rows, padded to 1024)
+constexpr int kDMaxStages = 4;
+
+struct WgradDirectParams {
+  int H, W, tiles_x, tiles_y, tiles_total, tiles_per_split;
+  int taps, cout, cin, n_tile, n_blocks, a_cblocks;   // a_cblocks: 64-channel blocks of the activation per CTA (1 or 2)
+  int g_coff, a_coff;
+  int num_stages, tmem_cols;
+  uint32_t stage_bytes;
+  float* partial;   // [splits][taps][cout][cin]
+};
+
+// CLUSTER = true: the three ky CTAs of one (channel block, split) form a thread-block cluster (1 x 3 x 1). They walk the
+// same tile sequence and need the SAME gradient tile and activation halo, so every box is fetched from L2 once and
+// multicast into the three CTAs' shared memory (rank 0 issues the two gradient boxes, ranks 1 and 2 one activation box
+// each); a stage is recycled when the MMAs of all three CTAs have consumed it (multicast tcgen05.commit on the three
+// empty barriers). This cuts the L2 -> shared-memory traffic of the kernel by 3x - but measured slower than independent
+// CTAs (see csd_wgrad_direct_bf16), so it is an opt-in experiment, kept correct by the same parity tests.
+template <bool CLUSTER>
+__global__ void __launch_bounds__(kWThreads, 1)
+wgrad_direct_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapA,
+                    const WgradDirectParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + p.num_stages * p.stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kDMaxStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kDMaxStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kDMaxStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mb = blockIdx.x / p.n_blocks, nb = blockIdx.x % p.n_blocks;
+  const int m0 = mb * kWM, n0 = nb * p.n_tile;
+  const int ky = p.taps == 9 ? (int)blockIdx.y : 1;
+  const int ntap = p.taps == 9 ? 3 : 1;
+  const int split = blockIdx.z;
+  const int t_lo = split * p.tiles_per_split;
+  const int t_hi = min(p.tiles_total, t_lo + p.tiles_per_split);
+  const uint32_t a_off = 2u * kDGBlock;                  // activation blocks follow the two gradient blocks
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&mapG);
+    ptx::prefetch_tensormap(&mapA);
+    for (int s = 0; s < p.num_stages; ++s) {
+      ptx::mbar_init(full_bar(s), CLUSTER ? 1 : 2);
+      ptx::mbar_init(empty_bar(s), CLUSTER ? 3 : 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (CLUSTER) ptx::cluster_sync();       // peers' barriers are initialised before anyone multicasts into them
+  ptx::tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (CLUSTER && warp == 0) {
+    if (lane == 0) {
+      // ===== cluster producer: this CTA's share of every stage, multicast to the three ky CTAs =====
+      const uint32_t rank = ptx::cluster_ctarank();
+      const uint32_t total_bytes = 2u * kDGBlock + (uint32_t)p.a_cblocks * (kDHW * kDHH * 128);
+      uint32_t stage = 0, par = 1;
+      for (int t = t_lo; t < t_hi; ++t) {
+        const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * kDTW, y0 = ty * kDTH;
+        ptx::mbar_wait(empty_bar(stage), par);      // all three CTAs have consumed the previous use of this stage
+        const uint32_t base = smem_base + stage * p.stage_bytes;
+        ptx::mbar_arrive_expect_tx(full_bar(stage), total_bytes);
+        if (rank == 0) {
+          ptx::tma_load_4d_multicast(base, &mapG, full_bar(stage), p.g_coff + m0, x0, y0, b, 7);
+          ptx::tma_load_4d_multicast(base + kDGBlock, &mapG, full_bar(stage), p.g_coff + m0 + 64, x0, y0, b, 7);
+        } else if ((int)rank <= p.a_cblocks) {
+          const int cb = (int)rank - 1;
+          ptx::tma_load_4d_multicast(base + a_off + cb * kDABlock, &mapA, full_bar(stage), p.a_coff + n0 + cb * 64, x0 - 1,
+                                     y0 - 1, b, 7);
+        }
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; par ^= 1u; }
+      }
+    }
+  } else if (!CLUSTER && (warp == 0 || warp == 6)) {
+    if (lane == 0) {
+      // ===== producers: warp 0 loads the gradient tile (M side), warp 6 the activation halo (N side) =====
+      const bool is_g = warp == 0;
+      uint32_t stage = 0, par = 1;
+      for (int t = t_lo; t < t_hi; ++t) {
+        const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * kDTW, y0 = ty * kDTH;
+        ptx::mbar_wait(empty_bar(stage), par);
+        const uint32_t base = smem_base + stage * p.stage_bytes;
+        if (is_g) {
+          ptx::mbar_arrive_expect_tx(full_bar(stage), 2u * kDGBlock);
+          ptx::tma_load_4d(base, &mapG, full_bar(stage), p.g_coff + m0, x0, y0, b);
+          ptx::tma_load_4d(base + kDGBlock, &mapG, full_bar(stage), p.g_coff + m0 + 64, x0, y0, b);
+        } else {
+          ptx::mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.a_cblocks * (kDHW * kDHH * 128));
+          for (int cb = 0; cb < p.a_cblocks; ++cb)
+            ptx::tma_load_4d(base + a_off + cb * kDABlock, &mapA, full_bar(stage), p.a_coff + n0 + cb * 64, x0 - 1, y0 - 1, b);
+        }
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; par ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer: both operands MN-major (a_major = b_major = 1) =====
+      const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)p.n_tile) | (1u << 15) | (1u << 16);
+      const uint32_t hi = ptx::smem_desc_hi(1024, kLayoutSw128);
+      uint32_t stage = 0, par = 0, accumulate = 0;
+      for (int t = t_lo; t < t_hi; ++t) {
+        ptx::mbar_wait(full_bar(stage), par);
+        ptx::tcgen05_fence_after();
+        const uint32_t base = smem_base + stage * p.stage_bytes;
+        const uint32_t g_lo = ptx::smem_desc_lo(base, kDGBlock);             // LBO = next 64 output channels
+        const uint32_t a_lo = ptx::smem_desc_lo(base + a_off, kDABlock);     // LBO = next 64 input channels
+#pragma unroll 1
+        for (int r = 0; r < kDTH; ++r) {
+          const uint32_t g_r = g_lo + ((r * kDTW * 128) >> 4);
+          for (int kx = 0; kx < ntap; ++kx) {
+            const int dx = p.taps == 9 ? kx : 1;
+            const uint32_t a_r = a_lo + ((((r + ky) * kDHW + dx) * 128) >> 4);
+            ptx::mma_bf16_ss(tmem_base + kx * p.n_tile, ptx::smem_desc_join(hi, g_r), ptx::smem_desc_join(hi, a_r), idesc,
+                             accumulate);
+          }
+          accumulate = 1u;
+        }
+        if (CLUSTER) ptx::mma_commit_multicast(empty_bar(stage), 7);
+        else ptx::mma_commit(empty_bar(stage));
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; par ^= 1u; }
+      }
+      ptx::mma_commit(tmem_full_bar);
+    }
+  } else if (warp >= 2 && warp <= 5) {
+    // ===== epilogue (warps 2..5): TMEM lane = output channel, one accumulator per kx =====
+    const int q = warp & 3;
+    const int co = m0 + q * 32 + lane;
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tcgen05_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int ncols = min(p.n_tile, p.cin - n0);
+    for (int kx = 0; kx < ntap; ++kx) {
+      const int tap = p.taps == 9 ? ky * 3 + kx : 0;
+      float* orow = p.partial + (((long long)split * p.taps + tap) * p.cout + co) * p.cin;
+      for (int col = 0; col < ncols; col += 16) {
+        uint32_t r[16];
+        __syncwarp();
+        ptx::tmem_ld_x16(t_row + kx * p.n_tile + col, r);
+        ptx::tmem_ld_wait();
+        if (co < p.cout && t_hi > t_lo) {
+          const int cnt = min(16, ncols - col);
+          for (int i = 0; i < cnt; ++i) orow[n0 + col + i] = __uint_as_float(r[i]);
+        } else if (co < p.cout) {
+          const int cnt = min(16, ncols - col);
+          for (int i = 0; i < cnt; ++i) orow[n0 + col + i] = 0.f;
+        }
+      }
+    }
+  }
+
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (CLUSTER) ptx::cluster_sync();       // no CTA leaves while a peer may still multicast into it or signal its barriers
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// input channels per CTA of the direct kernel (developer knob CSD_WGRAD_NMAX = 64 trades operand re-reads for a deeper ring)
+static int direct_n_max() {
+  static const int v = [] {
+    const char* e = getenv("CSD_WGRAD_NMAX");
+    const int n = e ? atoi(e) : 128;
+    return (n == 64 || n == 128) ? n : 128;
+  }();
+  return v;
+}
+
 static int next_pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -352,6 +550,94 @@ int csd_wgrad_gemm_bf16(const void* g_pm, int cout, const void* a_pm, int cin, i
   dim3 grid((unsigned)(m_tiles * p.n_tiles), (unsigned)taps, (unsigned)g->splits);
   wgrad_gemm_kernel<<<grid, kWThreads, smem, static_cast<cudaStream_t>(stream)>>>(mapG, mapA[0], mapA[1], mapA[2], p);
   CSD_LAUNCH_CHECK("wgrad_gemm_kernel");
+  return CSD_OK;
+}
+
+int csd_wgrad_direct_splits(int batch, int h, int w, int cout, int cin, int taps, int* splits) {
+  using namespace csd;
+  CSD_REQUIRE(splits != nullptr && batch >= 1 && h >= 1 && w >= 1 && cout >= 1 && cin >= 1, "wgrad_direct_splits: bad arguments");
+  const int tiles = batch * ceil_div(h, kDTH) * ceil_div(w, kDTW);
+  const int n_blocks = ceil_div(cin, direct_n_max());
+  const int ctas = ceil_div(cout, kWM) * n_blocks * (taps == 9 ? 3 : 1);
+  int s = ceil_div(2 * num_sms(), ctas);
+  s = std::max(1, std::min(s, std::max(1, tiles / 4)));
+  const int tps = ceil_div(tiles, s);
+  *splits = ceil_div(tiles, tps);
+  return CSD_OK;
+}
+
+int csd_wgrad_direct_bf16(const void* g, int g_pitch, int g_c_off, int cout, const void* a, int a_pitch, int a_c_off,
+                          int cin, int taps, int batch, int h, int w, float* partial, int splits, csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(g && a && partial, "wgrad_direct: null pointer");
+  CSD_REQUIRE(taps == 1 || taps == 9, "wgrad_direct: taps %d (1 or 9)", taps);
+  CSD_REQUIRE(g_pitch % 8 == 0 && a_pitch % 8 == 0 && g_c_off % 8 == 0 && a_c_off % 8 == 0,
+              "wgrad_direct: channel pitches / offsets must be multiples of 8");
+  CSD_REQUIRE(g_pitch >= 64 && a_pitch >= 64, "wgrad_direct: tensors with fewer than 64 channels take the pixel-major path");
+  WgradDirectParams p;
+  p.H = h; p.W = w;
+  p.tiles_x = ceil_div(w, kDTW); p.tiles_y = ceil_div(h, kDTH);
+  p.tiles_total = batch * p.tiles_x * p.tiles_y;
+  int want = 0;
+  int st = csd_wgrad_direct_splits(batch, h, w, cout, cin, taps, &want);
+  if (st != CSD_OK) return st;
+  CSD_REQUIRE(splits == want, "wgrad_direct: splits %d != csd_wgrad_direct_splits() = %d", splits, want);
+  p.tiles_per_split = ceil_div(p.tiles_total, splits);
+  p.taps = taps; p.cout = cout; p.cin = cin;
+  p.n_blocks = ceil_div(cin, direct_n_max());
+  p.n_tile = ceil_div(ceil_div(cin, p.n_blocks), 16) * 16;
+  p.a_cblocks = ceil_div(p.n_tile, 64);
+  p.g_coff = g_c_off; p.a_coff = a_c_off;
+  p.stage_bytes = 2u * kDGBlock + (uint32_t)p.a_cblocks * kDABlock;
+  p.num_stages = std::min<int>(kDMaxStages, (int)((200 * 1024) / p.stage_bytes));
+  p.tmem_cols = next_pow2_cols((taps == 9 ? 3 : 1) * p.n_tile);
+  p.partial = partial;
+  CUtensorMap mapG, mapA;
+  {
+    uint64_t dims[4] = {(uint64_t)g_pitch, (uint64_t)w, (uint64_t)h, (uint64_t)batch};
+    uint64_t strides[3] = {(uint64_t)g_pitch * 2, (uint64_t)g_pitch * 2 * w, (uint64_t)g_pitch * 2 * w * h};
+    uint32_t box[4] = {64, (uint32_t)kDTW, (uint32_t)kDTH, 1};
+    st = encode_tensor_map(&mapG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, g, dims, strides, box, TMA_SW_128);
+    if (st != CSD_OK) return st;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)a_pitch, (uint64_t)w, (uint64_t)h, (uint64_t)batch};
+    uint64_t strides[3] = {(uint64_t)a_pitch * 2, (uint64_t)a_pitch * 2 * w, (uint64_t)a_pitch * 2 * w * h};
+    uint32_t box[4] = {64, (uint32_t)kDHW, (uint32_t)kDHH, 1};
+    st = encode_tensor_map(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a, dims, strides, box, TMA_SW_128);
+    if (st != CSD_OK) return st;
+  }
+  const size_t smem = (size_t)p.num_stages * p.stage_bytes + 8 * (2 * kDMaxStages + 2) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSD_CUDA(cudaFuncSetAttribute(wgrad_direct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(wgrad_direct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(ceil_div(cout, kWM) * p.n_blocks), (unsigned)(taps == 9 ? 3 : 1), (unsigned)splits);
+  // Opt-in (CSD_WGRAD_CLUSTER=1): measured on B200 the multicast variant is SLOWER than three independent CTAs (64 px,
+  // 128 -> 128 channels, batch 50: 205 us vs 146 us; 160 px, 96 -> 96, batch 64: 749 us vs 515 us, tools/wgrad_bench.py):
+  // the kernel is not L2-bandwidth bound, and coupling three CTAs per 2-deep stage ring costs more than it saves.
+  static const bool use_cluster = getenv("CSD_WGRAD_CLUSTER") != nullptr;
+  if (taps == 9 && use_cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kWThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 3;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CSD_CUDA(cudaLaunchKernelEx(&cfg, wgrad_direct_kernel<true>, mapG, mapA, p));
+    count_launch();
+    return CSD_OK;
+  }
+  wgrad_direct_kernel<false><<<grid, kWThreads, smem, static_cast<cudaStream_t>(stream)>>>(mapG, mapA, p);
+  CSD_LAUNCH_CHECK("wgrad_direct_kernel");
   return CSD_OK;
 }
 

@@ -274,6 +274,23 @@ class TrainPlan(NetPlan):
         bwd = self.bwd
         b = a_t.shape[0]
         ih, iw = geom_hw
+        g_grid = g_pm_cache.get("g_grid", g_t if stride == 1 else None)    # gradient on the activation grid (NHWC)
+        if (K.WGRAD_DIRECT and g_grid is not None and ih >= 8 and iw >= 8 and g_grid.shape[-1] >= 64
+                and a_t.shape[-1] >= 64 and g_c_off % 8 == 0 and a_c_off % 8 == 0):
+            # MN-major operands straight from the NHWC tensors: no pixel-major copies, 3 taps per loaded tile
+            splits = K.wgrad_direct_splits(b, ih, iw, cout, cin, taps)
+            n = splits * taps * cout * cin
+            self.partial_numel = max(self.partial_numel, n)
+            holder = [None]
+            self._partials.append(holder)
+
+            def run_direct(holder=holder, g_grid=g_grid):
+                K.wgrad_direct(g_grid, g_c_off, cout, a_t, a_c_off, cin, taps, holder[0], splits)
+                K.wgrad_reduce(holder[0], splits, taps, cout, cin, scale, dst, strides[0], strides[1], strides[2], ci_off,
+                               True)
+
+            bwd.add(run_direct)
+            return
         geom = K.pixmajor_geometry(b, ih, iw)
         g_off = (1 - pad) if taps == 9 else 0
         gkey = (g_t.data_ptr(), g_c_off, cout, stride, g_off, ih, iw)
@@ -350,7 +367,7 @@ class TrainPlan(NetPlan):
         if stride != 1:
             g_in = self.pool.get((b, ih, iw, g.shape[-1]))
             bwd.add(K.zero_stuff, g, g_in, stride, 1 - pad)
-        cache = {}
+        cache = {"g_grid": g_in}
         for i, (a, taps) in enumerate(info["segs"]):
             srcs = pc.segs[i]
             is_input = a is self.xin_act

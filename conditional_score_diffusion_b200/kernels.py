@@ -455,6 +455,25 @@ def wgrad_gemm(g_pm, cout, a_pm, cin, taps, geom, partial):
     return partial
 
 
+# MN-major direct wgrad kernel (csd_wgrad_direct_bf16); CSD_NO_WGRAD_DIRECT=1 keeps the pixel-major GEMM path everywhere
+WGRAD_DIRECT = os.environ.get("CSD_NO_WGRAD_DIRECT", "0") != "1"
+
+
+def wgrad_direct_splits(batch, h, w, cout, cin, taps):
+    s = ctypes.c_int(0)
+    check(_lib.lib().csd_wgrad_direct_splits(batch, h, w, cout, cin, taps, ctypes.byref(s)))
+    return s.value
+
+
+def wgrad_direct(g, g_c_off, cout, a, a_c_off, cin, taps, partial, splits):
+    """g, a: NHWC bf16 [B, h, w, pitch] on the same (activation) grid."""
+    b, h, w, _ = a.shape
+    assert g.shape[:3] == a.shape[:3]
+    check(_lib.lib().csd_wgrad_direct_bf16(_ptr(g), g.shape[-1], g_c_off, cout, _ptr(a), a.shape[-1], a_c_off, cin, taps,
+                                           b, h, w, _ptr(partial), splits, _stream()))
+    return partial
+
+
 def wgrad_reduce(partial, splits, taps, cout, cin, scale, dw, stride_co, stride_ci, stride_tap, ci_off=0,
                  accumulate=False):
     check(_lib.lib().csd_wgrad_reduce_f32(_ptr(partial), splits, taps, cout, cin, float(scale), _ptr(dw), stride_co,

@@ -175,3 +175,19 @@ def to_flattened_numpy(x):
 
 def from_flattened_numpy(x, shape):
     return torch.from_numpy(x.reshape(shape))
+
+
+def load_lightning_checkpoint(model, path_or_state, ema=False, strict=True):
+    """Load a checkpoint written by the reference's Lightning modules into an engine-backed network.
+
+    The reference saves `pl_module.state_dict()`, whose score-network entries are keyed `score_model.all_modules.<i>...`
+    (lightning_modules/BaseSdeGenerativeModel.py:22-23), next to `hyper_parameters`. `path_or_state` is a checkpoint
+    path, the loaded checkpoint dict, or a bare state dict; the `score_model.` prefix is stripped and the rest loaded
+    with the reference's own key names (the positional `all_modules` order is identical here). Returns the
+    (missing, unexpected) keys of load_state_dict."""
+    ckpt = torch.load(path_or_state, map_location="cpu", weights_only=False) if isinstance(path_or_state, str) else path_or_state
+    state = ckpt.get("state_dict", ckpt) if isinstance(ckpt, dict) else ckpt
+    prefix = "score_model."
+    if any(k.startswith(prefix) for k in state):
+        state = {k[len(prefix):]: v for k, v in state.items() if k.startswith(prefix)}
+    return model.load_state_dict(state, strict=strict)

@@ -329,6 +329,15 @@ int csd_nhwc_to_pixmajor_bf16(const void* src, int pitch, int c_off, int c_cnt, 
 int csd_wgrad_gemm_bf16(const void* g_pm, int cout, const void* a_pm, int cin, int taps, const csd_pixmajor_geom* g,
                         float* partial, csd_stream_t stream);
 
+/* The same partial sums straight from the NHWC tensors (no pixel-major copies): g [batch, h, w, g_pitch] is the output
+ * gradient ON THE ACTIVATION GRID (the zero-stuffed gradient for stride-2 convolutions), a [batch, h, w, a_pitch] the
+ * activation; channels [g_c_off, +cout) x [a_c_off, +cin). MN-major tcgen05 operands, one TMA halo load feeds the three
+ * kx taps of a CTA. Needs >= 64-channel pitches (narrower tensors use the pixel-major path). `splits` must be the value
+ * csd_wgrad_direct_splits returns for the same shape: partial is [splits][taps][cout][cin].                      */
+int csd_wgrad_direct_splits(int batch, int h, int w, int cout, int cin, int taps, int* splits);
+int csd_wgrad_direct_bf16(const void* g, int g_pitch, int g_c_off, int cout, const void* a, int a_pitch, int a_c_off,
+                          int cin, int taps, int batch, int h, int w, float* partial, int splits, csd_stream_t stream);
+
 /* dw[co*stride_co + (ci_off+ci)*stride_ci + tap*stride_tap] (+)= scale * sum_split partial[split][tap][co][ci]
  * (fixed summation order). nn.Conv2d weight [Cout, Cin, 3, 3]: strides (Cin*9, 9, 1); NIN.W [in, out]: (1, out, 0). */
 int csd_wgrad_reduce_f32(const float* partial, int splits, int taps, int cout, int cin, float scale, float* dw,

@@ -355,3 +355,41 @@ def test_time_features_match_fused_embedding():
         k.sgemm_small(0, 1, b, 4 * nf, 4 * nf, h0, 4 * nf, w1, 4 * nf, t, 4 * nf, bias=b1)
         k.silu_f32(t, t)
         _close(t, fused, 1e-5, f"time embedding decomposition {et}")
+
+
+def _wgrad_direct(a, g, taps, scale=1.0, a_pitch=None, g_pitch=None):
+    """Direct (MN-major) path: a [B,Cin,H,W], g [B,Cout,H,W] on the same grid."""
+    k = K()
+    b, cin, h, w = a.shape
+    cout = g.shape[1]
+    an, gn = _nhwc(a, a_pitch), _nhwc(g, g_pitch)
+    splits = k.wgrad_direct_splits(b, h, w, cout, cin, taps)
+    partial = torch.full((splits, taps, cout, cin), float("nan"), device="cuda")
+    k.wgrad_direct(gn, 0, cout, an, 0, cin, taps, partial, splits)
+    kk = 3 if taps == 9 else 1
+    dw = torch.zeros(cout, cin, kk, kk, device="cuda")
+    k.wgrad_reduce(partial, splits, taps, cout, cin, scale, dw, cin * taps, taps, 1)
+    return dw
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 16, 16), (3, 96, 96, 16, 24), (2, 128, 128, 32, 32), (2, 192, 96, 40, 40),
+                                   (2, 256, 288, 10, 12), (1, 72, 136, 9, 21), (2, 320, 64, 16, 16)])
+def test_wgrad_direct_3x3(shape):
+    b, cin, cout, h, w = shape
+    g_ = torch.Generator().manual_seed(sum(shape) + 1)
+    a = _rt(torch.randn(b, cin, h, w, generator=g_))
+    g = _rt(torch.randn(b, cout, h, w, generator=g_))
+    _close(_wgrad_direct(a, g, 9), _wgrad_ref(a, g, 3, 1, 1), 2.0 ** -8, f"wgrad direct 3x3 {shape}")
+
+
+def test_wgrad_direct_1x1_pitch_and_known_answer():
+    g_ = torch.Generator().manual_seed(9)
+    a = _rt(torch.randn(3, 72, 12, 20, generator=g_))
+    g = _rt(torch.randn(3, 104, 12, 20, generator=g_))
+    _close(_wgrad_direct(a, g, 1, scale=0.5, a_pitch=80, g_pitch=112), 0.5 * _wgrad_ref(a, g, 1, 1, 0), 2.0 ** -8,
+           "wgrad direct 1x1")
+    b, c, h, w = 4, 96, 160, 160
+    dw = _wgrad_direct(torch.ones(b, c, h, w), torch.ones(b, c, h, w), 9).cpu()
+    assert torch.all(dw[:, :, 1, 1] == b * h * w)
+    assert torch.all(dw[:, :, 0, 0] == b * (h - 1) * (w - 1))
+    assert torch.all(dw[:, :, 2, 1] == b * (h - 1) * w)

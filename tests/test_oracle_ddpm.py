@@ -95,3 +95,16 @@ def test_training_loss_has_no_cpu_fallback():
     fn = losses.get_general_sde_loss_fn(sde_lib.cVESDE(5e-3, 27.7, 1000), train=True, conditional=True)
     with pytest.raises(CsdError):
         fn(None, (torch.zeros(1, 3, 4, 4), torch.zeros(1, 3, 4, 4)))
+
+
+def test_lightning_checkpoint_keys_load():
+    """A Lightning checkpoint of the reference ({'state_dict': {'score_model.all_modules...': ...}}) loads unchanged."""
+    fx, sd, _ = ddpm_golden()
+    from conditional_score_diffusion_b200.models import ddpm, utils  # noqa: F401
+    model = utils.create_model(to_namespace(fx["ddpm_paired"]["config"]))
+    ckpt = {"state_dict": {"score_model." + k: v for k, v in sd.items()}, "hyper_parameters": {"config": None},
+            "epoch": 3}
+    missing, unexpected = utils.load_lightning_checkpoint(model, ckpt)
+    assert not missing and not unexpected
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k])
