@@ -393,3 +393,19 @@ def test_wgrad_direct_1x1_pitch_and_known_answer():
     assert torch.all(dw[:, :, 1, 1] == b * h * w)
     assert torch.all(dw[:, :, 0, 0] == b * (h - 1) * (w - 1))
     assert torch.all(dw[:, :, 2, 1] == b * (h - 1) * w)
+
+
+def test_wgrad_direct_cluster_multicast_variant():
+    """The opt-in 3-CTA cluster / TMA-multicast variant (CSD_WGRAD_CLUSTER=1) computes the same weight gradient."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys; sys.path.insert(0, 'tests'); import test_gpu_backward_ops as t;"
+        "g_ = torch.Generator().manual_seed(3);"
+        "a = t._rt(torch.randn(2, 128, 32, 32, generator=g_)); g = t._rt(torch.randn(2, 128, 32, 32, generator=g_));"
+        "t._close(t._wgrad_direct(a, g, 9), t._wgrad_ref(a, g, 3, 1, 1), 2.0 ** -8, 'cluster variant'); print('CLUSTER_OK')")
+    env = dict(os.environ, CSD_WGRAD_CLUSTER="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert "CLUSTER_OK" in r.stdout, r.stdout + r.stderr
