@@ -53,7 +53,30 @@ __global__ void gn_bwd_stats_kernel(GnBwdStatsParams p) {
       const float2 c = p.coef[(long long)b * C + v * 8 + i];
       sc[i] = c.x; sh[i] = c.y;
     }
-    for (long long pix = lo + pp; pix < hi; pix += ppb) {
+    constexpr int U = 1;   // measured: 2 or 4 loads in flight cost more in registers / occupancy than they hide here
+    long long pix = lo + pp;
+    for (; pix + (long long)(U - 1) * ppb < hi; pix += (long long)U * ppb) {
+      bf16x8 vx[U], vd[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long bp = (long long)b * p.hw + pix + (long long)u * ppb;
+        vx[u] = p.x[bp * p.xpv + v];
+        vd[u] = p.dy[bp * p.dy_pv + p.dy_voff + v];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float fx[8], fd[8];
+        unpack8(vx[u], fx);
+        unpack8(vd[u], fd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float du = p.silu ? fd[i] * silu_grad(fmaf(fx[i], sc[i], sh[i])) : fd[i];
+          s1[i] += du;
+          s2[i] = fmaf(du, fx[i], s2[i]);
+        }
+      }
+    }
+    for (; pix < hi; pix += ppb) {
       float fx[8], fd[8];
       unpack8(p.x[((long long)b * p.hw + pix) * p.xpv + v], fx);
       unpack8(p.dy[((long long)b * p.hw + pix) * p.dy_pv + p.dy_voff + v], fd);
@@ -181,7 +204,37 @@ __global__ void gn_bwd_apply_kernel(GnBwdApplyParams p) {
     const float4 bc = p.bcoef[(long long)b * p.c_total + p.b_coff + v * 8 + i];
     sc[i] = fc.x; sh[i] = fc.y; ca[i] = bc.x; cb[i] = bc.y; cc[i] = bc.z;
   }
-  for (long long pix = lo + pp; pix < hi; pix += ppb) {
+  constexpr int U = 4;   // independent 16-byte loads in flight per tensor (the kernel is latency-bound otherwise)
+  long long pix = lo + pp;
+  for (; pix + (long long)(U - 1) * ppb < hi; pix += (long long)U * ppb) {
+    bf16x8 vx[U], vd[U], vo[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long bp = (long long)b * p.hw + pix + (long long)u * ppb;
+      vx[u] = p.x[bp * p.xpv + v];
+      vd[u] = p.dy[bp * p.dy_pv + p.dy_voff + v];
+      if (p.accumulate) vo[u] = p.dx[bp * p.dx_pv + v];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long bp = (long long)b * p.hw + pix + (long long)u * ppb;
+      float fx[8], fd[8], o[8];
+      unpack8(vx[u], fx);
+      unpack8(vd[u], fd);
+      if (p.accumulate) unpack8(vo[u], o);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float du = p.silu ? fd[i] * silu_grad(fmaf(fx[i], sc[i], sh[i])) : fd[i];
+        o[i] += fmaf(ca[i], du, fmaf(cb[i], fx[i], cc[i]));
+      }
+      p.dx[bp * p.dx_pv + v] = pack8(o);
+    }
+  }
+  for (; pix < hi; pix += ppb) {
     const long long bp = (long long)b * p.hw + pix;
     float fx[8], fd[8], o[8];
     unpack8(p.x[bp * p.xpv + v], fx);
@@ -434,6 +487,33 @@ sgemm_small_kernel(int ta, int tb, int m, int n, int k, float alpha, const float
   }
 }
 
+// Long-K variant: one warp per output element, lanes stride over k (the d act_temb = dtproj @ W contraction has
+// K = sum of all Dense_0 widths ~ 5-16 k and only batch x 4nf outputs: a thread-per-output loop would be one long
+// dependent chain).
+__global__ void __launch_bounds__(256)
+sgemm_longk_kernel(int ta, int tb, int m, int n, int k, float alpha, const float* __restrict__ a, int lda,
+                   const float* __restrict__ b, int ldb, float beta, float* c, int ldc, const float* __restrict__ bias) {
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)m * n;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; idx < total; idx += warps) {
+    const int col = (int)(idx % n), row = (int)(idx / n);
+    float acc = 0.f;
+    for (int kk = lane; kk < k; kk += 32) {
+      const float av = ta ? a[(long long)kk * lda + row] : a[(long long)row * lda + kk];
+      const float bv = tb ? b[(long long)col * ldb + kk] : b[(long long)kk * ldb + col];
+      acc = fmaf(av, bv, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float r = alpha * acc;
+      if (beta != 0.f) r = fmaf(beta, c[(long long)row * ldc + col], r);
+      if (bias != nullptr) r += bias[col];
+      c[(long long)row * ldc + col] = r;
+    }
+  }
+}
+
 // y = silu(x) (grad == 0) or y = dy * silu'(x) (grad == 1), full-precision exp like the forward time-embedding kernel
 __global__ void __launch_bounds__(256)
 silu_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ y, long long n, int grad) {
@@ -668,6 +748,12 @@ int csd_sgemm_small_f32(int trans_a, int trans_b, int m, int n, int k, float alp
                         const float* b, int ldb, float beta, float* c, int ldc, const float* bias, csd_stream_t stream) {
   using namespace csd;
   CSD_REQUIRE(a && b && c && m >= 1 && n >= 1 && k >= 1, "sgemm_small: bad arguments");
+  if (k >= 512 && (long long)m * n <= (1 << 17)) {
+    sgemm_longk_kernel<<<flat_blocks((long long)m * n * 32, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        trans_a, trans_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, bias);
+    CSD_LAUNCH_CHECK("sgemm_longk_kernel");
+    return CSD_OK;
+  }
   sgemm_small_kernel<<<flat_blocks((long long)m * n, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       trans_a, trans_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, bias);
   CSD_LAUNCH_CHECK("sgemm_small_kernel");

@@ -466,15 +466,22 @@ class TrainPlan(NetPlan):
         embed = info["emb"].shape[1]
         f32 = dict(device=self.eng.device, dtype=torch.float32)
         ones = torch.ones(1, b, **f32)
-        off = 0
+        total = sum(d.weight.shape[0] for d in info["dense_mods"])
+        # every block's Dense_0 gradient in two GEMMs over the concatenated projection (dWcat = dt^T act, dbcat = colsum dt),
+        # then one batched scatter (csd_pack_weights fp32 jobs) into the per-block parameter gradients
+        dwcat = torch.empty(total, hid, **f32)
+        dbcat = torch.empty(total, **f32)
+        bwd.add(K.sgemm_small, 1, 0, total, hid, b, dt, tpitch, info["act"], hid, dwcat, hid)
+        bwd.add(K.sgemm_small, 0, 0, 1, total, b, ones, b, dt, tpitch, dbcat, total)
+        jobs, off = [], 0
         for d in info["dense_mods"]:
             n = d.weight.shape[0]
-            # dW[n, hid] += dt[:, off:off+n]^T @ act ; db[n] += colsum(dt[:, off:off+n])
-            bwd.add(K.sgemm_small, 1, 0, n, hid, b, dt[:, off:], tpitch, info["act"], hid, self.pgrad(d.weight), hid,
-                    beta=1.0)
-            bwd.add(K.sgemm_small, 0, 0, 1, n, b, ones, b, dt[:, off:], tpitch, self.pgrad(d.bias), n, beta=1.0)
+            gw, gb = self.pgrad(d.weight), self.pgrad(d.bias)
+            jobs.append(K.bias_job(gw, 0, dwcat[off:off + n], gw))       # gw += dwcat rows (kind 1: dst = src + src2)
+            jobs.append(K.bias_job(gb, 0, dbcat[off:off + n], gb))
             off += n
-        total = off
+        self.dense_scatter = K.PackTable(jobs, self.eng.device)
+        bwd.add(self.dense_scatter.run)
         dact = torch.empty(b, hid, **f32)
         bwd.add(K.sgemm_small, 0, 0, b, hid, total, dt, tpitch, info["dense_w"], hid, dact, hid)
         dtpre = torch.empty(b, hid, **f32)

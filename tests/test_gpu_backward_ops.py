@@ -409,3 +409,18 @@ def test_wgrad_direct_cluster_multicast_variant():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert "CLUSTER_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_sgemm_long_k_variant():
+    k = K()
+    g_ = torch.Generator().manual_seed(15)
+    m, n, kk = 50, 96, 3000
+    A = torch.randn(m, kk, generator=g_)
+    B = torch.randn(kk, n, generator=g_)
+    C = torch.zeros(m, n, device="cuda")
+    k.sgemm_small(0, 0, m, n, kk, A.cuda(), kk, B.cuda(), n, C, n)
+    _close(C, A @ B, 1e-5, "sgemm long-K")
+    Bt = torch.randn(n, kk, generator=g_)
+    bias = torch.randn(n, generator=g_)
+    k.sgemm_small(0, 1, m, n, kk, A.cuda(), kk, Bt.cuda(), kk, C, n, alpha=0.5, beta=1.0, bias=bias.cuda())
+    _close(C, A @ B + 0.5 * A @ Bt.t() + bias, 1e-5, "sgemm long-K transposed, beta, bias")
