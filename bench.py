@@ -298,8 +298,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"    # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings go to stderr: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg = workload_config()
     B, K_steps, W = BATCH_PER_GPU, args.steps, max(args.warmup, 3)
@@ -534,8 +533,7 @@ def run_train(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     model = utils.create_model(cfg).to(dev).train()
