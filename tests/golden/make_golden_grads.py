@@ -144,6 +144,25 @@ def main():
                          "evolution_y": info_p["evolution"]["y"].clone(), "seed": 506, "snr": 0.15, "p_steps": 3,
                          "sigma_min": 5e-3, "sigma_max_x": smax, "sigma_max_y": 0.5, "eps": 1e-5}
 
+    # ---- legacy discrete losses (losses.py:55-85 SMLD, :320-340 DDPM), evaluation mode, on the unconditional network ----
+    vesde = sde_lib.VESDE(sigma_min=0.01, sigma_max=50, N=1000)
+    vpsde = sde_lib.VPSDE(beta_min=0.1, beta_max=20, N=1000)
+    leg = {"x": xb}
+    for rm in (False, True):
+        torch.manual_seed(507)
+        with torch.no_grad():
+            leg[f"smld_rm{int(rm)}"] = ref_losses.get_smld_loss_fn(vesde, train=False, reduce_mean=rm)(model, xb).clone()
+        torch.manual_seed(508)
+        with torch.no_grad():
+            leg[f"ddpm_rm{int(rm)}"] = ref_losses.get_ddpm_loss_fn(vpsde, train=False, reduce_mean=rm)(model, xb).clone()
+    torch.manual_seed(507)
+    leg["smld_labels"] = torch.randint(0, 1000, (B,))
+    leg["smld_z"] = torch.randn_like(xb)
+    torch.manual_seed(508)
+    leg["ddpm_labels"] = torch.randint(0, 1000, (B,))
+    leg["ddpm_z"] = torch.randn_like(xb)
+    fx["legacy_losses"] = leg
+
     # ---- SR3 on ddpm_paired_SR3 ----
     rec = base_ddpm["ddpm_paired"]
     sd_paired = {k: v.float() for k, v in rec["state_dict_bf16"].items()}
