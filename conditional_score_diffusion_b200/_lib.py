@@ -129,6 +129,9 @@ _PROTOTYPES = {
                                        c_void_p, c_void_p, c_void_p]),
     "csd_dense_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "csd_conv_gemm": (c_int, [ctypes.POINTER(ConvGemmDesc), c_void_p]),
+    "csd_rk_combine_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float_p, c_float, c_void_p, c_void_p]),
+    "csd_rk_error_sumsq_f32": (c_int, [c_void_p, c_int64, c_int, c_float_p, c_float, c_void_p, c_void_p, c_float, c_float,
+                                       c_void_p, c_void_p]),
     "csd_sumsq_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "csd_fused_adam_ema_f32": (c_int, [c_void_p] * 5 + [c_int64] + [c_float] * 8 + [c_void_p, c_float, c_void_p]),
     "csd_pack_weights": (c_int, [c_void_p, c_int, c_int64, c_void_p]),

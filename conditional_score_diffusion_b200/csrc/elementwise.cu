@@ -241,6 +241,43 @@ inpaint_merge_kernel(const float* x, const float* __restrict__ data, const float
   }
 }
 
+// ---- device-resident Runge-Kutta pieces (probability-flow ODE sampler / likelihood) ------------
+// k is a stack of stage derivatives [stages, n]; out = y + h * sum_i coef[i] * k[i] for i < ns.
+struct RkCoefs { float c[8]; };
+
+__global__ void __launch_bounds__(256)
+rk_combine_kernel(const float* __restrict__ y, const float* __restrict__ k, long long n, int ns, RkCoefs coef, float h,
+                  float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < ns; ++s) acc = fmaf(coef.c[s], k[(long long)s * n + i], acc);
+    out[i] = fmaf(h, acc, y[i]);
+  }
+}
+
+// out[0] += sum_i ( h * sum_s e[s] k[s][i] / (atol + max(|y_i|, |y2_i|) * rtol) )^2
+__global__ void __launch_bounds__(256)
+rk_error_sumsq_kernel(const float* __restrict__ k, long long n, int ns, RkCoefs e, float h, const float* __restrict__ y,
+                      const float* __restrict__ y2, float atol, float rtol, float* out) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float err = 0.f;
+    for (int s = 0; s < ns; ++s) err = fmaf(e.c[s], k[(long long)s * n + i], err);
+    const float sc = fmaf(fmaxf(fabsf(y[i]), fabsf(y2[i])), rtol, atol);
+    const float r = h * err / sc;
+    acc = fmaf(r, r, acc);
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out, t);
+  }
+}
+
 // ---- fused optimizer step over the flat parameter buffer --------------------------------------------------------
 // out[0] += sum x^2 (block partials combined with one atomic per block).
 __global__ void __launch_bounds__(256) sumsq_f32_kernel(const float* __restrict__ x, long long n, float* out) {
@@ -350,6 +387,30 @@ int csd_sde_perturb_f32(const float* x, const float* z, float* out, int batch, i
   else
     sde_perturb_kernel<1><<<ps_grid(batch, per_sample, 1), 256, 0, st>>>(x, z, out, per_sample, mean_coef, std_dev);
   CSD_LAUNCH_CHECK("sde_perturb_kernel");
+  return CSD_OK;
+}
+
+int csd_rk_combine_f32(const float* y, const float* k_stack, int64_t n, int stages, const float* coef_host, float h,
+                       float* out, csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(y && k_stack && out && coef_host && n >= 1 && stages >= 1 && stages <= 8, "rk_combine: bad arguments");
+  RkCoefs c;
+  for (int i = 0; i < 8; ++i) c.c[i] = i < stages ? coef_host[i] : 0.f;
+  rk_combine_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, k_stack, n, stages, c, h, out);
+  CSD_LAUNCH_CHECK("rk_combine_kernel");
+  return CSD_OK;
+}
+
+int csd_rk_error_sumsq_f32(const float* k_stack, int64_t n, int stages, const float* e_host, float h, const float* y,
+                           const float* y2, float atol, float rtol, float* out, csd_stream_t stream_) {
+  using namespace csd;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CSD_REQUIRE(k_stack && y && y2 && out && e_host && n >= 1 && stages >= 1 && stages <= 8, "rk_error_sumsq: bad arguments");
+  RkCoefs e;
+  for (int i = 0; i < 8; ++i) e.c[i] = i < stages ? e_host[i] : 0.f;
+  CSD_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
+  rk_error_sumsq_kernel<<<ew_blocks(n), 256, 0, stream>>>(k_stack, n, stages, e, h, y, y2, atol, rtol, out);
+  CSD_LAUNCH_CHECK("rk_error_sumsq_kernel");
   return CSD_OK;
 }
 

@@ -378,6 +378,21 @@ def dense_rows(act, w, bias, out, total_out=None):
     return out
 
 
+def rk_combine(y, k_stack, stages, coefs, h, out):
+    _require_cuda(y, k_stack, out)
+    arr = (ctypes.c_float * stages)(*[float(c) for c in coefs[:stages]])
+    check(_lib.lib().csd_rk_combine_f32(_ptr(y), _ptr(k_stack), y.numel(), stages, arr, float(h), _ptr(out), _stream()))
+    return out
+
+
+def rk_error_sumsq(k_stack, stages, e, h, y, y2, atol, rtol, out):
+    _require_cuda(y, y2, k_stack, out)
+    arr = (ctypes.c_float * stages)(*[float(c) for c in e[:stages]])
+    check(_lib.lib().csd_rk_error_sumsq_f32(_ptr(k_stack), y.numel(), stages, arr, float(h), _ptr(y), _ptr(y2), float(atol),
+                                            float(rtol), _ptr(out), _stream()))
+    return out
+
+
 def sumsq(x, out):
     check(_lib.lib().csd_sumsq_f32(_ptr(x), x.numel(), _ptr(out), _stream()))
     return out

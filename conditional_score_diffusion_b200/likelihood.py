@@ -30,8 +30,10 @@ def get_div_fn(fn):
     return div_fn
 
 
-def get_likelihood_fn(sde, inverse_scaler, hutchinson_type="Rademacher", rtol=1e-5, atol=1e-5, method="RK45", eps=1e-5):
-    """likelihood.py:40-113. Returns likelihood_fn(model, data) -> (bpd [B], z, nfe)."""
+def get_likelihood_fn(sde, inverse_scaler, hutchinson_type="Rademacher", rtol=1e-5, atol=1e-5, method="RK45", eps=1e-5,
+                      device_integrator=True):
+    """likelihood.py:40-113. Returns likelihood_fn(model, data) -> (bpd [B], z, nfe). method='RK45' on CUDA data runs
+    `ode.solve_rk45` (scipy's RK45 restated with the state resident in HBM) unless device_integrator=False."""
 
     def drift_fn(model, x, t):
         score_fn = mutils.get_score_fn(sde, model, train=False, continuous=True)
@@ -71,12 +73,29 @@ def get_likelihood_fn(sde, inverse_scaler, hutchinson_type="Rademacher", rtol=1e
                 drift, logp_grad = drift_and_div(model, sample, vec_t, noise)
                 return np.concatenate([mutils.to_flattened_numpy(drift), mutils.to_flattened_numpy(logp_grad)], axis=0)
 
-            init = np.concatenate([mutils.to_flattened_numpy(data), np.zeros((shape[0],))], axis=0)
-            solution = integrate.solve_ivp(ode_func, (eps, sde.T), init, rtol=rtol, atol=atol, method=method)
-            nfe = solution.nfev
-            zp = solution.y[:, -1]
-            z = mutils.from_flattened_numpy(zp[:-shape[0]], shape).to(data.device).type(torch.float32)
-            delta_logp = mutils.from_flattened_numpy(zp[-shape[0]:], (shape[0],)).to(data.device).type(torch.float32)
+            if device_integrator and method == "RK45" and data.is_cuda:
+                from . import ode
+                n = data.numel()
+                out = torch.empty(n + shape[0], device=data.device, dtype=torch.float32)
+
+                def rhs(t, yflat):
+                    vec_t = torch.ones(shape[0], device=data.device) * t
+                    drift, logp_grad = drift_and_div(model, yflat[:n].view(shape), vec_t, noise)
+                    out[:n].copy_(drift.reshape(-1))
+                    out[n:].copy_(logp_grad)
+                    return out
+
+                y0 = torch.cat([data.reshape(-1).float(), torch.zeros(shape[0], device=data.device)])
+                yT, nfe = ode.solve_rk45(rhs, float(eps), float(sde.T), y0, rtol, atol)
+                z = yT[:n].view(shape).clone()
+                delta_logp = yT[n:].clone()
+            else:
+                init = np.concatenate([mutils.to_flattened_numpy(data), np.zeros((shape[0],))], axis=0)
+                solution = integrate.solve_ivp(ode_func, (eps, sde.T), init, rtol=rtol, atol=atol, method=method)
+                nfe = solution.nfev
+                zp = solution.y[:, -1]
+                z = mutils.from_flattened_numpy(zp[:-shape[0]], shape).to(data.device).type(torch.float32)
+                delta_logp = mutils.from_flattened_numpy(zp[-shape[0]:], (shape[0],)).to(data.device).type(torch.float32)
             prior_logp = sde.prior_logp(z)
             bpd = -(prior_logp + delta_logp) / np.log(2)
             bpd = bpd / np.prod(shape[1:])

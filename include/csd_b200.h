@@ -263,6 +263,18 @@ typedef struct csd_conv_gemm_desc {
 
 int csd_conv_gemm(const csd_conv_gemm_desc* desc, csd_stream_t stream);
 
+/* ---- device-resident adaptive Runge-Kutta pieces ---------------------------------------------
+ * The reference integrates the probability-flow ODE with scipy's RK45 on the host: the full state crosses PCIe twice
+ * per right-hand side (likelihood.py:91-99, sampling/unconditional.py:140-150). With these two kernels the state and
+ * the stage derivatives stay in HBM; only the 4-byte error norm returns to the host for step-size control.
+ * k_stack is [stages, n] fp32; coefficient vectors are HOST arrays of `stages` floats (stages <= 8).            */
+/* out = y + h * sum_s coef[s] * k_stack[s]                                                                     */
+int csd_rk_combine_f32(const float* y, const float* k_stack, int64_t n, int stages, const float* coef_host, float h,
+                       float* out, csd_stream_t stream);
+/* out[0] = sum_i (h * sum_s e[s] k_stack[s][i] / (atol + max(|y_i|, |y2_i|) * rtol))^2 (device scalar)          */
+int csd_rk_error_sumsq_f32(const float* k_stack, int64_t n, int stages, const float* e_host, float h, const float* y,
+                           const float* y2, float atol, float rtol, float* out, csd_stream_t stream);
+
 /* ---- fused optimizer step ----------------------------------------------------------------
  * The reference runs torch.nn.utils.clip_grad_norm_ + optim.Adam.step (losses.py:38-52) and then
  * ExponentialMovingAverage.update (models/ema.py:64-93: a Python loop of 3 kernels per parameter tensor) after every

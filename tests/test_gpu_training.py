@@ -412,3 +412,48 @@ def test_legacy_discrete_losses_match_reference():
     with pytest.raises(NotImplementedError):
         sd = {"x": sde_lib.cVESDE(5e-3, 27.7, 1000), "y": sde_lib.VESDE(5e-3, 0.5, 1000)}
         losses.get_inverse_problem_smld_loss_fn(sd, train=False)(m, (x, x))
+
+
+def test_device_rk45_matches_scipy_rk45():
+    """ode.solve_rk45 (state resident in HBM) against scipy.integrate.solve_ivp(method='RK45') on the same right-hand
+    sides: (a) the closed-form Gaussian-score flow (tests/test_likelihood_cpu.py) - same step sequence (nfev) and the
+    same answer to 1e-4; (b) the engine-backed network - same bits/dim to 1e-2 relative."""
+    import math
+    from conditional_score_diffusion_b200 import likelihood, sde_lib
+    from conditional_score_diffusion_b200.sampling import unconditional
+    from test_likelihood_cpu import GaussianScore
+    s, shape = 1.5, (4, 1, 8, 8)
+    sde = sde_lib.VESDE(0.01, 50, 1000)
+    torch.manual_seed(1)
+    z = (torch.randn(*shape) * math.sqrt(s ** 2 + 50 ** 2)).cuda()
+    model = GaussianScore(s).cuda()
+    outs = {}
+    for dev_int in (True, False):
+        sampler = unconditional.get_ode_sampler(sde, shape, denoise=True, rtol=1e-5, atol=1e-5, eps=1e-3,
+                                                device_integrator=dev_int)
+        outs[dev_int] = sampler(model, z=z.clone())
+    (xd, nd), (xs, ns) = outs[True], outs[False]
+    print(f"[rk45] gaussian flow: device nfe {nd}, scipy nfe {ns}, max diff {(xd - xs).abs().max().item():.3e}")
+    assert abs(nd - ns) <= 12
+    assert torch.allclose(xd, xs, rtol=1e-4, atol=1e-4)
+    expect = z * math.sqrt((s ** 2 + (0.01 * 5000 ** 1e-3) ** 2) / (s ** 2 + 50 ** 2))
+    assert torch.allclose(xd, expect, rtol=3e-3, atol=3e-3)
+    # likelihood of the Gaussian: closed form
+    data = (torch.randn(3, 2, 4, 4) * s).cuda()
+    bpd, _, nfe = likelihood.get_likelihood_fn(sde, lambda v: v, rtol=1e-6, atol=1e-6, eps=1e-5)(model, data)
+    n = 32
+    var0 = s ** 2 + (0.01 * (50 / 0.01) ** 1e-5) ** 2
+    logp = -0.5 * n * math.log(2 * math.pi * var0) - data.pow(2).sum(dim=(1, 2, 3)) / (2 * var0)
+    assert torch.allclose(bpd, (-logp / math.log(2) / n + 8.0), atol=5e-3), (bpd, -logp / math.log(2) / n + 8.0)
+    # engine network: device integrator vs scipy on the same model
+    gl = grads_golden()["likelihood"]
+    m = _ncsnpp("cifar").eval()
+    res = {}
+    for dev_int in (True, False):
+        fn = likelihood.get_likelihood_fn(sde, lambda v: (v + 1.0) / 2.0, rtol=gl["rtol"], atol=gl["atol"], eps=gl["eps"],
+                                          device_integrator=dev_int)
+        res[dev_int] = fn(m, gl["x"].cuda(), epsilon=gl["epsilon"])
+    print(f"[rk45] engine likelihood: device bpd {res[True][0].tolist()} nfe {res[True][2]}, scipy bpd {res[False][0].tolist()} "
+          f"nfe {res[False][2]}, reference {gl['bpd'].tolist()} nfe {gl['nfe']}")
+    assert (res[True][0] - res[False][0]).abs().max().item() <= 1e-2 * res[False][0].abs().max().item()
+    assert (res[True][0].cpu() - gl["bpd"]).abs().max().item() <= 2e-2 * gl["bpd"].abs().max().item()
