@@ -57,6 +57,27 @@ def workload_config(image=IMAGE, nf=96, ch_mult=(1, 1, 2, 2, 3, 3), attn=(20, 10
     )
 
 
+_SAVED_STDOUT = []
+
+
+def quiet_stdout():
+    """Point file descriptor 1 at stderr until emit() restores it: native libraries (NCCL's version banner) then cannot
+    put extra lines in front of the one JSON line the driver parses."""
+    if not _SAVED_STDOUT:
+        sys.stdout.flush()
+        _SAVED_STDOUT.append(os.dup(1))
+        os.dup2(2, 1)
+
+
+def emit(line):
+    """Print the result line on the real stdout."""
+    sys.stdout.flush()
+    if _SAVED_STDOUT:
+        os.dup2(_SAVED_STDOUT.pop(), 1)
+    print(json.dumps(line))
+    sys.stdout.flush()
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -298,7 +319,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings go to stderr: stdout carries ONE JSON line
+        quiet_stdout()      # NCCL prints its version banner on stdout at the first collective: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg = workload_config()
     B, K_steps, W = BATCH_PER_GPU, args.steps, max(args.warmup, 3)
@@ -444,7 +465,7 @@ def run_b200(args):
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info,
         "plan_buffers_gb": fs.plan.pool.nbytes() / 1e9,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -533,7 +554,7 @@ def run_train(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        quiet_stdout()
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     model = utils.create_model(cfg).to(dev).train()
@@ -619,7 +640,7 @@ def run_train(args):
             "gpu_launches": launches_per_step * K_steps, "launches_per_step": launches_per_step,
             "clocks": ck, "peaks": peaks,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
