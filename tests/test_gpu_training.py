@@ -457,3 +457,29 @@ def test_device_rk45_matches_scipy_rk45():
           f"nfe {res[False][2]}, reference {gl['bpd'].tolist()} nfe {gl['nfe']}")
     assert (res[True][0] - res[False][0]).abs().max().item() <= 1e-2 * res[False][0].abs().max().item()
     assert (res[True][0].cpu() - gl["bpd"]).abs().max().item() <= 2e-2 * gl["bpd"].abs().max().item()
+
+
+def test_input_and_parameter_gradients_together_and_stale_graph_error():
+    """likelihood.get_div_fn's own call pattern (parameters still require grad while the input gradient is taken,
+    likelihood.py:26-37): the plan computes both; and evaluating the network again before backward() is an error, not a
+    silently wrong gradient (the plan's stored activations would have been overwritten)."""
+    from conditional_score_diffusion_b200 import likelihood, sde_lib
+    from conditional_score_diffusion_b200.models import utils as mutils
+    g = grads_golden()["uncond"]
+    m = _ncsnpp("cifar").eval()
+    sde = sde_lib.VESDE(g["sigma_min"], g["sigma_max"], 1000)
+    score_fn = mutils.get_score_fn(sde, m, conditional=False, train=False, continuous=True)
+    x = g["div_x"].cuda()
+    div = likelihood.get_div_fn(lambda xx, tt: score_fn(xx, tt))(x, g["div_t"].cuda(), g["div_eps"].cuda())
+    ref = (g["div_grad"] * g["div_eps"]).sum(dim=(1, 2, 3))
+    rel = ((div.cpu() - ref).abs() / ref.abs()).max().item()
+    print(f"[train] Hutchinson divergence with live parameters: rel err {rel:.3e}")
+    assert rel < 5e-2 and not x.requires_grad
+    # stale graph
+    xs = g["div_x"].cuda().requires_grad_(True)
+    s1 = score_fn(xs, g["div_t"].cuda())
+    s2 = score_fn(xs, g["div_t"].cuda())          # same plan, second evaluation
+    with pytest.raises(RuntimeError, match="evaluated again"):
+        s1.sum().backward()
+    s2.sum().backward()                            # the latest evaluation is still differentiable
+    assert torch.isfinite(xs.grad).all()
