@@ -198,26 +198,39 @@ __device__ __forceinline__ void epilogue_rows(const ConvGemmKernelParams& p, uin
   }
 }
 
-// Built by the 128 epilogue threads while the main loop runs: s_add[i] = bias[n0+i] + temb[b, n0+i].
-// Only when every row of the tile belongs to the same image b (tile_b == 1) and the bias is per column.
-__device__ __forceinline__ const float* build_addend_table(const ConvGemmKernelParams& p, uint32_t s_add_addr, int b,
+// Built by the 128 epilogue threads while the main loop runs: s_add[bl][i] = bias[n0+i] + temb[b0+bl, n0+i] for the
+// tile's tb images (tb > 1 at the <= 8 px levels, where one 128-pixel tile spans several images). Only when the
+// bias is per column and the table fits its kAddendFloats slots.
+constexpr int kAddendFloats = 2048;
+__device__ __forceinline__ const float* build_addend_table(const ConvGemmKernelParams& p, uint32_t s_add_addr, int b0,
                                                            int n0, int et /*0..127*/) {
-  if (p.bias_per_row || (p.bias == nullptr && p.temb == nullptr)) return nullptr;
+  if (p.bias_per_row || (p.bias == nullptr && p.temb == nullptr) || p.TB * p.n_tile > kAddendFloats) return nullptr;
   float* s_add = reinterpret_cast<float*>(__cvta_shared_to_generic(s_add_addr));
-  for (int i = et; i < p.n_tile; i += 128) {
+  for (int idx = et; idx < p.TB * p.n_tile; idx += 128) {
+    const int bl = idx / p.n_tile, i = idx - bl * p.n_tile;
     float a = p.bias != nullptr ? __ldg(p.bias + n0 + i) : 0.f;
-    if (p.temb != nullptr) a += __ldg(p.temb + (long long)b * p.temb_pitch + n0 + i);
-    s_add[i] = a;
+    if (p.temb != nullptr && b0 + bl < p.B) a += __ldg(p.temb + (long long)(b0 + bl) * p.temb_pitch + n0 + i);
+    s_add[idx] = a;
   }
   asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
   return s_add;
 }
 
+// kChunk = channels per pipeline stage: 64 (128-byte rows, SWIZZLE_128B, 4 MMAs per stage) for every launch with a
+// segment wider than 32 channels, 32 (64-byte rows, SWIZZLE_64B, 2 MMAs) for the narrow ones (6-channel input conv).
+// The single issuing thread spends ~450 cycles of scalar bookkeeping per stage (measured with the loads switched off,
+// tools/tap_nodata_probe.py: the K loop takes the same time with and without data), so the stage has to carry
+// more tensor work than that; the weight K layout stays taps x ceil32(C): a 64-channel box that runs past the end
+// of a tap reads the next tap's columns against activation channels the TMA unit zero-fills.
+template <int kChunk>
 __global__ void __launch_bounds__(kTapThreads)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                  const __grid_constant__ CUtensorMap mapB, const ConvGemmKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t kARows = kTileM * kChunk * 2;                 // bytes of the A part of a stage
+  constexpr uint32_t kLayout = kChunk == 64 ? 2u : kLayoutSw64;    // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
+  constexpr uint32_t kSbo = 8u * kChunk * 2;                       // 8 rows of the swizzle atom
   // 1024-byte aligned base: the swizzle pattern is a function of the shared-memory address bits.
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + p.num_stages * p.stage_bytes;
@@ -275,29 +288,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       uint32_t stage = 0, par = 1;
       int turn = 0;
       int kcol = p.wt_k_off;  // running K column into Wt
-      const uint32_t tx_bytes = p.a_box_bytes + p.b_box_bytes * p.nsplit;
+      int issued = 0;         // perf experiment (debug_nodata): loads beyond the first ring fill can be switched off
       for (int s = 0; s < p.nseg; ++s) {
         const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
         const int taps = p.seg_taps[s];
-        for (int tap = 0; tap < taps; ++tap) {
+        const int kpad = ((p.seg_ccnt[s] + kChunkK - 1) / kChunkK) * kChunkK;   // K columns of one tap in Wt
+        for (int tap = 0; tap < taps; ++tap, kcol += kpad) {
           const int dy = (taps == 9) ? (tap / 3 - p.pad) : 0;
           const int dx = (taps == 9) ? (tap % 3 - p.pad) : 0;
           const int cw = w0 * p.stride + dx, ch = h0 * p.stride + dy;
-          for (int c = 0; c < p.seg_chunks[s]; ++c, kcol += kChunkK) {
+          for (int c = 0; c < p.seg_chunks[s]; ++c) {
             if (turn == me) {
               ptx::mbar_wait(empty_bar(stage), par);
 #ifdef CSD_ENABLE_PHASE_TIMESTAMPS
               if (p.debug_ts != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && me == 0 &&
-                  (kcol - p.wt_k_off) / kChunkK < 96)
-                p.debug_ts[64 + (kcol - p.wt_k_off) / kChunkK] = clock64();
+                  issued < 96)
+                p.debug_ts[64 + issued] = clock64();
 #endif
               const uint32_t a_dst = smem_base + stage * p.stage_bytes;
-              const uint32_t b_dst = a_dst + kAStageBytes;
-              ptx::mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-              ptx::tma_load_4d(a_dst, mapA, full_bar(stage), p.seg_coff[s] + c * kChunkK, cw, ch, b0 + z * p.a_batch_step);
-              ptx::tma_load_3d(b_dst, &mapB, full_bar(stage), kcol, n0, z);
-              if (p.nsplit > 1) ptx::tma_load_3d(b_dst + p.b_box_bytes, &mapB, full_bar(stage), kcol, n0 + p.n_sub, z);
+              const uint32_t b_dst = a_dst + kARows;
+              const int kc = kcol + c * kChunk;
+              const bool steady = p.debug_nodata != 0 && issued >= p.num_stages;
+              const bool load_a = !(steady && (p.debug_nodata & 2)), load_b = !(steady && (p.debug_nodata & 1));
+              ptx::mbar_arrive_expect_tx(full_bar(stage),
+                                         (load_a ? p.a_box_bytes : 0u) + (load_b ? p.b_box_bytes * p.nsplit : 0u));
+              if (load_a)
+                ptx::tma_load_4d(a_dst, mapA, full_bar(stage), p.seg_coff[s] + c * kChunk, cw, ch, b0 + z * p.a_batch_step);
+              if (load_b) {
+                ptx::tma_load_3d(b_dst, &mapB, full_bar(stage), kc, n0, z);
+                if (p.nsplit > 1) ptx::tma_load_3d(b_dst + p.b_box_bytes, &mapB, full_bar(stage), kc, n0 + p.n_sub, z);
+              }
             }
+            ++issued;
             if (++turn == p.producers) turn = 0;
             if (++stage == (uint32_t)p.num_stages) { stage = 0; par ^= 1u; }
           }
@@ -307,33 +329,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
+      // everything the loop needs lives in registers: the issuing thread's scalar work per stage is what bounds
+      // the small-level launches
       const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)p.n_sub);
-      const uint32_t hi = ptx::smem_desc_hi(512, kLayoutSw64);
+      const uint32_t hi = ptx::smem_desc_hi(kSbo, kLayout);
       const bool split = p.nsplit > 1;
       const uint32_t b2_off = p.b_box_bytes >> 4;
+      const uint32_t num_stages = (uint32_t)p.num_stages, stage_bytes = p.stage_bytes;
+      const uint32_t tmem_d0 = tmem_base, tmem_d1 = tmem_base + (uint32_t)p.n_sub;
       uint32_t stage = 0, par = 0, accumulate = 0;
-      bool ready = ptx::mbar_test_wait(full_bar(0), 0);
+      uint32_t a_lo = ptx::smem_desc_lo(smem_base, 16);
+      const uint32_t a_lo0 = a_lo, stage_step = stage_bytes >> 4;
+      uint32_t fbar = full_bar(0);
+      bool ready = ptx::mbar_test_wait(fbar, 0);
       for (int it = 0; it < total_iters; ++it) {
-        if (!ready) ptx::mbar_wait(full_bar(stage), par);
+        if (!ready) ptx::mbar_wait(fbar, par);
         ptx::tcgen05_fence_after();
         // look at the next stage's barrier now: the test's latency overlaps with the MMAs issued below
-        uint32_t nstage = stage + 1, npar = par;
-        if (nstage == (uint32_t)p.num_stages) { nstage = 0; npar ^= 1u; }
-        ready = (it + 1 < total_iters) && ptx::mbar_test_wait(full_bar(nstage), npar);
-        const uint32_t a_lo = ptx::smem_desc_lo(smem_base + stage * p.stage_bytes, 16);
-        const uint32_t b_lo = a_lo + (kAStageBytes >> 4);
-        ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(hi, a_lo), ptx::smem_desc_join(hi, b_lo), idesc, accumulate);
-        if (split)
-          ptx::mma_bf16_ss(tmem_base + p.n_sub, ptx::smem_desc_join(hi, a_lo), ptx::smem_desc_join(hi, b_lo + b2_off), idesc,
-                           accumulate);
-        ptx::mma_bf16_ss(tmem_base, ptx::smem_desc_join(hi, a_lo + 2), ptx::smem_desc_join(hi, b_lo + 2), idesc, 1u);
-        if (split)
-          ptx::mma_bf16_ss(tmem_base + p.n_sub, ptx::smem_desc_join(hi, a_lo + 2), ptx::smem_desc_join(hi, b_lo + b2_off + 2),
-                           idesc, 1u);
+        const uint32_t ebar = fbar + 8u * kMaxStages;
+        uint32_t nstage = stage + 1, npar = par, n_lo = a_lo + stage_step;
+        fbar += 8u;
+        if (nstage == num_stages) { nstage = 0; npar ^= 1u; n_lo = a_lo0; fbar = full_bar(0); }
+        ready = (it + 1 < total_iters) && ptx::mbar_test_wait(fbar, npar);
+        const uint32_t b_lo = a_lo + (kARows >> 4);
+#pragma unroll
+        for (int k16 = 0; k16 < kChunk / 16; ++k16) {
+          const uint32_t acc = (k16 == 0) ? accumulate : 1u;
+          ptx::mma_bf16_ss(tmem_d0, ptx::smem_desc_join(hi, a_lo + 2 * k16), ptx::smem_desc_join(hi, b_lo + 2 * k16), idesc,
+                           acc);
+          if (split)
+            ptx::mma_bf16_ss(tmem_d1, ptx::smem_desc_join(hi, a_lo + 2 * k16),
+                             ptx::smem_desc_join(hi, b_lo + b2_off + 2 * k16), idesc, acc);
+        }
         accumulate = 1u;
-        ptx::mma_commit(empty_bar(stage));  // frees the stage when the MMAs above have read it
+        ptx::mma_commit(ebar);  // frees the stage when the MMAs above have read it
         stage = nstage;
         par = npar;
+        a_lo = n_lo;
       }
       ptx::mma_commit(tmem_full_bar);       // accumulator complete
     }
@@ -348,7 +380,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const bool valid = (bl < p.TB) && (b < p.B) && (h < p.H) && (w < p.W);
     const long long pix = ((long long)b * p.H + h) * p.W + w;
 
-    const float* s_add = (p.TB == 1 && b0 < p.B) ? build_addend_table(p, s_add_addr, b0, n0, threadIdx.x - 64) : nullptr;
+    const float* s_add = build_addend_table(p, s_add_addr, b0, n0, threadIdx.x - 64);
+    if (s_add != nullptr && valid) s_add += bl * p.n_tile;
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tcgen05_fence_after();
     if (threadIdx.x == 64) CSD_TS(5);
@@ -977,6 +1010,7 @@ static int next_pow2_cols(int n) {
 
 // Host launcher shared by csd_conv_gemm and the program executor (which pre-encodes the maps).
 struct ConvGemmLaunch {
+  int tap_chunk;   // channels per stage of the per-tap kernel (32 or 64)
   CUtensorMap mapA[CSD_MAX_SEGMENTS];
   CUtensorMap mapB;
   CUtensorMap mapOut;
@@ -1048,6 +1082,14 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   p.a_batch_step = d->a_batch_step;
   p.tmem_cols = t_mode ? kTPix : next_pow2_cols(d->n_tile * mt);
 
+  // per-tap kernel: 64-channel stages unless every segment fits one 32-channel chunk (see conv_gemm_kernel)
+  int tap_chunk = kChunkK;
+  if (!halo_mode && getenv("CSD_TAP_CHUNK32") == nullptr)
+    for (int s = 0; s < d->nseg; ++s)
+      if (d->seg[s].c_cnt > kChunkK) tap_chunk = 64;
+  L->tap_chunk = tap_chunk;
+  const int tap_row_bytes = tap_chunk * 2;
+  int tap_iters = 0;
   int k_total = 0;
   int k_total_chan = 0;  // padded channels over all segments (one (scale, shift) slot each)
   for (int s = 0; s < d->nseg; ++s) {
@@ -1058,10 +1100,11 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     CSD_REQUIRE(sg.pitch % 8 == 0 && sg.c_cnt >= 1 && sg.c_off >= 0 && sg.c_off + sg.c_cnt <= sg.pitch,
                 "segment %d: bad channel range off=%d cnt=%d pitch=%d", s, sg.c_off, sg.c_cnt, sg.pitch);
     p.seg_taps[s] = sg.taps;
-    p.seg_chunks[s] = ceil_div(sg.c_cnt, kChunkK);
+    p.seg_chunks[s] = ceil_div(sg.c_cnt, halo_mode ? kChunkK : tap_chunk);
     p.seg_coff[s] = sg.c_off;
     p.seg_kbase[s] = k_total / kChunkK;
-    k_total += sg.taps * p.seg_chunks[s] * kChunkK;
+    k_total += sg.taps * ceil_div(sg.c_cnt, kChunkK) * kChunkK;
+    tap_iters += sg.taps * p.seg_chunks[s];
     CSD_REQUIRE(sg.norm == nullptr || (t_mode && sg.c_off == 0),
                 "segment %d: the fused GroupNorm prologue needs the transposed halo mode and c_off == 0", s);
     p.seg_norm[s] = sg.norm;
@@ -1076,7 +1119,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     uint64_t strides[3] = {(uint64_t)sg.pitch * 2, (uint64_t)sg.pitch * 2 * in_w,
                            (uint64_t)sg.pitch * 2 * in_w * in_h};
     // with a traversal stride s the box spans (t-1)*s+1 source elements and delivers t of them
-    uint32_t box[4] = {(uint32_t)kChunkK, (uint32_t)((p.TW - 1) * p.stride + 1),
+    uint32_t box[4] = {(uint32_t)(halo_mode ? kChunkK : tap_chunk), (uint32_t)((p.TW - 1) * p.stride + 1),
                        (uint32_t)((p.TH - 1) * p.stride + 1), (uint32_t)p.TB};
     if (halo_mode) {  // whole halo of the mt stacked tiles (a 1-tap segment needs no halo)
       const int hl = sg.taps == 9 ? 1 : 0;
@@ -1085,7 +1128,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     }
     uint32_t estr[4] = {1, (uint32_t)p.stride, (uint32_t)p.stride, 1};
     int st = encode_tensor_map(&L->mapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, sg.a, dims, strides, box,
-                               TMA_SW_64, estr);
+                               (!halo_mode && tap_chunk == 64) ? TMA_SW_128 : TMA_SW_64, estr);
     if (st != CSD_OK) return st;
   }
   for (int s = d->nseg; s < CSD_MAX_SEGMENTS; ++s) L->mapA[s] = L->mapA[0];
@@ -1097,16 +1140,16 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     const uint64_t row_bytes = (uint64_t)(d->wt_pitch > 0 ? d->wt_pitch : d->k_total) * 2;
     uint64_t strides[2] = {row_bytes, d->wt_batch_stride != 0 ? (uint64_t)d->wt_batch_stride * 2
                                                                : row_bytes * (uint64_t)d->wt_rows};
-    uint32_t box[3] = {(uint32_t)kChunkK, (uint32_t)(t_mode ? kTChan : p.n_sub), 1};
+    uint32_t box[3] = {(uint32_t)(halo_mode ? kChunkK : tap_chunk), (uint32_t)(t_mode ? kTChan : p.n_sub), 1};
     int st = encode_tensor_map(&L->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, d->wt, dims, strides, box,
-                               TMA_SW_64);
+                               (!halo_mode && tap_chunk == 64) ? TMA_SW_128 : TMA_SW_64);
     if (st != CSD_OK) return st;
   }
 
-  p.a_box_bytes = (uint32_t)(p.TW * p.TH * p.TB * kRowBytes);
-  p.b_box_bytes = (uint32_t)(p.n_sub * kRowBytes);
-  p.stage_bytes = (uint32_t)((kAStageBytes + d->n_tile * kRowBytes + 1023) & ~1023);
-  const int total_iters = k_total / kChunkK;
+  p.a_box_bytes = (uint32_t)(p.TW * p.TH * p.TB * tap_row_bytes);
+  p.b_box_bytes = (uint32_t)(p.n_sub * tap_row_bytes);
+  p.stage_bytes = (uint32_t)((kTileM * tap_row_bytes + d->n_tile * tap_row_bytes + 1023) & ~1023);
+  const int total_iters = tap_iters;
   int budget = p.tmem_cols <= 128 ? 56 * 1024 : (p.tmem_cols <= 256 ? 100 * 1024 : 200 * 1024);
   {
     // Small grids (the 5/10/20 px levels: fewer CTAs than SMs) run one CTA per SM whatever their footprint and
@@ -1117,6 +1160,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   }
   int stages = budget / (int)p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (const char* e = getenv("CSD_TAP_STAGES")) stages = std::min(stages, std::max(2, atoi(e)));   // probe only
   if (stages > total_iters) stages = total_iters;
   if (stages < 2) stages = 2;
   if (stages >= kTapProducers) {
@@ -1143,7 +1187,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   CSD_REQUIRE(d->res == nullptr || d->res_pitch % 8 == 0, "res_pitch=%d must be a multiple of 8", d->res_pitch);
 
   L->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * tiles_b), (unsigned)n_tiles, (unsigned)d->z_batches);
-  L->smem = (size_t)stages * p.stage_bytes + 1024 /*alignment slack*/ + 8 * (2 * kMaxStages + 2) + 4 * 512;
+  L->smem = (size_t)stages * p.stage_bytes + 1024 /*alignment slack*/ + 8 * (2 * kMaxStages + 2) + 4 * kAddendFloats;
   if (halo_mode) {
     p.a_stage_bytes = (uint32_t)(((kHaloTW + 2) * (kHaloTH * mt + 2) * kRowBytes + 1023) & ~1023);
     p.b_stage_bytes = (uint32_t)(((t_mode ? kTChan : d->n_tile) * kRowBytes + 1023) & ~1023);
@@ -1214,7 +1258,8 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
 int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CSD_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CSD_CUDA(cudaFuncSetAttribute(conv_halo_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
@@ -1225,9 +1270,12 @@ int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
   } else if (L->halo) {
     conv_halo_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
                                                                  L->mapB, L->p);
+  } else if (L->tap_chunk == 64) {
+    conv_gemm_kernel<64><<<L->grid, kTapThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
+                                                                    L->mapB, L->p);
   } else {
-    conv_gemm_kernel<<<L->grid, kTapThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
-                                                                L->mapB, L->p);
+    conv_gemm_kernel<32><<<L->grid, kTapThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
+                                                                    L->mapB, L->p);
   }
   CSD_LAUNCH_CHECK("conv_gemm_kernel");
   return CSD_OK;

@@ -240,6 +240,168 @@ static int gn_fill(GnParams& p, const void* src0, int c0, int pitch0, const void
   return CSD_OK;
 }
 
+// ---- one-launch GroupNorm for the small levels ---------------------------------------------------------
+// At <= 20 px the producer of a tensor does not deliver channel sums for free (only the transposed convolution
+// does) and a whole image is a few KB, so statistics -> apply as separate launches is three latency-bound
+// kernels per GroupNorm. Here one CTA owns (image b, a slice of Vs 8-channel vectors that covers whole groups):
+// it reads its [hw, Vs] sub-tensor ONCE into registers, reduces per-channel sums in shared memory (fixed-order
+// tree, deterministic), forms the group statistics of its own groups, and writes the normalised (+SiLU)
+// result from the registers. grid = (slices, batch); block = Vs * ppb threads; hw <= R * ppb.
+struct GnFusedPlan {
+  int vs;        // vectors per slice
+  int slices;
+  int threads;
+  int ppb;       // pixel lanes per CTA
+  int r;         // register-cached vectors per thread (template instance)
+  size_t smem;
+};
+
+template <int R>
+__global__ void __launch_bounds__(512)
+gn_fused_kernel(GnParams p, int Vs) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.y;
+  const int ppb = blockDim.x / Vs;
+  const int v = threadIdx.x % Vs, pp = threadIdx.x / Vs;
+  const int gv = blockIdx.x * Vs + v;       // vector index in the channel concatenation
+  const int n2 = Vs * 16;                   // (sum, sumsq) slots of the slice
+  float* part = sm;                         // [ppb][n2]
+  float* red = sm + (size_t)ppb * n2;       // [8][n2]
+  float* chs = red + 8 * n2;                // [n2]
+  float* gstat = chs + n2;                  // [groups in slice][2] = (mean, rstd)
+
+  bf16x8 cache[R];
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  const bool active = pp < ppb;
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int pix = pp + u * ppb;
+      if (pix < p.hw) cache[u] = gn_load(p, b, pix, gv);
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int pix = pp + u * ppb;
+      if (pix < p.hw) {
+        float f[8];
+        unpack8(cache[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += f[i];
+          q[i] = fmaf(f[i], f[i], q[i]);
+        }
+      }
+    }
+    float* row = part + (size_t)pp * n2 + v * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      row[2 * i] = s[i];
+      row[2 * i + 1] = q[i];
+    }
+  }
+  __syncthreads();
+  // two-level fixed-order reduction over the pixel lanes
+  const int parts = min(8, max(1, (int)blockDim.x / n2));
+  for (int idx = threadIdx.x; idx < parts * n2; idx += blockDim.x) {
+    const int c2 = idx % n2, pt = idx / n2;
+    float a = 0.f;
+    for (int r = pt; r < ppb; r += parts) a += part[(size_t)r * n2 + c2];
+    red[pt * n2 + c2] = a;
+  }
+  __syncthreads();
+  for (int c2 = threadIdx.x; c2 < n2; c2 += blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < parts; ++k) a += red[k * n2 + c2];
+    chs[c2] = a;
+  }
+  __syncthreads();
+  const int gs = (Vs * 8) / p.cpg;          // groups of this slice
+  const float inv_n = 1.f / ((float)p.hw * (float)p.cpg);
+  for (int g = threadIdx.x; g < gs; g += blockDim.x) {
+    float su = 0.f, sq = 0.f;
+    for (int i = 0; i < p.cpg; ++i) {
+      su += chs[2 * (g * p.cpg + i)];
+      sq += chs[2 * (g * p.cpg + i) + 1];
+    }
+    const float mean = su * inv_n;
+    const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+    gstat[2 * g] = mean;
+    gstat[2 * g + 1] = rsqrtf(var + p.eps);
+  }
+  __syncthreads();
+  if (!active) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int lc = v * 8 + i;
+    const int g = lc / p.cpg;
+    const float a = gstat[2 * g + 1] * __ldg(p.gamma + gv * 8 + i);
+    sc[i] = a;
+    sh[i] = __ldg(p.beta + gv * 8 + i) - gstat[2 * g] * a;
+  }
+#pragma unroll
+  for (int u = 0; u < R; ++u) {
+    const int pix = pp + u * ppb;
+    if (pix < p.hw) {
+      float f[8];
+      unpack8(cache[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float y = fmaf(f[i], sc[i], sh[i]);
+        f[i] = p.silu ? silu_f(y) : y;
+      }
+      p.out[((long long)b * p.hw + pix) * p.out_pv + gv] = pack8(f);
+    }
+  }
+}
+
+static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+// Host-side planning (no CUDA calls): returns false when the shape does not fit the one-launch kernel.
+static bool gn_fused_plan(int c0, int c1, int hw, int groups, int batch, int sms, GnFusedPlan* pl) {
+  const int C = c0 + c1;
+  if (c0 < 8 || c0 % 8 || c1 % 8 || groups < 1 || C % groups || hw < 1 || batch < 1) return false;
+  const int cpg = C / groups;
+  const int V = C / 8;
+  const int base = cpg / gcd_int(cpg, 8);   // lcm(cpg, 8) / 8 vectors: smallest slice made of whole groups
+  if (V % base) return false;
+  const int nb = V / base;
+  // most slices whose rows are still >= 64 B (4 vectors) unless the tensor is narrower than that; with a big batch
+  // fewer, wider slices are enough to fill the machine
+  int best = 1;
+  for (int d = nb; d >= 1; --d) {
+    if (nb % d) continue;
+    const int vs = V / d;
+    if (vs >= 4 || d == 1) { best = d; break; }
+  }
+  while (best > 1) {   // shrink while the grid stays >= 2 waves and the next divisor exists
+    int d2 = best - 1;
+    while (d2 >= 1 && nb % d2) --d2;
+    if (d2 < 1 || (long long)batch * d2 < 2LL * sms) break;
+    const int vs2 = V / d2;
+    if (vs2 > 128 || ceil_div(hw, 512 / vs2) > 8) break;   // stay within the register-cached iteration budget
+    best = d2;
+  }
+  const int vs = V / best;
+  if (vs > 128) return false;
+  int threads = 256;
+  int ppb = threads / vs;
+  if (ppb < 1) return false;
+  if (ceil_div(hw, ppb) > 8) { threads = 512; ppb = threads / vs; }
+  const int iters = ceil_div(hw, ppb);
+  if (iters > 16) return false;
+  pl->vs = vs;
+  pl->slices = best;
+  pl->ppb = ppb;
+  pl->threads = vs * ppb;
+  pl->r = iters <= 1 ? 1 : (iters <= 2 ? 2 : (iters <= 4 ? 4 : (iters <= 8 ? 8 : 16)));
+  const int n2 = vs * 16;
+  pl->smem = sizeof(float) * ((size_t)ppb * n2 + 8 * n2 + n2 + 2 * (size_t)((vs * 8) / cpg));
+  return pl->smem <= 96 * 1024;
+}
+
 // ---- layout conversion ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1, bf16x8* __restrict__ out,
@@ -303,7 +465,7 @@ softmax_rows_kernel(const float* __restrict__ logits, int in_pitch, __nv_bfloat1
 // ---- time embedding ----------------------------------------------------------------------------------
 // One CTA per batch row. emb -> Linear -> SiLU -> Linear -> SiLU (the SiLU every block applies to temb
 // before its Dense_0, models/layerspp.py:263, is hoisted here).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 time_embedding_kernel(const float* __restrict__ labels, int nf, int embedding_type, const float* __restrict__ fourier_w,
                       const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
                       const float* __restrict__ b1, float* __restrict__ act_temb) {
@@ -331,47 +493,73 @@ time_embedding_kernel(const float* __restrict__ labels, int nf, int embedding_ty
     if ((nf & 1) && threadIdx.x == 0) emb[nf - 1] = 0.f;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < hid; j += blockDim.x) {
-    float acc = b0[j];
+  // one warp per output: lanes stride the input dimension, so the weight row reads coalesce
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < hid; j += nwarps) {
     const float* wr = w0 + (long long)j * embed;
-    for (int k = 0; k < embed; ++k) acc = fmaf(wr[k], emb[k], acc);
-    h0[j] = acc / (1.f + expf(-acc));  // SiLU, full-precision exp
+    float acc = 0.f;
+    for (int k = lane; k < embed; k += 32) acc = fmaf(__ldg(wr + k), emb[k], acc);
+    acc = warp_sum(acc) + b0[j];
+    if (lane == 0) h0[j] = acc / (1.f + expf(-acc));  // SiLU, full-precision exp
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < hid; j += blockDim.x) {
-    float acc = b1[j];
+  for (int j = warp; j < hid; j += nwarps) {
     const float* wr = w1 + (long long)j * hid;
-    for (int k = 0; k < hid; ++k) acc = fmaf(wr[k], h0[k], acc);
-    act_temb[(long long)b * hid + j] = acc / (1.f + expf(-acc));
+    float acc = 0.f;
+    for (int k = lane; k < hid; k += 32) acc = fmaf(__ldg(wr + k), h0[k], acc);
+    acc = warp_sum(acc) + b1[j];
+    if (lane == 0) act_temb[(long long)b * hid + j] = acc / (1.f + expf(-acc));
   }
 }
 
-// One warp per output row j: the weight row stays in registers, the batch loop reuses it.
+// out[b, j] = bias[j] + sum_k w[j, k] act[b, k]: every block's Dense_0 projection as ONE small fp32 GEMM.
+// CTA tile = 64 batch rows x 64 outputs, K in chunks of 32 staged (transposed) in shared memory; each of the 256
+// threads owns a 4 x 4 register tile. Both operands are read with coalesced 128-byte rows.
+constexpr int kDenseTile = 64, kDenseK = 32;
 __global__ void __launch_bounds__(256)
 dense_rows_kernel(const float* __restrict__ act, const float* __restrict__ w, const float* __restrict__ bias,
                   float* __restrict__ out, int batch, int in_dim, int total_out) {
-  const int lane = threadIdx.x & 31;
-  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (j >= total_out) return;
-  constexpr int MAXR = 32;  // in_dim <= 1024
-  float wr[MAXR];
-  const int per = ceil_div(in_dim, 32);
+  __shared__ float As[kDenseK][kDenseTile + 4];   // [k][batch row]
+  __shared__ float Ws[kDenseK][kDenseTile + 4];   // [k][output]
+  const int j0 = blockIdx.x * kDenseTile, b0 = blockIdx.y * kDenseTile;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // outputs tx*4.., batch rows ty*4..
+  const int lk = threadIdx.x & 31, lr = threadIdx.x >> 5;   // loader: k lane, row group (8 groups x 8 rows)
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < MAXR; ++i) {
-    const int k = lane + 32 * i;
-    wr[i] = (i < per && k < in_dim) ? __ldg(w + (long long)j * in_dim + k) : 0.f;
-  }
-  const float bj = bias != nullptr ? bias[j] : 0.f;
-  for (int b = 0; b < batch; ++b) {
-    const float* a = act + (long long)b * in_dim;
-    float acc = 0.f;
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int i = 0; i < MAXR; ++i) {
-      const int k = lane + 32 * i;
-      if (i < per && k < in_dim) acc = fmaf(wr[i], __ldg(a + k), acc);
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < in_dim; k0 += kDenseK) {
+    const int k = k0 + lk;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int row = lr * 8 + r;
+      const int bb = b0 + row, jj = j0 + row;
+      As[lk][row] = (k < in_dim && bb < batch) ? __ldg(act + (long long)bb * in_dim + k) : 0.f;
+      Ws[lk][row] = (k < in_dim && jj < total_out) ? __ldg(w + (long long)jj * in_dim + k) : 0.f;
     }
-    acc = warp_sum(acc);
-    if (lane == 0) out[(long long)b * total_out + j] = acc + bj;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kDenseK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int bb = b0 + ty * 4 + i;
+    if (bb >= batch) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int jj = j0 + tx * 4 + j;
+      if (jj < total_out) out[(long long)bb * total_out + jj] = acc[i][j] + (bias != nullptr ? __ldg(bias + jj) : 0.f);
+    }
   }
 }
 
@@ -428,6 +616,54 @@ int csd_gn_apply_bf16(const void* src0, int c0, int pitch0, const float* sums0, 
   p.eps = eps; p.silu = apply_silu;
   gn_apply_kernel<<<batch * p.slabs, threads, smem, static_cast<cudaStream_t>(stream)>>>(p);
   CSD_LAUNCH_CHECK("gn_apply_kernel");
+  return CSD_OK;
+}
+
+int csd_gn_fused_supported(int c0, int c1, int hw, int groups, int batch) {
+  csd::GnFusedPlan pl;
+  return csd::gn_fused_plan(c0, c1, hw, groups, batch, 148, &pl) ? 1 : 0;
+}
+
+int csd_gn_fused_bf16(const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1, const float* gamma,
+                      const float* beta, void* out, int out_pitch, int batch, int hw, int groups, float eps,
+                      int apply_silu, csd_stream_t stream_) {
+  using namespace csd;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CSD_REQUIRE(src0 && gamma && beta && out && batch >= 1 && hw >= 1, "gn_fused: bad arguments");
+  if (src1 == nullptr) c1 = 0;
+  GnFusedPlan pl;
+  if (!gn_fused_plan(c0, c1, hw, groups, batch, 148, &pl))
+    return set_error(CSD_ERR_UNSUPPORTED, "gn_fused: shape c=%d+%d hw=%d groups=%d does not fit the one-launch kernel "
+                     "(ask csd_gn_fused_supported first)", c0, c1, hw, groups);
+  GnParams p;
+  memset(&p, 0, sizeof(p));
+  int threads;
+  size_t smem;
+  int st = gn_fill(p, src0, c0, pitch0, src1, c1, pitch1, batch, hw, groups, &threads, &smem);
+  if (st != CSD_OK) return st;
+  CSD_REQUIRE(out_pitch % 8 == 0 && out_pitch >= c0 + c1, "gn_fused: out pitch %d too small", out_pitch);
+  p.gamma = gamma; p.beta = beta;
+  p.out = static_cast<bf16x8*>(out);
+  p.out_pv = out_pitch / 8;
+  p.eps = eps; p.silu = apply_silu;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  const dim3 grid((unsigned)pl.slices, (unsigned)batch);
+  switch (pl.r) {
+    case 1: gn_fused_kernel<1><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
+    case 2: gn_fused_kernel<2><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
+    case 4: gn_fused_kernel<4><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
+    case 8: gn_fused_kernel<8><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
+    default: gn_fused_kernel<16><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
+  }
+  CSD_LAUNCH_CHECK("gn_fused_kernel");
   return CSD_OK;
 }
 
@@ -491,7 +727,7 @@ int csd_time_embedding_f32(const float* labels, int batch, int nf, int embedding
   CSD_REQUIRE(labels && w0 && b0 && w1 && b1 && act_temb && batch >= 1 && nf >= 4, "time_embedding: bad arguments");
   CSD_REQUIRE(embedding_type == 0 || (embedding_type == 1 && fourier_w != nullptr), "time_embedding: bad embedding type");
   const size_t smem = sizeof(float) * ((embedding_type == 1 ? 2 * nf : nf) + 4 * nf);
-  time_embedding_kernel<<<batch, 256, smem, static_cast<cudaStream_t>(stream)>>>(labels, nf, embedding_type, fourier_w, w0,
+  time_embedding_kernel<<<batch, 512, smem, static_cast<cudaStream_t>(stream)>>>(labels, nf, embedding_type, fourier_w, w0,
                                                                                b0, w1, b1, act_temb);
   CSD_LAUNCH_CHECK("time_embedding_kernel");
   return CSD_OK;
@@ -500,10 +736,10 @@ int csd_time_embedding_f32(const float* labels, int batch, int nf, int embedding
 int csd_dense_rows_f32(const float* act_temb, const float* w, const float* bias, float* out, int batch, int in_dim,
                        int total_out, csd_stream_t stream) {
   using namespace csd;
-  CSD_REQUIRE(act_temb && w && out && batch >= 1 && in_dim >= 1 && in_dim <= 1024 && total_out >= 1,
-              "dense_rows: bad arguments (in_dim <= 1024)");
-  dense_rows_kernel<<<ceil_div(total_out, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(act_temb, w, bias, out, batch,
-                                                                                         in_dim, total_out);
+  CSD_REQUIRE(act_temb && w && out && batch >= 1 && in_dim >= 1 && total_out >= 1, "dense_rows: bad arguments");
+  const dim3 grid((unsigned)ceil_div(total_out, kDenseTile), (unsigned)ceil_div(batch, kDenseTile));
+  dense_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(act_temb, w, bias, out, batch, in_dim,
+                                                                         total_out);
   CSD_LAUNCH_CHECK("dense_rows_kernel");
   return CSD_OK;
 }

@@ -286,6 +286,10 @@ class Recorder:
 class BlockOps:
     """Builders that append the kernels of one reference layer to a Recorder."""
 
+    # inference: a GroupNorm whose inputs have no channel sums yet runs as one launch when the shape allows it
+    # (K.gn_fused). The training subclass keeps the separate statistics: its backward reads them.
+    fuse_small_gn = True
+
     def __init__(self, device, pool, rec, stats_arena):
         self.device = device
         self.pool = pool
@@ -318,6 +322,13 @@ class BlockOps:
         groups = groups or _groups(c)
         s0 = srcs[0]
         s1 = srcs[1] if len(srcs) > 1 else None
+        if (self.fuse_small_gn and any(a.sums is None for a in srcs)
+                and K.gn_fused_supported(s0.c, s1.c if s1 else 0, h * w, groups, b)):
+            # small levels: statistics + apply in ONE launch (nobody delivers these tensors' sums for free)
+            out = self.pool.get((b, h, w, c))
+            self.rec.add(K.gn_fused, s0.t, s0.c, s1.t if s1 else None, s1.c if s1 else 0, gamma, beta, out, groups,
+                         1e-6, silu)
+            return Act(out, c)
         sums0 = self.ensure_sums(s0)
         sums1 = self.ensure_sums(s1) if s1 is not None else None
         out = self.pool.get((b, h, w, c))

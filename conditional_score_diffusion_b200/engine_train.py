@@ -36,6 +36,8 @@ class NoRecyclePool(BufferPool):
 class TrainOps(BlockOps):
     """BlockOps that keeps every activation and records a tape of (kind, info) for the backward builder."""
 
+    fuse_small_gn = False   # the GroupNorm backward needs every tensor's channel sums
+
     def __init__(self, device, pool, rec, stats_arena, dropout_p=0.0, seed_dev=None):
         super().__init__(device, pool, rec, stats_arena)
         self.tape = []

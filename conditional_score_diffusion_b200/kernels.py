@@ -349,6 +349,20 @@ def gn_apply(src0, c0, sums0, src1, c1, sums1, gamma, beta, out, groups, eps=1e-
     return out
 
 
+def gn_fused_supported(c0, c1, hw, groups, batch):
+    """Host-side test: does the one-launch GroupNorm (statistics + apply) take this shape?"""
+    return bool(_lib.lib().csd_gn_fused_supported(int(c0), int(c1), int(hw), int(groups), int(batch)))
+
+
+def gn_fused(src0, c0, src1, c1, gamma, beta, out, groups, eps=1e-6, silu=True):
+    b = src0.shape[0]
+    hw = src0.numel() // (b * src0.shape[-1])
+    check(_lib.lib().csd_gn_fused_bf16(_ptr(src0), c0, src0.shape[-1], _ptr(src1), c1,
+                                       src1.shape[-1] if src1 is not None else 0, _ptr(gamma), _ptr(beta), _ptr(out),
+                                       out.shape[-1], b, hw, groups, float(eps), int(silu), _stream()))
+    return out
+
+
 def fir_resample(src, out, mode, taps, add=None):
     """mode 'up' | 'down' | 'prefilter'; src/out NHWC bf16."""
     b, h, w, pitch = src.shape

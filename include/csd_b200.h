@@ -163,6 +163,17 @@ int csd_gn_apply_bf16(const void* src0, int c0, int pitch0, const float* sums0, 
                       int out_pitch, int batch, int hw, int groups, float eps, int apply_silu,
                       csd_stream_t stream);
 
+/* One-launch form of csd_gn_chan_stats_bf16 + csd_gn_apply_bf16 for small images (the <= 20 px levels of
+ * NCSN++ / the DDPM U-Net, where no producer delivers channel sums for free and three latency-bound launches
+ * per nn.GroupNorm (models/layerspp.py:67,219,231,242) cost more than the data movement): one CTA per
+ * (image, slice of whole groups) reads its sub-tensor once into registers, reduces the statistics on chip and
+ * writes [SiLU](GroupNorm(cat(src0, src1))). csd_gn_fused_supported is pure host logic (1 = the shape fits:
+ * hw * slice width within the register budget); csd_gn_fused_bf16 returns CSD_ERR_UNSUPPORTED otherwise.   */
+int csd_gn_fused_supported(int c0, int c1, int hw, int groups, int batch);
+int csd_gn_fused_bf16(const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1,
+                      const float* gamma, const float* beta, void* out, int out_pitch, int batch, int hw,
+                      int groups, float eps, int apply_silu, csd_stream_t stream);
+
 /* Fused-prologue form of the GroupNorm above: instead of writing the normalised tensor, write per (image,
  * channel) the pair (scale, shift) = (rstd_g * gamma_c, beta_c - mean_g * rstd_g * gamma_c) of the GroupNorm
  * over cat(src0, src1), split per source: coef0 [batch, c0, 2], coef1 [batch, c1, 2] fp32. A csd_conv_gemm

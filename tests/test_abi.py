@@ -74,6 +74,17 @@ def test_host_only_entry_points(lib):
     assert lib.csd_last_error()
 
 
+def test_gn_fused_planning_is_host_side(lib):
+    """The one-launch GroupNorm takes the <= 20 px shapes of NCSN++ (nf 96) and declines large images."""
+    for c0, c1, hw in ((288, 0, 25), (288, 288, 25), (288, 0, 100), (288, 192, 100), (192, 0, 400), (288, 192, 400),
+                       (192, 192, 400), (128, 0, 64)):
+        groups = min((c0 + c1) // 4, 32)
+        assert lib.csd_gn_fused_supported(c0, c1, hw, groups, 64) == 1, (c0, c1, hw)
+    assert lib.csd_gn_fused_supported(96, 0, 160 * 160, 24, 64) == 0      # large image: statistics ride in the conv epilogue
+    assert lib.csd_gn_fused_supported(100, 0, 25, 25, 64) == 0            # channels not a multiple of 8
+    assert lib.csd_gn_fused_supported(96, 0, 25, 7, 64) == 0              # groups do not divide the channels
+
+
 def test_descriptor_validation_is_host_side(lib):
     """A malformed descriptor is rejected before any CUDA call (so this runs without a GPU)."""
     d = _lib.ConvGemmDesc()

@@ -176,7 +176,8 @@ def test_pc_update_kernels_vs_oracle():
     assert dst.tolist() == [20.0, 21.0, 22.0, 23.0, 24.0]
 
 
-@pytest.mark.parametrize("c0,c1,hw", [(96, 0, 24 * 24), (192, 96, 100), (288, 288, 25), (16, 0, 256), (288, 192, 400), (8, 0, 64)])
+@pytest.mark.parametrize("c0,c1,hw", [(96, 0, 24 * 24), (192, 96, 100), (288, 288, 25), (16, 0, 256), (288, 192, 400), (8, 0, 64),
+                                      (288, 0, 25), (192, 0, 400), (192, 192, 400), (128, 0, 64), (576, 0, 100)])
 def test_groupnorm_silu_vs_torch(c0, c1, hw):
     k_ = K()
     g = torch.Generator().manual_seed(c0 + c1)
@@ -204,6 +205,15 @@ def test_groupnorm_silu_vs_torch(c0, c1, hw):
     _close(out, ref, BF16, f"gn+silu C={C} hw={hw}")
     k_.gn_apply(ag, c0, sums0, bg, c1, sums1, gamma.cuda(), beta.cuda(), out, groups, 1e-6, False)
     _close(out, F.group_norm(ref_in, groups, gamma, beta, eps=1e-6).reshape(B, C, hw).permute(0, 2, 1), BF16, "gn only")
+    # one-launch form (statistics + apply) used at the small levels
+    if k_.gn_fused_supported(c0, c1, hw, groups, B):
+        for silu in (True, False):
+            fo = torch.full((B, hw, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+            k_.gn_fused(ag, c0, bg, c1, gamma.cuda(), beta.cuda(), fo, groups, 1e-6, silu)
+            gn = F.group_norm(ref_in, groups, gamma, beta, eps=1e-6).reshape(B, C, hw).permute(0, 2, 1)
+            _close(fo, F.silu(gn) if silu else gn, BF16, f"fused gn C={C} hw={hw} silu={silu}")
+    else:
+        assert hw > 400, f"one-launch GroupNorm declined a small shape C={C} hw={hw}"
     # per-tile partials -> channel sums (the path fed by the transposed convolution's epilogue)
     tiles = 7
     parts = torch.randn(B * tiles, c0, 2, device="cuda")
@@ -283,3 +293,9 @@ def test_layout_softmax_temb_dense():
         od = torch.empty(3, 500, device="cuda")
         k_.dense_rows(ref.cuda(), wd.cuda(), bd.cuda(), od)
         _close(od, F.linear(ref, wd, bd), 1e-5, "dense rows")
+    # ragged tile edges in both dimensions (tiles are 64 x 64, K chunks of 32)
+    a70 = torch.randn(70, 100, generator=g)
+    w70 = torch.randn(130, 100, generator=g) / 10
+    o70 = torch.empty(70, 130, device="cuda")
+    k_.dense_rows(a70.cuda(), w70.cuda(), None, o70)
+    _close(o70, F.linear(a70, w70), 1e-5, "dense rows ragged, no bias")
