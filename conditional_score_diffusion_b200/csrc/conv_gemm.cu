@@ -165,7 +165,11 @@ __device__ __forceinline__ void epilogue_rows(const ConvGemmKernelParams& p, uin
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += f[i];
         } else {
-          for (int i = 0; i < cnt; ++i) v[i] += __bfloat162float(res_row[n + i]);
+          // (static indices under a predicate: a dynamically indexed v[] would live in local memory and drag every
+          //  access of the fast path through the stack as well)
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < cnt) v[i] += __bfloat162float(res_row[n + i]);
         }
       }
 #pragma unroll
@@ -178,7 +182,9 @@ __device__ __forceinline__ void epilogue_rows(const ConvGemmKernelParams& p, uin
           for (int i = 0; i < 4; ++i)
             reinterpret_cast<float4*>(op)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         } else {
-          for (int i = 0; i < cnt; ++i) op[i] = v[i];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < cnt) op[i] = v[i];
         }
       } else {
         __nv_bfloat16* op =
@@ -191,7 +197,9 @@ __device__ __forceinline__ void epilogue_rows(const ConvGemmKernelParams& p, uin
           bf16x8 o0 = pack8(v);
           reinterpret_cast<uint4*>(op)[0] = *reinterpret_cast<uint4*>(&o0);
         } else {
-          for (int i = 0; i < cnt; ++i) op[i] = __float2bfloat16_rn(v[i]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < cnt) op[i] = __float2bfloat16_rn(v[i]);
         }
       }
     }
@@ -342,9 +350,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const uint32_t a_lo0 = a_lo, stage_step = stage_bytes >> 4;
       uint32_t fbar = full_bar(0);
       bool ready = ptx::mbar_test_wait(fbar, 0);
+#ifdef CSD_ENABLE_PHASE_TIMESTAMPS
+      const bool ts_on = p.debug_ts != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
+#define CSD_TSM(slot) do { if (ts_on && it < 12) p.debug_ts[16 + 4 * it + (slot)] = clock64(); } while (0)
+#else
+#define CSD_TSM(slot) do { } while (0)
+#endif
       for (int it = 0; it < total_iters; ++it) {
+        CSD_TSM(0);
         if (!ready) ptx::mbar_wait(fbar, par);
         ptx::tcgen05_fence_after();
+        CSD_TSM(1);
         // look at the next stage's barrier now: the test's latency overlaps with the MMAs issued below
         const uint32_t ebar = fbar + 8u * kMaxStages;
         uint32_t nstage = stage + 1, npar = par, n_lo = a_lo + stage_step;
@@ -362,7 +378,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                              ptx::smem_desc_join(hi, b_lo + b2_off + 2 * k16), idesc, acc);
         }
         accumulate = 1u;
+        CSD_TSM(2);
         ptx::mma_commit(ebar);  // frees the stage when the MMAs above have read it
+        CSD_TSM(3);
         stage = nstage;
         par = npar;
         a_lo = n_lo;

@@ -30,6 +30,25 @@
 
 namespace csd {
 
+// One 16-column chunk of an accumulator row to the fp32 partial buffer: 4 x 16-byte stores when the row segment is
+// complete and aligned, statically indexed predicated stores otherwise (a dynamically indexed r[] would be placed
+// in local memory and every chunk would round-trip through the stack).
+__device__ __forceinline__ void store_partial_chunk(float* dst, const uint32_t (&r)[16], int cnt, bool zero) {
+  if (cnt == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      reinterpret_cast<float4*>(dst)[i] =
+          zero ? make_float4(0.f, 0.f, 0.f, 0.f)
+               : make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                             __uint_as_float(r[4 * i + 3]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < cnt) dst[i] = zero ? 0.f : __uint_as_float(r[i]);
+  }
+}
+
+
 // ---------------------------------------------------------------------------------------------------------
 // NHWC bf16 -> pixel-major copies
 // ---------------------------------------------------------------------------------------------------------
@@ -221,10 +240,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constan
       __syncwarp();
       ptx::tmem_ld_x16(t_row + col, r);
       ptx::tmem_ld_wait();
-      if (co < p.cout) {
-        const int cnt = min(16, ncols - col);
-        for (int i = 0; i < cnt; ++i) orow[n0 + col + i] = __uint_as_float(r[i]);
-      }
+      if (co < p.cout) store_partial_chunk(orow + n0 + col, r, min(16, ncols - col), false);
     }
   }
 
@@ -420,13 +436,7 @@ wgrad_direct_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
         __syncwarp();
         ptx::tmem_ld_x16(t_row + kx * p.n_tile + col, r);
         ptx::tmem_ld_wait();
-        if (co < p.cout && t_hi > t_lo) {
-          const int cnt = min(16, ncols - col);
-          for (int i = 0; i < cnt; ++i) orow[n0 + col + i] = __uint_as_float(r[i]);
-        } else if (co < p.cout) {
-          const int cnt = min(16, ncols - col);
-          for (int i = 0; i < cnt; ++i) orow[n0 + col + i] = 0.f;
-        }
+        if (co < p.cout) store_partial_chunk(orow + n0 + col, r, min(16, ncols - col), !(t_hi > t_lo));
       }
     }
   }

@@ -283,12 +283,21 @@ class Recorder:
         return len(self.ops)
 
 
+# A/B switch for the output heads: 0 = GroupNorm pass + per-tap kernel, 1 = transposed kernel with the pyramid as an
+# identity K segment, 2 = transposed kernel, pyramid added by its FIR upsampling.
+HEAD_MODE = int(os.environ.get("CSD_HEAD_MODE", "0"))
+
+
 class BlockOps:
     """Builders that append the kernels of one reference layer to a Recorder."""
 
     # inference: a GroupNorm whose inputs have no channel sums yet runs as one launch when the shape allows it
     # (K.gn_fused). The training subclass keeps the separate statistics: its backward reads them.
     fuse_small_gn = True
+    # inference: the few-channel output heads (GroupNorm + SiLU + conv3x3 -> 3/6 channels) run in the transposed
+    # kernel with the GroupNorm in its prologue; the training subclass keeps the plain path (its backward needs the
+    # normalised tensor and takes the residual from the epilogue).
+    fast_heads = True
 
     def __init__(self, device, pool, rec, stats_arena):
         self.device = device
@@ -365,20 +374,22 @@ class BlockOps:
                 and K.transposed_shape_ok(h, w) and all(a.c % 8 == 0 for a in srcs))
 
     def conv(self, segs, pc, out_hw=None, temb=None, temb_pitch=0, res=None, scale=1.0, stride=1, pad=1,
-             out=None):
+             out=None, head=False):
         """segs: list of (Act, taps[, coef]); coef = fused GroupNorm+SiLU table of that segment (gn_coeffs).
-        pc: PackedConv. Returns Act [B, oh, ow, n_store]."""
+        pc: PackedConv. head: few-channel output head forced into the transposed kernel (no statistics).
+        Returns Act [B, oh, ow, n_store]."""
         a0 = segs[0][0]
         b, ih, iw, _ = a0.shape
         oh, ow = out_hw if out_hw is not None else (ih, iw)
         if out is None:
             out = self.pool.get((b, oh, ow, pc.n_store))
         seg_list = [(sg[0].t, sg[0].pitch, 0, sg[0].c, sg[1], sg[2] if len(sg) > 2 else None, True) for sg in segs]
-        use_t = (self.will_transpose(oh, ow, pc.cout) and K.transposed_eligible(seg_list, oh, ow, stride, pad))
+        use_t = ((head or self.will_transpose(oh, ow, pc.cout))
+                 and K.transposed_eligible(seg_list, oh, ow, stride, pad))
         if use_t and res is not None:
             raise CsdError("transposed conv takes its residual as an identity K segment (engine planning error)")
         partials = sums = None
-        if use_t:
+        if use_t and not head:
             # GroupNorm statistics of the output for free: per-(tile, pixel half) partial sums from the epilogue
             tiles_img = math.ceil(oh / K.transposed_tile_rows(oh)) * math.ceil(ow / 8) * 2
             partials = self.pool.get((b * tiles_img, pc.n_store, 2), torch.float32)
@@ -391,6 +402,36 @@ class BlockOps:
             self.rec.add(K.gn_finalize_partials, partials, sums, b, tiles_img, pc.cout)
             self.pool.put(partials)
         return Act(out, pc.cout, sums)
+
+    def head_in_transposed_kernel(self, pc, hcur):
+        b, h, w, _ = hcur.shape
+        return (self.fast_heads and HEAD_MODE != 0 and K.TRANSPOSED_DEFAULT and K.FUSE_GN_DEFAULT
+                and K.transposed_shape_ok(h, w) and hcur.c % 8 == 0 and pc.n_store == 8 and len(pc.segs) == 1)
+
+    def head(self, gn, pc, hcur, extra, key, res=None):
+        """Output head: conv3x3(SiLU(GroupNorm(h))) [+ res] -> the few image channels (models/ncsnpp.py:337-352,
+        372-381). Where the image tiles into the transposed kernel's macro tiles the head runs there: M = 128
+        channel rows of which 8 are stored, but N = 256 pixels per instruction instead of 16 columns at the
+        per-instruction floor of the pixel-major kernel (2x faster, measured), GroupNorm+SiLU in the prologue (no
+        normalised copy), the residual pyramid as an identity K segment. extra: dict that owns the derived packs
+        (visited by the engine's refresh); key: this head's slot in it."""
+        gamma, beta, groups = gn
+        if self.head_in_transposed_kernel(pc, hcur) and (res is None or res.c == pc.cout):
+            pct = pc
+            if res is not None:
+                pct = extra.get(key)
+                if pct is None:
+                    pct = extra[key] = PackedConv([pc.segs[0][0], WSrc(pc.cout, "eye")], list(pc.bias_srcs) or None,
+                                                  self.device)
+            (cf,) = self.gn_coeffs([hcur], gamma, beta, groups)
+            segs = [(hcur, 9, cf)] + ([(res, 1)] if res is not None else [])
+            out = self.conv(segs, pct, head=True)
+            self.pool.put(cf)
+            return out
+        a = self.group_norm([hcur], gamma, beta, True, groups)
+        out = self.conv([(a, 9)], pc, res=res, scale=1.0)
+        self.release(a)
+        return out
 
     def time_embedding(self, labels, nf, embedding_type, fourier_w, lin0, lin1, P, mods=None):
         """temb MLP (fused kernel) + every block's Dense_0 projection in one launch. Returns (tproj, pitch)."""
@@ -599,6 +640,7 @@ class NetEngine:
                     visit(v)
 
         visit(self.packed["mods"])
+        visit(self.packed.get("extra", {}))
 
     def _build_pack_table(self):
         jobs, ok = [], [True]
@@ -653,6 +695,7 @@ class NetEngine:
                     visit(v)
 
         visit(self.packed["mods"])
+        visit(self.packed.get("extra", {}))
         if "dense_mods" in self.packed:
             self._refresh_dense(self.packed)
 
@@ -1100,17 +1143,22 @@ class NetPlan:
                 if net.progressive == "residual":
                     raise CsdError("progressive='residual' relies on upsample_conv_2d, which is dead code in the "
                                    "reference (up_or_down_sampling.py:123 indexes with a negative step); unsupported")
-                gamma, beta, gn_groups = pk[m_idx]
-                a = ops.group_norm([hcur], gamma, beta, True, gn_groups)
+                gn = pk[m_idx]
                 m_idx += 1
+                extra = self.eng.packed.setdefault("extra", {})
                 if lvl == num_res - 1:
-                    pyramid = ops.conv([(a, 9)], pk[m_idx])
+                    pyramid = ops.head(gn, pk[m_idx], hcur, extra, m_idx)
+                elif ops.head_in_transposed_kernel(pk[m_idx], hcur) and HEAD_MODE == 2:
+                    # conv first, then the pyramid's FIR upsampling adds it (fir_nhwc `add`): no residual operand
+                    ho = ops.head(gn, pk[m_idx], hcur, extra, m_idx)
+                    pu = ops.fir(pyramid, "up", fir_taps, add=ho)
+                    ops.release(pyramid, ho)
+                    pyramid = pu
                 else:
                     pu = ops.fir(pyramid, "up", fir_taps)
                     ops.release(pyramid)
-                    pyramid = ops.conv([(a, 9)], pk[m_idx], res=pu, scale=1.0)
+                    pyramid = ops.head(gn, pk[m_idx], hcur, extra, m_idx, res=pu)
                     ops.release(pu)
-                ops.release(a)
                 m_idx += 1
             if lvl != 0:
                 if net.resblock_type == "ddpm":
@@ -1123,10 +1171,9 @@ class NetPlan:
         if net.progressive == "output_skip":
             final = pyramid
         else:
-            gamma, beta, gn_groups = pk[m_idx]
-            a = ops.group_norm([hcur], gamma, beta, True, gn_groups)
+            gn = pk[m_idx]
             m_idx += 1
-            final = ops.conv([(a, 9)], pk[m_idx])
+            final = ops.head(gn, pk[m_idx], hcur, self.eng.packed.setdefault("extra", {}), m_idx)
             m_idx += 1
         assert m_idx == len(mods), (m_idx, len(mods))
         return final

@@ -37,6 +37,7 @@ class TrainOps(BlockOps):
     """BlockOps that keeps every activation and records a tape of (kind, info) for the backward builder."""
 
     fuse_small_gn = False   # the GroupNorm backward needs every tensor's channel sums
+    fast_heads = False      # the tape records the plain GroupNorm -> conv (+ epilogue residual) form
 
     def __init__(self, device, pool, rec, stats_arena, dropout_p=0.0, seed_dev=None):
         super().__init__(device, pool, rec, stats_arena)

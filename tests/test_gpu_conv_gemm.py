@@ -493,6 +493,40 @@ def test_transposed_fused_groupnorm_prologue():
     assert _t_norm_case("TN (192+192)->192 40x40 20-row tiles", 2, 40, 40, [192, 192], 192, seed=6, skip_c=384) < T_NORM_RTOL
 
 
+def test_transposed_output_head():
+    """The 6-channel output heads in the transposed kernel: 8 stored channels (pitch 8), fused GroupNorm+SiLU
+    prologue, bias, and the upsampled pyramid as a 6-channel identity K segment (engine.BlockOps.head)."""
+    k = _kern()
+    dev = "cuda"
+    for (B, H, W, with_res, seed) in ((2, 32, 32, True, 0), (2, 40, 40, True, 1), (3, 64, 64, False, 2)):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        cin, cout = 96, 6
+        x = torch.randn(B, cin, H, W, device=dev, generator=g).to(torch.bfloat16)
+        sc = torch.rand(B, cin, device=dev, generator=g) + 0.5
+        sh = torch.randn(B, cin, device=dev, generator=g)
+        y = F.silu(x.float() * sc[:, :, None, None] + sh[:, :, None, None]).to(torch.bfloat16).float()
+        wgt = (torch.randn(cout, cin, 3, 3, device=dev, generator=g) / math.sqrt(9 * cin)).to(torch.bfloat16)
+        bias = torch.zeros(32, device=dev)
+        bias[:cout] = torch.randn(cout, device=dev, generator=g)
+        ref = F.conv2d(y, wgt.float(), bias[:cout], padding=1)
+        parts = [k.pack_conv_weight(wgt, n_pad=16)]
+        segs = [(_nhwc(x), cin, 0, cin, 9, torch.stack([sc, sh], dim=-1).contiguous(), True)]
+        if with_res:
+            r = torch.randn(B, cout, H, W, device=dev, generator=g).to(torch.bfloat16)
+            r8 = torch.zeros(B, H, W, 8, device=dev, dtype=torch.bfloat16)
+            r8[..., :cout] = r.permute(0, 2, 3, 1)
+            ref = ref + r.float()
+            parts.append(k.pack_conv_weight(torch.eye(cout, device=dev).view(cout, cout, 1, 1).to(torch.bfloat16), n_pad=16))
+            segs.append((r8, 8, 0, cout, 1))
+        wt = torch.cat(parts, dim=1).contiguous()
+        out = torch.full((B, H, W, 8), float("nan"), device=dev, dtype=torch.bfloat16)
+        k.conv_gemm(segs, wt, cout, out, batch=B, h=H, w=W, n_store=8, n_tile=16, bias=bias, transposed=True)
+        torch.cuda.synchronize()
+        assert torch.isfinite(out.float()).all(), "head: non-finite"
+        assert (out[..., cout:].float() == 0).all(), "head: padding channels must be zero"
+        assert _report(f"T head 96->6 {H}x{W} res={with_res}", out[..., :cout].permute(0, 3, 1, 2), ref, T_NORM_RTOL) < T_NORM_RTOL
+
+
 def test_gn_coeffs_match_group_norm():
     k = _kern()
     dev = "cuda"

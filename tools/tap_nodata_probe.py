@@ -2,7 +2,7 @@
 (CSD_DEBUG_NODATA bit 0 = weights, bit 1 = activations; results are garbage) and with a capped ring depth
 (CSD_TAP_STAGES) - separates MMA issue, TMA feed and ring depth for the latency-bound small levels."""
 import os, subprocess, sys
-if len(sys.argv) > 1:
+if len(sys.argv) > 1 and sys.argv[1] == "run":
     import torch
     sys.path.insert(0, ".")
     from conditional_score_diffusion_b200 import kernels as k
@@ -40,7 +40,8 @@ if len(sys.argv) > 1:
         print(f"  {tag} {H}x{H} {cin}->{cout} taps={taps}: {us:.1f} us/launch, {stages} stages, "
               f"{us * 1.9e3 / stages:.0f} cyc/stage, {2.0*B*H*H*cin*cout*taps/us/1e6:.0f} TF/s", flush=True)
 else:
-    for nd, st, c32 in (("0", None, False), ("0", None, True), ("3", None, False), ("0", "2", False)):
+    cfgs = (("0", None, False),) if "--quick" in sys.argv else (("0", None, False), ("0", None, True), ("3", None, False), ("0", "2", False))
+    for nd, st, c32 in cfgs:
         env = dict(os.environ, CSD_DEBUG_NODATA=nd)
         if st:
             env["CSD_TAP_STAGES"] = st

@@ -23,8 +23,8 @@ for (B, H, cin, cout) in ((64, 5, 288, 288), (64, 20, 192, 192)):
         torch.cuda.synchronize()
     t = ts.tolist()
     t0 = t[0]
-    mma = [(t[16 + 2 * i] - t0, t[17 + 2 * i] - t0) for i in range(24) if t[17 + 2 * i]]
+    mma = [tuple(t[16 + 4 * i + j] - t0 for j in range(4)) for i in range(12) if t[16 + 4 * i + 3]]
     prod = [t[64 + i] - t0 for i in range(96) if t[64 + i]]
     print(f"H={H} {cin}->{cout} n_tile={n_tile}: {e0.elapsed_time(e1)*1e3:.0f} us; setup={t[1]-t0} accum_ready={t[5]-t0} epi_end={t[6]-t0} dealloc={t[7]-t0}")
-    print("  mma (arrive at wait, pass wait):", mma[:16])
+    print("  mma (loop top, after wait+fence, after MMA issue, after commit):", mma)
     print("  producer0 issue times:", prod[:12])
