@@ -120,6 +120,9 @@ _PROTOTYPES = {
     "csd_gn_finalize_partials_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "csd_gn_coeffs_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                   c_int, c_int, c_float, c_void_p]),
+    "csd_gn_coeffs_partials_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                           c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                           c_void_p]),
     "csd_gn_fused_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "csd_gn_fused_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                   c_int, c_int, c_int, c_float, c_int, c_void_p]),

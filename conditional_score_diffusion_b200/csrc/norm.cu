@@ -10,6 +10,9 @@
 #include "common.cuh"
 #include "../../include/csd_b200.h"
 
+#include <algorithm>
+#include <cstring>
+
 namespace csd {
 
 struct GnParams {
@@ -206,6 +209,84 @@ gn_coeffs_kernel(const float* __restrict__ sums0, int c0, const float* __restric
       const float* sp = (cc < c0) ? sums0 + ((long long)b * c0 + cc) * 2 : sums1 + ((long long)b * c1 + (cc - c0)) * 2;
       su += sp[0];
       sq += sp[1];
+    }
+    const float mean = su * inv_n;
+    const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+    const float sc = rsqrtf(var + eps) * gamma[c];
+    const float2 v = make_float2(sc, beta[c] - mean * sc);
+    if (c < c0) coef0[(long long)b * c0 + c] = v;
+    else coef1[(long long)b * c1 + (c - c0)] = v;
+  }
+}
+
+// gn_coeffs with the finalize pass folded in: a source may arrive as the per-tile partial sums of the transposed
+// convolution's epilogue ([batch * tiles, c, 2]); the CTA of image b reduces them in a fixed order (lanes of tiles,
+// then lanes), writes the channel sums for later consumers (skip connections) and goes on to the coefficients.
+// One launch instead of gn_finalize_partials + gn_coeffs. grid = (batch, slices of whole groups), block = 256.
+struct GnCoefSrc {
+  const float* sums;      // [batch, c, 2] or null
+  const float* partials;  // [batch * tiles, c, 2] or null
+  float* sums_out;        // where the reduced partials go (may be null)
+  int tiles, c;
+};
+
+__global__ void __launch_bounds__(256)
+gn_coeffs_partials_kernel(GnCoefSrc s0, GnCoefSrc s1, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          float2* __restrict__ coef0, float2* __restrict__ coef1, int hw, int cpg, float eps,
+                          int slice /* channels per CTA, a multiple of cpg */) {
+  // grid = (batch, slices): CTA (b, y) owns channels [y * slice, (y + 1) * slice) of the concatenation
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, c0 = s0.c, c1 = s1.c, C = c0 + c1;
+  const int cs = blockIdx.y * slice, ce = min(C, cs + slice);
+  if (cs >= ce) return;
+  const int n2 = 2 * (ce - cs);
+  const int lanes = max(1, min(16, (int)blockDim.x / n2));
+  float* sums = sm;              // [n2]
+  float* red = sm + n2;          // [lanes][n2]
+  for (int idx = threadIdx.x; idx < lanes * n2; idx += blockDim.x) {
+    const int i = idx % n2, g = idx / n2;
+    const int cc = cs + (i >> 1), comp = i & 1;
+    const bool first = cc < c0;
+    const GnCoefSrc& s = first ? s0 : s1;
+    const int lc = first ? cc : cc - c0;
+    float acc = 0.f;
+    if (s.partials != nullptr) {
+      const long long stride = 2LL * s.c;
+      const float* p0 = s.partials + (long long)b * s.tiles * stride + 2 * lc + comp;
+      float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int t = g;
+      for (; t + 3 * lanes < s.tiles; t += 4 * lanes) {     // 4 independent loads in flight per thread
+        acc += p0[(long long)t * stride];
+        a1 += p0[(long long)(t + lanes) * stride];
+        a2 += p0[(long long)(t + 2 * lanes) * stride];
+        a3 += p0[(long long)(t + 3 * lanes) * stride];
+      }
+      for (; t < s.tiles; t += lanes) acc += p0[(long long)t * stride];
+      acc = (acc + a1) + (a2 + a3);
+    } else if (g == 0) {
+      acc = s.sums[((long long)b * s.c + lc) * 2 + comp];
+    }
+    red[idx] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    float a = 0.f;
+    for (int g = 0; g < lanes; ++g) a += red[g * n2 + i];
+    sums[i] = a;
+    const int cc = cs + (i >> 1);
+    const bool first = cc < c0;
+    const GnCoefSrc& s = first ? s0 : s1;
+    if (s.partials != nullptr && s.sums_out != nullptr)
+      s.sums_out[((long long)b * s.c + (first ? cc : cc - c0)) * 2 + (i & 1)] = a;
+  }
+  __syncthreads();
+  const float inv_n = 1.f / ((float)hw * (float)cpg);
+  for (int c = cs + threadIdx.x; c < ce; c += blockDim.x) {
+    const int g0 = ((c - cs) / cpg) * cpg;
+    float su = 0.f, sq = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      su += sums[2 * (g0 + i)];
+      sq += sums[2 * (g0 + i) + 1];
     }
     const float mean = su * inv_n;
     const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
@@ -679,6 +760,35 @@ int csd_gn_coeffs_f32(const float* sums0, int c0, const float* sums1, int c1, co
       sums0, c0, sums1, c1, gamma, beta, reinterpret_cast<float2*>(coef0), reinterpret_cast<float2*>(coef1), hw,
       (c0 + c1) / groups, eps);
   CSD_LAUNCH_CHECK("gn_coeffs_kernel");
+  return CSD_OK;
+}
+
+int csd_gn_coeffs_partials_f32(const float* sums0, const float* partials0, int tiles0, float* sums_out0, int c0,
+                               const float* sums1, const float* partials1, int tiles1, float* sums_out1, int c1,
+                               const float* gamma, const float* beta, float* coef0, float* coef1, int batch, int hw,
+                               int groups, float eps, csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(gamma && beta && coef0 && batch >= 1 && hw >= 1 && c0 >= 1, "gn_coeffs_partials: bad arguments");
+  CSD_REQUIRE((sums0 != nullptr) != (partials0 != nullptr), "gn_coeffs_partials: source 0 needs sums OR partials");
+  CSD_REQUIRE(partials0 == nullptr || tiles0 >= 1, "gn_coeffs_partials: tiles0=%d", tiles0);
+  if (sums1 == nullptr && partials1 == nullptr) c1 = 0;
+  CSD_REQUIRE(c1 == 0 || (coef1 != nullptr && (sums1 != nullptr) != (partials1 != nullptr) &&
+                          (partials1 == nullptr || tiles1 >= 1)),
+              "gn_coeffs_partials: source 1 needs its coefficient output and sums OR partials");
+  CSD_REQUIRE(groups >= 1 && (c0 + c1) % groups == 0, "gn_coeffs_partials: %d channels not divisible by %d groups",
+              c0 + c1, groups);
+  GnCoefSrc s0{sums0, partials0, sums_out0, tiles0, c0};
+  GnCoefSrc s1{sums1, partials1, sums_out1, tiles1, c1};
+  const int cpg = (c0 + c1) / groups;
+  // enough CTAs for ~2 waves, each owning whole groups
+  int slices = std::max(1, std::min(groups, ceil_div(2 * num_sms(), batch)));
+  const int slice = ceil_div(groups, slices) * cpg;
+  slices = ceil_div(c0 + c1, slice);
+  const size_t smem = sizeof(float) * (2 * (size_t)slice + (size_t)std::max(256, 2 * slice));
+  CSD_REQUIRE(smem <= 48 * 1024, "gn_coeffs_partials: %d channels per slice exceed the shared-memory budget", slice);
+  gn_coeffs_partials_kernel<<<dim3((unsigned)batch, (unsigned)slices), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      s0, s1, gamma, beta, reinterpret_cast<float2*>(coef0), reinterpret_cast<float2*>(coef1), hw, cpg, eps, slice);
+  CSD_LAUNCH_CHECK("gn_coeffs_partials_kernel");
   return CSD_OK;
 }
 

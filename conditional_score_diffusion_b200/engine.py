@@ -25,10 +25,13 @@ class Act:
     """NHWC bf16 activation: tensor [B, H, W, pitch] with `c` valid channels and, once some GroupNorm
     needs them, its per-channel (sum, sum of squares) [B, c, 2]."""
 
-    __slots__ = ("t", "c", "sums")
+    __slots__ = ("t", "c", "sums", "pending")
 
-    def __init__(self, t, c, sums=None):
-        self.t, self.c, self.sums = t, c, sums
+    def __init__(self, t, c, sums=None, pending=None):
+        # pending = (partials [B * tiles, c, 2], tiles per image, sums slot): the transposed convolution that wrote the
+        # tensor left per-tile partial sums; whoever needs the channel sums first reduces them (BlockOps.ensure_sums /
+        # gn_coeffs) - folded into the coefficient kernel when that consumer is a fused GroupNorm prologue
+        self.t, self.c, self.sums, self.pending = t, c, sums, pending
 
     @property
     def shape(self):
@@ -298,6 +301,9 @@ class BlockOps:
     # kernel with the GroupNorm in its prologue; the training subclass keeps the plain path (its backward needs the
     # normalised tensor and takes the residual from the epilogue).
     fast_heads = True
+    # inference: the reduction of a transposed convolution's per-tile statistics waits for the first consumer and is
+    # folded into its coefficient kernel (gn_coeffs_partials); the training subclass finalizes at once.
+    defer_finalize = os.environ.get("CSD_NO_DEFER_FINALIZE", "0") != "1"
 
     def __init__(self, device, pool, rec, stats_arena):
         self.device = device
@@ -319,6 +325,11 @@ class BlockOps:
     def ensure_sums(self, a):
         """Per-channel sums of a tensor: produced by the convolution that wrote it when that ran in the
         transposed mode, otherwise by one statistics pass - in both cases once per tensor."""
+        if a.sums is None and a.pending is not None:
+            partials, tiles_img, slot = a.pending
+            self.rec.add(K.gn_finalize_partials, partials, slot, a.shape[0], tiles_img, a.c)
+            self.pool.put(partials)
+            a.sums, a.pending = slot, None
         if a.sums is None:
             a.sums = self._stats_slot(a.shape[0], a.c)
             self.rec.add(K.gn_chan_stats, a.t, a.c, a.sums)
@@ -352,10 +363,28 @@ class BlockOps:
         c = sum(a.c for a in srcs)
         s0 = srcs[0]
         s1 = srcs[1] if len(srcs) > 1 else None
-        sums0 = self.ensure_sums(s0)
-        sums1 = self.ensure_sums(s1) if s1 is not None else None
         coef0 = self.pool.get((b, s0.c, 2), torch.float32)
         coef1 = self.pool.get((b, s1.c, 2), torch.float32) if s1 is not None else None
+        if any(a is not None and a.sums is None and a.pending is not None for a in (s0, s1)):
+            # a source still carries its convolution's per-tile partials: reduce them inside the coefficient kernel
+            args, done = [], []
+            for a in (s0, s1):
+                if a is None:
+                    args.append(None)
+                elif a.sums is None and a.pending is not None:
+                    partials, tiles_img, slot = a.pending
+                    args.append((None, partials, tiles_img, slot, a.c))
+                    done.append((a, partials, slot))
+                else:
+                    args.append((self.ensure_sums(a), None, 0, None, a.c))
+            self.rec.add(K.gn_coeffs_partials, args[0], args[1], gamma, beta, coef0, coef1, b, h * w,
+                         groups or _groups(c), 1e-6)
+            for a, partials, slot in done:
+                self.pool.put(partials)
+                a.sums, a.pending = slot, None
+            return [coef0] + ([coef1] if s1 is not None else [])
+        sums0 = self.ensure_sums(s0)
+        sums1 = self.ensure_sums(s1) if s1 is not None else None
         self.rec.add(K.gn_coeffs, sums0, s0.c, sums1, s1.c if s1 else 0, gamma, beta, coef0, coef1, h * w,
                      groups or _groups(c), 1e-6)
         return [coef0] + ([coef1] if s1 is not None else [])
@@ -398,6 +427,8 @@ class BlockOps:
                      n_tile=pc.n_tile, bias=pc.bias, temb=temb, temb_pitch=temb_pitch,
                      res=res.t if res is not None else None, res_pitch=res.pitch if res is not None else 0,
                      scale=scale, stride=stride, pad=pad, in_h=ih, in_w=iw, transposed=use_t, stat_partials=partials)
+        if partials is not None and self.defer_finalize:
+            return Act(out, pc.cout, None, (partials, tiles_img, sums))
         if partials is not None:
             self.rec.add(K.gn_finalize_partials, partials, sums, b, tiles_img, pc.cout)
             self.pool.put(partials)
@@ -461,6 +492,9 @@ class BlockOps:
         for a in acts:
             if a is not None:
                 self.pool.put(a.t)
+                if a.pending is not None:       # nobody asked for its statistics
+                    self.pool.put(a.pending[0])
+                    a.pending = None
 
     # -- reference layers ----------------------------------------------------------------------
     def resblock(self, pk, srcs, tproj, tproj_pitch, fir_taps, skip_rescale):

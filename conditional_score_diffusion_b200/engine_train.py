@@ -38,6 +38,7 @@ class TrainOps(BlockOps):
 
     fuse_small_gn = False   # the GroupNorm backward needs every tensor's channel sums
     fast_heads = False      # the tape records the plain GroupNorm -> conv (+ epilogue residual) form
+    defer_finalize = False  # every activation's channel sums exist as soon as it does (the backward reads them)
 
     def __init__(self, device, pool, rec, stats_arena, dropout_p=0.0, seed_dev=None):
         super().__init__(device, pool, rec, stats_arena)

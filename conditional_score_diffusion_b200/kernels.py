@@ -349,6 +349,16 @@ def gn_apply(src0, c0, sums0, src1, c1, sums1, gamma, beta, out, groups, eps=1e-
     return out
 
 
+def gn_coeffs_partials(src0, src1, gamma, beta, coef0, coef1, batch, hw, groups, eps=1e-6):
+    """srcN = (sums, partials, tiles, sums_out, c) with exactly one of sums / partials set (src1 may be None)."""
+    s1 = src1 if src1 is not None else (None, None, 0, None, 0)
+    check(_lib.lib().csd_gn_coeffs_partials_f32(_ptr(src0[0]), _ptr(src0[1]), int(src0[2]), _ptr(src0[3]), int(src0[4]),
+                                                _ptr(s1[0]), _ptr(s1[1]), int(s1[2]), _ptr(s1[3]), int(s1[4]),
+                                                _ptr(gamma), _ptr(beta), _ptr(coef0), _ptr(coef1), batch, hw, groups,
+                                                float(eps), _stream()))
+    return coef0
+
+
 def gn_fused_supported(c0, c1, hw, groups, batch):
     """Host-side test: does the one-launch GroupNorm (statistics + apply) take this shape?"""
     return bool(_lib.lib().csd_gn_fused_supported(int(c0), int(c1), int(hw), int(groups), int(batch)))

@@ -183,6 +183,15 @@ int csd_gn_fused_bf16(const void* src0, int c0, int pitch0, const void* src1, in
 int csd_gn_coeffs_f32(const float* sums0, int c0, const float* sums1, int c1, const float* gamma, const float* beta,
                       float* coef0, float* coef1, int batch, int hw, int groups, float eps, csd_stream_t stream);
 
+/* csd_gn_coeffs_f32 with csd_gn_finalize_partials_f32 folded in: each source arrives either as channel sums
+ * (sumsN) or as the per-tile partials of the transposed convolution's epilogue (partialsN [batch * tilesN, cN, 2],
+ * exactly one of the two non-null); reduced partials are also written to sums_outN (may be null) for the tensor's
+ * later consumers. One launch per fused GroupNorm instead of two.                                   */
+int csd_gn_coeffs_partials_f32(const float* sums0, const float* partials0, int tiles0, float* sums_out0, int c0,
+                               const float* sums1, const float* partials1, int tiles1, float* sums_out1, int c1,
+                               const float* gamma, const float* beta, float* coef0, float* coef1, int batch, int hw,
+                               int groups, float eps, csd_stream_t stream);
+
 /* Depthwise separable FIR resampling of an NHWC bf16 tensor with the [1,3,3,1] family
  * (up_or_down_sampling.upsample_2d / downsample_2d, models/up_or_down_sampling.py:195-257):
  * mode 1 = up x2 (pad (2,1), gain 4), mode 2 = down x2 (pad (1,1)), mode 3 = same-rate pre-filter with

@@ -547,3 +547,46 @@ def test_gn_coeffs_match_group_norm():
     coef = torch.cat([f0, f1], dim=1)
     got = x * coef[:, :, 0, None, None] + coef[:, :, 1, None, None]
     assert (got - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("c0,c1,tiles", [(96, 0, 200), (192, 96, 50), (96, 288, 7), (288, 192, 20)])
+def test_gn_coeffs_from_partials(c0, c1, tiles):
+    """gn_coeffs_partials == gn_finalize_partials + gn_coeffs, for either source arriving as per-tile partials."""
+    k = _kern()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(c0 + c1 + tiles)
+    B, hw = 3, 1600
+    C = c0 + c1
+    groups = min(C // 4, 32)
+    gamma, beta = torch.randn(C, device=dev, generator=g), torch.randn(C, device=dev, generator=g)
+
+    def make(c):
+        # partial sums of plausible data: sum ~ N(0, n), sumsq ~ n per tile
+        p = torch.randn(B * tiles, c, 2, device=dev, generator=g) * 3
+        p[..., 1] = p[..., 1].abs() * 4 + (hw / tiles)
+        return p.contiguous()
+
+    p0 = make(c0)
+    s0 = p0.view(B, tiles, c0, 2).sum(1).contiguous()
+    p1 = make(c1) if c1 else None
+    s1 = p1.view(B, tiles, c1, 2).sum(1).contiguous() if c1 else None
+    ref0, ref1 = torch.empty(B, c0, 2, device=dev), (torch.empty(B, c1, 2, device=dev) if c1 else None)
+    k.gn_coeffs(s0, c0, s1, c1, gamma, beta, ref0, ref1, hw, groups)
+    for mode in ((True, False), (False, True), (True, True)) if c1 else ((True, False),):
+        f0 = torch.full((B, c0, 2), float("nan"), device=dev)
+        f1 = torch.full((B, c1, 2), float("nan"), device=dev) if c1 else None
+        o0 = torch.full((B, c0, 2), float("nan"), device=dev)
+        o1 = torch.full((B, c1, 2), float("nan"), device=dev) if c1 else None
+        a0 = (None, p0, tiles, o0, c0) if mode[0] else (s0, None, 0, None, c0)
+        a1 = None
+        if c1:
+            a1 = (None, p1, tiles, o1, c1) if mode[1] else (s1, None, 0, None, c1)
+        k.gn_coeffs_partials(a0, a1, gamma, beta, f0, f1, B, hw, groups)
+        torch.cuda.synchronize()
+        if mode[0]:
+            assert (o0 - s0).abs().max().item() <= 1e-5 * s0.abs().max().item(), "reduced partials (source 0)"
+        if c1 and mode[1]:
+            assert (o1 - s1).abs().max().item() <= 1e-5 * s1.abs().max().item(), "reduced partials (source 1)"
+        assert (f0 - ref0).abs().max().item() <= 2e-4 * ref0.abs().max().item(), f"coef0 mode={mode}"
+        if c1:
+            assert (f1 - ref1).abs().max().item() <= 2e-4 * ref1.abs().max().item(), f"coef1 mode={mode}"
