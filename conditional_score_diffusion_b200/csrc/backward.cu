@@ -449,19 +449,33 @@ nchw_grad_to_nhwc_kernel(const float* __restrict__ s0, int c0, const float* __re
 }
 
 // ---- bias / time-embedding projection gradients from per-(image, channel) sums of the output gradient -----------
-__global__ void __launch_bounds__(128)
+// Block = 32 channels x 8 batch lanes: the per-image loads (and the dtproj read-modify-writes, one owner per (b, ch))
+// of the lanes are independent, so the batch loop is ~batch/8 deep instead of a serial chain of `batch` L2 round trips
+// (14 us per launch x 73 launches per training step as a one-thread-per-channel loop, ncu). The per-channel bias sum
+// is combined over the lanes in a fixed order.
+__global__ void __launch_bounds__(256)
 bias_temb_grad_kernel(const float* __restrict__ sums, int sums_c, int batch, int c, float scale, float* dbias0,
                       float* dbias1, float* dtproj, int tpitch) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, by = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  for (int b = 0; b < batch; ++b) {
-    const float v = sums[((long long)b * sums_c + ch) * 2] * scale;
-    acc += v;
-    if (dtproj != nullptr) dtproj[(long long)b * tpitch + ch] += v;
+  if (ch < c) {
+    for (int b = by; b < batch; b += 8) {
+      const float v = sums[((long long)b * sums_c + ch) * 2] * scale;
+      acc += v;
+      if (dtproj != nullptr) dtproj[(long long)b * tpitch + ch] += v;
+    }
   }
-  if (dbias0 != nullptr) dbias0[ch] += acc;
-  if (dbias1 != nullptr) dbias1[ch] += acc;
+  red[by][lane] = acc;
+  __syncthreads();
+  if (by == 0 && ch < c) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += red[k][lane];
+    if (dbias0 != nullptr) dbias0[ch] += a;
+    if (dbias1 != nullptr) dbias1[ch] += a;
+  }
 }
 
 // ---- small fp32 GEMM (time-embedding MLP and Dense_0 projections; <= 1 GFLOP per call) ---------------------------
@@ -738,8 +752,8 @@ int csd_bias_temb_grad_f32(const float* chan_sums, int sums_c, int batch, int c,
                            float* dbias1, float* dtproj, int tproj_pitch, csd_stream_t stream) {
   using namespace csd;
   CSD_REQUIRE(chan_sums && batch >= 1 && c >= 1 && sums_c >= c, "bias_temb_grad: bad arguments");
-  bias_temb_grad_kernel<<<ceil_div(c, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(chan_sums, sums_c, batch, c, scale,
-                                                                                      dbias0, dbias1, dtproj, tproj_pitch);
+  bias_temb_grad_kernel<<<ceil_div(c, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(chan_sums, sums_c, batch, c, scale,
+                                                                                     dbias0, dbias1, dtproj, tproj_pitch);
   CSD_LAUNCH_CHECK("bias_temb_grad_kernel");
   return CSD_OK;
 }

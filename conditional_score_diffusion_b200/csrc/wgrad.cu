@@ -269,6 +269,32 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int
   }
 }
 
+// nn.Conv2d 3x3 layout ([Cout, Cin, 3, 3]: s_ci = 9, s_tap = 1): the generic kernel above writes with a 36-byte stride
+// between neighbouring threads (one sector per 4-byte store). Here a block owns (co, 32 input channels): warp `tap`
+// sums the splits of its tap with coalesced 128-byte reads (same split order as above: bitwise the same sums), the
+// 9 x 32 results turn through shared memory and leave as 288 consecutive floats.
+__global__ void __launch_bounds__(288)
+wgrad_reduce_conv9_kernel(const float* __restrict__ partial, int splits, int cout, int cin, float scale,
+                          float* __restrict__ dw, long long s_co, int ci_off, int accumulate) {
+  __shared__ float tile[9][33];
+  const int co = blockIdx.y, ci0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, tap = threadIdx.x >> 5;
+  const long long per_split = 9LL * cout * cin;
+  float acc = 0.f;
+  if (ci0 + lane < cin) {
+    const float* p = partial + ((long long)tap * cout + co) * cin + ci0 + lane;
+    for (int s = 0; s < splits; ++s) acc += p[(long long)s * per_split];
+  }
+  tile[tap][lane] = acc * scale;
+  __syncthreads();
+  const int cl = threadIdx.x / 9, tp = threadIdx.x - cl * 9;   // output order: ci_local * 9 + tap
+  if (ci0 + cl < cin) {
+    float* o = dw + co * s_co + (long long)(ci_off + ci0 + cl) * 9 + tp;
+    const float v = tile[tp][cl];
+    *o = accumulate ? (*o + v) : v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Direct wgrad: MN-major operands straight from the NHWC tensors (no pixel-major copies)
 // ---------------------------------------------------------------------------------------------------------
@@ -657,6 +683,13 @@ int csd_wgrad_reduce_f32(const float* partial, int splits, int taps, int cout, i
   using namespace csd;
   CSD_REQUIRE(partial && dw && splits >= 1 && taps >= 1 && cout >= 1 && cin >= 1, "wgrad_reduce: bad arguments");
   const long long per_split = (long long)taps * cout * cin;
+  if (taps == 9 && stride_tap == 1 && stride_ci == 9 && cout <= 65535) {
+    wgrad_reduce_conv9_kernel<<<dim3((unsigned)ceil_div(cin, 32), (unsigned)cout), 288, 0,
+                                static_cast<cudaStream_t>(stream)>>>(partial, splits, cout, cin, scale, dw, stride_co, ci_off,
+                                                                     accumulate);
+    CSD_LAUNCH_CHECK("wgrad_reduce_conv9_kernel");
+    return CSD_OK;
+  }
   const int blocks = (int)std::min<long long>(ceil_div_ll(per_split, 256), (long long)num_sms() * 8);
   wgrad_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, splits, taps, cout, cin, scale, dw,
                                                                            stride_co, stride_ci, stride_tap, ci_off,
