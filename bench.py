@@ -39,22 +39,10 @@ EPS = 1e-5
 METRIC = "sampled images/sec NCSN++ 160px VE PC-1000"
 
 
-def workload_config(image=IMAGE, nf=96, ch_mult=(1, 1, 2, 2, 3, 3), attn=(20, 10, 5), num_res_blocks=2):
-    """configs/ve/inverse_problems/super_resolution/celebA_ours_NDV_160.py:83-144 with
-    model.name='ncsnpp_paired'  and init_scale=1."""
-    ns = SimpleNamespace
-    return ns(
-        training=ns(continuous=True),
-        data=ns(image_size=image, effective_image_size=image, num_channels=6, centered=False),
-        model=ns(name="ncsnpp_paired", nf=nf, ch_mult=ch_mult, num_res_blocks=num_res_blocks,
-                 attn_resolutions=attn, dropout=0.1, resamp_with_conv=True, conditional=True, fir=True,
-                 fir_kernel=[1, 3, 3, 1], skip_rescale=True, resblock_type="biggan", progressive="output_skip",
-                 progressive_input="input_skip", progressive_combine="sum", embedding_type="positional",
-                 init_scale=1.0, fourier_scale=16, nonlinearity="swish", num_scales=1000,
-                 sigma_max_x=math.sqrt(3 * image * image), sigma_max_y=0.5, sigma_min_x=5e-3, sigma_min_y=5e-3),
-        sampling=ns(method="pc", predictor="conditional_reverse_diffusion", corrector="conditional_langevin",
-                    n_steps_each=1, noise_removal=True, probability_flow=False, snr=SNR),
-    )
+def workload_config():
+    """BASELINE configs[1] in its NCSN++ form (conditional_score_diffusion_b200/workloads.py)."""
+    from conditional_score_diffusion_b200 import workloads
+    return workloads.config2_ncsnpp_paired_160()
 
 
 _SAVED_STDOUT = []
@@ -188,6 +176,52 @@ def cpu_oracle_steps(cfg, sample_batch, steps, warmup, time_budget_s):
             "images_per_s": sample_batch / (s_per_step * PC_STEPS)}
 
 
+def bench_state_dict(cfg):
+    """The bench network's weights (seed 0, init_scale = 1) as a CPU state dict: the reference's own modules load it
+    strictly (same parameter names and shapes = the checkpoint contract)."""
+    import torch
+    from conditional_score_diffusion_b200.models import ncsnpp, utils  # noqa: F401  (parameter container only)
+    torch.manual_seed(0)
+    model = utils.create_model(cfg)
+    return {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+
+def reference_cpu_steps(cfg, sample_batch, steps, warmup):
+    """Time the UNMODIFIED reference (baseline/_ref: sampling/conditional.py:47-228 driving models/ncsnpp.py) on the
+    host cores; falls back to the oracle port when baseline/_ref did not travel. Returns (result, kind)."""
+    import torch
+    from baseline import ref_harness
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if not ref_harness.available():
+        r = cpu_oracle_steps(cfg, sample_batch, steps, warmup, time_budget_s=150.0)
+        return r, "port"
+    torch.manual_seed(1)
+    y = torch.rand(sample_batch, 3, cfg.data.image_size, cfg.data.image_size)
+    r = ref_harness.conditional_pc_time(cfg, bench_state_dict(cfg), y, steps, warmup, "cpu", SNR, EPS)
+    return {"s_per_step": r["s_per_step"], "steps_timed": r["steps"], "cores": cores, "finite": r["finite"],
+            "images_per_s": sample_batch / (r["s_per_step"] * PC_STEPS)}, "reference"
+
+
+def stock_gpu_steps(cfg, batch, steps, warmup, device):
+    """The denominator of the north star's ">= 10x stock PyTorch + cuDNN": the UNMODIFIED reference on the same B200 -
+    its own eager modules, fp32 storage, PyTorch defaults (cuDNN convolutions with TF32 allowed, fp32 matmul), its own
+    JIT-built `upfirdn2d` CUDA op (pre-built by baseline/install_ref.py from the reference's sources)."""
+    import torch
+    from baseline import ref_harness
+    if not ref_harness.available():
+        return None
+    torch.manual_seed(2)
+    y = torch.rand(batch, 3, cfg.data.image_size, cfg.data.image_size)
+    r = ref_harness.conditional_pc_time(cfg, bench_state_dict(cfg), y, steps, warmup, device, SNR, EPS)
+    torch.cuda.empty_cache()
+    ms = r["s_per_step"] * 1e3
+    return {"ms_per_step": ms, "images_per_s": batch / (r["s_per_step"] * PC_STEPS), "batch": batch, "steps": steps,
+            "warmup_steps": warmup, "finite_output": r["finite"], "dtype": "f32 storage, cuDNN TF32 convolutions (PyTorch defaults)",
+            "what": "unmodified reference (baseline/_ref) on cuda: sampling/conditional.py PC loop, models/ncsnpp.py eager "
+                    "modules, the reference's own upfirdn2d CUDA extension"}
+
+
 def torch_eager_gpu_steps(cfg, batch, steps, warmup):
     """Context number, not a contract arm: the oracle's plain-PyTorch restatement of the reference path run on
     cuda:0 with PyTorch defaults (fp32 storage, cuDNN convolutions with TF32 allowed, fp32 matmul, eager launches) -
@@ -249,17 +283,20 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = workload_config()
-    sample_b = 1
-    r = cpu_oracle_steps(cfg, sample_b, args.steps, min(args.warmup, 1), time_budget_s=150.0)
-    sample = (f"batch {sample_b} of {BATCH_PER_GPU}, {r['steps_timed']} PC steps timed after 1 warm-up, oracle port of "
-              f"the reference path (torch CPU fp32), {r['cores']} threads")
+    sample_b = 2
+    steps = max(1, min(args.steps, 20))
+    r, kind = reference_cpu_steps(cfg, sample_b, steps, 1)
+    what = ("the unmodified reference (baseline/_ref: sampling/conditional.py + models/ncsnpp.py, torch CPU fp32)"
+            if kind == "reference" else "oracle port of the reference path (torch CPU fp32)")
+    sample = (f"batch {sample_b} of {BATCH_PER_GPU}, {r['steps_timed']} PC steps timed after 1 warm-up step, {what}, "
+              f"{r['cores']} threads, extrapolated x1000 steps")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["images_per_s"], "unit": "images/s", "n_gpus": args.gpus,
-        "steps": r["steps_timed"], "warmup": min(args.warmup, 1), "ms_per_step": r["s_per_step"] * 1e3,
+        "steps": r["steps_timed"], "warmup": 1, "ms_per_step": r["s_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "celebA_ours_NDV_160 as ncsnpp_paired nf96, conditional PC-1000, 160x160",
                    "batch_per_step": sample_b, "pc_steps_per_image": PC_STEPS},
-        "cpu_baseline": {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port",
+        "cpu_baseline": {"value": r["images_per_s"], "unit": "images/s", "cores": r["cores"], "kind": kind,
                          "sample": sample},
         "e2e": {"value": r["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -270,10 +307,25 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def identity_segments(eng):
+    """wt data_ptr -> per-segment flag 'identity weights' (a residual riding as a K segment): those MACs are not
+    algorithmic work of the reference's network and are left out of every FLOP figure."""
+    from conditional_score_diffusion_b200.engine import PackedConv
+    table = {}
+
+    def add(obj):
+        if isinstance(obj, PackedConv):
+            table[obj.wt.data_ptr()] = [any(s.kind == "eye" for s in seg) for seg in obj.segs]
+
+    eng._walk_packed(add)
+    return table
+
+
 def conv_profile(plan):
     """CUDA-event time and algorithmic FLOPs of every tcgen05 conv/GEMM launch of one forward."""
     import torch
     from conditional_score_diffusion_b200 import kernels as K
+    eye = identity_segments(plan.eng)
     ev = []
     torch.cuda.synchronize()
     for fn, a, kw in plan.rec.ops:
@@ -284,7 +336,8 @@ def conv_profile(plan):
             e1.record()
             segs, _, n, _ = a
             pixels = kw["batch"] * kw["h"] * kw["w"] * kw.get("z_batches", 1)
-            k_real = sum(sg[4] * sg[3] for sg in segs)
+            flags = eye.get(a[1].data_ptr(), [])
+            k_real = sum(sg[4] * sg[3] for i, sg in enumerate(segs) if not (i < len(flags) and flags[i]))
             ev.append((e0, e1, 2.0 * pixels * n * k_real, (kw["h"], kw["w"], n, k_real), bool(kw.get("transposed"))))
         else:
             fn(*a, **kw)
@@ -302,6 +355,32 @@ def ncu_traffic(kernel):
             return json.load(f)[kernel]["dram_bytes_per_launch"]
     except Exception:
         return None
+
+
+def network_parity(cfg, model, dev, precision="bf16"):
+    """max / L2 relative error of the benchmarked network (the bench weights, B = 2, sigma-scaled inputs) against the
+    CPU oracle restatement of models/ncsnpp.py (pinned to the unmodified reference by tests/test_oracle_golden.py)."""
+    import torch
+    from oracle import ncsnpp as o_net
+    g = torch.Generator().manual_seed(77)
+    hw = cfg.data.image_size
+    x = torch.randn(2, 3, hw, hw, generator=g) * 20.0
+    y = torch.rand(2, 3, hw, hw, generator=g)
+    labels = torch.tensor([700.0, 150.0])
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    o = o_net.model_options(cfg)
+    with torch.no_grad():
+        ref = o_net.forward_paired(sd, o, x, y, labels)
+        out = model({"x": x.to(dev), "y": y.to(dev)}, labels.to(dev))
+    res = {"config": "configs[1] network (ncsnpp_paired 160 px nf 96), bench weights, B=2, vs CPU fp32 oracle",
+           "precision": precision}
+    mx = l2 = 0.0
+    for k in ("x", "y"):
+        got, r = out[k].float().cpu(), ref[k]
+        mx = max(mx, (got - r).abs().max().item() / (r.abs().max().item() + 1e-30))
+        l2 = max(l2, ((got - r).norm() / (r.norm() + 1e-30)).item())
+    res["max_rel"], res["l2_rel"] = mx, l2
+    return res
 
 
 def run_b200(args):
@@ -452,10 +531,22 @@ def run_b200(args):
                                   "algorithmic_gflop_per_forward": (tp_fl + tap_fl + heads_fl) / 1e9,
                                   "achieved_tflops": (tp_fl + tap_fl + heads_fl) / ((tp_ms + tap_ms + heads_ms) * 1e-3) / 1e12}}
 
-    # ---- CPU baseline (oracle port) on a bounded sample ----
-    cpu = cpu_oracle_steps(cfg, 1, 3, 1, time_budget_s=60.0)
-    cpu_baseline = {"value": cpu["images_per_s"], "unit": "images/s", "cores": cpu["cores"], "kind": "port",
-                    "sample": f"batch 1 of {B}, {cpu['steps_timed']} PC steps after 1 warm-up, oracle port (torch CPU "
+    # ---- parity of the benchmarked network (same weights, B = 2) against the CPU oracle ----
+    parity = network_parity(cfg, model, dev)
+
+    # ---- stock PyTorch + cuDNN on the same GPU: the unmodified reference, B = 64 ----
+    stock = None
+    if not args.no_stock_gpu:
+        try:
+            stock = stock_gpu_steps(cfg, B, 5, 2, dev)
+        except Exception as e:  # noqa: BLE001 - the leg is context; the b200 line must still print
+            stock = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+    # ---- CPU baseline: the unmodified reference on the host cores, bounded sample ----
+    cpu, cpu_kind = reference_cpu_steps(cfg, 2, 3, 1)
+    cpu_what = "unmodified reference (baseline/_ref)" if cpu_kind == "reference" else "oracle port"
+    cpu_baseline = {"value": cpu["images_per_s"], "unit": "images/s", "cores": cpu["cores"], "kind": cpu_kind,
+                    "sample": f"batch 2 of {B}, {cpu['steps_timed']} PC steps after 1 warm-up step, {cpu_what} (torch CPU "
                               f"fp32, {cpu['cores']} threads), extrapolated x1000 steps"}
 
     line = {
@@ -471,8 +562,12 @@ def run_b200(args):
                    "weights": "random init, init_scale=1", "finite_output": finite},
         "e2e": e2e, "gpu_launches": int(launches_per_step * k_eff), "launches_per_step": int(launches_per_step),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info,
-        "plan_buffers_gb": fs.plan.pool.nbytes() / 1e9,
+        "plan_buffers_gb": fs.plan.pool.nbytes() / 1e9, "parity": parity,
     }
+    if stock is not None:
+        line["stock_gpu"] = stock
+        if "ms_per_step" in stock:
+            line["vs_stock_gpu"] = stock["ms_per_step"] / ms_per_step
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -659,6 +754,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)  # 200 of the 1000 identical steps
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_eager_gpu"])
+    ap.add_argument("--no-stock-gpu", action="store_true", help="skip the stock PyTorch + cuDNN leg (the unmodified "
+                    "reference on the same GPU)")
     ap.add_argument("--torch-optim", action="store_true", help="train workload: torch Adam instead of the fused optimizer")
     ap.add_argument("--workload", default="sample", choices=["sample", "train"],
                     help="sample = the headline PC-1000 sampling line (default); train = BASELINE configs[3] training step")

@@ -44,6 +44,9 @@ def broadcast_parameters(module, src=0):
         n = t.numel()
         t.copy_(flat[off:off + n].view_as(t))
         off += n
+    eng = getattr(module, "_engine", None)
+    if eng is not None:
+        eng.invalidate()      # written through .data: autograd's version counters did not move
     return flat.numel() * 4
 
 

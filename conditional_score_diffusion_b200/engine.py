@@ -619,15 +619,22 @@ class NetEngine:
     def _structure(self):
         return tuple((id(p), p.data_ptr(), p.device) for p in self.net.parameters())
 
-    def ensure_packed(self, device):
+    def ensure_packed(self, device, force_refresh=False):
+        """Make the packed operands current. Staleness is detected through the parameters' autograd version counters,
+        which in-place ops (optimizer steps, `p.copy_`) bump - but writes through `p.data` (the reference's EMA
+        `copy_to` / `restore`, models/ema.py:111,149; DDP-style broadcasts) do not. Callers that cannot know how the
+        weights were last written (inference entry points: the eval forward, the samplers) pass force_refresh=True: one
+        csd_pack_weights launch (0.3 ms for 48.5 M parameters) re-packs from the live parameters unconditionally."""
         v = self._version()
-        if self.packed is not None and self.param_version == v and self.device == device:
+        st = self._structure()
+        same_home = (self.packed is not None and self.device == device and self.param_structure == st)
+        if same_home and self.param_version == v:
+            if force_refresh and not torch.cuda.is_current_stream_capturing():
+                self._refresh()
             return
         if device.type != "cuda":
             raise CsdError("the score network runs on CUDA only (libcsd_b200 has no CPU path)")
-        st = self._structure()
-        if (self.packed is not None and self.device == device and self.param_structure == st
-                and all(p.device == device for p in self.net.parameters())):
+        if same_home and all(p.device == device for p in self.net.parameters()):
             # same parameter tensors, new values (an optimizer step): re-pack in place, recorded plans stay valid
             self._refresh()
             self.param_version = v

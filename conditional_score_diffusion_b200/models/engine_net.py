@@ -103,7 +103,8 @@ class EngineNet(_Base):
             raise NotImplementedError("train-mode dropout without autograd (torch.no_grad() on a .train() network) is "
                                       "not planned by the B200 engine; call .eval() for inference")
         eng = self._engine
-        eng.ensure_packed(x0.device)
+        # inference entry: weights may have been swapped through `.data` (EMA copy_to/restore) - always re-pack
+        eng.ensure_packed(x0.device, force_refresh=not (want_p or want_in))
         b, c0, h, w = x0.shape
         c1 = x1.shape[1] if x1 is not None else 0
         if c0 + c1 != self.in_channels:

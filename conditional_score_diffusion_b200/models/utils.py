@@ -177,17 +177,64 @@ def from_flattened_numpy(x, shape):
     return torch.from_numpy(x.reshape(shape))
 
 
-def load_lightning_checkpoint(model, path_or_state, ema=False, strict=True):
+def load_lightning_checkpoint(model, path_or_state, ema=None, strict=True):
     """Load a checkpoint written by the reference's Lightning modules into an engine-backed network.
 
     The reference saves `pl_module.state_dict()`, whose score-network entries are keyed `score_model.all_modules.<i>...`
-    (lightning_modules/BaseSdeGenerativeModel.py:22-23), next to `hyper_parameters`. `path_or_state` is a checkpoint
-    path, the loaded checkpoint dict, or a bare state dict; the `score_model.` prefix is stripped and the rest loaded
-    with the reference's own key names (the positional `all_modules` order is identical here). Returns the
-    (missing, unexpected) keys of load_state_dict."""
+    (lightning_modules/BaseSdeGenerativeModel.py:22-23), next to `hyper_parameters` (the whole config,
+    BaseSdeGenerativeModel.py:17). `path_or_state` is a checkpoint path, the loaded checkpoint dict, or a bare state
+    dict; the `score_model.` prefix is stripped and the rest loaded with the reference's own key names (the positional
+    `all_modules` order is identical here). ema: an `models.ema.ExponentialMovingAverage` to restore from the
+    checkpoint's `ema_state` entry (written by save_lightning_checkpoint; reference checkpoints have none -
+    lightning_callbacks/callbacks.py:119-133 never saves the shadows - in which case the EMA is re-seeded from the loaded
+    weights). Returns the (missing, unexpected) keys of load_state_dict."""
     ckpt = torch.load(path_or_state, map_location="cpu", weights_only=False) if isinstance(path_or_state, str) else path_or_state
     state = ckpt.get("state_dict", ckpt) if isinstance(ckpt, dict) else ckpt
     prefix = "score_model."
     if any(k.startswith(prefix) for k in state):
         state = {k[len(prefix):]: v for k, v in state.items() if k.startswith(prefix)}
-    return model.load_state_dict(state, strict=strict)
+    res = model.load_state_dict(state, strict=strict)
+    eng = getattr(model, "_engine", None)
+    if eng is not None:
+        eng.invalidate()
+    if ema is not None and ema is not False:
+        ema_state = ckpt.get("ema_state") if isinstance(ckpt, dict) else None
+        if ema_state is not None:
+            ema.load_state_dict(ema_state)
+        else:
+            with torch.no_grad():
+                for s, p in zip(ema.shadow_params, [p for p in model.parameters() if p.requires_grad]):
+                    s.copy_(p.detach().to(s.device))
+    return res
+
+
+def checkpoint_config(path_or_ckpt):
+    """The config a reference checkpoint was trained with: `hyper_parameters['config']` (save_hyperparameters(),
+    lightning_modules/BaseSdeGenerativeModel.py:17), or None for a bare state dict."""
+    ckpt = torch.load(path_or_ckpt, map_location="cpu", weights_only=False) if isinstance(path_or_ckpt, str) else path_or_ckpt
+    if isinstance(ckpt, dict):
+        hp = ckpt.get("hyper_parameters")
+        if isinstance(hp, dict):
+            return hp.get("config")
+    return None
+
+
+def save_lightning_checkpoint(model, path=None, config=None, ema=None, extra=None):
+    """Write the network back in the reference's Lightning checkpoint layout: `state_dict` with the `score_model.`
+    prefix (so `load_from_checkpoint`, lightning_modules/utils.py:24-28, and `resume_from_checkpoint`, run_lib.py:63,
+    read it), `hyper_parameters.config`, and - unlike the reference, whose EMACallback has no save hook - the EMA
+    shadow parameters under `ema_state` (ignored by Lightning, restored by load_lightning_checkpoint). `extra`: more
+    top-level entries (epoch, global_step, optimizer_states ...). Returns the checkpoint dict; writes it when `path`
+    is given."""
+    state = {"score_model." + k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    ckpt = {"state_dict": state, "hyper_parameters": {"config": config if config is not None else getattr(model, "config", None)}}
+    if ema is not None:
+        es = ema.state_dict()
+        ckpt["ema_state"] = {"decay": es["decay"], "num_updates": es["num_updates"],
+                             "shadow_params": [t.detach().cpu().clone() for t in es["shadow_params"]],
+                             "collected_params": [t.detach().cpu().clone() for t in es["collected_params"]]}
+    if extra:
+        ckpt.update(extra)
+    if path is not None:
+        torch.save(ckpt, path)
+    return ckpt

@@ -43,7 +43,7 @@ class FusedPCSampler:
     # ---- setup -----------------------------------------------------------------------------------
     def _setup(self, device):
         m = self.model
-        m._engine.ensure_packed(device)
+        m._engine.ensure_packed(device, force_refresh=True)
         b, c, h, w = self.shape
         c1 = c if self.conditional else 0
         if self.conditional and m.in_channels != 2 * c:
@@ -138,6 +138,16 @@ class FusedPCSampler:
         """Run the full loop. noise_source(name, step, inner) -> tensor replaces the generator
         (names 'y_c', 'x_c', 'y_p', 'x_p')."""
         device = self.model.device
+        if self.ready:
+            # the network may have new weights (load_state_dict, optimizer step, EMA swap through `.data`) or new
+            # parameter storage (.to(), a fused optimizer re-homing them) since the graphs were captured: re-pack from
+            # the live parameters on every call; if the engine rebuilt its plans, re-plan and re-capture
+            b, c, h, w = self.shape
+            eng = self.model._engine
+            eng.ensure_packed(device, force_refresh=True)
+            if eng.plan(b, h, w, c, c if self.conditional else 0) is not self.plan:
+                self.ready = False
+                self.graphs = {}
         if not self.ready:
             self._setup(device)
         if self.conditional:

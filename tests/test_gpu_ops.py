@@ -62,8 +62,10 @@ def test_upfirdn2d_hot_modes_vs_oracle(shape):
     _close(_upfirdn(x, k_dn, 1, 2, (1, 1)), o_ops.upfirdn2d(x, k_dn, 1, 2, (1, 1)), F32, f"down2 {shape}")
     _close(_upfirdn(x, k_rand, 1, 2, (1, 1)), o_ops.upfirdn2d(x, k_rand, 1, 2, (1, 1)), F32, f"down2 rand-k {shape}")
     _close(_upfirdn(x, k_rand, 1, 1, (2, 2)), o_ops.upfirdn2d(x, k_rand, 1, 1, (2, 2)), F32, f"1:1 {shape}")
-    # backward geometry of up2: down2 with g_pad = (1, 1) for k=4, pad=(2,1)  (op/upfirdn2d.py:110-113)
-    _close(_upfirdn(x, k_rand, 1, 2, (1, 1)), o_ops.upfirdn2d(x, k_rand, 1, 2, (1, 1)), F32, f"bwd-of-up2 {shape}")
+    # backward geometry of up2: up/down swapped, the FLIPPED kernel, g_pad = (1, 1) for k=4, pad=(2,1)
+    # (op/upfirdn2d.py:25-44,110-113)
+    k_flip = torch.flip(k_rand, [0, 1])
+    _close(_upfirdn(x, k_flip, 1, 2, (1, 1)), o_ops.upfirdn2d(x, k_flip, 1, 2, (1, 1)), F32, f"bwd-of-up2 {shape}")
 
 
 def test_upfirdn2d_generic_paths():
@@ -299,3 +301,84 @@ def test_layout_softmax_temb_dense():
     o70 = torch.empty(70, 130, device="cuda")
     k_.dense_rows(a70.cuda(), w70.cuda(), None, o70)
     _close(o70, F.linear(a70, w70), 1e-5, "dense rows ragged, no bias")
+
+
+# ---- module surface: the autograd Functions around the kernels (op/upfirdn2d.py:19-142, op/fused_act.py:20-97) ----
+@pytest.mark.parametrize("up,down,pad", [(2, 1, (2, 1)), (1, 2, (1, 1)), (1, 1, (2, 2))])
+def test_op_upfirdn2d_autograd_grad_and_double_backward(up, down, pad):
+    """`op.upfirdn2d` is differentiable with a defined double backward (UpFirDn2d / UpFirDn2dBackward): first and
+    second derivatives against torch autograd through the oracle's plain-PyTorch restatement."""
+    from conditional_score_diffusion_b200.op import upfirdn2d
+    g = torch.Generator().manual_seed(11 * up + down)
+    x = torch.randn(2, 3, 12, 10, generator=g)
+    k = torch.rand(4, 4, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = o_ops.upfirdn2d(xr, k, up, down, pad)
+    w = torch.randn(yr.shape, generator=g)
+    v = torch.randn(x.shape, generator=g)
+    (gr,) = torch.autograd.grad((yr * w).sum(), xr, create_graph=True)
+    wr = w.clone().requires_grad_(True)
+    yr2 = o_ops.upfirdn2d(xr, k, up, down, pad)
+    (gr2,) = torch.autograd.grad((yr2 * wr).sum(), xr, create_graph=True)
+    (ggr,) = torch.autograd.grad((gr2 * v).sum(), wr)            # d/dw <grad_x, v> = forward op applied to v
+
+    xc = x.cuda().requires_grad_(True)
+    wc = w.cuda().requires_grad_(True)
+    yc = upfirdn2d(xc, k.cuda(), up=up, down=down, pad=pad)
+    _close(yc.detach(), yr.detach(), F32, "op.upfirdn2d forward")
+    (gc,) = torch.autograd.grad((yc * wc).sum(), xc, create_graph=True)
+    _close(gc.detach(), gr.detach(), F32, "op.upfirdn2d grad")
+    (ggc,) = torch.autograd.grad((gc * v.cuda()).sum(), wc)      # runs UpFirDn2dBackward.backward
+    _close(ggc, ggr, F32, "op.upfirdn2d double backward")
+
+
+def test_upsample_downsample_2d_module_surface():
+    """models/up_or_down_sampling.py:195-257 (`upsample_2d`, `downsample_2d`) incl. their gradients."""
+    from conditional_score_diffusion_b200.models import up_or_down_sampling as uds
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 4, 10, 14, generator=g)
+    for fn, ofn in ((uds.upsample_2d, o_ops.upsample_2d), (uds.downsample_2d, o_ops.downsample_2d)):
+        xr = x.clone().requires_grad_(True)
+        yr = ofn(xr, (1, 3, 3, 1), factor=2)
+        w = torch.randn(yr.shape, generator=g)
+        (gr,) = torch.autograd.grad((yr * w).sum(), xr)
+        xc = x.cuda().requires_grad_(True)
+        yc = fn(xc, (1, 3, 3, 1), factor=2)
+        (gc,) = torch.autograd.grad((yc * w.cuda()).sum(), xc)
+        _close(yc.detach(), yr.detach(), F32, f"{fn.__name__} forward")
+        _close(gc, gr, F32, f"{fn.__name__} grad")
+
+
+def test_fused_leaky_relu_module_autograd():
+    """`FusedLeakyReLU` / `fused_leaky_relu` forward, gradients w.r.t. input and bias, and the double backward
+    (op/fused_act.py:20-97) against torch autograd of leaky_relu(x + b) * scale."""
+    import torch.nn.functional as F
+    from conditional_score_diffusion_b200.op import FusedLeakyReLU, fused_leaky_relu
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(3, 6, 5, 7, generator=g)
+    b = torch.randn(6, generator=g)
+    w = torch.randn(3, 6, 5, 7, generator=g)
+    v = torch.randn(3, 6, 5, 7, generator=g)
+
+    def ref(xx, bb):
+        return F.leaky_relu(xx + bb.view(1, -1, 1, 1), 0.2) * (2 ** 0.5)
+
+    xr, br = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    yr = ref(xr, br)
+    gxr, gbr = torch.autograd.grad((yr * wr).sum(), (xr, br), create_graph=True)
+    (ggr,) = torch.autograd.grad((gxr * v).sum(), wr)
+
+    xc, bc = x.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    wc = w.cuda().requires_grad_(True)
+    yc = fused_leaky_relu(xc, bc, 0.2, 2 ** 0.5)
+    _close(yc.detach(), yr.detach(), F32, "fused_leaky_relu forward")
+    gxc, gbc = torch.autograd.grad((yc * wc).sum(), (xc, bc), create_graph=True)
+    _close(gxc.detach(), gxr.detach(), F32, "fused_leaky_relu grad input")
+    _close(gbc.detach(), gbr.detach(), F32, "fused_leaky_relu grad bias")
+    (ggc,) = torch.autograd.grad((gxc * v.cuda()).sum(), wc)
+    _close(ggc, ggr, F32, "fused_leaky_relu double backward")
+    mod = FusedLeakyReLU(6).cuda()
+    with torch.no_grad():
+        mod.bias.copy_(b)
+    _close(mod(x.cuda()).detach(), yr.detach(), F32, "FusedLeakyReLU module")
