@@ -135,6 +135,13 @@ def conditional_pc_time(cfg_ns, state_dict, y, steps, warmup_steps, device, snr,
     cm = cfg_ns.model
     sde = {"x": m.sde_lib.cVESDE(cm.sigma_min_x, cm.sigma_max_x, n_scales),
            "y": m.sde_lib.VESDE(cm.sigma_min_y, cm.sigma_max_y, n_scales)}
+    if dev.type == "cuda":
+        # sde_lib.py:359,415 index the CPU table `discrete_sigmas` with a CUDA index tensor - accepted by the torch 1.x the
+        # reference was written for, rejected by torch 2.11 ("indices should be either on cpu or on the same device").
+        # The table is moved to the device on the INSTANCES (the `.to(t.device)` the reference then does is a no-op);
+        # the reference's files stay byte-identical.
+        for s_ in sde.values():
+            s_.discrete_sigmas = s_.discrete_sigmas.to(dev)
     shape = tuple(y.shape)
     pred = m.predictors.get_predictor("conditional_reverse_diffusion")
     corr = m.correctors.get_corrector("conditional_langevin")

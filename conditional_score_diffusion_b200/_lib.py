@@ -71,6 +71,8 @@ class ConvGemmDesc(ctypes.Structure):
         ("res_z_stride", c_int64),
         ("scale", c_float),
         ("stat_partials", c_void_p),
+        ("dtype", c_int32),
+        ("reserved_", c_int32),
     ]
 
 
@@ -131,6 +133,20 @@ _PROTOTYPES = {
     "csd_fir_resample_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                            c_float_p, c_void_p]),
     "csd_softmax_rows_f32_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_float, c_void_p]),
+    # fp32-activation ("tf32" plan) variants: same argument lists as the *_bf16 entries
+    "csd_nchw_to_nhwc_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_float, c_float, c_void_p]),
+    "csd_nhwc_f32_to_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                                     c_void_p]),
+    "csd_gn_chan_stats_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "csd_gn_fused_supported_f32": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "csd_gn_fused_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "csd_gn_apply_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "csd_fir_resample_nhwc_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                          c_float_p, c_void_p]),
+    "csd_softmax_rows_f32_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_float, c_void_p]),
     "csd_time_embedding_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p]),
     "csd_dense_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

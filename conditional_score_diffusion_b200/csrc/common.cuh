@@ -103,6 +103,42 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
   return p;
 }
 
+// 32-byte vector of 8 fp32 values: the fp32-activation ("tf32" precision) counterpart of bf16x8. Kernels that walk
+// NHWC activations are templates over the vector type; channel pitches are multiples of 8, so both are aligned.
+struct __align__(32) f32x8 {
+  float4 lo, hi;
+};
+
+__device__ __forceinline__ void unpack8(const f32x8& p, float* f) {
+  f[0] = p.lo.x; f[1] = p.lo.y; f[2] = p.lo.z; f[3] = p.lo.w;
+  f[4] = p.hi.x; f[5] = p.hi.y; f[6] = p.hi.z; f[7] = p.hi.w;
+}
+
+template <typename VT> __device__ __forceinline__ VT pack8_as(const float* f);
+template <> __device__ __forceinline__ bf16x8 pack8_as<bf16x8>(const float* f) { return pack8(f); }
+template <> __device__ __forceinline__ f32x8 pack8_as<f32x8>(const float* f) {
+  f32x8 p;
+  p.lo = make_float4(f[0], f[1], f[2], f[3]);
+  p.hi = make_float4(f[4], f[5], f[6], f[7]);
+  return p;
+}
+
+// SiLU per storage precision: the fast-division form for bf16 storage (error far below the bf16 rounding of the
+// result), the full-precision form for fp32 storage (the "tf32" plan is held to 1e-3 against the fp32 oracle).
+template <typename VT> __device__ __forceinline__ float silu_act(float v);
+template <> __device__ __forceinline__ float silu_act<bf16x8>(float v) { return silu_f(v); }
+template <> __device__ __forceinline__ float silu_act<f32x8>(float v) { return v / (1.0f + expf(-v)); }
+
+// scalar element type of a vector type
+template <typename VT> struct ElemOf;
+template <> struct ElemOf<bf16x8> { using type = __nv_bfloat16; };
+template <> struct ElemOf<f32x8> { using type = float; };
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+
 // Streaming 16-byte global load/store (read-once data: keep it out of L1).
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 r;

@@ -103,12 +103,17 @@ struct ConvGemmKernelParams {
 // Latency hiding: the per-column addend (bias + temb) comes from a shared-memory table built while the
 // main loop runs (s_add, may be null), and the residual of chunk k+1 is fetched while chunk k's
 // tcgen05.ld is in flight, so no global-load latency sits between TMEM read and the store.
+template <bool kF32>
 __device__ __forceinline__ void epilogue_rows(const ConvGemmKernelParams& p, uint32_t t_row, bool valid, long long pix,
                                               int b, int n0, int z, const float* s_add) {
   const float row_bias = (p.bias != nullptr && p.bias_per_row && valid) ? p.bias[pix] : 0.0f;
   const float* temb_row = (p.temb != nullptr && valid) ? p.temb + (long long)b * p.temb_pitch : nullptr;
   const __nv_bfloat16* res_row =
-      (p.res != nullptr && valid) ? p.res + (long long)z * p.res_z_stride + pix * p.res_pitch : nullptr;
+      (!kF32 && p.res != nullptr && valid) ? p.res + (long long)z * p.res_z_stride + pix * p.res_pitch : nullptr;
+  // fp32-activation plan: the residual is an fp32 tensor addressed like the output
+  const float* res_row_f = (kF32 && p.res != nullptr && valid)
+                               ? reinterpret_cast<const float*>(p.res) + (long long)z * p.res_z_stride + pix * p.res_pitch
+                               : nullptr;
   const int ncols = min(p.n_tile, p.n_store - n0);  // columns of this tile that are stored
   uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
   if (res_row != nullptr && ncols >= 16) {
@@ -172,10 +177,23 @@ __device__ __forceinline__ void epilogue_rows(const ConvGemmKernelParams& p, uin
             if (i < cnt) v[i] += __bfloat162float(res_row[n + i]);
         }
       }
+      if (kF32 && res_row_f != nullptr) {
+        if (cnt == 16) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(res_row_f + n + i));
+            v[i] += a.x; v[i + 1] += a.y; v[i + 2] += a.z; v[i + 3] += a.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < cnt) v[i] += __ldg(res_row_f + n + i);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] *= p.scale;
 
-      if (p.out_f32) {
+      if (kF32 || p.out_f32) {
         float* op = reinterpret_cast<float*>(p.out) + (long long)z * p.out_z_stride + pix * p.out_pitch + n;
         if (cnt == 16) {
 #pragma unroll
@@ -230,15 +248,16 @@ __device__ __forceinline__ const float* build_addend_table(const ConvGemmKernelP
 // tools/tap_nodata_probe.py: the K loop takes the same time with and without data), so the stage has to carry
 // more tensor work than that; the weight K layout stays taps x ceil32(C): a 64-channel box that runs past the end
 // of a tap reads the next tap's columns against activation channels the TMA unit zero-fills.
-template <int kChunk>
+template <int kChunk, bool kTf32>
 __global__ void __launch_bounds__(kTapThreads)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                  const __grid_constant__ CUtensorMap mapB, const ConvGemmKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr uint32_t kARows = kTileM * kChunk * 2;                 // bytes of the A part of a stage
-  constexpr uint32_t kLayout = kChunk == 64 ? 2u : kLayoutSw64;    // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
-  constexpr uint32_t kSbo = 8u * kChunk * 2;                       // 8 rows of the swizzle atom
+  constexpr uint32_t kRowB = kChunk * (kTf32 ? 4 : 2);             // bytes per operand row of a stage: 128 or 64
+  constexpr uint32_t kARows = kTileM * kRowB;                      // bytes of the A part of a stage
+  constexpr uint32_t kLayout = kRowB == 128 ? 2u : kLayoutSw64;    // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
+  constexpr uint32_t kSbo = 8u * kRowB;                            // 8 rows of the swizzle atom
   // 1024-byte aligned base: the swizzle pattern is a function of the shared-memory address bits.
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + p.num_stages * p.stage_bytes;
@@ -339,7 +358,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     if (lane == 0) {
       // everything the loop needs lives in registers: the issuing thread's scalar work per stage is what bounds
       // the small-level launches
-      const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)p.n_sub);
+      const uint32_t idesc = kTf32 ? ptx::make_idesc_tf32_m128((uint32_t)p.n_sub) : ptx::make_idesc_bf16_m128((uint32_t)p.n_sub);
       const uint32_t hi = ptx::smem_desc_hi(kSbo, kLayout);
       const bool split = p.nsplit > 1;
       const uint32_t b2_off = p.b_box_bytes >> 4;
@@ -369,13 +388,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         ready = (it + 1 < total_iters) && ptx::mbar_test_wait(fbar, npar);
         const uint32_t b_lo = a_lo + (kARows >> 4);
 #pragma unroll
-        for (int k16 = 0; k16 < kChunk / 16; ++k16) {
+        for (int k16 = 0; k16 < (int)kRowB / 32; ++k16) {      // one MMA per 32 bytes of K: 16 bf16 or 8 tf32 values
           const uint32_t acc = (k16 == 0) ? accumulate : 1u;
-          ptx::mma_bf16_ss(tmem_d0, ptx::smem_desc_join(hi, a_lo + 2 * k16), ptx::smem_desc_join(hi, b_lo + 2 * k16), idesc,
-                           acc);
-          if (split)
-            ptx::mma_bf16_ss(tmem_d1, ptx::smem_desc_join(hi, a_lo + 2 * k16),
-                             ptx::smem_desc_join(hi, b_lo + b2_off + 2 * k16), idesc, acc);
+          if (kTf32) {
+            ptx::mma_tf32_ss(tmem_d0, ptx::smem_desc_join(hi, a_lo + 2 * k16), ptx::smem_desc_join(hi, b_lo + 2 * k16),
+                             idesc, acc);
+            if (split)
+              ptx::mma_tf32_ss(tmem_d1, ptx::smem_desc_join(hi, a_lo + 2 * k16),
+                               ptx::smem_desc_join(hi, b_lo + b2_off + 2 * k16), idesc, acc);
+          } else {
+            ptx::mma_bf16_ss(tmem_d0, ptx::smem_desc_join(hi, a_lo + 2 * k16), ptx::smem_desc_join(hi, b_lo + 2 * k16),
+                             idesc, acc);
+            if (split)
+              ptx::mma_bf16_ss(tmem_d1, ptx::smem_desc_join(hi, a_lo + 2 * k16),
+                               ptx::smem_desc_join(hi, b_lo + b2_off + 2 * k16), idesc, acc);
+          }
         }
         accumulate = 1u;
         CSD_TSM(2);
@@ -403,7 +430,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tcgen05_fence_after();
     if (threadIdx.x == 64) CSD_TS(5);
-    epilogue_rows(p, tmem_base + ((uint32_t)(q * 32) << 16), valid, pix, b, n0, z, s_add);
+    epilogue_rows<kTf32>(p, tmem_base + ((uint32_t)(q * 32) << 16), valid, pix, b, n0, z, s_add);
     if (threadIdx.x == 64) CSD_TS(6);
   }
 
@@ -569,7 +596,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const int h = h0 + kHaloTH * tt + m / kHaloTW, w = w0 + m % kHaloTW;
       const bool valid = (h < p.H) && (w < p.W);
       const long long pix = ((long long)b * p.H + h) * p.W + w;
-      epilogue_rows(p, tmem_base + ((uint32_t)(q * 32) << 16) + tt * p.n_tile, valid, pix, b, n0, 0, s_add);
+      epilogue_rows<false>(p, tmem_base + ((uint32_t)(q * 32) << 16) + tt * p.n_tile, valid, pix, b, n0, 0, s_add);
     }
     if (threadIdx.x == 64) CSD_TS(6);
   }
@@ -1029,6 +1056,7 @@ static int next_pow2_cols(int n) {
 // Host launcher shared by csd_conv_gemm and the program executor (which pre-encodes the maps).
 struct ConvGemmLaunch {
   int tap_chunk;   // channels per stage of the per-tap kernel (32 or 64)
+  bool tf32;       // fp32 activations / weights, kind::tf32 (per-tap kernel only)
   CUtensorMap mapA[CSD_MAX_SEGMENTS];
   CUtensorMap mapB;
   CUtensorMap mapOut;
@@ -1046,6 +1074,12 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   CSD_REQUIRE(d->batch >= 1 && d->h >= 1 && d->w >= 1, "bad spatial dims %d %d %d", d->batch, d->h, d->w);
   const bool t_mode = d->mode == 2;
   const bool halo_mode = d->mode == 1 || t_mode;
+  const bool tf32 = d->dtype == 1;
+  const int E = tf32 ? 4 : 2;                 // bytes per activation / weight element
+  CSD_REQUIRE(d->dtype == 0 || d->dtype == 1, "conv_gemm: dtype=%d (0 = bf16, 1 = fp32 storage / tf32 operands)", d->dtype);
+  CSD_REQUIRE(!tf32 || (!halo_mode && d->out_f32 == 1),
+              "conv_gemm: the fp32 / tf32 plan runs in the per-tap kernel (mode 0) and writes fp32");
+  L->tf32 = tf32;
   L->halo = halo_mode;
   L->transposed = t_mode;
   L->persistent = false;
@@ -1102,11 +1136,12 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
 
   // per-tap kernel: 64-channel stages unless every segment fits one 32-channel chunk (see conv_gemm_kernel)
   int tap_chunk = kChunkK;
-  if (!halo_mode && getenv("CSD_TAP_CHUNK32") == nullptr)
+  if (!halo_mode && !tf32 && getenv("CSD_TAP_CHUNK32") == nullptr)
     for (int s = 0; s < d->nseg; ++s)
       if (d->seg[s].c_cnt > kChunkK) tap_chunk = 64;
   L->tap_chunk = tap_chunk;
-  const int tap_row_bytes = tap_chunk * 2;
+  const int tap_row_bytes = tap_chunk * E;     // 128 (SWIZZLE_128B: 64 bf16 or 32 fp32 channels) or 64
+  const CUtensorMapDataType tm_dtype = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   int tap_iters = 0;
   int k_total = 0;
   int k_total_chan = 0;  // padded channels over all segments (one (scale, shift) slot each)
@@ -1134,8 +1169,8 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     const uint64_t z_extra = (uint64_t)(d->z_batches - 1) * (uint64_t)d->a_batch_step;
     uint64_t dims[4] = {(uint64_t)(sg.c_off + sg.c_cnt), (uint64_t)in_w, (uint64_t)in_h,
                         (uint64_t)d->batch + z_extra};
-    uint64_t strides[3] = {(uint64_t)sg.pitch * 2, (uint64_t)sg.pitch * 2 * in_w,
-                           (uint64_t)sg.pitch * 2 * in_w * in_h};
+    uint64_t strides[3] = {(uint64_t)sg.pitch * E, (uint64_t)sg.pitch * E * in_w,
+                           (uint64_t)sg.pitch * E * in_w * in_h};
     // with a traversal stride s the box spans (t-1)*s+1 source elements and delivers t of them
     uint32_t box[4] = {(uint32_t)(halo_mode ? kChunkK : tap_chunk), (uint32_t)((p.TW - 1) * p.stride + 1),
                        (uint32_t)((p.TH - 1) * p.stride + 1), (uint32_t)p.TB};
@@ -1145,8 +1180,8 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
       box[2] = (uint32_t)((t_mode ? p.t_rows : kHaloTH * mt) + 2 * hl);
     }
     uint32_t estr[4] = {1, (uint32_t)p.stride, (uint32_t)p.stride, 1};
-    int st = encode_tensor_map(&L->mapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, sg.a, dims, strides, box,
-                               (!halo_mode && tap_chunk == 64) ? TMA_SW_128 : TMA_SW_64, estr);
+    int st = encode_tensor_map(&L->mapA[s], tm_dtype, 4, sg.a, dims, strides, box,
+                               (!halo_mode && tap_row_bytes == 128) ? TMA_SW_128 : TMA_SW_64, estr);
     if (st != CSD_OK) return st;
   }
   for (int s = d->nseg; s < CSD_MAX_SEGMENTS; ++s) L->mapA[s] = L->mapA[0];
@@ -1155,12 +1190,12 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     // 3-D map over Wt [z][rows][k]; rows beyond wt_rows and k beyond k_total are zero-filled.
     const uint64_t zb = d->wt_batch_stride != 0 ? (uint64_t)d->z_batches : 1;
     uint64_t dims[3] = {(uint64_t)(d->wt_k_off + (d->k_valid > 0 ? d->k_valid : d->k_total)), (uint64_t)d->wt_rows, zb};
-    const uint64_t row_bytes = (uint64_t)(d->wt_pitch > 0 ? d->wt_pitch : d->k_total) * 2;
-    uint64_t strides[2] = {row_bytes, d->wt_batch_stride != 0 ? (uint64_t)d->wt_batch_stride * 2
+    const uint64_t row_bytes = (uint64_t)(d->wt_pitch > 0 ? d->wt_pitch : d->k_total) * E;
+    uint64_t strides[2] = {row_bytes, d->wt_batch_stride != 0 ? (uint64_t)d->wt_batch_stride * E
                                                                : row_bytes * (uint64_t)d->wt_rows};
     uint32_t box[3] = {(uint32_t)(halo_mode ? kChunkK : tap_chunk), (uint32_t)(t_mode ? kTChan : p.n_sub), 1};
-    int st = encode_tensor_map(&L->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, d->wt, dims, strides, box,
-                               (!halo_mode && tap_chunk == 64) ? TMA_SW_128 : TMA_SW_64);
+    int st = encode_tensor_map(&L->mapB, tm_dtype, 3, d->wt, dims, strides, box,
+                               (!halo_mode && tap_row_bytes == 128) ? TMA_SW_128 : TMA_SW_64);
     if (st != CSD_OK) return st;
   }
 
@@ -1276,8 +1311,9 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
 int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CSD_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CSD_CUDA(cudaFuncSetAttribute(conv_halo_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
@@ -1288,12 +1324,15 @@ int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
   } else if (L->halo) {
     conv_halo_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
                                                                  L->mapB, L->p);
+  } else if (L->tf32) {
+    conv_gemm_kernel<32, true><<<L->grid, kTapThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
+                                                                          L->mapB, L->p);
   } else if (L->tap_chunk == 64) {
-    conv_gemm_kernel<64><<<L->grid, kTapThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
-                                                                    L->mapB, L->p);
+    conv_gemm_kernel<64, false><<<L->grid, kTapThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2],
+                                                                           L->mapA[3], L->mapB, L->p);
   } else {
-    conv_gemm_kernel<32><<<L->grid, kTapThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
-                                                                    L->mapB, L->p);
+    conv_gemm_kernel<32, false><<<L->grid, kTapThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2],
+                                                                           L->mapA[3], L->mapB, L->p);
   }
   CSD_LAUNCH_CHECK("conv_gemm_kernel");
   return CSD_OK;

@@ -15,9 +15,10 @@
 
 namespace csd {
 
-struct GnParams {
-  const bf16x8* src0;
-  const bf16x8* src1;
+template <typename VT>
+struct GnParamsT {
+  const VT* src0;
+  const VT* src1;
   int v0, v1;          // 8-channel vectors taken from each source
   int pv0, pv1;        // pitch of each source in vectors
   int batch, hw, groups, cpg;
@@ -25,39 +26,44 @@ struct GnParams {
   float* sums1;        //                                     [batch, c1, 2]
   const float* gamma;
   const float* beta;
-  bf16x8* out;
+  VT* out;
   int out_pv;
   float eps;
   int silu;
   int slabs;
 };
+using GnParams = GnParamsT<bf16x8>;
 
-__device__ __forceinline__ bf16x8 gn_load(const GnParams& p, int b, long long pix, int v) {
+template <typename VT>
+__device__ __forceinline__ VT gn_load(const GnParamsT<VT>& p, int b, long long pix, int v) {
   if (v < p.v0) return p.src0[((long long)b * p.hw + pix) * p.pv0 + v];
   return p.src1[((long long)b * p.hw + pix) * p.pv1 + (v - p.v0)];
 }
 
-// Per-channel statistics of ONE tensor. grid = batch * slabs; block = V * PPB threads (V = vectors per
-// pixel). Dynamic smem: 2*C floats. Each tensor's sums are computed once and shared by every GroupNorm
-// that reads the tensor (the down-path activations are normalised twice: by the next block and, through
-// the skip concatenation, by the up path).
-__global__ void gn_chan_stats_kernel(GnParams p) {
-  extern __shared__ float sm[];     // [ppb][2*C] partial sums, reduced by a fixed-order tree (no shared atomics)
-  const int V = p.v0, C = V * 8;
-  const int b = blockIdx.x / p.slabs, slab = blockIdx.x % p.slabs;
-  const int ppb = blockDim.x / V;
-  const int v = threadIdx.x % V, pp = threadIdx.x / V;
-  const long long chunk = ceil_div_ll(p.hw, p.slabs);
-  const long long lo = slab * chunk, hi = min((long long)p.hw, lo + chunk);
+// Per-channel statistics of ONE tensor, deterministic (no atomics: the reference is bitwise reproducible under a seed,
+// SURVEY.md §8c). grid = (V / Vs, batch): a CTA owns Vs channel vectors of one image and walks ALL its pixels with
+// ppb = 256 / Vs pixel lanes (4 independent vector loads in flight per thread); the lanes are reduced by a
+// fixed-order tree in shared memory and the sums are stored, not accumulated. Each tensor's sums are computed once and
+// shared by every GroupNorm that reads the tensor (the down-path activations are normalised twice: by the next
+// block and, through the skip concatenation, by the up path).
+template <typename VT>
+__global__ void __launch_bounds__(256) gn_chan_stats_kernel(GnParamsT<VT> p, int Vs) {
+  extern __shared__ float sm[];     // [ppb][16 * Vs] (sum, sumsq) interleaved per channel
+  const int b = blockIdx.y;
+  const int ppb = blockDim.x / Vs;
+  const int v = threadIdx.x % Vs, pp = threadIdx.x / Vs;
+  const int gv = blockIdx.x * Vs + v;
+  const int n2 = 16 * Vs;
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  if (pp < ppb) {
-    long long pix = lo + pp;
-    for (; pix + 3LL * ppb < hi; pix += 4LL * ppb) {   // 4 independent 16-byte loads in flight
-      bf16x8 v4[4];
+  if (pp < ppb && gv < p.v0) {
+    long long pix = pp;
+    const long long hi = p.hw;
+    for (; pix + 3LL * ppb < hi; pix += 4LL * ppb) {   // 4 independent vector loads in flight
+      VT v4[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v4[u] = gn_load(p, b, pix + (long long)u * ppb, v);
+      for (int u = 0; u < 4; ++u) v4[u] = gn_load(p, b, pix + (long long)u * ppb, gv);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float f[8];
@@ -71,14 +77,16 @@ __global__ void gn_chan_stats_kernel(GnParams p) {
     }
     for (; pix < hi; pix += ppb) {
       float f[8];
-      unpack8(gn_load(p, b, pix, v), f);
+      unpack8(gn_load(p, b, pix, gv), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s[i] += f[i];
         q[i] = fmaf(f[i], f[i], q[i]);
       }
     }
-    float* row = sm + (size_t)pp * 2 * C + v * 16;   // (sum, sumsq) interleaved per channel
+  }
+  if (pp < ppb) {
+    float* row = sm + (size_t)pp * n2 + v * 16;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       row[2 * i] = s[i];
@@ -86,10 +94,20 @@ __global__ void gn_chan_stats_kernel(GnParams p) {
     }
   }
   __syncthreads();
-  for (int c2 = threadIdx.x; c2 < 2 * C; c2 += blockDim.x) {
-    float a = 0.f;
-    for (int r = 0; r < ppb; ++r) a += sm[(size_t)r * 2 * C + c2];
-    atomicAdd(p.sums0 + (long long)b * 2 * C + c2, a);
+  // fixed-order reduction over the pixel lanes: lanes are folded in halves, then one thread per slot stores
+  for (int c2 = threadIdx.x; c2 < n2; c2 += blockDim.x) {
+    const int ch = blockIdx.x * Vs * 8 + (c2 >> 1);
+    if (ch >= p.v0 * 8) continue;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int r = 0;
+    for (; r + 3 < ppb; r += 4) {
+      a0 += sm[(size_t)r * n2 + c2];
+      a1 += sm[(size_t)(r + 1) * n2 + c2];
+      a2 += sm[(size_t)(r + 2) * n2 + c2];
+      a3 += sm[(size_t)(r + 3) * n2 + c2];
+    }
+    for (; r < ppb; ++r) a0 += sm[(size_t)r * n2 + c2];
+    p.sums0[((long long)b * p.v0 * 8 + ch) * 2 + (c2 & 1)] = (a0 + a1) + (a2 + a3);
   }
 }
 
@@ -119,7 +137,8 @@ gn_finalize_partials_kernel(const float* __restrict__ partials, float* __restric
 
 // Normalise + affine (+SiLU) over the channel concatenation of up to two tensors; the group statistics
 // are assembled from the tensors' per-channel sums. Dynamic smem: 2*C + 2*G floats.
-__global__ void gn_apply_kernel(GnParams p) {
+template <typename VT>
+__global__ void gn_apply_kernel(GnParamsT<VT> p) {
   extern __shared__ float sm[];
   const int V = p.v0 + p.v1, C = V * 8, C0 = p.v0 * 8;
   float* scale = sm;
@@ -163,7 +182,7 @@ __global__ void gn_apply_kernel(GnParams p) {
   }
   long long pix = lo + pp;
   for (; pix + 3LL * ppb < hi; pix += 4LL * ppb) {
-    bf16x8 v4[4];
+    VT v4[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) v4[u] = gn_load(p, b, pix + (long long)u * ppb, v);
 #pragma unroll
@@ -173,9 +192,9 @@ __global__ void gn_apply_kernel(GnParams p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float y = fmaf(f[i], sc[i], sh[i]);
-        f[i] = p.silu ? silu_f(y) : y;
+        f[i] = p.silu ? silu_act<VT>(y) : y;
       }
-      p.out[((long long)b * p.hw + pix + (long long)u * ppb) * p.out_pv + v] = pack8(f);
+      p.out[((long long)b * p.hw + pix + (long long)u * ppb) * p.out_pv + v] = pack8_as<VT>(f);
     }
   }
   for (; pix < hi; pix += ppb) {
@@ -184,9 +203,9 @@ __global__ void gn_apply_kernel(GnParams p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float y = fmaf(f[i], sc[i], sh[i]);
-      f[i] = p.silu ? silu_f(y) : y;
+      f[i] = p.silu ? silu_act<VT>(y) : y;
     }
-    p.out[((long long)b * p.hw + pix) * p.out_pv + v] = pack8(f);
+    p.out[((long long)b * p.hw + pix) * p.out_pv + v] = pack8_as<VT>(f);
   }
 }
 
@@ -297,7 +316,8 @@ gn_coeffs_partials_kernel(GnCoefSrc s0, GnCoefSrc s1, const float* __restrict__ 
   }
 }
 
-static int gn_fill(GnParams& p, const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1, int batch,
+template <typename VT>
+static int gn_fill(GnParamsT<VT>& p, const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1, int batch,
                    int hw, int groups, int* threads, size_t* smem) {
   CSD_REQUIRE(src0 != nullptr && c0 >= 8 && c0 % 8 == 0 && pitch0 % 8 == 0 && c0 <= pitch0,
               "groupnorm: source 0 needs >= 8 channels in multiples of 8 (c=%d pitch=%d)", c0, pitch0);
@@ -308,8 +328,8 @@ static int gn_fill(GnParams& p, const void* src0, int c0, int pitch0, const void
   CSD_REQUIRE(groups >= 1 && C % groups == 0, "groupnorm: %d channels not divisible by %d groups", C, groups);
   const int V = C / 8;
   CSD_REQUIRE(V <= 1024, "groupnorm: %d channels exceed the 8192 supported", C);
-  p.src0 = static_cast<const bf16x8*>(src0);
-  p.src1 = static_cast<const bf16x8*>(src1);
+  p.src0 = static_cast<const VT*>(src0);
+  p.src1 = static_cast<const VT*>(src1);
   p.v0 = c0 / 8; p.v1 = c1 / 8; p.pv0 = pitch0 / 8; p.pv1 = src1 ? pitch1 / 8 : 0;
   p.batch = batch; p.hw = hw; p.groups = groups; p.cpg = C / groups;
   const int ppb = std::max(1, 256 / V);
@@ -337,9 +357,9 @@ struct GnFusedPlan {
   size_t smem;
 };
 
-template <int R>
+template <int R, typename VT>
 __global__ void __launch_bounds__(512)
-gn_fused_kernel(GnParams p, int Vs) {
+gn_fused_kernel(GnParamsT<VT> p, int Vs) {
   extern __shared__ float sm[];
   const int b = blockIdx.y;
   const int ppb = blockDim.x / Vs;
@@ -351,7 +371,7 @@ gn_fused_kernel(GnParams p, int Vs) {
   float* chs = red + 8 * n2;                // [n2]
   float* gstat = chs + n2;                  // [groups in slice][2] = (mean, rstd)
 
-  bf16x8 cache[R];
+  VT cache[R];
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
@@ -431,9 +451,9 @@ gn_fused_kernel(GnParams p, int Vs) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float y = fmaf(f[i], sc[i], sh[i]);
-        f[i] = p.silu ? silu_f(y) : y;
+        f[i] = p.silu ? silu_act<VT>(y) : y;
       }
-      p.out[((long long)b * p.hw + pix) * p.out_pv + gv] = pack8(f);
+      p.out[((long long)b * p.hw + pix) * p.out_pv + gv] = pack8_as<VT>(f);
     }
   }
 }
@@ -441,7 +461,7 @@ gn_fused_kernel(GnParams p, int Vs) {
 static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
 // Host-side planning (no CUDA calls): returns false when the shape does not fit the one-launch kernel.
-static bool gn_fused_plan(int c0, int c1, int hw, int groups, int batch, int sms, GnFusedPlan* pl) {
+static bool gn_fused_plan(int c0, int c1, int hw, int groups, int batch, int sms, GnFusedPlan* pl, int elem_bytes = 2) {
   const int C = c0 + c1;
   if (c0 < 8 || c0 % 8 || c1 % 8 || groups < 1 || C % groups || hw < 1 || batch < 1) return false;
   const int cpg = C / groups;
@@ -472,7 +492,7 @@ static bool gn_fused_plan(int c0, int c1, int hw, int groups, int batch, int sms
   if (ppb < 1) return false;
   if (ceil_div(hw, ppb) > 8) { threads = 512; ppb = threads / vs; }
   const int iters = ceil_div(hw, ppb);
-  if (iters > 16) return false;
+  if (iters > (elem_bytes == 4 ? 8 : 16)) return false;   // register-cached vectors per thread (fp32 vectors are 8 registers)
   pl->vs = vs;
   pl->slices = best;
   pl->ppb = ppb;
@@ -484,8 +504,9 @@ static bool gn_fused_plan(int c0, int c1, int hw, int groups, int batch, int sms
 }
 
 // ---- layout conversion ---------------------------------------------------------------------------
+template <typename VT>
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1, bf16x8* __restrict__ out,
+nchw_to_nhwc_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1, VT* __restrict__ out,
                     int cvec, int batch, long long hw, float scale, float shift) {
   const long long total = (long long)batch * hw * cvec;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -503,12 +524,13 @@ nchw_to_nhwc_kernel(const float* __restrict__ s0, int c0, const float* __restric
       else if (c < c0 + c1) v = fmaf(__ldg(s1 + ((long long)b * c1 + (c - c0)) * hw + pix), scale, shift);
       f[i] = v;
     }
-    out[((long long)b * hw + pix) * cvec + cv] = pack8(f);
+    out[((long long)b * hw + pix) * cvec + cv] = pack8_as<VT>(f);
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int pitch, int c_off, int c_cnt, float* __restrict__ dst,
+nhwc_to_nchw_kernel(const T* __restrict__ src, int pitch, int c_off, int c_cnt, float* __restrict__ dst,
                     int batch, long long hw, const float* __restrict__ row_scale) {
   const long long total = (long long)batch * c_cnt * hw;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -516,7 +538,7 @@ nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int pitch, int c_off,
     const long long pix = idx % hw;
     const int c = (int)((idx / hw) % c_cnt);
     const int b = (int)(idx / (hw * c_cnt));
-    float v = __bfloat162float(src[((long long)b * hw + pix) * pitch + c_off + c]);
+    float v = to_f32(src[((long long)b * hw + pix) * pitch + c_off + c]);
     if (row_scale != nullptr) v *= __ldg(row_scale + b);
     dst[idx] = v;
   }
@@ -524,8 +546,9 @@ nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int pitch, int c_off,
 
 // ---- softmax ---------------------------------------------------------------------------------------
 // One warp per row; rows are short (<= 1024 keys), so the three passes hit L1.
+template <typename T>
 __global__ void __launch_bounds__(256)
-softmax_rows_kernel(const float* __restrict__ logits, int in_pitch, __nv_bfloat16* __restrict__ probs, int out_pitch,
+softmax_rows_kernel(const float* __restrict__ logits, int in_pitch, T* __restrict__ probs, int out_pitch,
                     long long rows, int cols, float scale) {
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -538,9 +561,9 @@ softmax_rows_kernel(const float* __restrict__ logits, int in_pitch, __nv_bfloat1
   for (int c = lane; c < cols; c += 32) s += __expf(in[c] * scale - m);
   s = warp_sum(s);
   const float inv = 1.f / s;
-  __nv_bfloat16* out = probs + row * out_pitch;
+  T* out = probs + row * out_pitch;
   for (int c = lane; c < out_pitch; c += 32)
-    out[c] = __float2bfloat16_rn(c < cols ? __expf(in[c] * scale - m) * inv : 0.f);
+    out[c] = from_f32<T>(c < cols ? __expf(in[c] * scale - m) * inv : 0.f);
 }
 
 // ---- time embedding ----------------------------------------------------------------------------------
@@ -644,25 +667,150 @@ dense_rows_kernel(const float* __restrict__ act, const float* __restrict__ w, co
   }
 }
 
-}  // namespace csd
-
-extern "C" {
-
-int csd_gn_chan_stats_bf16(const void* src, int c, int pitch, float* chan_sums, int batch, int hw,
-                           csd_stream_t stream) {
-  using namespace csd;
+// ---- host launchers shared by the bf16 / fp32-activation entry points ---------------------------------------
+template <typename VT>
+static int gn_chan_stats_launch(const void* src, int c, int pitch, float* chan_sums, int batch, int hw, cudaStream_t stream) {
   CSD_REQUIRE(chan_sums != nullptr && batch >= 1 && hw >= 1, "gn_chan_stats: bad arguments");
-  GnParams p;
+  GnParamsT<VT> p;
   memset(&p, 0, sizeof(p));
   int threads;
   size_t smem;
   int st = gn_fill(p, src, c, pitch, nullptr, 0, 0, batch, hw, 1, &threads, &smem);
   if (st != CSD_OK) return st;
   p.sums0 = chan_sums;
-  const size_t stat_smem = sizeof(float) * 2 * c * (size_t)(threads / (c / 8));
-  gn_chan_stats_kernel<<<batch * p.slabs, threads, stat_smem, static_cast<cudaStream_t>(stream)>>>(p);
+  // Vs channel vectors per CTA: 32-byte rows per pixel at least (a full DRAM sector), more when the batch alone fills
+  // the machine several times over (fewer, fatter CTAs re-use their pixel rows' sectors)
+  const int V = c / 8;
+  int vs = sizeof(VT) == 32 ? 1 : 2;
+  while (vs * 2 <= 8 && V % (vs * 2) == 0 && (long long)batch * (V / (vs * 2)) >= 4LL * num_sms()) vs *= 2;
+  if (V % vs != 0) vs = 1;
+  const int ppb = 256 / vs;
+  const size_t stat_smem = sizeof(float) * 16 * vs * (size_t)ppb;
+  gn_chan_stats_kernel<VT><<<dim3((unsigned)(V / vs), (unsigned)batch), vs * ppb, stat_smem, stream>>>(p, vs);
   CSD_LAUNCH_CHECK("gn_chan_stats_kernel");
   return CSD_OK;
+}
+
+template <typename VT>
+static int gn_apply_launch(const void* src0, int c0, int pitch0, const float* sums0, const void* src1, int c1, int pitch1,
+                           const float* sums1, const float* gamma, const float* beta, void* out, int out_pitch, int batch,
+                           int hw, int groups, float eps, int apply_silu, cudaStream_t stream) {
+  CSD_REQUIRE(sums0 && gamma && beta && out && batch >= 1 && hw >= 1, "gn_apply: bad arguments");
+  CSD_REQUIRE(src1 == nullptr || sums1 != nullptr, "gn_apply: second source without its channel sums");
+  GnParamsT<VT> p;
+  memset(&p, 0, sizeof(p));
+  int threads;
+  size_t smem;
+  int st = gn_fill(p, src0, c0, pitch0, src1, c1, pitch1, batch, hw, groups, &threads, &smem);
+  if (st != CSD_OK) return st;
+  CSD_REQUIRE(out_pitch % 8 == 0 && out_pitch >= (p.v0 + p.v1) * 8, "gn_apply: out pitch %d too small", out_pitch);
+  p.sums0 = const_cast<float*>(sums0);
+  p.sums1 = const_cast<float*>(sums1);
+  p.gamma = gamma; p.beta = beta;
+  p.out = static_cast<VT*>(out);
+  p.out_pv = out_pitch / 8;
+  p.eps = eps; p.silu = apply_silu;
+  gn_apply_kernel<VT><<<batch * p.slabs, threads, smem, stream>>>(p);
+  CSD_LAUNCH_CHECK("gn_apply_kernel");
+  return CSD_OK;
+}
+
+template <typename VT>
+static int gn_fused_launch(const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1, const float* gamma,
+                           const float* beta, void* out, int out_pitch, int batch, int hw, int groups, float eps,
+                           int apply_silu, cudaStream_t stream) {
+  CSD_REQUIRE(src0 && gamma && beta && out && batch >= 1 && hw >= 1, "gn_fused: bad arguments");
+  if (src1 == nullptr) c1 = 0;
+  GnFusedPlan pl;
+  if (!gn_fused_plan(c0, c1, hw, groups, batch, 148, &pl, (int)sizeof(VT) / 8))
+    return set_error(CSD_ERR_UNSUPPORTED, "gn_fused: shape c=%d+%d hw=%d groups=%d does not fit the one-launch kernel "
+                     "(ask csd_gn_fused_supported first)", c0, c1, hw, groups);
+  GnParamsT<VT> p;
+  memset(&p, 0, sizeof(p));
+  int threads;
+  size_t smem;
+  int st = gn_fill(p, src0, c0, pitch0, src1, c1, pitch1, batch, hw, groups, &threads, &smem);
+  if (st != CSD_OK) return st;
+  CSD_REQUIRE(out_pitch % 8 == 0 && out_pitch >= c0 + c1, "gn_fused: out pitch %d too small", out_pitch);
+  p.gamma = gamma; p.beta = beta;
+  p.out = static_cast<VT*>(out);
+  p.out_pv = out_pitch / 8;
+  p.eps = eps; p.silu = apply_silu;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<1, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<2, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<4, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<8, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    if (sizeof(VT) == 16)
+      CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<16, bf16x8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  const dim3 grid((unsigned)pl.slices, (unsigned)batch);
+  switch (pl.r) {
+    case 1: gn_fused_kernel<1, VT><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
+    case 2: gn_fused_kernel<2, VT><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
+    case 4: gn_fused_kernel<4, VT><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
+    case 8: gn_fused_kernel<8, VT><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
+    default:
+      if constexpr (sizeof(VT) == 16) {
+        gn_fused_kernel<16, VT><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs);
+      } else {
+        return set_error(CSD_ERR_UNSUPPORTED, "gn_fused (fp32 activations): more than 8 cached vectors per thread");
+      }
+      break;
+  }
+  CSD_LAUNCH_CHECK("gn_fused_kernel");
+  return CSD_OK;
+}
+
+template <typename VT>
+static int nchw_to_nhwc_launch(const float* src0, int c0, const float* src1, int c1, void* out, int c_pad, int batch, int h,
+                               int w, float scale, float shift, cudaStream_t stream) {
+  CSD_REQUIRE(src0 && out && c0 >= 1, "nchw_to_nhwc: bad arguments");
+  if (src1 == nullptr) c1 = 0;
+  CSD_REQUIRE(c_pad % 8 == 0 && c_pad >= c0 + c1, "nchw_to_nhwc: c_pad=%d must be a multiple of 8 >= %d", c_pad, c0 + c1);
+  const long long total = (long long)batch * h * w * (c_pad / 8);
+  const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)num_sms() * 16);
+  nchw_to_nhwc_kernel<VT><<<blocks, 256, 0, stream>>>(src0, c0, src1, c1, static_cast<VT*>(out), c_pad / 8, batch,
+                                                      (long long)h * w, scale, shift);
+  CSD_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+  return CSD_OK;
+}
+
+template <typename T>
+static int nhwc_to_nchw_launch(const void* src, int c_pitch, int c_off, int c_cnt, float* dst, int batch, int h, int w,
+                               const float* row_scale, cudaStream_t stream) {
+  CSD_REQUIRE(src && dst && c_cnt >= 1 && c_off >= 0 && c_off + c_cnt <= c_pitch, "nhwc_to_nchw: bad channel range");
+  const long long total = (long long)batch * c_cnt * h * w;
+  const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)num_sms() * 16);
+  nhwc_to_nchw_kernel<T><<<blocks, 256, 0, stream>>>(static_cast<const T*>(src), c_pitch, c_off, c_cnt, dst, batch,
+                                                     (long long)h * w, row_scale);
+  CSD_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return CSD_OK;
+}
+
+template <typename T>
+static int softmax_rows_launch(const float* logits, int in_pitch, void* probs, int out_pitch, int64_t rows, int cols,
+                               float scale, cudaStream_t stream) {
+  CSD_REQUIRE(logits && probs && cols >= 1 && in_pitch >= cols && out_pitch >= cols, "softmax: bad arguments");
+  if (rows == 0) return CSD_OK;
+  const int blocks = (int)ceil_div_ll(rows, 8);
+  softmax_rows_kernel<T><<<blocks, 256, 0, stream>>>(logits, in_pitch, static_cast<T*>(probs), out_pitch, rows, cols, scale);
+  CSD_LAUNCH_CHECK("softmax_rows_kernel");
+  return CSD_OK;
+}
+
+}  // namespace csd
+
+extern "C" {
+
+int csd_gn_chan_stats_bf16(const void* src, int c, int pitch, float* chan_sums, int batch, int hw,
+                           csd_stream_t stream) {
+  return csd::gn_chan_stats_launch<csd::bf16x8>(src, c, pitch, chan_sums, batch, hw, static_cast<cudaStream_t>(stream));
+}
+int csd_gn_chan_stats_f32(const void* src, int c, int pitch, float* chan_sums, int batch, int hw, csd_stream_t stream) {
+  return csd::gn_chan_stats_launch<csd::f32x8>(src, c, pitch, chan_sums, batch, hw, static_cast<cudaStream_t>(stream));
 }
 
 int csd_gn_finalize_partials_f32(const float* partials, float* chan_sums, int batch, int tiles_per_img, int c,
@@ -679,73 +827,36 @@ int csd_gn_finalize_partials_f32(const float* partials, float* chan_sums, int ba
 int csd_gn_apply_bf16(const void* src0, int c0, int pitch0, const float* sums0, const void* src1, int c1, int pitch1,
                       const float* sums1, const float* gamma, const float* beta, void* out, int out_pitch, int batch,
                       int hw, int groups, float eps, int apply_silu, csd_stream_t stream) {
-  using namespace csd;
-  CSD_REQUIRE(sums0 && gamma && beta && out && batch >= 1 && hw >= 1, "gn_apply: bad arguments");
-  CSD_REQUIRE(src1 == nullptr || sums1 != nullptr, "gn_apply: second source without its channel sums");
-  GnParams p;
-  memset(&p, 0, sizeof(p));
-  int threads;
-  size_t smem;
-  int st = gn_fill(p, src0, c0, pitch0, src1, c1, pitch1, batch, hw, groups, &threads, &smem);
-  if (st != CSD_OK) return st;
-  CSD_REQUIRE(out_pitch % 8 == 0 && out_pitch >= (p.v0 + p.v1) * 8, "gn_apply: out pitch %d too small", out_pitch);
-  p.sums0 = const_cast<float*>(sums0);
-  p.sums1 = const_cast<float*>(sums1);
-  p.gamma = gamma; p.beta = beta;
-  p.out = static_cast<bf16x8*>(out);
-  p.out_pv = out_pitch / 8;
-  p.eps = eps; p.silu = apply_silu;
-  gn_apply_kernel<<<batch * p.slabs, threads, smem, static_cast<cudaStream_t>(stream)>>>(p);
-  CSD_LAUNCH_CHECK("gn_apply_kernel");
-  return CSD_OK;
+  return csd::gn_apply_launch<csd::bf16x8>(src0, c0, pitch0, sums0, src1, c1, pitch1, sums1, gamma, beta, out, out_pitch,
+                                           batch, hw, groups, eps, apply_silu, static_cast<cudaStream_t>(stream));
+}
+int csd_gn_apply_f32(const void* src0, int c0, int pitch0, const float* sums0, const void* src1, int c1, int pitch1,
+                     const float* sums1, const float* gamma, const float* beta, void* out, int out_pitch, int batch,
+                     int hw, int groups, float eps, int apply_silu, csd_stream_t stream) {
+  return csd::gn_apply_launch<csd::f32x8>(src0, c0, pitch0, sums0, src1, c1, pitch1, sums1, gamma, beta, out, out_pitch,
+                                          batch, hw, groups, eps, apply_silu, static_cast<cudaStream_t>(stream));
 }
 
 int csd_gn_fused_supported(int c0, int c1, int hw, int groups, int batch) {
   csd::GnFusedPlan pl;
   return csd::gn_fused_plan(c0, c1, hw, groups, batch, 148, &pl) ? 1 : 0;
 }
+int csd_gn_fused_supported_f32(int c0, int c1, int hw, int groups, int batch) {
+  csd::GnFusedPlan pl;
+  return csd::gn_fused_plan(c0, c1, hw, groups, batch, 148, &pl, 4) ? 1 : 0;
+}
 
 int csd_gn_fused_bf16(const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1, const float* gamma,
                       const float* beta, void* out, int out_pitch, int batch, int hw, int groups, float eps,
-                      int apply_silu, csd_stream_t stream_) {
-  using namespace csd;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CSD_REQUIRE(src0 && gamma && beta && out && batch >= 1 && hw >= 1, "gn_fused: bad arguments");
-  if (src1 == nullptr) c1 = 0;
-  GnFusedPlan pl;
-  if (!gn_fused_plan(c0, c1, hw, groups, batch, 148, &pl))
-    return set_error(CSD_ERR_UNSUPPORTED, "gn_fused: shape c=%d+%d hw=%d groups=%d does not fit the one-launch kernel "
-                     "(ask csd_gn_fused_supported first)", c0, c1, hw, groups);
-  GnParams p;
-  memset(&p, 0, sizeof(p));
-  int threads;
-  size_t smem;
-  int st = gn_fill(p, src0, c0, pitch0, src1, c1, pitch1, batch, hw, groups, &threads, &smem);
-  if (st != CSD_OK) return st;
-  CSD_REQUIRE(out_pitch % 8 == 0 && out_pitch >= c0 + c1, "gn_fused: out pitch %d too small", out_pitch);
-  p.gamma = gamma; p.beta = beta;
-  p.out = static_cast<bf16x8*>(out);
-  p.out_pv = out_pitch / 8;
-  p.eps = eps; p.silu = apply_silu;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CSD_CUDA(cudaFuncSetAttribute(gn_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
-  const dim3 grid((unsigned)pl.slices, (unsigned)batch);
-  switch (pl.r) {
-    case 1: gn_fused_kernel<1><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
-    case 2: gn_fused_kernel<2><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
-    case 4: gn_fused_kernel<4><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
-    case 8: gn_fused_kernel<8><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
-    default: gn_fused_kernel<16><<<grid, pl.threads, pl.smem, stream>>>(p, pl.vs); break;
-  }
-  CSD_LAUNCH_CHECK("gn_fused_kernel");
-  return CSD_OK;
+                      int apply_silu, csd_stream_t stream) {
+  return csd::gn_fused_launch<csd::bf16x8>(src0, c0, pitch0, src1, c1, pitch1, gamma, beta, out, out_pitch, batch, hw,
+                                           groups, eps, apply_silu, static_cast<cudaStream_t>(stream));
+}
+int csd_gn_fused_f32(const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1, const float* gamma,
+                     const float* beta, void* out, int out_pitch, int batch, int hw, int groups, float eps,
+                     int apply_silu, csd_stream_t stream) {
+  return csd::gn_fused_launch<csd::f32x8>(src0, c0, pitch0, src1, c1, pitch1, gamma, beta, out, out_pitch, batch, hw,
+                                          groups, eps, apply_silu, static_cast<cudaStream_t>(stream));
 }
 
 int csd_gn_coeffs_f32(const float* sums0, int c0, const float* sums1, int c1, const float* gamma, const float* beta,
@@ -794,40 +905,35 @@ int csd_gn_coeffs_partials_f32(const float* sums0, const float* partials0, int t
 
 int csd_nchw_to_nhwc_bf16(const float* src0, int c0, const float* src1, int c1, void* out, int c_pad, int batch, int h,
                           int w, float scale, float shift, csd_stream_t stream) {
-  using namespace csd;
-  CSD_REQUIRE(src0 && out && c0 >= 1, "nchw_to_nhwc: bad arguments");
-  if (src1 == nullptr) c1 = 0;
-  CSD_REQUIRE(c_pad % 8 == 0 && c_pad >= c0 + c1, "nchw_to_nhwc: c_pad=%d must be a multiple of 8 >= %d", c_pad, c0 + c1);
-  const long long total = (long long)batch * h * w * (c_pad / 8);
-  const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)num_sms() * 16);
-  nchw_to_nhwc_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src0, c0, src1, c1, static_cast<bf16x8*>(out),
-                                                                           c_pad / 8, batch, (long long)h * w, scale, shift);
-  CSD_LAUNCH_CHECK("nchw_to_nhwc_kernel");
-  return CSD_OK;
+  return csd::nchw_to_nhwc_launch<csd::bf16x8>(src0, c0, src1, c1, out, c_pad, batch, h, w, scale, shift,
+                                               static_cast<cudaStream_t>(stream));
+}
+int csd_nchw_to_nhwc_f32(const float* src0, int c0, const float* src1, int c1, void* out, int c_pad, int batch, int h,
+                         int w, float scale, float shift, csd_stream_t stream) {
+  return csd::nchw_to_nhwc_launch<csd::f32x8>(src0, c0, src1, c1, out, c_pad, batch, h, w, scale, shift,
+                                              static_cast<cudaStream_t>(stream));
 }
 
 int csd_nhwc_bf16_to_nchw(const void* src, int c_pitch, int c_off, int c_cnt, float* dst, int batch, int h, int w,
                           const float* row_scale, csd_stream_t stream) {
-  using namespace csd;
-  CSD_REQUIRE(src && dst && c_cnt >= 1 && c_off >= 0 && c_off + c_cnt <= c_pitch, "nhwc_to_nchw: bad channel range");
-  const long long total = (long long)batch * c_cnt * h * w;
-  const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)num_sms() * 16);
-  nhwc_to_nchw_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(src), c_pitch, c_off, c_cnt, dst, batch, (long long)h * w, row_scale);
-  CSD_LAUNCH_CHECK("nhwc_to_nchw_kernel");
-  return CSD_OK;
+  return csd::nhwc_to_nchw_launch<__nv_bfloat16>(src, c_pitch, c_off, c_cnt, dst, batch, h, w, row_scale,
+                                                 static_cast<cudaStream_t>(stream));
+}
+int csd_nhwc_f32_to_nchw(const void* src, int c_pitch, int c_off, int c_cnt, float* dst, int batch, int h, int w,
+                         const float* row_scale, csd_stream_t stream) {
+  return csd::nhwc_to_nchw_launch<float>(src, c_pitch, c_off, c_cnt, dst, batch, h, w, row_scale,
+                                         static_cast<cudaStream_t>(stream));
 }
 
 int csd_softmax_rows_f32_bf16(const float* logits, int in_pitch, void* probs, int out_pitch, int64_t rows, int cols,
                               float scale, csd_stream_t stream) {
-  using namespace csd;
-  CSD_REQUIRE(logits && probs && cols >= 1 && in_pitch >= cols && out_pitch >= cols, "softmax: bad arguments");
-  if (rows == 0) return CSD_OK;
-  const int blocks = (int)ceil_div_ll(rows, 8);
-  softmax_rows_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, in_pitch, static_cast<__nv_bfloat16*>(probs), out_pitch, rows, cols, scale);
-  CSD_LAUNCH_CHECK("softmax_rows_kernel");
-  return CSD_OK;
+  return csd::softmax_rows_launch<__nv_bfloat16>(logits, in_pitch, probs, out_pitch, rows, cols, scale,
+                                                 static_cast<cudaStream_t>(stream));
+}
+int csd_softmax_rows_f32_f32(const float* logits, int in_pitch, void* probs, int out_pitch, int64_t rows, int cols,
+                             float scale, csd_stream_t stream) {
+  return csd::softmax_rows_launch<float>(logits, in_pitch, probs, out_pitch, rows, cols, scale,
+                                         static_cast<cudaStream_t>(stream));
 }
 
 int csd_time_embedding_f32(const float* labels, int batch, int nf, int embedding_type, const float* fourier_w,

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const csd_pack_job* _
     return;
   }
   __nv_bfloat16* d = static_cast<__nv_bfloat16*>(j.dst);
+  float* df = static_cast<float*>(j.dst);     // kind 2: the same image in fp32 (tf32 plan)
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     // destination order (row, tap, col): consecutive threads write consecutive bf16 elements
     const int c = (int)(i % j.cols);
@@ -27,7 +28,9 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const csd_pack_job* _
     const int r = (int)(i / ((long long)j.cols * j.taps));
     const int ts = j.flip ? j.taps - 1 - tap : tap;
     const float v = j.src[(long long)r * j.s_row + (long long)c * j.s_col + (long long)ts * j.s_tap] * j.scale;
-    d[(long long)r * j.dst_pitch + (long long)tap * j.k_pad + c] = __float2bfloat16_rn(v);
+    const long long o = (long long)r * j.dst_pitch + (long long)tap * j.k_pad + c;
+    if (j.kind == 2) df[o] = v;
+    else d[o] = __float2bfloat16_rn(v);
   }
 }
 

@@ -188,6 +188,19 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with tf32 x tf32 -> fp32 (operands are fp32 words in shared memory, the tensor core reads their upper 19 bits;
+// K = 8 per instruction = the same 32 bytes per row as a K = 16 bf16 instruction).
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -246,6 +259,11 @@ __device__ __forceinline__ uint64_t smem_desc_join(uint32_t hi, uint32_t lo) {
 //  a_major 15, b_major 16, n >> 3 at [17,23), m >> 4 at [24,29)).
 __device__ __forceinline__ uint32_t make_idesc_bf16_m128(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// kind::tf32: a_format = b_format = 2 (TF32), fp32 accumulate, K-major both, M = 128.
+__device__ __forceinline__ uint32_t make_idesc_tf32_m128(uint32_t n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -215,16 +215,18 @@ static int launch_tile(const UpfirdnParams& p0, cudaStream_t stream) {
 // mode 1: up x2, pad (2,1), taps scaled by 2 per axis  (upsample_2d, up_or_down_sampling.py:195-224)
 // mode 2: down x2, pad (1,1)                           (downsample_2d, :227-257)
 // One thread = one output pixel x 8 channels (16-byte vectors, coalesced along channels).
-struct FirNhwcParams {
-  const bf16x8* src;
-  bf16x8* out;
-  const bf16x8* add;
+template <typename VT>
+struct FirNhwcParamsT {
+  const VT* src;
+  VT* out;
+  const VT* add;
   int batch, h, w, oh, ow, cvec;  // cvec = channel pitch / 8
   float kf[4];                    // flipped, normalised 1-D taps (already x2 for mode 1)
 };
+using FirNhwcParams = FirNhwcParamsT<bf16x8>;
 
-template <int MODE>
-__global__ void __launch_bounds__(256) fir_nhwc_kernel(FirNhwcParams p) {
+template <int MODE, typename VT>
+__global__ void __launch_bounds__(256) fir_nhwc_kernel(FirNhwcParamsT<VT> p) {
   const long long total = (long long)p.batch * p.oh * p.ow * p.cvec;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(256) fir_nhwc_kernel(FirNhwcParams p) {
       for (int c = 0; c < 4; ++c) {
         if (c >= nx) break;
         if (ix[c] < 0 || ix[c] >= p.w) continue;
-        const bf16x8 v = p.src[(((long long)b * p.h + iy[a]) * p.w + ix[c]) * p.cvec + cv];
+        const VT v = p.src[(((long long)b * p.h + iy[a]) * p.w + ix[c]) * p.cvec + cv];
         float f[8];
         unpack8(v, f);
         const float wgt = wy[a] * wx[c];
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256) fir_nhwc_kernel(FirNhwcParams p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += f[i];
     }
-    p.out[idx] = pack8(acc);
+    p.out[idx] = pack8_as<VT>(acc);
   }
 }
 
@@ -303,10 +305,10 @@ struct FirTile {
   static constexpr int TI = MODE == 1 ? TO / 2 + 2 : 2 * TO + 2;  // input tile edge
 };
 
-template <int MODE>
+template <int MODE, typename VT>
 __global__ void __launch_bounds__(256)
-fir_tma_kernel(const __grid_constant__ CUtensorMap map, const FirNhwcParams p, int tiles_x, int tiles_y, int cchunks,
-               int cb /* channels per chunk, multiple of 8, <= 64 */) {
+fir_tma_kernel(const __grid_constant__ CUtensorMap map, const FirNhwcParamsT<VT> p, int tiles_x, int tiles_y, int cchunks,
+               int cb /* channels per chunk, multiple of 8, <= 64 (bf16) / 32 (fp32) */) {
   using T = FirTile<MODE>;
   extern __shared__ __align__(128) uint8_t fir_smem[];
   __shared__ __align__(8) unsigned long long bar;
@@ -323,12 +325,12 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map, const FirNhwcParams p, i
   if (threadIdx.x == 0) {
     ptx::mbar_init(ptx::smem_u32(&bar), 1);
     ptx::fence_mbar_init();
-    ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar), (uint32_t)(T::TI * T::TI * cb * 2));
+    ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar), (uint32_t)(T::TI * T::TI * cb * (sizeof(VT) / 8)));
     ptx::tma_load_4d(ptx::smem_u32(fir_smem), &map, ptx::smem_u32(&bar), cc * cb, ix0, iy0, b);
   }
   __syncthreads();
   ptx::mbar_wait(ptx::smem_u32(&bar), 0);
-  const uint4* tile = reinterpret_cast<const uint4*>(fir_smem);   // [TI][TI][cvs] 16-byte vectors
+  const VT* tile = reinterpret_cast<const VT*>(fir_smem);         // [TI][TI][cvs] 8-channel vectors
   const int items = T::TO * T::TO * cvs;
   for (int item = threadIdx.x; item < items; item += 256) {
     const int cv = item % cvs;
@@ -350,8 +352,7 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map, const FirNhwcParams p, i
       for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          bf16x8 v;
-          *reinterpret_cast<uint4*>(&v) = tile[((ry + a) * T::TI + rx + c) * cvs + cv];
+          const VT v = tile[((ry + a) * T::TI + rx + c) * cvs + cv];
           float f[8];
           unpack8(v, f);
           const float wgt = (a ? wy1 : wy0) * (c ? wx1 : wx0);
@@ -364,8 +365,7 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map, const FirNhwcParams p, i
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          bf16x8 v;
-          *reinterpret_cast<uint4*>(&v) = tile[((2 * ly + a) * T::TI + 2 * lx + c) * cvs + cv];
+          const VT v = tile[((2 * ly + a) * T::TI + 2 * lx + c) * cvs + cv];
           float f[8];
           unpack8(v, f);
           const float wgt = p.kf[a] * p.kf[c];
@@ -380,27 +380,29 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map, const FirNhwcParams p, i
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += f[e];
     }
-    p.out[o] = pack8(acc);
+    p.out[o] = pack8_as<VT>(acc);
   }
 }
 
-template <int MODE>
-static int launch_fir_tma(const FirNhwcParams& p, cudaStream_t stream) {
+template <int MODE, typename VT>
+static int launch_fir_tma(const FirNhwcParamsT<VT>& p, cudaStream_t stream) {
   using T = FirTile<MODE>;
+  constexpr int eb = (int)sizeof(VT) / 8;        // bytes per element
   const int pitch = p.cvec * 8;
-  const int cb = std::min(64, pitch);
+  const int cb = std::min(eb == 2 ? 64 : 32, pitch);
   const int cchunks = ceil_div(pitch, cb);
   const int tiles_x = ceil_div(p.ow, T::TO), tiles_y = ceil_div(p.oh, T::TO);
   CUtensorMap map;
   uint64_t dims[4] = {(uint64_t)pitch, (uint64_t)p.w, (uint64_t)p.h, (uint64_t)p.batch};
-  uint64_t strides[3] = {(uint64_t)pitch * 2, (uint64_t)pitch * 2 * p.w, (uint64_t)pitch * 2 * p.w * p.h};
+  uint64_t strides[3] = {(uint64_t)pitch * eb, (uint64_t)pitch * eb * p.w, (uint64_t)pitch * eb * p.w * p.h};
   uint32_t box[4] = {(uint32_t)cb, (uint32_t)T::TI, (uint32_t)T::TI, 1};
-  int st = encode_tensor_map(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p.src, dims, strides, box, TMA_SW_NONE);
+  int st = encode_tensor_map(&map, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                             p.src, dims, strides, box, TMA_SW_NONE);
   if (st != CSD_OK) return st;
   const long long blocks = (long long)p.batch * tiles_x * tiles_y * cchunks;
   CSD_REQUIRE(blocks < (1LL << 31), "fir_resample: too many tiles");
-  const size_t smem = (size_t)T::TI * T::TI * cb * 2;
-  fir_tma_kernel<MODE><<<(unsigned)blocks, 256, smem, stream>>>(map, p, tiles_x, tiles_y, cchunks, cb);
+  const size_t smem = (size_t)T::TI * T::TI * cb * eb;
+  fir_tma_kernel<MODE, VT><<<(unsigned)blocks, 256, smem, stream>>>(map, p, tiles_x, tiles_y, cchunks, cb);
   CSD_LAUNCH_CHECK("fir_tma_kernel");
   return CSD_OK;
 }
@@ -450,18 +452,20 @@ int csd_upfirdn2d_f32(const float* input, const float* kernel, float* output, in
   return CSD_OK;
 }
 
-int csd_fir_resample_nhwc_bf16(const void* src, void* out, const void* add, int batch, int h, int w, int c_pitch,
-                               int mode, const float* taps4_host, csd_stream_t stream_) {
-  using namespace csd;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+}  // extern "C"
+
+namespace csd {
+template <typename VT>
+static int fir_resample_launch(const void* src, void* out, const void* add, int batch, int h, int w, int c_pitch, int mode,
+                               const float* taps4_host, cudaStream_t stream) {
   CSD_REQUIRE(src && out && taps4_host, "fir_resample: null pointer");
   CSD_REQUIRE(mode >= 1 && mode <= 3, "fir_resample: mode %d (1 = up, 2 = down, 3 = pre-filter)", mode);
   CSD_REQUIRE(c_pitch % 8 == 0, "fir_resample: channel pitch %d not a multiple of 8", c_pitch);
   CSD_REQUIRE(mode != 2 || (h % 2 == 0 && w % 2 == 0), "fir_resample: odd size %dx%d for downsampling", h, w);
-  FirNhwcParams p;
-  p.src = static_cast<const bf16x8*>(src);
-  p.out = static_cast<bf16x8*>(out);
-  p.add = static_cast<const bf16x8*>(add);
+  FirNhwcParamsT<VT> p;
+  p.src = static_cast<const VT*>(src);
+  p.out = static_cast<VT*>(out);
+  p.add = static_cast<const VT*>(add);
   p.batch = batch; p.h = h; p.w = w; p.cvec = c_pitch / 8;
   p.oh = mode == 1 ? h * 2 : (mode == 2 ? h / 2 : h + 1);
   p.ow = mode == 1 ? w * 2 : (mode == 2 ? w / 2 : w + 1);
@@ -474,13 +478,27 @@ int csd_fir_resample_nhwc_bf16(const void* src, void* out, const void* add, int 
   const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)num_sms() * 16);
   static const bool per_output = getenv("CSD_FIR_PER_OUTPUT") != nullptr;   // A/B switch
   if (mode != 3 && !per_output && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-    return mode == 1 ? launch_fir_tma<1>(p, stream) : launch_fir_tma<2>(p, stream);
+    return mode == 1 ? launch_fir_tma<1, VT>(p, stream) : launch_fir_tma<2, VT>(p, stream);
   }
-  if (mode == 1) fir_nhwc_kernel<1><<<blocks, 256, 0, stream>>>(p);
-  else if (mode == 2) fir_nhwc_kernel<2><<<blocks, 256, 0, stream>>>(p);
-  else fir_nhwc_kernel<3><<<blocks, 256, 0, stream>>>(p);
+  if (mode == 1) fir_nhwc_kernel<1, VT><<<blocks, 256, 0, stream>>>(p);
+  else if (mode == 2) fir_nhwc_kernel<2, VT><<<blocks, 256, 0, stream>>>(p);
+  else fir_nhwc_kernel<3, VT><<<blocks, 256, 0, stream>>>(p);
   CSD_LAUNCH_CHECK("fir_nhwc_kernel");
   return CSD_OK;
+}
+}  // namespace csd
+
+extern "C" {
+
+int csd_fir_resample_nhwc_bf16(const void* src, void* out, const void* add, int batch, int h, int w, int c_pitch,
+                               int mode, const float* taps4_host, csd_stream_t stream) {
+  return csd::fir_resample_launch<csd::bf16x8>(src, out, add, batch, h, w, c_pitch, mode, taps4_host,
+                                               static_cast<cudaStream_t>(stream));
+}
+int csd_fir_resample_nhwc_f32(const void* src, void* out, const void* add, int batch, int h, int w, int c_pitch,
+                              int mode, const float* taps4_host, csd_stream_t stream) {
+  return csd::fir_resample_launch<csd::f32x8>(src, out, add, batch, h, w, c_pitch, mode, taps4_host,
+                                              static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

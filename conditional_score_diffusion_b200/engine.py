@@ -45,12 +45,14 @@ class Act:
 class BufferPool:
     """Stream-ordered reuse of activation buffers (all work is issued on one stream in plan order)."""
 
-    def __init__(self, device):
+    def __init__(self, device, dtype=BF16):
         self.device = device
+        self.dtype = dtype          # activation storage of the plan: bf16, or fp32 for the tf32 plan
         self.free = {}
         self.all = []
 
-    def get(self, shape, dtype=BF16):
+    def get(self, shape, dtype=None):
+        dtype = dtype or self.dtype
         key = (tuple(shape), dtype)
         lst = self.free.get(key)
         if lst:
@@ -116,9 +118,10 @@ class PackedConv:
     persistent: refresh() re-packs them in place from the live parameters, so recorded launch lists stay valid
     across optimizer steps."""
 
-    def __init__(self, weights, bias, device):
+    def __init__(self, weights, bias, device, dtype=BF16):
         self.segs = _as_segments(weights)
         self.device = device
+        self.dtype = dtype          # operand storage: bf16 (kind::f16) or fp32 (kind::tf32)
         w0 = [s.weight(device) for s in self.segs[0]]
         cout = sum(w.shape[0] for w in w0)
         self.cout = cout
@@ -217,7 +220,7 @@ class PackedConv:
         return ws[0] if len(ws) == 1 else torch.cat(ws, 0)
 
     def refresh(self):
-        parts = [K.pack_conv_weight(self.seg_weight(i), n_pad=self.n_pad) for i in range(len(self.segs))]
+        parts = [K.pack_conv_weight(self.seg_weight(i), n_pad=self.n_pad, dtype=self.dtype) for i in range(len(self.segs))]
         wt = torch.cat(parts, dim=1) if len(parts) > 1 else parts[0]
         if self.wt is None:
             self.wt = wt.contiguous()
@@ -233,6 +236,8 @@ class PackedConv:
     def dgrad(self, i, scale=1.0):
         """Packed weights of the data gradient of segment i: [Cin_i, Cout, kh, kw] = scale * W_i flipped in (ky, kx)
         and transposed in (co, ci), so that d a_i = conv(d out, this) with the same 'same' padding."""
+        if self.dtype != BF16:
+            raise CsdError("the training plan (data-gradient packs) exists for the bf16 plan only")
         key = (i, float(scale))
         if key not in self._dgrads:
             self._dgrads[key] = DgradPack(self, i, scale)
@@ -308,6 +313,7 @@ class BlockOps:
     def __init__(self, device, pool, rec, stats_arena):
         self.device = device
         self.pool = pool
+        self.act_dtype = pool.dtype     # bf16 plan: transposed tcgen05 kernel + fused GroupNorm; fp32 (tf32) plan: per-tap
         self.rec = rec
         self.stats = stats_arena  # fp32 [n_slots, ...] zeroed at the start of every forward
         self.stats_used = 0
@@ -343,7 +349,7 @@ class BlockOps:
         s0 = srcs[0]
         s1 = srcs[1] if len(srcs) > 1 else None
         if (self.fuse_small_gn and any(a.sums is None for a in srcs)
-                and K.gn_fused_supported(s0.c, s1.c if s1 else 0, h * w, groups, b)):
+                and K.gn_fused_supported(s0.c, s1.c if s1 else 0, h * w, groups, b, self.act_dtype)):
             # small levels: statistics + apply in ONE launch (nobody delivers these tensors' sums for free)
             out = self.pool.get((b, h, w, c))
             self.rec.add(K.gn_fused, s0.t, s0.c, s1.t if s1 else None, s1.c if s1 else 0, gamma, beta, out, groups,
@@ -389,17 +395,16 @@ class BlockOps:
                      groups or _groups(c), 1e-6)
         return [coef0] + ([coef1] if s1 is not None else [])
 
-    @staticmethod
-    def will_transpose(h, w, cout):
+    def will_transpose(self, h, w, cout):
         """3x3 stride-1 convolutions with >= 32 output channels on images that tile into 32x8-pixel macro tiles
-        run in the persistent transposed kernel (output channels on M, 256 pixels on N)."""
-        return K.TRANSPOSED_DEFAULT and cout >= 32 and cout % 8 == 0 and K.transposed_shape_ok(h, w)
+        run in the persistent transposed kernel (output channels on M, 256 pixels on N) - bf16 plan only."""
+        return (self.act_dtype == BF16 and K.TRANSPOSED_DEFAULT and cout >= 32 and cout % 8 == 0
+                and K.transposed_shape_ok(h, w))
 
-    @staticmethod
-    def fusable(srcs, cout):
+    def fusable(self, srcs, cout):
         """GroupNorm+SiLU can ride in the convolution's prologue when the 3x3 conv runs in the transposed mode."""
         _, h, w, _ = srcs[0].shape
-        return (K.FUSE_GN_DEFAULT and K.TRANSPOSED_DEFAULT and cout >= 32 and cout % 8 == 0
+        return (self.act_dtype == BF16 and K.FUSE_GN_DEFAULT and K.TRANSPOSED_DEFAULT and cout >= 32 and cout % 8 == 0
                 and K.transposed_shape_ok(h, w) and all(a.c % 8 == 0 for a in srcs))
 
     def conv(self, segs, pc, out_hw=None, temb=None, temb_pitch=0, res=None, scale=1.0, stride=1, pad=1,
@@ -436,7 +441,7 @@ class BlockOps:
 
     def head_in_transposed_kernel(self, pc, hcur):
         b, h, w, _ = hcur.shape
-        return (self.fast_heads and HEAD_MODE != 0 and K.TRANSPOSED_DEFAULT and K.FUSE_GN_DEFAULT
+        return (self.act_dtype == BF16 and self.fast_heads and HEAD_MODE != 0 and K.TRANSPOSED_DEFAULT and K.FUSE_GN_DEFAULT
                 and K.transposed_shape_ok(h, w) and hcur.c % 8 == 0 and pc.n_store == 8 and len(pc.segs) == 1)
 
     def head(self, gn, pc, hcur, extra, key, res=None):
@@ -453,7 +458,7 @@ class BlockOps:
                 pct = extra.get(key)
                 if pct is None:
                     pct = extra[key] = PackedConv([pc.segs[0][0], WSrc(pc.cout, "eye")], list(pc.bias_srcs) or None,
-                                                  self.device)
+                                                  self.device, pc.dtype)
             (cf,) = self.gn_coeffs([hcur], gamma, beta, groups)
             segs = [(hcur, 9, cf)] + ([(res, 1)] if res is not None else [])
             out = self.conv(segs, pct, head=True)
@@ -604,6 +609,7 @@ class NetEngine:
 
     def __init__(self, net):
         self.net = net
+        self.precision = "bf16"     # 'bf16' (fast plan) | 'tf32' (fp32 storage + tf32 operands: the reference's class)
         self.device = None
         self.packed = None
         self.param_version = None
@@ -646,6 +652,25 @@ class NetEngine:
         self._pack_table = None
         self.plans = {}
         self.train_plans = {}
+
+    @property
+    def wt_dtype(self):
+        return torch.float32 if self.precision == "tf32" else BF16
+
+    def set_precision(self, precision):
+        """Select the arithmetic of every plan built from now on. 'bf16': bf16 activations in HBM and bf16 tensor-core
+        operands (fp32 accumulation and statistics) - the fast plan, held to 2e-2 of the output maximum. 'tf32': fp32
+        activations in HBM like the reference (sampling/unconditional.py:206, models/ncsnpp.py:264-266) and tf32
+        tensor-core operands like its cuDNN convolutions under PyTorch's defaults - held to 1e-3. Drops packed operands
+        and plans (they are rebuilt on next use); inference only."""
+        if precision not in ("bf16", "tf32"):
+            raise ValueError(f"precision {precision!r}: 'bf16' or 'tf32'")
+        if precision != self.precision:
+            self.precision = precision
+            self.packed = None
+            self.param_version = None
+            self.plans = {}
+            self.train_plans = {}
 
     def invalidate(self):
         """Parameters were modified outside autograd's version tracking (a fused optimizer kernel): re-pack on next use."""
@@ -754,7 +779,8 @@ class NetEngine:
         pk["gn1_w"], pk["gn1_b"] = _gn_params(m.GroupNorm_1, device)
         pk["groups0"], pk["groups1"] = m.GroupNorm_0.num_groups, m.GroupNorm_1.num_groups
         pk["mod"] = m
-        pk["conv0"] = PackedConv([WSrc(m.Conv_0.weight)], m.Conv_0.bias, device)
+        pk["dtype"] = self.wt_dtype
+        pk["conv0"] = PackedConv([WSrc(m.Conv_0.weight)], m.Conv_0.bias, device, self.wt_dtype)
         pk["conv0_w"], pk["conv0_b"] = m.Conv_0.weight, m.Conv_0.bias
         if hasattr(m, "Dense_0"):
             pk["temb_off"] = sum(d.weight.shape[0] for d in dense_w)
@@ -792,7 +818,7 @@ class NetEngine:
                 ws.append(WSrc(pk["conv0_w"], "conv", off, c))
                 off += c
             assert off == pk["conv0_w"].shape[1]
-            pk[key] = PackedConv(ws, pk["conv0_b"], device)
+            pk[key] = PackedConv(ws, pk["conv0_b"], device, pk["dtype"])
         return pk[key]
 
     @staticmethod
@@ -806,7 +832,7 @@ class NetEngine:
         if identity_skip and not pk["has_skip_conv"]:
             c = pk["out_ch"]
             assert split == [c] or tuple(split) == (c,)
-            pc = PackedConv([WSrc(pk["conv1_w"]), WSrc(c, "eye")], pk["conv1_b"], device)
+            pc = PackedConv([WSrc(pk["conv1_w"]), WSrc(c, "eye")], pk["conv1_b"], device, pk["dtype"])
             pc.identity_skip = True
             pk[key] = pc
             return pc
@@ -817,9 +843,9 @@ class NetEngine:
                 ws.append(WSrc(pk["skip_w"], pk["skip_kind"], off, c))
                 off += c
             assert off == pk["skip_cin"], (off, pk["skip_cin"])
-            pc = PackedConv(ws, [(pk["conv1_b"], 0), (pk["skip_b"], 0)], device)
+            pc = PackedConv(ws, [(pk["conv1_b"], 0), (pk["skip_b"], 0)], device, pk["dtype"])
         else:
-            pc = PackedConv([WSrc(pk["conv1_w"])], pk["conv1_b"], device)
+            pc = PackedConv([WSrc(pk["conv1_w"])], pk["conv1_b"], device, pk["dtype"])
         pk[key] = pc
         return pc
 
@@ -828,12 +854,13 @@ class NetEngine:
         pk = {"mod": m}
         pk["gn_w"], pk["gn_b"] = _gn_params(m.GroupNorm_0, device)
         pk["groups"] = m.GroupNorm_0.num_groups
-        pk["qk"] = PackedConv([[WSrc(m.NIN_0.W, "nin"), WSrc(m.NIN_1.W, "nin")]], [(m.NIN_0.b, 0), (m.NIN_1.b, c)], device)
+        dt = self.wt_dtype
+        pk["qk"] = PackedConv([[WSrc(m.NIN_0.W, "nin"), WSrc(m.NIN_1.W, "nin")]], [(m.NIN_0.b, 0), (m.NIN_1.b, c)], device, dt)
         # A-operand "image" of the V^T GEMM: rows = output channel, K = input channel
-        pk["wv_img"] = torch.empty(1, 1, c, c, device=device, dtype=BF16)
+        pk["wv_img"] = torch.empty(1, 1, c, c, device=device, dtype=dt)
         pk["bv"] = torch.zeros(c + 16, device=device, dtype=torch.float32)
-        pk["v"] = PackedConv([WSrc(m.NIN_2.W, "nin")], m.NIN_2.b, device)   # training backward (dgrad of V)
-        pk["proj"] = PackedConv([WSrc(m.NIN_3.W, "nin")], m.NIN_3.b, device)
+        pk["v"] = PackedConv([WSrc(m.NIN_2.W, "nin")], m.NIN_2.b, device, dt)   # training backward (dgrad of V)
+        pk["proj"] = PackedConv([WSrc(m.NIN_3.W, "nin")], m.NIN_3.b, device, dt)
         self._refresh_attn(pk)
         return pk
 
@@ -856,18 +883,18 @@ class NetEngine:
             elif isinstance(m, (layerspp.AttnBlockpp, layers.AttnBlock)):
                 packed[i] = self._pack_attn(m, device)
             elif isinstance(m, (layers.Upsample, layers.Downsample)):
-                packed[i] = PackedConv([WSrc(m.Conv_0.weight)], m.Conv_0.bias, device) if m.with_conv else None
+                packed[i] = PackedConv([WSrc(m.Conv_0.weight)], m.Conv_0.bias, device, self.wt_dtype) if m.with_conv else None
             elif isinstance(m, torch.nn.Conv2d):
-                packed[i] = PackedConv([WSrc(m.weight)], m.bias, device)
+                packed[i] = PackedConv([WSrc(m.weight)], m.bias, device, self.wt_dtype)
             elif isinstance(m, layerspp.Combine):
-                packed[i] = PackedConv([WSrc(m.Conv_0.weight)], m.Conv_0.bias, device)
+                packed[i] = PackedConv([WSrc(m.Conv_0.weight)], m.Conv_0.bias, device, self.wt_dtype)
             elif isinstance(m, torch.nn.GroupNorm):
                 packed[i] = _gn_params(m, device) + (m.num_groups,)
             elif isinstance(m, (layerspp.Downsample, layerspp.Upsample)):
                 if hasattr(m, "Conv2d_0"):
-                    packed[i] = PackedConv([WSrc(m.Conv2d_0.weight)], m.Conv2d_0.bias, device)
+                    packed[i] = PackedConv([WSrc(m.Conv2d_0.weight)], m.Conv2d_0.bias, device, self.wt_dtype)
                 elif hasattr(m, "Conv_0"):
-                    packed[i] = PackedConv([WSrc(m.Conv_0.weight)], m.Conv_0.bias, device)
+                    packed[i] = PackedConv([WSrc(m.Conv_0.weight)], m.Conv_0.bias, device, self.wt_dtype)
             elif isinstance(m, torch.nn.Linear):
                 packed[i] = (m.weight.detach().to(device=device, dtype=torch.float32).contiguous(),
                              m.bias.detach().to(device=device, dtype=torch.float32).contiguous())
@@ -894,6 +921,9 @@ class NetEngine:
     def train_plan(self, batch, h, w, c0, c1, want_params=True, want_input=False, dropout=0.0):
         """Forward + backward plan (engine_train.TrainPlan) for differentiating the network."""
         from .engine_train import TrainPlan
+        if self.precision != "bf16":
+            raise CsdError("the differentiable (training / likelihood) plan exists for the bf16 plan only; "
+                           "call set_precision('bf16')")
         key = (batch, h, w, c0, c1, want_params, want_input, float(dropout))
         if key not in self.train_plans:
             self.train_plans[key] = TrainPlan(self, batch, h, w, c0, c1, want_params, want_input, float(dropout))
@@ -937,7 +967,7 @@ class NetPlan:
         self.use_graph = os.environ.get("CSD_NO_GRAPH", "0") != "1"
 
     def _make_pool(self, dev):
-        return BufferPool(dev)
+        return BufferPool(dev, self.eng.wt_dtype)
 
     def _make_ops(self, dev):
         return BlockOps(dev, self.pool, self.rec, self.stats)
@@ -952,7 +982,7 @@ class NetPlan:
         """cat(x, y) + `2x - 1` + NCHW fp32 -> NHWC bf16 in one kernel."""
         net, dev = self.eng.net, self.eng.device
         channels = c0 + c1
-        xin = Act(torch.empty(self.batch, self.h, self.w, K.ceil_to(channels, 8), device=dev, dtype=BF16), channels)
+        xin = Act(torch.empty(self.batch, self.h, self.w, K.ceil_to(channels, 8), device=dev, dtype=self.eng.wt_dtype), channels)
         if net.centered:
             self.rec.add(K.nchw_to_nhwc, self.in0, self.in1, xin.t, 1.0, 0.0)
         else:
@@ -1085,7 +1115,7 @@ class NetPlan:
             m_idx += 2
         # ---- input ----
         cpad = K.ceil_to(channels, 8)
-        xin = self.xin_act = Act(torch.empty(batch, h, w, cpad, device=dev, dtype=BF16), channels)
+        xin = self.xin_act = Act(torch.empty(batch, h, w, cpad, device=dev, dtype=eng.wt_dtype), channels)
         if net.centered:
             rec.add(K.nchw_to_nhwc, self.in0, self.in1, xin.t, 1.0, 0.0)
         else:

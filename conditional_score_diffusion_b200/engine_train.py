@@ -54,8 +54,7 @@ class TrainOps(BlockOps):
         self.tape.append(("dropout", dict(act=a, salt=salt)))
         return a
 
-    @staticmethod
-    def fusable(srcs, cout):
+    def fusable(self, srcs, cout):
         # the normalised + activated tensor is the wgrad operand of the convolution, so it has to exist in HBM
         return False
 

@@ -121,8 +121,9 @@ def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None
     nt_ = n_tile if n_tile is not None else None
     d.nseg = len(segments)
     k_total = 0
+    tf32 = segments[0][0].dtype == torch.float32     # fp32 activations + weights: the kind::tf32 per-tap kernel
     for i, (a, pitch, c_off, c_cnt, taps, norm, norm_silu) in enumerate(segments):
-        assert a.dtype == _BF16
+        assert a.dtype == (torch.float32 if tf32 else _BF16), "conv_gemm: mixed activation precisions"
         d.seg[i].a = a.data_ptr()
         d.seg[i].pitch = pitch
         d.seg[i].c_off = c_off
@@ -139,6 +140,12 @@ def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None
         n16 = ceil_to(d.n_store, 16)
         n_tile = n16 if n16 <= 256 else (ceil_to(n16 // 2, 16) if n16 <= 512 else 256)
     d.n_tile = n_tile
+    if tf32:
+        if transposed or halo:
+            raise _lib.CsdError("the fp32 / tf32 plan runs in the per-tap kernel only")
+        assert wt.dtype == torch.float32 and out.dtype == torch.float32 and (res is None or res.dtype == torch.float32)
+        halo = transposed = False
+        d.dtype = 1
     if halo is None:
         halo = (HALO_DEFAULT and tile is None and segments[0][4] == 9 and stride == 1 and pad == 1 and z_batches == 1
                 and w % 8 == 0 and h >= 16 and n_tile <= 512)
@@ -308,22 +315,24 @@ def step_advance(step_idx):
 def nchw_to_nhwc(src0, src1, out, scale=1.0, shift=0.0):
     b, c0, h, w = src0.shape
     c1 = src1.shape[1] if src1 is not None else 0
-    check(_lib.lib().csd_nchw_to_nhwc_bf16(_ptr(src0), c0, _ptr(src1), c1, _ptr(out), out.shape[-1], b, h, w,
-                                           float(scale), float(shift), _stream()))
+    fn = _lib.lib().csd_nchw_to_nhwc_f32 if out.dtype == torch.float32 else _lib.lib().csd_nchw_to_nhwc_bf16
+    check(fn(_ptr(src0), c0, _ptr(src1), c1, _ptr(out), out.shape[-1], b, h, w, float(scale), float(shift), _stream()))
     return out
 
 
 def nhwc_to_nchw(src, c_off, c_cnt, dst, row_scale=None):
     b, h, w, pitch = src.shape
-    check(_lib.lib().csd_nhwc_bf16_to_nchw(_ptr(src), pitch, c_off, c_cnt, _ptr(dst), b, h, w, _ptr(row_scale), _stream()))
+    fn = _lib.lib().csd_nhwc_f32_to_nchw if src.dtype == torch.float32 else _lib.lib().csd_nhwc_bf16_to_nchw
+    check(fn(_ptr(src), pitch, c_off, c_cnt, _ptr(dst), b, h, w, _ptr(row_scale), _stream()))
     return dst
 
 
 def gn_chan_stats(src, c, chan_sums):
-    """src [B, H, W, pitch] (or [B, HW, pitch]) bf16; chan_sums [B, c, 2] fp32, pre-zeroed."""
+    """src [B, H, W, pitch] (or [B, HW, pitch]) bf16 or fp32; chan_sums [B, c, 2] fp32 (stored, deterministic)."""
     b = src.shape[0]
     hw = src.numel() // (b * src.shape[-1])
-    check(_lib.lib().csd_gn_chan_stats_bf16(_ptr(src), c, src.shape[-1], _ptr(chan_sums), b, hw, _stream()))
+    fn = _lib.lib().csd_gn_chan_stats_f32 if src.dtype == torch.float32 else _lib.lib().csd_gn_chan_stats_bf16
+    check(fn(_ptr(src), c, src.shape[-1], _ptr(chan_sums), b, hw, _stream()))
     return chan_sums
 
 
@@ -343,9 +352,10 @@ def gn_coeffs(sums0, c0, sums1, c1, gamma, beta, coef0, coef1, hw, groups, eps=1
 def gn_apply(src0, c0, sums0, src1, c1, sums1, gamma, beta, out, groups, eps=1e-6, silu=True):
     b = src0.shape[0]
     hw = src0.numel() // (b * src0.shape[-1])
-    check(_lib.lib().csd_gn_apply_bf16(_ptr(src0), c0, src0.shape[-1], _ptr(sums0), _ptr(src1), c1,
-                                       src1.shape[-1] if src1 is not None else 0, _ptr(sums1), _ptr(gamma), _ptr(beta),
-                                       _ptr(out), out.shape[-1], b, hw, groups, float(eps), int(silu), _stream()))
+    fn = _lib.lib().csd_gn_apply_f32 if src0.dtype == torch.float32 else _lib.lib().csd_gn_apply_bf16
+    check(fn(_ptr(src0), c0, src0.shape[-1], _ptr(sums0), _ptr(src1), c1,
+             src1.shape[-1] if src1 is not None else 0, _ptr(sums1), _ptr(gamma), _ptr(beta),
+             _ptr(out), out.shape[-1], b, hw, groups, float(eps), int(silu), _stream()))
     return out
 
 
@@ -359,17 +369,19 @@ def gn_coeffs_partials(src0, src1, gamma, beta, coef0, coef1, batch, hw, groups,
     return coef0
 
 
-def gn_fused_supported(c0, c1, hw, groups, batch):
+def gn_fused_supported(c0, c1, hw, groups, batch, dtype=_BF16):
     """Host-side test: does the one-launch GroupNorm (statistics + apply) take this shape?"""
-    return bool(_lib.lib().csd_gn_fused_supported(int(c0), int(c1), int(hw), int(groups), int(batch)))
+    fn = _lib.lib().csd_gn_fused_supported_f32 if dtype == torch.float32 else _lib.lib().csd_gn_fused_supported
+    return bool(fn(int(c0), int(c1), int(hw), int(groups), int(batch)))
 
 
 def gn_fused(src0, c0, src1, c1, gamma, beta, out, groups, eps=1e-6, silu=True):
     b = src0.shape[0]
     hw = src0.numel() // (b * src0.shape[-1])
-    check(_lib.lib().csd_gn_fused_bf16(_ptr(src0), c0, src0.shape[-1], _ptr(src1), c1,
-                                       src1.shape[-1] if src1 is not None else 0, _ptr(gamma), _ptr(beta), _ptr(out),
-                                       out.shape[-1], b, hw, groups, float(eps), int(silu), _stream()))
+    fn = _lib.lib().csd_gn_fused_f32 if src0.dtype == torch.float32 else _lib.lib().csd_gn_fused_bf16
+    check(fn(_ptr(src0), c0, src0.shape[-1], _ptr(src1), c1,
+             src1.shape[-1] if src1 is not None else 0, _ptr(gamma), _ptr(beta), _ptr(out),
+             out.shape[-1], b, hw, groups, float(eps), int(silu), _stream()))
     return out
 
 
@@ -377,15 +389,15 @@ def fir_resample(src, out, mode, taps, add=None):
     """mode 'up' | 'down' | 'prefilter'; src/out NHWC bf16."""
     b, h, w, pitch = src.shape
     arr = (ctypes.c_float * 4)(*[float(t) for t in taps])
-    check(_lib.lib().csd_fir_resample_nhwc_bf16(_ptr(src), _ptr(out), _ptr(add), b, h, w, pitch,
-                                                {"up": 1, "down": 2, "prefilter": 3}[mode], arr, _stream()))
+    fn = _lib.lib().csd_fir_resample_nhwc_f32 if src.dtype == torch.float32 else _lib.lib().csd_fir_resample_nhwc_bf16
+    check(fn(_ptr(src), _ptr(out), _ptr(add), b, h, w, pitch, {"up": 1, "down": 2, "prefilter": 3}[mode], arr, _stream()))
     return out
 
 
 def softmax_rows(logits, probs, cols, scale):
     rows = logits.numel() // logits.shape[-1]
-    check(_lib.lib().csd_softmax_rows_f32_bf16(_ptr(logits), logits.shape[-1], _ptr(probs), probs.shape[-1], rows, cols,
-                                               float(scale), _stream()))
+    fn = _lib.lib().csd_softmax_rows_f32_f32 if probs.dtype == torch.float32 else _lib.lib().csd_softmax_rows_f32_bf16
+    check(fn(_ptr(logits), logits.shape[-1], _ptr(probs), probs.shape[-1], rows, cols, float(scale), _stream()))
     return probs
 
 
@@ -447,14 +459,14 @@ class PackTable:
 
 
 def pack_job(src, dst, rows, cols, taps, k_pad, dst_pitch, s_row, s_col, s_tap, flip=False, scale=1.0, src_off=0, dst_off=0):
-    """kind-0 job; src fp32 tensor (+ element offset), dst bf16 tensor (+ element offset)."""
+    """kind-0 / kind-2 job; src fp32 tensor (+ element offset), dst bf16 or fp32 tensor (+ element offset)."""
     j = _lib.PackJob()
     j.src = src.data_ptr() + 4 * src_off
     j.src2 = None
-    j.dst = dst.data_ptr() + 2 * dst_off
+    j.dst = dst.data_ptr() + dst.element_size() * dst_off
     j.s_row, j.s_col, j.s_tap = s_row, s_col, s_tap
     j.rows, j.cols, j.taps, j.k_pad, j.dst_pitch = rows, cols, taps, k_pad, dst_pitch
-    j.flip, j.kind, j.scale = int(flip), 0, float(scale)
+    j.flip, j.kind, j.scale = int(flip), (2 if dst.dtype == torch.float32 else 0), float(scale)
     return j
 
 

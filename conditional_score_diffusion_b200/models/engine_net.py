@@ -124,6 +124,18 @@ class EngineNet(_Base):
         """forward(x, time_cond) * inv_std[:, None, None, None], fused into the output kernel."""
         return self._run(x, None, time_cond, scale0=inv_std)[0]
 
+    def set_precision(self, precision):
+        """'bf16' (default: bf16 activations + bf16 tensor-core operands, the fast plan) or 'tf32' (fp32 activations in
+        HBM + tf32 tensor-core operands: the reference's own precision class - fp32 storage everywhere,
+        sampling/unconditional.py:206, cuDNN TF32 convolutions under PyTorch's defaults). Inference plans only; cached
+        samplers re-plan on their next call. Returns self."""
+        self._engine.set_precision(precision)
+        return self
+
+    @property
+    def precision(self):
+        return self._engine.precision
+
 
 class SqueezeBlock(nn.Module):
     """models/ncsnpp.py:403-416: space-to-depth by 2 (channel order c*4 + dy*2 + dx) and its inverse. A pure

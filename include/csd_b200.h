@@ -143,9 +143,9 @@ int csd_nchw_to_nhwc_bf16(const float* src0, int c0, const float* src1, int c1, 
 int csd_nhwc_bf16_to_nchw(const void* src, int c_pitch, int c_off, int c_cnt, float* dst, int batch,
                           int h, int w, const float* row_scale, csd_stream_t stream);
 
-/* Per-channel GroupNorm statistics of ONE NHWC bf16 tensor: chan_sums[b, c, 0..1] += (sum x, sum x^2);
- * the caller zeroes chan_sums beforehand. A tensor's sums are computed once and reused by every
- * GroupNorm that reads it (nn.GroupNorm call sites: models/layerspp.py:67,219,231; ncsnpp.py:200-233). */
+/* Per-channel GroupNorm statistics of ONE NHWC bf16 tensor: chan_sums[b, c, 0..1] = (sum x, sum x^2), stored (not
+ * accumulated) by a fixed-order reduction: bitwise reproducible run to run. A tensor's sums are computed once and
+ * reused by every GroupNorm that reads it (nn.GroupNorm call sites: models/layerspp.py:67,219,231; ncsnpp.py:200-233). */
 int csd_gn_chan_stats_bf16(const void* src, int c, int pitch, float* chan_sums, int batch, int hw,
                            csd_stream_t stream);
 
@@ -200,6 +200,27 @@ int csd_gn_coeffs_partials_f32(const float* sums0, const float* partials0, int t
  * models/ncsnpp.py:344-349).                                                                    */
 int csd_fir_resample_nhwc_bf16(const void* src, void* out, const void* add, int batch, int h, int w,
                                int c_pitch, int mode, const float* taps4_host, csd_stream_t stream);
+
+/* ---- fp32-activation variants ("tf32" plan: NHWC fp32 tensors, channel pitch a multiple of 8) ----
+ * Same arguments and semantics as their *_bf16 namesakes above; src / out / add / probs are float. Together with
+ * csd_conv_gemm's dtype = 1 they form the reference-precision plan (fp32 storage like the reference,
+ * sampling/unconditional.py:206, models/ncsnpp.py:264-266; TF32 tensor-core operands like its cuDNN convolutions). */
+int csd_nchw_to_nhwc_f32(const float* src0, int c0, const float* src1, int c1, void* out, int c_pad, int batch, int h,
+                         int w, float scale, float shift, csd_stream_t stream);
+int csd_nhwc_f32_to_nchw(const void* src, int c_pitch, int c_off, int c_cnt, float* dst, int batch, int h, int w,
+                         const float* row_scale, csd_stream_t stream);
+int csd_gn_chan_stats_f32(const void* src, int c, int pitch, float* chan_sums, int batch, int hw, csd_stream_t stream);
+int csd_gn_apply_f32(const void* src0, int c0, int pitch0, const float* sums0, const void* src1, int c1, int pitch1,
+                     const float* sums1, const float* gamma, const float* beta, void* out, int out_pitch, int batch,
+                     int hw, int groups, float eps, int apply_silu, csd_stream_t stream);
+int csd_gn_fused_supported_f32(int c0, int c1, int hw, int groups, int batch);
+int csd_gn_fused_f32(const void* src0, int c0, int pitch0, const void* src1, int c1, int pitch1, const float* gamma,
+                     const float* beta, void* out, int out_pitch, int batch, int hw, int groups, float eps,
+                     int apply_silu, csd_stream_t stream);
+int csd_fir_resample_nhwc_f32(const void* src, void* out, const void* add, int batch, int h, int w, int c_pitch,
+                              int mode, const float* taps4_host, csd_stream_t stream);
+int csd_softmax_rows_f32_f32(const float* logits, int in_pitch, void* probs, int out_pitch, int64_t rows, int cols,
+                             float scale, csd_stream_t stream);
 
 /* rows x cols softmax of fp32 logits (pitch in_pitch) times `scale`, bf16 output (pitch out_pitch,
  * columns >= cols zero-filled): F.softmax of models/layerspp.py:82-85.                          */
@@ -279,6 +300,11 @@ typedef struct csd_conv_gemm_desc {
   float scale;
   float* stat_partials;         /* mode 2 only: [pixel tiles, n_store, 2] per-tile per-channel (sum, sum of
                                    squares) of the stored bf16 output (GroupNorm statistics), or NULL */
+  int32_t dtype;                /* 0 = bf16 activations / weights / residual, tcgen05 kind::f16 (the fast plan);
+                                   1 = fp32 activations / weights / residual / output, tcgen05 kind::tf32 - the
+                                   reference's own precision class (fp32 storage, sampling/unconditional.py:206; cuDNN
+                                   TF32 convolutions): A, wt, res, out are float, pitches stay in elements      */
+  int32_t reserved_;
 } csd_conv_gemm_desc;
 
 int csd_conv_gemm(const csd_conv_gemm_desc* desc, csd_stream_t stream);
@@ -313,7 +339,8 @@ int csd_fused_adam_ema_f32(float* p, const float* g, float* m, float* v, float* 
  * c*s_col + ts*s_tap], ts = flip ? taps-1-tap : tap, for r < rows, c < cols, tap < taps (dst / src already offset to
  * the block; padding elements of dst are never written and stay zero). Forward nn.Conv2d weight [Cout,Cin,kh,kw]: r =
  * co, c = ci, (s_row, s_col, s_tap) = (Cin*taps, taps, 1); its data gradient: r = ci, c = co, flip = 1; NIN.W [in,out]:
- * (1, out, 0). kind 1: dst (fp32) [i] = src[i] + src2[i] for i < rows (bias vectors; src2 may be NULL).         */
+ * (1, out, 0). kind 1: dst (fp32) [i] = src[i] + src2[i] for i < rows (bias vectors; src2 may be NULL). kind 2: kind 0
+ * with an fp32 destination (operands of the tf32 plan, csd_conv_gemm dtype = 1).                                   */
 typedef struct csd_pack_job {
   const float* src;
   const float* src2;
