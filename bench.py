@@ -214,9 +214,27 @@ def stock_gpu_steps(cfg, batch, steps, warmup, device):
     torch.manual_seed(2)
     y = torch.rand(batch, 3, cfg.data.image_size, cfg.data.image_size)
     r = ref_harness.conditional_pc_time(cfg, bench_state_dict(cfg), y, steps, warmup, device, SNR, EPS)
+    # what the reference's own precision class (fp32 storage, cuDNN TF32 convolutions) costs against exact fp32: the
+    # same network / weights / inputs as network_parity(), evaluated by the unmodified reference on the GPU
+    par = None
+    try:
+        from oracle import ncsnpp as o_net
+        sd = bench_state_dict(cfg)
+        x, yy, labels = parity_inputs(cfg)
+        ref = o_net.forward_paired(sd, o_net.model_options(cfg), x, yy, labels)
+        rm = ref_harness.create_model(cfg, sd, device)
+        with torch.no_grad():
+            out = rm({"x": x.to(device), "y": yy.to(device)}, labels.to(device))
+        mx = max((out[k].cpu() - ref[k]).abs().max().item() / ref[k].abs().max().item() for k in ("x", "y"))
+        l2 = max(((out[k].cpu() - ref[k]).norm() / ref[k].norm()).item() for k in ("x", "y"))
+        par = {"max_rel": mx, "l2_rel": l2, "what": "unmodified reference on cuda (TF32 convolutions) vs CPU fp32 oracle, "
+                                                    "same network / inputs as `parity`"}
+        del rm
+    except Exception as e:  # noqa: BLE001
+        par = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     torch.cuda.empty_cache()
     ms = r["s_per_step"] * 1e3
-    return {"ms_per_step": ms, "images_per_s": batch / (r["s_per_step"] * PC_STEPS), "batch": batch, "steps": steps,
+    return {"ms_per_step": ms, "parity_vs_fp32": par, "images_per_s": batch / (r["s_per_step"] * PC_STEPS), "batch": batch, "steps": steps,
             "warmup_steps": warmup, "finite_output": r["finite"], "dtype": "f32 storage, cuDNN TF32 convolutions (PyTorch defaults)",
             "what": "unmodified reference (baseline/_ref) on cuda: sampling/conditional.py PC loop, models/ncsnpp.py eager "
                     "modules, the reference's own upfirdn2d CUDA extension"}
@@ -357,16 +375,22 @@ def ncu_traffic(kernel):
         return None
 
 
-def network_parity(cfg, model, dev, precision="bf16"):
-    """max / L2 relative error of the benchmarked network (the bench weights, B = 2, sigma-scaled inputs) against the
-    CPU oracle restatement of models/ncsnpp.py (pinned to the unmodified reference by tests/test_oracle_golden.py)."""
+def parity_inputs(cfg):
     import torch
-    from oracle import ncsnpp as o_net
     g = torch.Generator().manual_seed(77)
     hw = cfg.data.image_size
     x = torch.randn(2, 3, hw, hw, generator=g) * 20.0
     y = torch.rand(2, 3, hw, hw, generator=g)
     labels = torch.tensor([700.0, 150.0])
+    return x, y, labels
+
+
+def network_parity(cfg, model, dev, precision="bf16"):
+    """max / L2 relative error of the benchmarked network (the bench weights, B = 2, sigma-scaled inputs) against the
+    CPU oracle restatement of models/ncsnpp.py (pinned to the unmodified reference by tests/test_oracle_golden.py)."""
+    import torch
+    from oracle import ncsnpp as o_net
+    x, y, labels = parity_inputs(cfg)
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     o = o_net.model_options(cfg)
     with torch.no_grad():
@@ -381,6 +405,40 @@ def network_parity(cfg, model, dev, precision="bf16"):
         l2 = max(l2, ((got - r).norm() / (r.norm() + 1e-30)).item())
     res["max_rel"], res["l2_rel"] = mx, l2
     return res
+
+
+def tf32_line(cfg, model, sde, shape, dev, steps, B, world):
+    """The same PC step on the reference-precision plan (model.set_precision('tf32')): device-timed like `value`
+    (rank 0 only; a context line beside the bf16 headline, same workload, same batch)."""
+    import torch
+    from conditional_score_diffusion_b200.sampling.fused import FusedPCSampler
+    model.set_precision("tf32")
+    fs = FusedPCSampler(model, sde, shape, "reverse_diffusion", "langevin", SNR, PC_STEPS, 1, False, True, True, EPS,
+                        conditional=True)
+    fs._setup(dev)
+    fs.y.copy_(torch.rand(*shape, device=dev))
+    graph = fs._graph(draw_noise=True)
+    fs.x.copy_(torch.randn(*shape, device=dev) * cfg.model.sigma_max_x)
+    fs.step_idx.zero_()
+    for _ in range(3):
+        graph.replay()
+    fs.step_idx.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    finite = bool(torch.isfinite(fs.x).all().item())
+    par = network_parity(cfg, model, dev, "tf32")
+    gb = fs.plan.pool.nbytes() / 1e9
+    del fs, graph
+    torch.cuda.empty_cache()
+    return {"dtype": "tf32 operands, fp32 activations in HBM (the reference's precision class)", "ms_per_step": ms,
+            "value": B / (ms * 1e-3 * PC_STEPS), "unit": "images/s per GPU", "steps": steps, "finite_output": finite,
+            "parity": par, "plan_buffers_gb": gb}
 
 
 def run_b200(args):
@@ -534,6 +592,15 @@ def run_b200(args):
     # ---- parity of the benchmarked network (same weights, B = 2) against the CPU oracle ----
     parity = network_parity(cfg, model, dev)
 
+    # ---- the reference-precision plan next to the bf16 one: fp32 activations in HBM, tcgen05 kind::tf32 operands ----
+    tf32 = None
+    if not args.no_tf32:
+        try:
+            tf32 = tf32_line(cfg, model, sde, shape, dev, min(k_eff, 10), B, world)
+        except Exception as e:  # noqa: BLE001
+            tf32 = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        model.set_precision("bf16")
+
     # ---- stock PyTorch + cuDNN on the same GPU: the unmodified reference, B = 64 ----
     stock = None
     if not args.no_stock_gpu:
@@ -564,10 +631,14 @@ def run_b200(args):
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info,
         "plan_buffers_gb": fs.plan.pool.nbytes() / 1e9, "parity": parity,
     }
+    if tf32 is not None:
+        line["tf32"] = tf32
     if stock is not None:
         line["stock_gpu"] = stock
         if "ms_per_step" in stock:
             line["vs_stock_gpu"] = stock["ms_per_step"] / ms_per_step
+            if tf32 is not None and "ms_per_step" in tf32:
+                tf32["vs_stock_gpu"] = stock["ms_per_step"] / tf32["ms_per_step"]
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -754,6 +825,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)  # 200 of the 1000 identical steps
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_eager_gpu"])
+    ap.add_argument("--no-tf32", action="store_true", help="skip the reference-precision (tf32 plan) context line")
     ap.add_argument("--no-stock-gpu", action="store_true", help="skip the stock PyTorch + cuDNN leg (the unmodified "
                     "reference on the same GPU)")
     ap.add_argument("--torch-optim", action="store_true", help="train workload: torch Adam instead of the fused optimizer")

@@ -72,7 +72,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("scale", c_float),
         ("stat_partials", c_void_p),
         ("dtype", c_int32),
-        ("reserved_", c_int32),
+        ("out_round_tf32", c_int32),
     ]
 
 

@@ -36,50 +36,29 @@ struct GnBwdStatsParams {
   int hw, slabs, silu;
 };
 
-__global__ void gn_bwd_stats_kernel(GnBwdStatsParams p) {
-  extern __shared__ float sm[];            // [ppb][2*C]
+// Deterministic (no atomics): grid = (V / Vs, batch), a CTA owns Vs channel vectors of one image, walks all its pixels
+// with ppb = blockDim / Vs pixel lanes, reduces the lanes in a fixed order and STORES the sums.
+__global__ void __launch_bounds__(256) gn_bwd_stats_kernel(GnBwdStatsParams p, int Vs) {
+  extern __shared__ float sm[];            // [ppb][16 * Vs]
   const int V = p.xv, C = V * 8;
-  const int b = blockIdx.x / p.slabs, slab = blockIdx.x % p.slabs;
-  const int ppb = blockDim.x / V;
-  const int v = threadIdx.x % V, pp = threadIdx.x / V;
-  const long long chunk = ceil_div_ll(p.hw, p.slabs);
-  const long long lo = slab * chunk, hi = min((long long)p.hw, lo + chunk);
+  const int b = blockIdx.y;
+  const int ppb = blockDim.x / Vs;
+  const int v = threadIdx.x % Vs, pp = threadIdx.x / Vs;
+  const int gv = blockIdx.x * Vs + v;
+  const int n2 = 16 * Vs;
   float s1[8], s2[8], sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-  if (pp < ppb) {
+  if (pp < ppb && gv < V) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float2 c = p.coef[(long long)b * C + v * 8 + i];
+      const float2 c = p.coef[(long long)b * C + gv * 8 + i];
       sc[i] = c.x; sh[i] = c.y;
     }
-    constexpr int U = 1;   // measured: 2 or 4 loads in flight cost more in registers / occupancy than they hide here
-    long long pix = lo + pp;
-    for (; pix + (long long)(U - 1) * ppb < hi; pix += (long long)U * ppb) {
-      bf16x8 vx[U], vd[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long bp = (long long)b * p.hw + pix + (long long)u * ppb;
-        vx[u] = p.x[bp * p.xpv + v];
-        vd[u] = p.dy[bp * p.dy_pv + p.dy_voff + v];
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float fx[8], fd[8];
-        unpack8(vx[u], fx);
-        unpack8(vd[u], fd);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float du = p.silu ? fd[i] * silu_grad(fmaf(fx[i], sc[i], sh[i])) : fd[i];
-          s1[i] += du;
-          s2[i] = fmaf(du, fx[i], s2[i]);
-        }
-      }
-    }
-    for (; pix < hi; pix += ppb) {
+    for (long long pix = pp; pix < p.hw; pix += ppb) {
       float fx[8], fd[8];
-      unpack8(p.x[((long long)b * p.hw + pix) * p.xpv + v], fx);
-      unpack8(p.dy[((long long)b * p.hw + pix) * p.dy_pv + p.dy_voff + v], fd);
+      unpack8(p.x[((long long)b * p.hw + pix) * p.xpv + gv], fx);
+      unpack8(p.dy[((long long)b * p.hw + pix) * p.dy_pv + p.dy_voff + gv], fd);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float du = p.silu ? fd[i] * silu_grad(fmaf(fx[i], sc[i], sh[i])) : fd[i];
@@ -87,15 +66,26 @@ __global__ void gn_bwd_stats_kernel(GnBwdStatsParams p) {
         s2[i] = fmaf(du, fx[i], s2[i]);
       }
     }
-    float* row = sm + (size_t)pp * 2 * C + v * 16;
+  }
+  if (pp < ppb) {
+    float* row = sm + (size_t)pp * n2 + v * 16;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { row[2 * i] = s1[i]; row[2 * i + 1] = s2[i]; }
   }
   __syncthreads();
-  for (int c2 = threadIdx.x; c2 < 2 * C; c2 += blockDim.x) {
-    float a = 0.f;
-    for (int r = 0; r < ppb; ++r) a += sm[(size_t)r * 2 * C + c2];
-    atomicAdd(p.s + ((long long)b * p.c_total + p.s_coff) * 2 + c2, a);
+  for (int c2 = threadIdx.x; c2 < n2; c2 += blockDim.x) {
+    const int ch2 = blockIdx.x * n2 + c2;          // (channel, sum | sum*x) slot of this source
+    if (ch2 >= 2 * C) continue;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int r = 0;
+    for (; r + 3 < ppb; r += 4) {
+      a0 += sm[(size_t)r * n2 + c2];
+      a1 += sm[(size_t)(r + 1) * n2 + c2];
+      a2 += sm[(size_t)(r + 2) * n2 + c2];
+      a3 += sm[(size_t)(r + 3) * n2 + c2];
+    }
+    for (; r < ppb; ++r) a0 += sm[(size_t)r * n2 + c2];
+    p.s[((long long)b * p.c_total + p.s_coff) * 2 + ch2] = (a0 + a1) + (a2 + a3);
   }
 }
 
@@ -594,14 +584,15 @@ int csd_gn_bwd_stats_bf16(const void* x, int c, int x_pitch, const void* dy, int
   p.coef = reinterpret_cast<const float2*>(fwd_coef);
   p.s = s; p.c_total = c_total; p.s_coff = s_c_off; p.hw = hw; p.silu = silu;
   const int V = c / 8;
-  const int ppb = std::max(1, 256 / V);
-  const int threads = V * ppb;
-  int slabs = ceil_div(num_sms() * 8, batch);
-  p.slabs = std::max(1, std::min(slabs, std::max(1, hw / (ppb * 4))));
-  const size_t smem = sizeof(float) * 2 * c * ppb;
-  if (smem > 48 * 1024)
-    CSD_CUDA(cudaFuncSetAttribute(gn_bwd_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gn_bwd_stats_kernel<<<batch * p.slabs, threads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  p.slabs = 1;
+  // Vs channel vectors per CTA: 32-byte pixel rows at least, fatter CTAs once the batch alone fills the machine
+  int vs = 2;
+  while (vs * 2 <= 8 && V % (vs * 2) == 0 && (long long)batch * (V / (vs * 2)) >= 4LL * num_sms()) vs *= 2;
+  if (V % vs != 0) vs = 1;
+  const int ppb = 256 / vs;
+  const size_t smem = sizeof(float) * 16 * vs * (size_t)ppb;
+  CSD_REQUIRE(batch <= 65535, "gn_bwd_stats: batch %d too large", batch);
+  gn_bwd_stats_kernel<<<dim3((unsigned)(V / vs), (unsigned)batch), vs * ppb, smem, static_cast<cudaStream_t>(stream)>>>(p, vs);
   CSD_LAUNCH_CHECK("gn_bwd_stats_kernel");
   return CSD_OK;
 }

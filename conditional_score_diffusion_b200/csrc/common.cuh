@@ -129,6 +129,16 @@ template <typename VT> __device__ __forceinline__ float silu_act(float v);
 template <> __device__ __forceinline__ float silu_act<bf16x8>(float v) { return silu_f(v); }
 template <> __device__ __forceinline__ float silu_act<f32x8>(float v) { return v / (1.0f + expf(-v)); }
 
+// Round-to-nearest fp32 -> tf32 (10 explicit mantissa bits, low 13 bits zero). tcgen05 kind::tf32 TRUNCATES the fp32
+// words it reads, which biases every product towards zero by ~2^-11; tensors of the tf32 plan that are consumed only as
+// tensor-core operands (normalised activations, FIR outputs, attention q/k/v/probabilities, packed weights) are
+// therefore rounded when they are produced - what cuDNN/CUTLASS TF32 convolutions do to their operands internally.
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
 // scalar element type of a vector type
 template <typename VT> struct ElemOf;
 template <> struct ElemOf<bf16x8> { using type = __nv_bfloat16; };

@@ -87,6 +87,7 @@ struct ConvGemmKernelParams {
   int has_norm;
   void* out;
   int out_pitch, out_f32;
+  int out_round;   // fp32 output rounded to tf32 (tensors that only feed further tensor-core operands: q|k, V^T, P V)
   long long out_z_stride;
   const float* bias;
   int bias_per_row;
@@ -192,6 +193,10 @@ __device__ __forceinline__ void epilogue_rows(const ConvGemmKernelParams& p, uin
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] *= p.scale;
+      if (kF32 && p.out_round) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = round_tf32(v[i]);
+      }
 
       if (kF32 || p.out_f32) {
         float* op = reinterpret_cast<float*>(p.out) + (long long)z * p.out_z_stride + pix * p.out_pitch + n;
@@ -1225,6 +1230,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   p.num_stages = stages;
 
   p.out = d->out; p.out_pitch = d->out_pitch; p.out_f32 = d->out_f32; p.out_z_stride = d->out_z_stride;
+  p.out_round = tf32 ? d->out_round_tf32 : 0;
   p.bias = d->bias; p.bias_per_row = d->bias_per_row;
   p.temb = d->temb; p.temb_pitch = d->temb_pitch;
   p.res = reinterpret_cast<const __nv_bfloat16*>(d->res); p.res_pitch = d->res_pitch;

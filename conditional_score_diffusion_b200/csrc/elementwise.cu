@@ -10,10 +10,60 @@
 #include "common.cuh"
 #include "../../include/csd_b200.h"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <initializer_list>
 
 namespace csd {
+
+namespace cg = cooperative_groups;
+
+// ---- deterministic reductions ---------------------------------------------------------------------------------
+// The reference is bitwise reproducible under a seed; float atomics are not (the Langevin norms set the
+// step size of the whole batch). Every reduction here has a FIXED summation order:
+//   * block level: per-thread strided accumulation, xor-shuffle tree inside a warp, warps summed in index order;
+//   * per-sample sums (Langevin norms, loss terms): one thread-block cluster of kRedCluster CTAs per sample, the
+//     CTAs' partials are read back through distributed shared memory by rank 0 and summed in rank order;
+//   * device-wide sums (gradient norm, RK45 error norm): every CTA stores its partial in a caller-provided workspace,
+//     the CTA that takes the last ticket (integer atomic: order-free) sums the partials in index order.
+constexpr int kRedCluster = 8;
+constexpr int kRedThreads = 512;
+
+// Sum over the block of `v` (two values at once), valid in thread 0. smem: 2 * 32 floats.
+__device__ __forceinline__ float2 block_sum2(float a, float c, float* red /*[64]*/) {
+  a = warp_sum(a);
+  c = warp_sum(c);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) { red[warp] = a; red[32 + warp] = c; }
+  __syncthreads();
+  float ta = 0.f, tc = 0.f;
+  if (threadIdx.x == 0)
+    for (int k = 0; k < nw; ++k) { ta += red[k]; tc += red[32 + k]; }
+  return make_float2(ta, tc);
+}
+
+// Device-wide deterministic sum: ws[0] = result, ws[1] = ticket counter (kept zero between calls), ws[8 + i] = partial
+// of CTA i. `t` is this CTA's partial (valid in thread 0).
+__device__ __forceinline__ void grid_sum_store(float t, float* ws, float* red /*[64]*/) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    ws[8 + blockIdx.x] = t;
+    __threadfence();
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(ws) + 1, 1u);
+    s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float a = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) a += __ldcg(ws + 8 + i);
+  const float2 r = block_sum2(a, 0.f, red);
+  if (threadIdx.x == 0) {
+    ws[0] = r.x;
+    reinterpret_cast<unsigned*>(ws)[1] = 0u;
+  }
+}
 
 static inline int ew_blocks(long long n_vec) {
   long long b = ceil_div_ll(n_vec, 256);
@@ -106,14 +156,18 @@ sde_perturb_kernel(const float* __restrict__ x, const float* __restrict__ z, flo
 
 // Per-sample denoising score-matching residual: losses[b] += w[b] * sum_i (a[b]*score_i + c[b]*z_i)^2
 // (losses.py:139-145 / 197-203 / 223-229: a = 1, c = 1/std, w = g^2 * reduce factor with likelihood weighting;
-// a = std, c = 1 without). One CTA row per sample slab, partial sums combined with atomics.
-__global__ void __launch_bounds__(256)
+// a = std, c = 1 without). One cluster of kRedCluster CTAs per sample; deterministic (see above).
+__global__ void __cluster_dims__(kRedCluster, 1, 1) __launch_bounds__(kRedThreads)
 dsm_loss_kernel(const float* __restrict__ score, const float* __restrict__ z, const float* __restrict__ a,
                 const float* __restrict__ c, const float* __restrict__ w, float* __restrict__ losses,
-                long long per_sample, int slabs) {
-  const int b = blockIdx.x / slabs, slab = blockIdx.x % slabs;
-  const long long chunk = ceil_div_ll(per_sample, slabs);
-  const long long lo = slab * chunk, hi = min(per_sample, lo + chunk);
+                long long per_sample) {
+  __shared__ float red[64];
+  __shared__ float part[2];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.y;
+  const long long chunk = ceil_div_ll(per_sample, kRedCluster);
+  const long long lo = rank * chunk, hi = min(per_sample, lo + chunk);
   const float* sp = score + (long long)b * per_sample;
   const float* zp = z + (long long)b * per_sample;
   const float ab = a[b], cb = c[b];
@@ -122,51 +176,66 @@ dsm_loss_kernel(const float* __restrict__ score, const float* __restrict__ z, co
     const float r = fmaf(ab, sp[i], cb * zp[i]);
     acc = fmaf(r, r, acc);
   }
-  acc = warp_sum(acc);
-  __shared__ float red[8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) red[warp] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int k = 0; k < 8; ++k) t += red[k];
-    atomicAdd(losses + b, t * w[b]);
+  const float2 t = block_sum2(acc, 0.f, red);
+  if (threadIdx.x == 0) part[0] = t.x;
+  cluster.sync();
+  if (rank == 0 && threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int k = 0; k < kRedCluster; ++k) tot += *cluster.map_shared_rank(part, k);
+    losses[b] += tot * w[b];
   }
+  cluster.sync();     // the peers' shared memory stays alive until rank 0 has read it
 }
 
-// One CTA row per sample slab; partial sums of squares are combined with atomics into sq[2*batch].
-__global__ void __launch_bounds__(256)
-sumsq_pair_kernel(const float* __restrict__ g, const float* __restrict__ z, float* __restrict__ sq, int batch,
-                  long long per_sample, int slabs) {
-  const int b = blockIdx.x / slabs, slab = blockIdx.x % slabs;
-  const long long chunk = ceil_div_ll(per_sample, slabs);
-  const long long lo = slab * chunk, hi = min(per_sample, lo + chunk);
+// norms[b] = ||g_b||, norms[batch + b] = ||z_b|| (sampling/correctors.py:72-74,102-104): per-sample L2 norms of the
+// score and the noise in ONE launch (sums of squares and the square root), deterministic.
+__global__ void __cluster_dims__(kRedCluster, 1, 1) __launch_bounds__(kRedThreads)
+norm_pair_kernel(const float* __restrict__ g, const float* __restrict__ z, float* __restrict__ norms, int batch,
+                 long long per_sample, int vec4) {
+  __shared__ float red[64];
+  __shared__ float part[2];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.y;
   const float* gp = g + (long long)b * per_sample;
   const float* zp = z + (long long)b * per_sample;
   float sg = 0.f, sz = 0.f;
-  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const float a = gp[i], c = zp[i];
-    sg = fmaf(a, a, sg);
-    sz = fmaf(c, c, sz);
+  if (vec4) {
+    const long long n4 = per_sample >> 2;
+    const long long chunk = ceil_div_ll(n4, kRedCluster);
+    const long long lo = rank * chunk, hi = min(n4, lo + chunk);
+    const float4* g4 = reinterpret_cast<const float4*>(gp);
+    const float4* z4 = reinterpret_cast<const float4*>(zp);
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const float4 a = __ldg(g4 + i), c = __ldg(z4 + i);
+      sg = fmaf(a.x, a.x, sg); sg = fmaf(a.y, a.y, sg); sg = fmaf(a.z, a.z, sg); sg = fmaf(a.w, a.w, sg);
+      sz = fmaf(c.x, c.x, sz); sz = fmaf(c.y, c.y, sz); sz = fmaf(c.z, c.z, sz); sz = fmaf(c.w, c.w, sz);
+    }
+  } else {
+    const long long chunk = ceil_div_ll(per_sample, kRedCluster);
+    const long long lo = rank * chunk, hi = min(per_sample, lo + chunk);
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const float a = gp[i], c = zp[i];
+      sg = fmaf(a, a, sg);
+      sz = fmaf(c, c, sz);
+    }
   }
-  sg = warp_sum(sg);
-  sz = warp_sum(sz);
-  __shared__ float red[2][8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { red[0][warp] = sg; red[1][warp] = sz; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  const float2 t = block_sum2(sg, sz, red);
+  if (threadIdx.x == 0) { part[0] = t.x; part[1] = t.y; }
+  cluster.sync();
+  if (rank == 0 && threadIdx.x == 0) {
     float a = 0.f, c = 0.f;
-    for (int w = 0; w < 8; ++w) { a += red[0][w]; c += red[1][w]; }
-    atomicAdd(sq + b, a);
-    atomicAdd(sq + batch + b, c);
+    for (int k = 0; k < kRedCluster; ++k) {
+      const float* rp = cluster.map_shared_rank(part, k);
+      a += rp[0];
+      c += rp[1];
+    }
+    norms[b] = sqrtf(a);
+    norms[batch + b] = sqrtf(c);
   }
+  cluster.sync();
 }
 
-__global__ void sqrt_inplace_kernel(float* v, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) v[i] = sqrtf(v[i]);
-}
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
@@ -255,7 +324,7 @@ rk_combine_kernel(const float* __restrict__ y, const float* __restrict__ k, long
   }
 }
 
-// out[0] += sum_i ( h * sum_s e[s] k[s][i] / (atol + max(|y_i|, |y2_i|) * rtol) )^2
+// ws[0] = sum_i ( h * sum_s e[s] k[s][i] / (atol + max(|y_i|, |y2_i|) * rtol) )^2   (deterministic, see grid_sum_store)
 __global__ void __launch_bounds__(256)
 rk_error_sumsq_kernel(const float* __restrict__ k, long long n, int ns, RkCoefs e, float h, const float* __restrict__ y,
                       const float* __restrict__ y2, float atol, float rtol, float* out) {
@@ -267,32 +336,22 @@ rk_error_sumsq_kernel(const float* __restrict__ k, long long n, int ns, RkCoefs 
     const float r = h * err / sc;
     acc = fmaf(r, r, acc);
   }
-  acc = warp_sum(acc);
-  __shared__ float red[8];
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __shared__ float red[64];
+  const float2 t = block_sum2(acc, 0.f, red);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += red[w];
-    atomicAdd(out, t);
-  }
+  grid_sum_store(t.x, out, red);
 }
 
 // ---- fused optimizer step over the flat parameter buffer --------------------------------------------------------
-// out[0] += sum x^2 (block partials combined with one atomic per block).
+// ws[0] = sum x^2 (deterministic, see grid_sum_store).
 __global__ void __launch_bounds__(256) sumsq_f32_kernel(const float* __restrict__ x, long long n, float* out) {
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     acc = fmaf(x[i], x[i], acc);
-  acc = warp_sum(acc);
-  __shared__ float red[8];
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __shared__ float red[64];
+  const float2 t = block_sum2(acc, 0.f, red);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int k = 0; k < 8; ++k) t += red[k];
-    atomicAdd(out, t);
-  }
+  grid_sum_store(t.x, out, red);
 }
 
 // clip_grad_norm_ + torch.optim.Adam (L2 weight decay, no amsgrad) + ExponentialMovingAverage.update in one pass:
@@ -408,8 +467,8 @@ int csd_rk_error_sumsq_f32(const float* k_stack, int64_t n, int stages, const fl
   CSD_REQUIRE(k_stack && y && y2 && out && e_host && n >= 1 && stages >= 1 && stages <= 8, "rk_error_sumsq: bad arguments");
   RkCoefs e;
   for (int i = 0; i < 8; ++i) e.c[i] = i < stages ? e_host[i] : 0.f;
-  CSD_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
-  rk_error_sumsq_kernel<<<ew_blocks(n), 256, 0, stream>>>(k_stack, n, stages, e, h, y, y2, atol, rtol, out);
+  rk_error_sumsq_kernel<<<std::min(ew_blocks(n), CSD_REDUCE_WS_FLOATS - 8), 256, 0, stream>>>(k_stack, n, stages, e, h, y,
+                                                                                              y2, atol, rtol, out);
   CSD_LAUNCH_CHECK("rk_error_sumsq_kernel");
   return CSD_OK;
 }
@@ -418,8 +477,7 @@ int csd_sumsq_f32(const float* x, int64_t n, float* out, csd_stream_t stream_) {
   using namespace csd;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CSD_REQUIRE(x && out && n >= 1, "sumsq: bad arguments");
-  CSD_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
-  sumsq_f32_kernel<<<ew_blocks(n), 256, 0, stream>>>(x, n, out);
+  sumsq_f32_kernel<<<std::min(ew_blocks(n), CSD_REDUCE_WS_FLOATS - 8), 256, 0, stream>>>(x, n, out);
   CSD_LAUNCH_CHECK("sumsq_f32_kernel");
   return CSD_OK;
 }
@@ -454,9 +512,8 @@ int csd_dsm_loss_f32(const float* score, const float* z, const float* a, const f
   using namespace csd;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CSD_REQUIRE(score && z && a && c && w && losses && batch >= 1 && per_sample >= 1, "dsm_loss: bad arguments");
-  int slabs = (int)std::max<long long>(1, std::min<long long>(ceil_div_ll(per_sample, 8192),
-                                                              ceil_div_ll((long long)num_sms() * 4, batch)));
-  dsm_loss_kernel<<<batch * slabs, 256, 0, stream>>>(score, z, a, c, w, losses, per_sample, slabs);
+  CSD_REQUIRE(batch <= 65535, "dsm_loss: batch %d too large", batch);
+  dsm_loss_kernel<<<dim3(kRedCluster, (unsigned)batch), kRedThreads, 0, stream>>>(score, z, a, c, w, losses, per_sample);
   CSD_LAUNCH_CHECK("dsm_loss_kernel");
   return CSD_OK;
 }
@@ -466,13 +523,11 @@ int csd_langevin_norms_f32(const float* grad, const float* noise, float* norms, 
   using namespace csd;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CSD_REQUIRE(grad && noise && norms && batch >= 1 && per_sample >= 1, "langevin_norms: bad arguments");
-  CSD_CUDA(cudaMemsetAsync(norms, 0, sizeof(float) * 2 * batch, stream));
-  int slabs = (int)std::max<long long>(1, std::min<long long>(ceil_div_ll(per_sample, 8192),
-                                                              ceil_div_ll((long long)num_sms() * 4, batch)));
-  sumsq_pair_kernel<<<batch * slabs, 256, 0, stream>>>(grad, noise, norms, batch, per_sample, slabs);
-  CSD_LAUNCH_CHECK("sumsq_pair_kernel");
-  sqrt_inplace_kernel<<<ceil_div(2 * batch, 128), 128, 0, stream>>>(norms, 2 * batch);
-  CSD_LAUNCH_CHECK("sqrt_inplace_kernel");
+  CSD_REQUIRE(batch <= 65535, "langevin_norms: batch %d too large", batch);
+  const int vec4 = vec4_ok(per_sample, {grad, noise}) ? 1 : 0;
+  norm_pair_kernel<<<dim3(kRedCluster, (unsigned)batch), kRedThreads, 0, stream>>>(grad, noise, norms, batch, per_sample,
+                                                                                  vec4);
+  CSD_LAUNCH_CHECK("norm_pair_kernel");
   return CSD_OK;
 }
 

@@ -192,7 +192,8 @@ __global__ void gn_apply_kernel(GnParamsT<VT> p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float y = fmaf(f[i], sc[i], sh[i]);
-        f[i] = p.silu ? silu_act<VT>(y) : y;
+        y = (p.silu & 1) ? silu_act<VT>(y) : y;
+        f[i] = (sizeof(VT) == 32 && (p.silu & 2)) ? round_tf32(y) : y;
       }
       p.out[((long long)b * p.hw + pix + (long long)u * ppb) * p.out_pv + v] = pack8_as<VT>(f);
     }
@@ -203,7 +204,8 @@ __global__ void gn_apply_kernel(GnParamsT<VT> p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float y = fmaf(f[i], sc[i], sh[i]);
-      f[i] = p.silu ? silu_act<VT>(y) : y;
+      y = (p.silu & 1) ? silu_act<VT>(y) : y;
+      f[i] = (sizeof(VT) == 32 && (p.silu & 2)) ? round_tf32(y) : y;
     }
     p.out[((long long)b * p.hw + pix) * p.out_pv + v] = pack8_as<VT>(f);
   }
@@ -450,8 +452,9 @@ gn_fused_kernel(GnParamsT<VT> p, int Vs) {
       unpack8(cache[u], f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float y = fmaf(f[i], sc[i], sh[i]);
-        f[i] = p.silu ? silu_act<VT>(y) : y;
+        float y = fmaf(f[i], sc[i], sh[i]);
+        y = (p.silu & 1) ? silu_act<VT>(y) : y;
+        f[i] = (sizeof(VT) == 32 && (p.silu & 2)) ? round_tf32(y) : y;
       }
       p.out[((long long)b * p.hw + pix) * p.out_pv + gv] = pack8_as<VT>(f);
     }
@@ -522,7 +525,7 @@ nchw_to_nhwc_kernel(const float* __restrict__ s0, int c0, const float* __restric
       float v = 0.f;
       if (c < c0) v = fmaf(__ldg(s0 + ((long long)b * c0 + c) * hw + pix), scale, shift);
       else if (c < c0 + c1) v = fmaf(__ldg(s1 + ((long long)b * c1 + (c - c0)) * hw + pix), scale, shift);
-      f[i] = v;
+      f[i] = sizeof(VT) == 32 ? round_tf32(v) : v;    // fp32 plan: the network input only feeds tensor-core operands
     }
     out[((long long)b * hw + pix) * cvec + cv] = pack8_as<VT>(f);
   }
@@ -546,6 +549,9 @@ nhwc_to_nchw_kernel(const T* __restrict__ src, int pitch, int c_off, int c_cnt, 
 
 // ---- softmax ---------------------------------------------------------------------------------------
 // One warp per row; rows are short (<= 1024 keys), so the three passes hit L1.
+template <typename T> __device__ __forceinline__ float store_round(float v) { return v; }
+template <> __device__ __forceinline__ float store_round<float>(float v) { return round_tf32(v); }   // P feeds the PV GEMM
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ logits, int in_pitch, T* __restrict__ probs, int out_pitch,
@@ -563,7 +569,7 @@ softmax_rows_kernel(const float* __restrict__ logits, int in_pitch, T* __restric
   const float inv = 1.f / s;
   T* out = probs + row * out_pitch;
   for (int c = lane; c < out_pitch; c += 32)
-    out[c] = from_f32<T>(c < cols ? __expf(in[c] * scale - m) * inv : 0.f);
+    out[c] = from_f32<T>(c < cols ? store_round<T>(__expf(in[c] * scale - m) * inv) : 0.f);
 }
 
 // ---- time embedding ----------------------------------------------------------------------------------

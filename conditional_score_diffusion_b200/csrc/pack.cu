@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const csd_pack_job* _
     const int ts = j.flip ? j.taps - 1 - tap : tap;
     const float v = j.src[(long long)r * j.s_row + (long long)c * j.s_col + (long long)ts * j.s_tap] * j.scale;
     const long long o = (long long)r * j.dst_pitch + (long long)tap * j.k_pad + c;
-    if (j.kind == 2) df[o] = v;
+    if (j.kind == 2) df[o] = round_tf32(v);
     else d[o] = __float2bfloat16_rn(v);
   }
 }

@@ -222,6 +222,7 @@ struct FirNhwcParamsT {
   const VT* add;
   int batch, h, w, oh, ow, cvec;  // cvec = channel pitch / 8
   float kf[4];                    // flipped, normalised 1-D taps (already x2 for mode 1)
+  int round_out;                  // fp32 tensors: round the output to tf32 (it only feeds tensor-core operands)
 };
 using FirNhwcParams = FirNhwcParamsT<bf16x8>;
 
@@ -288,6 +289,10 @@ __global__ void __launch_bounds__(256) fir_nhwc_kernel(FirNhwcParamsT<VT> p) {
       unpack8(p.add[idx], f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+    if (sizeof(VT) == 32 && p.round_out) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = round_tf32(acc[i]);
     }
     p.out[idx] = pack8_as<VT>(acc);
   }
@@ -380,6 +385,10 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map, const FirNhwcParamsT<VT>
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += f[e];
     }
+    if (sizeof(VT) == 32 && p.round_out) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = round_tf32(acc[e]);
+    }
     p.out[o] = pack8_as<VT>(acc);
   }
 }
@@ -459,6 +468,8 @@ template <typename VT>
 static int fir_resample_launch(const void* src, void* out, const void* add, int batch, int h, int w, int c_pitch, int mode,
                                const float* taps4_host, cudaStream_t stream) {
   CSD_REQUIRE(src && out && taps4_host, "fir_resample: null pointer");
+  const int round_out = (mode & 0x10) ? 1 : 0;
+  mode &= 0xf;
   CSD_REQUIRE(mode >= 1 && mode <= 3, "fir_resample: mode %d (1 = up, 2 = down, 3 = pre-filter)", mode);
   CSD_REQUIRE(c_pitch % 8 == 0, "fir_resample: channel pitch %d not a multiple of 8", c_pitch);
   CSD_REQUIRE(mode != 2 || (h % 2 == 0 && w % 2 == 0), "fir_resample: odd size %dx%d for downsampling", h, w);
@@ -467,6 +478,7 @@ static int fir_resample_launch(const void* src, void* out, const void* add, int 
   p.out = static_cast<VT*>(out);
   p.add = static_cast<const VT*>(add);
   p.batch = batch; p.h = h; p.w = w; p.cvec = c_pitch / 8;
+  p.round_out = round_out;
   p.oh = mode == 1 ? h * 2 : (mode == 2 ? h / 2 : h + 1);
   p.ow = mode == 1 ? w * 2 : (mode == 2 ? w / 2 : w + 1);
   float sum = 0.f;

@@ -342,7 +342,9 @@ class BlockOps:
         return a.sums
 
     def group_norm(self, srcs, gamma, beta, silu, groups=None):
-        """srcs: list of 1 or 2 Act (channel concatenation). Returns a new Act."""
+        """srcs: list of 1 or 2 Act (channel concatenation). Returns a new Act. Every GroupNorm output of these
+        networks feeds a convolution / GEMM operand (directly or through a FIR pass), so the fp32 plan rounds it to
+        tf32 on store (kernels.gn_apply round_out)."""
         b, h, w, _ = srcs[0].shape
         c = sum(a.c for a in srcs)
         groups = groups or _groups(c)
@@ -353,13 +355,13 @@ class BlockOps:
             # small levels: statistics + apply in ONE launch (nobody delivers these tensors' sums for free)
             out = self.pool.get((b, h, w, c))
             self.rec.add(K.gn_fused, s0.t, s0.c, s1.t if s1 else None, s1.c if s1 else 0, gamma, beta, out, groups,
-                         1e-6, silu)
+                         1e-6, silu, True)
             return Act(out, c)
         sums0 = self.ensure_sums(s0)
         sums1 = self.ensure_sums(s1) if s1 is not None else None
         out = self.pool.get((b, h, w, c))
         self.rec.add(K.gn_apply, s0.t, s0.c, sums0, s1.t if s1 else None, s1.c if s1 else 0, sums1, gamma, beta, out,
-                     groups, 1e-6, silu)
+                     groups, 1e-6, silu, True)
         return Act(out, c)
 
     def gn_coeffs(self, srcs, gamma, beta, groups=None):
@@ -486,11 +488,13 @@ class BlockOps:
         """Dropout_0 of the ResNet blocks: identity outside training (nn.Dropout in eval mode)."""
         return a
 
-    def fir(self, a, mode, taps, add=None):
+    def fir(self, a, mode, taps, add=None, operand=True):
+        """operand: the result only feeds convolution operands (fp32 plan: rounded to tf32 on store); False for the
+        output pyramid, which is added to a head's output."""
         b, h, w, p = a.shape
         oh, ow = {"up": (h * 2, w * 2), "down": (h // 2, w // 2), "prefilter": (h + 1, w + 1)}[mode]
         out = self.pool.get((b, oh, ow, p))
-        self.rec.add(K.fir_resample, a.t, out, mode, list(taps), add.t if add is not None else None)
+        self.rec.add(K.fir_resample, a.t, out, mode, list(taps), add.t if add is not None else None, operand)
         return Act(out, a.c)
 
     def release(self, *acts):
@@ -566,14 +570,14 @@ class BlockOps:
         # q | k in one GEMM: [B, L, 2C]
         qk = self.pool.get((b, 1, L, 2 * c))
         self.rec.add(K.conv_gemm, [(hn_flat.t, hn.pitch, 0, c, 1)], pk["qk"].wt, 2 * c, qk, batch=b, h=1, w=L,
-                     n_store=2 * c, n_tile=pk["qk"].n_tile, bias=pk["qk"].bias)
+                     n_store=2 * c, n_tile=pk["qk"].n_tile, bias=pk["qk"].bias, round_out=True)
         # V^T[b] = Wv^T h[b]^T : A = weight image [C rows, C], B = hn[b] (batched over z)
         vt = self.pool.get((b, c, lp))
         nt_l = K.ceil_to(L, 16) if L <= 256 else K.ceil_to(math.ceil(L / math.ceil(L / 256)), 16)
         self.rec.add(K.conv_gemm, [(pk["wv_img"], c, 0, c, 1)], hn.t, L, vt, batch=1, h=1, w=c, out_pitch=lp,
                      n_store=L, n_tile=nt_l, z_batches=b, a_batch_step=0, wt_batch_stride=L * hn.pitch,
                      wt_pitch=hn.pitch, k_valid=c, wt_rows=L, out_z_stride=c * lp, bias=pk["bv"],
-                     bias_per_row=True)
+                     bias_per_row=True, round_out=True)
         # logits S[b] = Q[b] K[b]^T (fp32)
         s = self.pool.get((b, L, lp), torch.float32)
         self.rec.add(K.conv_gemm, [(qk, 2 * c, 0, c, 1)], qk, L, s, batch=1, h=1, w=L, out_pitch=lp, n_store=L,
@@ -586,7 +590,7 @@ class BlockOps:
         pc_o_ntile = pk["proj"].n_tile
         self.rec.add(K.conv_gemm, [(p, lp, 0, L, 1)], vt, c, o, batch=1, h=1, w=L, out_pitch=c, n_store=c,
                      n_tile=pc_o_ntile, z_batches=b, a_batch_step=1, wt_batch_stride=c * lp, wt_pitch=lp,
-                     k_valid=L, wt_rows=c, out_z_stride=L * c)
+                     k_valid=L, wt_rows=c, out_z_stride=L * c, round_out=True)
         out = self.pool.get((b, h, w, K.ceil_to(c, 8)))
         self.rec.add(K.conv_gemm, [(o, c, 0, c, 1)], pk["proj"].wt, c, out.view(b, 1, L, out.shape[-1]), batch=b,
                      h=1, w=L, n_store=pk["proj"].n_store, n_tile=pk["proj"].n_tile, bias=pk["proj"].bias,
@@ -1222,11 +1226,11 @@ class NetPlan:
                 elif ops.head_in_transposed_kernel(pk[m_idx], hcur) and HEAD_MODE == 2:
                     # conv first, then the pyramid's FIR upsampling adds it (fir_nhwc `add`): no residual operand
                     ho = ops.head(gn, pk[m_idx], hcur, extra, m_idx)
-                    pu = ops.fir(pyramid, "up", fir_taps, add=ho)
+                    pu = ops.fir(pyramid, "up", fir_taps, add=ho, operand=False)
                     ops.release(pyramid, ho)
                     pyramid = pu
                 else:
-                    pu = ops.fir(pyramid, "up", fir_taps)
+                    pu = ops.fir(pyramid, "up", fir_taps, operand=False)
                     ops.release(pyramid)
                     pyramid = ops.head(gn, pk[m_idx], hcur, extra, m_idx, res=pu)
                     ops.release(pu)

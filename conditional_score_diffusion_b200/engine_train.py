@@ -75,8 +75,8 @@ class TrainOps(BlockOps):
                                      groups=groups or min(c // 4, 32), out=o)))
         return o
 
-    def fir(self, a, mode, taps, add=None):
-        o = super().fir(a, mode, taps, add)
+    def fir(self, a, mode, taps, add=None, operand=True):
+        o = super().fir(a, mode, taps, add, operand)
         self.tape.append(("fir", dict(src=a, mode=mode, taps=tuple(taps), add=add, out=o)))
         return o
 

@@ -107,7 +107,8 @@ def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None
               tile=None, bias=None, bias_per_row=False, temb=None, temb_pitch=0, res=None,
               res_pitch=0, scale=1.0, out_f32=None, z_batches=1, a_batch_step=0, wt_batch_stride=0,
               out_z_stride=0, res_z_stride=0, wt_pitch=0, wt_k_off=0, k_valid=0, wt_rows=None,
-              stride=1, pad=1, in_h=0, in_w=0, halo=None, mt=None, transposed=None, stat_partials=None):
+              stride=1, pad=1, in_h=0, in_w=0, halo=None, mt=None, transposed=None, stat_partials=None,
+              round_out=False):
     """Launch csd_conv_gemm. segments: list of (tensor, pitch, c_off, c_cnt, taps[, norm, norm_silu]): `norm` is the
     [batch, c_cnt, 2] (scale, shift) table of gn_coeffs for the fused GroupNorm(+SiLU) prologue (transposed mode)."""
     _require_cuda(wt, out, bias, temb, res, *[s[0] for s in segments])
@@ -146,6 +147,7 @@ def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None
         assert wt.dtype == torch.float32 and out.dtype == torch.float32 and (res is None or res.dtype == torch.float32)
         halo = transposed = False
         d.dtype = 1
+        d.out_round_tf32 = int(bool(round_out))
     if halo is None:
         halo = (HALO_DEFAULT and tile is None and segments[0][4] == 9 and stride == 1 and pad == 1 and z_batches == 1
                 and w % 8 == 0 and h >= 16 and n_tile <= 512)
@@ -349,13 +351,18 @@ def gn_coeffs(sums0, c0, sums1, c1, gamma, beta, coef0, coef1, hw, groups, eps=1
     return coef0, coef1
 
 
-def gn_apply(src0, c0, sums0, src1, c1, sums1, gamma, beta, out, groups, eps=1e-6, silu=True):
+def _gn_flags(silu, round_out, dtype):
+    """apply_silu argument: bit 0 = SiLU, bit 1 (fp32 tensors) = round the result to tf32 (it feeds an MMA operand)."""
+    return int(bool(silu)) | (2 if (round_out and dtype == torch.float32) else 0)
+
+
+def gn_apply(src0, c0, sums0, src1, c1, sums1, gamma, beta, out, groups, eps=1e-6, silu=True, round_out=False):
     b = src0.shape[0]
     hw = src0.numel() // (b * src0.shape[-1])
     fn = _lib.lib().csd_gn_apply_f32 if src0.dtype == torch.float32 else _lib.lib().csd_gn_apply_bf16
     check(fn(_ptr(src0), c0, src0.shape[-1], _ptr(sums0), _ptr(src1), c1,
              src1.shape[-1] if src1 is not None else 0, _ptr(sums1), _ptr(gamma), _ptr(beta),
-             _ptr(out), out.shape[-1], b, hw, groups, float(eps), int(silu), _stream()))
+             _ptr(out), out.shape[-1], b, hw, groups, float(eps), _gn_flags(silu, round_out, src0.dtype), _stream()))
     return out
 
 
@@ -375,22 +382,23 @@ def gn_fused_supported(c0, c1, hw, groups, batch, dtype=_BF16):
     return bool(fn(int(c0), int(c1), int(hw), int(groups), int(batch)))
 
 
-def gn_fused(src0, c0, src1, c1, gamma, beta, out, groups, eps=1e-6, silu=True):
+def gn_fused(src0, c0, src1, c1, gamma, beta, out, groups, eps=1e-6, silu=True, round_out=False):
     b = src0.shape[0]
     hw = src0.numel() // (b * src0.shape[-1])
     fn = _lib.lib().csd_gn_fused_f32 if src0.dtype == torch.float32 else _lib.lib().csd_gn_fused_bf16
     check(fn(_ptr(src0), c0, src0.shape[-1], _ptr(src1), c1,
              src1.shape[-1] if src1 is not None else 0, _ptr(gamma), _ptr(beta), _ptr(out),
-             out.shape[-1], b, hw, groups, float(eps), int(silu), _stream()))
+             out.shape[-1], b, hw, groups, float(eps), _gn_flags(silu, round_out, src0.dtype), _stream()))
     return out
 
 
-def fir_resample(src, out, mode, taps, add=None):
+def fir_resample(src, out, mode, taps, add=None, round_out=False):
     """mode 'up' | 'down' | 'prefilter'; src/out NHWC bf16."""
     b, h, w, pitch = src.shape
     arr = (ctypes.c_float * 4)(*[float(t) for t in taps])
     fn = _lib.lib().csd_fir_resample_nhwc_f32 if src.dtype == torch.float32 else _lib.lib().csd_fir_resample_nhwc_bf16
-    check(fn(_ptr(src), _ptr(out), _ptr(add), b, h, w, pitch, {"up": 1, "down": 2, "prefilter": 3}[mode], arr, _stream()))
+    m = {"up": 1, "down": 2, "prefilter": 3}[mode] | (0x10 if (round_out and src.dtype == torch.float32) else 0)
+    check(fn(_ptr(src), _ptr(out), _ptr(add), b, h, w, pitch, m, arr, _stream()))
     return out
 
 
@@ -421,8 +429,17 @@ def rk_combine(y, k_stack, stages, coefs, h, out):
     return out
 
 
+REDUCE_WS = 1024   # CSD_REDUCE_WS_FLOATS: workspace of the deterministic device-wide sums (result in [0])
+
+
+def reduce_workspace(device):
+    """Zeroed workspace for rk_error_sumsq / sumsq (allocate once, reuse: the kernels keep its ticket counter at zero)."""
+    return torch.zeros(REDUCE_WS, device=device, dtype=torch.float32)
+
+
 def rk_error_sumsq(k_stack, stages, e, h, y, y2, atol, rtol, out):
     _require_cuda(y, y2, k_stack, out)
+    assert out.numel() >= REDUCE_WS, "rk_error_sumsq: `out` is a kernels.reduce_workspace()"
     arr = (ctypes.c_float * stages)(*[float(c) for c in e[:stages]])
     check(_lib.lib().csd_rk_error_sumsq_f32(_ptr(k_stack), y.numel(), stages, arr, float(h), _ptr(y), _ptr(y2), float(atol),
                                             float(rtol), _ptr(out), _stream()))
@@ -430,6 +447,7 @@ def rk_error_sumsq(k_stack, stages, e, h, y, y2, atol, rtol, out):
 
 
 def sumsq(x, out):
+    assert out.numel() >= REDUCE_WS, "sumsq: `out` is a kernels.reduce_workspace()"
     check(_lib.lib().csd_sumsq_f32(_ptr(x), x.numel(), _ptr(out), _stream()))
     return out
 

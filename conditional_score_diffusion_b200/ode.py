@@ -45,12 +45,12 @@ def solve_rk45(fun, t0, t_bound, y0, rtol=1e-5, atol=1e-5, max_steps=100000):
     y_new = torch.empty_like(y)
     y_stage = torch.empty_like(y)
     ks = torch.empty(7, n, device=dev, dtype=torch.float32)
-    norm_buf = torch.zeros(1, device=dev, dtype=torch.float32)
+    norm_buf = K.reduce_workspace(dev)                   # [0] = the error norm's sum of squares (deterministic)
     nfev = 0
 
     def rms(stages, e, h, ya, yb):
         K.rk_error_sumsq(ks, stages, e, h, ya, yb, atol, rtol, norm_buf)
-        return math.sqrt(norm_buf.item() / n)
+        return math.sqrt(norm_buf[0].item() / n)
 
     ks[0].copy_(fun(t0, y))
     nfev += 1
@@ -64,7 +64,7 @@ def solve_rk45(fun, t0, t_bound, y0, rtol=1e-5, atol=1e-5, max_steps=100000):
     nfev += 1
     d2 = rms(2, [-1.0, 1.0], 1.0, y, y) / h0
     h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / (_ORDER + 1))
-    h_abs = min(100 * h0, h1)
+    h_abs = min(100 * h0, h1, abs(t_bound - t0))        # scipy >= 1.10 clamps the first step to the interval length
 
     t = float(t0)
     steps = 0

@@ -40,7 +40,7 @@ class FusedAdamEMA:
         self.v = torch.zeros_like(self.flat)
         self.ema = self.flat.clone() if ema_decay is not None else None
         self.gflat = torch.zeros_like(self.flat)
-        self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.gnorm_sq = K.reduce_workspace(dev)     # [0] = squared gradient norm (deterministic device-wide sum)
         self.step_count = 0
         self.num_updates = 0
         self._stored = None
@@ -85,11 +85,12 @@ class FusedAdamEMA:
         """One optimizer + EMA step. Equivalent reference sequence: optimize_fn(optimizer, params, step) (losses.py:38-52)
         then ema.update(params) (losses.py:393)."""
         g = self._flat_grads()
-        self.step_count += 1
+        # warm-up as in losses.py:46-48: lr * min(step / warmup, 1) with `step` counted from 0 (the first update runs
+        # at lr = 0). param_groups[0]['lr'] is the BASE rate an external scheduler may change; it is scaled, not replaced
         lr = self.param_groups[0]["lr"]
         if self.warmup > 0:
-            lr = self.lr * min(self.step_count / self.warmup, 1.0)
-            self.param_groups[0]["lr"] = lr
+            lr = lr * min(self.step_count / self.warmup, 1.0)
+        self.step_count += 1
         b1, b2 = self.betas
         if self.grad_clip >= 0:
             K.sumsq(g, self.gnorm_sq)

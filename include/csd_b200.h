@@ -78,7 +78,9 @@ int csd_fused_bias_act_f32(const float* x, const float* bias, const float* refer
 int csd_ve_perturb_f32(const float* y, const float* z, float* y_pert, int batch, int64_t per_sample,
                        const float* sigma_tab, const int* step_idx, int sample_stride, csd_stream_t stream);
 
-/* norms[0..batch) = ||grad_b||_2, norms[batch..2*batch) = ||noise_b||_2 (correctors.py:72-73). */
+/* norms[0..batch) = ||grad_b||_2, norms[batch..2*batch) = ||noise_b||_2 (correctors.py:72-73). One launch; a
+ * thread-block cluster per sample sums in a fixed order (bitwise reproducible: these norms set the Langevin step size
+ * of the whole batch).                                                                            */
 int csd_langevin_norms_f32(const float* grad, const float* noise, float* norms, int batch,
                            int64_t per_sample, csd_stream_t stream);
 
@@ -202,7 +204,10 @@ int csd_fir_resample_nhwc_bf16(const void* src, void* out, const void* add, int 
                                int c_pitch, int mode, const float* taps4_host, csd_stream_t stream);
 
 /* ---- fp32-activation variants ("tf32" plan: NHWC fp32 tensors, channel pitch a multiple of 8) ----
- * Same arguments and semantics as their *_bf16 namesakes above; src / out / add / probs are float. Together with
+ * Same arguments and semantics as their *_bf16 namesakes above; src / out / add / probs are float. tcgen05 kind::tf32
+ * truncates the fp32 words it reads, so producers of tensors that ONLY feed tensor-core operands round them to tf32
+ * (nearest) on request: apply_silu bit 1 (csd_gn_apply_f32 / csd_gn_fused_f32), mode | 0x10 (csd_fir_resample_nhwc_f32),
+ * always in csd_nchw_to_nhwc_f32 (the network input) and csd_softmax_rows_f32_f32 (attention probabilities). Together with
  * csd_conv_gemm's dtype = 1 they form the reference-precision plan (fp32 storage like the reference,
  * sampling/unconditional.py:206, models/ncsnpp.py:264-266; TF32 tensor-core operands like its cuDNN convolutions). */
 int csd_nchw_to_nhwc_f32(const float* src0, int c0, const float* src1, int c1, void* out, int c_pad, int batch, int h,
@@ -304,7 +309,9 @@ typedef struct csd_conv_gemm_desc {
                                    1 = fp32 activations / weights / residual / output, tcgen05 kind::tf32 - the
                                    reference's own precision class (fp32 storage, sampling/unconditional.py:206; cuDNN
                                    TF32 convolutions): A, wt, res, out are float, pitches stay in elements      */
-  int32_t reserved_;
+  int32_t out_round_tf32;       /* dtype 1: round the stored output to tf32 (nearest): set for tensors that only feed
+                                   further tensor-core operands (attention q|k, V^T, P V), whose fp32 words the
+                                   kind::tf32 MMA would otherwise truncate                                      */
 } csd_conv_gemm_desc;
 
 int csd_conv_gemm(const csd_conv_gemm_desc* desc, csd_stream_t stream);
@@ -317,6 +324,10 @@ int csd_conv_gemm(const csd_conv_gemm_desc* desc, csd_stream_t stream);
 /* out = y + h * sum_s coef[s] * k_stack[s]                                                                     */
 int csd_rk_combine_f32(const float* y, const float* k_stack, int64_t n, int stages, const float* coef_host, float h,
                        float* out, csd_stream_t stream);
+/* Device-wide sums below are deterministic (fixed summation order, no float atomics): `out` is a workspace of
+ * CSD_REDUCE_WS_FLOATS floats that the caller zeroes ONCE when it allocates it; out[0] receives the result, out[1] is
+ * a ticket counter the kernel leaves at zero, out[8..] hold per-CTA partials.                                    */
+#define CSD_REDUCE_WS_FLOATS 1024
 /* out[0] = sum_i (h * sum_s e[s] k_stack[s][i] / (atol + max(|y_i|, |y2_i|) * rtol))^2 (device scalar)          */
 int csd_rk_error_sumsq_f32(const float* k_stack, int64_t n, int stages, const float* e_host, float h, const float* y,
                            const float* y2, float atol, float rtol, float* out, csd_stream_t stream);
@@ -325,7 +336,7 @@ int csd_rk_error_sumsq_f32(const float* k_stack, int64_t n, int stages, const fl
  * The reference runs torch.nn.utils.clip_grad_norm_ + optim.Adam.step (losses.py:38-52) and then
  * ExponentialMovingAverage.update (models/ema.py:64-93: a Python loop of 3 kernels per parameter tensor) after every
  * training step. Over a flat fp32 parameter buffer this is one reduction and one elementwise pass.              */
-/* out[0] = sum x^2 (device scalar).                                                                            */
+/* out[0] = sum x^2 (device scalar; `out` = CSD_REDUCE_WS_FLOATS workspace, see csd_rk_error_sumsq_f32).        */
 int csd_sumsq_f32(const float* x, int64_t n, float* out, csd_stream_t stream);
 /* g' = g * min(1, max_norm / (sqrt(*gnorm_sq) + 1e-6)) (max_norm < 0: no clipping) + weight_decay * p;
  * m = beta1 m + (1-beta1) g'; v = beta2 v + (1-beta2) g'^2; p -= lr / bias_corr1 * m / (sqrt(v / bias_corr2) + eps);

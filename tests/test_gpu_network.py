@@ -48,8 +48,8 @@ def test_paired_forward_matches_reference_golden():
         out3 = m({"x": f["x"].cuda(), "y": f["y"].cuda()}, f["labels"].cuda())
     assert out2["x"].data_ptr() != out3["x"].data_ptr()
     _check(out3["x"], f["out_x"], "paired x (graph replay)")
-    # run-to-run: GroupNorm sums use fp32 atomics, so a few outputs may flip by one bf16 ulp (2^-8 rel)
-    assert (out2["x"] - out3["x"]).abs().max().item() < 2.0 ** -6 * f["out_x"].abs().max().item()
+    # run-to-run: no float atomics on the path (fixed-order statistics) -> bitwise identical
+    assert torch.equal(out2["x"], out3["x"])
 
 
 def test_cifar_forward_matches_reference_golden():

@@ -154,17 +154,16 @@ def test_config5_ncsnpp_256(precision):
 
 
 def test_config2_trajectory_50_steps():
-    """50 PC steps (100 network evaluations) at the config-2 network shape on a 2-image batch with replayed noise,
-    bf16 plan and tf32 plan against the fp32 oracle: the error growth over the trajectory is what the precision
-    contract costs. The oracle at 160 px would take ~4 min on the host, so the trajectory runs the same architecture
-    at 80 px (levels 80..., attention at 20/10/5): ~1 min of CPU."""
+    """50 PC steps (100 network evaluations) of the config-2 network (160 px, nf 96, 6 levels) on a 2-image batch with
+    replayed noise, bf16 plan and tf32 plan against the fp32 oracle: the error growth over the trajectory is what the
+    precision contract costs (~1 min of host time for the oracle)."""
     from conditional_score_diffusion_b200 import sampling, sde_lib, workloads
     from oracle import sampling as o_samp
     from oracle import sde as o_sde
-    cfg = workloads.config2_ncsnpp_paired_160(image=80)
+    cfg = workloads.config2_ncsnpp_paired_160()
     m, sd = _build(cfg, 160)
     steps, B = 50, 2
-    shape = (B, 3, 80, 80)
+    shape = (B, 3, 160, 160)
     g = torch.Generator().manual_seed(161)
     y = torch.rand(*shape, generator=g)
     names = ("y_c", "x_c", "y_p", "x_p")

@@ -84,9 +84,10 @@ def test_pc_conditional_fused_vs_oracle_injected_noise():
         print(f"[pc-cond] step {i}: rel={r:.3e} |x|max={rec[i].abs().max().item():.3e}")
         assert r < STATE_TOL
     assert _rel(got, ref) < STATE_TOL
-    # graph path twice: deterministic given the same injected noise (up to GroupNorm atomics order)
+    # graph path twice: bitwise reproducible given the same injected noise (no float atomics anywhere on the path:
+    # fixed-order GroupNorm statistics and cluster-reduced Langevin norms; the reference is reproducible under a seed)
     got2, _ = sampler(m, p["y"].cuda(), x_init=x0, noise_source=tape.named)
-    assert _rel(got2, got) < 5e-3
+    assert torch.equal(got2, got)
 
 
 def test_pc_unconditional_fused_vs_oracle_injected_noise():
@@ -133,7 +134,7 @@ def test_generator_noise_path_runs_and_is_seed_reproducible():
         out, _ = sampler(m, p["y"].cuda())
         assert torch.isfinite(out).all()
         outs.append(out)
-    assert _rel(outs[0], outs[1]) < 5e-3
+    assert torch.equal(outs[0], outs[1]), "same seed, same samples - bitwise"
     torch.manual_seed(124)
     out3, _ = sampler(m, p["y"].cuda())
     assert _rel(out3, outs[0]) > 1e-2  # a different seed gives a different sample

@@ -227,10 +227,18 @@ def test_f32_fir_resample_vs_oracle(shape):
     g = torch.Generator().manual_seed(h)
     x = torch.randn(*shape, generator=g)
     a = _nhwc(x.cuda())
-    for mode, ref in (("up", o_ops.upsample_2d(x, (1, 3, 3, 1))), ("down", o_ops.downsample_2d(x, (1, 3, 3, 1)))):
+    modes = [("up", o_ops.upsample_2d(x, (1, 3, 3, 1)))]
+    if h % 2 == 0:
+        modes.append(("down", o_ops.downsample_2d(x, (1, 3, 3, 1))))
+    for mode, ref in modes:
         out = torch.empty(b, ref.shape[2], ref.shape[3], a.shape[-1], device="cuda")
         k.fir_resample(a, out, mode, [1, 3, 3, 1])
         assert _rel(out[..., :c].permute(0, 3, 1, 2).cpu(), ref) < F32_RTOL, mode
+        # operand form: the same values rounded to tf32 (10 mantissa bits): relative error <= 2^-11 per element
+        out_r = torch.empty_like(out)
+        k.fir_resample(a, out_r, mode, [1, 3, 3, 1], round_out=True)
+        assert ((out_r - out).abs() <= out.abs() * 2.0 ** -11 + 1e-30).all()
+        assert (out_r.view(torch.int32) & 0x1FFF).eq(0).all(), "tf32-rounded words have 13 zero low bits"
     add = torch.randn(b, 2 * h, 2 * w, a.shape[-1], device="cuda")
     out = torch.empty_like(add)
     k.fir_resample(a, out, "up", [1, 3, 3, 1], add=add)
