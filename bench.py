@@ -441,6 +441,117 @@ def tf32_line(cfg, model, sde, shape, dev, steps, B, world):
             "parity": par, "plan_buffers_gb": gb}
 
 
+def _pc_steps_ms(model, sde, shape, conditional, snr, n_scales, steps, dev, eps=EPS):
+    """ms per PC step of a fused sampler (device-timed graph replays, inputs resident)."""
+    import torch
+    from conditional_score_diffusion_b200.sampling.fused import FusedPCSampler
+    fs = FusedPCSampler(model, sde, shape, "reverse_diffusion", "langevin", snr, n_scales, 1, False, True, True, eps,
+                        conditional=conditional)
+    fs._setup(dev)
+    if conditional:
+        fs.y.copy_(torch.rand(*shape, device=dev))
+    graph = fs._graph(draw_noise=True)
+    c_sde = sde["x"] if isinstance(sde, dict) else sde
+    fs.x.copy_(torch.randn(*shape, device=dev) * c_sde.sigma_max)
+    fs.step_idx.zero_()
+    for _ in range(3):
+        graph.replay()
+    fs.step_idx.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    finite = bool(torch.isfinite(fs.x).all().item())
+    gb = fs.plan.pool.nbytes() / 1e9
+    return e0.elapsed_time(e1) / steps, finite, gb
+
+
+def other_configs(dev, steps=5):
+    """Short device-timed records of the other BASELINE.json configs (rank 0, after the headline): configs[2]
+    (ddpm_paired 128 px inpainting net, conditional PC), configs[4] (NCSN++ 256 px nf 128, unconditional PC-2000) and
+    configs[3] (ddpm_paired_SR3 training step at 64 px as shipped and at 128 px). Context for the reader and the driver,
+    not part of `value`."""
+    import torch
+    from conditional_score_diffusion_b200 import losses, optim, sde_lib, workloads
+    from conditional_score_diffusion_b200.models import ddpm, ncsnpp, utils  # noqa: F401
+    out = {}
+
+    def guard(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as e:  # noqa: BLE001 - context records must not take the headline down
+            out[name] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+
+    def cfg3():
+        cfg = workloads.config3_ddpm_paired_128()
+        torch.manual_seed(3)
+        m = utils.create_model(cfg).to(dev).eval()
+        sde = {"x": sde_lib.cVESDE(cfg.model.sigma_min_x, cfg.model.sigma_max_x, 1000),
+               "y": sde_lib.VESDE(cfg.model.sigma_min_y, cfg.model.sigma_max_y, 1000)}
+        B = 64
+        ms, finite, gb = _pc_steps_ms(m, sde, (B, 3, 128, 128), True, 0.15, 1000, steps, dev)
+        return {"workload": "configs[2]: inpainting/celebA_ours_DV.py as shipped (ddpm_paired nf96, 128x128), conditional "
+                            "PC-1000, batch 64 per GPU (512 over 8 GPUs)", "ms_per_pc_step": ms,
+                "images_per_s_per_gpu": B / (ms * 1e-3 * 1000), "finite_output": finite, "plan_buffers_gb": gb}
+
+    def cfg5():
+        cfg = workloads.config5_ncsnpp_256()
+        torch.manual_seed(5)
+        m = utils.create_model(cfg).to(dev).eval()
+        sde = sde_lib.VESDE(cfg.model.sigma_min, cfg.model.sigma_max, cfg.model.num_scales)
+        B = 16
+        ms, finite, gb = _pc_steps_ms(m, sde, (B, 3, 256, 256), False, cfg.sampling.snr, cfg.model.num_scales, steps, dev)
+        return {"workload": "configs[4]: church_ncsnpp_continuous (NCSN++ nf128, 7 levels, attention at 16x16, 256x256), "
+                            "unconditional PC-2000, batch 16 per GPU (128 over 8 GPUs)", "ms_per_pc_step": ms,
+                "images_per_s_per_gpu": B / (ms * 1e-3 * cfg.model.num_scales), "finite_output": finite,
+                "plan_buffers_gb": gb}
+
+    def train(image, B):
+        def run():
+            cfg = workloads.config4_ddpm_sr3_64(image)
+            torch.manual_seed(4)
+            m = utils.create_model(cfg).to(dev).train()
+            sde = sde_lib.cVESDE(cfg.model.sigma_min_x, cfg.model.sigma_max_x, 1000)
+            loss_fn = losses.get_general_sde_loss_fn(sde, train=True, conditional=True, reduce_mean=True, continuous=True,
+                                                     likelihood_weighting=True)
+            opt = optim.FusedAdamEMA(m.parameters(), lr=cfg.optim.lr, betas=(cfg.optim.beta1, 0.999), eps=cfg.optim.eps,
+                                     weight_decay=cfg.optim.weight_decay, grad_clip=cfg.optim.grad_clip, ema_decay=0.999,
+                                     warmup=cfg.optim.warmup, model=m)
+            x, y = torch.rand(B, 3, image, image, device=dev), torch.rand(B, 3, image, image, device=dev)
+
+            def step():
+                opt.zero_grad()
+                loss = loss_fn(m, (y, x))
+                loss.backward()
+                opt.step()
+                return loss
+
+            for _ in range(3):
+                step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            return {"workload": f"configs[3]: edges2shoes_SR3 training step (ddpm_paired_SR3 nf128, {image}x{image}, dropout "
+                                f"0.1, SR3 loss, clip 1.0, fused Adam + EMA), batch {B} per GPU", "ms_per_step": ms,
+                    "images_per_s_per_gpu": B / (ms * 1e-3), "finite_loss": bool(math.isfinite(loss.item()))}
+        return run
+
+    guard("config3_ddpm_paired_128_pc", cfg3)
+    guard("config5_ncsnpp_256_pc", cfg5)
+    guard("config4_train_64", train(64, 50))
+    guard("config4_train_128", train(128, 25))
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -589,6 +700,7 @@ def run_b200(args):
                                   "algorithmic_gflop_per_forward": (tp_fl + tap_fl + heads_fl) / 1e9,
                                   "achieved_tflops": (tp_fl + tap_fl + heads_fl) / ((tp_ms + tap_ms + heads_ms) * 1e-3) / 1e12}}
 
+    plan_gb = fs.plan.pool.nbytes() / 1e9
     # ---- parity of the benchmarked network (same weights, B = 2) against the CPU oracle ----
     parity = network_parity(cfg, model, dev)
 
@@ -608,6 +720,13 @@ def run_b200(args):
             stock = stock_gpu_steps(cfg, B, 5, 2, dev)
         except Exception as e:  # noqa: BLE001 - the leg is context; the b200 line must still print
             stock = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+    # ---- the other BASELINE configs, briefly ----
+    extras = None
+    if not args.no_extras:
+        del fs, graph
+        torch.cuda.empty_cache()
+        extras = other_configs(dev)
 
     # ---- CPU baseline: the unmodified reference on the host cores, bounded sample ----
     cpu, cpu_kind = reference_cpu_steps(cfg, 2, 3, 1)
@@ -629,8 +748,10 @@ def run_b200(args):
                    "weights": "random init, init_scale=1", "finite_output": finite},
         "e2e": e2e, "gpu_launches": int(launches_per_step * k_eff), "launches_per_step": int(launches_per_step),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info,
-        "plan_buffers_gb": fs.plan.pool.nbytes() / 1e9, "parity": parity,
+        "plan_buffers_gb": plan_gb, "parity": parity,
     }
+    if extras is not None:
+        line["other_configs"] = extras
     if tf32 is not None:
         line["tf32"] = tf32
     if stock is not None:
@@ -825,6 +946,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)  # 200 of the 1000 identical steps
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_eager_gpu"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the short records of the other BASELINE configs")
     ap.add_argument("--no-tf32", action="store_true", help="skip the reference-precision (tf32 plan) context line")
     ap.add_argument("--no-stock-gpu", action="store_true", help="skip the stock PyTorch + cuDNN leg (the unmodified "
                     "reference on the same GPU)")

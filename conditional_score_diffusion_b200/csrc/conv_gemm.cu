@@ -1052,6 +1052,22 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   }
 }
 
+// Rows of the transposed kernel's macro tile (t_rows x 8 pixels = N of the MMA): the candidate that minimises
+// tiles x cycles per instruction, with cycles ~ max(100, N / 2) (tools/mma_rate_probe.cu: an M = 128 instruction never
+// costs less than ~100 cycles). 160 -> 32 (5 exact tiles), 80 -> 28 (3 tiles, 5 % padding instead of the 17 % of
+// 3 x 32), 40 -> 20 (2 exact tiles). kernels.transposed_tile_rows() mirrors this rule.
+static int pick_t_rows(int h) {
+  const int cand[4] = {32, 28, 24, 20};
+  int best = 32;
+  long long best_cost = -1;
+  for (int i = 0; i < 4; ++i) {
+    const int t = cand[i];
+    const long long cost = (long long)ceil_div(h, t) * std::max(100, t * 4);
+    if (best_cost < 0 || cost <= best_cost) { best = t; best_cost = cost; }
+  }
+  return best;
+}
+
 static int next_pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -1112,7 +1128,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   // transposed mode: macro tile = t_rows x 8 pixels. 32 rows (N = 256) by default; 20 rows (N = 160) when that
   // tiles the image exactly and 32 would waste more than the shorter MMA loses (40-row images).
   // kernels.transposed_tile_rows() mirrors this rule for the statistics-partials geometry.
-  p.t_rows = (t_mode && d->h % 32 != 0 && d->h < 64 && d->h % 20 == 0) ? 20 : kTRows;
+  p.t_rows = t_mode ? pick_t_rows(d->h) : kTRows;
   p.t_pix = p.t_rows * kHaloTW;
   p.tiles_w = ceil_div(d->w, p.TW);
   p.tiles_h = t_mode ? ceil_div(d->h, p.t_rows) : ceil_div(d->h, p.TH * mt);

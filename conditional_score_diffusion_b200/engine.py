@@ -872,7 +872,8 @@ class NetEngine:
     def _refresh_attn(pk):
         m = pk["mod"]
         c = m.NIN_2.W.shape[0]
-        pk["wv_img"].copy_(m.NIN_2.W.detach().t().reshape(1, 1, c, c))
+        w = m.NIN_2.W.detach().t().reshape(1, 1, c, c).to(torch.float32)
+        pk["wv_img"].copy_(K.round_tf32(w) if pk["wv_img"].dtype == torch.float32 else w)
         pk["bv"][:c] = m.NIN_2.b.detach()
 
     def _pack(self, device):

@@ -48,7 +48,17 @@ def pack_conv_weight(weight, n_pad=None, dtype=_BF16):
     w = weight.detach().to(torch.float32).permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
     out = torch.zeros(n_pad, kh * kw, cpad, dtype=torch.float32, device=weight.device)
     out[:cout, :, :cin] = w
-    return out.reshape(n_pad, kh * kw * cpad).to(dtype).contiguous()
+    out = out.reshape(n_pad, kh * kw * cpad)
+    if dtype == torch.float32:
+        return round_tf32(out).contiguous()      # tf32 plan: operands are stored rounded (see csrc/common.cuh round_tf32)
+    return out.to(dtype).contiguous()
+
+
+def round_tf32(t):
+    """fp32 -> nearest tf32 value (10 mantissa bits, ties away from zero = PTX cvt.rna.tf32.f32), kept in fp32 words:
+    what csd_pack_weights (kind 2) and the operand-producing kernels of the tf32 plan store."""
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
 _TILE_CACHE = {}
@@ -99,8 +109,14 @@ def transposed_shape_ok(h, w):
 
 
 def transposed_tile_rows(h):
-    """Rows of the transposed kernel's macro tile (conv_gemm_prepare): 32, or 20 for images such as 40x40."""
-    return 20 if (h % 32 != 0 and h < 64 and h % 20 == 0) else 32
+    """Rows of the transposed kernel's macro tile: mirrors pick_t_rows() in csrc/conv_gemm.cu (tiles x cycles per
+    instruction, cycles ~ max(100, N / 2) with N = 8 * rows): 160 -> 32, 80 -> 28, 40 -> 20."""
+    best, best_cost = 32, None
+    for t in (32, 28, 24, 20):
+        cost = math.ceil(h / t) * max(100, t * 4)
+        if best_cost is None or cost <= best_cost:
+            best, best_cost = t, cost
+    return best
 
 
 def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None, n_tile=None,

@@ -17,7 +17,8 @@ from oracle import ops as o_ops
 
 pytestmark = pytest.mark.gpu
 
-TF32_RTOL = 1e-3
+TF32_RTOL = 1e-3          # single kernels
+TF32_NET_RTOL = 2e-3      # whole networks (see tests/test_gpu_real_shapes.py for where the number comes from)
 F32_RTOL = 1e-5
 
 
@@ -254,17 +255,20 @@ def test_f32_layout_and_softmax():
     out = torch.full((2, 12, 10, 8), float("nan"), device="cuda")
     k.nchw_to_nhwc(x, y, out, 2.0, -1.0)
     ref = torch.cat([x, y], 1) * 2 - 1
-    assert torch.allclose(out[..., :6].permute(0, 3, 1, 2), ref, atol=1e-6)
+    got = out[..., :6].permute(0, 3, 1, 2)
+    # the fp32 plan's network input is stored rounded to tf32 (it only feeds tensor-core operands)
+    assert torch.equal(got, k.round_tf32(ref)) or ((got - ref).abs() <= ref.abs() * 2.0 ** -11 + 1e-7).all()
+    assert (out.view(torch.int32) & 0x1FFF).eq(0).all()
     assert (out[..., 6:] == 0).all()
     back = torch.empty(2, 3, 12, 10, device="cuda")
     rs = torch.tensor([0.5, 3.0], device="cuda")
     k.nhwc_to_nchw(out, 3, 3, back, rs)
-    assert torch.allclose(back, (y * 2 - 1) * rs.view(2, 1, 1, 1), atol=1e-6)
+    assert torch.allclose(back, out[..., 3:6].permute(0, 3, 1, 2) * rs.view(2, 1, 1, 1), atol=1e-6)
     logits = torch.randn(6, 37, 40, device="cuda", generator=g) * 4
     probs = torch.empty(6, 37, 40, device="cuda")
     k.softmax_rows(logits, probs, 37, 0.3)
     ref = torch.softmax(logits[..., :37] * 0.3, -1)
-    assert torch.allclose(probs[..., :37], ref, atol=2e-6)
+    assert ((probs[..., :37] - ref).abs() <= ref * 2.0 ** -11 + 2e-6).all()     # stored rounded to tf32
     assert (probs[..., 37:] == 0).all()
 
 
@@ -282,7 +286,7 @@ def test_tf32_network_small_golden():
     for key, ref in (("x", f["out_x"]), ("y", f["out_y"])):
         rel = _rel(out[key].cpu(), ref)
         print(f"[tf32 net] golden ncsnpp_paired {key}: rel={rel:.3e}")
-        assert rel < TF32_RTOL
+        assert rel < TF32_NET_RTOL
     assert torch.equal(out["x"], out2["x"]), "the tf32 plan has no atomics: two runs must agree bitwise"
     # switching back re-plans in bf16
     m.set_precision("bf16")
@@ -297,4 +301,4 @@ def test_tf32_network_small_golden():
         o2 = m2(f2["x"].cuda(), f2["labels"].cuda())
     rel = _rel(o2.cpu(), f2["out"])
     print(f"[tf32 net] golden ncsnpp cifar: rel={rel:.3e}")
-    assert rel < TF32_RTOL
+    assert rel < TF32_NET_RTOL
