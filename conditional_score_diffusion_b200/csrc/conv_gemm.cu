@@ -1057,6 +1057,9 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
 // costs less than ~100 cycles). 160 -> 32 (5 exact tiles), 80 -> 28 (3 tiles, 5 % padding instead of the 17 % of
 // 3 x 32), 40 -> 20 (2 exact tiles). kernels.transposed_tile_rows() mirrors this rule.
 static int pick_t_rows(int h) {
+  if (const char* e = getenv("CSD_TROWS_LEGACY")) {      // A/B switch: the round-1 rule (32, or 20 for 40-row images)
+    if (atoi(e) != 0) return (h % 32 != 0 && h < 64 && h % 20 == 0) ? 20 : 32;
+  }
   const int cand[4] = {32, 28, 24, 20};
   int best = 32;
   long long best_cost = -1;

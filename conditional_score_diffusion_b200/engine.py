@@ -306,6 +306,9 @@ class BlockOps:
     # kernel with the GroupNorm in its prologue; the training subclass keeps the plain path (its backward needs the
     # normalised tensor and takes the residual from the epilogue).
     fast_heads = True
+    # inference: QK^T / softmax / PV / projection of an attention block in one kernel (csrc/attention.cu); the training
+    # subclass keeps the separate GEMMs (its backward re-uses their operands).
+    fused_attention = True
     # inference: the reduction of a transposed convolution's per-tile statistics waits for the first consumer and is
     # folded into its coefficient kernel (gn_coeffs_partials); the training subclass finalizes at once.
     defer_finalize = os.environ.get("CSD_NO_DEFER_FINALIZE", "0") != "1"
@@ -567,6 +570,19 @@ class BlockOps:
         lp = K.ceil_to(L, 8)
         hn = self.group_norm([x], pk["gn_w"], pk["gn_b"], False, pk["groups"])
         hn_flat = Act(hn.t.view(b, 1, L, hn.pitch), c)
+        if self.fused_attention and self.act_dtype == BF16 and x.pitch % 8 == 0 and K.attn_core_supported(L, c):
+            # q | k | v in ONE 1x1 GEMM, then QK^T -> softmax -> PV -> projection -> residual in ONE kernel
+            # (csrc/attention.cu): 3 launches per block instead of 7, no [B, L, L] tensor in HBM
+            qkv = self.pool.get((b, 1, L, 3 * c))
+            self.rec.add(K.conv_gemm, [(hn_flat.t, hn.pitch, 0, c, 1)], pk["qkv"].wt, 3 * c, qkv, batch=b, h=1, w=L,
+                         n_store=3 * c, n_tile=pk["qkv"].n_tile, bias=pk["qkv"].bias)
+            out = self.pool.get((b, h, w, K.ceil_to(c, 8)))
+            self.rec.add(K.attn_core, qkv.view(b, L, 3 * c), pk["proj"].wt, pk["proj"].bias,
+                         x.t.view(b, L, x.pitch), out.view(b, L, out.shape[-1]), b, L, c,
+                         SQRT1_2 if skip_rescale else 1.0)
+            self.pool.put(hn.t)
+            self.pool.put(qkv)
+            return Act(out, c)
         # q | k in one GEMM: [B, L, 2C]
         qk = self.pool.get((b, 1, L, 2 * c))
         self.rec.add(K.conv_gemm, [(hn_flat.t, hn.pitch, 0, c, 1)], pk["qk"].wt, 2 * c, qk, batch=b, h=1, w=L,
@@ -860,6 +876,9 @@ class NetEngine:
         pk["groups"] = m.GroupNorm_0.num_groups
         dt = self.wt_dtype
         pk["qk"] = PackedConv([[WSrc(m.NIN_0.W, "nin"), WSrc(m.NIN_1.W, "nin")]], [(m.NIN_0.b, 0), (m.NIN_1.b, c)], device, dt)
+        if dt == BF16:     # fused attention core: q | k | v from one GEMM
+            pk["qkv"] = PackedConv([[WSrc(m.NIN_0.W, "nin"), WSrc(m.NIN_1.W, "nin"), WSrc(m.NIN_2.W, "nin")]],
+                                   [(m.NIN_0.b, 0), (m.NIN_1.b, c), (m.NIN_2.b, 2 * c)], device, dt)
         # A-operand "image" of the V^T GEMM: rows = output channel, K = input channel
         pk["wv_img"] = torch.empty(1, 1, c, c, device=device, dtype=dt)
         pk["bv"] = torch.zeros(c + 16, device=device, dtype=torch.float32)

@@ -111,6 +111,8 @@ def transposed_shape_ok(h, w):
 def transposed_tile_rows(h):
     """Rows of the transposed kernel's macro tile: mirrors pick_t_rows() in csrc/conv_gemm.cu (tiles x cycles per
     instruction, cycles ~ max(100, N / 2) with N = 8 * rows): 160 -> 32, 80 -> 28, 40 -> 20."""
+    if os.environ.get("CSD_TROWS_LEGACY", "0") != "0":
+        return 20 if (h % 32 != 0 and h < 64 and h % 20 == 0) else 32
     best, best_cost = 32, None
     for t in (32, 28, 24, 20):
         cost = math.ceil(h / t) * max(100, t * 4)
@@ -423,6 +425,25 @@ def softmax_rows(logits, probs, cols, scale):
     fn = _lib.lib().csd_softmax_rows_f32_f32 if probs.dtype == torch.float32 else _lib.lib().csd_softmax_rows_f32_bf16
     check(fn(_ptr(logits), logits.shape[-1], _ptr(probs), probs.shape[-1], rows, cols, float(scale), _stream()))
     return probs
+
+
+# Fused attention core (csd_attn_core_bf16); CSD_NO_FUSED_ATTN=1 keeps the separate GEMM / softmax launches (A/B).
+FUSED_ATTN_DEFAULT = os.environ.get("CSD_NO_FUSED_ATTN", "0") != "1"
+
+
+def attn_core_supported(L, c):
+    return FUSED_ATTN_DEFAULT and bool(_lib.lib().csd_attn_core_supported(int(L), int(c)))
+
+
+def attn_core(qkv, wo, bo, res, out, batch, L, c, out_scale):
+    """qkv [B, L, >=3c] bf16 (q | k | v), wo packed NIN_3 weights [rows >= c, pitch] bf16, bo fp32, res / out
+    [B, L, pitch] bf16: out = (res + softmax(q k^T c^-0.5) v Wo + bo) * out_scale, one launch."""
+    _require_cuda(qkv, wo, bo, res, out)
+    assert qkv.dtype == _BF16 and wo.dtype == _BF16 and res.dtype == _BF16 and out.dtype == _BF16
+    check(_lib.lib().csd_attn_core_bf16(_ptr(qkv), qkv.shape[-1], _ptr(wo), wo.shape[-1], wo.shape[-2], _ptr(bo),
+                                        _ptr(res), res.shape[-1], _ptr(out), out.shape[-1], batch, L, c,
+                                        float(out_scale), _stream()))
+    return out
 
 
 def time_embedding(labels, nf, embedding_type, fourier_w, w0, b0, w1, b1, out):

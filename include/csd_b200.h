@@ -316,6 +316,22 @@ typedef struct csd_conv_gemm_desc {
 
 int csd_conv_gemm(const csd_conv_gemm_desc* desc, csd_stream_t stream);
 
+/* ---- fused self-attention core -----------------------------------------------------------------------
+ * AttnBlockpp.forward after the q|k|v projection (models/layerspp.py:82-91) and the DDPM AttnBlock
+ * (models/layers.py:583-590) as ONE tcgen05 kernel, one CTA per (image, 128-query tile):
+ *   S = Q K^T (fp32 in TMEM) -> softmax over the L keys with logits * C^-0.5 -> O = P V -> Y = O Wo^T + bo ->
+ *   out = (res + Y) * out_scale.
+ * The [batch, L, L] logits / probabilities and the attention output never reach HBM.
+ * qkv: bf16 [batch, L, qkv_pitch] with q | k | v at channels [0,C) | [C,2C) | [2C,3C) (written by one 1x1
+ * csd_conv_gemm over the GroupNorm output); wo: bf16 K-major [wo_rows >= C, wo_pitch >= C] = NIN_3.W^T as packed
+ * for csd_conv_gemm; bo fp32 [>= C]; res / out: bf16 [batch, L, pitch] (x and the block output; out may alias
+ * neither input). L <= 512, C a multiple of 16 <= 320; csd_attn_core_supported tells whether (L, C) fits the kernel's
+ * shared-memory plan - callers fall back to separate GEMM / softmax launches otherwise.                       */
+int csd_attn_core_supported(int L, int C);
+int csd_attn_core_bf16(const void* qkv, int qkv_pitch, const void* wo, int wo_pitch, int wo_rows, const float* bo,
+                       const void* res, int res_pitch, void* out, int out_pitch, int batch, int L, int C,
+                       float out_scale, csd_stream_t stream);
+
 /* ---- device-resident adaptive Runge-Kutta pieces ---------------------------------------------
  * The reference integrates the probability-flow ODE with scipy's RK45 on the host: the full state crosses PCIe twice
  * per right-hand side (likelihood.py:91-99, sampling/unconditional.py:140-150). With these two kernels the state and

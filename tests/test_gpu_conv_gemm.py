@@ -590,3 +590,58 @@ def test_gn_coeffs_from_partials(c0, c1, tiles):
         assert (f0 - ref0).abs().max().item() <= 2e-4 * ref0.abs().max().item(), f"coef0 mode={mode}"
         if c1:
             assert (f1 - ref1).abs().max().item() <= 2e-4 * ref1.abs().max().item(), f"coef1 mode={mode}"
+
+
+# ---- fused attention core (csrc/attention.cu) --------------------------------------------------------------------
+@pytest.mark.parametrize("c,hw,b,rescale", [(192, 20, 3, True), (288, 10, 5, True), (288, 5, 7, True), (256, 16, 2, True),
+                                            (256, 8, 3, False), (288, 4, 2, False), (96, 20, 2, True), (128, 16, 1, False)])
+def test_fused_attention_core_vs_oracle(c, hw, b, rescale):
+    """AttnBlockpp / DDPM AttnBlock through BlockOps.attention (GroupNorm launch + one q|k|v GEMM + ONE fused
+    QK^T / softmax / PV / projection / residual kernel) against the oracle's fp32 block, and against the separate-launch
+    path it replaces (same bf16 roundings, so the two agree to ~1 bf16 ulp of the output)."""
+    from types import SimpleNamespace
+    from conditional_score_diffusion_b200 import engine as E
+    from conditional_score_diffusion_b200.models import layerspp
+    from oracle import ncsnpp as o_net
+    k = _kern()
+    L = hw * hw
+    assert k.attn_core_supported(L, c), (L, c)
+    torch.manual_seed(c + hw)
+    blk = layerspp.AttnBlockpp(c, skip_rescale=rescale, init_scale=1.0).cuda()
+    with torch.no_grad():
+        for prm in blk.parameters():
+            if prm.dim() == 1:
+                prm.add_(0.1 * torch.randn_like(prm))
+            else:
+                prm.mul_(3.0)          # sharper softmax than the default init gives
+    x = torch.randn(b, c, hw, hw, device="cuda").to(torch.bfloat16)
+    sd = {"all_modules.0." + n: v.detach().cpu() for n, v in blk.state_dict().items()}
+    ref = o_net.attn_block(sd, 0, x.float().cpu(), SimpleNamespace(skip_rescale=rescale))
+
+    class _Net(torch.nn.Module):
+        pass
+    net = _Net()
+    net.all_modules = torch.nn.ModuleList([blk])
+    eng = E.NetEngine(net)
+    eng.device = torch.device("cuda")
+    pk = eng._pack_attn(blk, eng.device)
+    outs = {}
+    for fused in (True, False):
+        rec = E.Recorder()
+        pool = E.BufferPool(eng.device)
+        ops = E.BlockOps(eng.device, pool, rec, torch.zeros(1 << 20, device="cuda"))
+        ops.fused_attention = fused
+        a = E.Act(_nhwc(x), c)
+        out = ops.attention(pk, a, rescale)
+        names = [getattr(fn, "__name__", "") for fn, _, _ in rec.ops]
+        assert ("attn_core" in names) == fused
+        rec.run()
+        torch.cuda.synchronize()
+        outs[fused] = out.t[..., :c].permute(0, 3, 1, 2).float().cpu()
+        assert torch.isfinite(outs[fused]).all()
+    scale = ref.abs().max().item()
+    e_f = (outs[True] - ref).abs().max().item() / scale
+    e_s = (outs[False] - ref).abs().max().item() / scale
+    e_fs = (outs[True] - outs[False]).abs().max().item() / scale
+    print(f"[attn] C={c} L={L} B={b}: fused vs oracle {e_f:.3e}, separate vs oracle {e_s:.3e}, fused vs separate {e_fs:.3e}")
+    assert e_f < 1e-2 and e_fs < 1e-2
