@@ -356,11 +356,12 @@ def conv_profile(plan):
             pixels = kw["batch"] * kw["h"] * kw["w"] * kw.get("z_batches", 1)
             flags = eye.get(a[1].data_ptr(), [])
             k_real = sum(sg[4] * sg[3] for i, sg in enumerate(segs) if not (i < len(flags) and flags[i]))
-            ev.append((e0, e1, 2.0 * pixels * n * k_real, (kw["h"], kw["w"], n, k_real), bool(kw.get("transposed"))))
+            head = bool(kw.get("transposed")) and segs[0][4] == 1       # tap-stacked output head (1x1 to 9 * Cout rows)
+            ev.append((e0, e1, 2.0 * pixels * n * k_real, (kw["h"], kw["w"], n, k_real), bool(kw.get("transposed")), head))
         else:
             fn(*a, **kw)
     torch.cuda.synchronize()
-    rows = [(e0.elapsed_time(e1), fl, shp, tp) for e0, e1, fl, shp, tp in ev]
+    rows = [(e0.elapsed_time(e1), fl, shp, tp, head) for e0, e1, fl, shp, tp, head in ev]
     return rows
 
 
@@ -671,8 +672,8 @@ def run_b200(args):
     # of its launches / their CUDA-event time, per launch on average; the other tcgen05 kernel is reported beside it
     # (the 3/6-channel output heads also run in that kernel, with 8 of the 128 M rows stored: by construction they
     # cannot approach the tensor roofline, so they are reported beside the >= 32-channel layers, not averaged in)
-    tp = [r for r in rows if r[3] and r[2][2] >= 32]
-    heads = [r for r in rows if r[3] and r[2][2] < 32]
+    tp = [r for r in rows if r[3] and r[2][2] >= 32 and not r[4]]
+    heads = [r for r in rows if r[3] and (r[2][2] < 32 or r[4])]
     tap = [r for r in rows if not r[3]]
     heads_ms, heads_fl = sum(r[0] for r in heads), sum(r[1] for r in heads)
     tp_ms, tp_fl = sum(r[0] for r in tp), sum(r[1] for r in tp)
@@ -695,7 +696,8 @@ def run_b200(args):
                                          "share_of_step": 2 * tap_ms / ms_per_step},
                 "output_heads_in_same_kernel": {"launches_per_forward": len(heads), "ms_per_forward": heads_ms,
                                                 "achieved_tflops": heads_fl / (heads_ms * 1e-3) / 1e12 if heads else None,
-                                                "note": "conv3x3 -> 6 channels: 8 of 128 M rows stored"},
+                                                "note": "conv3x3 -> 6 channels as a tap-stacked 1x1 convolution (54 of 128 M "
+                                                        "rows) + csd_tap_shift_sum"},
                 "all_conv_gemm": {"ms_per_forward": tp_ms + tap_ms + heads_ms,
                                   "algorithmic_gflop_per_forward": (tp_fl + tap_fl + heads_fl) / 1e9,
                                   "achieved_tflops": (tp_fl + tap_fl + heads_fl) / ((tp_ms + tap_ms + heads_ms) * 1e-3) / 1e12}}

@@ -151,6 +151,8 @@ _PROTOTYPES = {
                                        c_void_p, c_void_p, c_void_p]),
     "csd_dense_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "csd_conv_gemm": (c_int, [ctypes.POINTER(ConvGemmDesc), c_void_p]),
+    "csd_tap_shift_sum_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                       c_int, c_void_p]),
     "csd_attn_core_supported": (c_int, [c_int, c_int]),
     "csd_attn_core_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                    c_int, c_int, c_int, c_float, c_void_p]),

@@ -416,6 +416,52 @@ static int launch_fir_tma(const FirNhwcParamsT<VT>& p, cudaStream_t stream) {
   return CSD_OK;
 }
 
+// ---- tap-stacked output heads: shifted sum of per-tap partial maps ------------------------------------------------
+// A 3x3 convolution to a handful of channels (the 96 -> 6 output-skip heads, models/ncsnpp.py:337-352) wastes the tensor
+// core either way round (N = 8 at the per-instruction floor, or 8 of 128 M rows). It is computed instead as ONE 1x1
+// convolution to 9 * Cout "channels" - row t * Cout + co holds W[co, :, t] . a[pixel] for tap t at the UNSHIFTED pixel
+// (54 of 128 M rows, fused GroupNorm + SiLU prologue, no halo) - followed by this pass:
+//   out[b, y, x, co] = bias[co] + res[b, y, x, co] + sum_t P[b, y + t / 3 - 1, x + t % 3 - 1, t * Cout + co]
+// with out-of-image taps contributing zero (the reference zero-pads the normalised activation, padding = 1).
+// One thread per output pixel; every element of P is read exactly once.
+__global__ void __launch_bounds__(256)
+tap_shift_sum_kernel(const __nv_bfloat16* __restrict__ part, int p_pitch, int cout, const float* __restrict__ bias,
+                     const __nv_bfloat16* __restrict__ res, int res_pitch, __nv_bfloat16* __restrict__ out, int out_pitch,
+                     int batch, int H, int W) {
+  const long long total = (long long)batch * H * W;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W);
+    const int y = (int)((idx / W) % H);
+    const long long b = idx / ((long long)W * H);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = (i < cout && bias != nullptr) ? __ldg(bias + i) : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const __nv_bfloat16* src = part + ((b * H + yy) * W + xx) * p_pitch + t * cout;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < cout) acc[i] += __bfloat162float(src[i]);
+    }
+    if (res != nullptr) {
+      const __nv_bfloat16* rp = res + idx * res_pitch;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < cout) acc[i] += __bfloat162float(rp[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i >= cout) acc[i] = 0.f;
+    __nv_bfloat16* op = out + idx * out_pitch;
+    const bf16x8 o = pack8(acc);
+    *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(&o);
+    for (int c = 8; c < out_pitch; c += 8) *reinterpret_cast<uint4*>(op + c) = make_uint4(0, 0, 0, 0);
+  }
+}
+
 }  // namespace csd
 
 extern "C" {
@@ -511,6 +557,22 @@ int csd_fir_resample_nhwc_f32(const void* src, void* out, const void* add, int b
                               int mode, const float* taps4_host, csd_stream_t stream) {
   return csd::fir_resample_launch<csd::f32x8>(src, out, add, batch, h, w, c_pitch, mode, taps4_host,
                                               static_cast<cudaStream_t>(stream));
+}
+
+int csd_tap_shift_sum_bf16(const void* partial, int p_pitch, int cout, const float* bias, const void* res, int res_pitch,
+                           void* out, int out_pitch, int batch, int h, int w, csd_stream_t stream) {
+  using namespace csd;
+  CSD_REQUIRE(partial && out && batch >= 1 && h >= 1 && w >= 1, "tap_shift_sum: bad arguments");
+  CSD_REQUIRE(cout >= 1 && cout <= 8 && p_pitch >= 9 * cout, "tap_shift_sum: cout=%d (1..8), partial pitch %d", cout, p_pitch);
+  CSD_REQUIRE(out_pitch % 8 == 0 && out_pitch >= 8 && (res == nullptr || res_pitch >= cout),
+              "tap_shift_sum: output pitch %d must be a multiple of 8", out_pitch);
+  const long long total = (long long)batch * h * w;
+  const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)num_sms() * 16);
+  tap_shift_sum_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(partial), p_pitch, cout, bias, static_cast<const __nv_bfloat16*>(res), res_pitch,
+      static_cast<__nv_bfloat16*>(out), out_pitch, batch, h, w);
+  CSD_LAUNCH_CHECK("tap_shift_sum_kernel");
+  return CSD_OK;
 }
 
 }  // extern "C"

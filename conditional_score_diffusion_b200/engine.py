@@ -76,12 +76,13 @@ class WSrc:
     """Where one block of a packed weight comes from: a live parameter (so the pack can be refreshed in place after
     an optimizer step) and where its gradient goes. kind: 'conv' = nn.Conv2d weight [Cout, Cin, kh, kw] (optionally a
     slice [ci_off, ci_off + ci_cnt) of its input channels), 'nin' = NIN.W [in, out] (models/layers.py:555-564) used as
-    a 1x1 conv, 'eye' = identity (a residual carried as a K segment; no parameter)."""
+    a 1x1 conv, 'eye' = identity (a residual carried as a K segment; no parameter), 'tap' = tap `tap` of a 3x3
+    nn.Conv2d weight as a 1x1 convolution [Cout, Cin, 1, 1] (tap-stacked output heads)."""
 
-    __slots__ = ("param", "kind", "ci_off", "ci_cnt")
+    __slots__ = ("param", "kind", "ci_off", "ci_cnt", "tap")
 
-    def __init__(self, param, kind="conv", ci_off=0, ci_cnt=None):
-        self.param, self.kind, self.ci_off, self.ci_cnt = param, kind, ci_off, ci_cnt
+    def __init__(self, param, kind="conv", ci_off=0, ci_cnt=None, tap=0):
+        self.param, self.kind, self.ci_off, self.ci_cnt, self.tap = param, kind, ci_off, ci_cnt, tap
 
     def weight(self, device):
         """[Cout, Cin_slice, kh, kw] view of the live parameter."""
@@ -91,6 +92,9 @@ class WSrc:
         w = self.param.detach()
         if self.kind == "nin":
             w = w.t().reshape(w.shape[1], w.shape[0], 1, 1)
+        elif self.kind == "tap":
+            kw = w.shape[3]
+            w = w[:, :, self.tap // kw, self.tap % kw].reshape(w.shape[0], w.shape[1], 1, 1)
         if self.ci_cnt is not None:
             w = w[:, self.ci_off:self.ci_off + self.ci_cnt]
         return w
@@ -160,6 +164,11 @@ class PackedConv:
             cin_tot, cout = p.shape
             taps, cin = 1, (src.ci_cnt if src.ci_cnt is not None else cin_tot)
             s_co, s_ci, s_tap, off = 1, cout, 0, src.ci_off * cout
+        elif src.kind == "tap":
+            cout, cin_tot = p.shape[0], p.shape[1]
+            ntap = p.shape[2] * p.shape[3]
+            taps, cin = 1, (src.ci_cnt if src.ci_cnt is not None else cin_tot)
+            s_co, s_ci, s_tap, off = cin_tot * ntap, ntap, 0, src.ci_off * ntap + src.tap
         else:
             cout, cin_tot = p.shape[0], p.shape[1]
             taps = p.shape[2] * p.shape[3]
@@ -293,7 +302,9 @@ class Recorder:
 
 # A/B switch for the output heads: 0 = GroupNorm pass + per-tap kernel, 1 = transposed kernel with the pyramid as an
 # identity K segment, 2 = transposed kernel, pyramid added by its FIR upsampling.
-HEAD_MODE = int(os.environ.get("CSD_HEAD_MODE", "0"))
+# 3 (default) = tap-stacked: ONE 1x1 convolution to 9 * Cout rows in the transposed kernel (fused GroupNorm prologue, no
+# halo, 54 of 128 M rows for the 6-channel heads) + csd_tap_shift_sum (shifted sum of the 9 partial maps, bias, pyramid).
+HEAD_MODE = int(os.environ.get("CSD_HEAD_MODE", "3"))
 
 
 class BlockOps:
@@ -413,7 +424,7 @@ class BlockOps:
                 and K.transposed_shape_ok(h, w) and all(a.c % 8 == 0 for a in srcs))
 
     def conv(self, segs, pc, out_hw=None, temb=None, temb_pitch=0, res=None, scale=1.0, stride=1, pad=1,
-             out=None, head=False):
+             out=None, head=False, out_pitch=None):
         """segs: list of (Act, taps[, coef]); coef = fused GroupNorm+SiLU table of that segment (gn_coeffs).
         pc: PackedConv. head: few-channel output head forced into the transposed kernel (no statistics).
         Returns Act [B, oh, ow, n_store]."""
@@ -424,7 +435,7 @@ class BlockOps:
             out = self.pool.get((b, oh, ow, pc.n_store))
         seg_list = [(sg[0].t, sg[0].pitch, 0, sg[0].c, sg[1], sg[2] if len(sg) > 2 else None, True) for sg in segs]
         use_t = ((head or self.will_transpose(oh, ow, pc.cout))
-                 and K.transposed_eligible(seg_list, oh, ow, stride, pad))
+                 and K.transposed_eligible(seg_list, oh, ow, stride, pad, allow_1tap=head))
         if use_t and res is not None:
             raise CsdError("transposed conv takes its residual as an identity K segment (engine planning error)")
         partials = sums = None
@@ -436,7 +447,8 @@ class BlockOps:
         self.rec.add(K.conv_gemm, seg_list, pc.wt, pc.cout, out, batch=b, h=oh, w=ow, n_store=pc.n_store,
                      n_tile=pc.n_tile, bias=pc.bias, temb=temb, temb_pitch=temb_pitch,
                      res=res.t if res is not None else None, res_pitch=res.pitch if res is not None else 0,
-                     scale=scale, stride=stride, pad=pad, in_h=ih, in_w=iw, transposed=use_t, stat_partials=partials)
+                     scale=scale, stride=stride, pad=pad, in_h=ih, in_w=iw, transposed=use_t, stat_partials=partials,
+                     out_pitch=out_pitch)
         if partials is not None and self.defer_finalize:
             return Act(out, pc.cout, None, (partials, tiles_img, sums))
         if partials is not None:
@@ -444,9 +456,15 @@ class BlockOps:
             self.pool.put(partials)
         return Act(out, pc.cout, sums)
 
+    def head_tap_stacked(self, pc, hcur):
+        b, h, w, _ = hcur.shape
+        return (self.act_dtype == BF16 and self.fast_heads and HEAD_MODE == 3 and K.TRANSPOSED_DEFAULT and K.FUSE_GN_DEFAULT
+                and K.transposed_shape_ok(h, w) and hcur.c % 8 == 0 and pc.cout <= 8 and len(pc.segs) == 1
+                and len(pc.segs[0]) == 1 and pc.segs[0][0].kind == "conv" and pc.segs[0][0].param.shape[2:] == (3, 3))
+
     def head_in_transposed_kernel(self, pc, hcur):
         b, h, w, _ = hcur.shape
-        return (self.act_dtype == BF16 and self.fast_heads and HEAD_MODE != 0 and K.TRANSPOSED_DEFAULT and K.FUSE_GN_DEFAULT
+        return (self.act_dtype == BF16 and self.fast_heads and HEAD_MODE in (1, 2) and K.TRANSPOSED_DEFAULT and K.FUSE_GN_DEFAULT
                 and K.transposed_shape_ok(h, w) and hcur.c % 8 == 0 and pc.n_store == 8 and len(pc.segs) == 1)
 
     def head(self, gn, pc, hcur, extra, key, res=None):
@@ -457,6 +475,20 @@ class BlockOps:
         normalised copy), the residual pyramid as an identity K segment. extra: dict that owns the derived packs
         (visited by the engine's refresh); key: this head's slot in it."""
         gamma, beta, groups = gn
+        if self.head_tap_stacked(pc, hcur) and (res is None or res.c == pc.cout):
+            pct = extra.get((key, "taps"))
+            if pct is None:
+                src = pc.segs[0][0]
+                pct = extra[(key, "taps")] = PackedConv([[WSrc(src.param, "tap", tap=t) for t in range(9)]], None,
+                                                        self.device, pc.dtype)
+            (cf,) = self.gn_coeffs([hcur], gamma, beta, groups)
+            part = self.conv([(hcur, 1, cf)], pct, head=True)
+            self.pool.put(cf)
+            b, h, w, _ = hcur.shape
+            out = self.pool.get((b, h, w, pc.n_store))
+            self.rec.add(K.tap_shift_sum, part.t, pc.cout, pc.bias, res.t if res is not None else None, out)
+            self.release(part)
+            return Act(out, pc.cout)
         if self.head_in_transposed_kernel(pc, hcur) and (res is None or res.c == pc.cout):
             pct = pc
             if res is not None:
@@ -1122,7 +1154,10 @@ class NetPlan:
         if len(fir_taps) != 4:
             raise CsdError("the engine supports 4-tap FIR kernels only (config.model.fir_kernel)")
         if not net.fir:
-            raise CsdError("fir=False (naive resampling) is not supported by the engine yet")
+            # fir=False (the DDPM++ configs, e.g. configs/vp/cifar10_ddpmpp_continuous.py): nearest-neighbour x2 up
+            # (naive_upsample_2d / F.interpolate, up_or_down_sampling.py:59-63, layerspp.py:116) and 2x2 mean down
+            # (naive_downsample_2d / F.avg_pool2d, :66-69, layerspp.py:155) are the same polyphase kernel with taps [1, 1]
+            fir_taps = (0.0, 1.0, 1.0, 0.0)
         skip_rescale = net.skip_rescale
         channels = c0 + c1
 
@@ -1184,7 +1219,7 @@ class NetPlan:
                 hs.append(hold(hcur))
             if lvl != num_res - 1:
                 if net.resblock_type == "ddpm":
-                    hcur = self._ddpm_downsample(ops, mods[m_idx], pk[m_idx], hs[-1], fir_taps)
+                    hcur = self._resample_module(ops, mods[m_idx], pk[m_idx], hs[-1], fir_taps, down=True)
                 else:
                     hcur = resblock(m_idx, [hs[-1]])
                 m_idx += 1
@@ -1193,16 +1228,28 @@ class NetPlan:
                     if input_pyramid is not xin:
                         ops.release(input_pyramid)
                     input_pyramid = ip
-                    if net.combine_method != "sum":
-                        raise CsdError("progressive_combine='cat' is not supported by the engine yet")
-                    # Combine: conv1x1(pyramid) + h (layerspp.py:52-59)
-                    h2 = ops.conv([(input_pyramid, 1)], pk[m_idx], res=hcur, scale=1.0)
+                    if net.combine_method == "sum":
+                        # Combine: conv1x1(pyramid) + h (layerspp.py:52-59)
+                        h2 = ops.conv([(input_pyramid, 1)], pk[m_idx], res=hcur, scale=1.0)
+                    else:
+                        # Combine 'cat': cat([conv1x1(pyramid), h], dim=1) - the conv writes the first channels of the
+                        # concatenated tensor, h is copied behind them
+                        pcc = pk[m_idx]
+                        if not ops.fuse_small_gn:      # the training subclass: its tape does not know the copy below
+                            raise CsdError("progressive_combine='cat' has no backward plan (inference only)")
+                        if pcc.cout % 8 != 0:
+                            raise CsdError("progressive_combine='cat' needs a multiple of 8 channels")
+                        b_, hh_, ww_, _ = hcur.shape
+                        cat = self.pool.get((b_, hh_, ww_, pcc.cout + K.ceil_to(hcur.c, 8)))
+                        ops.conv([(input_pyramid, 1)], pcc, out=cat[..., :pcc.cout], out_pitch=cat.shape[-1])
+                        rec.add(cat[..., pcc.cout:pcc.cout + hcur.c].copy_, hcur.t[..., :hcur.c])
+                        h2 = Act(cat, pcc.cout + hcur.c)
                     ops.release(hcur)
                     hcur = h2
                     m_idx += 1
                 elif net.progressive_input == "residual":
-                    ip = self._fir_conv_down(ops, pk[m_idx], input_pyramid, fir_taps, res=hcur,
-                                             scale=SQRT1_2 if skip_rescale else 1.0)
+                    ip = self._resample_module(ops, mods[m_idx], pk[m_idx], input_pyramid, fir_taps, down=True, res=hcur,
+                                               scale=SQRT1_2 if skip_rescale else 1.0)
                     if input_pyramid is not xin:
                         drop(input_pyramid)
                     ops.release(hcur)
@@ -1235,6 +1282,9 @@ class NetPlan:
                 hcur = h2
                 m_idx += 1
             if net.progressive != "none":
+                if not net.fir:
+                    raise CsdError("progressive output pyramids with fir=False go through layerspp.Upsample(fir=False), "
+                                   "which raises in the reference (models/layerspp.py:116-117); unsupported")
                 if net.progressive == "residual":
                     raise CsdError("progressive='residual' relies on upsample_conv_2d, which is dead code in the "
                                    "reference (up_or_down_sampling.py:123 indexes with a negative step); unsupported")
@@ -1257,8 +1307,9 @@ class NetPlan:
                 m_idx += 1
             if lvl != 0:
                 if net.resblock_type == "ddpm":
-                    raise CsdError("resblock_type='ddpm' upsampling is not supported by the engine yet")
-                h2 = resblock(m_idx, [hcur])
+                    h2 = self._resample_module(ops, mods[m_idx], pk[m_idx], hcur, fir_taps, down=False)
+                else:
+                    h2 = resblock(m_idx, [hcur])
                 ops.release(hcur)
                 hcur = h2
                 m_idx += 1
@@ -1288,8 +1339,31 @@ class NetPlan:
         ops.release(f)
         return out
 
-    def _ddpm_downsample(self, ops, m, pc, a, fir_taps):
-        raise CsdError("resblock_type='ddpm' is not supported by the engine yet")
+    def _resample_module(self, ops, m, pc, a, fir_taps, down, res=None, scale=1.0):
+        """layerspp.Downsample / layerspp.Upsample (models/layerspp.py:94-163) as used by resblock_type='ddpm' and by the
+        'residual' input pyramid: fir x with_conv select FIR-filtered or naive resampling, with or without a 3x3 conv.
+        `a` is not released (callers own it). res/scale: epilogue residual of the conv forms."""
+        b, h, w, _ = a.shape
+        if down:
+            if m.with_conv and m.fir:          # up_or_down_sampling.Conv2d(down=True) = conv_downsample_2d + bias
+                return self._fir_conv_down(ops, pc, a, fir_taps, res=res, scale=scale)
+            if m.with_conv:                    # F.pad(x, (0, 1, 0, 1)) + 3x3 stride-2 VALID conv (layerspp.py:151-153)
+                return ops.conv([(a, 9)], pc, out_hw=(h // 2, w // 2), res=res, scale=scale, stride=2, pad=0)
+            if res is not None:
+                raise CsdError("resampling module without convolution cannot take a residual")
+            return ops.fir(a, "down", fir_taps, operand=False)      # downsample_2d / avg_pool2d
+        if m.with_conv and m.fir:
+            raise CsdError("layerspp.Upsample(fir=True, with_conv=True) relies on upsample_conv_2d, which is dead code in "
+                           "the reference (up_or_down_sampling.py:123 indexes with a negative step); unsupported")
+        if not m.fir:
+            raise CsdError("layerspp.Upsample(fir=False) cannot run in the reference: F.interpolate(x, (H*2, W*2), 'nearest') "
+                           "(models/layerspp.py:116-117) passes 'nearest' as scale_factor and raises; unsupported")
+        up = ops.fir(a, "up", fir_taps, operand=m.with_conv)           # upsample_2d
+        if not m.with_conv:
+            return up
+        out = ops.conv([(up, 9)], pc, res=res, scale=scale)
+        ops.release(up)
+        return out
 
     # -- execution ---------------------------------------------------------------------------------
     def run(self):

@@ -97,11 +97,12 @@ TRANSPOSED_DEFAULT = os.environ.get("CSD_NO_TRANSPOSED", "0") != "1"
 FUSE_GN_DEFAULT = os.environ.get("CSD_NO_FUSE_GN", "0") != "1"
 
 
-def transposed_eligible(segments, h, w, stride=1, pad=1, z_batches=1):
+def transposed_eligible(segments, h, w, stride=1, pad=1, z_batches=1, allow_1tap=False):
     """3x3 stride-1 convs whose image tiles well into 32x8-pixel macro tiles run in the transposed halo
     mode (output channels on M, 256 pixels on N): measured faster on B200 whenever the 32-row tiling
     wastes < ~20% of the rows (tests/test_gpu_conv_gemm.py::test_transposed_timing)."""
-    return (segments[0][4] == 9 and stride == 1 and pad == 1 and z_batches == 1 and transposed_shape_ok(h, w))
+    return ((segments[0][4] == 9 or allow_1tap) and stride == 1 and pad == 1 and z_batches == 1
+            and transposed_shape_ok(h, w))
 
 
 def transposed_shape_ok(h, w):
@@ -417,6 +418,15 @@ def fir_resample(src, out, mode, taps, add=None, round_out=False):
     fn = _lib.lib().csd_fir_resample_nhwc_f32 if src.dtype == torch.float32 else _lib.lib().csd_fir_resample_nhwc_bf16
     m = {"up": 1, "down": 2, "prefilter": 3}[mode] | (0x10 if (round_out and src.dtype == torch.float32) else 0)
     check(fn(_ptr(src), _ptr(out), _ptr(add), b, h, w, pitch, m, arr, _stream()))
+    return out
+
+
+def tap_shift_sum(partial, cout, bias, res, out):
+    """out[b,y,x,co] = bias[co] + res[...] + sum_t partial[b, y+dy_t, x+dx_t, t*cout + co] (tap-stacked output heads)."""
+    b, h, w, pitch = partial.shape
+    check(_lib.lib().csd_tap_shift_sum_bf16(_ptr(partial), pitch, cout, _ptr(bias), _ptr(res),
+                                            res.shape[-1] if res is not None else 0, _ptr(out), out.shape[-1], b, h, w,
+                                            _stream()))
     return out
 
 

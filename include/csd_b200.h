@@ -316,6 +316,14 @@ typedef struct csd_conv_gemm_desc {
 
 int csd_conv_gemm(const csd_conv_gemm_desc* desc, csd_stream_t stream);
 
+/* Few-channel 3x3 output heads (conv3x3(SiLU(GroupNorm(h))) -> 3 / 6 channels, models/ncsnpp.py:337-352, 372-381) as a
+ * tap-stacked 1x1 convolution + this pass: partial [batch, h, w, p_pitch] bf16 holds, at channel t * cout + co, tap t's
+ * contribution computed at the UNSHIFTED pixel; out[b, y, x, co] = bias[co] + res[b, y, x, co] + sum over the 9 taps of
+ * partial[b, y + t/3 - 1, x + t%3 - 1, t * cout + co] (zero outside the image). cout <= 8; out channels >= cout are
+ * written as zero.                                                                                               */
+int csd_tap_shift_sum_bf16(const void* partial, int p_pitch, int cout, const float* bias, const void* res, int res_pitch,
+                           void* out, int out_pitch, int batch, int h, int w, csd_stream_t stream);
+
 /* ---- fused self-attention core -----------------------------------------------------------------------
  * AttnBlockpp.forward after the q|k|v projection (models/layerspp.py:82-91) and the DDPM AttnBlock
  * (models/layers.py:583-590) as ONE tcgen05 kernel, one CTA per (image, 128-query tile):

@@ -95,12 +95,13 @@ def test_unsupported_modes_raise_loudly():
             m.cpu()({"x": f["x"], "y": f["y"]}, f["labels"])
 
 
-@pytest.mark.parametrize("head_mode,defer", [(0, True), (1, True), (2, True), (0, False)])
+@pytest.mark.parametrize("head_mode,defer", [(0, True), (1, True), (2, True), (3, True), (0, False)])
 def test_paired_forward_transposed_levels_vs_oracle(monkeypatch, head_mode, defer):
     """64x64, nf 32: the 64 px and 32 px levels run in the persistent transposed kernel (fused GroupNorm+SiLU
     prologue, skip / identity-residual K segments, epilogue GroupNorm sums); everything else as in the tiny nets.
     Parametrised over the engine's A/B switches: output heads in the per-tap kernel (0) or in the transposed kernel
-    with the pyramid as identity segment (1) / added by its FIR pass (2); per-tile statistics reduced by the
+    with the pyramid as identity segment (1) / added by its FIR pass (2) / tap-stacked 1x1 convolution + shifted sum
+    (3, the default); per-tile statistics reduced by the
     coefficient kernel (defer) or by their own finalize launch."""
     from conditional_score_diffusion_b200 import engine
     from conditional_score_diffusion_b200.models import ncsnpp, utils  # noqa: F401
