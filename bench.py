@@ -857,6 +857,9 @@ def run_train(args):
     model = utils.create_model(cfg).to(dev).train()
     if world > 1:
         D.broadcast_parameters(model, src=0)
+        if not args.no_overlap:
+            # bucketed gradient all-reduce overlapped with the reverse launch list (distributed.OverlappedGradSync)
+            D.enable_gradient_overlap(model, segments=4)
     sde = sde_lib.cVESDE(5e-3, math.sqrt(3 * TRAIN_IMAGE * TRAIN_IMAGE), 1000)
     loss_fn = losses.get_general_sde_loss_fn(sde, train=True, conditional=True, reduce_mean=True, continuous=True,
                                              likelihood_weighting=True)
@@ -930,7 +933,10 @@ def run_train(args):
                                    "dropout 0.1, SR3 loss (likelihood weighting), Adam 2e-4, clip 1.0, EMA 0.999",
                        "optimizer": "torch Adam + foreach EMA" if args.torch_optim else "optim.FusedAdamEMA (2 launches)",
                        "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"data parallel over {world} GPU(s), one all-reduce of the flat fp32 gradient buffer per step",
+                       "parallelism": (f"data parallel over {world} GPU(s), gradient all-reduce of the flat fp32 buffer in 4 "
+                                       f"segments overlapped with the backward pass" if (world > 1 and not args.no_overlap)
+                                       else f"data parallel over {world} GPU(s), one all-reduce of the flat fp32 gradient "
+                                            f"buffer after the backward pass"),
                        "l2": "activations + pixel-major copies per step (GBs) exceed the 126 MB L2", "finite_loss": bool(math.isfinite(loss_host))},
             "e2e": {"value": B * world / e2e_ms * 1e3, "unit": "images/s", "h2d_bytes_per_step": 2 * B * 3 * TRAIN_IMAGE * TRAIN_IMAGE * 4,
                     "d2h_bytes_per_step": 4},
@@ -948,6 +954,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)  # 200 of the 1000 identical steps
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_eager_gpu"])
+    ap.add_argument("--no-overlap", action="store_true", help="train workload: all-reduce after backward instead of the "
+                    "overlapped segment-wise all-reduce")
     ap.add_argument("--no-extras", action="store_true", help="skip the short records of the other BASELINE configs")
     ap.add_argument("--no-tf32", action="store_true", help="skip the reference-precision (tf32 plan) context line")
     ap.add_argument("--no-stock-gpu", action="store_true", help="skip the stock PyTorch + cuDNN leg (the unmodified "

@@ -101,12 +101,74 @@ def _shared_flat(grads):
     return flat
 
 
+class OverlappedGradSync:
+    """Bucketed gradient all-reduce overlapped with the backward pass (what Lightning's accelerator='ddp' gives the
+    reference through torch DDP's bucket hooks, run_lib.py:55-57). The engine's backward is a planned launch list over
+    ONE flat fp32 gradient buffer; `engine_train.TrainPlan.grad_segments` cuts it into `segments` pieces and knows which
+    spans of the buffer are final after each piece. This hook is called after every piece: it all-reduces those spans on
+    a side stream (NCCL over NVLink) while the compute stream runs the next piece, and joins the streams after the last
+    one, so `loss.backward()` returns averaged gradients. No other collective runs on the backward path."""
+
+    def __init__(self, segments=4, average=True, group=None):
+        self.segments, self.average, self.group = max(1, int(segments)), average, group
+        self.stream = None
+        self.bytes_last = 0
+        self.calls_last = 0
+
+    def __call__(self, flat, ranges, last):
+        world_size = world()[1]
+        if world_size > 1 and ranges:
+            if flat.is_cuda:
+                if self.stream is None:
+                    self.stream = torch.cuda.Stream(device=flat.device)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(flat.device))
+                with torch.cuda.stream(self.stream):
+                    self.stream.wait_event(ev)
+                    self._reduce(flat, ranges, world_size)
+            else:
+                self._reduce(flat, ranges, world_size)
+        if last and self.stream is not None:
+            torch.cuda.current_stream(flat.device).wait_stream(self.stream)
+
+    def _reduce(self, flat, ranges, world_size):
+        for off, n in ranges:
+            span = flat[off:off + n]
+            dist.all_reduce(span, group=self.group)
+            if self.average:
+                span.div_(world_size)
+            self.bytes_last += n * 4
+            self.calls_last += 1
+
+
+def enable_gradient_overlap(module, segments=4, average=True, group=None):
+    """Install an OverlappedGradSync on an engine-backed network: from now on `loss.backward()` returns gradients that
+    are already averaged over the ranks, and `allreduce_gradients(module)` becomes a no-op for it. Returns the hook (its
+    `bytes_last` / `calls_last` counters accumulate what was reduced). A single-process run is left untouched."""
+    eng = getattr(module, "_engine", None)
+    if eng is None:
+        raise ValueError("enable_gradient_overlap needs an engine-backed network (models.ncsnpp / models.ddpm)")
+    if world()[1] == 1:
+        eng.grad_sync = None
+        return None
+    eng.grad_sync = OverlappedGradSync(segments, average, group)
+    return eng.grad_sync
+
+
+def disable_gradient_overlap(module):
+    eng = getattr(module, "_engine", None)
+    if eng is not None:
+        eng.grad_sync = None
+
+
 def allreduce_gradients(module_or_params, average=True, bucket_bytes=64 << 20, group=None):
     """Sum (or average) the .grad of every parameter over the ranks: the DDP gradient all-reduce the reference gets
     from Lightning's accelerator='ddp' (run_lib.py:55-57). Gradients produced by the engine's backward pass live in
     one flat buffer and are reduced in place with ONE collective over NVLink; otherwise they are packed into buckets of
     `bucket_bytes`. Returns the number of bytes reduced."""
     rank, world_size = world()
+    if getattr(getattr(module_or_params, "_engine", None), "grad_sync", None) is not None:
+        return 0            # enable_gradient_overlap: the backward pass has already averaged the gradients
     params = module_or_params.parameters() if hasattr(module_or_params, "parameters") else module_or_params
     grads = [p.grad for p in params if p.grad is not None]
     if world_size == 1 or not grads:

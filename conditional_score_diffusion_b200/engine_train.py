@@ -171,6 +171,7 @@ class TrainPlan(NetPlan):
         self.pviews, off = {}, 0
         self.param_list = params
         self.param_offsets = []
+        self._grad_touch, self._cur_entry, self._entry_end = {}, 0, []
         for p in params:
             self.pviews[p.data_ptr()] = self.gflat[off:off + p.numel()].view(p.shape)
             self.param_offsets.append(off)
@@ -181,6 +182,9 @@ class TrainPlan(NetPlan):
         v = self.pviews.get(t.data_ptr())
         if v is None:
             raise CsdError("gradient requested for a tensor that is not a network parameter")
+        # which tape entry (in backward order) asked for this gradient last: after that entry's launches the gradient
+        # is final, which is what lets a data-parallel all-reduce of it start while the rest of the backward still runs
+        self._grad_touch[t.data_ptr()] = self._cur_entry
         return v
 
     def _grad(self, a):
@@ -241,8 +245,11 @@ class TrainPlan(NetPlan):
             bwd.add(K.nchw_grad_to_nhwc, self.gouts[0], out_c, self.row_scale, None, 0, None, gfin[0])
         gfin[1] = True
         self.temb_info = None
-        for kind, info in reversed(tape):
+        for i, (kind, info) in enumerate(reversed(tape)):
+            self._cur_entry = i
             getattr(self, "_bwd_" + kind)(info)
+            self._entry_end.append(len(bwd.ops))
+        self._cur_entry = len(self._entry_end)          # anything requested from here on is final only at the very end
         # one scratch tensor for the split-K partial sums of every wgrad
         if self.partial_numel:
             part = torch.empty(self.partial_numel, device=dev, dtype=torch.float32)
@@ -602,9 +609,74 @@ class TrainPlan(NetPlan):
         K.sgemm_small(0, 0, 1, n, 1, one, 1, src[off:], n, dst, n, beta=1.0)
 
     # -- execution -----------------------------------------------------------------------------------------------
+    # -- data-parallel overlap: the reverse list in segments, finished gradient ranges handed to a sync hook ----------
+    def grad_segments(self, nseg):
+        """Split the reverse launch list at tape-entry boundaries into <= nseg segments of roughly equal launch counts.
+        Returns [(op_lo, op_hi, ranges)]: `ranges` = coalesced (offset, length) spans of the flat gradient buffer whose
+        last writer sits inside the segment - they are final once the segment has run. Every element of the buffer
+        appears in exactly one segment's ranges."""
+        key = ("segs", nseg)
+        if key in self.scratch:
+            return self.scratch[key]
+        n_ops = len(self.bwd.ops)
+        ends = self._entry_end
+        cuts = []
+        for k in range(1, nseg):
+            target = n_ops * k / nseg
+            e = min(range(len(ends)), key=lambda i: abs(ends[i] - target))
+            if not cuts or e > cuts[-1]:
+                cuts.append(e)
+        bounds = [(-1, 0)] + [(e, ends[e]) for e in cuts] + [(len(ends) + 1, n_ops)]
+        touch = self._grad_touch
+        segs = []
+        for (e_lo, op_lo), (e_hi, op_hi) in zip(bounds[:-1], bounds[1:]):
+            spans = []
+            for p, off in zip(self.param_list, self.param_offsets):
+                last = touch.get(p.data_ptr(), len(ends) + 1)       # never requested: stays zero, "final" at the end
+                if e_lo < last <= e_hi:
+                    spans.append((off, K.ceil_to(p.numel(), 4)))
+            spans.sort()
+            merged = []
+            for off, n in spans:
+                if merged and merged[-1][0] + merged[-1][1] == off:
+                    merged[-1] = (merged[-1][0], merged[-1][1] + n)
+                else:
+                    merged.append((off, n))
+            segs.append((op_lo, op_hi, merged))
+        self.scratch[key] = segs
+        return segs
+
+    def _run_segmented(self, sync):
+        segs = self.grad_segments(sync.segments)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if self.use_graph and not capturing and self.bwd_warm >= 1 and not hasattr(self, "_seg_graphs"):
+            torch.cuda.synchronize()
+            self._seg_graphs = []
+            for lo, hi, _ in segs:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for fn, a, kw in self.bwd.ops[lo:hi]:
+                        fn(*a, **kw)
+                self._seg_graphs.append(g)
+        graphs = getattr(self, "_seg_graphs", None) if (self.use_graph and not capturing) else None
+        for i, (lo, hi, ranges) in enumerate(segs):
+            if graphs is not None:
+                graphs[i].replay()
+            else:
+                for fn, a, kw in self.bwd.ops[lo:hi]:
+                    fn(*a, **kw)
+            sync(self.gflat, ranges, last=(i == len(segs) - 1))
+        self.bwd_warm += 1
+
     def run_backward(self):
         """Run the reverse launch list: eagerly the first time, as a replayed CUDA graph afterwards (the list is static:
-        every buffer, including the parameter-gradient buffer and the split-K scratch, belongs to the plan)."""
+        every buffer, including the parameter-gradient buffer and the split-K scratch, belongs to the plan). With a
+        gradient-sync hook on the engine (distributed.enable_gradient_overlap) the list runs in segments and every
+        segment's finished gradient ranges are all-reduced on a side stream while the next segment computes."""
+        sync = getattr(self.eng, "grad_sync", None)
+        if sync is not None and self.want_params:
+            self._run_segmented(sync)
+            return
         if not self.use_graph or torch.cuda.is_current_stream_capturing():
             self.bwd.run()
             return

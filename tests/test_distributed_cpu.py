@@ -103,3 +103,104 @@ def test_broadcast_shard_gather_world2():
     assert r[0]["max"] == 2.0 and r[1]["max"] == 2.0
     assert r[0]["flat_ok"] and r[1]["flat_ok"], "in-place all-reduce of the flat gradient buffer"
     assert r[0]["bucket_ok"] and r[1]["bucket_ok"], "bucketed gradient all-reduce"
+
+
+# ---- overlapped gradient all-reduce (training, DDP) ---------------------------------------------------------------
+def _overlap_worker(rank, world_size, port, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        # the hook is fed what engine_train.TrainPlan.grad_segments produces: disjoint spans of one flat buffer, segment
+        # by segment; after the last segment the buffer must equal the plain averaged all-reduce
+        g = torch.Generator().manual_seed(rank)
+        flat = torch.randn(1000, generator=g)
+        ref = flat.clone()
+        dist.all_reduce(ref)
+        ref /= world_size
+        sync = D.OverlappedGradSync(segments=3, average=True)
+        segs = [[(600, 400)], [(200, 100), (350, 250)], [(0, 200), (300, 50)]]       # tail first, holes filled last
+        for i, ranges in enumerate(segs):
+            sync(flat, ranges, last=(i == len(segs) - 1))
+        covered = sorted(r for s in segs for r in s)
+        results[rank] = {"ok": bool(torch.allclose(flat, ref)), "bytes": sync.bytes_last, "calls": sync.calls_last,
+                         "covered": covered}
+
+        class Net(torch.nn.Module):      # engine-backed networks carry `_engine`; allreduce_gradients defers to the hook
+            pass
+        net = Net()
+        net._engine = type("E", (), {"grad_sync": None})()
+        hook = D.enable_gradient_overlap(net, segments=2)
+        results[rank]["installed"] = hook is not None and net._engine.grad_sync is hook
+        results[rank]["noop"] = D.allreduce_gradients(net) == 0
+        D.disable_gradient_overlap(net)
+        results[rank]["removed"] = net._engine.grad_sync is None
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_overlap(rank, world_size, port, q):
+    res = {}
+    _overlap_worker(rank, world_size, port, res)
+    q.put((rank, res[rank]))
+
+
+def test_overlapped_gradient_sync_world_size_2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_run_overlap, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    for r in range(2):
+        assert out[r]["ok"], "segment-wise all-reduce differs from the plain averaged all-reduce"
+        assert out[r]["bytes"] == 1000 * 4 and out[r]["calls"] == 5
+        assert out[r]["installed"] and out[r]["noop"] and out[r]["removed"]
+
+
+def test_grad_segments_cover_the_flat_buffer_once():
+    """TrainPlan.grad_segments on a stand-in plan: spans are disjoint, cover every parameter exactly once, and a parameter
+    lands in the segment of the LAST tape entry that touched it (late writers such as Dense_0 stay out of early ones)."""
+    from conditional_score_diffusion_b200 import kernels as K
+    from conditional_score_diffusion_b200.engine_train import TrainPlan
+
+    class P:      # parameter stand-in
+        def __init__(self, n, ptr):
+            self._n, self._ptr = n, ptr
+
+        def numel(self):
+            return self._n
+
+        def data_ptr(self):
+            return self._ptr
+
+    plan = TrainPlan.__new__(TrainPlan)
+    params = [P(10, 1), P(7, 2), P(64, 3), P(5, 4), P(32, 5), P(9, 6)]
+    plan.param_list = params
+    plan.param_offsets, off = [], 0
+    for p in params:
+        plan.param_offsets.append(off)
+        off += K.ceil_to(p.numel(), 4)
+    plan.scratch = {}
+    plan.bwd = type("R", (), {"ops": [None] * 40})()
+    plan._entry_end = [4, 9, 15, 22, 30, 40]                   # op count after each tape entry (backward order)
+    # backward order: last layers first. param 6 (tail) touched by entry 0, param 5 by entry 1, param 4 by entries 1 AND 5
+    # (a late writer), param 3 by entry 2, param 2 by entry 4, param 1 by entry 5
+    plan._grad_touch = {6: 0, 5: 1, 4: 5, 3: 2, 2: 4, 1: 5}
+    segs = plan.grad_segments(3)
+    assert [s[:2] for s in segs][0][0] == 0 and segs[-1][1] == 40
+    assert all(a[1] == b[0] for a, b in zip(segs[:-1], segs[1:]))
+    spans = sorted(sp for _, _, r in segs for sp in r)
+    assert spans[0][0] == 0 and all(a[0] + a[1] <= b[0] for a, b in zip(spans[:-1], spans[1:]))
+    assert sum(n for _, n in spans) == off
+    seg_of = {}
+    for i, (_, _, r) in enumerate(segs):
+        for o, n in r:
+            for p, po in zip(params, plan.param_offsets):
+                if o <= po < o + n:
+                    seg_of[p.data_ptr()] = i
+    assert seg_of[6] == 0 and seg_of[4] == len(segs) - 1 and seg_of[1] == len(segs) - 1
+    assert seg_of[5] <= seg_of[3] <= seg_of[2]
