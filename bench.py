@@ -857,8 +857,11 @@ def run_train(args):
     model = utils.create_model(cfg).to(dev).train()
     if world > 1:
         D.broadcast_parameters(model, src=0)
-        if not args.no_overlap:
-            # bucketed gradient all-reduce overlapped with the reverse launch list (distributed.OverlappedGradSync)
+        if args.overlap:
+            # bucketed gradient all-reduce overlapped with the reverse launch list (distributed.OverlappedGradSync).
+            # Opt-in: measured at N = 2 (profiles/ddp_overlap_r2.json) the whole 115 MB all-reduce is 0.28 ms exposed
+            # after the backward pass and 0.44 ms when split into 36 spans over 4 segments - NVLink makes the collective
+            # too short for the extra launches to pay
             D.enable_gradient_overlap(model, segments=4)
     sde = sde_lib.cVESDE(5e-3, math.sqrt(3 * TRAIN_IMAGE * TRAIN_IMAGE), 1000)
     loss_fn = losses.get_general_sde_loss_fn(sde, train=True, conditional=True, reduce_mean=True, continuous=True,
@@ -934,7 +937,7 @@ def run_train(args):
                        "optimizer": "torch Adam + foreach EMA" if args.torch_optim else "optim.FusedAdamEMA (2 launches)",
                        "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": (f"data parallel over {world} GPU(s), gradient all-reduce of the flat fp32 buffer in 4 "
-                                       f"segments overlapped with the backward pass" if (world > 1 and not args.no_overlap)
+                                       f"segments overlapped with the backward pass" if (world > 1 and args.overlap)
                                        else f"data parallel over {world} GPU(s), one all-reduce of the flat fp32 gradient "
                                             f"buffer after the backward pass"),
                        "l2": "activations + pixel-major copies per step (GBs) exceed the 126 MB L2", "finite_loss": bool(math.isfinite(loss_host))},
@@ -954,8 +957,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)  # 200 of the 1000 identical steps
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_eager_gpu"])
-    ap.add_argument("--no-overlap", action="store_true", help="train workload: all-reduce after backward instead of the "
-                    "overlapped segment-wise all-reduce")
+    ap.add_argument("--overlap", action="store_true", help="train workload: segment-wise gradient all-reduce overlapped "
+                    "with the backward pass instead of one all-reduce after it")
     ap.add_argument("--no-extras", action="store_true", help="skip the short records of the other BASELINE configs")
     ap.add_argument("--no-tf32", action="store_true", help="skip the reference-precision (tf32 plan) context line")
     ap.add_argument("--no-stock-gpu", action="store_true", help="skip the stock PyTorch + cuDNN leg (the unmodified "

@@ -13,6 +13,9 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 cfg = bench.workload_config()
 torch.manual_seed(0)
 model = utils.create_model(cfg).cuda().eval()
+import os
+if os.environ.get("CSD_PRECISION"):
+    model.set_precision(os.environ["CSD_PRECISION"])
 model._engine.ensure_packed(torch.device("cuda", 0))
 plan = model._engine.plan(B, 160, 160, 3, 3)
 plan.in0.normal_(); plan.in1.uniform_(); plan.labels.fill_(500.0)
