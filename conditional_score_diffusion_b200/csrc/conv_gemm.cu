@@ -685,11 +685,16 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmKernelParams& p, 
   return t;
 }
 
+template <bool kTf32>
 __global__ void __launch_bounds__(kPThreads, 1)
 conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                     const ConvGemmKernelParams p) {
+  // kTf32: the reference-precision plan. Activations, weights and the output are fp32 words, the MMA is kind::tf32.
+  // Every shared-memory structure keeps its BYTE geometry (64-byte rows, SWIZZLE_64B, 2 MMAs of 32 bytes of K per
+  // (chunk, tap)): a chunk is 16 fp32 channels instead of 32 bf16 channels, so only the chunk counts double.
+  constexpr int CH = kTf32 ? 16 : kChunkK;                             // channels per 64-byte chunk
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;                                   // pixel halos
@@ -746,7 +751,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             ptx::mbar_wait(a_empty0 + 8u * sa, a_par);
             if (s == 0 && c == 0) CSD_TSP(11);
             ptx::mbar_arrive_expect_tx(a_full0 + 8u * sa, a_bytes);
-            ptx::tma_load_4d(a_base + sa * p.a_stage_bytes, mapA, a_full0 + 8u * sa, p.seg_coff[s] + c * kChunkK,
+            ptx::tma_load_4d(a_base + sa * p.a_stage_bytes, mapA, a_full0 + 8u * sa, p.seg_coff[s] + c * CH,
                              tc.w0 - halo, tc.h0 - halo, tc.b);
             if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
           }
@@ -765,9 +770,9 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         for (int s = 0; s < p.nseg; ++s) {
           const int taps = p.seg_taps[s];
           const int nchunks = p.seg_chunks[s];
-          const int kstep = nchunks * kChunkK;
+          const int kstep = ((p.seg_ccnt[s] + kChunkK - 1) / kChunkK) * kChunkK;   // K columns of one tap in Wt (ceil32)
           for (int c = 0; c < nchunks; ++c) {
-            int kcol = p.wt_k_off + (p.seg_kbase[s] + c) * kChunkK;
+            int kcol = p.wt_k_off + p.seg_kbase[s] * kChunkK + c * CH;
             for (int tap = 0; tap < taps; ++tap, kcol += kstep) {
               if (p.debug_nodata & 1) continue;   // perf experiment: no weight traffic
               if (turn == me) {
@@ -785,8 +790,12 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16_m128((uint32_t)p.t_pix);
+      const uint32_t idesc = kTf32 ? ptx::make_idesc_tf32_m128((uint32_t)p.t_pix) : ptx::make_idesc_bf16_m128((uint32_t)p.t_pix);
       const uint32_t w_hi = ptx::smem_desc_hi(512, kLayoutSw64);
+      auto mma = [](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
+        if (kTf32) ptx::mma_tf32_ss(d, ad, bd, id, acc);
+        else ptx::mma_bf16_ss(d, ad, bd, id, acc);
+      };
       const uint32_t a_go0 = p.has_norm ? a_ready0 : a_full0;
       uint32_t sa = 0, a_par = 0, sb = 0, b_par = 0;
       uint32_t acc = 0, acc_par = 1;   // a fresh tmem_empty barrier passes a wait on parity 1
@@ -819,10 +828,8 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 b_ready = ptx::mbar_test_wait(b_full0 + 8u * nsb, nb_par);
                 const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
                 const uint32_t x_lo = x_lo0 + (uint32_t)((((tap / 3) * pitch + (tap % 3)) * kRowBytes) >> 4);
-                ptx::mma_bf16_ss(d_tmem, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi, x_lo), idesc,
-                                 accumulate);
-                ptx::mma_bf16_ss(d_tmem, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi, x_lo + 2),
-                                 idesc, 1u);
+                mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi, x_lo), idesc, accumulate);
+                mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi, x_lo + 2), idesc, 1u);
                 accumulate = 1u;
                 ptx::mma_commit(b_empty0 + 8u * sb);
                 sb = nsb;
@@ -839,10 +846,8 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
               ptx::tcgen05_fence_after();
               const uint32_t x_lo = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
               const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
-              ptx::mma_bf16_ss(d_tmem, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi, x_lo), idesc,
-                               accumulate);
-              ptx::mma_bf16_ss(d_tmem, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi, x_lo + 2),
-                               idesc, 1u);
+              mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi, x_lo), idesc, accumulate);
+              mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi, x_lo + 2), idesc, 1u);
               accumulate = 1u;
               ptx::mma_commit(b_empty0 + 8u * sb);
               if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
@@ -875,7 +880,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           asm volatile("bar.sync 2, 256;" ::: "memory");
           int base = 0;
           for (int s = 0; s < p.nseg; ++s) {
-            const int nch = p.seg_chunks[s] * kChunkK;
+            const int nch = p.seg_chunks[s] * CH;
             const float2* src = reinterpret_cast<const float2*>(p.seg_norm[s]);
             const float pre = p.seg_silu[s] ? 0.5f : 1.0f;     // SiLU path stores (sc/2, sh/2)
             for (int i = tt; i < nch; i += kPTransformThreads) {
@@ -900,9 +905,12 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             if (tt == 0 && s == 0 && c == 0) CSD_TSP(8);
             if (norm) {
               uint4* st = reinterpret_cast<uint4*>(__cvta_shared_to_generic(a_base + sa * p.a_stage_bytes));
+              // (scale, shift) pairs of this thread's 16-byte unit: 8 bf16 channels (4 float4) or 4 fp32 channels (2)
+              constexpr int NCF = kTf32 ? 2 : 4;
               float4 cf[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) cf[i] = *reinterpret_cast<const float4*>(tab + base + c * kChunkK + j * 8 + 2 * i);
+              for (int i = 0; i < NCF; ++i)
+                cf[i] = *reinterpret_cast<const float4*>(tab + base + c * CH + j * (2 * NCF) + 2 * i);
               auto row_unit = [&](int r) -> int {     // 16-byte unit index of this thread's channels in row r, or -1
                 const int hy = halo ? r / (kHaloTW + 2) : (r >> 3);
                 const int hx = r - hy * pitch;
@@ -911,6 +919,23 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 return ok ? r * 4 + (j ^ ((r >> 1) & 3)) : -1;                          // SWIZZLE_64B unit
               };
               auto apply = [&](uint4 raw) -> uint4 {
+                if (kTf32) {      // 4 fp32 channels; the result feeds the tensor core only: rounded to tf32 (nearest)
+                  float f[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z),
+                                __uint_as_float(raw.w)};
+#pragma unroll
+                  for (int i = 0; i < 2; ++i) {
+                    float y0 = fmaf(f[2 * i], cf[i].x, cf[i].y), y1 = fmaf(f[2 * i + 1], cf[i].z, cf[i].w);
+                    if (act) {    // coefficients are pre-halved: y = h + h * tanh(h) would cost 2^-11; use the exact form
+                      y0 = 2.f * y0; y1 = 2.f * y1;
+                      y0 = y0 / (1.f + __expf(-y0));
+                      y1 = y1 / (1.f + __expf(-y1));
+                    }
+                    f[2 * i] = round_tf32(y0);
+                    f[2 * i + 1] = round_tf32(y1);
+                  }
+                  return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                                    __float_as_uint(f[3]));
+                }
                 bf16x8 v;
                 *reinterpret_cast<uint4*>(&v) = raw;
                 float f[8];
@@ -947,10 +972,104 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             if (tt == 0 && s == 0 && c == 0) CSD_TSP(9);
             if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
           }
-          base += p.seg_chunks[s] * kChunkK;
+          base += p.seg_chunks[s] * CH;
         }
       }
     }
+  } else if (kTf32) {
+    // ===== epilogue, fp32 output (8 warps) =====
+    // Same thread <-> channel mapping as the bf16 epilogue below. An fp32 [256 pixels x 128 channels] staging tile would
+    // be 128 KB, so the tile leaves in two passes of 64 channels through a [256 x 64] fp32 tile (64 KB): pass h is
+    // staged by the warps of lane quadrants 2h and 2h + 1 and written with one TMA store while the other quadrants
+    // wait. The residual of the fp32 plan is added here from global memory (an identity K segment would be truncated to
+    // tf32 by the tensor core and bias the residual stream of every block towards zero).
+    const int et = threadIdx.x - 320;
+    const int q = warp & 3;
+    const int half = (warp - 10) >> 2;
+    const int cl = q * 32 + lane;
+    float* stage = reinterpret_cast<float*>(__cvta_shared_to_generic(stage_base));
+    const int spitch = p.out_box_c;                   // <= 64 channels per pass
+    const int half_pix = p.t_pix >> 1;
+    const bool has_stats = p.stat_partials != nullptr;
+    const float scale = p.scale;
+    const float* res = reinterpret_cast<const float*>(p.res);
+    uint32_t acc = 0, full_par = 0;
+    bool store_pending = false;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int c = tc.n0 + cl;
+      const int cb = min(kTChan, p.n_store - tc.n0);
+      const bool c_valid = cl < cb;
+      const float add_cs = c_valid ? scale * ((p.bias != nullptr ? __ldg(p.bias + c) : 0.f) +
+                                              (p.temb != nullptr ? __ldg(p.temb + (long long)tc.b * p.temb_pitch + c) : 0.f))
+                                   : 0.f;
+      const int w_lim = min(kHaloTW, p.W - tc.w0);
+      const int m_lim_h = (w_lim == kHaloTW) ? min(half_pix, min(p.t_pix, (p.H - tc.h0) * kHaloTW) - half * half_pix) : 0;
+      ptx::mbar_wait(tmem_full0 + 8u * acc, full_par);
+      ptx::tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + acc * kTPix + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * half_pix);
+      float s1 = 0.f, s2 = 0.f;
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass * 64 >= cb) break;                               // uniform over the CTA
+        if (et == 0 && store_pending) ptx::bulk_wait_group_read0();
+        asm volatile("bar.sync 1, 256;" ::: "memory");            // staging tile free
+        if ((q >> 1) == pass && c_valid) {
+          float* sp0 = stage + (half * half_pix) * spitch + (cl - pass * 64);
+#pragma unroll 1
+          for (int col = 0; col < half_pix; col += 16) {
+            uint32_t r0[16];
+            __syncwarp();
+            ptx::tmem_ld_x16(t_row + col, r0);
+            // residual of the columns' pixels (column = 8 * tile row + x): issued before the TMEM wait
+            float rv[16];
+            if (res != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int pc = half * half_pix + col + i;
+                const int gh = tc.h0 + (pc >> 3), gw = tc.w0 + (pc & 7);
+                rv[i] = (col + i < m_lim_h) ? __ldg(res + (((long long)tc.b * p.H + gh) * p.W + gw) * p.res_pitch + c) : 0.f;
+              }
+            }
+            ptx::tmem_ld_wait();
+            float* sp = sp0 + col * spitch;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float v = fmaf(__uint_as_float(r0[i]), scale, add_cs);
+              if (res != nullptr) v = fmaf(rv[i], scale, v);
+              if (col + i < m_lim_h) {
+                s1 += v;
+                s2 = fmaf(v, v, s2);
+              }
+              if (col + i < half_pix) sp[i * spitch] = v;
+            }
+          }
+        } else if ((q >> 1) == pass) {
+          // channel beyond n_store: nothing to stage, but the TMEM loads are warp-collective
+#pragma unroll 1
+          for (int col = 0; col < half_pix; col += 16) {
+            uint32_t r0[16];
+            __syncwarp();
+            ptx::tmem_ld_x16(t_row + col, r0);
+            ptx::tmem_ld_wait();
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+          ptx::tma_store_4d(&mapOut, stage_base, tc.n0 + pass * 64, tc.w0, tc.h0, tc.b);
+          ptx::bulk_commit_group();
+        }
+        store_pending = true;
+      }
+      ptx::tcgen05_fence_before();
+      ptx::mbar_arrive(tmem_empty0 + 8u * acc);
+      if (++acc == 2u) { acc = 0; full_par ^= 1u; }
+      if (has_stats && c_valid) {
+        float2* sp2 = reinterpret_cast<float2*>(p.stat_partials) + ((long long)(tc.sp * 2 + half) * p.n_store + c);
+        *sp2 = make_float2(s1, s2);
+      }
+    }
+    if (et == 0 && store_pending) ptx::bulk_wait_group0();
   } else {
     // ===== epilogue (8 warps) =====
     // TMEM lane = output channel, column = pixel. Warp w reads lane quadrant w % 4 (the hardware's TMEM access
@@ -1101,8 +1220,10 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   const bool tf32 = d->dtype == 1;
   const int E = tf32 ? 4 : 2;                 // bytes per activation / weight element
   CSD_REQUIRE(d->dtype == 0 || d->dtype == 1, "conv_gemm: dtype=%d (0 = bf16, 1 = fp32 storage / tf32 operands)", d->dtype);
-  CSD_REQUIRE(!tf32 || (!halo_mode && d->out_f32 == 1),
-              "conv_gemm: the fp32 / tf32 plan runs in the per-tap kernel (mode 0) and writes fp32");
+  CSD_REQUIRE(!tf32 || ((!halo_mode || t_mode) && d->out_f32 == 1),
+              "conv_gemm: the fp32 / tf32 plan runs in the per-tap kernel (mode 0) or the transposed kernel (mode 2) and "
+              "writes fp32");
+  const int halo_chunk = tf32 ? 16 : kChunkK;     // channels per 64-byte halo chunk
   L->tf32 = tf32;
   L->halo = halo_mode;
   L->transposed = t_mode;
@@ -1114,8 +1235,8 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   CSD_REQUIRE(!halo_mode || (d->z_batches == 1 && (d->stride <= 1) && d->pad == 1 && mt >= 1 && mt <= 4 &&
                              (t_mode || mt * d->n_tile <= 512)),
               "halo mode needs stride 1, pad 1, no z batching and mt*n_tile <= 512 (mt=%d n_tile=%d)", mt, d->n_tile);
-  CSD_REQUIRE(!t_mode || (d->out_f32 == 0 && d->bias_per_row == 0),
-              "transposed halo mode writes bf16 with per-channel bias only");
+  CSD_REQUIRE(!t_mode || (d->out_f32 == (tf32 ? 1 : 0) && d->bias_per_row == 0),
+              "transposed halo mode writes bf16 (fp32 in the tf32 plan) with per-channel bias only");
   CSD_REQUIRE(d->n_tile >= 16 && d->n_tile % 16 == 0 && d->n_tile <= 512, "n_tile=%d invalid", d->n_tile);
   CSD_REQUIRE(d->n >= 1 && d->n_store >= 1, "n=%d n_store=%d invalid", d->n, d->n_store);
   CSD_REQUIRE(d->out != nullptr && d->wt != nullptr, "null out / wt pointer");
@@ -1171,13 +1292,13 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   int k_total_chan = 0;  // padded channels over all segments (one (scale, shift) slot each)
   for (int s = 0; s < d->nseg; ++s) {
     const csd_conv_segment& sg = d->seg[s];
-    k_total_chan += ceil_div(sg.c_cnt, kChunkK) * kChunkK;
+    k_total_chan += ceil_div(sg.c_cnt, halo_chunk) * halo_chunk;
     CSD_REQUIRE(sg.a != nullptr, "segment %d: null tensor", s);
     CSD_REQUIRE(sg.taps == 1 || sg.taps == 9, "segment %d: taps=%d (1 or 9)", s, sg.taps);
     CSD_REQUIRE(sg.pitch % 8 == 0 && sg.c_cnt >= 1 && sg.c_off >= 0 && sg.c_off + sg.c_cnt <= sg.pitch,
                 "segment %d: bad channel range off=%d cnt=%d pitch=%d", s, sg.c_off, sg.c_cnt, sg.pitch);
     p.seg_taps[s] = sg.taps;
-    p.seg_chunks[s] = ceil_div(sg.c_cnt, halo_mode ? kChunkK : tap_chunk);
+    p.seg_chunks[s] = ceil_div(sg.c_cnt, halo_mode ? halo_chunk : tap_chunk);
     p.seg_coff[s] = sg.c_off;
     p.seg_kbase[s] = k_total / kChunkK;
     k_total += sg.taps * ceil_div(sg.c_cnt, kChunkK) * kChunkK;
@@ -1196,7 +1317,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     uint64_t strides[3] = {(uint64_t)sg.pitch * E, (uint64_t)sg.pitch * E * in_w,
                            (uint64_t)sg.pitch * E * in_w * in_h};
     // with a traversal stride s the box spans (t-1)*s+1 source elements and delivers t of them
-    uint32_t box[4] = {(uint32_t)(halo_mode ? kChunkK : tap_chunk), (uint32_t)((p.TW - 1) * p.stride + 1),
+    uint32_t box[4] = {(uint32_t)(halo_mode ? halo_chunk : tap_chunk), (uint32_t)((p.TW - 1) * p.stride + 1),
                        (uint32_t)((p.TH - 1) * p.stride + 1), (uint32_t)p.TB};
     if (halo_mode) {  // whole halo of the mt stacked tiles (a 1-tap segment needs no halo)
       const int hl = sg.taps == 9 ? 1 : 0;
@@ -1217,7 +1338,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     const uint64_t row_bytes = (uint64_t)(d->wt_pitch > 0 ? d->wt_pitch : d->k_total) * E;
     uint64_t strides[2] = {row_bytes, d->wt_batch_stride != 0 ? (uint64_t)d->wt_batch_stride * E
                                                                : row_bytes * (uint64_t)d->wt_rows};
-    uint32_t box[3] = {(uint32_t)(halo_mode ? kChunkK : tap_chunk), (uint32_t)(t_mode ? kTChan : p.n_sub), 1};
+    uint32_t box[3] = {(uint32_t)(halo_mode ? halo_chunk : tap_chunk), (uint32_t)(t_mode ? kTChan : p.n_sub), 1};
     int st = encode_tensor_map(&L->mapB, tm_dtype, 3, d->wt, dims, strides, box,
                                (!halo_mode && tap_row_bytes == 128) ? TMA_SW_128 : TMA_SW_64);
     if (st != CSD_OK) return st;
@@ -1312,14 +1433,17 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
       L->smem = fixed + (size_t)pbs * p.b_stage_bytes;
       const int sms = num_sms();
       L->grid = dim3((unsigned)std::min(p.num_tiles, sms), 1, 1);
-      CSD_REQUIRE(d->res == nullptr, "transposed conv: pass the residual as a 1-tap segment with identity weights");
-      // TMA store map over out [batch, h, w, out_pitch], box = 128 (or n_store) channels x 8 x 32 pixels
-      p.out_box_c = std::min(kTChan, d->n_store);
+      CSD_REQUIRE(d->res == nullptr || tf32,
+                  "transposed conv (bf16): pass the residual as a 1-tap segment with identity weights");
+      CSD_REQUIRE(d->res == nullptr || d->res_pitch >= d->n_store, "transposed conv: residual pitch %d", d->res_pitch);
+      // TMA store map over out [batch, h, w, out_pitch], box = 128 (or n_store) channels x 8 x 32 pixels; the fp32
+      // plan stores 64 channels per pass
+      p.out_box_c = std::min(tf32 ? 64 : kTChan, d->n_store);
       uint64_t odims[4] = {(uint64_t)d->n_store, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->batch};
-      uint64_t ostr[3] = {(uint64_t)d->out_pitch * 2, (uint64_t)d->out_pitch * 2 * d->w,
-                          (uint64_t)d->out_pitch * 2 * d->w * d->h};
+      uint64_t ostr[3] = {(uint64_t)d->out_pitch * E, (uint64_t)d->out_pitch * E * d->w,
+                          (uint64_t)d->out_pitch * E * d->w * d->h};
       uint32_t obox[4] = {(uint32_t)p.out_box_c, (uint32_t)kHaloTW, (uint32_t)p.t_rows, 1};
-      int st = encode_tensor_map(&L->mapOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out, odims, ostr, obox, TMA_SW_NONE);
+      int st = encode_tensor_map(&L->mapOut, tm_dtype, 4, d->out, odims, ostr, obox, TMA_SW_NONE);
       if (st != CSD_OK) return st;
     }
   }
@@ -1340,12 +1464,16 @@ int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
     CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CSD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CSD_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CSD_CUDA(cudaFuncSetAttribute(conv_halo_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(conv_halo_tp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CSD_CUDA(cudaFuncSetAttribute(conv_halo_tp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  if (L->persistent) {
-    conv_halo_tp_kernel<<<L->grid, kPThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
-                                                                   L->mapB, L->mapOut, L->p);
+  if (L->persistent && L->tf32) {
+    conv_halo_tp_kernel<true><<<L->grid, kPThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
+                                                                         L->mapB, L->mapOut, L->p);
+  } else if (L->persistent) {
+    conv_halo_tp_kernel<false><<<L->grid, kPThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
+                                                                          L->mapB, L->mapOut, L->p);
   } else if (L->halo) {
     conv_halo_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
                                                                  L->mapB, L->p);

@@ -305,6 +305,9 @@ class Recorder:
 # 3 (default) = tap-stacked: ONE 1x1 convolution to 9 * Cout rows in the transposed kernel (fused GroupNorm prologue, no
 # halo, 54 of 128 M rows for the 6-channel heads) + csd_tap_shift_sum (shifted sum of the 9 partial maps, bias, pyramid).
 HEAD_MODE = int(os.environ.get("CSD_HEAD_MODE", "3"))
+# fp32 (tf32) plan: 3x3 convolutions of the large levels in the transposed kernel's kind::tf32 instance (fused GroupNorm
+# prologue, epilogue statistics, fp32 residual in the epilogue); 0 = everything in the per-tap tf32 kernel.
+TF32_TRANSPOSED = os.environ.get("CSD_NO_TF32_TRANSPOSED", "0") != "1"
 
 
 class BlockOps:
@@ -413,14 +416,18 @@ class BlockOps:
 
     def will_transpose(self, h, w, cout):
         """3x3 stride-1 convolutions with >= 32 output channels on images that tile into 32x8-pixel macro tiles
-        run in the persistent transposed kernel (output channels on M, 256 pixels on N) - bf16 plan only."""
-        return (self.act_dtype == BF16 and K.TRANSPOSED_DEFAULT and cout >= 32 and cout % 8 == 0
-                and K.transposed_shape_ok(h, w))
+        run in the persistent transposed kernel (output channels on M, 256 pixels on N); the fp32 plan runs its
+        kind::tf32 instance (CSD_NO_TF32_TRANSPOSED=1 keeps the per-tap kernel: A/B switch)."""
+        if self.act_dtype != BF16 and not TF32_TRANSPOSED:
+            return False
+        return K.TRANSPOSED_DEFAULT and cout >= 32 and cout % 8 == 0 and K.transposed_shape_ok(h, w)
 
     def fusable(self, srcs, cout):
         """GroupNorm+SiLU can ride in the convolution's prologue when the 3x3 conv runs in the transposed mode."""
         _, h, w, _ = srcs[0].shape
-        return (self.act_dtype == BF16 and K.FUSE_GN_DEFAULT and K.TRANSPOSED_DEFAULT and cout >= 32 and cout % 8 == 0
+        if self.act_dtype != BF16 and not TF32_TRANSPOSED:
+            return False
+        return (K.FUSE_GN_DEFAULT and K.TRANSPOSED_DEFAULT and cout >= 32 and cout % 8 == 0
                 and K.transposed_shape_ok(h, w) and all(a.c % 8 == 0 for a in srcs))
 
     def conv(self, segs, pc, out_hw=None, temb=None, temb_pitch=0, res=None, scale=1.0, stride=1, pad=1,
@@ -436,7 +443,7 @@ class BlockOps:
         seg_list = [(sg[0].t, sg[0].pitch, 0, sg[0].c, sg[1], sg[2] if len(sg) > 2 else None, True) for sg in segs]
         use_t = ((head or self.will_transpose(oh, ow, pc.cout))
                  and K.transposed_eligible(seg_list, oh, ow, stride, pad, allow_1tap=head))
-        if use_t and res is not None:
+        if use_t and res is not None and self.act_dtype == BF16:
             raise CsdError("transposed conv takes its residual as an identity K segment (engine planning error)")
         partials = sums = None
         if use_t and not head:
@@ -1059,7 +1066,9 @@ class NetPlan:
         def resblock(idx, srcs):
             p = dict(pk[idx])
             _, sh, sw, _ = srcs[0].shape
-            ident = ops.will_transpose(sh, sw, p["out_ch"])
+            # bf16: the residual rides as an identity K segment (exact); fp32 plan: the tensor core would truncate it to
+            # tf32, so it is added in the epilogue instead
+            ident = ops.will_transpose(sh, sw, p["out_ch"]) and ops.act_dtype == BF16
             p["conv1"] = eng.finish_resblock(pk[idx], [a.c for a in srcs], dev, identity_skip=ident)
             p["conv0_split"] = eng.finish_conv0(pk[idx], [a.c for a in srcs], dev)
             return ops.resblock(p, srcs, tproj if p["temb_off"] is not None else None, tpitch, None, False)
@@ -1184,7 +1193,7 @@ class NetPlan:
         def resblock(idx, srcs):
             p = pk[idx]
             _, sh, sw, _ = srcs[0].shape
-            ident = (not (p["up"] or p["down"])) and ops.will_transpose(sh, sw, p["out_ch"])
+            ident = (not (p["up"] or p["down"])) and ops.will_transpose(sh, sw, p["out_ch"]) and ops.act_dtype == BF16
             pc1 = eng.finish_resblock(p, [a.c for a in srcs], dev, identity_skip=ident)
             p = dict(p)
             p["conv1"] = pc1

@@ -161,10 +161,11 @@ def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None
         n_tile = n16 if n16 <= 256 else (ceil_to(n16 // 2, 16) if n16 <= 512 else 256)
     d.n_tile = n_tile
     if tf32:
-        if transposed or halo:
-            raise _lib.CsdError("the fp32 / tf32 plan runs in the per-tap kernel only")
+        if halo:
+            raise _lib.CsdError("the fp32 / tf32 plan runs in the per-tap and the transposed kernels only")
         assert wt.dtype == torch.float32 and out.dtype == torch.float32 and (res is None or res.dtype == torch.float32)
-        halo = transposed = False
+        halo = False
+        transposed = bool(transposed)
         d.dtype = 1
         d.out_round_tf32 = int(bool(round_out))
     if halo is None:

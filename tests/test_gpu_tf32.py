@@ -302,3 +302,119 @@ def test_tf32_network_small_golden():
     rel = _rel(o2.cpu(), f2["out"])
     print(f"[tf32 net] golden ncsnpp cifar: rel={rel:.3e}")
     assert rel < TF32_NET_RTOL
+
+
+# ---- the transposed kernel's kind::tf32 instance (fused GroupNorm prologue, epilogue statistics, fp32 residual) ------
+def _tp_case(name, B, H, W, cins, cout, seed=0, silu=True, skip_c=0, norm=True, res=False, temb=False, scale=1.0):
+    k = _k()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(seed)
+    xs, coefs, normed = [], [], []
+    for c in cins:
+        x = torch.randn(B, c, H, W, device=dev, generator=g)
+        sc = torch.rand(B, c, device=dev, generator=g) + 0.5
+        sh = torch.randn(B, c, device=dev, generator=g)
+        y = x * sc[:, :, None, None] + sh[:, :, None, None] if norm else x
+        if norm and silu:
+            y = F.silu(y)
+        xs.append(x)
+        coefs.append(torch.stack([sc, sh], dim=-1).contiguous() if norm else None)
+        normed.append(y)
+    cin = sum(cins)
+    wgt = torch.randn(cout, cin, 3, 3, device=dev, generator=g) / math.sqrt(9 * cin)
+    ref = F.conv2d(torch.cat(normed, 1), wgt, padding=1)
+    parts, off = [], 0
+    for c in cins:
+        parts.append(k.pack_conv_weight(wgt[:, off:off + c], dtype=torch.float32))
+        off += c
+    segs = [(_nhwc(x), c, 0, c, 9, cf, silu) for x, c, cf in zip(xs, cins, coefs)]
+    if skip_c:
+        xr = torch.randn(B, skip_c, H, W, device=dev, generator=g)
+        w1 = torch.randn(cout, skip_c, 1, 1, device=dev, generator=g) / math.sqrt(skip_c)
+        ref = ref + F.conv2d(xr, w1)
+        parts.append(k.pack_conv_weight(w1, dtype=torch.float32))
+        segs.append((_nhwc(xr), skip_c, 0, skip_c, 1))
+    wt = torch.cat(parts, dim=1).contiguous()
+    npad = wt.shape[0]
+    bias_t = torch.zeros(npad + 16, device=dev)
+    bias_t[:cout] = torch.randn(cout, device=dev, generator=g)
+    ref = ref + bias_t[:cout].view(1, -1, 1, 1)
+    temb_t = res_t = None
+    if temb:
+        temb_t = torch.zeros(B, npad + 16, device=dev)
+        temb_t[:, :cout] = torch.randn(B, cout, device=dev, generator=g)
+        ref = ref + temb_t[:, :cout].reshape(B, cout, 1, 1)
+    if res:
+        r = torch.randn(B, cout, H, W, device=dev, generator=g) * 3
+        res_t = _nhwc(r)
+        ref = ref + r
+    ref = ref * scale
+    out = torch.full((B, H, W, cout), float("nan"), device=dev)
+    tiles_img = math.ceil(H / k.transposed_tile_rows(H)) * math.ceil(W / 8) * 2
+    partials = torch.full((B * tiles_img, cout, 2), float("nan"), device=dev)
+    k.conv_gemm(segs, wt, cout, out, batch=B, h=H, w=W, bias=bias_t, temb=temb_t, temb_pitch=npad + 16, res=res_t,
+                res_pitch=cout, scale=scale, transposed=True, stat_partials=partials)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all(), f"{name}: non-finite output"
+    rel = _rel(out.permute(0, 3, 1, 2), ref)
+    sums = torch.empty(B, cout, 2, device=dev)
+    k.gn_finalize_partials(partials, sums, B, tiles_img, cout)
+    o = out.permute(0, 3, 1, 2)
+    ref_s = torch.stack([o.sum((2, 3)), (o * o).sum((2, 3))], -1)
+    rel_s = _rel(sums, ref_s)
+    print(f"[tf32 transposed] {name}: rel={rel:.3e} stats rel={rel_s:.3e}")
+    assert rel < TF32_RTOL, f"{name}: rel {rel:.3e}"
+    assert rel_s < 1e-4, f"{name}: epilogue statistics {rel_s:.3e}"
+
+
+def test_tf32_transposed_kernel():
+    _tp_case("96->96 32x32 plain", 2, 32, 32, [96], 96, norm=False)
+    _tp_case("96->96 32x32 GN+SiLU +temb", 2, 32, 32, [96], 96, temb=True)
+    _tp_case("96->96 80x80 (28-row tiles) +res*0.707", 2, 80, 80, [96], 96, seed=1, res=True, scale=1 / math.sqrt(2))
+    _tp_case("64->96 24x24 padded cin", 2, 24, 24, [64], 96, seed=2)
+    _tp_case("(96+96)->96 64x64 cat + skip conv", 2, 64, 64, [96, 96], 96, seed=3, skip_c=192, scale=1 / math.sqrt(2))
+    _tp_case("(192+96)->192 32x32 cat (two 128-row blocks)", 2, 32, 32, [192, 96], 192, seed=4, skip_c=288)
+    _tp_case("192->192 32x32 affine only +res", 2, 32, 32, [192], 192, seed=5, silu=False, res=True)
+    _tp_case("(192+192)->192 40x40 20-row tiles", 2, 40, 40, [192, 192], 192, seed=6, skip_c=384)
+    _tp_case("96->96 160x160", 1, 160, 160, [96], 96, seed=7, temb=True, res=True, scale=1 / math.sqrt(2))
+    _tp_case("288->288 64x64 (three blocks, 64 + 32 channel tail)", 1, 64, 64, [288], 288, seed=8, res=True)
+
+
+def test_tf32_network_transposed_vs_per_tap(monkeypatch):
+    """The 64 px / nf 32 network of test_gpu_network through the tf32 plan with and without the transposed kernel: both
+    within the tf32 tolerance of the oracle, and close to each other."""
+    from golden_utils import golden, to_namespace
+    from conditional_score_diffusion_b200 import engine
+    from conditional_score_diffusion_b200.models import ncsnpp, utils  # noqa: F401
+    from oracle import ncsnpp as o_net
+    f = golden()["ncsnpp_paired"]
+    cfg = to_namespace(f["config"])
+    cfg.data.image_size = cfg.data.effective_image_size = 64
+    cfg.model.nf = 32
+    cfg.model.attn_resolutions = (16,)
+    torch.manual_seed(41)
+    m0 = utils.create_model(cfg)
+    g = torch.Generator().manual_seed(42)
+    with torch.no_grad():
+        for pn, p in m0.named_parameters():
+            if pn.endswith("bias") or pn.endswith(".b"):
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    sd = {k_: v.detach().clone() for k_, v in m0.state_dict().items()}
+    x = torch.randn(3, 3, 64, 64, generator=g) * 5
+    y = torch.rand(3, 3, 64, 64, generator=g)
+    labels = torch.rand(3, generator=g) * 999
+    ref = o_net.forward_paired(sd, o_net.model_options(cfg), x, y, labels)
+    outs = {}
+    for tp in (True, False):
+        monkeypatch.setattr(engine, "TF32_TRANSPOSED", tp)
+        m = utils.create_model(cfg)
+        m.load_state_dict(sd)
+        m = m.cuda().eval().set_precision("tf32")
+        with torch.no_grad():
+            outs[tp] = m({"x": x.cuda(), "y": y.cuda()}, labels.cuda())
+        names = [getattr(fn, "__name__", "") for fn, _, _ in next(iter(m._engine.plans.values())).rec.ops]
+        assert ("gn_coeffs_partials" in names or "gn_coeffs" in names) == tp
+        for key in ("x", "y"):
+            rel = _rel(outs[tp][key].cpu(), ref[key])
+            print(f"[tf32 net 64px] transposed={tp} {key}: rel={rel:.3e}")
+            assert rel < TF32_NET_RTOL
