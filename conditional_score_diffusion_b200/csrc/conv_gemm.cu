@@ -979,22 +979,22 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   } else if (kTf32) {
     // ===== epilogue, fp32 output (8 warps) =====
     // Same thread <-> channel mapping as the bf16 epilogue below. An fp32 [256 pixels x 128 channels] staging tile would
-    // be 128 KB, so the tile leaves in two passes of 64 channels through a [256 x 64] fp32 tile (64 KB): pass h is
-    // staged by the warps of lane quadrants 2h and 2h + 1 and written with one TMA store while the other quadrants
-    // wait. The residual of the fp32 plan is added here from global memory (an identity K segment would be truncated to
-    // tf32 by the tensor core and bias the residual stream of every block towards zero).
+    // be 128 KB, so the tile leaves in up to four passes of 32 channels (one lane quadrant each) through two
+    // [256 x 32] fp32 staging tiles (2 x 32 KB): pass q is staged by the two warps of quadrant q while the TMA store of
+    // pass q - 1 drains from the other tile. The residual of the fp32 plan is added here from global memory (an
+    // identity K segment would be truncated to tf32 by the tensor core and bias the residual stream of every block
+    // towards zero).
     const int et = threadIdx.x - 320;
     const int q = warp & 3;
     const int half = (warp - 10) >> 2;
     const int cl = q * 32 + lane;
-    float* stage = reinterpret_cast<float*>(__cvta_shared_to_generic(stage_base));
-    const int spitch = p.out_box_c;                   // <= 64 channels per pass
+    constexpr int kPassC = 32;                        // channels per pass = staging row pitch
     const int half_pix = p.t_pix >> 1;
     const bool has_stats = p.stat_partials != nullptr;
     const float scale = p.scale;
     const float* res = reinterpret_cast<const float*>(p.res);
     uint32_t acc = 0, full_par = 0;
-    bool store_pending = false;
+    int stores = 0;                                   // TMA stores issued so far (uniform over the CTA)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int c = tc.n0 + cl;
@@ -1009,12 +1009,15 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + acc * kTPix + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * half_pix);
       float s1 = 0.f, s2 = 0.f;
-      for (int pass = 0; pass < 2; ++pass) {
-        if (pass * 64 >= cb) break;                               // uniform over the CTA
-        if (et == 0 && store_pending) ptx::bulk_wait_group_read0();
-        asm volatile("bar.sync 1, 256;" ::: "memory");            // staging tile free
-        if ((q >> 1) == pass && c_valid) {
-          float* sp0 = stage + (half * half_pix) * spitch + (cl - pass * 64);
+      for (int pass = 0; pass < 4; ++pass) {
+        if (pass * kPassC >= cb) break;                           // uniform over the CTA
+        const uint32_t buf = (uint32_t)(stores & 1);
+        // the store issued two passes ago read from this staging tile: it must have drained (at most 1 newer pending)
+        if (et == 0 && stores >= 2) ptx::bulk_wait_group_read1();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (q == pass) {
+          float* sp0 = reinterpret_cast<float*>(__cvta_shared_to_generic(stage_base + buf * (kPStagingBytes / 2))) +
+                       (half * half_pix) * kPassC + lane;
 #pragma unroll 1
           for (int col = 0; col < half_pix; col += 16) {
             uint32_t r0[16];
@@ -1022,7 +1025,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             ptx::tmem_ld_x16(t_row + col, r0);
             // residual of the columns' pixels (column = 8 * tile row + x): issued before the TMEM wait
             float rv[16];
-            if (res != nullptr) {
+            if (res != nullptr && c_valid) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const int pc = half * half_pix + col + i;
@@ -1031,35 +1034,28 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
               }
             }
             ptx::tmem_ld_wait();
-            float* sp = sp0 + col * spitch;
+            if (c_valid) {
+              float* sp = sp0 + col * kPassC;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float v = fmaf(__uint_as_float(r0[i]), scale, add_cs);
-              if (res != nullptr) v = fmaf(rv[i], scale, v);
-              if (col + i < m_lim_h) {
-                s1 += v;
-                s2 = fmaf(v, v, s2);
+              for (int i = 0; i < 16; ++i) {
+                float v = fmaf(__uint_as_float(r0[i]), scale, add_cs);
+                if (res != nullptr) v = fmaf(rv[i], scale, v);
+                if (col + i < m_lim_h) {
+                  s1 += v;
+                  s2 = fmaf(v, v, s2);
+                }
+                if (col + i < half_pix) sp[i * kPassC] = v;
               }
-              if (col + i < half_pix) sp[i * spitch] = v;
             }
-          }
-        } else if ((q >> 1) == pass) {
-          // channel beyond n_store: nothing to stage, but the TMEM loads are warp-collective
-#pragma unroll 1
-          for (int col = 0; col < half_pix; col += 16) {
-            uint32_t r0[16];
-            __syncwarp();
-            ptx::tmem_ld_x16(t_row + col, r0);
-            ptx::tmem_ld_wait();
           }
         }
         ptx::fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
-          ptx::tma_store_4d(&mapOut, stage_base, tc.n0 + pass * 64, tc.w0, tc.h0, tc.b);
+          ptx::tma_store_4d(&mapOut, stage_base + buf * (kPStagingBytes / 2), tc.n0 + pass * kPassC, tc.w0, tc.h0, tc.b);
           ptx::bulk_commit_group();
         }
-        store_pending = true;
+        ++stores;
       }
       ptx::tcgen05_fence_before();
       ptx::mbar_arrive(tmem_empty0 + 8u * acc);
@@ -1069,7 +1065,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         *sp2 = make_float2(s1, s2);
       }
     }
-    if (et == 0 && store_pending) ptx::bulk_wait_group0();
+    if (et == 0 && stores > 0) ptx::bulk_wait_group0();
   } else {
     // ===== epilogue (8 warps) =====
     // TMEM lane = output channel, column = pixel. Warp w reads lane quadrant w % 4 (the hardware's TMEM access
@@ -1437,8 +1433,8 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
                   "transposed conv (bf16): pass the residual as a 1-tap segment with identity weights");
       CSD_REQUIRE(d->res == nullptr || d->res_pitch >= d->n_store, "transposed conv: residual pitch %d", d->res_pitch);
       // TMA store map over out [batch, h, w, out_pitch], box = 128 (or n_store) channels x 8 x 32 pixels; the fp32
-      // plan stores 64 channels per pass
-      p.out_box_c = std::min(tf32 ? 64 : kTChan, d->n_store);
+      // plan stores 32 channels per pass
+      p.out_box_c = std::min(tf32 ? 32 : kTChan, d->n_store);
       uint64_t odims[4] = {(uint64_t)d->n_store, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->batch};
       uint64_t ostr[3] = {(uint64_t)d->out_pitch * E, (uint64_t)d->out_pitch * E * d->w,
                           (uint64_t)d->out_pitch * E * d->w * d->h};

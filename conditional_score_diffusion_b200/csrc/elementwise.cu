@@ -92,6 +92,69 @@ fused_bias_act_kernel(const float* __restrict__ x, const float* __restrict__ bia
   }
 }
 
+// Vector form: one row = the step_b contiguous elements that share a bias entry (a channel plane of an NCHW tensor).
+// grid.y walks rows (bias index = row % size_b: no per-element division), grid.x x 256 threads stream the row with
+// 16-byte loads / stores, 4 independent vectors in flight per thread. Needs step_b % 4 == 0 and 16-byte aligned
+// pointers; anything else takes the scalar kernel above.
+__device__ __forceinline__ float bias_act_1(float v, float r, int act, int grad, float alpha, float scale) {
+  float o;
+  if (act == 3) {
+    if (grad == 0) o = v > 0.f ? v : v * alpha;
+    else if (grad == 1) o = r > 0.f ? v : v * alpha;
+    else o = 0.f;
+  } else {
+    o = grad == 2 ? 0.f : v;
+  }
+  return o * scale;
+}
+
+__global__ void __launch_bounds__(256)
+fused_bias_act_vec_kernel(const float4* __restrict__ x, const float* __restrict__ bias, const float4* __restrict__ ref,
+                          float4* __restrict__ y, long long rows, long long row_vec, int size_b, int act, int grad,
+                          float alpha, float scale) {
+  for (long long row = blockIdx.y; row < rows; row += gridDim.y) {
+    const float b = bias != nullptr ? __ldg(bias + (int)(row % size_b)) : 0.f;
+    const float4* xr = x + row * row_vec;
+    const float4* rr = ref != nullptr ? ref + row * row_vec : nullptr;
+    float4* yr = y + row * row_vec;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < row_vec; i += 4 * stride) {
+      float4 v[4], r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint4 t = ldg_stream(xr + i + u * stride);
+        v[u] = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w));
+        r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rr != nullptr) {
+          const uint4 q = ldg_stream(rr + i + u * stride);
+          r[u] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float4 o;
+        o.x = bias_act_1(v[u].x + b, r[u].x, act, grad, alpha, scale);
+        o.y = bias_act_1(v[u].y + b, r[u].y, act, grad, alpha, scale);
+        o.z = bias_act_1(v[u].z + b, r[u].z, act, grad, alpha, scale);
+        o.w = bias_act_1(v[u].w + b, r[u].w, act, grad, alpha, scale);
+        stg_stream(yr + i + u * stride, make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z),
+                                                   __float_as_uint(o.w)));
+      }
+    }
+    for (; i < row_vec; i += stride) {
+      const float4 v = xr[i];
+      const float4 r = rr != nullptr ? rr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 o;
+      o.x = bias_act_1(v.x + b, r.x, act, grad, alpha, scale);
+      o.y = bias_act_1(v.y + b, r.y, act, grad, alpha, scale);
+      o.z = bias_act_1(v.z + b, r.z, act, grad, alpha, scale);
+      o.w = bias_act_1(v.w + b, r.w, act, grad, alpha, scale);
+      yr[i] = o;
+    }
+  }
+}
+
 // ---- PC updates ------------------------------------------------------------------------------------
 // Per-step / per-sample scalar lookup. Tables are [n_steps] (sample_stride = 0: one value per step,
 // shared by the batch) or [n_steps, batch] (sample_stride = 1). step_idx may be null (step 0), which
@@ -414,6 +477,22 @@ int csd_fused_bias_act_f32(const float* x, const float* bias, const float* refer
   CSD_REQUIRE(grad >= 0 && grad <= 2, "fused_bias_act: grad %d", grad);
   CSD_REQUIRE(bias == nullptr || (size_b >= 1 && step_b >= 1), "fused_bias_act: bad bias geometry");
   if (n == 0) return CSD_OK;
+  {
+    // rows of step_b contiguous elements sharing one bias entry (no bias: the whole tensor as rows of 64 K elements)
+    long long row = bias != nullptr ? step_b : 65536;
+    if (bias == nullptr && n % row != 0) row = 0;
+    if (row > 0 && row % 4 == 0 && n % row == 0 && vec4_ok(row, {x, refer, y})) {
+      const long long rows = n / row, row_vec = row / 4;
+      long long bx = std::max<long long>(1, std::min<long long>(row_vec / (256 * 4), 64));   // 4 vectors per thread in flight
+      long long by = std::max<long long>(1, std::min<long long>(rows, ceil_div_ll((long long)num_sms() * 16, bx)));
+      if (by > 65535) by = 65535;
+      fused_bias_act_vec_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          reinterpret_cast<const float4*>(x), bias, reinterpret_cast<const float4*>(refer), reinterpret_cast<float4*>(y),
+          rows, row_vec, bias != nullptr ? size_b : 1, act, grad, alpha, scale);
+      CSD_LAUNCH_CHECK("fused_bias_act_vec_kernel");
+      return CSD_OK;
+    }
+  }
   fused_bias_act_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, bias, refer, y, n, size_b, step_b,
                                                                                     act, grad, alpha, scale);
   CSD_LAUNCH_CHECK("fused_bias_act_kernel");
