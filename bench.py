@@ -707,8 +707,10 @@ def run_b200(args):
     parity = network_parity(cfg, model, dev)
 
     # ---- the reference-precision plan next to the bf16 one: fp32 activations in HBM, tcgen05 kind::tf32 operands ----
+    # (context legs - tf32 plan, stock reference on the GPU, other configs - run at N = 1 only: they are rank-0 work and
+    #  would only lengthen the multi-GPU runs, whose job is the scaling of `value`)
     tf32 = None
-    if not args.no_tf32:
+    if not args.no_tf32 and world == 1:
         try:
             tf32 = tf32_line(cfg, model, sde, shape, dev, min(k_eff, 10), B, world)
         except Exception as e:  # noqa: BLE001
@@ -717,7 +719,7 @@ def run_b200(args):
 
     # ---- stock PyTorch + cuDNN on the same GPU: the unmodified reference, B = 64 ----
     stock = None
-    if not args.no_stock_gpu:
+    if not args.no_stock_gpu and world == 1:
         try:
             stock = stock_gpu_steps(cfg, B, 5, 2, dev)
         except Exception as e:  # noqa: BLE001 - the leg is context; the b200 line must still print
@@ -725,7 +727,7 @@ def run_b200(args):
 
     # ---- the other BASELINE configs, briefly ----
     extras = None
-    if not args.no_extras:
+    if not args.no_extras and world == 1:
         del fs, graph
         torch.cuda.empty_cache()
         extras = other_configs(dev)

@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
 conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
-                    const ConvGemmKernelParams p) {
+                    const __grid_constant__ CUtensorMap mapOut2, const ConvGemmKernelParams p) {
   // kTf32: the reference-precision plan. Activations, weights and the output are fp32 words, the MMA is kind::tf32.
   // Every shared-memory structure keeps its BYTE geometry (64-byte rows, SWIZZLE_64B, 2 MMAs of 32 bytes of K per
   // (chunk, tap)): a chunk is 16 fp32 channels instead of 32 bf16 channels, so only the chunk counts double.
@@ -978,23 +978,26 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     }
   } else if (kTf32) {
     // ===== epilogue, fp32 output (8 warps) =====
-    // Same thread <-> channel mapping as the bf16 epilogue below. An fp32 [256 pixels x 128 channels] staging tile would
-    // be 128 KB, so the tile leaves in up to four passes of 32 channels (one lane quadrant each) through two
-    // [256 x 32] fp32 staging tiles (2 x 32 KB): pass q is staged by the two warps of quadrant q while the TMA store of
-    // pass q - 1 drains from the other tile. The residual of the fp32 plan is added here from global memory (an
-    // identity K segment would be truncated to tf32 by the tensor core and bias the residual stream of every block
-    // towards zero).
+    // Same thread <-> channel mapping as the bf16 epilogue below (thread = output channel, warps 10-13 the first half of
+    // the tile's pixel rows, warps 14-17 the second). An fp32 [256 pixels x 128 channels] staging tile would be 128 KB,
+    // so the tile leaves in two passes over the pixel rows: pass A = the first 8 rows of each half, pass B = the rest
+    // (8 / 6 / 4 / 2 rows for 32 / 28 / 24 / 20-row tiles), each through a [2 halves x 64 pixels x 128 channels] fp32
+    // staging tile (64 KB) and one TMA store per half (mapOut: 8-row boxes, mapOut2: the remainder rows). All 256
+    // threads work in both passes. The residual of the fp32 plan is added here from global memory (an identity K
+    // segment would be truncated to tf32 by the tensor core and bias the residual stream of every block towards zero).
     const int et = threadIdx.x - 320;
     const int q = warp & 3;
     const int half = (warp - 10) >> 2;
     const int cl = q * 32 + lane;
-    constexpr int kPassC = 32;                        // channels per pass = staging row pitch
-    const int half_pix = p.t_pix >> 1;
+    const int spitch = p.out_box_c;                   // staging row pitch = channels per store box
+    const int half_pix = p.t_pix >> 1, half_rows = p.t_rows >> 1;
+    float* stage_h = reinterpret_cast<float*>(__cvta_shared_to_generic(stage_base)) + half * (64 * spitch) + cl;
+    const uint32_t stage_h_addr = stage_base + (uint32_t)(half * 64 * spitch * 4);
     const bool has_stats = p.stat_partials != nullptr;
     const float scale = p.scale;
     const float* res = reinterpret_cast<const float*>(p.res);
     uint32_t acc = 0, full_par = 0;
-    int stores = 0;                                   // TMA stores issued so far (uniform over the CTA)
+    bool store_pending = false;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int c = tc.n0 + cl;
@@ -1009,53 +1012,50 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       ptx::tcgen05_fence_after();
       const uint32_t t_row = tmem_base + acc * kTPix + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * half_pix);
       float s1 = 0.f, s2 = 0.f;
-      for (int pass = 0; pass < 4; ++pass) {
-        if (pass * kPassC >= cb) break;                           // uniform over the CTA
-        const uint32_t buf = (uint32_t)(stores & 1);
-        // the store issued two passes ago read from this staging tile: it must have drained (at most 1 newer pending)
-        if (et == 0 && stores >= 2) ptx::bulk_wait_group_read1();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (q == pass) {
-          float* sp0 = reinterpret_cast<float*>(__cvta_shared_to_generic(stage_base + buf * (kPStagingBytes / 2))) +
-                       (half * half_pix) * kPassC + lane;
 #pragma unroll 1
-          for (int col = 0; col < half_pix; col += 16) {
-            uint32_t r0[16];
-            __syncwarp();
-            ptx::tmem_ld_x16(t_row + col, r0);
-            // residual of the columns' pixels (column = 8 * tile row + x): issued before the TMEM wait
-            float rv[16];
-            if (res != nullptr && c_valid) {
+      for (int pass = 0; pass < 2; ++pass) {
+        const int col0 = pass * 64, col1 = pass == 0 ? min(64, half_pix) : half_pix;
+        if (col0 >= col1) break;                                  // uniform over the CTA
+        if (lane == 0 && q == 0 && store_pending) ptx::bulk_wait_group_read0();   // (bulk groups are per thread)
+        asm volatile("bar.sync 1, 256;" ::: "memory");            // staging tile free
+#pragma unroll 1
+        for (int col = col0; col < col1; col += 16) {
+          uint32_t r0[16];
+          __syncwarp();
+          ptx::tmem_ld_x16(t_row + col, r0);
+          // residual of the columns' pixels (column = 8 * tile row + x): issued before the TMEM wait
+          float rv[16];
+          if (res != nullptr && c_valid) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int pc = half * half_pix + col + i;
-                const int gh = tc.h0 + (pc >> 3), gw = tc.w0 + (pc & 7);
-                rv[i] = (col + i < m_lim_h) ? __ldg(res + (((long long)tc.b * p.H + gh) * p.W + gw) * p.res_pitch + c) : 0.f;
-              }
+            for (int i = 0; i < 16; ++i) {
+              const int pc = half * half_pix + col + i;
+              const int gh = tc.h0 + (pc >> 3), gw = tc.w0 + (pc & 7);
+              rv[i] = (col + i < m_lim_h) ? __ldg(res + (((long long)tc.b * p.H + gh) * p.W + gw) * p.res_pitch + c) : 0.f;
             }
-            ptx::tmem_ld_wait();
-            if (c_valid) {
-              float* sp = sp0 + col * kPassC;
+          }
+          ptx::tmem_ld_wait();
+          if (c_valid) {
+            float* sp = stage_h + (col - col0) * spitch;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float v = fmaf(__uint_as_float(r0[i]), scale, add_cs);
-                if (res != nullptr) v = fmaf(rv[i], scale, v);
-                if (col + i < m_lim_h) {
-                  s1 += v;
-                  s2 = fmaf(v, v, s2);
-                }
-                if (col + i < half_pix) sp[i * kPassC] = v;
+            for (int i = 0; i < 16; ++i) {
+              float v = fmaf(__uint_as_float(r0[i]), scale, add_cs);
+              if (res != nullptr) v = fmaf(rv[i], scale, v);
+              if (col + i < m_lim_h) {
+                s1 += v;
+                s2 = fmaf(v, v, s2);
               }
+              if (col + i < col1) sp[i * spitch] = v;
             }
           }
         }
         ptx::fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et == 0) {
-          ptx::tma_store_4d(&mapOut, stage_base + buf * (kPStagingBytes / 2), tc.n0 + pass * kPassC, tc.w0, tc.h0, tc.b);
+        if (lane == 0 && q == 0) {                                // one thread per half issues that half's store
+          const int row0 = tc.h0 + half * half_rows + pass * 8;
+          if (row0 < p.H) ptx::tma_store_4d(pass == 0 ? &mapOut : &mapOut2, stage_h_addr, tc.n0, tc.w0, row0, tc.b);
           ptx::bulk_commit_group();
         }
-        ++stores;
+        store_pending = true;
       }
       ptx::tcgen05_fence_before();
       ptx::mbar_arrive(tmem_empty0 + 8u * acc);
@@ -1065,7 +1065,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         *sp2 = make_float2(s1, s2);
       }
     }
-    if (et == 0 && stores > 0) ptx::bulk_wait_group0();
+    if (lane == 0 && q == 0 && store_pending) ptx::bulk_wait_group0();
   } else {
     // ===== epilogue (8 warps) =====
     // TMEM lane = output channel, column = pixel. Warp w reads lane quadrant w % 4 (the hardware's TMEM access
@@ -1199,6 +1199,7 @@ struct ConvGemmLaunch {
   CUtensorMap mapA[CSD_MAX_SEGMENTS];
   CUtensorMap mapB;
   CUtensorMap mapOut;
+  CUtensorMap mapOut2;   // fp32 plan: store box of the remainder rows of a half tile (pass B)
   ConvGemmKernelParams p;
   dim3 grid;
   size_t smem;
@@ -1434,13 +1435,19 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
       CSD_REQUIRE(d->res == nullptr || d->res_pitch >= d->n_store, "transposed conv: residual pitch %d", d->res_pitch);
       // TMA store map over out [batch, h, w, out_pitch], box = 128 (or n_store) channels x 8 x 32 pixels; the fp32
       // plan stores 32 channels per pass
-      p.out_box_c = std::min(tf32 ? 32 : kTChan, d->n_store);
+      p.out_box_c = std::min(kTChan, d->n_store);
       uint64_t odims[4] = {(uint64_t)d->n_store, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->batch};
       uint64_t ostr[3] = {(uint64_t)d->out_pitch * E, (uint64_t)d->out_pitch * E * d->w,
                           (uint64_t)d->out_pitch * E * d->w * d->h};
-      uint32_t obox[4] = {(uint32_t)p.out_box_c, (uint32_t)kHaloTW, (uint32_t)p.t_rows, 1};
+      uint32_t obox[4] = {(uint32_t)p.out_box_c, (uint32_t)kHaloTW, (uint32_t)(tf32 ? 8 : p.t_rows), 1};
       int st = encode_tensor_map(&L->mapOut, tm_dtype, 4, d->out, odims, ostr, obox, TMA_SW_NONE);
       if (st != CSD_OK) return st;
+      L->mapOut2 = L->mapOut;
+      if (tf32 && p.t_rows / 2 > 8) {      // pass B of the fp32 epilogue: the half tile's rows beyond the first 8
+        uint32_t obox2[4] = {(uint32_t)p.out_box_c, (uint32_t)kHaloTW, (uint32_t)(p.t_rows / 2 - 8), 1};
+        st = encode_tensor_map(&L->mapOut2, tm_dtype, 4, d->out, odims, ostr, obox2, TMA_SW_NONE);
+        if (st != CSD_OK) return st;
+      }
     }
   }
   p.stat_partials = t_mode ? d->stat_partials : nullptr;
@@ -1466,10 +1473,10 @@ int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
   }
   if (L->persistent && L->tf32) {
     conv_halo_tp_kernel<true><<<L->grid, kPThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
-                                                                         L->mapB, L->mapOut, L->p);
+                                                                         L->mapB, L->mapOut, L->mapOut2, L->p);
   } else if (L->persistent) {
     conv_halo_tp_kernel<false><<<L->grid, kPThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
-                                                                          L->mapB, L->mapOut, L->p);
+                                                                          L->mapB, L->mapOut, L->mapOut, L->p);
   } else if (L->halo) {
     conv_halo_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
                                                                  L->mapB, L->p);
