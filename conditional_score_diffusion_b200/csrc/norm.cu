@@ -261,7 +261,7 @@ gn_coeffs_partials_kernel(GnCoefSrc s0, GnCoefSrc s1, const float* __restrict__ 
   const int cs = blockIdx.y * slice, ce = min(C, cs + slice);
   if (cs >= ce) return;
   const int n2 = 2 * (ce - cs);
-  const int lanes = max(1, min(16, (int)blockDim.x / n2));
+  const int lanes = max(1, min(32, (int)blockDim.x / n2));
   float* sums = sm;              // [n2]
   float* red = sm + n2;          // [lanes][n2]
   for (int idx = threadIdx.x; idx < lanes * n2; idx += blockDim.x) {
@@ -897,11 +897,12 @@ int csd_gn_coeffs_partials_f32(const float* sums0, const float* partials0, int t
   GnCoefSrc s0{sums0, partials0, sums_out0, tiles0, c0};
   GnCoefSrc s1{sums1, partials1, sums_out1, tiles1, c1};
   const int cpg = (c0 + c1) / groups;
-  // enough CTAs for ~2 waves, each owning whole groups
-  int slices = std::max(1, std::min(groups, ceil_div(2 * num_sms(), batch)));
+  // Many small CTAs, each owning whole groups: the kernel is a dependent chain of L2 reads (tiles per lane), so narrower
+  // slices (more lanes of tiles per channel, up to 32) shorten it; ~8 CTAs per SM keep the machine covered
+  int slices = std::max(1, std::min(groups, ceil_div(8 * num_sms(), batch)));
   const int slice = ceil_div(groups, slices) * cpg;
   slices = ceil_div(c0 + c1, slice);
-  const size_t smem = sizeof(float) * (2 * (size_t)slice + (size_t)std::max(256, 2 * slice));
+  const size_t smem = sizeof(float) * (2 * (size_t)slice + (size_t)std::max(256, 2 * slice) + 64);
   CSD_REQUIRE(smem <= 48 * 1024, "gn_coeffs_partials: %d channels per slice exceed the shared-memory budget", slice);
   gn_coeffs_partials_kernel<<<dim3((unsigned)batch, (unsigned)slices), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       s0, s1, gamma, beta, reinterpret_cast<float2*>(coef0), reinterpret_cast<float2*>(coef1), hw, cpg, eps, slice);

@@ -135,83 +135,139 @@ upfirdn2d_tile_kernel(const __grid_constant__ CUtensorMap map, const UpfirdnPara
     __syncthreads();
   }
 
-  // Register-blocked polyphase evaluation: a thread owns a CX x RY output block. Its input footprint (FW x FH samples of
-  // the shared-memory tile) and the K x K filter are read into registers ONCE, then every output is a static sum over
-  // them - 16 (up x2) / 60 (down x2) / 49 (1:1) shared-memory loads per block instead of 2 per multiply-add. For UP = 2
-  // the tap phase of an output alternates with its coordinate; the phase of the block's first row / column (A, B) is
-  // uniform over the warp, so the four phase combinations are four fully unrolled code paths.
-  const int txx = tid & 31, tyy = tid >> 5;
-  const int oxb = ox0 + txx * C::CX, oyb = oy0 + tyy * C::RY;
-  const int ux0 = oxb * DOWN - p.pad_x0, uy0 = oyb * DOWN - p.pad_y0;
-  const int B0 = pmod(-ux0, UP), A0 = pmod(-uy0, UP);
-  const int xi0 = (ux0 + B0 - ix0 * UP) / UP, yi0 = (uy0 + A0 - iy0 * UP) / UP;
-  constexpr int FW = UP == 1 ? (C::CX - 1) * DOWN + K : C::CX / 2 + 2;
-  constexpr int FH = UP == 1 ? (C::RY - 1) * DOWN + K : C::RY / 2 + 2;
-  static_assert(UP == 1 || (UP == 2 && DOWN == 1 && K == 4), "register-blocked evaluation: UP 1, or UP 2 with a 4-tap filter");
-  float in[FH][FW];
-#pragma unroll
-  for (int a = 0; a < FH; ++a)
-#pragma unroll
-    for (int bb = 0; bb < FW; ++bb) in[a][bb] = tile[(yi0 + a) * C::IN_TW + xi0 + bb];
-  float kr[K * K];
-#pragma unroll
-  for (int i = 0; i < K * K; ++i) kr[i] = kf[i];
-  float acc[C::RY][C::CX];
-#pragma unroll
-  for (int r = 0; r < C::RY; ++r)
-#pragma unroll
-    for (int c = 0; c < C::CX; ++c) acc[r][c] = 0.f;
-
-  auto eval = [&](auto a_tag, auto b_tag) {
-    constexpr int A = decltype(a_tag)::value, Bp = decltype(b_tag)::value;
-#pragma unroll
+  if constexpr (UP == 1) {
+    // UP = 1 (down x2, 1:1): per-output evaluation straight from the shared-memory tile. The register-blocked form below
+    // was measured SLOWER here (ncu r2: 100 vs 78 us for down x2): adjacent lanes sit 4 floats apart in the tile, so each
+    // of its footprint loads is a 4-way bank conflict, and the footprint (60 / 49 samples) is not reused enough to pay.
+    const int txx = tid & 31, tyy = tid >> 5;
+    const int oxb = ox0 + txx * C::CX;
+    constexpr int NT = (K + UP - 1) / UP;  // taps that can hit a real sample, per axis
+    int kx0[C::CX], xi[C::CX];
+  #pragma unroll
+    for (int c = 0; c < C::CX; ++c) {
+      const int ux = (oxb + c) * DOWN - p.pad_x0;
+      kx0[c] = pmod(-ux, UP);
+      xi[c] = (ux + kx0[c] - ix0 * UP) / UP;  // column in the tile of the first contributing sample
+    }
+    float* dst_plane = p.out + plane * p.out_h * p.out_w;
+  #pragma unroll
     for (int r = 0; r < C::RY; ++r) {
-      // first tap row of output row r and its offset inside the footprint
-      constexpr int dummy = 0;
-      (void)dummy;
-      const int ky0 = UP == 1 ? 0 : ((A + r) & 1);
-      const int fy = UP == 1 ? r * DOWN : (r + ((A + r) & 1) - A) / 2;
-#pragma unroll
-      for (int c = 0; c < C::CX; ++c) {
-        const int kx0 = UP == 1 ? 0 : ((Bp + c) & 1);
-        const int fx = UP == 1 ? c * DOWN : (c + ((Bp + c) & 1) - Bp) / 2;
-        float s = 0.f;
-#pragma unroll
-        for (int jy = 0; jy < (K + UP - 1) / UP; ++jy)
-#pragma unroll
-          for (int jx = 0; jx < (K + UP - 1) / UP; ++jx)
-            s = fmaf(kr[(ky0 + jy * UP) * K + kx0 + jx * UP], in[fy + jy][fx + jx], s);
-        acc[r][c] = s;
+      const int oy = oy0 + tyy * C::RY + r;
+      if (oy >= p.out_h) break;
+      const int uy = oy * DOWN - p.pad_y0;
+      const int ky0 = pmod(-uy, UP);
+      const int yi = (uy + ky0 - iy0 * UP) / UP;
+      float acc[C::CX];
+  #pragma unroll
+      for (int c = 0; c < C::CX; ++c) acc[c] = 0.f;
+  #pragma unroll
+      for (int jy = 0; jy < NT; ++jy) {
+        const int ky = ky0 + jy * UP;
+        if (ky < K) {
+          const float* srow = tile + (yi + jy) * C::IN_TW;
+  #pragma unroll
+          for (int c = 0; c < C::CX; ++c) {
+  #pragma unroll
+            for (int jx = 0; jx < NT; ++jx) {
+              const int kx = kx0[c] + jx * UP;
+              if (kx < K) acc[c] = fmaf(kf[ky * K + kx], srow[xi[c] + jx], acc[c]);
+            }
+          }
+        }
+      }
+      float* dst = dst_plane + (long long)oy * p.out_w + oxb;
+      const bool vec_ok = (oxb + C::CX <= p.out_w) && ((p.out_w & (C::CX - 1)) == 0);
+      if (vec_ok) {
+        if (C::CX == 4) {
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        } else {
+          *reinterpret_cast<float2*>(dst) = make_float2(acc[0], acc[1]);
+        }
+      } else {
+  #pragma unroll
+        for (int c = 0; c < C::CX; ++c)
+          if (oxb + c < p.out_w) dst[c] = acc[c];
       }
     }
-  };
-  if (UP == 1) {
-    eval(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
-  } else if (A0 == 0) {
-    if (B0 == 0) eval(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
-    else eval(std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{});
   } else {
-    if (B0 == 0) eval(std::integral_constant<int, 1>{}, std::integral_constant<int, 0>{});
-    else eval(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
-  }
+    // Register-blocked polyphase evaluation: a thread owns a CX x RY output block. Its input footprint (FW x FH samples of
+    // the shared-memory tile) and the K x K filter are read into registers ONCE, then every output is a static sum over
+    // them - 16 (up x2) / 60 (down x2) / 49 (1:1) shared-memory loads per block instead of 2 per multiply-add. For UP = 2
+    // the tap phase of an output alternates with its coordinate; the phase of the block's first row / column (A, B) is
+    // uniform over the warp, so the four phase combinations are four fully unrolled code paths.
+    const int txx = tid & 31, tyy = tid >> 5;
+    const int oxb = ox0 + txx * C::CX, oyb = oy0 + tyy * C::RY;
+    const int ux0 = oxb * DOWN - p.pad_x0, uy0 = oyb * DOWN - p.pad_y0;
+    const int B0 = pmod(-ux0, UP), A0 = pmod(-uy0, UP);
+    const int xi0 = (ux0 + B0 - ix0 * UP) / UP, yi0 = (uy0 + A0 - iy0 * UP) / UP;
+    constexpr int FW = UP == 1 ? (C::CX - 1) * DOWN + K : C::CX / 2 + 2;
+    constexpr int FH = UP == 1 ? (C::RY - 1) * DOWN + K : C::RY / 2 + 2;
+    static_assert(UP == 1 || (UP == 2 && DOWN == 1 && K == 4), "register-blocked evaluation: UP 1, or UP 2 with a 4-tap filter");
+    float in[FH][FW];
+  #pragma unroll
+    for (int a = 0; a < FH; ++a)
+  #pragma unroll
+      for (int bb = 0; bb < FW; ++bb) in[a][bb] = tile[(yi0 + a) * C::IN_TW + xi0 + bb];
+    float kr[K * K];
+  #pragma unroll
+    for (int i = 0; i < K * K; ++i) kr[i] = kf[i];
+    float acc[C::RY][C::CX];
+  #pragma unroll
+    for (int r = 0; r < C::RY; ++r)
+  #pragma unroll
+      for (int c = 0; c < C::CX; ++c) acc[r][c] = 0.f;
 
-  float* dst_plane = p.out + plane * p.out_h * p.out_w;
-  const bool vec_ok = (oxb + C::CX <= p.out_w) && ((p.out_w & (C::CX - 1)) == 0);
-#pragma unroll
-  for (int r = 0; r < C::RY; ++r) {
-    const int oy = oyb + r;
-    if (oy >= p.out_h) break;
-    float* dst = dst_plane + (long long)oy * p.out_w + oxb;
-    if (vec_ok) {
-      if (C::CX == 4) {
-        *reinterpret_cast<float4*>(dst) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-      } else {
-        *reinterpret_cast<float2*>(dst) = make_float2(acc[r][0], acc[r][1]);
+    auto eval = [&](auto a_tag, auto b_tag) {
+      constexpr int A = decltype(a_tag)::value, Bp = decltype(b_tag)::value;
+  #pragma unroll
+      for (int r = 0; r < C::RY; ++r) {
+        // first tap row of output row r and its offset inside the footprint
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int ky0 = UP == 1 ? 0 : ((A + r) & 1);
+        const int fy = UP == 1 ? r * DOWN : (r + ((A + r) & 1) - A) / 2;
+  #pragma unroll
+        for (int c = 0; c < C::CX; ++c) {
+          const int kx0 = UP == 1 ? 0 : ((Bp + c) & 1);
+          const int fx = UP == 1 ? c * DOWN : (c + ((Bp + c) & 1) - Bp) / 2;
+          float s = 0.f;
+  #pragma unroll
+          for (int jy = 0; jy < (K + UP - 1) / UP; ++jy)
+  #pragma unroll
+            for (int jx = 0; jx < (K + UP - 1) / UP; ++jx)
+              s = fmaf(kr[(ky0 + jy * UP) * K + kx0 + jx * UP], in[fy + jy][fx + jx], s);
+          acc[r][c] = s;
+        }
       }
+    };
+    if (UP == 1) {
+      eval(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+    } else if (A0 == 0) {
+      if (B0 == 0) eval(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+      else eval(std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{});
     } else {
-#pragma unroll
-      for (int c = 0; c < C::CX; ++c)
-        if (oxb + c < p.out_w) dst[c] = acc[r][c];
+      if (B0 == 0) eval(std::integral_constant<int, 1>{}, std::integral_constant<int, 0>{});
+      else eval(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
+    }
+
+    float* dst_plane = p.out + plane * p.out_h * p.out_w;
+    const bool vec_ok = (oxb + C::CX <= p.out_w) && ((p.out_w & (C::CX - 1)) == 0);
+  #pragma unroll
+    for (int r = 0; r < C::RY; ++r) {
+      const int oy = oyb + r;
+      if (oy >= p.out_h) break;
+      float* dst = dst_plane + (long long)oy * p.out_w + oxb;
+      if (vec_ok) {
+        if (C::CX == 4) {
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        } else {
+          *reinterpret_cast<float2*>(dst) = make_float2(acc[r][0], acc[r][1]);
+        }
+      } else {
+  #pragma unroll
+        for (int c = 0; c < C::CX; ++c)
+          if (oxb + c < p.out_w) dst[c] = acc[r][c];
+      }
     }
   }
 }
@@ -367,60 +423,95 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map, const FirNhwcParamsT<VT>
   __syncthreads();
   ptx::mbar_wait(ptx::smem_u32(&bar), 0);
   const VT* tile = reinterpret_cast<const VT*>(fir_smem);         // [TI][TI][cvs] 8-channel vectors
-  const int items = T::TO * T::TO * cvs;
+  // One work item = a 2 x 2 output quad x one 8-channel vector. The quad's input footprint (3 x 3 pixels for up x2,
+  // 6 x 6 for down x2) is read and unpacked once and feeds all four outputs: 2.25 / 9 shared-memory vector loads and
+  // unpacks per output instead of 4 / 16 (the per-output form was instruction-issue bound: SM 70-82 % busy at 25-31 % of
+  // the HBM bandwidth, profiles/named_kernels_full_r2.md). Consecutive lanes take consecutive channel vectors of the
+  // same quad, so every shared-memory access is a contiguous 16/32-byte-per-lane row: conflict free.
+  constexpr int Q = T::TO / 2;
+  const int items = Q * Q * cvs;
   for (int item = threadIdx.x; item < items; item += 256) {
     const int cv = item % cvs;
-    const int px = item / cvs;
-    const int lx = px % T::TO, ly = px / T::TO;
-    const int ox = ox0 + lx, oy = oy0 + ly;
+    const int qd = item / cvs;
+    const int qx = qd % Q, qy = qd / Q;
+    const int ox = ox0 + 2 * qx, oy = oy0 + 2 * qy;
     const int gcv = cc * cvs + cv;                                // channel vector in the tensor
     if (ox >= p.ow || oy >= p.oh || gcv >= p.cvec) continue;
-    float acc[8];
+    float acc[4][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[o][e] = 0.f;
     if (MODE == 1) {
-      // out[2i] = in[i-1] kf[0] + in[i] kf[2];  out[2i+1] = in[i] kf[1] + in[i+1] kf[3]; local row of in[i-1] = i
-      const int i = ly >> 1, j = lx >> 1;
-      const int ry = i + (ly & 1), rx = j + (lx & 1);
-      const float wy0 = (ly & 1) ? p.kf[1] : p.kf[0], wy1 = (ly & 1) ? p.kf[3] : p.kf[2];
-      const float wx0 = (lx & 1) ? p.kf[1] : p.kf[0], wx1 = (lx & 1) ? p.kf[3] : p.kf[2];
+      // out[2i] = in[i-1] kf[0] + in[i] kf[2];  out[2i+1] = in[i] kf[1] + in[i+1] kf[3]; local row of in[i-1] = i = qy
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+      for (int a = 0; a < 3; ++a) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const VT v = tile[((ry + a) * T::TI + rx + c) * cvs + cv];
+        for (int c = 0; c < 3; ++c) {
           float f[8];
-          unpack8(v, f);
-          const float wgt = (a ? wy1 : wy0) * (c ? wx1 : wx0);
+          unpack8(tile[((qy + a) * T::TI + qx + c) * cvs + cv], f);
+          // weights of this sample for the even / odd output row and column (0 where the tap does not reach)
+          const float wy0 = a == 0 ? p.kf[0] : (a == 1 ? p.kf[2] : 0.f), wy1 = a == 0 ? 0.f : (a == 1 ? p.kf[1] : p.kf[3]);
+          const float wx0 = c == 0 ? p.kf[0] : (c == 1 ? p.kf[2] : 0.f), wx1 = c == 0 ? 0.f : (c == 1 ? p.kf[1] : p.kf[3]);
+          if (a < 2 && c < 2) {
+            const float wgt = wy0 * wx0;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, f[e], acc[e]);
+            for (int e = 0; e < 8; ++e) acc[0][e] = fmaf(wgt, f[e], acc[0][e]);
+          }
+          if (a < 2 && c > 0) {
+            const float wgt = wy0 * wx1;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[1][e] = fmaf(wgt, f[e], acc[1][e]);
+          }
+          if (a > 0 && c < 2) {
+            const float wgt = wy1 * wx0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[2][e] = fmaf(wgt, f[e], acc[2][e]);
+          }
+          if (a > 0 && c > 0) {
+            const float wgt = wy1 * wx1;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[3][e] = fmaf(wgt, f[e], acc[3][e]);
+          }
         }
+      }
     } else {
-      // out[o] = sum_k kf[k] in[2o - 1 + k]; local index of in[2o - 1 + k] = 2 l + k
+      // out[o] = sum_k kf[k] in[2o - 1 + k]; local index of in[2o - 1 + k] = 2 l + k; quad rows l = 2 qy, 2 qy + 1
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 6; ++a) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const VT v = tile[((2 * ly + a) * T::TI + 2 * lx + c) * cvs + cv];
+        for (int c = 0; c < 6; ++c) {
           float f[8];
-          unpack8(v, f);
-          const float wgt = p.kf[a] * p.kf[c];
+          unpack8(tile[((4 * qy + a) * T::TI + 4 * qx + c) * cvs + cv], f);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, f[e], acc[e]);
+          for (int o = 0; o < 4; ++o) {
+            const int ka = a - 2 * (o >> 1), kc = c - 2 * (o & 1);      // tap indices for output o (compile time)
+            if (ka >= 0 && ka < 4 && kc >= 0 && kc < 4) {
+              const float wgt = p.kf[ka] * p.kf[kc];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[o][e] = fmaf(wgt, f[e], acc[o][e]);
+            }
+          }
         }
+      }
     }
-    const long long o = (((long long)b * p.oh + oy) * p.ow + ox) * p.cvec + gcv;
-    if (p.add != nullptr) {
-      float f[8];
-      unpack8(p.add[o], f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] += f[e];
-    }
-    if (sizeof(VT) == 32 && p.round_out) {
+    for (int o = 0; o < 4; ++o) {
+      const int oxx = ox + (o & 1), oyy = oy + (o >> 1);
+      if (oxx >= p.ow || oyy >= p.oh) continue;
+      const long long off = (((long long)b * p.oh + oyy) * p.ow + oxx) * p.cvec + gcv;
+      if (p.add != nullptr) {
+        float f[8];
+        unpack8(p.add[off], f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = round_tf32(acc[e]);
+        for (int e = 0; e < 8; ++e) acc[o][e] += f[e];
+      }
+      if (sizeof(VT) == 32 && p.round_out) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[o][e] = round_tf32(acc[o][e]);
+      }
+      p.out[off] = pack8_as<VT>(acc[o]);
     }
-    p.out[o] = pack8_as<VT>(acc);
   }
 }
 
