@@ -73,6 +73,8 @@ class ConvGemmDesc(ctypes.Structure):
         ("stat_partials", c_void_p),
         ("dtype", c_int32),
         ("out_round_tf32", c_int32),
+        ("k_splits", c_int32),
+        ("splitk_ws", c_void_p),
     ]
 
 

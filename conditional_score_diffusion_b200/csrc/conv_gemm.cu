@@ -67,6 +67,8 @@ struct ConvGemmKernelParams {
   int wt_k_off;
   int a_batch_step;
   int num_stages, tmem_cols;
+  int ksplit;     // per-tap kernel: split-K over gridDim.z (each z computes a contiguous range of the (segment, tap, chunk)
+                  // iterations and writes raw fp32 partial sums; csd_splitk_reduce_bf16 finishes the epilogue)
   int producers;  // per-tap kernel: issuing threads; num_stages is a multiple of it, so a ring slot always belongs to
                   // the same producer (the two-phase mbarrier parity scheme needs every use of a slot seen in order)
   uint32_t stage_bytes, a_box_bytes, b_box_bytes;
@@ -285,8 +287,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   const int n0 = blockIdx.y * p.n_tile;
   const int z = blockIdx.z;
 
-  int total_iters = 0;
-  for (int s = 0; s < p.nseg; ++s) total_iters += p.seg_taps[s] * p.seg_chunks[s];
+  int all_iters = 0;
+  for (int s = 0; s < p.nseg; ++s) all_iters += p.seg_taps[s] * p.seg_chunks[s];
+  // split-K: this CTA owns iterations [it_lo, it_hi) of the flattened (segment, tap, chunk) list
+  const int it_lo = p.ksplit > 1 ? (int)(((long long)all_iters * z) / p.ksplit) : 0;
+  const int it_hi = p.ksplit > 1 ? (int)(((long long)all_iters * (z + 1)) / p.ksplit) : all_iters;
+  const int total_iters = it_hi - it_lo;
+  const int zb = p.ksplit > 1 ? 0 : z;              // batched-GEMM index of the operands (split-K shares them)
   if (threadIdx.x == 0) CSD_TS(0);
 
   if (warp == 0 && lane == 0) {
@@ -321,6 +328,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       int turn = 0;
       int kcol = p.wt_k_off;  // running K column into Wt
       int issued = 0;         // perf experiment (debug_nodata): loads beyond the first ring fill can be switched off
+      int git = 0;            // index in the flattened (segment, tap, chunk) list
       for (int s = 0; s < p.nseg; ++s) {
         const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
         const int taps = p.seg_taps[s];
@@ -329,7 +337,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           const int dy = (taps == 9) ? (tap / 3 - p.pad) : 0;
           const int dx = (taps == 9) ? (tap % 3 - p.pad) : 0;
           const int cw = w0 * p.stride + dx, ch = h0 * p.stride + dy;
-          for (int c = 0; c < p.seg_chunks[s]; ++c) {
+          for (int c = 0; c < p.seg_chunks[s]; ++c, ++git) {
+            if (git < it_lo || git >= it_hi) continue;      // another split's iteration
             if (turn == me) {
               ptx::mbar_wait(empty_bar(stage), par);
 #ifdef CSD_ENABLE_PHASE_TIMESTAMPS
@@ -345,10 +354,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               ptx::mbar_arrive_expect_tx(full_bar(stage),
                                          (load_a ? p.a_box_bytes : 0u) + (load_b ? p.b_box_bytes * p.nsplit : 0u));
               if (load_a)
-                ptx::tma_load_4d(a_dst, mapA, full_bar(stage), p.seg_coff[s] + c * kChunk, cw, ch, b0 + z * p.a_batch_step);
+                ptx::tma_load_4d(a_dst, mapA, full_bar(stage), p.seg_coff[s] + c * kChunk, cw, ch, b0 + zb * p.a_batch_step);
               if (load_b) {
-                ptx::tma_load_3d(b_dst, &mapB, full_bar(stage), kc, n0, z);
-                if (p.nsplit > 1) ptx::tma_load_3d(b_dst + p.b_box_bytes, &mapB, full_bar(stage), kc, n0 + p.n_sub, z);
+                ptx::tma_load_3d(b_dst, &mapB, full_bar(stage), kc, n0, zb);
+                if (p.nsplit > 1) ptx::tma_load_3d(b_dst + p.b_box_bytes, &mapB, full_bar(stage), kc, n0 + p.n_sub, zb);
               }
             }
             ++issued;
@@ -1193,6 +1202,58 @@ static int next_pow2_cols(int n) {
 }
 
 // Host launcher shared by csd_conv_gemm and the program executor (which pre-encodes the maps).
+// ---------------------------------------------------------------------------------------------------
+// Split-K finish (small levels). A 5 or 10 px level has fewer 128-pixel tiles than the GPU has SMs and every CTA
+// walks the whole K = 9 * C range on its own, bound by the latency of its shared-memory ring rather than by the
+// tensor core. With k_splits > 1 gridDim.z CTAs share one tile's K range, each writing raw fp32 partial sums to
+// splitk_ws [split][pixel][ws_pitch]; this pass adds the partials in split order (fixed order: deterministic) and
+// applies the epilogue the single-pass kernel would have: + bias[n] + temb[b][n] + res, * scale, optional tf32
+// rounding, bf16 or fp32 store.
+// ---------------------------------------------------------------------------------------------------
+struct SplitKReduceParams {
+  const float* ws;
+  long long split_stride;   // floats between splits
+  int ws_pitch, splits;
+  long long pixels;
+  int pix_per_image;
+  int n_store;
+  void* out; int out_pitch, out_f32, out_round;
+  const float* bias;
+  const float* temb; int temb_pitch;
+  const void* res; int res_pitch, res_f32;
+  float scale;
+};
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitKReduceParams p) {
+  const int groups = (p.n_store + 3) >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.pixels * groups) return;
+  const long long pix = idx / groups;
+  const int n = (int)(idx - pix * groups) * 4;
+  const float* w = p.ws + pix * p.ws_pitch + n;
+  float4 acc = __ldg(reinterpret_cast<const float4*>(w));
+  for (int s = 1; s < p.splits; ++s) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(w + s * p.split_stride));
+    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+  }
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+  const int cnt = min(4, p.n_store - n);
+  const int b = (int)(pix / p.pix_per_image);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i >= cnt) break;
+    if (p.bias != nullptr) v[i] += __ldg(p.bias + n + i);
+    if (p.temb != nullptr) v[i] += __ldg(p.temb + (long long)b * p.temb_pitch + n + i);
+    if (p.res != nullptr)
+      v[i] += p.res_f32 ? __ldg(reinterpret_cast<const float*>(p.res) + pix * p.res_pitch + n + i)
+                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[pix * p.res_pitch + n + i]);
+    v[i] *= p.scale;
+    if (p.out_round) v[i] = round_tf32(v[i]);
+    if (p.out_f32) reinterpret_cast<float*>(p.out)[pix * p.out_pitch + n + i] = v[i];
+    else reinterpret_cast<__nv_bfloat16*>(p.out)[pix * p.out_pitch + n + i] = __float2bfloat16_rn(v[i]);
+  }
+}
+
 struct ConvGemmLaunch {
   int tap_chunk;   // channels per stage of the per-tap kernel (32 or 64)
   bool tf32;       // fp32 activations / weights, kind::tf32 (per-tap kernel only)
@@ -1206,6 +1267,8 @@ struct ConvGemmLaunch {
   bool halo;
   bool transposed;
   bool persistent;
+  int ksplit;                // > 1: split-K partials + splitk_reduce_kernel
+  SplitKReduceParams red;
 };
 
 int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
@@ -1344,13 +1407,19 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   p.a_box_bytes = (uint32_t)(p.TW * p.TH * p.TB * tap_row_bytes);
   p.b_box_bytes = (uint32_t)(p.n_sub * tap_row_bytes);
   p.stage_bytes = (uint32_t)((kTileM * tap_row_bytes + d->n_tile * tap_row_bytes + 1023) & ~1023);
-  const int total_iters = tap_iters;
+  const int ks = d->k_splits > 1 ? d->k_splits : 1;
+  CSD_REQUIRE(ks == 1 || (!halo_mode && d->z_batches == 1 && d->bias_per_row == 0 && d->splitk_ws != nullptr &&
+                          ks <= 16 && ks <= tap_iters),
+              "k_splits=%d needs the per-tap kernel (mode 0), z_batches == 1, per-channel bias, a workspace and at "
+              "least one K iteration per split (%d iterations)", ks, tap_iters);
+  L->ksplit = ks;
+  const int total_iters = ceil_div(tap_iters, ks);
   int budget = p.tmem_cols <= 128 ? 56 * 1024 : (p.tmem_cols <= 256 ? 100 * 1024 : 200 * 1024);
   {
     // Small grids (the 5/10/20 px levels: fewer CTAs than SMs) run one CTA per SM whatever their footprint and
     // their K loop is TMA-latency bound, so they take the whole shared memory for a deeper ring instead of
     // leaving room for co-resident CTAs that will never come.
-    const long long ctas = (long long)p.tiles_w * p.tiles_h * tiles_b * n_tiles * d->z_batches;
+    const long long ctas = (long long)p.tiles_w * p.tiles_h * tiles_b * n_tiles * d->z_batches * ks;
     if (!halo_mode && ctas <= num_sms()) budget = 200 * 1024;
   }
   int stages = budget / (int)p.stage_bytes;
@@ -1373,6 +1442,22 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   p.res = reinterpret_cast<const __nv_bfloat16*>(d->res); p.res_pitch = d->res_pitch;
   p.res_z_stride = d->res_z_stride;
   p.scale = d->scale;
+  p.ksplit = ks;
+  if (ks > 1) {
+    // the conv kernel writes raw partial sums; the epilogue moves to splitk_reduce_kernel
+    SplitKReduceParams& r = L->red;
+    const int ws_pitch = ceil_div(d->n_store, 8) * 8;
+    r.ws = d->splitk_ws; r.ws_pitch = ws_pitch; r.splits = ks;
+    r.pixels = (long long)d->batch * d->h * d->w; r.pix_per_image = d->h * d->w;
+    r.split_stride = r.pixels * ws_pitch;
+    r.n_store = d->n_store;
+    r.out = d->out; r.out_pitch = d->out_pitch; r.out_f32 = (tf32 || d->out_f32) ? 1 : 0; r.out_round = p.out_round;
+    r.bias = d->bias; r.temb = d->temb; r.temb_pitch = d->temb_pitch;
+    r.res = d->res; r.res_pitch = d->res_pitch; r.res_f32 = tf32 ? 1 : 0;
+    r.scale = d->scale;
+    p.out = d->splitk_ws; p.out_pitch = ws_pitch; p.out_f32 = 1; p.out_z_stride = r.split_stride;
+    p.out_round = 0; p.bias = nullptr; p.temb = nullptr; p.res = nullptr; p.scale = 1.0f;
+  }
   {
     const char* e = getenv("CSD_DEBUG_NODATA");
     p.debug_nodata = (e != nullptr) ? atoi(e) : 0;  // bit 0: skip weight loads, bit 1: skip activation loads
@@ -1382,7 +1467,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
   CSD_REQUIRE(d->out_pitch % 8 == 0, "out_pitch=%d must be a multiple of 8", d->out_pitch);
   CSD_REQUIRE(d->res == nullptr || d->res_pitch % 8 == 0, "res_pitch=%d must be a multiple of 8", d->res_pitch);
 
-  L->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * tiles_b), (unsigned)n_tiles, (unsigned)d->z_batches);
+  L->grid = dim3((unsigned)(p.tiles_w * p.tiles_h * tiles_b), (unsigned)n_tiles, (unsigned)(d->z_batches * ks));
   L->smem = (size_t)stages * p.stage_bytes + 1024 /*alignment slack*/ + 8 * (2 * kMaxStages + 2) + 4 * kAddendFloats;
   if (halo_mode) {
     p.a_stage_bytes = (uint32_t)(((kHaloTW + 2) * (kHaloTH * mt + 2) * kRowBytes + 1023) & ~1023);
@@ -1491,6 +1576,11 @@ int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
                                                                            L->mapA[3], L->mapB, L->p);
   }
   CSD_LAUNCH_CHECK("conv_gemm_kernel");
+  if (L->ksplit > 1) {
+    const long long work = L->red.pixels * ((L->red.n_store + 3) / 4);
+    splitk_reduce_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(L->red);
+    CSD_LAUNCH_CHECK("splitk_reduce_kernel");
+  }
   return CSD_OK;
 }
 

@@ -11,6 +11,7 @@
 #include "../../include/csd_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace csd {
@@ -474,11 +475,15 @@ static bool gn_fused_plan(int c0, int c1, int hw, int groups, int batch, int sms
   const int nb = V / base;
   // most slices whose rows are still >= 64 B (4 vectors) unless the tensor is narrower than that; with a big batch
   // fewer, wider slices are enough to fill the machine
+  int min_vs = 4;
+  int max_threads = 512;
+  if (const char* e = getenv("CSD_GNF_MINVEC")) min_vs = std::max(1, atoi(e));          // probe only
+  if (const char* e = getenv("CSD_GNF_THREADS")) max_threads = std::max(64, atoi(e));   // probe only
   int best = 1;
   for (int d = nb; d >= 1; --d) {
     if (nb % d) continue;
     const int vs = V / d;
-    if (vs >= 4 || d == 1) { best = d; break; }
+    if (vs >= min_vs || d == 1) { best = d; break; }
   }
   while (best > 1) {   // shrink while the grid stays >= 2 waves and the next divisor exists
     int d2 = best - 1;
@@ -493,7 +498,7 @@ static bool gn_fused_plan(int c0, int c1, int hw, int groups, int batch, int sms
   int threads = 256;
   int ppb = threads / vs;
   if (ppb < 1) return false;
-  if (ceil_div(hw, ppb) > 8) { threads = 512; ppb = threads / vs; }
+  if (ceil_div(hw, ppb) > 8 && max_threads >= 512) { threads = 512; ppb = threads / vs; }
   const int iters = ceil_div(hw, ppb);
   if (iters > (elem_bytes == 4 ? 8 : 16)) return false;   // register-cached vectors per thread (fp32 vectors are 8 registers)
   pl->vs = vs;

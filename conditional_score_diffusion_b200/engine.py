@@ -451,11 +451,18 @@ class BlockOps:
             tiles_img = math.ceil(oh / K.transposed_tile_rows(oh)) * math.ceil(ow / 8) * 2
             partials = self.pool.get((b * tiles_img, pc.n_store, 2), torch.float32)
             sums = self._stats_slot(b, pc.cout)
+        ks, ws = 1, None
+        if not use_t:
+            ks = K.pick_k_splits(seg_list, b, oh, ow, pc.n_store, pc.n_tile)
+            if ks > 1:
+                ws = self.pool.get((ks, b * oh * ow, -(-pc.n_store // 8) * 8), torch.float32)
         self.rec.add(K.conv_gemm, seg_list, pc.wt, pc.cout, out, batch=b, h=oh, w=ow, n_store=pc.n_store,
                      n_tile=pc.n_tile, bias=pc.bias, temb=temb, temb_pitch=temb_pitch,
                      res=res.t if res is not None else None, res_pitch=res.pitch if res is not None else 0,
                      scale=scale, stride=stride, pad=pad, in_h=ih, in_w=iw, transposed=use_t, stat_partials=partials,
-                     out_pitch=out_pitch)
+                     out_pitch=out_pitch, k_splits=ks, splitk_ws=ws)
+        if ws is not None:
+            self.pool.put(ws)
         if partials is not None and self.defer_finalize:
             return Act(out, pc.cout, None, (partials, tiles_img, sums))
         if partials is not None:

@@ -127,7 +127,7 @@ def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None
               res_pitch=0, scale=1.0, out_f32=None, z_batches=1, a_batch_step=0, wt_batch_stride=0,
               out_z_stride=0, res_z_stride=0, wt_pitch=0, wt_k_off=0, k_valid=0, wt_rows=None,
               stride=1, pad=1, in_h=0, in_w=0, halo=None, mt=None, transposed=None, stat_partials=None,
-              round_out=False):
+              round_out=False, k_splits=1, splitk_ws=None):
     """Launch csd_conv_gemm. segments: list of (tensor, pitch, c_off, c_cnt, taps[, norm, norm_silu]): `norm` is the
     [batch, c_cnt, 2] (scale, shift) table of gn_coeffs for the fused GroupNorm(+SiLU) prologue (transposed mode)."""
     _require_cuda(wt, out, bias, temb, res, *[s[0] for s in segments])
@@ -203,8 +203,34 @@ def conv_gemm(segments, wt, n, out, *, batch, h, w, out_pitch=None, n_store=None
     d.res_pitch = res_pitch
     d.res_z_stride = res_z_stride
     d.scale = scale
+    if k_splits > 1:
+        assert (splitk_ws is not None and splitk_ws.dtype == torch.float32 and splitk_ws.is_cuda
+                and splitk_ws.numel() >= k_splits * batch * h * w * ceil_to(d.n_store, 8)), "split-K workspace"
+        d.k_splits = k_splits
+        d.splitk_ws = splitk_ws.data_ptr()
     check(_lib.lib().csd_conv_gemm(ctypes.byref(d), _stream()))
     return out
+
+
+# Split-K for the small levels: at most this many CTAs share one tile's K range (0 / 1 = off; A/B switch).
+SPLITK_MAX = int(os.environ.get("CSD_SPLITK_MAX", "4"))
+
+
+def pick_k_splits(segments, batch, h, w, n_store, n_tile, tile=None, sms=148):
+    """How many ways csd_conv_gemm's per-tap kernel should split K for this launch. A level with fewer 128-pixel
+    tiles than half the SMs (5 / 10 px at batch 64) leaves most of the GPU idle while each CTA walks K = 9 C alone,
+    bound by its own TMA ring; sharing K between idle SMs shortens that walk. At least 4 ring iterations per split."""
+    if SPLITK_MAX <= 1:
+        return 1
+    tw, th, tb = tile if tile is not None else pick_tile(h, w, batch)
+    tiles = -(-w // tw) * -(-h // th) * -(-batch // tb)
+    ctas = tiles * -(-n_store // n_tile)
+    if ctas * 2 > sms:
+        return 1
+    f32 = segments[0][0].dtype == torch.float32
+    chunk = 64 if (not f32 and any(sg[3] > 32 for sg in segments)) else 32
+    iters = sum(sg[4] * -(-sg[3] // chunk) for sg in segments)
+    return max(1, min(SPLITK_MAX, sms // ctas, iters // 4))
 
 
 # --------------------------------------------------------------------------------------------

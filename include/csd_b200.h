@@ -312,6 +312,10 @@ typedef struct csd_conv_gemm_desc {
   int32_t out_round_tf32;       /* dtype 1: round the stored output to tf32 (nearest): set for tensors that only feed
                                    further tensor-core operands (attention q|k, V^T, P V), whose fp32 words the
                                    kind::tf32 MMA would otherwise truncate                                      */
+  int32_t k_splits;             /* mode 0, z_batches 1: > 1 splits the K range (taps x channel chunks) over gridDim.z
+                                   CTAs per tile - for levels with fewer tiles than SMs. Partial sums go to splitk_ws
+                                   and a second launch adds them in split order and applies bias / temb / res / scale */
+  float* splitk_ws;             /* k_splits > 1: fp32 workspace, k_splits * batch*h*w * ceil8(n_store) floats           */
 } csd_conv_gemm_desc;
 
 int csd_conv_gemm(const csd_conv_gemm_desc* desc, csd_stream_t stream);

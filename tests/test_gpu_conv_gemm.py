@@ -39,7 +39,7 @@ def _report(name, got, ref, rtol):
 
 
 def _conv_case(name, B, H, W, cin, cout, taps=9, bias=True, temb=False, res=False, scale=1.0,
-               c_pitch=None, out_f32=False, seed=0, tile=None, n_tile=None):
+               c_pitch=None, out_f32=False, seed=0, tile=None, n_tile=None, k_splits=1):
     k = _kern()
     g = torch.Generator(device="cuda").manual_seed(seed)
     dev = "cuda"
@@ -73,7 +73,9 @@ def _conv_case(name, B, H, W, cin, cout, taps=9, bias=True, temb=False, res=Fals
                      dtype=torch.float32 if out_f32 else torch.bfloat16)
     k.conv_gemm([(a, c_pitch, 0, cin, taps)], wt, cout, out, batch=B, h=H, w=W, n_store=n_store,
                 bias=bias_t, temb=temb_t, temb_pitch=(npad + 16), res=res_t, res_pitch=out_pitch,
-                scale=scale, tile=tile, n_tile=n_tile, transposed=False)
+                scale=scale, tile=tile, n_tile=n_tile, transposed=False, k_splits=k_splits,
+                splitk_ws=(torch.full((k_splits, B * H * W, n_store), float("nan"), device=dev)
+                           if k_splits > 1 else None))
     torch.cuda.synchronize()
     got = out[..., :cout].permute(0, 3, 1, 2)
     assert torch.isfinite(out[..., :n_store].float()).all(), f"{name}: non-finite outputs"
@@ -122,6 +124,44 @@ def test_conv3x3_ragged_tiles():
 def test_conv3x3_explicit_tiles():
     for tile in [(16, 8, 1), (8, 16, 1), (8, 8, 2), (4, 4, 8), (32, 4, 1)]:
         assert _conv_case(f"3x3 96->96 32x32 tile={tile}", 8, 32, 32, 96, 96, tile=tile) < BF16_RTOL
+
+
+@pytest.mark.parametrize("ks", [2, 3, 4, 7])
+def test_conv3x3_split_k(ks):
+    """Small levels: gridDim.z CTAs share one tile's K range and a second launch adds the fp32 partials in split
+    order and applies the whole epilogue (bias, temb, residual, scale). Uneven splits (45 iterations / 7) included."""
+    assert _conv_case(f"3x3 288->288 5x5 B=7 split-K {ks}", 7, 5, 5, 288, 288, temb=True, res=True,
+                      scale=1 / math.sqrt(2), k_splits=ks) < BF16_RTOL
+    assert _conv_case(f"3x3 192->288 10x10 split-K {ks}", 5, 10, 10, 192, 288, n_tile=144, k_splits=ks) < BF16_RTOL
+    assert _conv_case(f"3x3 96->6 split-K {ks} f32", 2, 8, 8, 96, 6, out_f32=True, k_splits=ks) < F32_RTOL
+    assert _conv_case(f"1x1 288->288 split-K {min(ks, 4)}", 3, 5, 5, 288, 288, taps=1, res=True,
+                      k_splits=min(ks, 4)) < BF16_RTOL
+
+
+def test_split_k_two_segments_and_determinism():
+    """Split boundaries falling inside and between segments; run-to-run bitwise identical (fixed summation order)."""
+    k = _kern()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(15)
+    B, H, W, c1, c2, cs, cout = 3, 10, 10, 96, 64, 160, 96
+    a1 = torch.randn(B, c1, H, W, device=dev, generator=g).to(torch.bfloat16)
+    a2 = torch.randn(B, c2, H, W, device=dev, generator=g).to(torch.bfloat16)
+    xs = torch.randn(B, cs, H, W, device=dev, generator=g).to(torch.bfloat16)
+    w3 = (torch.randn(cout, c1 + c2, 3, 3, device=dev, generator=g) / math.sqrt(9 * (c1 + c2))).to(torch.bfloat16)
+    w1 = (torch.randn(cout, cs, 1, 1, device=dev, generator=g) / math.sqrt(cs)).to(torch.bfloat16)
+    ref = F.conv2d(torch.cat([a1, a2], 1).float(), w3.float(), padding=1) + F.conv2d(xs.float(), w1.float())
+    wt = torch.cat([k.pack_conv_weight(w3[:, :c1]), k.pack_conv_weight(w3[:, c1:]), k.pack_conv_weight(w1)], dim=1).contiguous()
+    segs = [(_nhwc(a1), c1, 0, c1, 9), (_nhwc(a2), c2, 0, c2, 9), (_nhwc(xs), cs, 0, cs, 1)]
+    assert k.pick_k_splits(segs, B, H, W, cout, 96) > 1
+    outs = []
+    for ks in (1, 2, 3, 5, 5):
+        out = torch.empty(B, H, W, cout, device=dev, dtype=torch.bfloat16)
+        ws = torch.empty(ks, B * H * W, cout, device=dev) if ks > 1 else None
+        k.conv_gemm(segs, wt, cout, out, batch=B, h=H, w=W, k_splits=ks, splitk_ws=ws)
+        torch.cuda.synchronize()
+        assert _report(f"2 segments + skip, split-K {ks}", out.permute(0, 3, 1, 2), ref, BF16_RTOL) < BF16_RTOL
+        outs.append(out)
+    assert torch.equal(outs[-1], outs[-2])
 
 
 def test_two_segments_concat_plus_skip():
