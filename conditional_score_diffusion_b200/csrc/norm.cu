@@ -360,8 +360,17 @@ struct GnFusedPlan {
   size_t smem;
 };
 
+// Makes the compiler forget what it knows about the words of a register-cached vector: without it the unpacked fp32
+// values of the statistics pass are kept alive across the barriers for the apply pass (2-4x the registers of the packed
+// form, spilled under the 2-CTAs-per-SM bound) instead of being unpacked again.
+template <typename VT> __device__ __forceinline__ void keep_packed(VT& v) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(VT) / 4); ++i) asm volatile("" : "+r"(w[i]));
+}
+
 template <int R, typename VT>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, (R <= 8 && sizeof(VT) == 16) ? 2 : 1)
 gn_fused_kernel(GnParamsT<VT> p, int Vs) {
   extern __shared__ float sm[];
   const int b = blockIdx.y;
@@ -372,14 +381,13 @@ gn_fused_kernel(GnParamsT<VT> p, int Vs) {
   float* part = sm;                         // [ppb][n2]
   float* red = sm + (size_t)ppb * n2;       // [8][n2]
   float* chs = red + 8 * n2;                // [n2]
-  float* gstat = chs + n2;                  // [groups in slice][2] = (mean, rstd)
+  float* coef = chs + n2;                   // [n2] = (scale, shift) per channel of the slice
 
   VT cache[R];
-  float s[8], q[8];
+  {
+    float s[8], q[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  const bool active = pp < ppb;
-  if (active) {
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
 #pragma unroll
     for (int u = 0; u < R; ++u) {
       const int pix = pp + u * ppb;
@@ -398,12 +406,11 @@ gn_fused_kernel(GnParamsT<VT> p, int Vs) {
         }
       }
     }
-    float* row = part + (size_t)pp * n2 + v * 16;
+    float4* row = reinterpret_cast<float4*>(part + (size_t)pp * n2 + v * 16);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      row[2 * i] = s[i];
-      row[2 * i + 1] = q[i];
-    }
+    for (int i = 0; i < 4; ++i) row[i] = make_float4(s[2 * i], q[2 * i], s[2 * i + 1], q[2 * i + 1]);
+#pragma unroll
+    for (int u = 0; u < R; ++u) keep_packed(cache[u]);
   }
   __syncthreads();
   // two-level fixed-order reduction over the pixel lanes
@@ -421,29 +428,32 @@ gn_fused_kernel(GnParamsT<VT> p, int Vs) {
     chs[c2] = a;
   }
   __syncthreads();
-  const int gs = (Vs * 8) / p.cpg;          // groups of this slice
-  const float inv_n = 1.f / ((float)p.hw * (float)p.cpg);
-  for (int g = threadIdx.x; g < gs; g += blockDim.x) {
+  // one thread per channel of the slice: statistics of its group (every member of a group adds the same channel sums
+  // in the same order), then the channel's (scale, shift)
+  for (int lc = threadIdx.x; lc < Vs * 8; lc += blockDim.x) {
+    const int g0 = (lc / p.cpg) * p.cpg;
     float su = 0.f, sq = 0.f;
     for (int i = 0; i < p.cpg; ++i) {
-      su += chs[2 * (g * p.cpg + i)];
-      sq += chs[2 * (g * p.cpg + i) + 1];
+      const float2 t = *reinterpret_cast<const float2*>(chs + 2 * (g0 + i));
+      su += t.x;
+      sq += t.y;
     }
+    const float inv_n = 1.f / ((float)p.hw * (float)p.cpg);
     const float mean = su * inv_n;
     const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
-    gstat[2 * g] = mean;
-    gstat[2 * g + 1] = rsqrtf(var + p.eps);
+    const int c = blockIdx.x * Vs * 8 + lc;
+    const float a = rsqrtf(var + p.eps) * __ldg(p.gamma + c);
+    *reinterpret_cast<float2*>(coef + 2 * lc) = make_float2(a, __ldg(p.beta + c) - mean * a);
   }
   __syncthreads();
-  if (!active) return;
   float sc[8], sh[8];
+  {
+    const float4* cp = reinterpret_cast<const float4*>(coef + v * 16);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int lc = v * 8 + i;
-    const int g = lc / p.cpg;
-    const float a = gstat[2 * g + 1] * __ldg(p.gamma + gv * 8 + i);
-    sc[i] = a;
-    sh[i] = __ldg(p.beta + gv * 8 + i) - gstat[2 * g] * a;
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = cp[i];
+      sc[2 * i] = t.x; sh[2 * i] = t.y; sc[2 * i + 1] = t.z; sh[2 * i + 1] = t.w;
+    }
   }
 #pragma unroll
   for (int u = 0; u < R; ++u) {
@@ -465,20 +475,14 @@ gn_fused_kernel(GnParamsT<VT> p, int Vs) {
 static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
 // Host-side planning (no CUDA calls): returns false when the shape does not fit the one-launch kernel.
-static bool gn_fused_plan(int c0, int c1, int hw, int groups, int batch, int sms, GnFusedPlan* pl, int elem_bytes = 2) {
-  const int C = c0 + c1;
-  if (c0 < 8 || c0 % 8 || c1 % 8 || groups < 1 || C % groups || hw < 1 || batch < 1) return false;
-  const int cpg = C / groups;
+static bool gn_fused_plan_with(int min_vs, int max_threads, int C, int hw, int cpg, int batch, int sms, GnFusedPlan* pl,
+                               int elem_bytes) {
   const int V = C / 8;
   const int base = cpg / gcd_int(cpg, 8);   // lcm(cpg, 8) / 8 vectors: smallest slice made of whole groups
   if (V % base) return false;
   const int nb = V / base;
-  // most slices whose rows are still >= 64 B (4 vectors) unless the tensor is narrower than that; with a big batch
+  // most slices whose rows are still >= min_vs vectors unless the tensor is narrower than that; with a big batch
   // fewer, wider slices are enough to fill the machine
-  int min_vs = 4;
-  int max_threads = 512;
-  if (const char* e = getenv("CSD_GNF_MINVEC")) min_vs = std::max(1, atoi(e));          // probe only
-  if (const char* e = getenv("CSD_GNF_THREADS")) max_threads = std::max(64, atoi(e));   // probe only
   int best = 1;
   for (int d = nb; d >= 1; --d) {
     if (nb % d) continue;
@@ -507,8 +511,22 @@ static bool gn_fused_plan(int c0, int c1, int hw, int groups, int batch, int sms
   pl->threads = vs * ppb;
   pl->r = iters <= 1 ? 1 : (iters <= 2 ? 2 : (iters <= 4 ? 4 : (iters <= 8 ? 8 : 16)));
   const int n2 = vs * 16;
-  pl->smem = sizeof(float) * ((size_t)ppb * n2 + 8 * n2 + n2 + 2 * (size_t)((vs * 8) / cpg));
+  pl->smem = sizeof(float) * ((size_t)ppb * n2 + 8 * n2 + n2 + n2);
   return pl->smem <= 96 * 1024;
+}
+
+static bool gn_fused_plan(int c0, int c1, int hw, int groups, int batch, int sms, GnFusedPlan* pl, int elem_bytes = 2) {
+  const int C = c0 + c1;
+  if (c0 < 8 || c0 % 8 || c1 % 8 || groups < 1 || C % groups || hw < 1 || batch < 1) return false;
+  const int cpg = C / groups;
+  int max_threads = 512;
+  if (const char* e = getenv("CSD_GNF_THREADS")) max_threads = std::max(64, atoi(e));   // probe only
+  if (const char* e = getenv("CSD_GNF_MINVEC"))                                         // probe only
+    return gn_fused_plan_with(std::max(1, atoi(e)), max_threads, C, hw, cpg, batch, sms, pl, elem_bytes);
+  // 20 px class images in bf16: rows of >= 8 vectors (128 B) and half as many, fatter CTAs measured 9.8 vs 11.8 us at
+  // [64, 400, 192] (tools/gn_fused_probe.py); everything else, and whatever does not fit that way: >= 4 vectors
+  if (elem_bytes == 2 && hw >= 256 && gn_fused_plan_with(8, max_threads, C, hw, cpg, batch, sms, pl, elem_bytes)) return true;
+  return gn_fused_plan_with(4, max_threads, C, hw, cpg, batch, sms, pl, elem_bytes);
 }
 
 // ---- layout conversion ---------------------------------------------------------------------------

@@ -14,6 +14,9 @@ from .correctors import NoneCorrector, get_corrector
 from .predictors import NonePredictor, get_predictor
 from .unconditional import fused_kinds
 
+# use_path=True on the fused CUDA-graph loop (False keeps the per-step Python loop; A/B switch for the parity tests)
+FUSED_PATH = True
+
 
 def get_conditional_sampling_fn(config, sde, shape, eps, predictor="default", corrector="default", p_steps="default",
                                 c_steps="default", snr="default", denoise="default", use_path="default"):
@@ -83,12 +86,22 @@ def get_pc_conditional_sampler(sde, shape, predictor, corrector, snr, p_steps, c
         mean = K.sde_perturb(y0, y_tpt, torch.empty_like(y0), a, b)
         return K.sde_perturb(mean, torch.randn_like(y0), torch.empty_like(y0), None, std)
 
-    def pc_conditional_sampler_path(model, y, show_evolution=False, x_init=None):
+    def pc_conditional_sampler_path(model, y, show_evolution=False, x_init=None, noise_source=None):
         """use_path=True (sampling/conditional.py:87-94,124-176): y walks down ONE consistent path y_T -> y_0 through
         the backward kernel; predictor first, then the corrector on the same y_t."""
         if not pair:
             raise NotImplementedError("use_path=True needs the {'x', 'y'} SDE pair (sampling/conditional.py:86-87)")
         c_sde = sde["x"]
+        if kinds is not None and hasattr(model, "_engine") and FUSED_PATH:
+            fs = cache.get(("path", id(model)))
+            if fs is None:
+                fs = fused.FusedPCSampler(model, sde, shape, kinds[0], kinds[1], snr, p_steps, c_steps,
+                                          probability_flow, continuous, denoise, eps, conditional=True, use_path=True)
+                cache[("path", id(model))] = fs
+            samples, evo = fs.sample(y=y, x_init=x_init, noise_source=noise_source, show_evolution=show_evolution)
+            if show_evolution:
+                return samples, {"evolution": {"x": torch.stack(evo["x"]), "y": torch.stack(evo["y"])}}
+            return samples, {}
         with torch.no_grad():
             dev = model.device
             y = y.to(dev).contiguous().float()

@@ -15,6 +15,13 @@ captured once with torch.cuda.graph and replayed p_steps times: no host arithmet
 and no Python between launches. The state x lives in the network's own input buffer, so the update
 kernels write the next network input in place.
 
+Two more step shapes run on the same graph machinery:
+  * use_path (sampling/conditional.py:84-176): the condition walks ONE path y_T -> y_0 through the backward kernel
+    p(y_t | y_0, y_{t+tau}); the state y_t lives in the network's second input buffer and is advanced in place from
+    per-step coefficient tables; predictor first, then the corrector on the same y_t.
+  * inpainting (sampling/unconditional.py:230-345): after the corrector and after the predictor the known pixels are
+    replaced by the data at the current noise level (one merge kernel each, coefficients from device tables).
+
 Noise: torch's CUDA generator (`normal_` on static buffers, captured in the graph) in the same draw
 order as the reference (y, x, y, x per conditional step); `noise_source` replaces it with injected
 tensors for parity tests and reproducible replays.
@@ -27,7 +34,7 @@ from . import tables
 
 class FusedPCSampler:
     def __init__(self, model, sde, shape, predictor, corrector, snr, p_steps, c_steps, probability_flow,
-                 continuous, denoise, eps, conditional):
+                 continuous, denoise, eps, conditional, use_path=False, inpaint=False):
         self.model = model
         self.sde = sde
         self.shape = tuple(shape)
@@ -36,6 +43,12 @@ class FusedPCSampler:
         self.snr, self.p_steps, self.c_steps = snr, p_steps, c_steps
         self.probability_flow, self.continuous, self.denoise, self.eps = probability_flow, continuous, denoise, eps
         self.conditional = conditional      # {'x','y'} pair with a perturbed condition
+        self.use_path = use_path            # conditional pair: y follows one backward-kernel path
+        self.inpaint = inpaint              # unconditional: known pixels re-imposed after every update
+        if use_path and not conditional:
+            raise ValueError("use_path needs the {'x', 'y'} SDE pair")
+        if inpaint and conditional:
+            raise ValueError("the inpainter runs on an unconditional score model")
         self.c_sde = sde["x"] if isinstance(sde, dict) else sde
         self.graphs = {}
         self.ready = False
@@ -73,6 +86,24 @@ class FusedPCSampler:
             self.y = torch.empty_like(self.x)
             self.noise_y = [torch.empty_like(self.x) for _ in range(2)]
             self.t_sigma_y = dev(self.sde["y"].marginal_prob(ts, ts)[1])
+        if self.use_path:
+            # VESDE.compute_backward_kernel (sde_lib.py:323-339) on the whole time grid: y_t = a y_0 + b y_{t+tau} + s z
+            sy = self.sde["y"]
+            tau = ts[0] - ts[1]
+            s_t = sy.marginal_prob(ts, ts)[1] ** 2
+            s_tau = sy.marginal_prob(ts, ts + tau)[1] ** 2
+            self.t_pa, self.t_pb = dev((s_tau - s_t) / s_tau), dev(s_t / s_tau)
+            self.t_ps = dev(torch.sqrt(s_t * (s_tau - s_t) / s_tau))
+            one = torch.ones(1)
+            self.std_T = dev(sy.marginal_prob(one, one * (ts[0] + tau))[1].expand(b))
+            self.vec_a, self.vec_b, self.vec_s = (torch.empty(b, device=device, dtype=torch.float32) for _ in range(3))
+            self.y_tmp = torch.empty_like(self.x)
+        if self.inpaint:
+            mc, ms = self.c_sde.marginal_prob(torch.ones_like(ts), ts)
+            self.t_mc, self.t_ms = dev(mc), dev(ms)
+            self.vec_mc, self.vec_ms = (torch.empty(b, device=device, dtype=torch.float32) for _ in range(2))
+            self.data, self.mask = torch.empty_like(self.x), torch.empty_like(self.x)
+            self.noise_m = [torch.zeros_like(self.x) for _ in range(2)]      # merge after corrector, after predictor
         self.ready = True
 
     # ---- one PC step (recorded into a graph) ---------------------------------------------------------
@@ -83,33 +114,72 @@ class FusedPCSampler:
             K.ve_perturb(self.y, self.noise_y[which], self.plan.in1, self.t_sigma_y, self.step_idx, 0)
         self.plan.launch()
 
+    def _corrector(self, fresh_condition):
+        p = self.plan
+        for k in range(self.c_steps):
+            if k == 0 and fresh_condition:
+                self._score(0)
+            else:
+                p.launch()   # same condition for every inner Langevin iteration (and, on a path, as the predictor)
+            if self.draw_noise:
+                self.noise_x[0].normal_()
+            K.langevin_norms(self.score, self.noise_x[0], self.norms)
+            K.langevin_update(self.x, self.score, self.noise_x[0], self.norms, self.x, self.x_mean, self.snr,
+                              self.t_alpha, self.step_idx, 0)
+
+    def _predictor(self, fresh_condition):
+        if fresh_condition:
+            self._score(1)
+        else:
+            self.plan.launch()
+        if self.draw_noise:
+            self.noise_x[1].normal_()
+        if self.predictor == "reverse_diffusion":
+            K.reverse_diffusion_update(self.x, self.score, self.noise_x[1], self.x, self.x_mean, self.t_lin,
+                                       self.t_g, self.probability_flow, self.step_idx, 0)
+        else:
+            K.euler_maruyama_update(self.x, self.score, self.noise_x[1], self.x, self.x_mean, self.t_lin, self.t_g,
+                                    -1.0 / self.c_sde.N, self.probability_flow, self.step_idx, 0)
+
+    def _merge(self, which):
+        """Inpainting: x <- x (1 - mask) + (mean_coef data + std z) mask, x_mean likewise without the noise
+        (sampling/unconditional.py:259-275), in place on the network's input buffer."""
+        if self.draw_noise:
+            self.noise_m[which].normal_()
+        K.inpaint_merge(self.x, self.data, self.noise_m[which], self.mask, self.x, self.x_mean, self.vec_mc, self.vec_ms)
+
     def _step(self):
         p = self.plan
         K.broadcast_table(p.labels, self.t_labels, self.step_idx, 0)
         K.broadcast_table(p.row_scale, self.t_inv_x, self.step_idx, 0)
         if self.t_inv_y is not None:
             K.broadcast_table(p.row_scale1, self.t_inv_y, self.step_idx, 0)
-        if self.corrector == "langevin":
-            for k in range(self.c_steps):
-                if k == 0:
-                    self._score(0)
-                else:
-                    p.launch()   # same perturbed condition for every inner Langevin iteration
-                if self.draw_noise:
-                    self.noise_x[0].normal_()
-                K.langevin_norms(self.score, self.noise_x[0], self.norms)
-                K.langevin_update(self.x, self.score, self.noise_x[0], self.norms, self.x, self.x_mean, self.snr,
-                                  self.t_alpha, self.step_idx, 0)
-        if self.predictor != "none":
-            self._score(1)
+        if self.use_path:
+            # y_t ~ p(y_t | y_0, y_{t+tau}) in place on the network's condition input, then predictor and corrector on it
+            K.broadcast_table(self.vec_a, self.t_pa, self.step_idx, 0)
+            K.broadcast_table(self.vec_b, self.t_pb, self.step_idx, 0)
+            K.broadcast_table(self.vec_s, self.t_ps, self.step_idx, 0)
             if self.draw_noise:
-                self.noise_x[1].normal_()
-            if self.predictor == "reverse_diffusion":
-                K.reverse_diffusion_update(self.x, self.score, self.noise_x[1], self.x, self.x_mean, self.t_lin,
-                                           self.t_g, self.probability_flow, self.step_idx, 0)
-            else:
-                K.euler_maruyama_update(self.x, self.score, self.noise_x[1], self.x, self.x_mean, self.t_lin, self.t_g,
-                                        -1.0 / self.c_sde.N, self.probability_flow, self.step_idx, 0)
+                self.noise_y[1].normal_()
+            K.sde_perturb(self.y, p.in1, self.y_tmp, self.vec_a, self.vec_b)
+            K.sde_perturb(self.y_tmp, self.noise_y[1], p.in1, None, self.vec_s)
+            if self.predictor != "none":
+                self._predictor(False)
+            if self.corrector == "langevin":
+                self._corrector(False)
+            K.step_advance(self.step_idx)
+            return
+        if self.inpaint:
+            K.broadcast_table(self.vec_mc, self.t_mc, self.step_idx, 0)
+            K.broadcast_table(self.vec_ms, self.t_ms, self.step_idx, 0)
+        if self.corrector == "langevin":
+            self._corrector(True)
+        if self.inpaint:
+            self._merge(0)
+        if self.predictor != "none":
+            self._predictor(True)
+        if self.inpaint:
+            self._merge(1)
         K.step_advance(self.step_idx)
 
     def _graph(self, draw_noise):
@@ -119,7 +189,7 @@ class FusedPCSampler:
             rng_state = torch.cuda.get_rng_state(self.x.device)   # warm-up must not consume the caller's stream
             for _ in range(2):               # warm-up outside capture (lazy init, the plan's own warm-up)
                 self.x.normal_()
-                for n in self.noise_x + (self.noise_y if self.conditional else []):
+                for n in self.noise_x + (self.noise_y if self.conditional else []) + (self.noise_m if self.inpaint else []):
                     n.normal_()
                 self.step_idx.zero_()
                 self._step()
@@ -134,9 +204,11 @@ class FusedPCSampler:
 
     # ---- public ----------------------------------------------------------------------------------------
     @torch.no_grad()
-    def sample(self, y=None, x_init=None, noise_source=None, show_evolution=False, use_graph=True):
-        """Run the full loop. noise_source(name, step, inner) -> tensor replaces the generator
-        (names 'y_c', 'x_c', 'y_p', 'x_p')."""
+    def sample(self, y=None, x_init=None, noise_source=None, show_evolution=False, use_graph=True, data=None,
+               mask=None):
+        """Run the full loop. noise_source(name, step, inner) -> tensor replaces the generator (names 'y_c', 'x_c',
+        'y_p', 'x_p'; on a path 'y_T' (step -1) and 'y_p'; inpainting adds 'z_c', 'z_p' for the merge draws).
+        data, mask: the known image and its mask (inpainting only)."""
         device = self.model.device
         if self.ready:
             # the network may have new weights (load_state_dict, optimizer step, EMA swap through `.data`) or new
@@ -164,11 +236,30 @@ class FusedPCSampler:
         self.x.copy_(x_init.to(device=device, dtype=torch.float32))
         self.step_idx.zero_()
         evolution = {"x": [], "y": []}
+        if self.use_path:
+            # y_{T+tau} = y + sigma_y(T + tau) z starts the path (sampling/conditional.py:141-143)
+            z_T = noise_source("y_T", -1, 0) if injected else torch.randn_like(self.y)
+            K.sde_perturb(self.y, z_T.to(device=device, dtype=torch.float32).contiguous(), self.plan.in1, None, self.std_T)
+        if self.inpaint:
+            if data is None or mask is None:
+                raise ValueError("the inpainter needs data and mask")
+            self.data.copy_(data.to(device=device, dtype=torch.float32))
+            self.mask.copy_(mask.to(device=device, dtype=torch.float32).expand_as(self.data))
+            # x = data * mask + prior * (1 - mask) (sampling/unconditional.py:300): the merge kernel with coefficient 1, std 0
+            self.vec_ms.zero_()
+            K.inpaint_merge(self.x, self.data, self.noise_m[0], self.mask, self.x, self.x_mean, None, self.vec_ms)
+            if show_evolution:
+                evolution["x"].append(self.x.cpu())
         for i in range(self.p_steps):
             if injected:
-                if self.conditional:
+                if self.use_path:
+                    self.noise_y[1].copy_(noise_source("y_p", i, 0))
+                elif self.conditional:
                     self.noise_y[0].copy_(noise_source("y_c", i, 0))
                     self.noise_y[1].copy_(noise_source("y_p", i, 0))
+                if self.inpaint:
+                    self.noise_m[0].copy_(noise_source("z_c", i, 0))
+                    self.noise_m[1].copy_(noise_source("z_p", i, 0))
                 if self.corrector == "langevin":
                     self.noise_x[0].copy_(noise_source("x_c", i, 0))
                 if self.predictor != "none":

@@ -21,6 +21,10 @@ _FUSED_CORRECTORS = {"langevin": "langevin", "none": "none", "conditional_langev
                      "conditional_none": "none"}
 
 
+# get_pc_inpainter on the fused CUDA-graph loop (False keeps the per-step Python loop; A/B switch for the parity tests)
+FUSED_INPAINT = True
+
+
 def _registry_name(cls, registry):
     if cls is None:
         return "none"
@@ -128,7 +132,20 @@ def get_pc_inpainter(sde, predictor, corrector, snr, n_steps=1, probability_flow
         return K.inpaint_merge(x.contiguous(), data, z, mask, torch.empty_like(x), torch.empty_like(x),
                                mean_coef.float().contiguous(), std.float().contiguous())
 
-    def pc_inpainter(model, data, mask, show_evolution=False, x_init=None):
+    kinds = fused_kinds(predictor, corrector)
+    cache = {}
+
+    def pc_inpainter(model, data, mask, show_evolution=False, x_init=None, noise_source=None):
+        if kinds is not None and hasattr(model, "_engine") and FUSED_INPAINT:
+            key = (id(model), tuple(data.shape))
+            fs = cache.get(key)
+            if fs is None:
+                fs = fused.FusedPCSampler(model, sde, tuple(data.shape), kinds[0], kinds[1], snr, sde.N, n_steps,
+                                          probability_flow, continuous, denoise, eps, conditional=False, inpaint=True)
+                cache[key] = fs
+            samples, evo = fs.sample(x_init=x_init, noise_source=noise_source, show_evolution=show_evolution, data=data,
+                                     mask=mask)
+            return samples, ({"evolution": torch.stack(evo["x"])} if show_evolution else {})
         with torch.no_grad():
             data = data.contiguous().float()
             mask = mask.expand_as(data).contiguous().float()

@@ -242,3 +242,66 @@ def test_pc_conditional_use_path_vs_oracle_replayed_noise():
         print(f"[use_path] step {i}: rel {_rel(evo[i], rec[i]):.3e}")
     assert _rel(evo[0], rec[0]) < STATE_TOL
     assert _rel(got, ref) < 5 * STATE_TOL
+
+
+def test_use_path_and_inpainter_run_on_the_graph_loop(monkeypatch):
+    """use_path=True and get_pc_inpainter run on the fused CUDA-graph loop (one graph replay per PC step,
+    coefficients from device tables) and reproduce the per-step Python loop they replace under the same seed - same
+    kernels, same draw order, so the captured generator draws must line up with the eager ones."""
+    from conditional_score_diffusion_b200.sampling import conditional, fused, unconditional
+    sampling, sde_lib, utils = _pkg()
+    launches = []
+    orig = fused.FusedPCSampler.sample
+
+    def counting(self, *a, **k):
+        launches.append((self.use_path, self.inpaint))
+        return orig(self, *a, **k)
+    monkeypatch.setattr(fused.FusedPCSampler, "sample", counting)
+
+    # --- use_path ---
+    f, m = _model("paired")
+    p = golden()["pc_conditional"]
+    y = p["y"]
+    g = torch.Generator().manual_seed(33)
+    x_init = torch.randn(y.shape, generator=g) * p["sigma_max_x"]
+    sde = {"x": sde_lib.cVESDE(p["sigma_min_x"], p["sigma_max_x"], p["N"]), "y": sde_lib.VESDE(p["sigma_min_y"], p["sigma_max_y"], p["N"])}
+    outs = {}
+    for fused_on in (False, True):
+        monkeypatch.setattr(conditional, "FUSED_PATH", fused_on)
+        fn = conditional.get_pc_conditional_sampler(sde, tuple(y.shape), sampling.get_predictor("conditional_reverse_diffusion"),
+                                                    sampling.get_corrector("conditional_langevin"), snr=p["snr"], p_steps=5,
+                                                    c_steps=1, continuous=True, denoise=True, use_path=True, eps=p["eps"])
+        torch.manual_seed(79)
+        outs[fused_on] = fn(m, y.cuda(), show_evolution=True, x_init=x_init)
+    assert launches == [(True, False)]
+    e_loop, e_graph = outs[False][1]["evolution"], outs[True][1]["evolution"]
+    for i in range(5):
+        print(f"[use_path graph vs loop] step {i}: x rel {_rel(e_graph['x'][i], e_loop['x'][i]):.3e} "
+              f"y rel {_rel(e_graph['y'][i], e_loop['y'][i]):.3e}")
+    assert _rel(e_graph["y"][-1], e_loop["y"][-1]) < 1e-5          # the condition path is fp32 elementwise work
+    assert _rel(outs[True][0], outs[False][0]) < 5 * STATE_TOL
+
+    # --- inpainter ---
+    launches.clear()
+    f, m = _model("cifar")
+    g = torch.Generator().manual_seed(34)
+    data = torch.rand(2, 3, 16, 16, generator=g)
+    mask = torch.ones_like(data)
+    mask[:, :, 2:9, 4:12] = 0.0
+    x_init = torch.randn(2, 3, 16, 16, generator=g) * 50
+    sde_u = sde_lib.VESDE(0.01, 50, 5)
+    outs = {}
+    for fused_on in (False, True):
+        monkeypatch.setattr(unconditional, "FUSED_INPAINT", fused_on)
+        fn = unconditional.get_pc_inpainter(sde_u, sampling.get_predictor("reverse_diffusion"), sampling.get_corrector("langevin"),
+                                            snr=0.16, n_steps=1, continuous=True, denoise=True, eps=1e-5)
+        torch.manual_seed(80)
+        outs[fused_on] = fn(m, data.cuda(), mask.cuda(), show_evolution=True, x_init=x_init)
+    assert launches == [(False, True)]
+    e_loop, e_graph = outs[False][1]["evolution"], outs[True][1]["evolution"]
+    assert e_loop.shape == e_graph.shape
+    for i in range(e_loop.shape[0]):
+        print(f"[inpaint graph vs loop] state {i}: rel {_rel(e_graph[i], e_loop[i]):.3e}")
+    assert _rel(e_graph[0], e_loop[0]) < 1e-6
+    assert _rel(outs[True][0], outs[False][0]) < 5 * STATE_TOL
+    assert torch.allclose(outs[True][0].cpu() * mask, data * mask, atol=1e-6)
