@@ -680,6 +680,17 @@ def run_b200(args):
     tap_ms, tap_fl = sum(r[0] for r in tap), sum(r[1] for r in tap)
     top = max(rows, key=lambda r: r[0])
     achieved = tp_fl / (tp_ms * 1e-3) / 1e12
+    # per-shape table of the dominant kernel: launches of one forward grouped by (H, W, C_out, K without identity rows)
+    shapes = {}
+    for ms_, fl_, shp_, _, _ in tp:
+        e = shapes.setdefault(tuple(shp_), [0, 0.0, 0.0])
+        e[0] += 1
+        e[1] += ms_
+        e[2] += fl_
+    per_shape = [{"h_w_n_k": list(k), "launches": v[0], "ms": round(v[1], 4),
+                  "tflops": round(v[2] / (v[1] * 1e-3) / 1e12, 1),
+                  "frac": round(v[2] / (v[1] * 1e-3) / 1e12 / peaks["bf16_tflops"], 3)}
+                 for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])]
     roofline = {"bound": "tensor", "kernel": "conv_halo_tp_kernel (persistent tcgen05 implicit-GEMM 3x3 conv, fused "
                                              "GroupNorm+SiLU prologue)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
@@ -689,6 +700,7 @@ def run_b200(args):
                 "avg_launch_ms": tp_ms / max(1, len(tp)), "algorithmic_gflop_per_launch": tp_fl / 1e9 / max(1, len(tp)),
                 "ms_per_forward_in_kernel": tp_ms, "share_of_step": 2 * tp_ms / ms_per_step,
                 "top_launch": {"ms": top[0], "tflops": top[1] / (top[0] * 1e-3) / 1e12, "h_w_n_k": top[2]},
+                "per_shape": per_shape,
                 "other_tcgen05_kernel": {"kernel": "conv_gemm_kernel (per-tap implicit GEMM: <= 20 px levels, 1x1, "
                                                    "stride 2, attention GEMMs)",
                                          "launches_per_forward": len(tap), "ms_per_forward": tap_ms,

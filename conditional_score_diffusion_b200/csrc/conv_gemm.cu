@@ -20,6 +20,8 @@
 #include "../../include/csd_b200.h"
 
 #include <algorithm>
+#include <utility>
+#include <vector>
 #include <cstdlib>
 
 namespace csd {
@@ -55,6 +57,8 @@ constexpr int kTapThreads = kConvThreads + 32 * (kTapProducers - 1);   // warps 
 constexpr int kMaxStages = 12;
 constexpr uint32_t kLayoutSw64 = 4;
 
+constexpr int kMaxSched = 256;   // chunk schedule entries of the transposed kernel (more chunks: segment order)
+
 struct ConvGemmKernelParams {
   int B, H, W, TW, TH, TB;
   int tiles_w, tiles_h;
@@ -67,6 +71,15 @@ struct ConvGemmKernelParams {
   int wt_k_off;
   int a_batch_step;
   int num_stages, tmem_cols;
+  // transposed kernel: the order in which the (segment, chunk) pairs of a tile are walked - the same for the halo
+  // producer, the weight producers, the transform warps and the MMA issuer. Short 1-tap chunks (two MMAs per pixel
+  // halo: skip 1x1 convolutions, identity residuals) are spread between the 9-tap chunks (18 MMAs), so their TMA
+  // latency hides behind tensor work instead of draining the 3-4 deep halo ring at the end of every tile.
+  int b_box_rows;                        // weight rows per slab that TMA actually writes (<= 128; see conv_gemm_prepare)
+  int n_sched;                           // chunks per tile
+  int sched_tab;                         // 1: sched_seg / sched_chunk hold the order; 0: segment order (too many chunks)
+  unsigned char sched_seg[kMaxSched], sched_chunk[kMaxSched];
+  int seg_tab_base[CSD_MAX_SEGMENTS];    // first (scale, shift) slot of the segment in the coefficient table
   int ksplit;     // per-tap kernel: split-K over gridDim.z (each z computes a contiguous range of the (segment, tap, chunk)
                   // iterations and writes raw fp32 partial sums; csd_splitk_reduce_bf16 finishes the epilogue)
   int producers;  // per-tap kernel: issuing threads; num_stages is a multiple of it, so a ring slot always belongs to
@@ -680,6 +693,17 @@ constexpr int kPBarBytes = 8 * (3 * kMaxAStages + 2 * kPMaxBStages + 4 + 1) + 8;
 struct TileCoord {
   int b, h0, w0, n0, sp;
 };
+// i-th (segment, chunk) of a tile in schedule order
+__device__ __forceinline__ void sched_at(const ConvGemmKernelParams& p, int i, int& s, int& c) {
+  if (p.sched_tab) {
+    s = p.sched_seg[i];
+    c = p.sched_chunk[i];
+  } else {
+    s = 0;
+    while (i >= p.seg_chunks[s]) { i -= p.seg_chunks[s]; ++s; }
+    c = i;
+  }
+}
 __device__ __forceinline__ TileCoord decode_tile(const ConvGemmKernelParams& p, int tile) {
   TileCoord t;
   const int nb = tile % p.n_blocks;
@@ -751,19 +775,19 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         CSD_TSP(10);
-        for (int s = 0; s < p.nseg; ++s) {
+        for (int i = 0; i < p.n_sched; ++i) {
+          int s, c;
+          sched_at(p, i, s, c);
           const CUtensorMap* mapA = (s == 0) ? &mapA0 : (s == 1) ? &mapA1 : (s == 2) ? &mapA2 : &mapA3;
           const int halo = (p.seg_taps[s] == 9) ? 1 : 0;
           const uint32_t a_bytes = (uint32_t)((kHaloTW + 2 * halo) * (p.t_rows + 2 * halo) * kRowBytes);
-          for (int c = 0; c < p.seg_chunks[s]; ++c) {
-            if (p.debug_nodata & 2) continue;
-            ptx::mbar_wait(a_empty0 + 8u * sa, a_par);
-            if (s == 0 && c == 0) CSD_TSP(11);
-            ptx::mbar_arrive_expect_tx(a_full0 + 8u * sa, a_bytes);
-            ptx::tma_load_4d(a_base + sa * p.a_stage_bytes, mapA, a_full0 + 8u * sa, p.seg_coff[s] + c * CH,
-                             tc.w0 - halo, tc.h0 - halo, tc.b);
-            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
-          }
+          if (p.debug_nodata & 2) continue;
+          ptx::mbar_wait(a_empty0 + 8u * sa, a_par);
+          if (i == 0) CSD_TSP(11);
+          ptx::mbar_arrive_expect_tx(a_full0 + 8u * sa, a_bytes);
+          ptx::tma_load_4d(a_base + sa * p.a_stage_bytes, mapA, a_full0 + 8u * sa, p.seg_coff[s] + c * CH,
+                           tc.w0 - halo, tc.h0 - halo, tc.b);
+          if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
         }
       }
     }
@@ -776,22 +800,21 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       uint32_t sb = 0, b_par = 1;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
-        for (int s = 0; s < p.nseg; ++s) {
+        for (int i = 0; i < p.n_sched; ++i) {
+          int s, c;
+          sched_at(p, i, s, c);
           const int taps = p.seg_taps[s];
-          const int nchunks = p.seg_chunks[s];
           const int kstep = ((p.seg_ccnt[s] + kChunkK - 1) / kChunkK) * kChunkK;   // K columns of one tap in Wt (ceil32)
-          for (int c = 0; c < nchunks; ++c) {
-            int kcol = p.wt_k_off + p.seg_kbase[s] * kChunkK + c * CH;
-            for (int tap = 0; tap < taps; ++tap, kcol += kstep) {
-              if (p.debug_nodata & 1) continue;   // perf experiment: no weight traffic
-              if (turn == me) {
-                ptx::mbar_wait(b_empty0 + 8u * sb, b_par);
-                ptx::mbar_arrive_expect_tx(b_full0 + 8u * sb, kTChan * kRowBytes);
-                ptx::tma_load_3d(b_base + sb * p.b_stage_bytes, &mapB, b_full0 + 8u * sb, kcol, tc.n0, 0);
-              }
-              if (++turn == kPBProducers) turn = 0;
-              if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
+          int kcol = p.wt_k_off + p.seg_kbase[s] * kChunkK + c * CH;
+          for (int tap = 0; tap < taps; ++tap, kcol += kstep) {
+            if (p.debug_nodata & 1) continue;   // perf experiment: no weight traffic
+            if (turn == me) {
+              ptx::mbar_wait(b_empty0 + 8u * sb, b_par);
+              ptx::mbar_arrive_expect_tx(b_full0 + 8u * sb, (uint32_t)p.b_box_rows * kRowBytes);
+              ptx::tma_load_3d(b_base + sb * p.b_stage_bytes, &mapB, b_full0 + 8u * sb, kcol, tc.n0, 0);
             }
+            if (++turn == kPBProducers) turn = 0;
+            if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
           }
         }
       }
@@ -815,54 +838,51 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         CSD_TSP(0);
         const uint32_t d_tmem = tmem_base + acc * kTPix;
         uint32_t accumulate = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const int nchunks = p.seg_chunks[s];
+        constexpr int pitch9 = kHaloTW + 2;
+        const uint32_t x_hi9 = ptx::smem_desc_hi(pitch9 * kRowBytes, kLayoutSw64);
+        const uint32_t x_hi1 = ptx::smem_desc_hi(kHaloTW * kRowBytes, kLayoutSw64);
+        for (int i = 0; i < p.n_sched; ++i) {
+          int s, c;
+          sched_at(p, i, s, c);
           if (p.seg_taps[s] == 9) {
-            constexpr int pitch = kHaloTW + 2;
-            const uint32_t x_hi = ptx::smem_desc_hi(pitch * kRowBytes, kLayoutSw64);
-            for (int c = 0; c < nchunks; ++c) {
-              if (!(p.debug_nodata & 2)) ptx::mbar_wait(a_go0 + 8u * sa, a_par);
-              ptx::tcgen05_fence_after();
-              if (s == 0 && c == 0) CSD_TSP(1);
-              if (s == 0 && c == 1) CSD_TSP(13);
-              const uint32_t x_lo0 = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
-              bool b_ready = ptx::mbar_test_wait(b_full0 + 8u * sb, b_par);
+            if (!(p.debug_nodata & 2)) ptx::mbar_wait(a_go0 + 8u * sa, a_par);
+            ptx::tcgen05_fence_after();
+            if (i == 0) CSD_TSP(1);
+            if (i == 1) CSD_TSP(13);
+            const uint32_t x_lo0 = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
+            bool b_ready = ptx::mbar_test_wait(b_full0 + 8u * sb, b_par);
 #pragma unroll
-              for (int tap = 0; tap < 9; ++tap) {
-                if (!b_ready && !(p.debug_nodata & 1)) ptx::mbar_wait(b_full0 + 8u * sb, b_par);
-                ptx::tcgen05_fence_after();
-                // test the next slab's barrier before issuing this slab's MMAs (latency overlaps with tensor work)
-                uint32_t nsb = sb + 1, nb_par = b_par;
-                if (nsb == (uint32_t)p.b_stages) { nsb = 0; nb_par ^= 1u; }
-                b_ready = ptx::mbar_test_wait(b_full0 + 8u * nsb, nb_par);
-                const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
-                const uint32_t x_lo = x_lo0 + (uint32_t)((((tap / 3) * pitch + (tap % 3)) * kRowBytes) >> 4);
-                mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi, x_lo), idesc, accumulate);
-                mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi, x_lo + 2), idesc, 1u);
-                accumulate = 1u;
-                ptx::mma_commit(b_empty0 + 8u * sb);
-                sb = nsb;
-                b_par = nb_par;
-              }
-              ptx::mma_commit(a_empty0 + 8u * sa);
-              if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
-            }
-          } else {
-            const uint32_t x_hi = ptx::smem_desc_hi(kHaloTW * kRowBytes, kLayoutSw64);
-            for (int c = 0; c < nchunks; ++c) {
-              ptx::mbar_wait(a_go0 + 8u * sa, a_par);
-              ptx::mbar_wait(b_full0 + 8u * sb, b_par);
+            for (int tap = 0; tap < 9; ++tap) {
+              if (!b_ready && !(p.debug_nodata & 1)) ptx::mbar_wait(b_full0 + 8u * sb, b_par);
               ptx::tcgen05_fence_after();
-              const uint32_t x_lo = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
+              // test the next slab's barrier before issuing this slab's MMAs (latency overlaps with tensor work)
+              uint32_t nsb = sb + 1, nb_par = b_par;
+              if (nsb == (uint32_t)p.b_stages) { nsb = 0; nb_par ^= 1u; }
+              b_ready = ptx::mbar_test_wait(b_full0 + 8u * nsb, nb_par);
               const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
-              mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi, x_lo), idesc, accumulate);
-              mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi, x_lo + 2), idesc, 1u);
+              const uint32_t x_lo = x_lo0 + (uint32_t)((((tap / 3) * pitch9 + (tap % 3)) * kRowBytes) >> 4);
+              mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi9, x_lo), idesc, accumulate);
+              mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi9, x_lo + 2), idesc, 1u);
               accumulate = 1u;
               ptx::mma_commit(b_empty0 + 8u * sb);
-              if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
-              ptx::mma_commit(a_empty0 + 8u * sa);
-              if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+              sb = nsb;
+              b_par = nb_par;
             }
+            ptx::mma_commit(a_empty0 + 8u * sa);
+            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+          } else {
+            if (!(p.debug_nodata & 2)) ptx::mbar_wait(a_go0 + 8u * sa, a_par);
+            if (!(p.debug_nodata & 1)) ptx::mbar_wait(b_full0 + 8u * sb, b_par);
+            ptx::tcgen05_fence_after();
+            const uint32_t x_lo = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
+            const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
+            mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi1, x_lo), idesc, accumulate);
+            mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi1, x_lo + 2), idesc, 1u);
+            accumulate = 1u;
+            ptx::mma_commit(b_empty0 + 8u * sb);
+            if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
+            ptx::mma_commit(a_empty0 + 8u * sa);
+            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
           }
         }
         CSD_TSP(2);
@@ -902,16 +922,18 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           asm volatile("bar.sync 2, 256;" ::: "memory");
           tab_b = tc.b;
         }
-        int base = 0;
-        for (int s = 0; s < p.nseg; ++s) {
+        for (int i = 0; i < p.n_sched; ++i) {
+          int s, c;
+          sched_at(p, i, s, c);
+          const int base = p.seg_tab_base[s];
           const bool norm = p.seg_norm[s] != nullptr;
           const bool act = p.seg_silu[s] != 0;
           const int halo = (p.seg_taps[s] == 9) ? 1 : 0;
           const int pitch = kHaloTW + 2 * halo;
           const int rows = pitch * (p.t_rows + 2 * halo);
-          for (int c = 0; c < p.seg_chunks[s]; ++c) {
+          {
             ptx::mbar_wait(a_full0 + 8u * sa, a_par);
-            if (tt == 0 && s == 0 && c == 0) CSD_TSP(8);
+            if (tt == 0 && i == 0) CSD_TSP(8);
             if (norm) {
               uint4* st = reinterpret_cast<uint4*>(__cvta_shared_to_generic(a_base + sa * p.a_stage_bytes));
               // (scale, shift) pairs of this thread's 16-byte unit: 8 bf16 channels (4 float4) or 4 fp32 channels (2)
@@ -978,10 +1000,9 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
               ptx::fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async reads
             }
             ptx::mbar_arrive(a_ready0 + 8u * sa);
-            if (tt == 0 && s == 0 && c == 0) CSD_TSP(9);
+            if (tt == 0 && i == 0) CSD_TSP(9);
             if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
           }
-          base += p.seg_chunks[s] * CH;
         }
       }
     }
@@ -1398,7 +1419,10 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     const uint64_t row_bytes = (uint64_t)(d->wt_pitch > 0 ? d->wt_pitch : d->k_total) * E;
     uint64_t strides[2] = {row_bytes, d->wt_batch_stride != 0 ? (uint64_t)d->wt_batch_stride * E
                                                                : row_bytes * (uint64_t)d->wt_rows};
-    uint32_t box[3] = {(uint32_t)(halo_mode ? halo_chunk : tap_chunk), (uint32_t)(t_mode ? kTChan : p.n_sub), 1};
+    // (a slab box that stops at the last stored channel - 96 instead of 128 rows, a quarter less weight fill - was
+    //  measured neutral: 28.79 vs 28.68 ms per step; the full box stays)
+    p.b_box_rows = kTChan;
+    uint32_t box[3] = {(uint32_t)(halo_mode ? halo_chunk : tap_chunk), (uint32_t)(t_mode ? p.b_box_rows : p.n_sub), 1};
     int st = encode_tensor_map(&L->mapB, tm_dtype, 3, d->wt, dims, strides, box,
                                (!halo_mode && tap_row_bytes == 128) ? TMA_SW_128 : TMA_SW_64);
     if (st != CSD_OK) return st;
@@ -1497,6 +1521,31 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     if (t_mode) L->grid.y = (unsigned)ceil_div(d->n_store, kTChan);
     L->persistent = false;
     if (t_mode) {
+      // chunk schedule: 1-tap chunks spread evenly behind the 9-tap chunks (see ConvGemmKernelParams::sched_seg)
+      {
+        std::vector<std::pair<int, int>> nine, one, order;
+        int tab = 0;
+        for (int s = 0; s < d->nseg; ++s) {
+          p.seg_tab_base[s] = tab;
+          tab += p.seg_chunks[s] * halo_chunk;
+          for (int c = 0; c < p.seg_chunks[s]; ++c) (p.seg_taps[s] == 9 ? nine : one).push_back({s, c});
+        }
+        p.n_sched = (int)(nine.size() + one.size());
+        const bool interleave = !nine.empty() && !one.empty() && p.n_sched <= kMaxSched &&
+                                getenv("CSD_NO_CHUNK_INTERLEAVE") == nullptr;
+        if (interleave) {
+          const size_t n9 = nine.size(), n1 = one.size();
+          for (size_t i = 0; i < n9; ++i) {      // (1-tap chunks in front of their 9-tap chunk measured the same)
+            order.push_back(nine[i]);
+            for (size_t j = i * n1 / n9; j < (i + 1) * n1 / n9; ++j) order.push_back(one[j]);
+          }
+          for (int i = 0; i < p.n_sched; ++i) {
+            p.sched_seg[i] = (unsigned char)order[i].first;
+            p.sched_chunk[i] = (unsigned char)order[i].second;
+          }
+        }
+        p.sched_tab = interleave ? 1 : 0;
+      }
       // persistent kernel: one CTA per SM, whole shared memory
       L->persistent = true;
       p.n_blocks = ceil_div(d->n_store, kTChan);
