@@ -911,7 +911,8 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           for (int s = 0; s < p.nseg; ++s) {
             const int nch = p.seg_chunks[s] * CH;
             const float2* src = reinterpret_cast<const float2*>(p.seg_norm[s]);
-            const float pre = p.seg_silu[s] ? 0.5f : 1.0f;     // SiLU path stores (sc/2, sh/2)
+            // bf16 SiLU path stores (sc/2, sh/2) for y = h + h tanh(h); the fp32 path evaluates x sigmoid(x) directly
+            const float pre = (p.seg_silu[s] && !kTf32) ? 0.5f : 1.0f;
             for (int i = tt; i < nch; i += kPTransformThreads) {
               float2 v = make_float2(0.f, 0.f);
               if (src != nullptr && i < p.seg_ccnt[s]) v = __ldg(src + (long long)tc.b * p.seg_ccnt[s] + i);
@@ -956,10 +957,11 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
 #pragma unroll
                   for (int i = 0; i < 2; ++i) {
                     float y0 = fmaf(f[2 * i], cf[i].x, cf[i].y), y1 = fmaf(f[2 * i + 1], cf[i].z, cf[i].w);
-                    if (act) {    // coefficients are pre-halved: y = h + h * tanh(h) would cost 2^-11; use the exact form
-                      y0 = 2.f * y0; y1 = 2.f * y1;
-                      y0 = y0 / (1.f + __expf(-y0));
-                      y1 = y1 / (1.f + __expf(-y1));
+                    if (act) {    // tanh.approx would cost 2^-11 (the tf32 rounding itself); ex2.approx + rcp.approx cost
+                                  // ~2^-21 and a third of the instructions of an IEEE division - the transform warps were
+                                  // the tf32 main loop's limiter (4.9k cycles per chunk against 2.3k of tensor work)
+                      y0 = __fdividef(y0, 1.f + __expf(-y0));
+                      y1 = __fdividef(y1, 1.f + __expf(-y1));
                     }
                     f[2 * i] = round_tf32(y0);
                     f[2 * i + 1] = round_tf32(y1);
@@ -1038,8 +1040,10 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                                    : 0.f;
       const int w_lim = min(kHaloTW, p.W - tc.w0);
       const int m_lim_h = (w_lim == kHaloTW) ? min(half_pix, min(p.t_pix, (p.H - tc.h0) * kHaloTW) - half * half_pix) : 0;
+      if (et == 0) CSD_TSP(3);
       ptx::mbar_wait(tmem_full0 + 8u * acc, full_par);
       ptx::tcgen05_fence_after();
+      if (et == 0) CSD_TSP(4);
       const uint32_t t_row = tmem_base + acc * kTPix + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * half_pix);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
@@ -1085,6 +1089,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           if (row0 < p.H) ptx::tma_store_4d(pass == 0 ? &mapOut : &mapOut2, stage_h_addr, tc.n0, tc.w0, row0, tc.b);
           ptx::bulk_commit_group();
         }
+        if (et == 0) { if (pass == 0) CSD_TSP(6); else CSD_TSP(5); }
         store_pending = true;
       }
       ptx::tcgen05_fence_before();

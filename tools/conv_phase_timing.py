@@ -9,10 +9,13 @@ names = {10: "prod tile start", 11: "prod A0 slot free", 8: "xform A0 full", 9: 
          0: "mma acc free", 1: "mma A0 go", 13: "mma A1 go", 2: "mma issued", 3: "epi waits", 4: "epi acc full",
          5: "epi staged", 6: "epi stored", 7: "epi stats"}
 dev = "cuda"
+DT = torch.float32 if os.environ.get("CSD_PRECISION") == "tf32" else torch.bfloat16   # tf32: the fp32 / kind::tf32 instance
+if DT == torch.float32:
+    names[6] = "epi pass A staged"
 for (B, H, cin, cout, full) in ((64, 160, 96, 96, False), (64, 160, 96, 96, True), (64, 160, 192, 96, True), (64, 80, 192, 192, True)):
-    a = torch.randn(B, H, H, cin, device=dev).to(torch.bfloat16)
-    wt = k.pack_conv_weight((torch.randn(cout, cin, 3, 3, device=dev) / 30).to(torch.bfloat16))
-    out = torch.empty(B, H, H, cout, device=dev, dtype=torch.bfloat16)
+    a = torch.randn(B, H, H, cin, device=dev).to(DT)
+    wt = k.pack_conv_weight((torch.randn(cout, cin, 3, 3, device=dev) / 30).to(DT), dtype=DT)
+    out = torch.empty(B, H, H, cout, device=dev, dtype=DT)
     kw = {}
     seg = (a, cin, 0, cin, 9)
     if full:   # what the engine launches: fused GroupNorm prologue, temb, residual, statistics
