@@ -681,7 +681,10 @@ constexpr int kTChan = 128;     // output channels per CTA (M of the MMA)
 // the fill/drain cost is paid once per SM instead of once per tile. The whole 227 KB of shared memory
 // belongs to the CTA: 3 pixel-halo buffers, up to 12 weight slabs, a dedicated 64 KB staging tile.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kPBProducers = 3;                                    // weight-slab producer warps (issue-rate bound)
+#ifndef CSD_PB_PRODUCERS
+#define CSD_PB_PRODUCERS 3
+#endif
+constexpr int kPBProducers = CSD_PB_PRODUCERS;                     // weight-slab producer warps (issue-rate bound)
 constexpr int kPThreads = 576 + 32 * kPBProducers;
 constexpr int kPTransformThreads = 256;
 constexpr int kPEpiThreads = 256;
