@@ -414,13 +414,18 @@ class BlockOps:
                      groups or _groups(c), 1e-6)
         return [coef0] + ([coef1] if s1 is not None else [])
 
+    ragged_tiles = True     # inference plans may run w % 8 != 0 levels in the transposed kernel (bf16, K.T_RAGGED: off)
+
+    def _ragged(self):
+        return self.ragged_tiles and self.act_dtype == BF16
+
     def will_transpose(self, h, w, cout):
         """3x3 stride-1 convolutions with >= 32 output channels on images that tile into 32x8-pixel macro tiles
         run in the persistent transposed kernel (output channels on M, 256 pixels on N); the fp32 plan runs its
         kind::tf32 instance (CSD_NO_TF32_TRANSPOSED=1 keeps the per-tap kernel: A/B switch)."""
         if self.act_dtype != BF16 and not TF32_TRANSPOSED:
             return False
-        return K.TRANSPOSED_DEFAULT and cout >= 32 and cout % 8 == 0 and K.transposed_shape_ok(h, w)
+        return K.TRANSPOSED_DEFAULT and cout >= 32 and cout % 8 == 0 and K.transposed_shape_ok(h, w, self._ragged())
 
     def fusable(self, srcs, cout):
         """GroupNorm+SiLU can ride in the convolution's prologue when the 3x3 conv runs in the transposed mode."""
@@ -428,7 +433,7 @@ class BlockOps:
         if self.act_dtype != BF16 and not TF32_TRANSPOSED:
             return False
         return (K.FUSE_GN_DEFAULT and K.TRANSPOSED_DEFAULT and cout >= 32 and cout % 8 == 0
-                and K.transposed_shape_ok(h, w) and all(a.c % 8 == 0 for a in srcs))
+                and K.transposed_shape_ok(h, w, self._ragged()) and all(a.c % 8 == 0 for a in srcs))
 
     def conv(self, segs, pc, out_hw=None, temb=None, temb_pitch=0, res=None, scale=1.0, stride=1, pad=1,
              out=None, head=False, out_pitch=None):
@@ -442,7 +447,7 @@ class BlockOps:
             out = self.pool.get((b, oh, ow, pc.n_store))
         seg_list = [(sg[0].t, sg[0].pitch, 0, sg[0].c, sg[1], sg[2] if len(sg) > 2 else None, True) for sg in segs]
         use_t = ((head or self.will_transpose(oh, ow, pc.cout))
-                 and K.transposed_eligible(seg_list, oh, ow, stride, pad, allow_1tap=head))
+                 and K.transposed_eligible(seg_list, oh, ow, stride, pad, allow_1tap=head, ragged=self._ragged()))
         if use_t and res is not None and self.act_dtype == BF16:
             raise CsdError("transposed conv takes its residual as an identity K segment (engine planning error)")
         partials = sums = None
@@ -473,13 +478,13 @@ class BlockOps:
     def head_tap_stacked(self, pc, hcur):
         b, h, w, _ = hcur.shape
         return (self.act_dtype == BF16 and self.fast_heads and HEAD_MODE == 3 and K.TRANSPOSED_DEFAULT and K.FUSE_GN_DEFAULT
-                and K.transposed_shape_ok(h, w) and hcur.c % 8 == 0 and pc.cout <= 8 and len(pc.segs) == 1
+                and K.transposed_shape_ok(h, w, self._ragged()) and hcur.c % 8 == 0 and pc.cout <= 8 and len(pc.segs) == 1
                 and len(pc.segs[0]) == 1 and pc.segs[0][0].kind == "conv" and pc.segs[0][0].param.shape[2:] == (3, 3))
 
     def head_in_transposed_kernel(self, pc, hcur):
         b, h, w, _ = hcur.shape
         return (self.act_dtype == BF16 and self.fast_heads and HEAD_MODE in (1, 2) and K.TRANSPOSED_DEFAULT and K.FUSE_GN_DEFAULT
-                and K.transposed_shape_ok(h, w) and hcur.c % 8 == 0 and pc.n_store == 8 and len(pc.segs) == 1)
+                and K.transposed_shape_ok(h, w, self._ragged()) and hcur.c % 8 == 0 and pc.n_store == 8 and len(pc.segs) == 1)
 
     def head(self, gn, pc, hcur, extra, key, res=None):
         """Output head: conv3x3(SiLU(GroupNorm(h))) [+ res] -> the few image channels (models/ncsnpp.py:337-352,

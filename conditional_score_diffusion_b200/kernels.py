@@ -97,16 +97,25 @@ TRANSPOSED_DEFAULT = os.environ.get("CSD_NO_TRANSPOSED", "0") != "1"
 FUSE_GN_DEFAULT = os.environ.get("CSD_NO_FUSE_GN", "0") != "1"
 
 
-def transposed_eligible(segments, h, w, stride=1, pad=1, z_batches=1, allow_1tap=False):
+# Transposed kernel on images whose width is not a multiple of the 8-pixel tile width (20 px level: 3 tile columns, the
+# last one half empty - TMA clips the loads and the store, the epilogue's ragged statistics path counts valid pixels only).
+# bf16 instance only (the fp32 epilogue has no ragged path). Parity-tested, but measured slower than the per-tap kernel +
+# one-launch GroupNorm at that level (29.15 vs 28.96 ms per PC step: 3 tile columns for 2.5, 192 channels on 256 M rows,
+# 384 tiles on 148 SMs), so it is off unless CSD_T_RAGGED=1.
+T_RAGGED = os.environ.get("CSD_T_RAGGED", "0") == "1"
+
+
+def transposed_eligible(segments, h, w, stride=1, pad=1, z_batches=1, allow_1tap=False, ragged=False):
     """3x3 stride-1 convs whose image tiles well into 32x8-pixel macro tiles run in the transposed halo
     mode (output channels on M, 256 pixels on N): measured faster on B200 whenever the 32-row tiling
     wastes < ~20% of the rows (tests/test_gpu_conv_gemm.py::test_transposed_timing)."""
     return ((segments[0][4] == 9 or allow_1tap) and stride == 1 and pad == 1 and z_batches == 1
-            and transposed_shape_ok(h, w))
+            and transposed_shape_ok(h, w, ragged and segments[0][0].dtype == _BF16))
 
 
-def transposed_shape_ok(h, w):
-    return w % 8 == 0 and (h % 32 == 0 or h >= 64 or h % 20 == 0)
+def transposed_shape_ok(h, w, ragged=False):
+    w_ok = w % 8 == 0 or (ragged and T_RAGGED and w >= 16)
+    return w_ok and (h % 32 == 0 or h >= 64 or h % 20 == 0)
 
 
 def transposed_tile_rows(h):
