@@ -134,6 +134,10 @@ _PROTOTYPES = {
                                   c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "csd_fir_resample_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                            c_float_p, c_void_p]),
+    "csd_fir_norm_resample_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                                c_int, c_int, c_float_p, c_void_p]),
+    "csd_fir_norm_resample_nhwc_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                               c_int, c_int, c_float_p, c_void_p]),
     "csd_softmax_rows_f32_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_float, c_void_p]),
     # fp32-activation ("tf32" plan) variants: same argument lists as the *_bf16 entries
     "csd_nchw_to_nhwc_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,

@@ -310,6 +310,11 @@ struct FirNhwcParamsT {
   int batch, h, w, oh, ow, cvec;  // cvec = channel pitch / 8
   float kf[4];                    // flipped, normalised 1-D taps (already x2 for mode 1)
   int round_out;                  // fp32 tensors: round the output to tf32 (it only feeds tensor-core operands)
+  // fused GroupNorm(+SiLU) on the INPUT (TMA-staged kernel only): out = FIR(act(src * scale + shift)) with the
+  // per-(image, channel) (scale, shift) table of gn_coeffs - the normalised tensor never exists in HBM
+  const float2* norm;             // [batch, norm_c] or null
+  int norm_c;                     // channels covered by the table (multiple of 8); channels beyond it stay as loaded
+  int norm_silu;
 };
 using FirNhwcParams = FirNhwcParamsT<bf16x8>;
 
@@ -422,6 +427,36 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap map, const FirNhwcParamsT<VT>
   }
   __syncthreads();
   ptx::mbar_wait(ptx::smem_u32(&bar), 0);
+  if (p.norm != nullptr) {
+    // normalise + activate the staged input tile in place, every sample once (the quad loop below reads each sample
+    // up to 4 / 9 times). Pixels outside the image keep the zeros TMA wrote: the reference resamples the ACTIVATED
+    // tensor with zero padding (models/layerspp.py:245-258 after act(GroupNorm_0(x))).
+    VT* tl = reinterpret_cast<VT*>(fir_smem);
+    const int nvec = T::TI * T::TI * cvs;
+    for (int i = threadIdx.x; i < nvec; i += 256) {
+      const int cv = i % cvs;
+      const int px = (i / cvs) % T::TI, py = i / (cvs * T::TI);
+      const int gy = iy0 + py, gx = ix0 + px;
+      const int c0 = (cc * cvs + cv) * 8;
+      if (gy < 0 || gy >= p.h || gx < 0 || gx >= p.w || c0 + 8 > p.norm_c) continue;
+      float f[8];
+      unpack8(tl[i], f);
+      const float4* cf = reinterpret_cast<const float4*>(p.norm + (long long)b * p.norm_c + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 t4 = __ldg(cf + j);
+        float y0 = fmaf(f[2 * j], t4.x, t4.y), y1 = fmaf(f[2 * j + 1], t4.z, t4.w);
+        if (p.norm_silu) {
+          y0 = silu_act<VT>(y0);
+          y1 = silu_act<VT>(y1);
+        }
+        f[2 * j] = y0;
+        f[2 * j + 1] = y1;
+      }
+      tl[i] = pack8_as<VT>(f);
+    }
+    __syncthreads();
+  }
   const VT* tile = reinterpret_cast<const VT*>(fir_smem);         // [TI][TI][cvs] 8-channel vectors
   // One work item = a 2 x 2 output quad x one 8-channel vector. The quad's input footprint (3 x 3 pixels for up x2,
   // 6 x 6 for down x2) is read and unpacked once and feeds all four outputs: 2.25 / 9 shared-memory vector loads and
@@ -634,8 +669,11 @@ int csd_upfirdn2d_f32(const float* input, const float* kernel, float* output, in
 namespace csd {
 template <typename VT>
 static int fir_resample_launch(const void* src, void* out, const void* add, int batch, int h, int w, int c_pitch, int mode,
-                               const float* taps4_host, cudaStream_t stream) {
+                               const float* taps4_host, cudaStream_t stream, const float* norm = nullptr, int norm_c = 0,
+                               int norm_silu = 0) {
   CSD_REQUIRE(src && out && taps4_host, "fir_resample: null pointer");
+  CSD_REQUIRE(norm == nullptr || (norm_c >= 8 && norm_c % 8 == 0 && norm_c <= c_pitch),
+              "fir_resample: fused GroupNorm table covers %d channels (multiple of 8, <= pitch %d)", norm_c, c_pitch);
   const int round_out = (mode & 0x10) ? 1 : 0;
   mode &= 0xf;
   CSD_REQUIRE(mode >= 1 && mode <= 3, "fir_resample: mode %d (1 = up, 2 = down, 3 = pre-filter)", mode);
@@ -647,6 +685,7 @@ static int fir_resample_launch(const void* src, void* out, const void* add, int 
   p.add = static_cast<const VT*>(add);
   p.batch = batch; p.h = h; p.w = w; p.cvec = c_pitch / 8;
   p.round_out = round_out;
+  p.norm = reinterpret_cast<const float2*>(norm); p.norm_c = norm_c; p.norm_silu = norm_silu;
   p.oh = mode == 1 ? h * 2 : (mode == 2 ? h / 2 : h + 1);
   p.ow = mode == 1 ? w * 2 : (mode == 2 ? w / 2 : w + 1);
   float sum = 0.f;
@@ -660,6 +699,9 @@ static int fir_resample_launch(const void* src, void* out, const void* add, int 
   if (mode != 3 && !per_output && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     return mode == 1 ? launch_fir_tma<1, VT>(p, stream) : launch_fir_tma<2, VT>(p, stream);
   }
+  if (norm != nullptr)
+    return set_error(CSD_ERR_UNSUPPORTED, "fir_resample: the fused GroupNorm input transform needs the TMA-staged kernel "
+                     "(modes 1 / 2, 16-byte aligned source)");
   if (mode == 1) fir_nhwc_kernel<1, VT><<<blocks, 256, 0, stream>>>(p);
   else if (mode == 2) fir_nhwc_kernel<2, VT><<<blocks, 256, 0, stream>>>(p);
   else fir_nhwc_kernel<3, VT><<<blocks, 256, 0, stream>>>(p);
@@ -679,6 +721,19 @@ int csd_fir_resample_nhwc_f32(const void* src, void* out, const void* add, int b
                               int mode, const float* taps4_host, csd_stream_t stream) {
   return csd::fir_resample_launch<csd::f32x8>(src, out, add, batch, h, w, c_pitch, mode, taps4_host,
                                               static_cast<cudaStream_t>(stream));
+}
+
+int csd_fir_norm_resample_nhwc_bf16(const void* src, void* out, const void* add, const float* norm, int norm_c,
+                                    int norm_silu, int batch, int h, int w, int c_pitch, int mode,
+                                    const float* taps4_host, csd_stream_t stream) {
+  return csd::fir_resample_launch<csd::bf16x8>(src, out, add, batch, h, w, c_pitch, mode, taps4_host,
+                                               static_cast<cudaStream_t>(stream), norm, norm_c, norm_silu);
+}
+int csd_fir_norm_resample_nhwc_f32(const void* src, void* out, const void* add, const float* norm, int norm_c,
+                                   int norm_silu, int batch, int h, int w, int c_pitch, int mode,
+                                   const float* taps4_host, csd_stream_t stream) {
+  return csd::fir_resample_launch<csd::f32x8>(src, out, add, batch, h, w, c_pitch, mode, taps4_host,
+                                              static_cast<cudaStream_t>(stream), norm, norm_c, norm_silu);
 }
 
 int csd_tap_shift_sum_bf16(const void* partial, int p_pitch, int cout, const float* bias, const void* res, int res_pitch,

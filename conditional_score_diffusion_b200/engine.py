@@ -542,14 +542,22 @@ class BlockOps:
         """Dropout_0 of the ResNet blocks: identity outside training (nn.Dropout in eval mode)."""
         return a
 
-    def fir(self, a, mode, taps, add=None, operand=True):
+    def fir(self, a, mode, taps, add=None, operand=True, norm=None):
         """operand: the result only feeds convolution operands (fp32 plan: rounded to tf32 on store); False for the
-        output pyramid, which is added to a head's output."""
+        output pyramid, which is added to a head's output. norm: (scale, shift) table of gn_coeffs - the FIR then
+        resamples SiLU(GroupNorm(a)) without that tensor ever reaching HBM."""
         b, h, w, p = a.shape
         oh, ow = {"up": (h * 2, w * 2), "down": (h // 2, w // 2), "prefilter": (h + 1, w + 1)}[mode]
         out = self.pool.get((b, oh, ow, p))
-        self.rec.add(K.fir_resample, a.t, out, mode, list(taps), add.t if add is not None else None, operand)
+        self.rec.add(K.fir_resample, a.t, out, mode, list(taps), add.t if add is not None else None, operand, norm)
         return Act(out, a.c)
+
+    fir_norm = True         # resampling blocks: GroupNorm_0 + SiLU inside the FIR kernel when the sums are known
+
+    def fir_norm_ok(self, srcs):
+        a = srcs[0]
+        return (self.fir_norm and K.FIR_NORM_DEFAULT and len(srcs) == 1 and a.c % 8 == 0
+                and (a.sums is not None or a.pending is not None) and a.t.data_ptr() % 16 == 0)
 
     def release(self, *acts):
         for a in acts:
@@ -579,15 +587,24 @@ class BlockOps:
             for cf in coefs:
                 self.pool.put(cf)
         else:
-            a0 = self.group_norm(srcs, pk["gn0_w"], pk["gn0_b"], True, pk["groups0"])
-            if resample:
+            if resample and self.fir_norm_ok(srcs):
+                # act(GroupNorm_0(x)) is only ever read by the FIR: normalise the staged tile inside that kernel
                 mode = "up" if pk["up"] else "down"
-                assert len(srcs) == 1
-                a0r = self.fir(a0, mode, fir_taps)
-                self.release(a0)
-                a0 = a0r
+                (cf,) = self.gn_coeffs(srcs, pk["gn0_w"], pk["gn0_b"], pk["groups0"])
+                a0 = self.fir(srcs[0], mode, fir_taps, norm=cf)
+                self.pool.put(cf)
                 raw = [self.fir(srcs[0], mode, fir_taps)]
                 own_raw = True
+            else:
+                a0 = self.group_norm(srcs, pk["gn0_w"], pk["gn0_b"], True, pk["groups0"])
+                if resample:
+                    mode = "up" if pk["up"] else "down"
+                    assert len(srcs) == 1
+                    a0r = self.fir(a0, mode, fir_taps)
+                    self.release(a0)
+                    a0 = a0r
+                    raw = [self.fir(srcs[0], mode, fir_taps)]
+                    own_raw = True
             h1 = self.conv([(a0, 9)], pk["conv0"], temb=temb, temb_pitch=tproj_pitch)
             self.release(a0)
         scale = SQRT1_2 if skip_rescale else 1.0

@@ -38,6 +38,7 @@ class TrainOps(BlockOps):
 
     fuse_small_gn = False   # the GroupNorm backward needs every tensor's channel sums
     ragged_tiles = False    # (the training plan keeps the round-1 kernel choice at the 20 px level)
+    fir_norm = False        # the normalised tensor is needed again by the backward pass
     fast_heads = False      # the tape records the plain GroupNorm -> conv (+ epilogue residual) form
     defer_finalize = False  # every activation's channel sums exist as soon as it does (the backward reads them)
 

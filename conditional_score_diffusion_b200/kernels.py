@@ -447,14 +447,29 @@ def gn_fused(src0, c0, src1, c1, gamma, beta, out, groups, eps=1e-6, silu=True, 
     return out
 
 
-def fir_resample(src, out, mode, taps, add=None, round_out=False):
-    """mode 'up' | 'down' | 'prefilter'; src/out NHWC bf16."""
+def fir_resample(src, out, mode, taps, add=None, round_out=False, norm=None, norm_silu=True):
+    """mode 'up' | 'down' | 'prefilter'; src/out NHWC bf16 (fp32 in the tf32 plan). norm: [batch, c, 2] fp32 (scale, shift)
+    table of gn_coeffs - GroupNorm(+SiLU) is then applied to the input on the fly (up / down only)."""
     b, h, w, pitch = src.shape
     arr = (ctypes.c_float * 4)(*[float(t) for t in taps])
-    fn = _lib.lib().csd_fir_resample_nhwc_f32 if src.dtype == torch.float32 else _lib.lib().csd_fir_resample_nhwc_bf16
-    m = {"up": 1, "down": 2, "prefilter": 3}[mode] | (0x10 if (round_out and src.dtype == torch.float32) else 0)
+    f32 = src.dtype == torch.float32
+    m = {"up": 1, "down": 2, "prefilter": 3}[mode] | (0x10 if (round_out and f32) else 0)
+    if norm is not None:
+        assert norm.dtype == torch.float32 and norm.is_cuda and norm.shape[0] == b and norm.shape[2] == 2
+        fn = _lib.lib().csd_fir_norm_resample_nhwc_f32 if f32 else _lib.lib().csd_fir_norm_resample_nhwc_bf16
+        check(fn(_ptr(src), _ptr(out), _ptr(add), _ptr(norm), norm.shape[1], int(bool(norm_silu)), b, h, w, pitch, m, arr,
+                 _stream()))
+        return out
+    fn = _lib.lib().csd_fir_resample_nhwc_f32 if f32 else _lib.lib().csd_fir_resample_nhwc_bf16
     check(fn(_ptr(src), _ptr(out), _ptr(add), b, h, w, pitch, m, arr, _stream()))
     return out
+
+
+# GroupNorm_0 + SiLU of a resampling residual block applied inside the FIR kernel (no normalised tensor in HBM) when the
+# block input's channel sums are already known. Parity-tested, but the FIR kernel is instruction-issue bound and the
+# extra transform costs more than the saved gn_apply pass: 28.48 vs 28.34 ms per PC step (bf16), 52.31 vs 52.10 (tf32).
+# Off unless CSD_FIR_NORM=1.
+FIR_NORM_DEFAULT = os.environ.get("CSD_FIR_NORM", "0") == "1" and os.environ.get("CSD_FIR_PER_OUTPUT") is None
 
 
 def tap_shift_sum(partial, cout, bias, res, out):

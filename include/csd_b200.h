@@ -202,6 +202,18 @@ int csd_gn_coeffs_partials_f32(const float* sums0, const float* partials0, int t
  * models/ncsnpp.py:344-349).                                                                    */
 int csd_fir_resample_nhwc_bf16(const void* src, void* out, const void* add, int batch, int h, int w,
                                int c_pitch, int mode, const float* taps4_host, csd_stream_t stream);
+/* The same with GroupNorm(+SiLU) applied to the INPUT on the fly: out = FIR(act(src * scale + shift)) [+ add], with the
+ * per-(image, channel) fp32 (scale, shift) table `norm` [batch, norm_c, 2] of csd_gn_coeffs_* (norm_c a multiple of 8,
+ * channels >= norm_c are resampled as stored). This is act(GroupNorm_0(x)) followed by upsample_2d / downsample_2d in
+ * ResnetBlockBigGANpp (models/layerspp.py:242-258) without the normalised tensor in HBM; pixels outside the image
+ * contribute zero, as the reference's zero-padded FIR of the activated tensor does. Modes 1 and 2 with a 16-byte aligned
+ * source only (the TMA-staged kernel): CSD_ERR_UNSUPPORTED otherwise. *_f32: the fp32-activation plan.               */
+int csd_fir_norm_resample_nhwc_bf16(const void* src, void* out, const void* add, const float* norm, int norm_c,
+                                    int norm_silu, int batch, int h, int w, int c_pitch, int mode,
+                                    const float* taps4_host, csd_stream_t stream);
+int csd_fir_norm_resample_nhwc_f32(const void* src, void* out, const void* add, const float* norm, int norm_c,
+                                   int norm_silu, int batch, int h, int w, int c_pitch, int mode,
+                                   const float* taps4_host, csd_stream_t stream);
 
 /* ---- fp32-activation variants ("tf32" plan: NHWC fp32 tensors, channel pitch a multiple of 8) ----
  * Same arguments and semantics as their *_bf16 namesakes above; src / out / add / probs are float. tcgen05 kind::tf32

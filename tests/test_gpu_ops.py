@@ -247,6 +247,43 @@ def test_fir_nhwc_vs_oracle(h, c):
         _close(up.permute(0, 3, 1, 2), o_ops.upsample_2d(x.float(), (1, 2, 3, 4)), BF16, "fir up asym")
 
 
+@pytest.mark.parametrize("h,c,pitch", [(16, 96, 96), (40, 192, 192), (20, 40, 48), (6, 8, 8)])
+def test_fir_with_fused_groupnorm_input_vs_oracle(h, c, pitch):
+    """csd_fir_norm_resample_nhwc_*: FIR(SiLU(GroupNorm(x))) with the normalisation applied to the TMA-staged tile -
+    act(GroupNorm_0(x)) -> upsample_2d / downsample_2d of ResnetBlockBigGANpp (models/layerspp.py:242-258) in one pass.
+    bf16 and fp32 tensors; channel pitch > channels (padding channels stay zero); without SiLU as well."""
+    k_ = K()
+    g = torch.Generator().manual_seed(3 * h + c)
+    B = 2
+    groups = min(c // 4, 32)
+    x = (torch.randn(B, c, h, h, generator=g) * 2 + 0.5).to(torch.bfloat16)
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    for dtype, tol in ((torch.bfloat16, BF16), (torch.float32, 2e-5)):
+        xin = x.float() if dtype == torch.float32 else x
+        xn = torch.zeros(B, h, h, pitch, dtype=dtype)
+        xn[..., :c] = xin.permute(0, 2, 3, 1)
+        xn = xn.cuda()
+        sums = torch.empty(B, c, 2, device="cuda")
+        k_.gn_chan_stats(xn, c, sums)
+        coef = torch.empty(B, c, 2, device="cuda")
+        k_.gn_coeffs(sums, c, None, 0, gamma.cuda(), beta.cuda(), coef, None, h * h, groups, 1e-6)
+        for silu in (True, False):
+            gn = F.group_norm(xin.float(), groups, gamma, beta, eps=1e-6)
+            act = F.silu(gn) if silu else gn
+            if dtype == torch.bfloat16:
+                act = act.to(torch.bfloat16).float()          # the staged tile holds the activation in bf16
+            up = torch.full((B, 2 * h, 2 * h, pitch), float("nan"), device="cuda", dtype=dtype)
+            k_.fir_resample(xn, up, "up", [1, 3, 3, 1], norm=coef, norm_silu=silu)
+            _close(up[..., :c].permute(0, 3, 1, 2), o_ops.upsample_2d(act), tol, f"fir(norm) up {h} {c} {dtype} silu={silu}")
+            assert (up[..., c:] == 0).all()
+            dn = torch.full((B, h // 2, h // 2, pitch), float("nan"), device="cuda", dtype=dtype)
+            k_.fir_resample(xn, dn, "down", [1, 3, 3, 1], norm=coef, norm_silu=silu)
+            _close(dn[..., :c].permute(0, 3, 1, 2), o_ops.downsample_2d(act), tol, f"fir(norm) down {h} {c} {dtype}")
+            assert (dn[..., c:] == 0).all()
+    with pytest.raises(Exception):                            # pre-filter mode has no staged tile: refused, not ignored
+        k_.fir_resample(xn, torch.empty(B, h + 1, h + 1, pitch, device="cuda"), "prefilter", [1, 3, 3, 1], norm=coef)
+
+
 def test_layout_softmax_temb_dense():
     k_ = K()
     g = torch.Generator().manual_seed(21)
