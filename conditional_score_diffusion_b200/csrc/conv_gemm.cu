@@ -75,6 +75,7 @@ struct ConvGemmKernelParams {
   // producer, the weight producers, the transform warps and the MMA issuer. Short 1-tap chunks (two MMAs per pixel
   // halo: skip 1x1 convolutions, identity residuals) are spread between the 9-tap chunks (18 MMAs), so their TMA
   // latency hides behind tensor work instead of draining the 3-4 deep halo ring at the end of every tile.
+  int staging_bytes;                     // epilogue staging tile of this launch (1 KB aligned)
   int b_box_rows;                        // weight rows per slab that TMA actually writes (<= 128; see conv_gemm_prepare)
   int n_sched;                           // chunks per tile
   int sched_tab;                         // 1: sched_seg / sched_chunk hold the order; 0: segment order (too many chunks)
@@ -736,7 +737,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   const uint32_t a_base = smem_base;                                   // pixel halos
   const uint32_t b_base = a_base + p.a_stages * p.a_stage_bytes;       // weight slabs
   const uint32_t stage_base = b_base + p.b_stages * p.b_stage_bytes;   // epilogue staging tile (1 KB aligned)
-  const uint32_t bar_base = stage_base + kPStagingBytes;
+  const uint32_t bar_base = stage_base + (uint32_t)p.staging_bytes;
   const uint32_t a_full0 = bar_base, a_empty0 = a_full0 + 8u * kMaxAStages, a_ready0 = a_empty0 + 8u * kMaxAStages;
   const uint32_t b_full0 = a_ready0 + 8u * kMaxAStages, b_empty0 = b_full0 + 8u * kPMaxBStages;
   const uint32_t tmem_full0 = b_empty0 + 8u * kPMaxBStages, tmem_empty0 = tmem_full0 + 16u;
@@ -824,7 +825,13 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    // The whole warp walks the loop converged and one elected lane issues: ring indices, parities and descriptors are
+    // then warp-uniform values the compiler keeps in the uniform datapath. With the loop inside `if (lane == 0)` every
+    // tcgen05 operand went through R2UR moves from a divergent thread's registers, and the issue loop - not the tensor
+    // pipe - set the pace: ~168 cycles per MMA whatever N (profiles/conv_phase_timing_r2.txt: N = 160 tiles at 40 px
+    // cost as much per instruction as N = 256 tiles, with or without operand traffic), against 80 / 112 / 128 cycles for
+    // N = 160 / 224 / 256 in a bare issue loop (tools/mma_rate_probe3.cu).
+    {
       const uint32_t idesc = kTf32 ? ptx::make_idesc_tf32_m128((uint32_t)p.t_pix) : ptx::make_idesc_bf16_m128((uint32_t)p.t_pix);
       const uint32_t w_hi = ptx::smem_desc_hi(512, kLayoutSw64);
       auto mma = [](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
@@ -832,64 +839,93 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         else ptx::mma_bf16_ss(d, ad, bd, id, acc);
       };
       const uint32_t a_go0 = p.has_norm ? a_ready0 : a_full0;
+      // Everything the inner loop touches lives in registers and advances by additions: ring slot -> (descriptor low
+      // word, full / empty barrier address). One thread issues in order, so every dependent load or multiply in front of
+      // an MMA is exposed latency: with `b_base + sb * p.b_stage_bytes` (a constant-bank load + IMAD + R2UR chain per tap)
+      // the bare loop ran at ~148 cycles per MMA whatever N (profiles/conv_phase_timing_r2.txt), the tensor pipe's own
+      // rate being N/2 = 80 / 112 / 128 cycles (tools/mma_rate_probe3.cu).
+      const uint32_t n_b = (uint32_t)p.b_stages, n_a = (uint32_t)p.a_stages;
+      const uint32_t w_step = p.b_stage_bytes >> 4, x_step = p.a_stage_bytes >> 4;
+      const uint32_t w_lo_first = ptx::smem_desc_lo(b_base, 16), x_lo_first = ptx::smem_desc_lo(a_base, 16);
+      const int n_sched = p.n_sched;
+      const uint32_t nodata = (uint32_t)p.debug_nodata;
       uint32_t sa = 0, a_par = 0, sb = 0, b_par = 0;
+      uint32_t w_lo = w_lo_first, bf_bar = b_full0, be_bar = b_empty0;      // weight ring cursor
+      uint32_t x_lo_s = x_lo_first, ag_bar = a_go0, ae_bar = a_empty0;      // halo ring cursor
       uint32_t acc = 0, acc_par = 1;   // a fresh tmem_empty barrier passes a wait on parity 1
+      constexpr int pitch9 = kHaloTW + 2;
+      const uint32_t x_hi9 = ptx::smem_desc_hi(pitch9 * kRowBytes, kLayoutSw64);
+      const uint32_t x_hi1 = ptx::smem_desc_hi(kHaloTW * kRowBytes, kLayoutSw64);
+      const uint64_t w_desc_hi = static_cast<uint64_t>(w_hi) << 32;
+      const uint64_t x9_desc_hi = static_cast<uint64_t>(x_hi9) << 32, x1_desc_hi = static_cast<uint64_t>(x_hi1) << 32;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        CSD_TSP(12);
+        if (lane == 0) CSD_TSP(12);
         ptx::mbar_wait(tmem_empty0 + 8u * acc, acc_par);   // epilogue has drained this accumulator
         ptx::tcgen05_fence_after();
-        CSD_TSP(0);
+        if (lane == 0) CSD_TSP(0);
         const uint32_t d_tmem = tmem_base + acc * kTPix;
         uint32_t accumulate = 0;
-        constexpr int pitch9 = kHaloTW + 2;
-        const uint32_t x_hi9 = ptx::smem_desc_hi(pitch9 * kRowBytes, kLayoutSw64);
-        const uint32_t x_hi1 = ptx::smem_desc_hi(kHaloTW * kRowBytes, kLayoutSw64);
-        for (int i = 0; i < p.n_sched; ++i) {
+        for (int i = 0; i < n_sched; ++i) {
           int s, c;
           sched_at(p, i, s, c);
-          if (p.seg_taps[s] == 9) {
-            if (!(p.debug_nodata & 2)) ptx::mbar_wait(a_go0 + 8u * sa, a_par);
-            ptx::tcgen05_fence_after();
-            if (i == 0) CSD_TSP(1);
-            if (i == 1) CSD_TSP(13);
-            const uint32_t x_lo0 = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
-            bool b_ready = ptx::mbar_test_wait(b_full0 + 8u * sb, b_par);
+          const bool nine = p.seg_taps[s] == 9;
+          if (!(nodata & 2)) ptx::mbar_wait(ag_bar, a_par);
+          ptx::tcgen05_fence_after();
+          if (lane == 0 && i == 0) CSD_TSP(1);
+          if (lane == 0 && i == 1) CSD_TSP(13);
+          if (nine) {
+            // (three taps per election - six MMAs and three commits back to back - was measured too: faster with the
+            //  operand loads switched off, 1 % slower with them on)
+            bool b_ready = ptx::mbar_test_wait(bf_bar, b_par);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              if (!b_ready && !(p.debug_nodata & 1)) ptx::mbar_wait(b_full0 + 8u * sb, b_par);
+              if (!b_ready && !(nodata & 1)) ptx::mbar_wait(bf_bar, b_par);
               ptx::tcgen05_fence_after();
-              // test the next slab's barrier before issuing this slab's MMAs (latency overlaps with tensor work)
-              uint32_t nsb = sb + 1, nb_par = b_par;
-              if (nsb == (uint32_t)p.b_stages) { nsb = 0; nb_par ^= 1u; }
-              b_ready = ptx::mbar_test_wait(b_full0 + 8u * nsb, nb_par);
-              const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
-              const uint32_t x_lo = x_lo0 + (uint32_t)((((tap / 3) * pitch9 + (tap % 3)) * kRowBytes) >> 4);
-              mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi9, x_lo), idesc, accumulate);
-              mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi9, x_lo + 2), idesc, 1u);
-              accumulate = 1u;
-              ptx::mma_commit(b_empty0 + 8u * sb);
-              sb = nsb;
-              b_par = nb_par;
+              // next ring slot (additions and selects only), and its barrier tested before this slab's MMAs are issued
+              const bool wrap = sb + 1 == n_b;
+              const uint32_t nb_par = wrap ? b_par ^ 1u : b_par;
+              const uint32_t nw_lo = wrap ? w_lo_first : w_lo + w_step;
+              const uint32_t nbf = wrap ? b_full0 : bf_bar + 8u, nbe = wrap ? b_empty0 : be_bar + 8u;
+              b_ready = ptx::mbar_test_wait(nbf, nb_par);
+              const uint32_t x_lo = x_lo_s + (uint32_t)((((tap / 3) * pitch9 + (tap % 3)) * kRowBytes) >> 4);
+              if (ptx::elect_one()) {
+                mma(d_tmem, w_desc_hi | w_lo, x9_desc_hi | x_lo, idesc, tap == 0 ? accumulate : 1u);
+                mma(d_tmem, w_desc_hi | (w_lo + 2), x9_desc_hi | (x_lo + 2), idesc, 1u);
+                ptx::mma_commit(be_bar);
+                if (tap == 8) ptx::mma_commit(ae_bar);
+              }
+              __syncwarp();
+              sb = wrap ? 0u : sb + 1; b_par = nb_par; w_lo = nw_lo; bf_bar = nbf; be_bar = nbe;
             }
-            ptx::mma_commit(a_empty0 + 8u * sa);
-            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
-          } else {
-            if (!(p.debug_nodata & 2)) ptx::mbar_wait(a_go0 + 8u * sa, a_par);
-            if (!(p.debug_nodata & 1)) ptx::mbar_wait(b_full0 + 8u * sb, b_par);
-            ptx::tcgen05_fence_after();
-            const uint32_t x_lo = ptx::smem_desc_lo(a_base + sa * p.a_stage_bytes, 16);
-            const uint32_t w_lo = ptx::smem_desc_lo(b_base + sb * p.b_stage_bytes, 16);
-            mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo), ptx::smem_desc_join(x_hi1, x_lo), idesc, accumulate);
-            mma(d_tmem, ptx::smem_desc_join(w_hi, w_lo + 2), ptx::smem_desc_join(x_hi1, x_lo + 2), idesc, 1u);
             accumulate = 1u;
-            ptx::mma_commit(b_empty0 + 8u * sb);
-            if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
-            ptx::mma_commit(a_empty0 + 8u * sa);
-            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+          } else {
+            if (!(nodata & 1)) ptx::mbar_wait(bf_bar, b_par);
+            ptx::tcgen05_fence_after();
+            if (ptx::elect_one()) {
+              mma(d_tmem, w_desc_hi | w_lo, x1_desc_hi | x_lo_s, idesc, accumulate);
+              mma(d_tmem, w_desc_hi | (w_lo + 2), x1_desc_hi | (x_lo_s + 2), idesc, 1u);
+              ptx::mma_commit(be_bar);
+              ptx::mma_commit(ae_bar);
+            }
+            __syncwarp();
+            accumulate = 1u;
+            const bool wrap = sb + 1 == n_b;
+            sb = wrap ? 0u : sb + 1;
+            b_par = wrap ? b_par ^ 1u : b_par;
+            w_lo = wrap ? w_lo_first : w_lo + w_step;
+            bf_bar = wrap ? b_full0 : bf_bar + 8u;
+            be_bar = wrap ? b_empty0 : be_bar + 8u;
           }
+          const bool awrap = sa + 1 == n_a;
+          sa = awrap ? 0u : sa + 1;
+          a_par = awrap ? a_par ^ 1u : a_par;
+          x_lo_s = awrap ? x_lo_first : x_lo_s + x_step;
+          ag_bar = awrap ? a_go0 : ag_bar + 8u;
+          ae_bar = awrap ? a_empty0 : ae_bar + 8u;
         }
-        CSD_TSP(2);
-        ptx::mma_commit(tmem_full0 + 8u * acc);
+        if (lane == 0) CSD_TSP(2);
+        if (ptx::elect_one()) ptx::mma_commit(tmem_full0 + 8u * acc);
+        __syncwarp();
         if (++acc == 2u) { acc = 0; acc_par ^= 1u; }
       }
     }
@@ -1149,7 +1185,7 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       const uint32_t t_row = tmem_base + acc * kTPix + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * half_pix);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-      for (int col = 0; col < half_pix; col += 32) {
+      for (int col = 0; col < ((p.debug_nodata & 32) ? 0 : half_pix); col += 32) {   // (probe bit 32: idle epilogue)
         uint32_t r0[16], r1[16];
         __syncwarp();
         ptx::tmem_ld_x16(t_row + col, r0);
@@ -1430,6 +1466,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
     // (a slab box that stops at the last stored channel - 96 instead of 128 rows, a quarter less weight fill - was
     //  measured neutral: 28.79 vs 28.68 ms per step; the full box stays)
     p.b_box_rows = kTChan;
+    if (const char* e = getenv("CSD_DEBUG_SLAB_ROWS")) p.b_box_rows = std::max(8, std::min(kTChan, atoi(e)));   // probe: wrong results
     uint32_t box[3] = {(uint32_t)(halo_mode ? halo_chunk : tap_chunk), (uint32_t)(t_mode ? p.b_box_rows : p.n_sub), 1};
     int st = encode_tensor_map(&L->mapB, tm_dtype, 3, d->wt, dims, strides, box,
                                (!halo_mode && tap_row_bytes == 128) ? TMA_SW_128 : TMA_SW_64);
@@ -1561,7 +1598,11 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
       // with the fused prologue a halo goes TMA -> transform -> MMA: a fourth buffer lets the next tile's first
       // chunk be fetched and normalised while the current tile still has two chunks to multiply
       p.a_stages = p.has_norm ? 4 : 3;
-      const size_t fixed = 1024 + (size_t)p.a_stages * p.a_stage_bytes + kPStagingBytes + kPBarBytes +
+      // (Halo buffers and staging tile sized per launch - 15 instead of 9 weight slabs in flight at 40 px - measured
+      //  neutral, like quartering the slab bytes and doubling the producer warps: the ~15-20 % the weight stream costs at
+      //  N = 160 / 224 is neither bytes, nor ring depth, nor TMA issue rate; profiles/conv_nodata_r2.txt.)
+      p.staging_bytes = kPStagingBytes;
+      const size_t fixed = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.staging_bytes + kPBarBytes +
                            (size_t)k_total_chan * 8 + 16;
       CSD_REQUIRE(fixed + 4 * (size_t)p.b_stage_bytes <= 227 * 1024, "transposed conv: K=%d channels too many for the "
                   "shared-memory coefficient table", k_total_chan);

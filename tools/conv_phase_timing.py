@@ -12,7 +12,11 @@ dev = "cuda"
 DT = torch.float32 if os.environ.get("CSD_PRECISION") == "tf32" else torch.bfloat16   # tf32: the fp32 / kind::tf32 instance
 if DT == torch.float32:
     names[6] = "epi pass A staged"
-for (B, H, cin, cout, full) in ((64, 160, 96, 96, False), (64, 160, 96, 96, True), (64, 160, 192, 96, True), (64, 80, 192, 192, True)):
+SHAPES = ((64, 160, 96, 96, False), (64, 160, 96, 96, True), (64, 160, 192, 96, True), (64, 80, 192, 192, True),
+          (64, 80, 96, 96, False), (64, 40, 192, 192, False), (64, 40, 192, 192, True))
+if os.environ.get("CSD_DEBUG_NODATA", "0") != "0":
+    SHAPES = tuple(sh for sh in SHAPES if not sh[4])     # the fused prologue cannot run without its loads
+for (B, H, cin, cout, full) in SHAPES:
     a = torch.randn(B, H, H, cin, device=dev).to(DT)
     wt = k.pack_conv_weight((torch.randn(cout, cin, 3, 3, device=dev) / 30).to(DT), dtype=DT)
     out = torch.empty(B, H, H, cout, device=dev, dtype=DT)
@@ -21,7 +25,7 @@ for (B, H, cin, cout, full) in ((64, 160, 96, 96, False), (64, 160, 96, 96, True
     if full:   # what the engine launches: fused GroupNorm prologue, temb, residual, statistics
         coef = torch.rand(B, cin, 2, device=dev)
         seg = (a, cin, 0, cin, 9, coef, True)
-        tiles = B * math.ceil(H / 32) * math.ceil(H / 8)
+        tiles = B * math.ceil(H / k.transposed_tile_rows(H)) * math.ceil(H / 8) * 2
         kw = dict(temb=torch.randn(B, cout + 32, device=dev), temb_pitch=cout + 32,
                   bias=torch.randn(cout + 32, device=dev), stat_partials=torch.empty(tiles, cout, 2, device=dev))
     for rep in range(3):
