@@ -382,8 +382,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the loop converged, one elected lane issues (see conv_halo_tp_kernel) =====
+    {
       // everything the loop needs lives in registers: the issuing thread's scalar work per stage is what bounds
       // the small-level launches
       const uint32_t idesc = kTf32 ? ptx::make_idesc_tf32_m128((uint32_t)p.n_sub) : ptx::make_idesc_bf16_m128((uint32_t)p.n_sub);
@@ -398,7 +398,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       uint32_t fbar = full_bar(0);
       bool ready = ptx::mbar_test_wait(fbar, 0);
 #ifdef CSD_ENABLE_PHASE_TIMESTAMPS
-      const bool ts_on = p.debug_ts != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
+      const bool ts_on = lane == 0 && p.debug_ts != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
 #define CSD_TSM(slot) do { if (ts_on && it < 12) p.debug_ts[16 + 4 * it + (slot)] = clock64(); } while (0)
 #else
 #define CSD_TSM(slot) do { } while (0)
@@ -415,6 +415,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         if (nstage == num_stages) { nstage = 0; npar ^= 1u; n_lo = a_lo0; fbar = full_bar(0); }
         ready = (it + 1 < total_iters) && ptx::mbar_test_wait(fbar, npar);
         const uint32_t b_lo = a_lo + (kARows >> 4);
+        if (ptx::elect_one()) {
 #pragma unroll
         for (int k16 = 0; k16 < (int)kRowB / 32; ++k16) {      // one MMA per 32 bytes of K: 16 bf16 or 8 tf32 values
           const uint32_t acc = (k16 == 0) ? accumulate : 1u;
@@ -432,15 +433,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                                ptx::smem_desc_join(hi, b_lo + b2_off + 2 * k16), idesc, acc);
           }
         }
-        accumulate = 1u;
         CSD_TSM(2);
         ptx::mma_commit(ebar);  // frees the stage when the MMAs above have read it
         CSD_TSM(3);
+        }
+        __syncwarp();
+        accumulate = 1u;
         stage = nstage;
         par = npar;
         a_lo = n_lo;
       }
-      ptx::mma_commit(tmem_full_bar);       // accumulator complete
+      if (ptx::elect_one()) ptx::mma_commit(tmem_full_bar);       // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue (warps 2..5): warp q owns TMEM lanes [32q, 32q+32) with q = warp % 4 =====
