@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcsd_b200.so")
+# CSD_LIB_PATH: another build of the same library (A/B measurements of two kernels versions in one GPU call)
+LIB_PATH = os.environ.get("CSD_LIB_PATH") or os.path.join(_HERE, "libcsd_b200.so")
 
 CSD_MAX_SEGMENTS = 4
 

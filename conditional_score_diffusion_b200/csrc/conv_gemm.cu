@@ -731,7 +731,9 @@ __global__ void __launch_bounds__(kPThreads, 1)
 conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
-                    const __grid_constant__ CUtensorMap mapOut2, const ConvGemmKernelParams p) {
+                    const __grid_constant__ CUtensorMap mapOut2, const __grid_constant__ CUtensorMap mapW0,
+                    const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
+                    const __grid_constant__ CUtensorMap mapW3, const ConvGemmKernelParams p) {
   // kTf32: the reference-precision plan. Activations, weights and the output are fp32 words, the MMA is kind::tf32.
   // Every shared-memory structure keeps its BYTE geometry (64-byte rows, SWIZZLE_64B, 2 MMAs of 32 bytes of K per
   // (chunk, tap)): a chunk is 16 fp32 channels instead of 32 bf16 channels, so only the chunk counts double.
@@ -800,28 +802,33 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       }
     }
   } else if (warp >= 18) {
-    // ===== TMA producers B: one 128-channel x 32-K weight slab per (chunk, tap); slab i is issued by producer
-    //       i mod kPBProducers, every producer tracks the whole ring so slots and parities stay consistent =====
-    if (lane == 0) {
-      const int me = warp - 18;
-      int turn = 0;
+    // ===== TMA producer B: weights. A ring slot holds THREE slabs = the three taps of one kernel row for one channel
+    //       chunk, filled by ONE TMA op through the segment's 3-D map (k, row, tap) - the tap dimension has the smaller
+    //       stride, tools/tma_taps_probe.cu - so barrier round trips, TMA ops and commits are paid once per six MMAs.
+    //       (What the weight stream costs is per transaction, not per byte: profiles/conv_nodata_r2.txt.) A 1-tap chunk
+    //       takes one slot with a single slab through the 2-D map. One producer thread is enough now (an op every
+    //       ~360 cycles against one needed every 6 MMAs); warps 19-20 idle. =====
+    if (lane == 0 && warp == 18) {
       uint32_t sb = 0, b_par = 1;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         for (int i = 0; i < p.n_sched; ++i) {
           int s, c;
           sched_at(p, i, s, c);
-          const int taps = p.seg_taps[s];
-          const int kstep = ((p.seg_ccnt[s] + kChunkK - 1) / kChunkK) * kChunkK;   // K columns of one tap in Wt (ceil32)
-          int kcol = p.wt_k_off + p.seg_kbase[s] * kChunkK + c * CH;
-          for (int tap = 0; tap < taps; ++tap, kcol += kstep) {
-            if (p.debug_nodata & 1) continue;   // perf experiment: no weight traffic
-            if (turn == me) {
+          if (p.debug_nodata & 1) continue;   // perf experiment: no weight traffic
+          if (p.seg_taps[s] == 9) {
+            const CUtensorMap* mapW = (s == 0) ? &mapW0 : (s == 1) ? &mapW1 : (s == 2) ? &mapW2 : &mapW3;
+            for (int g3 = 0; g3 < 3; ++g3) {
               ptx::mbar_wait(b_empty0 + 8u * sb, b_par);
-              ptx::mbar_arrive_expect_tx(b_full0 + 8u * sb, (uint32_t)p.b_box_rows * kRowBytes);
-              ptx::tma_load_3d(b_base + sb * p.b_stage_bytes, &mapB, b_full0 + 8u * sb, kcol, tc.n0, 0);
+              ptx::mbar_arrive_expect_tx(b_full0 + 8u * sb, 3u * kTChan * kRowBytes);
+              ptx::tma_load_3d(b_base + sb * p.b_stage_bytes, mapW, b_full0 + 8u * sb, c * CH, tc.n0, 3 * g3);
+              if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
             }
-            if (++turn == kPBProducers) turn = 0;
+          } else {
+            const int kcol = p.wt_k_off + p.seg_kbase[s] * kChunkK + c * CH;
+            ptx::mbar_wait(b_empty0 + 8u * sb, b_par);
+            ptx::mbar_arrive_expect_tx(b_full0 + 8u * sb, (uint32_t)kTChan * kRowBytes);
+            ptx::tma_load_3d(b_base + sb * p.b_stage_bytes, &mapB, b_full0 + 8u * sb, kcol, tc.n0, 0);
             if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
           }
         }
@@ -878,28 +885,30 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           if (lane == 0 && i == 0) CSD_TSP(1);
           if (lane == 0 && i == 1) CSD_TSP(13);
           if (nine) {
-            // (three taps per election - six MMAs and three commits back to back - was measured too: faster with the
-            //  operand loads switched off, 1 % slower with them on)
-            bool b_ready = ptx::mbar_test_wait(bf_bar, b_par);
+            // one ring slot = the three slabs of a kernel row: one wait, six MMAs, one commit
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              if (!b_ready && !(nodata & 1)) ptx::mbar_wait(bf_bar, b_par);
+            for (int g3 = 0; g3 < 3; ++g3) {
+              if (!(nodata & 1)) ptx::mbar_wait(bf_bar, b_par);
               ptx::tcgen05_fence_after();
-              // next ring slot (additions and selects only), and its barrier tested before this slab's MMAs are issued
-              const bool wrap = sb + 1 == n_b;
-              const uint32_t nb_par = wrap ? b_par ^ 1u : b_par;
-              const uint32_t nw_lo = wrap ? w_lo_first : w_lo + w_step;
-              const uint32_t nbf = wrap ? b_full0 : bf_bar + 8u, nbe = wrap ? b_empty0 : be_bar + 8u;
-              b_ready = ptx::mbar_test_wait(nbf, nb_par);
-              const uint32_t x_lo = x_lo_s + (uint32_t)((((tap / 3) * pitch9 + (tap % 3)) * kRowBytes) >> 4);
+              const uint32_t x_row = x_lo_s + (uint32_t)((g3 * pitch9 * kRowBytes) >> 4);
               if (ptx::elect_one()) {
-                mma(d_tmem, w_desc_hi | w_lo, x9_desc_hi | x_lo, idesc, tap == 0 ? accumulate : 1u);
-                mma(d_tmem, w_desc_hi | (w_lo + 2), x9_desc_hi | (x_lo + 2), idesc, 1u);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                  const uint32_t wl = w_lo + (uint32_t)((j * kTChan * kRowBytes) >> 4);
+                  const uint32_t x_lo = x_row + (uint32_t)((j * kRowBytes) >> 4);
+                  mma(d_tmem, w_desc_hi | wl, x9_desc_hi | x_lo, idesc, (g3 == 0 && j == 0) ? accumulate : 1u);
+                  mma(d_tmem, w_desc_hi | (wl + 2), x9_desc_hi | (x_lo + 2), idesc, 1u);
+                }
                 ptx::mma_commit(be_bar);
-                if (tap == 8) ptx::mma_commit(ae_bar);
+                if (g3 == 2) ptx::mma_commit(ae_bar);
               }
               __syncwarp();
-              sb = wrap ? 0u : sb + 1; b_par = nb_par; w_lo = nw_lo; bf_bar = nbf; be_bar = nbe;
+              const bool wrap = sb + 1 == n_b;
+              sb = wrap ? 0u : sb + 1;
+              b_par = wrap ? b_par ^ 1u : b_par;
+              w_lo = wrap ? w_lo_first : w_lo + w_step;
+              bf_bar = wrap ? b_full0 : bf_bar + 8u;
+              be_bar = wrap ? b_empty0 : be_bar + 8u;
             }
             accumulate = 1u;
           } else {
@@ -1330,6 +1339,7 @@ struct ConvGemmLaunch {
   CUtensorMap mapB;
   CUtensorMap mapOut;
   CUtensorMap mapOut2;   // fp32 plan: store box of the remainder rows of a half tile (pass B)
+  CUtensorMap mapW[CSD_MAX_SEGMENTS];   // transposed kernel: (k, row, tap) weight maps of the 9-tap segments
   ConvGemmKernelParams p;
   dim3 grid;
   size_t smem;
@@ -1606,14 +1616,28 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
       //  neutral, like quartering the slab bytes and doubling the producer warps: the ~15-20 % the weight stream costs at
       //  N = 160 / 224 is neither bytes, nor ring depth, nor TMA issue rate; profiles/conv_nodata_r2.txt.)
       p.staging_bytes = kPStagingBytes;
+      // weight ring: slots of three slabs (the three taps of a kernel row, one TMA op through mapW[s])
+      p.b_stage_bytes = 3u * kTChan * kRowBytes;
       const size_t fixed = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.staging_bytes + kPBarBytes +
                            (size_t)k_total_chan * 8 + 16;
-      CSD_REQUIRE(fixed + 4 * (size_t)p.b_stage_bytes <= 227 * 1024, "transposed conv: K=%d channels too many for the "
+      CSD_REQUIRE(fixed + 2 * (size_t)p.b_stage_bytes <= 227 * 1024, "transposed conv: K=%d channels too many for the "
                   "shared-memory coefficient table", k_total_chan);
       int pbs = (int)((227 * 1024 - fixed) / p.b_stage_bytes);
       if (pbs > kPMaxBStages) pbs = kPMaxBStages;
-      pbs -= pbs % kPBProducers;   // a ring slot always belongs to the same weight producer (mbarrier parity scheme)
       p.b_stages = pbs;
+      for (int s = 0; s < CSD_MAX_SEGMENTS; ++s) L->mapW[s] = L->mapB;
+      for (int s = 0; s < d->nseg; ++s) {
+        if (p.seg_taps[s] != 9) continue;
+        // (k, row, tap) view of this segment's K range: Wt[row][wt_k_off + seg_kbase * 32 + tap * kstep + k]
+        const int kstep = ceil_div(p.seg_ccnt[s], kChunkK) * kChunkK;
+        const uint64_t row_bytes = (uint64_t)(d->wt_pitch > 0 ? d->wt_pitch : d->k_total) * E;
+        const char* base = static_cast<const char*>(d->wt) + ((size_t)d->wt_k_off + (size_t)p.seg_kbase[s] * kChunkK) * E;
+        uint64_t wdims[3] = {(uint64_t)kstep, (uint64_t)d->wt_rows, 9};
+        uint64_t wstr[2] = {row_bytes, (uint64_t)kstep * E};
+        uint32_t wbox[3] = {(uint32_t)halo_chunk, (uint32_t)kTChan, 3};
+        int st = encode_tensor_map(&L->mapW[s], tm_dtype, 3, base, wdims, wstr, wbox, TMA_SW_64);
+        if (st != CSD_OK) return st;
+      }
       L->smem = fixed + (size_t)pbs * p.b_stage_bytes;
       const int sms = num_sms();
       L->grid = dim3((unsigned)std::min(p.num_tiles, sms), 1, 1);
@@ -1660,10 +1684,12 @@ int conv_gemm_launch(const ConvGemmLaunch* L, cudaStream_t stream) {
   }
   if (L->persistent && L->tf32) {
     conv_halo_tp_kernel<true><<<L->grid, kPThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
-                                                                         L->mapB, L->mapOut, L->mapOut2, L->p);
+                                                                         L->mapB, L->mapOut, L->mapOut2, L->mapW[0], L->mapW[1], L->mapW[2],
+                                                                         L->mapW[3], L->p);
   } else if (L->persistent) {
     conv_halo_tp_kernel<false><<<L->grid, kPThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
-                                                                          L->mapB, L->mapOut, L->mapOut, L->p);
+                                                                          L->mapB, L->mapOut, L->mapOut, L->mapW[0], L->mapW[1], L->mapW[2],
+                                                                          L->mapW[3], L->p);
   } else if (L->halo) {
     conv_halo_kernel<<<L->grid, kConvThreads, L->smem, stream>>>(L->mapA[0], L->mapA[1], L->mapA[2], L->mapA[3],
                                                                  L->mapB, L->p);
