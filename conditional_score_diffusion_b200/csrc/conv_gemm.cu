@@ -1616,6 +1616,14 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
       //  neutral, like quartering the slab bytes and doubling the producer warps: the ~15-20 % the weight stream costs at
       //  N = 160 / 224 is neither bytes, nor ring depth, nor TMA issue rate; profiles/conv_nodata_r2.txt.)
       p.staging_bytes = kPStagingBytes;
+      if (getenv("CSD_FIXED_TP_SMEM") == nullptr) {
+        // halo buffers and staging tile sized for this launch's macro tile: at 40 px (20-row tiles) that is room for
+        // five 3-slab ring slots instead of three
+        p.out_box_c = std::min(kTChan, d->n_store);
+        p.a_stage_bytes = (uint32_t)(((kHaloTW + 2) * (p.t_rows + 2) * kRowBytes + 511) & ~511);   // SW64 pattern period
+        const int stg = tf32 ? 512 * p.out_box_c : 2 * p.t_pix * p.out_box_c;
+        p.staging_bytes = (stg + 1023) & ~1023;
+      }
       // weight ring: slots of three slabs (the three taps of a kernel row, one TMA op through mapW[s])
       p.b_stage_bytes = 3u * kTChan * kRowBytes;
       const size_t fixed = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.staging_bytes + kPBarBytes +
