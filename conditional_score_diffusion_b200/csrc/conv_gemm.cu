@@ -1612,6 +1612,7 @@ int conv_gemm_prepare(const csd_conv_gemm_desc* d, ConvGemmLaunch* L) {
       // with the fused prologue a halo goes TMA -> transform -> MMA: a fourth buffer lets the next tile's first
       // chunk be fetched and normalised while the current tile still has two chunks to multiply
       p.a_stages = p.has_norm ? 4 : 3;
+      if (const char* e = getenv("CSD_TP_A_STAGES")) p.a_stages = std::max(2, std::min(kMaxAStages, atoi(e)));   // probe
       // (Halo buffers and staging tile sized per launch - 15 instead of 9 weight slabs in flight at 40 px - measured
       //  neutral, like quartering the slab bytes and doubling the producer warps: the ~15-20 % the weight stream costs at
       //  N = 160 / 224 is neither bytes, nor ring depth, nor TMA issue rate; profiles/conv_nodata_r2.txt.)
