@@ -555,7 +555,13 @@ static int launch_fir_tma(const FirNhwcParamsT<VT>& p, cudaStream_t stream) {
   using T = FirTile<MODE>;
   constexpr int eb = (int)sizeof(VT) / 8;        // bytes per element
   const int pitch = p.cvec * 8;
-  const int cb = std::min(eb == 2 ? 64 : 32, pitch);
+  // Channels per CTA. 128-byte chunks (64 bf16 / 32 fp32 channels) by default; where that cuts a pixel's channel row
+  // into pieces that straddle 128-byte lines (96 bf16 channels = 192 bytes per pixel: every other 128-byte piece starts
+  // at offset 64, and the 64 bytes left over are written later by another CTA) the up x2 kernel - output bound, four
+  // stores per input sample - takes whole 96-channel rows instead, so a tile row leaves as one contiguous run.
+  int cb = std::min(eb == 2 ? 64 : 32, pitch);
+  static const bool whole_rows = [] { const char* e = getenv("CSD_FIR_CHUNK64"); return !(e && atoi(e) != 0); }();   // A/B
+  if (MODE == 1 && whole_rows && eb == 2 && pitch % 96 == 0 && (pitch * eb) % 128 != 0) cb = 96;
   const int cchunks = ceil_div(pitch, cb);
   const int tiles_x = ceil_div(p.ow, T::TO), tiles_y = ceil_div(p.oh, T::TO);
   CUtensorMap map;
@@ -617,6 +623,89 @@ tap_shift_sum_kernel(const __nv_bfloat16* __restrict__ part, int p_pitch, int co
     *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(&o);
     for (int c = 8; c < out_pitch; c += 8) *reinterpret_cast<uint4*>(op + c) = make_uint4(0, 0, 0, 0);
   }
+}
+
+
+// The same sum from a shared-memory tile. The kernel above issues 9 * cout two-byte global loads per pixel at a 112-byte
+// pixel pitch (profiles/step_launches_r2_final.md: 107 us for [64, 160, 160, 56], 0.33 of the HBM rate, LSU bound).
+// Here a CTA owns 8 x 32 output pixels: the partial rows of the 10 x 34 halo tile arrive as coalesced 16-byte vectors,
+// land in shared memory at an ODD word pitch (consecutive pixels hit different banks), and every thread sums its 9 taps
+// from there - same order of additions as above (bias, taps 0..8, residual), so both kernels agree bit for bit.
+// COUT is a template parameter: the vector count per pixel, the tap offsets and the index arithmetic of the staging loop
+// are compile-time constants (with run-time divisors the staging loop alone was ~100 instructions per vector).
+constexpr int kSsTH = 8, kSsTW = 32;
+
+template <int COUT>
+__global__ void __launch_bounds__(kSsTH * kSsTW)
+tap_shift_sum_tile_kernel(const __nv_bfloat16* __restrict__ part, const float* __restrict__ bias,
+                          const __nv_bfloat16* __restrict__ res, int res_pitch, __nv_bfloat16* __restrict__ out,
+                          int out_pitch, int H, int W, int tiles_x, int tiles_y) {
+  constexpr int PITCH = (9 * COUT + 7) / 8 * 8;        // channels per pixel row of `part`
+  constexpr int VECS = PITCH / 8;                      // 16-byte vectors per pixel row
+  constexpr int PW = (PITCH / 2) | 1;                  // shared-memory pixel pitch in words (odd)
+  constexpr int HW_ = kSsTW + 2, HH_ = kSsTH + 2;
+  __shared__ uint32_t ss_tile[HH_ * HW_ * PW];
+  int t = blockIdx.x;
+  const int tx = t % tiles_x;
+  t /= tiles_x;
+  const int ty = t % tiles_y, b = t / tiles_y;
+  const int x0 = tx * kSsTW, y0 = ty * kSsTH;
+  const __nv_bfloat16* img = part + (long long)b * H * W * PITCH;
+#pragma unroll 2
+  for (int i = threadIdx.x; i < HH_ * HW_ * VECS; i += kSsTH * kSsTW) {
+    const int v = i % VECS, pp = i / VECS, px = pp % HW_, py = pp / HW_;
+    const int gy = y0 - 1 + py, gx = x0 - 1 + px;
+    uint4 q = make_uint4(0, 0, 0, 0);                  // taps outside the image contribute zero
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      q = __ldg(reinterpret_cast<const uint4*>(img + ((long long)gy * W + gx) * PITCH) + v);
+    uint32_t* d = ss_tile + pp * PW + v * 4;
+    d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x % kSsTW, ly = threadIdx.x / kSsTW;
+  const int x = x0 + lx, y = y0 + ly;
+  if (x >= W || y >= H) return;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = (i < COUT && bias != nullptr) ? __ldg(bias + i) : 0.f;
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) {
+    const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;      // (zeros anyway; keeps the additions of the kernel above)
+    const uint32_t* row = ss_tile + ((ly + tp / 3) * HW_ + lx + tp % 3) * PW;
+    if (COUT % 2 == 0) {                               // tap tp starts on a word boundary
+      const uint32_t* src = row + (tp * COUT) / 2;
+#pragma unroll
+      for (int i = 0; i < COUT / 2; ++i) {
+        const uint32_t wv = src[i];
+        acc[2 * i] += __uint_as_float(wv << 16);
+        acc[2 * i + 1] += __uint_as_float(wv & 0xffff0000u);
+      }
+    } else {
+      const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(row) + tp * COUT;
+#pragma unroll
+      for (int i = 0; i < COUT; ++i) acc[i] += __bfloat162float(src[i]);
+    }
+  }
+  const long long idx = ((long long)b * H + y) * W + x;
+  if (res != nullptr) {
+    const __nv_bfloat16* rp = res + idx * res_pitch;
+#pragma unroll
+    for (int i = 0; i < COUT; ++i) acc[i] += __bfloat162float(rp[i]);
+  }
+  __nv_bfloat16* op = out + idx * out_pitch;
+  const bf16x8 o = pack8(acc);                         // (channels >= COUT are the zeros acc started with)
+  *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(&o);
+  for (int c = 8; c < out_pitch; c += 8) *reinterpret_cast<uint4*>(op + c) = make_uint4(0, 0, 0, 0);
+}
+
+template <int COUT>
+static void launch_shift_sum_tile(const void* partial, const float* bias, const void* res, int res_pitch, void* out,
+                                  int out_pitch, int batch, int h, int w, cudaStream_t stream) {
+  const int tiles_x = ceil_div(w, kSsTW), tiles_y = ceil_div(h, kSsTH);
+  tap_shift_sum_tile_kernel<COUT><<<(unsigned)(batch * tiles_x * tiles_y), kSsTH * kSsTW, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(partial), bias, static_cast<const __nv_bfloat16*>(res), res_pitch,
+      static_cast<__nv_bfloat16*>(out), out_pitch, h, w, tiles_x, tiles_y);
 }
 
 }  // namespace csd
@@ -743,6 +832,24 @@ int csd_tap_shift_sum_bf16(const void* partial, int p_pitch, int cout, const flo
   CSD_REQUIRE(cout >= 1 && cout <= 8 && p_pitch >= 9 * cout, "tap_shift_sum: cout=%d (1..8), partial pitch %d", cout, p_pitch);
   CSD_REQUIRE(out_pitch % 8 == 0 && out_pitch >= 8 && (res == nullptr || res_pitch >= cout),
               "tap_shift_sum: output pitch %d must be a multiple of 8", out_pitch);
+  static const bool legacy = [] { const char* e = getenv("CSD_SHIFT_SUM_LEGACY"); return e && atoi(e) != 0; }();   // A/B
+  const long long tiles = (long long)batch * ceil_div(h, kSsTH) * ceil_div(w, kSsTW);
+  // (cout = 8 would need 50 KB for the tile: it stays on the kernel above)
+  if (!legacy && cout <= 7 && p_pitch == (9 * cout + 7) / 8 * 8 && tiles < (1LL << 31) && reinterpret_cast<uintptr_t>(partial) % 16 == 0) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (cout) {
+      case 1: launch_shift_sum_tile<1>(partial, bias, res, res_pitch, out, out_pitch, batch, h, w, st); break;
+      case 2: launch_shift_sum_tile<2>(partial, bias, res, res_pitch, out, out_pitch, batch, h, w, st); break;
+      case 3: launch_shift_sum_tile<3>(partial, bias, res, res_pitch, out, out_pitch, batch, h, w, st); break;
+      case 4: launch_shift_sum_tile<4>(partial, bias, res, res_pitch, out, out_pitch, batch, h, w, st); break;
+      case 5: launch_shift_sum_tile<5>(partial, bias, res, res_pitch, out, out_pitch, batch, h, w, st); break;
+      case 6: launch_shift_sum_tile<6>(partial, bias, res, res_pitch, out, out_pitch, batch, h, w, st); break;
+      case 7: launch_shift_sum_tile<7>(partial, bias, res, res_pitch, out, out_pitch, batch, h, w, st); break;
+      default: break;
+    }
+    CSD_LAUNCH_CHECK("tap_shift_sum_tile_kernel");
+    return CSD_OK;
+  }
   const long long total = (long long)batch * h * w;
   const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)num_sms() * 16);
   tap_shift_sum_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -292,8 +292,11 @@ class Recorder:
     def add(self, fn, *args, **kwargs):
         self.ops.append((fn, args, kwargs))
 
-    def run(self):
+    def run(self, skip=()):
+        """skip: launch functions to leave out (their outputs from an earlier run of the same list are still valid)."""
         for fn, args, kwargs in self.ops:
+            if fn in skip:
+                continue
             fn(*args, **kwargs)
 
     def __len__(self):
@@ -1407,9 +1410,15 @@ class NetPlan:
     def run(self):
         self.rec.run()
 
-    def launch(self):
+    def launch(self, reuse_time_embedding=False):
         """Run the launch list: eagerly the first time (and inside someone else's capture), as a
-        replayed CUDA graph afterwards."""
+        replayed CUDA graph afterwards. reuse_time_embedding: the labels are the ones of the previous launch (the
+        corrector and the predictor of one PC step share vec_t, sampling/unconditional.py:216-220), so the temb MLP and
+        the blocks' Dense_0 projections it wrote are still current and their two launches are left out (only where the
+        list is run launch by launch - inside a caller's capture; the plan's own graph always holds the whole list)."""
+        if reuse_time_embedding and (not self.use_graph or torch.cuda.is_current_stream_capturing()):
+            self.rec.run(skip=(K.time_embedding, K.dense_rows))
+            return
         if not self.use_graph or torch.cuda.is_current_stream_capturing():
             self.rec.run()
             return

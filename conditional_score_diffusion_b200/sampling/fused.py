@@ -26,10 +26,15 @@ Noise: torch's CUDA generator (`normal_` on static buffers, captured in the grap
 order as the reference (y, x, y, x per conditional step); `noise_source` replaces it with injected
 tensors for parity tests and reproducible replays.
 """
+import os
+
 import torch
 
 from .. import kernels as K
 from . import tables
+
+
+REUSE_TEMB = os.environ.get("CSD_NO_TEMB_REUSE", "0") != "1"   # A/B switch
 
 
 class FusedPCSampler:
@@ -112,7 +117,14 @@ class FusedPCSampler:
             if self.draw_noise:
                 self.noise_y[which].normal_()
             K.ve_perturb(self.y, self.noise_y[which], self.plan.in1, self.t_sigma_y, self.step_idx, 0)
-        self.plan.launch()
+        self._net()
+
+    def _net(self):
+        """One score-network evaluation. Every evaluation of a PC step sees the same vec_t (corrector first, then the
+        predictor, sampling/unconditional.py:216-220, sampling/conditional.py:196-226), so only the first one runs
+        the time-embedding MLP and the Dense_0 projections; the others reuse what it wrote."""
+        self.plan.launch(reuse_time_embedding=REUSE_TEMB and not self._temb_stale)
+        self._temb_stale = False
 
     def _corrector(self, fresh_condition):
         p = self.plan
@@ -120,7 +132,7 @@ class FusedPCSampler:
             if k == 0 and fresh_condition:
                 self._score(0)
             else:
-                p.launch()   # same condition for every inner Langevin iteration (and, on a path, as the predictor)
+                self._net()  # same condition for every inner Langevin iteration (and, on a path, as the predictor)
             if self.draw_noise:
                 self.noise_x[0].normal_()
             K.langevin_norms(self.score, self.noise_x[0], self.norms)
@@ -131,7 +143,7 @@ class FusedPCSampler:
         if fresh_condition:
             self._score(1)
         else:
-            self.plan.launch()
+            self._net()
         if self.draw_noise:
             self.noise_x[1].normal_()
         if self.predictor == "reverse_diffusion":
@@ -150,6 +162,7 @@ class FusedPCSampler:
 
     def _step(self):
         p = self.plan
+        self._temb_stale = True
         K.broadcast_table(p.labels, self.t_labels, self.step_idx, 0)
         K.broadcast_table(p.row_scale, self.t_inv_x, self.step_idx, 0)
         if self.t_inv_y is not None:

@@ -247,6 +247,61 @@ def test_fir_nhwc_vs_oracle(h, c):
         _close(up.permute(0, 3, 1, 2), o_ops.upsample_2d(x.float(), (1, 2, 3, 4)), BF16, "fir up asym")
 
 
+def test_fir_nhwc_more_tiles_than_resident_ctas():
+    """FIR at a size with many more tiles than resident CTAs (B = 8, 80 px, 96 channels: the up x2 kernel takes whole
+    96-channel pixel rows per CTA there, csrc/resample.cu launch_fir_tma), repeated launches, `add`, down x2, and the fp32
+    instances on the same data."""
+    k_ = K()
+    g = torch.Generator().manual_seed(77)
+    B, h, c = 8, 80, 96
+    x = torch.randn(B, c, h, h, generator=g).to(torch.bfloat16)
+    xn = x.permute(0, 2, 3, 1).contiguous().cuda()
+    ref_up, ref_dn = o_ops.upsample_2d(x.float()), o_ops.downsample_2d(x.float())
+    add = torch.randn(B, 2 * h, 2 * h, c, generator=g).to(torch.bfloat16)
+    up = torch.empty(B, 2 * h, 2 * h, c, device="cuda", dtype=torch.bfloat16)
+    for rep in range(2):                                        # (a second launch must not depend on stale barriers)
+        k_.fir_resample(xn, up, "up", [1, 3, 3, 1])
+        _close(up.permute(0, 3, 1, 2), ref_up, BF16, f"fir up many tiles, launch {rep}")
+    k_.fir_resample(xn, up, "up", [1, 3, 3, 1], add=add.cuda())
+    _close(up.permute(0, 3, 1, 2), ref_up + add.float().permute(0, 3, 1, 2), BF16, "fir up + add, many tiles")
+    dn = torch.empty(B, h // 2, h // 2, c, device="cuda", dtype=torch.bfloat16)
+    k_.fir_resample(xn, dn, "down", [1, 3, 3, 1])
+    _close(dn.permute(0, 3, 1, 2), ref_dn, BF16, "fir down many tiles")
+    xf = xn.float()
+    upf = torch.empty(B, 2 * h, 2 * h, c, device="cuda", dtype=torch.float32)
+    k_.fir_resample(xf, upf, "up", [1, 3, 3, 1])
+    _close(upf.permute(0, 3, 1, 2), ref_up, 2e-5, "fir up many tiles fp32")
+    dnf = torch.empty(B, h // 2, h // 2, c, device="cuda", dtype=torch.float32)
+    k_.fir_resample(xf, dnf, "down", [1, 3, 3, 1])
+    _close(dnf.permute(0, 3, 1, 2), ref_dn, 2e-5, "fir down many tiles fp32")
+
+
+@pytest.mark.parametrize("cout,h,w,with_res", [(6, 40, 72, True), (6, 9, 5, False), (3, 33, 20, True), (8, 16, 64, True)])
+def test_tap_shift_sum_vs_torch(cout, h, w, with_res):
+    """csd_tap_shift_sum_bf16 (second half of the tap-stacked output heads, models/ncsnpp.py:337-352): out = bias + res +
+    the nine per-tap partial maps shifted to their output pixel, zero outside the image. Ragged tiles, odd channel
+    counts (two-byte tap offsets), with and without the pyramid residual."""
+    k_ = K()
+    g = torch.Generator().manual_seed(cout * 100 + h)
+    B = 3
+    pitch = -(-9 * cout // 8) * 8
+    part = torch.zeros(B, h, w, pitch)
+    part[..., :9 * cout] = torch.randn(B, h, w, 9 * cout, generator=g)
+    part = part.to(torch.bfloat16)
+    bias = torch.randn(cout, generator=g)
+    res = torch.randn(B, h, w, 8, generator=g).to(torch.bfloat16) if with_res else None
+    out = torch.full((B, h, w, 8), float("nan"), dtype=torch.bfloat16, device="cuda")
+    k_.tap_shift_sum(part.cuda(), cout, bias.cuda(), res.cuda() if with_res else None, out)
+    pf = F.pad(part.float(), (0, 0, 1, 1, 1, 1))               # [B, h + 2, w + 2, pitch]
+    ref = bias.view(1, 1, 1, cout).expand(B, h, w, cout).clone()
+    for t in range(9):
+        ref = ref + pf[:, t // 3:t // 3 + h, t % 3:t % 3 + w, t * cout:(t + 1) * cout]
+    if with_res:
+        ref = ref + res.float()[..., :cout]
+    _close(out[..., :cout], ref, BF16, f"tap_shift_sum cout={cout} {h}x{w} res={with_res}")
+    assert (out[..., cout:].float() == 0).all(), "tap_shift_sum: padding channels must be zero"
+
+
 @pytest.mark.parametrize("h,c,pitch", [(16, 96, 96), (40, 192, 192), (20, 40, 48), (6, 8, 8)])
 def test_fir_with_fused_groupnorm_input_vs_oracle(h, c, pitch):
     """csd_fir_norm_resample_nhwc_*: FIR(SiLU(GroupNorm(x))) with the normalisation applied to the TMA-staged tile -
