@@ -955,8 +955,60 @@ conv_halo_tp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       float2* tab = reinterpret_cast<float2*>(__cvta_shared_to_generic(coef_addr));
       uint32_t sa = 0, a_par = 0;
       int tab_b = -1;
+      // The tiles of a CTA are gridDim.x apart - more than the tiles of one image - so EVERY tile starts with a new
+      // image's (scale, shift) table, and these warps sit within a few hundred cycles per tile of the kernel's critical
+      // path (an experiment that added two dependent phases to the table build, +0.34 us per tile, slowed the whole PC
+      // step by exactly that: profiles/inline_groupnorm_experiment_r2.txt). The table's global loads (an L2 round trip:
+      // every image is new to this SM) are therefore issued one tile AHEAD, into registers, and only written to shared
+      // memory at the tile boundary. Up to kPre table slots per thread; wider tables keep the load-at-the-boundary path.
+      constexpr int kPre = 2;
+      int tab_total = 0;
+      for (int s = 0; s < p.nseg; ++s) tab_total += p.seg_chunks[s] * CH;
+      const bool prefetch = tab_total <= kPre * kPTransformThreads && !(p.debug_nodata & 64);
+      const float2* psrc[kPre];
+      int pcnt[kPre];
+      float ppre[kPre];
+      float2 nv[kPre];
+#pragma unroll
+      for (int q = 0; q < kPre; ++q) {
+        psrc[q] = nullptr;
+        pcnt[q] = 0;
+        ppre[q] = 1.0f;
+        nv[q] = make_float2(0.f, 0.f);
+        const int idx = tt + q * kPTransformThreads;
+        int base = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int nch = p.seg_chunks[s] * CH;
+          if (idx >= base && idx < base + nch) {
+            const int i = idx - base;
+            if (p.seg_norm[s] != nullptr && i < p.seg_ccnt[s]) {
+              psrc[q] = reinterpret_cast<const float2*>(p.seg_norm[s]) + i;
+              pcnt[q] = p.seg_ccnt[s];
+            }
+            ppre[q] = (p.seg_silu[s] && !kTf32) ? 0.5f : 1.0f;
+          }
+          base += nch;
+        }
+      }
+      auto fetch = [&](int b_img) {
+#pragma unroll
+        for (int q = 0; q < kPre; ++q)
+          nv[q] = psrc[q] != nullptr ? __ldg(psrc[q] + (long long)b_img * pcnt[q]) : make_float2(0.f, 0.f);
+      };
+      if (prefetch && (int)blockIdx.x < num_tiles) fetch(decode_tile(p, blockIdx.x).b);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
+        if (tc.b != tab_b && prefetch) {
+          asm volatile("bar.sync 2, 256;" ::: "memory");     // nobody still reads the previous image's table
+#pragma unroll
+          for (int q = 0; q < kPre; ++q) {
+            const int idx = tt + q * kPTransformThreads;
+            if (idx < tab_total) tab[idx] = make_float2(nv[q].x * ppre[q], nv[q].y * ppre[q]);
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          tab_b = tc.b;
+        }
+        if (prefetch && tile + (int)gridDim.x < num_tiles) fetch(decode_tile(p, tile + gridDim.x).b);
         if (tc.b != tab_b) {             // (scale, shift) of this image's channels, all segments back to back
           asm volatile("bar.sync 2, 256;" ::: "memory");
           int base = 0;
