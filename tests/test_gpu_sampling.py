@@ -90,6 +90,38 @@ def test_pc_conditional_fused_vs_oracle_injected_noise():
     assert torch.equal(got2, got)
 
 
+def test_time_embedding_reuse_inside_a_pc_step_is_bitwise_neutral(monkeypatch):
+    """Both network evaluations of a PC step see the same vec_t (sampling/conditional.py:196-226), so the fused loop runs
+    the time-embedding MLP and the Dense_0 projections once per step (FusedPCSampler._net). Same injected noise, reuse on
+    vs off: the samples must agree bit for bit, and the step with reuse must launch exactly two kernels fewer."""
+    from conditional_score_diffusion_b200 import _lib
+    from conditional_score_diffusion_b200.sampling import fused
+    sampling, sde_lib, _ = _pkg()
+    f, m = _model("paired")
+    p = golden()["pc_conditional"]
+    steps = 4
+    shape = tuple(p["y"].shape)
+    tape = NoiseTape(shape, steps, True, 25)
+    x0 = torch.randn(*shape, generator=torch.Generator().manual_seed(26)) * p["sigma_max_x"]
+    sde = {"x": sde_lib.cVESDE(p["sigma_min_x"], p["sigma_max_x"], p["N"]),
+           "y": sde_lib.VESDE(p["sigma_min_y"], p["sigma_max_y"], p["N"])}
+    outs, launches = [], []
+    for reuse in (True, False):
+        monkeypatch.setattr(fused, "REUSE_TEMB", reuse)
+        fs = fused.FusedPCSampler(m, sde, shape, "reverse_diffusion", "langevin", p["snr"], steps, 1, False, True, True,
+                                  p["eps"], conditional=True)
+        out, _ = fs.sample(y=p["y"].cuda(), x_init=x0, noise_source=tape.named)
+        outs.append(out.clone())
+        fs.plan.use_graph = False                      # count the launches of one step issued launch by launch
+        n0 = _lib.lib().csd_launch_count()
+        fs.draw_noise = False
+        fs._step()
+        torch.cuda.synchronize()
+        launches.append(_lib.lib().csd_launch_count() - n0)
+    assert torch.equal(outs[0], outs[1])
+    assert launches[1] - launches[0] == 2, launches
+
+
 def test_pc_unconditional_fused_vs_oracle_injected_noise():
     sampling, sde_lib, _ = _pkg()
     f, m = _model("cifar")
