@@ -604,7 +604,11 @@ def run_b200(args):
     fs.draw_noise = True
     fs.x.copy_(torch.randn(*shape, device=dev) * cfg.model.sigma_max_x)
     fs.step_idx.zero_()
-    fs._step()                      # eager step: counts this library's launches per PC step
+    # one step issued launch by launch (the form the step graph is captured from: the second network evaluation reuses
+    # the first one's time embedding) counts this library's launches per PC step
+    own_graph, fs.plan.use_graph = fs.plan.use_graph, False
+    fs._step()
+    fs.plan.use_graph = own_graph
     launches_per_step = _lib.lib().csd_launch_count() - launches0
     graph = fs._graph(draw_noise=True)
     fs.x.copy_(torch.randn(*shape, device=dev) * cfg.model.sigma_max_x)
