@@ -15,8 +15,12 @@ of the full trajectory (default K = 200; --steps 1000 times a complete PC-1000 t
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-Prints ONE JSON line (see the keys in main()). `--impl reference` times the CPU oracle port of the
-reference path (oracle/, PyTorch fp32 on all host cores) on a bounded sample of the same workload.
+Prints ONE JSON line (see the keys in main()). `--impl reference` times the UNMODIFIED reference
+(baseline/_ref, installed by baseline/install_ref.py: sampling/conditional.py driving models/ncsnpp.py,
+PyTorch fp32 on all host cores) on a bounded sample of the same workload - batch 2, a few PC steps,
+extrapolated to PC-1000; it falls back to the oracle port (oracle/, `kind: "port"`) only where
+baseline/_ref did not travel. The default line also carries the same reference on the GPU (`stock_gpu`:
+eager PyTorch, cuDNN TF32, its own upfirdn2d CUDA op, B = 64) and `vs_stock_gpu`.
 """
 import argparse
 import json
